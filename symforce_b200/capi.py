@@ -1,0 +1,93 @@
+"""
+ctypes binding of symforce_b200/lib/libsfx.so -- the product: CUDA (sm_100a) sparse LM behind the
+C ABI of include/sfx.h.  There is NO CPU fallback: if the library is missing this module raises,
+and without a CUDA device sfx_problem_create fails with SFX_ERR_CUDA.
+"""
+import ctypes as C
+import json
+import os
+
+import numpy as np
+
+from . import desc as D
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libsfx.so")
+
+EXPORTS = [
+    "sfx_default_params", "sfx_problem_create", "sfx_problem_destroy", "sfx_last_error", "sfx_update_params",
+    "sfx_set_values", "sfx_optimize", "sfx_get_best_values", "sfx_get_iterations", "sfx_get_dims",
+    "sfx_get_hessian_pattern", "sfx_linearize", "sfx_get_best_linearization", "sfx_solve_step",
+    "sfx_get_ordering", "sfx_get_timings", "sfx_get_info", "sfx_comm_unique_id", "sfx_comm_create",
+    "sfx_comm_destroy",
+]
+
+INFO_NAMES = ["N", "M", "nnz_H", "num_nodes", "reduced_dim", "nnz_L", "num_supernodes", "num_levels",
+              "factor_flops", "s_blocks", "schur_pairs", "max_front", "device_bytes"]
+
+_lib = None
+
+
+def load():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(symforce_b200 has no CPU fallback)")
+        _lib = C.CDLL(LIB_PATH)
+        _lib.sfx_last_error.restype = C.c_char_p
+        _lib.sfx_last_error.argtypes = [C.c_void_p]
+    return _lib
+
+
+def analysis_json(problem: D.Problem):
+    """Host-only structural analysis (no CUDA), for the CPU test-suite."""
+    lib = load()
+    d, keep = problem.desc()
+    out = C.c_char_p()
+    rc = lib.sfx_debug_analysis_json(C.byref(d), C.byref(out))
+    if rc != 0:
+        raise RuntimeError("analysis failed: " + out.value.decode())
+    return json.loads(out.value.decode())
+
+
+class SfxProblem(D._LibProblem):
+    prefix = "sfx_"
+
+    def __init__(self, problem: D.Problem, device=0, rank=0, world=1, comm=None):
+        self.lib = load()
+        self.problem = problem
+        self.n_values = problem.values.shape[0]
+        d, keep = problem.desc(device=device, rank=rank, world=world, comm=comm)
+        self._keep = keep
+        h = C.c_void_p()
+        rc = self.lib.sfx_problem_create(C.byref(d), C.byref(h))
+        if rc != 0:
+            raise RuntimeError(f"sfx_problem_create failed (rc={rc}): " + self.lib.sfx_last_error(None).decode())
+        self.h = h
+        self.set_values(problem.values)
+
+    def _last_error(self):
+        return self.lib.sfx_last_error(self.h).decode()
+
+    def timings(self):
+        t = D.Timings()
+        self._check(self.lib.sfx_get_timings(self.h, C.byref(t)), "get_timings")
+        return {f[0]: getattr(t, f[0]) for f in D.Timings._fields_}
+
+    def info(self):
+        out = (C.c_int64 * len(INFO_NAMES))()
+        self._check(self.lib.sfx_get_info(self.h, out, C.c_int32(len(INFO_NAMES))), "get_info")
+        return dict(zip(INFO_NAMES, list(out)))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.sfx_problem_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,601 @@
+// Host-side structural analysis, done ONCE per problem (replaces the index building of
+// sym::Linearizer::BuildInitialLinearization, symforce/opt/linearizer.cc:149-356, and of
+// SparseSchurSolver::ComputeSymbolicSparsity, symforce/opt/sparse_schur_solver.tcc:16-97):
+//   keys -> nodes, block-sparse Hessian layout in HBM, per-factor scatter indices,
+//   Schur match lists, CSC export map (reference layout of Linearization::hessian_lower).
+#include <algorithm>
+#include <cstring>
+#include <map>
+#include <numeric>
+#include <unordered_map>
+
+#include "sfx_internal.h"
+
+namespace sfx {
+
+int BlockMatrix::find(int row, int col) const {
+  const int* b = row_idx.data() + col_ptr[col];
+  const int* e = row_idx.data() + col_ptr[col + 1];
+  const int* it = std::lower_bound(b, e, row);
+  if (it == e || *it != row) return -1;
+  return (int)(it - row_idx.data());
+}
+
+static inline uint64_t mix64(uint64_t x) {
+  x += 0x9e3779b97f4a7c15ull;
+  x = (x ^ (x >> 30)) * 0xbf58476d1ce4e5b9ull;
+  x = (x ^ (x >> 27)) * 0x94d049bb133111ebull;
+  return x ^ (x >> 31);
+}
+
+struct FactorRef {
+  int batch, idx;  // input batch / position
+};
+
+void analyze_problem(const sfx_problem_desc& d, Analysis& a) {
+  SFX_CHECK(d.abi_version == SFX_ABI_VERSION, SFX_ERR_INVALID_ARG, "ABI version mismatch");
+  SFX_CHECK(d.n_keys > 0 && d.keys, SFX_ERR_INVALID_ARG, "no optimized keys");
+  SFX_CHECK(d.n_batches > 0 && d.batches, SFX_ERR_INVALID_ARG, "no factors");
+  a.n_keys = d.n_keys;
+  a.n_values = d.n_values;
+  a.n_factors = d.n_factors;
+  a.schur = d.solver == SFX_SOLVER_SCHUR;
+  const int nk = d.n_keys;
+  const int n_lm_keys = a.schur ? d.schur_num_keys : 0;
+  SFX_CHECK(!a.schur || (n_lm_keys > 0 && n_lm_keys < nk), SFX_ERR_INVALID_ARG,
+            "schur_num_keys must be in (0, n_keys)");
+  const int first_lm_key = nk - n_lm_keys;
+
+  a.keys.resize(nk);
+  int toff = 0;
+  for (int k = 0; k < nk; ++k) {
+    const sfx_key_entry& e = d.keys[k];
+    SFX_CHECK(e.type == SFX_TYPE_VECTOR || e.type == SFX_TYPE_ROT3 || e.type == SFX_TYPE_POSE3, SFX_ERR_UNSUPPORTED,
+              "key type has no device retract");
+    SFX_CHECK(e.tangent_dim > 0 && e.tangent_dim <= kMaxNodeDim, SFX_ERR_UNSUPPORTED, "tangent dim out of range");
+    SFX_CHECK(e.offset >= 0 && (int64_t)e.offset + e.storage_dim <= d.n_values, SFX_ERR_INVALID_ARG,
+              "key storage outside the values buffer");
+    if (e.type == SFX_TYPE_ROT3) SFX_CHECK(e.storage_dim == 4 && e.tangent_dim == 3, SFX_ERR_INVALID_ARG, "Rot3 dims");
+    if (e.type == SFX_TYPE_POSE3) SFX_CHECK(e.storage_dim == 7 && e.tangent_dim == 6, SFX_ERR_INVALID_ARG, "Pose3 dims");
+    if (e.type == SFX_TYPE_VECTOR) SFX_CHECK(e.storage_dim == e.tangent_dim, SFX_ERR_INVALID_ARG, "vector dims");
+    a.keys[k] = KeyInfo{e.type, e.offset, e.storage_dim, e.tangent_dim, toff, -1, 0};
+    toff += e.tangent_dim;
+  }
+  a.N = toff;
+
+  // ---- factor list in caller order; validate; key signatures ------------------------------------
+  std::vector<FactorRef> fref(d.n_factors, FactorRef{-1, -1});
+  int64_t total = 0;
+  for (int b = 0; b < d.n_batches; ++b) {
+    const sfx_factor_batch& fb = d.batches[b];
+    SFX_CHECK(fb.kind >= 0 && fb.kind < SFX_NUM_KINDS, SFX_ERR_UNSUPPORTED, "factor kind has no device implementation");
+    total += fb.n;
+    for (int f = 0; f < fb.n; ++f) {
+      int fi = fb.factor_index[f];
+      SFX_CHECK(fi >= 0 && fi < d.n_factors && fref[fi].batch < 0, SFX_ERR_INVALID_ARG,
+                "factor_index must be a permutation of [0, n_factors)");
+      fref[fi] = FactorRef{b, f};
+    }
+  }
+  SFX_CHECK(total == d.n_factors, SFX_ERR_INVALID_ARG, "n_factors != sum of batch sizes");
+
+  std::vector<uint64_t> h1(nk, 0), h2(nk, 0);
+  std::vector<int> cnt(nk, 0);
+  for (int b = 0; b < d.n_batches; ++b) {
+    const sfx_factor_batch& fb = d.batches[b];
+    const sfx_kind_meta& km = SFX_KIND_META[fb.kind];
+    for (int o = 0; o < km.n_opt; ++o)
+      for (int f = 0; f < fb.n; ++f) {
+        int key = fb.opt_keys[(int64_t)o * fb.n + f];
+        if (key < 0) continue;
+        SFX_CHECK(key < nk, SFX_ERR_INVALID_ARG, "opt key index out of range");
+        SFX_CHECK(a.keys[key].tdim == km.opt_dims[o], SFX_ERR_INVALID_ARG, "tangent dim of key does not match factor");
+        uint64_t fi = (uint64_t)fb.factor_index[f];
+        h1[key] += mix64(fi);
+        h2[key] += mix64(fi ^ 0x5bd1e995deadbeefull);
+        cnt[key]++;
+      }
+    for (int ar = 0; ar < km.n_args; ++ar)
+      if (km.arg_used[ar])
+        for (int f = 0; f < fb.n; ++f) {
+          int off = fb.arg_offsets[(int64_t)ar * fb.n + f];
+          SFX_CHECK(off >= 0 && (int64_t)off + km.arg_dims[ar] <= d.n_values, SFX_ERR_INVALID_ARG,
+                    "factor argument outside the values buffer");
+        }
+  }
+  for (int k = 0; k < nk; ++k)
+    if (cnt[k] == 0)
+      throw Error(SFX_ERR_STRUCTURE,
+                  "Key #" + std::to_string(k) + " is in the state vector but is not optimized by any factor.");
+
+  // ---- nodes: merge non-landmark keys with identical factor sets ---------------------------------
+  {
+    struct Sig {
+      uint64_t a, b;
+      int c;
+      bool operator<(const Sig& o) const { return std::tie(a, b, c) < std::tie(o.a, o.b, o.c); }
+    };
+    std::map<Sig, int> sig2node;
+    a.nodes.clear();
+    for (int k = 0; k < nk; ++k) {
+      int node = -1;
+      if (k < first_lm_key) {
+        Sig s{h1[k], h2[k], cnt[k]};
+        auto it = sig2node.find(s);
+        if (it != sig2node.end() && a.nodes[it->second].dim + a.keys[k].tdim <= kMaxNodeDim) {
+          node = it->second;
+        } else {
+          node = (int)a.nodes.size();
+          a.nodes.push_back(NodeInfo{0, 0, k, 0});
+          sig2node[s] = node;
+        }
+      } else {
+        SFX_CHECK(a.keys[k].tdim <= kMaxLandmarkDim, SFX_ERR_UNSUPPORTED, "Schur landmark dim > 3");
+        node = (int)a.nodes.size();
+        a.nodes.push_back(NodeInfo{0, 0, k, 0});
+      }
+      a.keys[k].node = node;
+      a.keys[k].sub = a.nodes[node].dim;
+      a.nodes[node].dim += a.keys[k].tdim;
+      a.nodes[node].n_keys++;
+    }
+    int off = 0;
+    for (auto& n : a.nodes) {
+      n.toff = off;
+      off += n.dim;
+    }
+    a.ref2int.resize(a.N);
+    for (int k = 0; k < nk; ++k)
+      for (int i = 0; i < a.keys[k].tdim; ++i)
+        a.ref2int[a.keys[k].ref_toff + i] = a.nodes[a.keys[k].node].toff + a.keys[k].sub + i;
+  }
+  const int nn = (int)a.nodes.size();
+  int first_lm_node = nn;
+  if (a.schur) first_lm_node = a.keys[first_lm_key].node;
+
+  // ---- batch plans: split by (kind, grouping pattern) -------------------------------------------
+  struct PatternKey {
+    int kind;
+    int grp[SFX_MAX_OPT], sub[SFX_MAX_OPT];
+    bool operator<(const PatternKey& o) const {
+      return std::tie(kind, grp[0], grp[1], grp[2], sub[0], sub[1], sub[2]) <
+             std::tie(o.kind, o.grp[0], o.grp[1], o.grp[2], o.sub[0], o.sub[1], o.sub[2]);
+    }
+  };
+  std::map<PatternKey, int> pat2plan;
+  std::vector<std::vector<FactorRef>> plan_factors;
+  std::vector<PatternKey> plan_pat;
+  // residual offsets in caller order
+  std::vector<int32_t> res_off_of_factor(d.n_factors);
+  {
+    int r = 0;
+    for (int fi = 0; fi < d.n_factors; ++fi) {
+      res_off_of_factor[fi] = r;
+      r += SFX_KIND_META[d.batches[fref[fi].batch].kind].res_dim;
+    }
+    a.M = r;
+  }
+  for (int fi = 0; fi < d.n_factors; ++fi) {
+    const sfx_factor_batch& fb = d.batches[fref[fi].batch];
+    const sfx_kind_meta& km = SFX_KIND_META[fb.kind];
+    const int f = fref[fi].idx;
+    PatternKey pk;
+    pk.kind = fb.kind;
+    int nodes_seen[SFX_MAX_OPT];
+    int ng = 0;
+    for (int o = 0; o < SFX_MAX_OPT; ++o) {
+      pk.grp[o] = -2;
+      pk.sub[o] = 0;
+    }
+    for (int o = 0; o < km.n_opt; ++o) {
+      int key = fb.opt_keys[(int64_t)o * fb.n + f];
+      if (key < 0) {
+        pk.grp[o] = -1;
+        continue;
+      }
+      int node = a.keys[key].node;
+      int g = -1;
+      for (int q = 0; q < ng; ++q)
+        if (nodes_seen[q] == node) g = q;
+      if (g < 0) {
+        g = ng;
+        nodes_seen[ng++] = node;
+      } else {
+        // the same key twice in one factor is not representable
+        for (int o2 = 0; o2 < o; ++o2)
+          SFX_CHECK(fb.opt_keys[(int64_t)o2 * fb.n + f] != key, SFX_ERR_UNSUPPORTED,
+                    "factor references the same optimized key twice");
+      }
+      pk.grp[o] = g;
+      pk.sub[o] = a.keys[key].sub;
+    }
+    auto it = pat2plan.find(pk);
+    int plan;
+    if (it == pat2plan.end()) {
+      plan = (int)plan_factors.size();
+      pat2plan[pk] = plan;
+      plan_factors.emplace_back();
+      plan_pat.push_back(pk);
+    } else {
+      plan = it->second;
+    }
+    plan_factors[plan].push_back(fref[fi]);
+  }
+
+  // ---- Hessian blocks ---------------------------------------------------------------------------
+  // contributions to off-diagonal blocks: (col node, row node) keyed, with (plan, slot, pair)
+  struct Contrib {
+    uint64_t key;
+    int plan, slot, pair;
+    uint32_t transposed;
+  };
+  std::vector<Contrib> contribs;
+  a.batches.assign(plan_factors.size(), BatchPlan{});
+  for (size_t pl = 0; pl < plan_factors.size(); ++pl) {
+    BatchPlan& bp = a.batches[pl];
+    const PatternKey& pk = plan_pat[pl];
+    const sfx_kind_meta& km = SFX_KIND_META[pk.kind];
+    bp.kind = pk.kind;
+    bp.n = (int)plan_factors[pl].size();
+    bp.n_opt = km.n_opt;
+    bp.n_used_args = 0;
+    for (int ar = 0; ar < km.n_args; ++ar)
+      if (km.arg_used[ar]) bp.used_args[bp.n_used_args++] = ar;
+    bp.n_groups = 0;
+    for (int o = 0; o < km.n_opt; ++o) {
+      bp.key_group[o] = pk.grp[o];
+      bp.key_sub[o] = pk.sub[o];
+      if (pk.grp[o] >= 0) bp.n_groups = std::max(bp.n_groups, pk.grp[o] + 1);
+    }
+    const int n = bp.n, ng = bp.n_groups;
+    const int npairs = ng * (ng - 1) / 2;
+    bp.arg_off.resize((size_t)bp.n_used_args * n);
+    bp.res_off.resize(n);
+    bp.rhs_off.resize((size_t)ng * n);
+    bp.diag_off.resize((size_t)ng * n);
+    bp.off_off.resize((size_t)npairs * n);
+    bp.factor_index.resize(n);
+    for (int s = 0; s < n; ++s) {
+      const FactorRef& fr = plan_factors[pl][s];
+      const sfx_factor_batch& fb = d.batches[fr.batch];
+      const int f = fr.idx;
+      const int fi = fb.factor_index[f];
+      bp.factor_index[s] = fi;
+      bp.res_off[s] = res_off_of_factor[fi];
+      for (int u = 0; u < bp.n_used_args; ++u)
+        bp.arg_off[(size_t)u * n + s] = fb.arg_offsets[(int64_t)bp.used_args[u] * fb.n + f];
+      int gnode[kMaxGroups];
+      for (int o = 0; o < km.n_opt; ++o)
+        if (pk.grp[o] >= 0) gnode[pk.grp[o]] = a.keys[fb.opt_keys[(int64_t)o * fb.n + f]].node;
+      for (int g = 0; g < ng; ++g) {
+        if (s == 0) bp.group_dim[g] = a.nodes[gnode[g]].dim;
+        SFX_CHECK(bp.group_dim[g] == a.nodes[gnode[g]].dim, SFX_ERR_STRUCTURE, "non-uniform node dims inside a batch");
+        bp.rhs_off[(size_t)g * n + s] = a.nodes[gnode[g]].toff;
+      }
+      int pair = 0;
+      for (int g = 1; g < ng; ++g)
+        for (int h = 0; h < g; ++h, ++pair) {
+          int I = gnode[g], J = gnode[h];
+          uint32_t tr = 0;
+          if (I < J) {
+            std::swap(I, J);
+            tr = 1;
+          }
+          contribs.push_back(Contrib{((uint64_t)J << 32) | (uint32_t)I, (int)pl, s, pair, tr});
+        }
+    }
+  }
+  // sort contributions by block; stable so that slot order is kept inside a block
+  std::vector<uint32_t> order(contribs.size());
+  std::iota(order.begin(), order.end(), 0u);
+  std::stable_sort(order.begin(), order.end(),
+                   [&](uint32_t x, uint32_t y) { return contribs[x].key < contribs[y].key; });
+  // unique blocks with contributor counts
+  std::vector<uint64_t> blk_key;
+  std::vector<int> blk_cnt;
+  std::vector<int> contrib_blk(contribs.size());
+  for (size_t i = 0; i < order.size(); ++i) {
+    const Contrib& c = contribs[order[i]];
+    if (blk_key.empty() || blk_key.back() != c.key) {
+      blk_key.push_back(c.key);
+      blk_cnt.push_back(0);
+    }
+    blk_cnt.back()++;
+    contrib_blk[order[i]] = (int)blk_key.size() - 1;
+  }
+  // Block matrix structure: per column, diagonal first then sorted off-diagonal rows
+  BlockMatrix& H = a.H;
+  H.n_nodes = nn;
+  H.node_dim.resize(nn);
+  H.node_off.resize(nn + 1);
+  for (int i = 0; i < nn; ++i) {
+    H.node_dim[i] = a.nodes[i].dim;
+    H.node_off[i] = a.nodes[i].toff;
+  }
+  H.node_off[nn] = a.N;
+  H.col_ptr.assign(nn + 1, 0);
+  for (uint64_t k : blk_key) H.col_ptr[(k >> 32) + 1]++;
+  for (int j = 0; j < nn; ++j) H.col_ptr[j + 1] += H.col_ptr[j] + 1;  // +1: diagonal block
+  const int nblk = H.col_ptr[nn];
+  H.row_idx.resize(nblk);
+  H.blk_off.assign(nblk, -1);
+  std::vector<int> offdiag_id(blk_key.size());
+  {
+    std::vector<int> fill(nn);
+    for (int j = 0; j < nn; ++j) {
+      H.row_idx[H.col_ptr[j]] = j;
+      fill[j] = H.col_ptr[j] + 1;
+    }
+    for (size_t b = 0; b < blk_key.size(); ++b) {  // blk_key is sorted by (col,row)
+      int col = (int)(blk_key[b] >> 32), row = (int)(blk_key[b] & 0xffffffffu);
+      offdiag_id[b] = fill[col];
+      H.row_idx[fill[col]++] = row;
+    }
+  }
+  if (a.schur) {
+    // C must be block diagonal: no block between two landmark nodes
+    for (size_t b = 0; b < blk_key.size(); ++b) {
+      int col = (int)(blk_key[b] >> 32);
+      SFX_CHECK(col < first_lm_node, SFX_ERR_STRUCTURE,
+                "Submatrix C of A is not block diagonal, cannot use a Schur complement solver");
+    }
+  }
+  // value offsets: [diag blocks | shared off-diag blocks] accumulated, then exclusive blocks in
+  // (plan, slot, pair) order so that a thread's stores are contiguous
+  int64_t off = 0;
+  for (int j = 0; j < nn; ++j) {
+    H.blk_off[H.col_ptr[j]] = off;
+    off += (int64_t)a.nodes[j].dim * a.nodes[j].dim;
+  }
+  for (size_t b = 0; b < blk_key.size(); ++b)
+    if (blk_cnt[b] > 1) {
+      int col = (int)(blk_key[b] >> 32), row = (int)(blk_key[b] & 0xffffffffu);
+      H.blk_off[offdiag_id[b]] = off;
+      off += (int64_t)a.nodes[row].dim * a.nodes[col].dim;
+    }
+  a.h_accum_values = off;
+  for (size_t c = 0; c < contribs.size(); ++c) {  // contribs are in (plan, slot, pair) order
+    int b = contrib_blk[c];
+    if (blk_cnt[b] == 1) {
+      int col = (int)(blk_key[b] >> 32), row = (int)(blk_key[b] & 0xffffffffu);
+      H.blk_off[offdiag_id[b]] = off;
+      off += (int64_t)a.nodes[row].dim * a.nodes[col].dim;
+    }
+  }
+  H.n_values = off;
+  SFX_CHECK(off < (int64_t)kOffMask, SFX_ERR_UNSUPPORTED, "Hessian has more than 2^30 block values");
+  // fill per-factor scatter indices
+  for (size_t c = 0; c < contribs.size(); ++c) {
+    const Contrib& ct = contribs[c];
+    BatchPlan& bp = a.batches[ct.plan];
+    int b = contrib_blk[c];
+    uint32_t v = (uint32_t)H.blk_off[offdiag_id[b]];
+    if (blk_cnt[b] == 1) v |= kOffExclusive;
+    if (ct.transposed) v |= kOffTransposed;
+    bp.off_off[(size_t)ct.pair * bp.n + ct.slot] = v;
+  }
+  for (auto& bp : a.batches) {
+    for (int g = 0; g < bp.n_groups; ++g)
+      for (int s = 0; s < bp.n; ++s) {
+        // node of this group: recover from rhs_off (toff) -> search; cheaper: use diag offsets by node
+        // (filled below through a toff->node map)
+      }
+  }
+  {
+    std::unordered_map<int, int> toff2node;
+    toff2node.reserve(nn * 2);
+    for (int i = 0; i < nn; ++i) toff2node[a.nodes[i].toff] = i;
+    for (auto& bp : a.batches)
+      for (size_t i = 0; i < bp.rhs_off.size(); ++i)
+        bp.diag_off[i] = (int32_t)H.blk_off[H.col_ptr[toff2node[bp.rhs_off[i]]]];
+  }
+  a.diag_pos.resize(a.N);
+  for (int i = 0; i < nn; ++i) {
+    const int dmn = a.nodes[i].dim;
+    for (int r = 0; r < dmn; ++r) a.diag_pos[a.nodes[i].toff + r] = (int32_t)(H.blk_off[H.col_ptr[i]] + r + (int64_t)r * dmn);
+  }
+
+  // ---- Schur plan -------------------------------------------------------------------------------
+  if (a.schur) {
+    SchurPlan& sp = a.sp;
+    sp.first_lm_node = first_lm_node;
+    sp.n_landmarks = nn - first_lm_node;
+    sp.reduced_dim = a.nodes[first_lm_node].toff;
+    const int nl = sp.n_landmarks, nr = first_lm_node;
+    sp.lm_dim.resize(nl);
+    sp.lm_cdiag_off.resize(nl);
+    sp.lm_toff.resize(nl);
+    sp.lm_e_ptr.assign(nl + 1, 0);
+    for (int l = 0; l < nl; ++l) {
+      int node = first_lm_node + l;
+      sp.lm_dim[l] = a.nodes[node].dim;
+      sp.lm_cdiag_off[l] = (int32_t)H.blk_off[H.col_ptr[node]];
+      sp.lm_toff[l] = a.nodes[node].toff;
+    }
+    // E blocks: blocks (row = landmark node, col = reduced node)
+    for (int j = 0; j < nr; ++j)
+      for (int p = H.col_ptr[j] + 1; p < H.col_ptr[j + 1]; ++p)
+        if (H.row_idx[p] >= first_lm_node) sp.lm_e_ptr[H.row_idx[p] - first_lm_node + 1]++;
+    for (int l = 0; l < nl; ++l) sp.lm_e_ptr[l + 1] += sp.lm_e_ptr[l];
+    sp.lm_e_off.resize(sp.lm_e_ptr[nl]);
+    sp.lm_e_node.resize(sp.lm_e_ptr[nl]);
+    {
+      std::vector<int> fill(sp.lm_e_ptr.begin(), sp.lm_e_ptr.end() - 1);
+      for (int j = 0; j < nr; ++j)  // increasing j -> each landmark's list sorted by node
+        for (int p = H.col_ptr[j] + 1; p < H.col_ptr[j + 1]; ++p)
+          if (H.row_idx[p] >= first_lm_node) {
+            int l = H.row_idx[p] - first_lm_node;
+            sp.lm_e_off[fill[l]] = (int32_t)H.blk_off[p];
+            sp.lm_e_node[fill[l]] = j;
+            fill[l]++;
+          }
+    }
+    // reduced rhs lists (per reduced node: E blocks of its column)
+    sp.r_ptr.assign(nr + 1, 0);
+    for (int j = 0; j < nr; ++j) {
+      int c = 0;
+      for (int p = H.col_ptr[j] + 1; p < H.col_ptr[j + 1]; ++p)
+        if (H.row_idx[p] >= first_lm_node) c++;
+      sp.r_ptr[j + 1] = sp.r_ptr[j] + c;
+    }
+    sp.r_eoff.resize(sp.r_ptr[nr]);
+    sp.r_lm.resize(sp.r_ptr[nr]);
+    for (int j = 0; j < nr; ++j) {
+      int q = sp.r_ptr[j];
+      for (int p = H.col_ptr[j] + 1; p < H.col_ptr[j + 1]; ++p)
+        if (H.row_idx[p] >= first_lm_node) {
+          sp.r_eoff[q] = (int32_t)H.blk_off[p];
+          sp.r_lm[q] = H.row_idx[p] - first_lm_node;
+          q++;
+        }
+    }
+    // S pattern: B blocks + all pairs (I >= J) of reduced nodes adjacent to a common landmark
+    struct Match {
+      uint64_t key;  // (col J << 32) | row I
+      int32_t ei, ej, lm;
+    };
+    std::vector<Match> matches;
+    {
+      int64_t cnt_m = 0;
+      for (int l = 0; l < nl; ++l) {
+        int64_t k = sp.lm_e_ptr[l + 1] - sp.lm_e_ptr[l];
+        cnt_m += k * (k + 1) / 2;
+      }
+      matches.reserve(cnt_m);
+    }
+    for (int l = 0; l < nl; ++l)
+      for (int q = sp.lm_e_ptr[l]; q < sp.lm_e_ptr[l + 1]; ++q)
+        for (int p = q; p < sp.lm_e_ptr[l + 1]; ++p)  // node[p] >= node[q]
+          matches.push_back(Match{((uint64_t)sp.lm_e_node[q] << 32) | (uint32_t)sp.lm_e_node[p], sp.lm_e_off[p],
+                                  sp.lm_e_off[q], l});
+    std::stable_sort(matches.begin(), matches.end(), [](const Match& x, const Match& y) { return x.key < y.key; });
+    // merged column structure
+    std::vector<uint64_t> skeys;
+    skeys.reserve(matches.size() / 4 + nr);
+    for (int j = 0; j < nr; ++j)
+      for (int p = H.col_ptr[j]; p < H.col_ptr[j + 1]; ++p)
+        if (H.row_idx[p] < first_lm_node) skeys.push_back(((uint64_t)j << 32) | (uint32_t)H.row_idx[p]);
+    {
+      uint64_t last = ~0ull;
+      for (const Match& m : matches)
+        if (m.key != last) {
+          skeys.push_back(m.key);
+          last = m.key;
+        }
+    }
+    std::sort(skeys.begin(), skeys.end());
+    skeys.erase(std::unique(skeys.begin(), skeys.end()), skeys.end());
+    BlockMatrix& S = sp.S;
+    S.n_nodes = nr;
+    S.node_dim.assign(H.node_dim.begin(), H.node_dim.begin() + nr);
+    S.node_off.assign(H.node_off.begin(), H.node_off.begin() + nr + 1);
+    S.col_ptr.assign(nr + 1, 0);
+    for (uint64_t k : skeys) S.col_ptr[(k >> 32) + 1]++;
+    for (int j = 0; j < nr; ++j) S.col_ptr[j + 1] += S.col_ptr[j];
+    S.row_idx.resize(skeys.size());
+    S.blk_off.resize(skeys.size());
+    int64_t soff = 0;
+    for (size_t b = 0; b < skeys.size(); ++b) {
+      int col = (int)(skeys[b] >> 32), row = (int)(skeys[b] & 0xffffffffu);
+      S.row_idx[b] = row;
+      S.blk_off[b] = soff;
+      soff += (int64_t)S.node_dim[row] * S.node_dim[col];
+    }
+    S.n_values = soff;
+    sp.s_b_src.assign(skeys.size(), -1);
+    for (int j = 0; j < nr; ++j)
+      for (int p = H.col_ptr[j]; p < H.col_ptr[j + 1]; ++p)
+        if (H.row_idx[p] < first_lm_node) sp.s_b_src[S.find(H.row_idx[p], j)] = (int32_t)H.blk_off[p];
+    sp.s_m_ptr.assign(skeys.size() + 1, 0);
+    sp.m_eoff_i.resize(matches.size());
+    sp.m_eoff_j.resize(matches.size());
+    sp.m_lm.resize(matches.size());
+    {
+      size_t b = 0;
+      for (size_t i = 0; i < matches.size(); ++i) {
+        while (skeys[b] != matches[i].key) ++b;
+        sp.s_m_ptr[b + 1]++;
+        sp.m_eoff_i[i] = matches[i].ei;
+        sp.m_eoff_j[i] = matches[i].ej;
+        sp.m_lm[i] = matches[i].lm;
+      }
+      for (size_t q = 0; q < skeys.size(); ++q) sp.s_m_ptr[q + 1] += sp.s_m_ptr[q];
+    }
+  }
+}
+
+// Reference CSC layout of Linearization::hessian_lower (key order, lower incl. explicit diagonal)
+// and, per entry, where it lives in the block storage.
+void build_csc(Analysis& a) {
+  if (a.csc_built) return;
+  const int nk = a.n_keys;
+  const BlockMatrix& H = a.H;
+  // key-level off-diagonal adjacency: keys ki > kj whose nodes share a block (or the same node)
+  // Per node column J: row nodes I (incl. J).  Keys of node: contiguous? not necessarily in key
+  // order, so go through a per-key list.
+  std::vector<std::vector<int>> node_keys(a.nodes.size());
+  for (int k = 0; k < nk; ++k) node_keys[a.keys[k].node].push_back(k);
+  a.csc_outer.assign(a.N + 1, 0);
+  // count per reference column
+  std::vector<std::vector<int>> rows_of_key(nk);  // off-diagonal row keys (ref order > key)
+  for (int J = 0; J < H.n_nodes; ++J)
+    for (int p = H.col_ptr[J]; p < H.col_ptr[J + 1]; ++p) {
+      int I = H.row_idx[p];
+      for (int kj : node_keys[J])
+        for (int ki : node_keys[I]) {
+          if (ki == kj) continue;
+          if (I == J && ki < kj) continue;  // handled when the roles are swapped
+          int lo = std::min(ki, kj), hi = std::max(ki, kj);
+          rows_of_key[lo].push_back(hi);
+        }
+    }
+  int64_t nnz = 0;
+  for (int k = 0; k < nk; ++k) {
+    auto& v = rows_of_key[k];
+    std::sort(v.begin(), v.end());
+    v.erase(std::unique(v.begin(), v.end()), v.end());
+    int offd = 0;
+    for (int r : v) offd += a.keys[r].tdim;
+    for (int c = 0; c < a.keys[k].tdim; ++c) {
+      int64_t n = (a.keys[k].tdim - c) + offd;
+      nnz += n;
+      SFX_CHECK(nnz < (int64_t)INT32_MAX, SFX_ERR_UNSUPPORTED,
+                "hessian_lower has >= 2^31 nonzeros (reference limit, linearizer.cc:317-323)");
+      a.csc_outer[a.keys[k].ref_toff + c + 1] = (int32_t)nnz;
+    }
+  }
+  a.nnz = nnz;
+  a.csc_inner.resize(nnz);
+  a.csc_src.resize(nnz);
+  auto value_pos = [&](int krow, int r, int kcol, int c) -> int32_t {
+    // H value offset of entry (key krow row r, key kcol col c), reference-lower (krow >= kcol)
+    int I = a.keys[krow].node, J = a.keys[kcol].node;
+    int rr = a.keys[krow].sub + r, cc = a.keys[kcol].sub + c;
+    if (I < J || (I == J && rr < cc)) {
+      std::swap(I, J);
+      std::swap(rr, cc);
+    }
+    int b = H.find(I, J);
+    return (int32_t)(H.blk_off[b] + rr + (int64_t)cc * H.node_dim[I]);
+  };
+  for (int k = 0; k < nk; ++k) {
+    const int dk = a.keys[k].tdim;
+    for (int c = 0; c < dk; ++c) {
+      int64_t p = a.csc_outer[a.keys[k].ref_toff + c];
+      for (int r = c; r < dk; ++r) {
+        a.csc_inner[p] = a.keys[k].ref_toff + r;
+        a.csc_src[p] = value_pos(k, r, k, c);
+        ++p;
+      }
+      for (int rk : rows_of_key[k])
+        for (int r = 0; r < a.keys[rk].tdim; ++r) {
+          a.csc_inner[p] = a.keys[rk].ref_toff + r;
+          a.csc_src[p] = value_pos(rk, r, k, c);
+          ++p;
+        }
+    }
+  }
+  a.csc_built = true;
+}
+
+}  // namespace sfx

@@ -1,0 +1,1053 @@
+// CUDA kernels of the sparse Levenberg-Marquardt inner loop (sm_100a).
+//
+//   K1 linearize_kernel<Kind>      factor residual/Jacobian (generated fp64 device functions), fused
+//                                  J^T J / J^T r block scatter + 0.5|r|^2 partial sums
+//                                  -> replaces Linearizer::Relinearize (symforce/opt/linearizer.cc:55-120, 359-433)
+//   K2 damping_kernel              DampHessian (levenberg_marquardt_solver.tcc:23-54) as a vector; H is never
+//                                  modified in place, so no save/restore of the diagonal is needed
+//   K3 schur_*                     C^-1 per landmark in registers, S = B - E C^-1 E^T per block from
+//                                  precomputed match lists, reduced rhs, back-substitution
+//                                  -> replaces SparseSchurSolver::Factorize/Solve (sparse_schur_solver.tcc:101-162)
+//   K4 front_factor_kernel         multifrontal supernodal Cholesky, one CTA per front, level scheduled
+//                                  -> replaces SparseCholeskySolver::Factorize (sparse_cholesky_solver.tcc:109-219)
+//   K5 front_solve_*               supernodal forward/backward substitution (…tcc:232-259)
+//   K6 retract_kernel              Values::Retract (symforce/opt/values.cc:315-327)
+//   K7 lm_* / *_reduce             gain ratio, accept/reject, lambda update, state-block bookkeeping on the
+//                                  device (levenberg_marquardt_solver.tcc:139-343) -- no host round trip
+#include <cstdio>
+
+#include "gen/factors_gen.cuh"
+#include "kernels.cuh"
+
+namespace sfx {
+
+int64_t g_launches = 0;  // kernels launched by this library (bench.py reports it)
+
+// ------------------------------------------------------------------------------------------------
+// helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// deterministic block sum (result valid in thread 0)
+template <int THREADS>
+__device__ __forceinline__ double block_sum(double v) {
+  __shared__ double sh[THREADS / 32];
+  v = warp_sum(v);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  __syncthreads();
+  if (lane == 0) sh[w] = v;
+  __syncthreads();
+  double r = 0;
+  if (threadIdx.x == 0) {
+#pragma unroll
+    for (int i = 0; i < THREADS / 32; ++i) r += sh[i];
+  }
+  return r;
+}
+
+__device__ __forceinline__ int sel_block(const Ctrl* c, int mode) { return mode == 0 ? c->init_idx : c->new_idx; }
+
+// ------------------------------------------------------------------------------------------------
+// K1: linearize
+// ------------------------------------------------------------------------------------------------
+template <int KIND>
+struct Kind;
+
+#define SFX_KIND_BEGIN(ID, R_, T_, NOPT_, NUSED_)   \
+  template <>                                       \
+  struct Kind<ID> {                                 \
+    static constexpr int R = R_, T = T_, NOPT = NOPT_, NUSED = NUSED_;
+
+// arg pointers are given for USED args only, in argument order
+SFX_KIND_BEGIN(SFX_KIND_SNAVELY, 2, 12, 3, 4)
+  __host__ __device__ static constexpr int dim(int k) { return k == 0 ? 6 : (k == 1 ? 3 : 3); }
+  __host__ __device__ static constexpr int col(int k) { return k == 0 ? 0 : (k == 1 ? 6 : 9); }
+  __device__ static void eval(const double* const* a, double* res, double* J) {
+    sfx_factor_snavely(a[0], a[1], a[2], a[3], nullptr, res, J);
+  }
+};
+SFX_KIND_BEGIN(SFX_KIND_BETWEEN_POSE3, 6, 12, 2, 5)
+  __host__ __device__ static constexpr int dim(int k) { return k == 0 ? 6 : (k == 1 ? 6 : 0); }
+  __host__ __device__ static constexpr int col(int k) { return k == 0 ? 0 : (k == 1 ? 6 : 12); }
+  __device__ static void eval(const double* const* a, double* res, double* J) {
+    sfx_factor_between_pose3(a[0], a[1], a[2], a[3], a[4], res, J);
+  }
+};
+SFX_KIND_BEGIN(SFX_KIND_PRIOR_POSE3, 6, 6, 1, 4)
+  __host__ __device__ static constexpr int dim(int k) { return k == 0 ? 6 : (k == 1 ? 0 : 0); }
+  __host__ __device__ static constexpr int col(int k) { return k == 0 ? 0 : (k == 1 ? 6 : 6); }
+  __device__ static void eval(const double* const* a, double* res, double* J) {
+    sfx_factor_prior_pose3(a[0], a[1], a[2], a[3], res, J);
+  }
+};
+SFX_KIND_BEGIN(SFX_KIND_MATCHING, 3, 6, 1, 4)
+  __host__ __device__ static constexpr int dim(int k) { return k == 0 ? 6 : (k == 1 ? 0 : 0); }
+  __host__ __device__ static constexpr int col(int k) { return k == 0 ? 0 : (k == 1 ? 6 : 6); }
+  __device__ static void eval(const double* const* a, double* res, double* J) {
+    sfx_factor_matching(a[0], a[1], a[2], a[3], res, J);
+  }
+};
+SFX_KIND_BEGIN(SFX_KIND_ODOMETRY, 6, 12, 2, 5)
+  __host__ __device__ static constexpr int dim(int k) { return k == 0 ? 6 : (k == 1 ? 6 : 0); }
+  __host__ __device__ static constexpr int col(int k) { return k == 0 ? 0 : (k == 1 ? 6 : 12); }
+  __device__ static void eval(const double* const* a, double* res, double* J) {
+    sfx_factor_odometry(a[0], a[1], a[2], a[3], a[4], res, J);
+  }
+};
+SFX_KIND_BEGIN(SFX_KIND_IRL_LINEAR_GNC, 2, 13, 3, 11)
+  __host__ __device__ static constexpr int dim(int k) { return k == 0 ? 6 : (k == 1 ? 6 : 1); }
+  __host__ __device__ static constexpr int col(int k) { return k == 0 ? 0 : (k == 1 ? 6 : 12); }
+  __device__ static void eval(const double* const* a, double* res, double* J) {
+    sfx_factor_irl_linear_gnc(a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[7], a[8], a[9], a[10], res, J);
+  }
+};
+SFX_KIND_BEGIN(SFX_KIND_IRL_PRIOR, 1, 1, 1, 5)
+  __host__ __device__ static constexpr int dim(int k) { return k == 0 ? 1 : (k == 1 ? 0 : 0); }
+  __host__ __device__ static constexpr int col(int k) { return k == 0 ? 0 : (k == 1 ? 1 : 1); }
+  __device__ static void eval(const double* const* a, double* res, double* J) {
+    sfx_factor_irl_prior(a[0], a[1], a[2], a[3], a[4], res, J);
+  }
+};
+SFX_KIND_BEGIN(SFX_KIND_BETWEEN_ROT3, 3, 6, 2, 5)
+  __host__ __device__ static constexpr int dim(int k) { return k == 0 ? 3 : (k == 1 ? 3 : 0); }
+  __host__ __device__ static constexpr int col(int k) { return k == 0 ? 0 : (k == 1 ? 3 : 6); }
+  __device__ static void eval(const double* const* a, double* res, double* J) {
+    sfx_factor_between_rot3(a[0], a[1], a[2], a[3], a[4], res, J);
+  }
+};
+SFX_KIND_BEGIN(SFX_KIND_PRIOR_ROT3, 3, 3, 1, 4)
+  __host__ __device__ static constexpr int dim(int k) { return k == 0 ? 3 : (k == 1 ? 0 : 0); }
+  __host__ __device__ static constexpr int col(int k) { return k == 0 ? 0 : (k == 1 ? 3 : 3); }
+  __device__ static void eval(const double* const* a, double* res, double* J) {
+    sfx_factor_prior_rot3(a[0], a[1], a[2], a[3], res, J);
+  }
+};
+
+constexpr int kLinThreads = 128;
+
+template <int KIND>
+__global__ void __launch_bounds__(kLinThreads) linearize_kernel(const Ctrl* __restrict__ ctrl, StatePtrs sp, LinBatch b,
+                                                                 int mode, double* __restrict__ partials) {
+  using K = Kind<KIND>;
+  if (ctrl->done) return;
+  const int blk = sel_block(ctrl, mode);
+  if (mode == 0 && ctrl->lin_valid[blk]) return;
+  const double* __restrict__ values = sp.values[blk];
+  double* __restrict__ H = sp.H[blk];
+  double* __restrict__ rhs = sp.rhs[blk];
+  double* __restrict__ resid = sp.res[blk];
+
+  const int s = blockIdx.x * kLinThreads + threadIdx.x;
+  double err = 0.0;
+  if (s < b.n) {
+    const double* a[K::NUSED];
+#pragma unroll
+    for (int u = 0; u < K::NUSED; ++u) a[u] = values + __ldg(b.arg_off + (size_t)u * b.n + s);
+    double res[K::R];
+    double J[K::R * K::T];
+    K::eval(a, res, J);
+    const int ro = __ldg(b.res_off + s);
+#pragma unroll
+    for (int q = 0; q < K::R; ++q) {
+      resid[ro + q] = res[q];
+      err += res[q] * res[q];
+    }
+    int rhs_base[3], diag_base[3];
+#pragma unroll
+    for (int g = 0; g < 3; ++g)
+      if (g < b.n_groups) {
+        rhs_base[g] = __ldg(b.rhs_off + (size_t)g * b.n + s);
+        diag_base[g] = __ldg(b.diag_off + (size_t)g * b.n + s);
+      }
+    uint32_t off_base[3];
+    {
+      const int npairs = b.n_groups * (b.n_groups - 1) / 2;
+#pragma unroll
+      for (int p = 0; p < 3; ++p)
+        if (p < npairs) off_base[p] = __ldg(b.off_off + (size_t)p * b.n + s);
+    }
+#pragma unroll
+    for (int ka = 0; ka < K::NOPT; ++ka) {
+      const int g = b.key_group[ka];
+      if (g < 0) continue;
+      const int sa = b.key_sub[ka];
+      // rhs = J^T r
+#pragma unroll
+      for (int r = 0; r < K::dim(ka); ++r) {
+        double v = 0;
+#pragma unroll
+        for (int q = 0; q < K::R; ++q) v += J[q + (K::col(ka) + r) * K::R] * res[q];
+        atomicAdd(rhs + rhs_base[g] + sa + r, v);
+      }
+#pragma unroll
+      for (int kb = 0; kb <= ka; ++kb) {
+        const int h = b.key_group[kb];
+        if (h < 0) continue;
+        const int sb = b.key_sub[kb];
+        if (g == h) {
+          const int ld = b.group_dim[g];
+          double* dst = H + diag_base[g];
+          if (ka == kb) {
+#pragma unroll
+            for (int c = 0; c < K::dim(ka); ++c)
+#pragma unroll
+              for (int r = c; r < K::dim(ka); ++r) {
+                double v = 0;
+#pragma unroll
+                for (int q = 0; q < K::R; ++q) v += J[q + (K::col(ka) + r) * K::R] * J[q + (K::col(ka) + c) * K::R];
+                atomicAdd(dst + (sa + r) + (size_t)(sa + c) * ld, v);
+              }
+          } else {
+            const bool a_is_row = sa > sb;
+#pragma unroll
+            for (int c = 0; c < K::dim(kb); ++c)
+#pragma unroll
+              for (int r = 0; r < K::dim(ka); ++r) {
+                double v = 0;
+#pragma unroll
+                for (int q = 0; q < K::R; ++q) v += J[q + (K::col(ka) + r) * K::R] * J[q + (K::col(kb) + c) * K::R];
+                const size_t o = a_is_row ? (size_t)(sa + r) + (size_t)(sb + c) * ld
+                                          : (size_t)(sb + c) + (size_t)(sa + r) * ld;
+                atomicAdd(dst + o, v);
+              }
+          }
+        } else {
+          const int G = g > h ? g : h, Hh = g > h ? h : g;
+          const uint32_t ob = off_base[G * (G - 1) / 2 + Hh];
+          double* dst = H + (ob & 0x3fffffffu);
+          const bool excl = (ob >> 31) != 0;
+          const bool tr = ((ob >> 30) & 1u) != 0;
+          // row side of the stored block: group G unless transposed
+          const bool a_is_row = ((g == G) != tr);
+          const int ld = a_is_row ? b.group_dim[g] : b.group_dim[h];
+#pragma unroll
+          for (int c = 0; c < K::dim(kb); ++c)
+#pragma unroll
+            for (int r = 0; r < K::dim(ka); ++r) {
+              double v = 0;
+#pragma unroll
+              for (int q = 0; q < K::R; ++q) v += J[q + (K::col(ka) + r) * K::R] * J[q + (K::col(kb) + c) * K::R];
+              const size_t o = a_is_row ? (size_t)(sa + r) + (size_t)(sb + c) * ld
+                                        : (size_t)(sb + c) + (size_t)(sa + r) * ld;
+              if (excl)
+                dst[o] = v;
+              else
+                atomicAdd(dst + o, v);
+            }
+        }
+      }
+    }
+  }
+  const double tot = block_sum<kLinThreads>(err);
+  if (threadIdx.x == 0) partials[b.partial_base + blockIdx.x] = tot;
+}
+
+__global__ void zero_lin_kernel(const Ctrl* __restrict__ ctrl, StatePtrs sp, int mode, int64_t n_h, int n_rhs) {
+  if (ctrl->done) return;
+  const int blk = sel_block(ctrl, mode);
+  if (mode == 0 && ctrl->lin_valid[blk]) return;
+  double* H = sp.H[blk];
+  double* rhs = sp.rhs[blk];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_h; i += stride) H[i] = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_rhs; i += stride) rhs[i] = 0.0;
+}
+
+// sums the per-CTA partials deterministically; err[target] = 0.5 * sum
+__global__ void finish_error_kernel(Ctrl* ctrl, const double* __restrict__ partials, int n, int mode) {
+  if (ctrl->done) return;
+  const int blk = sel_block(ctrl, mode);
+  if (mode == 0 && ctrl->lin_valid[blk]) return;
+  double v = 0;
+  for (int i = threadIdx.x; i < n; i += 1024) v += partials[i];
+  const double tot = block_sum<1024>(v);
+  if (threadIdx.x == 0) {
+    ctrl->err[blk] = 0.5 * tot;
+    ctrl->lin_valid[blk] = 1;
+  }
+}
+
+void launch_zero_lin(cudaStream_t st, const Ctrl* ctrl, StatePtrs sp, int mode, int64_t n_h, int n_rhs) {
+  int64_t work = n_h > n_rhs ? n_h : n_rhs;
+  int grid = (int)((work + 255) / 256);
+  if (grid > 148 * 16) grid = 148 * 16;
+  if (grid < 1) grid = 1;
+  zero_lin_kernel<<<grid, 256, 0, st>>>(ctrl, sp, mode, n_h, n_rhs); ++g_launches;
+}
+
+void launch_linearize(cudaStream_t st, const Ctrl* ctrl, StatePtrs sp, int mode, const LinBatch& b, double* partials) {
+  const int grid = (b.n + kLinThreads - 1) / kLinThreads;
+  switch (b.kind) {
+#define SFX_CASE(ID) \
+  case ID: linearize_kernel<ID><<<grid, kLinThreads, 0, st>>>(ctrl, sp, b, mode, partials); ++g_launches; break;
+    SFX_CASE(SFX_KIND_SNAVELY)
+    SFX_CASE(SFX_KIND_BETWEEN_POSE3)
+    SFX_CASE(SFX_KIND_PRIOR_POSE3)
+    SFX_CASE(SFX_KIND_MATCHING)
+    SFX_CASE(SFX_KIND_ODOMETRY)
+    SFX_CASE(SFX_KIND_IRL_LINEAR_GNC)
+    SFX_CASE(SFX_KIND_IRL_PRIOR)
+    SFX_CASE(SFX_KIND_BETWEEN_ROT3)
+    SFX_CASE(SFX_KIND_PRIOR_ROT3)
+#undef SFX_CASE
+  }
+}
+
+void launch_finish_error(cudaStream_t st, Ctrl* ctrl, int mode, const double* partials, int n_partials) {
+  finish_error_kernel<<<1, 1024, 0, st>>>(ctrl, partials, n_partials, mode); ++g_launches;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K2: damping vector (internal scalar order)
+// ------------------------------------------------------------------------------------------------
+__global__ void damping_kernel(Ctrl* ctrl, StatePtrs sp, const int32_t* __restrict__ diag_pos, int N,
+                               double* __restrict__ dvec, double* __restrict__ max_diag) {
+  if (ctrl->done) return;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const double* H = sp.H[ctrl->init_idx];
+  const sfx_params& p = ctrl->p;
+  const double lam = ctrl->lambda;
+  double d = 0.0;
+  if (p.use_diagonal_damping) {
+    const double diag = H[diag_pos[i]];
+    if (p.keep_max_diagonal_damping) {
+      double m = ctrl->have_max_diag ? fmax(max_diag[i], diag) : fmax(diag, p.diagonal_damping_min);
+      max_diag[i] = m;
+      d = m * lam;
+    } else {
+      d = fmax(diag, p.diagonal_damping_min) * lam;
+    }
+  }
+  if (p.use_unit_damping) d += lam;
+  dvec[i] = d;
+}
+
+__global__ void damping_flag_kernel(Ctrl* ctrl) {
+  if (ctrl->done) return;
+  if (ctrl->p.use_diagonal_damping && ctrl->p.keep_max_diagonal_damping) ctrl->have_max_diag = 1;
+}
+
+void launch_damping(cudaStream_t st, Ctrl* ctrl, StatePtrs sp, const int32_t* diag_pos, int N, double* dvec,
+                    double* max_diag) {
+  damping_kernel<<<(N + 255) / 256, 256, 0, st>>>(ctrl, sp, diag_pos, N, dvec, max_diag); ++g_launches;
+  damping_flag_kernel<<<1, 1, 0, st>>>(ctrl); ++g_launches;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K3: Schur complement
+// ------------------------------------------------------------------------------------------------
+// C^-1 per landmark via dense LLT solve of the identity (sparse_schur_solver.tcc:105-119), in registers.
+__global__ void schur_cinv_kernel(const Ctrl* __restrict__ ctrl, StatePtrs sp, SchurDev sd,
+                                  const double* __restrict__ dvec) {
+  if (ctrl->done) return;
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  if (l >= sd.n_landmarks) return;
+  const int blk = ctrl->init_idx;
+  const double* H = sp.H[blk];
+  const double* rhs = sp.rhs[blk];
+  const int d = sd.lm_dim[l];
+  const int to = sd.lm_toff[l];
+  const double* C = H + sd.lm_cdiag_off[l];
+  double A[3][3], L[3][3], Ci[3][3];
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      A[r][c] = 0.0;
+      L[r][c] = 0.0;
+      Ci[r][c] = 0.0;
+    }
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int r = c; r < 3; ++r)
+      if (r < d && c < d) A[r][c] = C[r + c * d] + (r == c ? dvec[to + r] : 0.0);
+  // Cholesky
+#pragma unroll
+  for (int j = 0; j < 3; ++j)
+    if (j < d) {
+      double x = A[j][j];
+#pragma unroll
+      for (int k = 0; k < j; ++k) x -= L[j][k] * L[j][k];
+      x = sqrt(x);
+      L[j][j] = x;
+#pragma unroll
+      for (int i = j + 1; i < 3; ++i)
+        if (i < d) {
+          double y = A[i][j];
+#pragma unroll
+          for (int k = 0; k < j; ++k) y -= L[i][k] * L[j][k];
+          L[i][j] = y / x;
+        }
+    }
+#pragma unroll
+  for (int e = 0; e < 3; ++e)
+    if (e < d) {
+      double y[3] = {0, 0, 0};
+#pragma unroll
+      for (int i = 0; i < 3; ++i)
+        if (i < d) {
+          double v = (i == e) ? 1.0 : 0.0;
+#pragma unroll
+          for (int k = 0; k < i; ++k) v -= L[i][k] * y[k];
+          y[i] = v / L[i][i];
+        }
+#pragma unroll
+      for (int i = 2; i >= 0; --i)
+        if (i < d) {
+          double v = y[i];
+#pragma unroll
+          for (int k = i + 1; k < 3; ++k)
+            if (k < d) v -= L[k][i] * y[k];
+          y[i] = v / L[i][i];
+        }
+#pragma unroll
+      for (int i = 0; i < 3; ++i) Ci[i][e] = y[i];
+    }
+  // symmetrise from the lower part (the reference keeps C_inv_lower and reads it as selfadjoint)
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int r = 0; r < c; ++r) Ci[r][c] = Ci[c][r];
+  double* out = sd.cinv + (size_t)l * 9;
+#pragma unroll
+  for (int c = 0; c < 3; ++c)
+#pragma unroll
+    for (int r = 0; r < 3; ++r) out[r + c * 3] = Ci[r][c];
+  double w[3] = {0, 0, 0};
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+    if (r < d) w[r] = rhs[to + r];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) sd.tl[(size_t)l * 3 + r] = Ci[r][0] * w[0] + Ci[r][1] * w[1] + Ci[r][2] * w[2];
+}
+
+// One warp per S block: S_IJ = B_IJ (+ D on the diagonal) - sum_matches E_I^T C^-1 E_J.
+constexpr int kSchurWarps = 4;
+__global__ void __launch_bounds__(kSchurWarps * 32) schur_s_kernel(const Ctrl* __restrict__ ctrl, StatePtrs sp,
+                                                                   SchurDev sd, const double* __restrict__ dvec) {
+  if (ctrl->done) return;
+  __shared__ double sh[kSchurWarps][3 * 16 * 2 + 3 * 16 + 9];
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * kSchurWarps + wid;
+  if (b >= sd.n_sblocks) return;
+  const double* H = sp.H[ctrl->init_idx];
+  const int I = sd.s_row[b], J = sd.s_col[b];
+  const int dI = sd.node_dim[I], dJ = sd.node_dim[J];
+  const int ne = dI * dJ;
+  double* EI = sh[wid];
+  double* EJ = EI + 48;
+  double* G = EJ + 48;
+  double* Cs = G + 48;
+  double acc[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) acc[k] = 0.0;
+  const int64_t m0 = sd.s_m_ptr[b], m1 = sd.s_m_ptr[b + 1];
+  for (int64_t m = m0; m < m1; ++m) {
+    const int l = sd.m_lm[m];
+    const int dl = sd.lm_dim[l];
+    const double* ei = H + sd.m_eoff_i[m];
+    const double* ej = H + sd.m_eoff_j[m];
+    __syncwarp();
+    for (int t = lane; t < dl * dI; t += 32) EI[t] = ei[t];
+    for (int t = lane; t < dl * dJ; t += 32) EJ[t] = ej[t];
+    if (lane < 9) Cs[lane] = sd.cinv[(size_t)l * 9 + lane];
+    __syncwarp();
+    // G = Cinv * EJ  (dl x dJ)
+    for (int t = lane; t < dl * dJ; t += 32) {
+      const int a = t % dl, c = t / dl;
+      double v = 0;
+      for (int q = 0; q < dl; ++q) v += Cs[a + q * 3] * EJ[q + c * dl];
+      G[t] = v;
+    }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int e = lane + 32 * k;
+      if (e < ne) {
+        const int r = e % dI, c = e / dI;
+        double v = 0;
+        for (int q = 0; q < dl; ++q) v += EI[q + r * dl] * G[q + c * dl];
+        acc[k] += v;
+      }
+    }
+  }
+  double* out = sd.S + sd.s_off[b];
+  const int bsrc = sd.s_b_src[b];
+  const int toI = sd.node_toff[I];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    const int e = lane + 32 * k;
+    if (e < ne) {
+      const int r = e % dI, c = e / dI;
+      double v = -acc[k];
+      if (bsrc >= 0) v += H[bsrc + e];
+      if (I == J && r == c) v += dvec[toI + r];
+      out[e] = v;
+    }
+  }
+}
+
+// reduced rhs: v_I - sum_l E_{l,I}^T (C_l^-1 w_l); one warp per reduced node
+__global__ void __launch_bounds__(128) schur_rhs_kernel(const Ctrl* __restrict__ ctrl, StatePtrs sp, SchurDev sd) {
+  if (ctrl->done) return;
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int I = blockIdx.x * 4 + wid;
+  if (I >= sd.n_reduced_nodes) return;
+  const int blk = ctrl->init_idx;
+  const double* H = sp.H[blk];
+  const double* rhs = sp.rhs[blk];
+  const int dI = sd.node_dim[I];
+  // lanes: r = lane % 16 is the column of E (component of node I), half = lane / 16 splits entries
+  const int r = lane & 15, half = lane >> 4;
+  double acc = 0.0;
+  for (int q = sd.r_ptr[I] + half; q < sd.r_ptr[I + 1]; q += 2) {
+    const int l = sd.r_lm[q];
+    const int dl = sd.lm_dim[l];
+    if (r < dI) {
+      const double* e = H + sd.r_eoff[q] + r * dl;
+      const double* t = sd.tl + (size_t)l * 3;
+      double v = 0;
+      for (int a = 0; a < dl; ++a) v += e[a] * t[a];
+      acc += v;
+    }
+  }
+  acc += __shfl_xor_sync(0xffffffffu, acc, 16);
+  if (half == 0 && r < dI) {
+    const int to = sd.node_toff[I];
+    sd.rhs_red[to + r] = rhs[to + r] - acc;
+  }
+}
+
+// z_l = C^-1 (w_l - E_l y) = t_l - C^-1 (E_l y); update = -[y; z]
+__global__ void schur_back_kernel(const Ctrl* __restrict__ ctrl, StatePtrs sp, SchurDev sd, const double* __restrict__ y,
+                                  double* __restrict__ upd) {
+  if (ctrl->done) return;
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = l; i < sd.reduced_dim; i += stride) upd[i] = -y[i];
+  if (l >= sd.n_landmarks) return;
+  const double* H = sp.H[ctrl->init_idx];
+  const int dl = sd.lm_dim[l];
+  double s[3] = {0, 0, 0};
+  for (int q = sd.lm_e_ptr[l]; q < sd.lm_e_ptr[l + 1]; ++q) {
+    const int J = sd.lm_e_node[q];
+    const int dJ = sd.node_dim[J];
+    const double* e = H + sd.lm_e_off[q];
+    const double* yj = y + sd.node_toff[J];
+    for (int c = 0; c < dJ; ++c) {
+      const double yc = yj[c];
+      for (int a = 0; a < dl; ++a) s[a] += e[a + c * dl] * yc;
+    }
+  }
+  const double* Ci = sd.cinv + (size_t)l * 9;
+  const double* t = sd.tl + (size_t)l * 3;
+  const int to = sd.lm_toff[l];
+  for (int a = 0; a < dl; ++a) {
+    double z = t[a] - (Ci[a] * s[0] + Ci[a + 3] * s[1] + Ci[a + 6] * s[2]);
+    upd[to + a] = -z;
+  }
+}
+
+void launch_schur(cudaStream_t st, const Ctrl* ctrl, StatePtrs sp, const SchurDev& sd, const double* dvec) {
+  schur_cinv_kernel<<<(sd.n_landmarks + 127) / 128, 128, 0, st>>>(ctrl, sp, sd, dvec); ++g_launches;
+  schur_s_kernel<<<(sd.n_sblocks + kSchurWarps - 1) / kSchurWarps, kSchurWarps * 32, 0, st>>>(ctrl, sp, sd, dvec); ++g_launches;
+  schur_rhs_kernel<<<(sd.n_reduced_nodes + 3) / 4, 128, 0, st>>>(ctrl, sp, sd); ++g_launches;
+}
+
+void launch_schur_back(cudaStream_t st, const Ctrl* ctrl, StatePtrs sp, const SchurDev& sd, const double* y,
+                       double* upd) {
+  int n = sd.n_landmarks > sd.reduced_dim ? sd.n_landmarks : sd.reduced_dim;
+  schur_back_kernel<<<(n + 127) / 128, 128, 0, st>>>(ctrl, sp, sd, y, upd); ++g_launches;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4: multifrontal Cholesky, one CTA per front
+// ------------------------------------------------------------------------------------------------
+constexpr int kFrontThreads = 256;
+constexpr int kPanel = 8;
+
+// Partial Cholesky of the leading w columns of the m x m (lower) matrix F with leading dimension ld;
+// leaves the Schur complement in F[w:, w:].
+__device__ void front_partial_cholesky(double* F, int ld, int m, int w, int* fail) {
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+  for (int kb = 0; kb < w; kb += kPanel) {
+    const int nb = min(kPanel, w - kb);
+    for (int k = kb; k < kb + nb; ++k) {
+      __syncthreads();
+      if (tid == 0) {
+        double d = F[k + (size_t)k * ld];
+        if (!(d > 0.0)) {
+          *fail = 1;
+          d = __longlong_as_double(0x7ff8000000000000LL);
+        }
+        F[k + (size_t)k * ld] = sqrt(d);
+      }
+      __syncthreads();
+      const double piv = F[k + (size_t)k * ld];
+      for (int i = k + 1 + tid; i < m; i += nt) F[i + (size_t)k * ld] /= piv;
+      __syncthreads();
+      // update the remaining panel columns
+      const int pc = kb + nb - (k + 1);
+      if (pc > 0)
+        for (int i = k + 1 + tid; i < m; i += nt) {
+          const double lik = F[i + (size_t)k * ld];
+          for (int j = k + 1; j < kb + nb; ++j)
+            if (i >= j) F[i + (size_t)j * ld] -= lik * F[j + (size_t)k * ld];
+        }
+    }
+    __syncthreads();
+    // trailing update: columns j >= kb+nb, rows i >= j
+    for (int j = kb + nb + warp; j < m; j += nw) {
+      double ljk[kPanel];
+#pragma unroll
+      for (int k = 0; k < kPanel; ++k) ljk[k] = k < nb ? F[j + (size_t)(kb + k) * ld] : 0.0;
+      for (int i = j + lane; i < m; i += 32) {
+        double v = F[i + (size_t)j * ld];
+#pragma unroll
+        for (int k = 0; k < kPanel; ++k)
+          if (k < nb) v -= F[i + (size_t)(kb + k) * ld] * ljk[k];
+        F[i + (size_t)j * ld] = v;
+      }
+    }
+  }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(kFrontThreads) front_factor_kernel(Ctrl* ctrl, FrontDev fd,
+                                                                     const double* __restrict__ sys_static, StatePtrs sp,
+                                                                     int use_state_H, const double* __restrict__ dvec,
+                                                                     int lvl_begin, int smem_m_max) {
+  extern __shared__ double smem[];
+  if (ctrl->done) return;
+  const int s = fd.level_fronts[lvl_begin + blockIdx.x];
+  const int w = fd.f_w[s], u = fd.f_u[s], m = w + u;
+  const double* sys = use_state_H ? sp.H[ctrl->init_idx] : sys_static;
+  double* Fg = fd.fronts + fd.f_off[s];
+  const bool in_smem = m <= smem_m_max;
+  double* F = in_smem ? smem : Fg;
+  const int ld = m;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  // zero (lower part suffices, zero all for simplicity)
+  for (int64_t i = tid; i < (int64_t)m * m; i += nt) F[i] = 0.0;
+  __syncthreads();
+  // system matrix blocks
+  for (int ci = fd.f_copy_ptr[s]; ci < fd.f_copy_ptr[s + 1]; ++ci) {
+    const FrontCopy c = fd.copies[ci];
+    const int ne = c.rows * c.cols;
+    for (int e = tid; e < ne; e += nt) {
+      const int r = e % c.rows, cc = e / c.rows;
+      if (c.lower_only && r < cc) continue;
+      const double v = sys[c.src + r + (int64_t)cc * c.src_ld];
+      if (c.transposed)
+        F[(c.dst_row + cc) + (size_t)(c.dst_col + r) * ld] += v;
+      else
+        F[(c.dst_row + r) + (size_t)(c.dst_col + cc) * ld] += v;
+    }
+  }
+  __syncthreads();
+  if (dvec != nullptr)
+    for (int r = tid; r < w; r += nt) F[r + (size_t)r * ld] += dvec[fd.scalar_perm[fd.f_piv[s] + r]];
+  __syncthreads();
+  // extend-add of the children's update matrices (sequential over children: deterministic)
+  for (int ci = fd.f_child_ptr[s]; ci < fd.f_child_ptr[s + 1]; ++ci) {
+    const int c = fd.f_child[ci];
+    const int wc = fd.f_w[c], uc = fd.f_u[c], mc = wc + uc;
+    const double* U = fd.fronts + fd.f_off[c] + wc + (size_t)wc * mc;
+    const int32_t* rel = fd.f_rel + fd.f_rows_ptr[c];
+    for (int e = tid; e < uc * uc; e += nt) {
+      const int i = e % uc, j = e / uc;
+      if (i < j) continue;
+      F[rel[i] + (size_t)rel[j] * ld] += U[i + (size_t)j * mc];
+    }
+    __syncthreads();
+  }
+  front_partial_cholesky(F, ld, m, w, &ctrl->chol_fail);
+  if (in_smem) {
+    for (int64_t e = tid; e < (int64_t)m * m; e += nt) {
+      const int i = (int)(e % m), j = (int)(e / m);
+      if (i >= j) Fg[e] = F[e];
+    }
+  }
+}
+
+void launch_front_factor(cudaStream_t st, Ctrl* ctrl, const FrontDev& fd, const double* sysvals_static, StatePtrs sp,
+                         int use_state_H, const double* dvec, int lvl_begin, int lvl_count, int smem_m_max) {
+  // smem_m_max: fronts with m <= smem_m_max are factored in shared memory (chosen per launch)
+  const size_t smem = (size_t)smem_m_max * smem_m_max * sizeof(double);
+  front_factor_kernel<<<lvl_count, kFrontThreads, smem, st>>>(ctrl, fd, sysvals_static, sp, use_state_H, dvec,
+                                                              lvl_begin, smem_m_max); ++g_launches;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K5: supernodal triangular solves
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kFrontThreads) front_solve_fwd_kernel(const Ctrl* __restrict__ ctrl, FrontDev fd,
+                                                                        const double* __restrict__ rhs_static,
+                                                                        StatePtrs sp, int use_state_rhs, int lvl_begin) {
+  extern __shared__ double f[];  // m doubles
+  if (ctrl->done) return;
+  const int s = fd.level_fronts[lvl_begin + blockIdx.x];
+  const int w = fd.f_w[s], u = fd.f_u[s], m = w + u;
+  const double* rhs = use_state_rhs ? sp.rhs[ctrl->init_idx] : rhs_static;
+  const double* L = fd.fronts + fd.f_off[s];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  for (int r = tid; r < m; r += nt) f[r] = r < w ? rhs[fd.scalar_perm[fd.f_piv[s] + r]] : 0.0;
+  __syncthreads();
+  for (int ci = fd.f_child_ptr[s]; ci < fd.f_child_ptr[s + 1]; ++ci) {
+    const int c = fd.f_child[ci];
+    const int uc = fd.f_u[c];
+    const double* t = fd.twork + fd.f_toff[c];
+    const int32_t* rel = fd.f_rel + fd.f_rows_ptr[c];
+    for (int q = tid; q < uc; q += nt) f[rel[q]] += t[q];
+    __syncthreads();
+  }
+  // L11 y = f1 (column oriented)
+  for (int k = 0; k < w; ++k) {
+    if (tid == 0) f[k] /= L[k + (size_t)k * m];
+    __syncthreads();
+    const double yk = f[k];
+    for (int i = k + 1 + tid; i < w; i += nt) f[i] -= L[i + (size_t)k * m] * yk;
+    __syncthreads();
+  }
+  // t = f2 - L21 y1
+  for (int q = tid; q < u; q += nt) {
+    double v = f[w + q];
+    for (int k = 0; k < w; ++k) v -= L[(w + q) + (size_t)k * m] * f[k];
+    fd.twork[fd.f_toff[s] + q] = v;
+  }
+  for (int r = tid; r < w; r += nt) fd.ywork[fd.f_piv[s] + r] = f[r];
+}
+
+__global__ void __launch_bounds__(kFrontThreads) front_solve_bwd_kernel(const Ctrl* __restrict__ ctrl, FrontDev fd,
+                                                                        int lvl_begin) {
+  extern __shared__ double f[];  // m doubles: [x1 (w) | x2 (u)]
+  if (ctrl->done) return;
+  const int s = fd.level_fronts[lvl_begin + blockIdx.x];
+  const int w = fd.f_w[s], u = fd.f_u[s], m = w + u;
+  const double* L = fd.fronts + fd.f_off[s];
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+  const int32_t* rows = fd.f_rows + fd.f_rows_ptr[s];
+  for (int r = tid; r < m; r += nt) f[r] = r < w ? fd.ywork[fd.f_piv[s] + r] : fd.ywork[rows[r - w]];
+  __syncthreads();
+  // g = y1 - L21^T x2 : one warp per column
+  for (int r = warp; r < w; r += nw) {
+    double v = 0;
+    for (int q = lane; q < u; q += 32) v += L[(w + q) + (size_t)r * m] * f[w + q];
+    v = warp_sum(v);
+    if (lane == 0) f[r] -= v;
+  }
+  __syncthreads();
+  // L11^T x1 = g (row oriented back substitution)
+  for (int k = w - 1; k >= 0; --k) {
+    if (tid == 0) f[k] /= L[k + (size_t)k * m];
+    __syncthreads();
+    const double xk = f[k];
+    for (int i = tid; i < k; i += nt) f[i] -= L[k + (size_t)i * m] * xk;
+    __syncthreads();
+  }
+  for (int r = tid; r < w; r += nt) fd.ywork[fd.f_piv[s] + r] = f[r];
+}
+
+void launch_front_solve_fwd(cudaStream_t st, const Ctrl* ctrl, const FrontDev& fd, const double* rhs_static,
+                            StatePtrs sp, int use_state_rhs, int lvl_begin, int lvl_count) {
+  // dynamic smem sized by the largest front; set by the driver through cudaFuncSetAttribute
+  extern int g_solve_smem;
+  front_solve_fwd_kernel<<<lvl_count, kFrontThreads, g_solve_smem, st>>>(ctrl, fd, rhs_static, sp, use_state_rhs,
+                                                                        lvl_begin); ++g_launches;
+}
+void launch_front_solve_bwd(cudaStream_t st, const Ctrl* ctrl, const FrontDev& fd, int lvl_begin, int lvl_count) {
+  extern int g_solve_smem;
+  front_solve_bwd_kernel<<<lvl_count, kFrontThreads, g_solve_smem, st>>>(ctrl, fd, lvl_begin); ++g_launches;
+}
+int g_solve_smem = 0;
+
+cudaError_t configure_front_kernels(int smem_m_max, int max_front) {
+  cudaError_t e = cudaFuncSetAttribute(front_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       smem_m_max * smem_m_max * (int)sizeof(double));
+  if (e != cudaSuccess) return e;
+  g_solve_smem = max_front * (int)sizeof(double);
+  if (g_solve_smem > 48 * 1024) {
+    e = cudaFuncSetAttribute(front_solve_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_solve_smem);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(front_solve_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_solve_smem);
+  }
+  return e;
+}
+
+// out[scalar_perm[p]] = scale * ywork[p]
+__global__ void unpermute_kernel(const Ctrl* __restrict__ ctrl, FrontDev fd, double* __restrict__ out, double scale) {
+  if (ctrl->done) return;
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p < fd.n) out[fd.scalar_perm[p]] = scale * fd.ywork[p];
+}
+void launch_unpermute(cudaStream_t st, const Ctrl* ctrl, const FrontDev& fd, double* out, double scale) {
+  unpermute_kernel<<<(fd.n + 255) / 256, 256, 0, st>>>(ctrl, fd, out, scale); ++g_launches;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6: retract
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void retract_rot3(const double* a, const double* v, double eps, double* out) {
+  const double t0 = sqrt(eps * eps + v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+  const double t1 = 0.5 * t0;
+  const double s = sin(t1) / t0, c = cos(t1);
+  const double bx = s * v[0], by = s * v[1], bz = s * v[2];
+  double r0 = a[0] * c + a[1] * bz - a[2] * by + a[3] * bx;
+  double r1 = -a[0] * bz + a[1] * c + a[2] * bx + a[3] * by;
+  double r2 = a[2] * c + a[3] * bz + a[0] * by - a[1] * bx;
+  double r3 = -a[2] * bz + a[3] * c - a[0] * bx - a[1] * by;
+  const double n2 = r0 * r0 + r1 * r1 + r2 * r2 + r3 * r3;
+  if (n2 > 0) {
+    const double n = sqrt(n2);
+    r0 /= n;
+    r1 /= n;
+    r2 /= n;
+    r3 /= n;
+  }
+  out[0] = r0;
+  out[1] = r1;
+  out[2] = r2;
+  out[3] = r3;
+}
+
+__global__ void retract_kernel(const Ctrl* __restrict__ ctrl, StatePtrs sp, const int32_t* __restrict__ key_type,
+                               const int32_t* __restrict__ key_voff, const int32_t* __restrict__ key_sdim,
+                               const int32_t* __restrict__ key_tdim, const int32_t* __restrict__ key_itoff, int n_keys,
+                               const double* __restrict__ upd) {
+  if (ctrl->done) return;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_keys) return;
+  const double* src = sp.values[ctrl->init_idx] + key_voff[k];
+  double* dst = sp.values[ctrl->new_idx] + key_voff[k];
+  const double* v = upd + key_itoff[k];
+  const int type = key_type[k];
+  const double eps = ctrl->epsilon;
+  if (type == SFX_TYPE_VECTOR) {
+    const int d = key_tdim[k];
+    for (int i = 0; i < d; ++i) dst[i] = src[i] + v[i];
+  } else if (type == SFX_TYPE_ROT3) {
+    retract_rot3(src, v, eps, dst);
+  } else {
+    retract_rot3(src, v, eps, dst);
+    dst[4] = src[4] + v[3];
+    dst[5] = src[5] + v[4];
+    dst[6] = src[6] + v[5];
+  }
+}
+void launch_retract(cudaStream_t st, const Ctrl* ctrl, StatePtrs sp, const int32_t* key_type, const int32_t* key_voff,
+                    const int32_t* key_sdim, const int32_t* key_tdim, const int32_t* key_itoff, int n_keys,
+                    const double* upd) {
+  retract_kernel<<<(n_keys + 127) / 128, 128, 0, st>>>(ctrl, sp, key_type, key_voff, key_sdim, key_tdim, key_itoff,
+                                                       n_keys, upd); ++g_launches;
+}
+
+// ------------------------------------------------------------------------------------------------
+// K7: reductions + LM bookkeeping
+// ------------------------------------------------------------------------------------------------
+constexpr int kRedBlocks = 296;
+__global__ void __launch_bounds__(256) step_reduce_kernel(const Ctrl* __restrict__ ctrl, StatePtrs sp,
+                                                          const double* __restrict__ upd, const double* __restrict__ dvec,
+                                                          const double* __restrict__ last, int N,
+                                                          double* __restrict__ partials) {
+  if (ctrl->done) return;
+  const double* rhs = sp.rhs[ctrl->init_idx];
+  double a = 0, b = 0, c = 0, d = 0;
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < N; i += gridDim.x * 256) {
+    const double u = upd[i];
+    a += u * (rhs[i] - dvec[i] * u);
+    const double l = last[i];
+    b += l * u;
+    c += l * l;
+    d += u * u;
+  }
+  a = block_sum<256>(a);
+  b = block_sum<256>(b);
+  c = block_sum<256>(c);
+  d = block_sum<256>(d);
+  if (threadIdx.x == 0) {
+    partials[blockIdx.x * 4 + 0] = a;
+    partials[blockIdx.x * 4 + 1] = b;
+    partials[blockIdx.x * 4 + 2] = c;
+    partials[blockIdx.x * 4 + 3] = d;
+  }
+}
+__global__ void step_reduce_final_kernel(Ctrl* ctrl, const double* __restrict__ partials, int nb) {
+  if (ctrl->done) return;
+  const int q = threadIdx.x;  // 4 threads
+  double v = 0;
+  for (int i = 0; i < nb; ++i) v += partials[i * 4 + q];
+  ctrl->red[1 + q] = v;
+}
+void launch_step_reduce(cudaStream_t st, Ctrl* ctrl, StatePtrs sp, const double* upd, const double* dvec,
+                        const double* last_upd, int N, double* partials) {
+  int nb = (N + 255) / 256;
+  if (nb > kRedBlocks) nb = kRedBlocks;
+  step_reduce_kernel<<<nb, 256, 0, st>>>(ctrl, sp, upd, dvec, last_upd, N, partials); ++g_launches;
+  step_reduce_final_kernel<<<1, 4, 0, st>>>(ctrl, partials, nb); ++g_launches;
+}
+
+// state_.Step(); iteration_++   (levenberg_marquardt_solver.tcc:145-149)
+__global__ void lm_begin_kernel(Ctrl* c) {
+  if (c->done) return;
+  const int t = c->init_idx;
+  c->init_idx = c->new_idx;
+  c->new_idx = t;
+  c->iteration++;
+}
+
+// after the first linearization of Init: SetBestToInit + stats[-1] (…tcc:151-186)
+__global__ void lm_after_first_kernel(Ctrl* c) {
+  if (c->done) return;
+  if (c->iteration != 0) return;
+  c->best_valid = 1;
+  if (c->best_idx != c->init_idx) {
+    if (c->best_idx != c->new_idx) c->free_idx = c->best_idx;
+    c->best_idx = c->init_idx;
+  }
+  sfx_iteration& it = c->iters[0];
+  it.iteration = -1;
+  it.update_accepted = 0;
+  it.current_lambda = c->lambda;
+  it.new_error = c->err[c->init_idx];
+  it.new_error_linear = 0;
+  it.relative_reduction = 0;
+  it.update_angle_change = 0;
+  c->n_iters = 1;
+  if (!isfinite(c->err[c->init_idx])) {
+    c->done = 3;
+    c->failure_reason = 2;
+  }
+}
+
+// everything after Relinearize in Iterate() (…tcc:239-343)
+__global__ void lm_end_kernel(Ctrl* c, const double* __restrict__ upd, double* __restrict__ last_upd, int N,
+                              int* host_done) {
+  __shared__ int s_accept;
+  if (c->done) return;
+  if (threadIdx.x == 0) {
+    const sfx_params& p = c->p;
+    const double init_error = c->err[c->init_idx];
+    const double new_error = c->err[c->new_idx];
+    const double eps = c->epsilon;
+    const double relative_reduction = (init_error - new_error) / (init_error + eps);
+    const double new_error_linear = init_error + 0.5 * c->red[1];
+    const double gain_ratio = (init_error - new_error) / (init_error - new_error_linear);
+    int status = 0;
+    if (relative_reduction > -p.early_exit_min_reduction / 10 && relative_reduction < p.early_exit_min_reduction)
+      status = 1;
+    else if (new_error < p.early_exit_min_absolute_error)
+      status = 1;
+    bool accept = relative_reduction > 0;
+    double angle = 0;
+    if (p.enable_bold_updates && c->have_last_update && !accept) {
+      angle = c->red[2] / (sqrt(c->red[3]) * sqrt(c->red[4]));
+      accept = ((1 - angle) * (1 - angle) * new_error) <= c->err[c->best_idx];
+    }
+    if (!accept && c->lambda >= p.lambda_upper_bound) {
+      status = 3;
+      c->failure_reason = 1;
+    }
+    sfx_iteration& it = c->iters[c->n_iters];
+    it.iteration = c->iteration;
+    it.current_lambda = c->lambda;
+    it.new_error = new_error;
+    it.new_error_linear = new_error_linear;
+    it.relative_reduction = relative_reduction;
+    if (!accept) {
+      if (p.lambda_update_type == 1) {
+        c->lambda *= p.lambda_up_factor;
+      } else {
+        c->lambda *= c->nu;
+        c->nu *= 2;
+      }
+      const int t = c->init_idx;  // SwapNewAndInit
+      c->init_idx = c->new_idx;
+      c->new_idx = t;
+    } else {
+      if (p.lambda_update_type == 1) {
+        c->lambda *= p.lambda_down_factor;
+      } else {
+        c->lambda *= fmax(1.0 / p.dynamic_lambda_update_gamma,
+                          1.0 - (p.dynamic_lambda_update_beta - 1) *
+                                    pow(2 * gain_ratio - 1, (double)p.dynamic_lambda_update_p));
+        c->nu = 2;
+      }
+      c->have_last_update = 1;
+      if (new_error <= c->err[c->best_idx]) {  // SetBestToNew
+        c->best_valid = 1;
+        if (c->best_idx != c->new_idx) {
+          if (c->best_idx != c->init_idx) c->free_idx = c->best_idx;
+          c->best_idx = c->new_idx;
+        }
+        c->best_index = c->n_iters;
+      }
+      if (c->best_idx == c->init_idx) {  // SetInitToNotBest
+        c->init_idx = c->free_idx;
+        c->free_idx = c->best_idx;
+      }
+    }
+    c->lambda = fmin(fmax(c->lambda, p.lambda_lower_bound), p.lambda_upper_bound);
+    it.update_angle_change = angle;
+    it.update_accepted = accept ? 1 : 0;
+    c->n_iters++;
+    s_accept = accept ? 1 : 0;
+    if (status) {
+      if (status != 3) c->failure_reason = 0;
+      c->done = status;
+      *host_done = status;
+    }
+  }
+  __syncthreads();
+  if (s_accept)
+    for (int i = threadIdx.x; i < N; i += blockDim.x) last_upd[i] = upd[i];
+}
+
+void launch_lm_begin(cudaStream_t st, Ctrl* ctrl) { lm_begin_kernel<<<1, 1, 0, st>>>(ctrl); ++g_launches; }
+void launch_lm_after_first_linearize(cudaStream_t st, Ctrl* ctrl) { lm_after_first_kernel<<<1, 1, 0, st>>>(ctrl); ++g_launches; }
+void launch_lm_end(cudaStream_t st, Ctrl* ctrl, const double* upd, double* last_upd, int N, int* host_done) {
+  lm_end_kernel<<<1, 1024, 0, st>>>(ctrl, upd, last_upd, N, host_done); ++g_launches;
+}
+
+// ------------------------------------------------------------------------------------------------
+// misc: copies / exports (parity hooks)
+// ------------------------------------------------------------------------------------------------
+__global__ void copy_kernel(double* __restrict__ dst, const double* __restrict__ src, int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = src[i];
+}
+void launch_copy_values(cudaStream_t st, double* dst, const double* src, int64_t n) {
+  int grid = (int)((n + 255) / 256);
+  if (grid > 148 * 8) grid = 148 * 8;
+  if (grid < 1) grid = 1;
+  copy_kernel<<<grid, 256, 0, st>>>(dst, src, n); ++g_launches;
+}
+__global__ void export_csc_kernel(const double* __restrict__ Hv, const int32_t* __restrict__ src, int64_t nnz,
+                                  double* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += stride) out[i] = Hv[src[i]];
+}
+void launch_export_csc(cudaStream_t st, const double* Hvals, const int32_t* csc_src, int64_t nnz, double* out) {
+  int grid = (int)((nnz + 255) / 256);
+  if (grid > 148 * 8) grid = 148 * 8;
+  if (grid < 1) grid = 1;
+  export_csc_kernel<<<grid, 256, 0, st>>>(Hvals, csc_src, nnz, out); ++g_launches;
+}
+// out[ref] = in[ref2int[ref]]
+__global__ void permute_vec_kernel(const double* __restrict__ in, const int32_t* __restrict__ ref2int, int N,
+                                   double* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) out[i] = in[ref2int[i]];
+}
+void launch_permute_vec(cudaStream_t st, const double* in, const int32_t* ref2int, int N, double* out) {
+  permute_vec_kernel<<<(N + 255) / 256, 256, 0, st>>>(in, ref2int, N, out); ++g_launches;
+}
+
+}  // namespace sfx

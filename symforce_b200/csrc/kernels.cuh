@@ -1,0 +1,122 @@
+// Device-side declarations shared between kernels.cu and the host driver (sfx_api.cu).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/sfx.h"
+
+namespace sfx {
+
+constexpr int kMaxIterations = 1024;   // stats capacity per sfx_optimize call
+constexpr int kReducePartials = 1 << 16;
+
+// Device-resident LM control block: everything LevenbergMarquardtSolver keeps in host members
+// (levenberg_marquardt_solver.h:228-262) plus the 3-block state indices
+// (internal/levenberg_marquardt_state.h:262-268).  Written only by single-thread kernels.
+struct Ctrl {
+  sfx_params p;
+  double epsilon;
+  double lambda, nu;
+  double err[3];          // cached 0.5*|r|^2 per state block
+  int lin_valid[3];       // linearization initialized flags
+  int init_idx, new_idx, best_idx, free_idx;
+  int best_valid;
+  int iteration;          // LM iteration counter (starts at -1)
+  int have_max_diag, have_last_update;
+  int done;               // 0 running, else optimization_status_t
+  int failure_reason;
+  int best_index;
+  int n_iters;            // entries in iters[]
+  int lin_target;         // state block the next linearize writes
+  int skip_linearize;     // first-iteration linearize of Init only when not valid
+  double red[8];          // reduction results: 0: new |r|^2 sum, 1: upd.(rhs - D.upd), 2: last.upd, 3: |last|^2, 4: |upd|^2
+  int chol_fail;          // non-positive pivot seen
+  int pad;
+  sfx_iteration iters[kMaxIterations + 1];
+};
+
+struct StatePtrs {
+  double* values[3];
+  double* H[3];
+  double* rhs[3];
+  double* res[3];
+};
+
+struct LinBatch {
+  int kind, n;
+  const int32_t* arg_off;
+  const int32_t* res_off;
+  const int32_t* rhs_off;
+  const int32_t* diag_off;
+  const uint32_t* off_off;
+  int key_group[3], key_sub[3];
+  int group_dim[3];
+  int n_groups;
+  int partial_base;  // offset of this batch's per-CTA partial sums
+};
+
+struct SchurDev {
+  int n_landmarks, n_reduced_nodes, reduced_dim;
+  const int32_t *lm_dim, *lm_cdiag_off, *lm_toff, *lm_e_ptr, *lm_e_off, *lm_e_node;
+  const int32_t* node_toff;   // reduced node -> internal tangent offset
+  const int32_t* node_dim;
+  int n_sblocks;
+  const int32_t *s_row, *s_col;  // node ids of each S block
+  const int64_t* s_off;          // S value offsets
+  const int32_t* s_b_src;
+  const int64_t* s_m_ptr;
+  const int32_t *m_eoff_i, *m_eoff_j, *m_lm;
+  const int32_t *r_ptr, *r_eoff, *r_lm;
+  double* cinv;   // [n_landmarks][9]
+  double* tl;     // [n_landmarks][3]
+  double* S;      // S values
+  double* rhs_red;  // reduced rhs (reduced_dim)
+};
+
+struct FrontCopy {
+  int64_t src;
+  int32_t rows, cols, src_ld, dst_row, dst_col, transposed, lower_only, pad;
+};
+
+struct FrontDev {
+  int n_fronts, n;
+  const int32_t *f_w, *f_u, *f_piv, *f_rows_ptr, *f_rows, *f_rel, *f_child_ptr, *f_child, *f_toff, *f_copy_ptr;
+  const int64_t* f_off;
+  const FrontCopy* copies;
+  const int32_t* level_fronts;
+  const int32_t* scalar_perm;
+  double* fronts;   // front_values
+  double* twork;    // solve_ws
+  double* ywork;    // n (elimination order)
+};
+
+// launchers (all asynchronous on `st`)
+void launch_zero_lin(cudaStream_t st, const Ctrl* ctrl, StatePtrs sp, int mode, int64_t n_h, int n_rhs);
+void launch_linearize(cudaStream_t st, const Ctrl* ctrl, StatePtrs sp, int mode, const LinBatch& b, double* partials);
+void launch_finish_error(cudaStream_t st, Ctrl* ctrl, int mode, const double* partials, int n_partials);
+void launch_damping(cudaStream_t st, Ctrl* ctrl, StatePtrs sp, const int32_t* diag_pos, int N, double* dvec,
+                    double* max_diag);
+void launch_schur(cudaStream_t st, const Ctrl* ctrl, StatePtrs sp, const SchurDev& sd, const double* dvec);
+void launch_schur_back(cudaStream_t st, const Ctrl* ctrl, StatePtrs sp, const SchurDev& sd, const double* y,
+                       double* upd);
+void launch_front_factor(cudaStream_t st, Ctrl* ctrl, const FrontDev& fd, const double* sysvals_static,
+                         StatePtrs sp, int use_state_H, const double* dvec, int lvl_begin, int lvl_count,
+                         int smem_m_max);
+void launch_front_solve_fwd(cudaStream_t st, const Ctrl* ctrl, const FrontDev& fd, const double* rhs_static,
+                            StatePtrs sp, int use_state_rhs, int lvl_begin, int lvl_count);
+void launch_front_solve_bwd(cudaStream_t st, const Ctrl* ctrl, const FrontDev& fd, int lvl_begin, int lvl_count);
+void launch_unpermute(cudaStream_t st, const Ctrl* ctrl, const FrontDev& fd, double* out, double scale);
+void launch_retract(cudaStream_t st, const Ctrl* ctrl, StatePtrs sp, const int32_t* key_type, const int32_t* key_voff,
+                    const int32_t* key_sdim, const int32_t* key_tdim, const int32_t* key_itoff, int n_keys,
+                    const double* upd);
+void launch_step_reduce(cudaStream_t st, Ctrl* ctrl, StatePtrs sp, const double* upd, const double* dvec,
+                        const double* last_upd, int N, double* partials);
+void launch_lm_begin(cudaStream_t st, Ctrl* ctrl);
+void launch_lm_after_first_linearize(cudaStream_t st, Ctrl* ctrl);
+void launch_lm_end(cudaStream_t st, Ctrl* ctrl, const double* upd, double* last_upd, int N, int* host_done);
+void launch_copy_values(cudaStream_t st, double* dst, const double* src, int64_t n);
+void launch_export_csc(cudaStream_t st, const double* Hvals, const int32_t* csc_src, int64_t nnz, double* out);
+cudaError_t configure_front_kernels(int smem_m_max, int max_front);
+void launch_permute_vec(cudaStream_t st, const double* in, const int32_t* ref2int, int N, double* out);
+
+}  // namespace sfx

@@ -1,0 +1,659 @@
+// libsfx: problem object, device residency, LM driver and the C ABI of include/sfx.h.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "kernels.cuh"
+#include "sfx_internal.h"
+
+namespace sfx {
+
+extern int64_t g_launches;
+
+#define CUDA_OK(expr)                                                                                   \
+  do {                                                                                                  \
+    cudaError_t e__ = (expr);                                                                           \
+    if (e__ != cudaSuccess)                                                                             \
+      throw Error(SFX_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));                   \
+  } while (0)
+
+struct DevPool {
+  std::vector<void*> ptrs;
+  int64_t bytes = 0;
+  template <typename T>
+  T* alloc(size_t n) {
+    void* p = nullptr;
+    size_t b = std::max<size_t>(n, 1) * sizeof(T);
+    CUDA_OK(cudaMalloc(&p, b));
+    ptrs.push_back(p);
+    bytes += (int64_t)b;
+    return (T*)p;
+  }
+  template <typename T>
+  T* upload(const std::vector<T>& v) {
+    T* p = alloc<T>(v.size());
+    if (!v.empty()) CUDA_OK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return p;
+  }
+  ~DevPool() {
+    for (void* p : ptrs) cudaFree(p);
+  }
+};
+
+enum Phase { PH_LIN = 0, PH_SCHUR, PH_FACTOR, PH_SOLVE, PH_UPDATE, PH_COUNT };
+
+}  // namespace sfx
+
+using namespace sfx;
+
+struct sfx_problem {
+  Analysis a;
+  sfx_params params;
+  double epsilon = 0;
+  int device = 0;
+  int ordering = 0;
+  std::string err;
+  DevPool pool;
+  cudaStream_t st = nullptr;
+  Ctrl* d_ctrl = nullptr;
+  Ctrl* h_ctrl = nullptr;  // pinned
+  int* h_done = nullptr;   // pinned + mapped
+  int* d_done = nullptr;
+  StatePtrs sp{};
+  double* d_cur_values = nullptr;
+  double *d_dvec = nullptr, *d_maxdiag = nullptr, *d_upd = nullptr, *d_last = nullptr, *d_y = nullptr;
+  double* d_partials = nullptr;
+  int n_partials = 0;
+  int32_t* d_diag_pos = nullptr;
+  int32_t *d_key_type = nullptr, *d_key_voff = nullptr, *d_key_sdim = nullptr, *d_key_tdim = nullptr,
+          *d_key_itoff = nullptr;
+  int32_t* d_ref2int = nullptr;
+  std::vector<LinBatch> lin;
+  SchurDev sd{};
+  FrontDev fd{};
+  std::vector<int> lvl_max_m;
+  int smem_cap_m = 168;
+  // csc export
+  int32_t* d_csc_src = nullptr;
+  double* d_export = nullptr;
+  int64_t export_cap = 0;
+  // timing
+  std::vector<cudaEvent_t> ev;
+  std::vector<int> ev_phase;  // phase ending at event i (event 0 = start)
+  sfx_timings tm{};
+  sfx_stats last_stats{};
+  bool values_set = false;
+
+  ~sfx_problem() {
+    for (auto e : ev) cudaEventDestroy(e);
+    if (st) cudaStreamDestroy(st);
+    if (h_ctrl) cudaFreeHost(h_ctrl);
+    if (h_done) cudaFreeHost(h_done);
+  }
+};
+
+static thread_local std::string g_create_err;
+
+namespace {
+
+void upload_structures(sfx_problem* p) {
+  Analysis& a = p->a;
+  DevPool& P = p->pool;
+  // keys
+  std::vector<int32_t> kt, kv, ks, kd, ki;
+  for (auto& k : a.keys) {
+    kt.push_back(k.type);
+    kv.push_back(k.voff);
+    ks.push_back(k.sdim);
+    kd.push_back(k.tdim);
+    ki.push_back(a.nodes[k.node].toff + k.sub);
+  }
+  p->d_key_type = P.upload(kt);
+  p->d_key_voff = P.upload(kv);
+  p->d_key_sdim = P.upload(ks);
+  p->d_key_tdim = P.upload(kd);
+  p->d_key_itoff = P.upload(ki);
+  p->d_ref2int = P.upload(std::vector<int32_t>(a.ref2int.begin(), a.ref2int.end()));
+  p->d_diag_pos = P.upload(a.diag_pos);
+  // batches
+  int partial_base = 0;
+  for (auto& bp : a.batches) {
+    LinBatch lb{};
+    lb.kind = bp.kind;
+    lb.n = bp.n;
+    lb.arg_off = P.upload(bp.arg_off);
+    lb.res_off = P.upload(bp.res_off);
+    lb.rhs_off = P.upload(bp.rhs_off);
+    lb.diag_off = P.upload(bp.diag_off);
+    lb.off_off = P.upload(bp.off_off);
+    for (int i = 0; i < 3; ++i) {
+      lb.key_group[i] = i < bp.n_opt ? bp.key_group[i] : -1;
+      lb.key_sub[i] = i < bp.n_opt ? bp.key_sub[i] : 0;
+      lb.group_dim[i] = i < bp.n_groups ? bp.group_dim[i] : 0;
+    }
+    lb.n_groups = bp.n_groups;
+    lb.partial_base = partial_base;
+    partial_base += (bp.n + 127) / 128;
+    p->lin.push_back(lb);
+  }
+  p->n_partials = partial_base;
+  p->d_partials = P.alloc<double>(std::max(partial_base, 4 * 296));
+  // state
+  for (int b = 0; b < 3; ++b) {
+    p->sp.values[b] = P.alloc<double>(a.n_values);
+    p->sp.H[b] = P.alloc<double>(a.H.n_values);
+    p->sp.rhs[b] = P.alloc<double>(a.N);
+    p->sp.res[b] = P.alloc<double>(a.M);
+  }
+  p->d_cur_values = P.alloc<double>(a.n_values);
+  p->d_dvec = P.alloc<double>(a.N);
+  p->d_maxdiag = P.alloc<double>(a.N);
+  p->d_upd = P.alloc<double>(a.N);
+  p->d_last = P.alloc<double>(a.N);
+  p->d_y = P.alloc<double>(a.N);
+  CUDA_OK(cudaMemset(p->d_last, 0, sizeof(double) * a.N));
+  CUDA_OK(cudaMemset(p->d_maxdiag, 0, sizeof(double) * a.N));
+  p->d_ctrl = P.alloc<Ctrl>(1);
+  CUDA_OK(cudaMallocHost(&p->h_ctrl, sizeof(Ctrl)));
+  CUDA_OK(cudaHostAlloc(&p->h_done, sizeof(int), cudaHostAllocMapped));
+  CUDA_OK(cudaHostGetDevicePointer(&p->d_done, p->h_done, 0));
+  *p->h_done = 0;
+
+  // Schur
+  if (a.schur) {
+    SchurPlan& s = a.sp;
+    SchurDev& d = p->sd;
+    d.n_landmarks = s.n_landmarks;
+    d.n_reduced_nodes = s.first_lm_node;
+    d.reduced_dim = s.reduced_dim;
+    d.lm_dim = P.upload(s.lm_dim);
+    d.lm_cdiag_off = P.upload(s.lm_cdiag_off);
+    d.lm_toff = P.upload(s.lm_toff);
+    d.lm_e_ptr = P.upload(s.lm_e_ptr);
+    d.lm_e_off = P.upload(s.lm_e_off);
+    d.lm_e_node = P.upload(s.lm_e_node);
+    std::vector<int32_t> nto, ndm;
+    for (int i = 0; i < s.first_lm_node; ++i) {
+      nto.push_back(a.nodes[i].toff);
+      ndm.push_back(a.nodes[i].dim);
+    }
+    d.node_toff = P.upload(nto);
+    d.node_dim = P.upload(ndm);
+    d.n_sblocks = (int)s.S.row_idx.size();
+    std::vector<int32_t> srow(s.S.row_idx.begin(), s.S.row_idx.end()), scol(srow.size());
+    for (int j = 0; j < s.S.n_nodes; ++j)
+      for (int q = s.S.col_ptr[j]; q < s.S.col_ptr[j + 1]; ++q) scol[q] = j;
+    d.s_row = P.upload(srow);
+    d.s_col = P.upload(scol);
+    d.s_off = P.upload(s.S.blk_off);
+    d.s_b_src = P.upload(s.s_b_src);
+    d.s_m_ptr = P.upload(s.s_m_ptr);
+    d.m_eoff_i = P.upload(s.m_eoff_i);
+    d.m_eoff_j = P.upload(s.m_eoff_j);
+    d.m_lm = P.upload(s.m_lm);
+    d.r_ptr = P.upload(s.r_ptr);
+    d.r_eoff = P.upload(s.r_eoff);
+    d.r_lm = P.upload(s.r_lm);
+    d.cinv = P.alloc<double>((size_t)s.n_landmarks * 9);
+    d.tl = P.alloc<double>((size_t)s.n_landmarks * 3);
+    d.S = P.alloc<double>(s.S.n_values);
+    d.rhs_red = P.alloc<double>(s.reduced_dim);
+  }
+  // fronts
+  {
+    FrontPlan& f = a.fp;
+    FrontDev& d = p->fd;
+    d.n_fronts = f.n_fronts;
+    d.n = f.n;
+    auto up32 = [&](const std::vector<int>& v) { return P.upload(std::vector<int32_t>(v.begin(), v.end())); };
+    d.f_w = up32(f.f_w);
+    d.f_u = up32(f.f_u);
+    d.f_piv = up32(f.f_piv);
+    d.f_rows_ptr = up32(f.f_rows_ptr);
+    d.f_rows = up32(f.f_rows);
+    d.f_rel = up32(f.f_rel);
+    d.f_child_ptr = up32(f.f_child_ptr);
+    d.f_child = up32(f.f_child);
+    d.f_toff = up32(f.f_toff);
+    d.f_copy_ptr = up32(f.f_copy_ptr);
+    d.f_off = P.upload(f.f_off);
+    std::vector<FrontCopy> cp(f.copies.size());
+    for (size_t i = 0; i < cp.size(); ++i) {
+      const auto& c = f.copies[i];
+      cp[i] = FrontCopy{c.src, c.rows, c.cols, c.src_ld, c.dst_row, c.dst_col, c.transposed, c.lower_only, 0};
+    }
+    d.copies = P.upload(cp);
+    d.level_fronts = up32(f.level_fronts);
+    d.scalar_perm = up32(f.scalar_perm);
+    d.fronts = P.alloc<double>(f.front_values);
+    d.twork = P.alloc<double>(f.solve_ws);
+    d.ywork = P.alloc<double>(f.n);
+    p->lvl_max_m.assign(f.n_levels, 0);
+    for (int s = 0; s < f.n_fronts; ++s)
+      p->lvl_max_m[f.f_level[s]] = std::max(p->lvl_max_m[f.f_level[s]], f.f_w[s] + f.f_u[s]);
+    CUDA_OK(configure_front_kernels(p->smem_cap_m, f.max_front));
+  }
+}
+
+void reset_ctrl(sfx_problem* p) {
+  Ctrl* c = p->h_ctrl;
+  std::memset(c, 0, offsetof(Ctrl, iters));
+  c->p = p->params;
+  c->epsilon = p->epsilon;
+  c->lambda = p->params.initial_lambda;
+  c->nu = p->params.dynamic_lambda_update_beta;
+  c->init_idx = 0;
+  c->new_idx = 1;
+  c->best_idx = 0;
+  c->free_idx = 2;
+  c->iteration = -1;
+  CUDA_OK(cudaMemcpyAsync(p->d_ctrl, c, offsetof(Ctrl, iters), cudaMemcpyHostToDevice, p->st));
+  *p->h_done = 0;
+}
+
+void enqueue_linearize(sfx_problem* p, int mode) {
+  launch_zero_lin(p->st, p->d_ctrl, p->sp, mode, p->a.h_accum_values, p->a.N);
+  for (auto& lb : p->lin) launch_linearize(p->st, p->d_ctrl, p->sp, mode, lb, p->d_partials);
+  launch_finish_error(p->st, p->d_ctrl, mode, p->d_partials, p->n_partials);
+}
+
+// damping + [Schur] + factorize + solve -> d_upd (internal order) = -H_damped^-1 rhs
+void enqueue_solve(sfx_problem* p, const std::function<void(int)>& mark) {
+  Analysis& a = p->a;
+  launch_damping(p->st, p->d_ctrl, p->sp, p->d_diag_pos, a.N, p->d_dvec, p->d_maxdiag);
+  if (a.schur) launch_schur(p->st, p->d_ctrl, p->sp, p->sd, p->d_dvec);
+  mark(PH_SCHUR);
+  const FrontPlan& f = a.fp;
+  for (int l = 0; l < f.n_levels; ++l) {
+    const int cnt = f.level_ptr[l + 1] - f.level_ptr[l];
+    const int sm = std::min(p->lvl_max_m[l], p->smem_cap_m);
+    launch_front_factor(p->st, p->d_ctrl, p->fd, a.schur ? p->sd.S : nullptr, p->sp, a.schur ? 0 : 1,
+                        a.schur ? nullptr : p->d_dvec, f.level_ptr[l], cnt, sm);
+  }
+  mark(PH_FACTOR);
+  for (int l = 0; l < f.n_levels; ++l)
+    launch_front_solve_fwd(p->st, p->d_ctrl, p->fd, a.schur ? p->sd.rhs_red : nullptr, p->sp, a.schur ? 0 : 1,
+                           f.level_ptr[l], f.level_ptr[l + 1] - f.level_ptr[l]);
+  for (int l = f.n_levels - 1; l >= 0; --l)
+    launch_front_solve_bwd(p->st, p->d_ctrl, p->fd, f.level_ptr[l], f.level_ptr[l + 1] - f.level_ptr[l]);
+  if (a.schur) {
+    launch_unpermute(p->st, p->d_ctrl, p->fd, p->d_y, 1.0);
+    launch_schur_back(p->st, p->d_ctrl, p->sp, p->sd, p->d_y, p->d_upd);
+  } else {
+    launch_unpermute(p->st, p->d_ctrl, p->fd, p->d_upd, -1.0);
+  }
+  mark(PH_SOLVE);
+}
+
+void ensure_csc(sfx_problem* p) {
+  if (!p->a.csc_built) {
+    build_csc(p->a);
+    p->d_csc_src = p->pool.upload(p->a.csc_src);
+  }
+  if (p->export_cap < p->a.nnz) {
+    p->d_export = p->pool.alloc<double>(p->a.nnz);
+    p->export_cap = p->a.nnz;
+  }
+}
+
+void export_linearization(sfx_problem* p, int blk, double* residual, double* rhs, double* Hv) {
+  Analysis& a = p->a;
+  if (residual)
+    CUDA_OK(cudaMemcpyAsync(residual, p->sp.res[blk], sizeof(double) * a.M, cudaMemcpyDeviceToHost, p->st));
+  if (rhs) {
+    launch_permute_vec(p->st, p->sp.rhs[blk], p->d_ref2int, a.N, p->d_y);
+    CUDA_OK(cudaMemcpyAsync(rhs, p->d_y, sizeof(double) * a.N, cudaMemcpyDeviceToHost, p->st));
+  }
+  if (Hv) {
+    ensure_csc(p);
+    launch_export_csc(p->st, p->sp.H[blk], p->d_csc_src, a.nnz, p->d_export);
+    CUDA_OK(cudaMemcpyAsync(Hv, p->d_export, sizeof(double) * a.nnz, cudaMemcpyDeviceToHost, p->st));
+  }
+  CUDA_OK(cudaStreamSynchronize(p->st));
+}
+
+}  // namespace
+
+#define SFX_API_BEGIN try {
+#define SFX_API_END(p)                                  \
+  return SFX_OK;                                        \
+  }                                                     \
+  catch (const sfx::Error& e) {                         \
+    if (p) (p)->err = e.what();                         \
+    g_create_err = e.what();                            \
+    return e.code;                                      \
+  }                                                     \
+  catch (const std::exception& e) {                     \
+    if (p) (p)->err = e.what();                         \
+    g_create_err = e.what();                            \
+    return SFX_ERR_INVALID_ARG;                         \
+  }
+
+extern "C" {
+
+sfx_status sfx_default_params(sfx_params* out) {
+  if (!out) return SFX_ERR_INVALID_ARG;
+  sfx_params p{};
+  p.initial_lambda = 1.0;
+  p.lambda_lower_bound = 0.0;
+  p.lambda_upper_bound = 1000000.0;
+  p.lambda_update_type = 1;
+  p.lambda_up_factor = 4.0;
+  p.lambda_down_factor = 1 / 4.0;
+  p.dynamic_lambda_update_beta = 2.0;
+  p.dynamic_lambda_update_gamma = 3.0;
+  p.dynamic_lambda_update_p = 3;
+  p.use_diagonal_damping = 0;
+  p.use_unit_damping = 1;
+  p.keep_max_diagonal_damping = 0;
+  p.diagonal_damping_min = 1e-6;
+  p.iterations = 50;
+  p.early_exit_min_reduction = 1e-6;
+  p.early_exit_min_absolute_error = 0.0;
+  p.enable_bold_updates = 0;
+  *out = p;
+  return SFX_OK;
+}
+
+const char* sfx_last_error(const sfx_problem* p) { return p ? p->err.c_str() : g_create_err.c_str(); }
+
+sfx_status sfx_problem_create(const sfx_problem_desc* desc, sfx_problem** out) {
+  sfx_problem* p = nullptr;
+  SFX_API_BEGIN
+  SFX_CHECK(desc && out, SFX_ERR_INVALID_ARG, "null argument");
+  *out = nullptr;
+  int ndev = 0;
+  cudaError_t ce = cudaGetDeviceCount(&ndev);
+  if (ce != cudaSuccess || ndev == 0)
+    throw Error(SFX_ERR_CUDA, "no CUDA device: libsfx has no CPU fallback");
+  SFX_CHECK(desc->device >= 0 && desc->device < ndev, SFX_ERR_INVALID_ARG, "device ordinal out of range");
+  CUDA_OK(cudaSetDevice(desc->device));
+  std::unique_ptr<sfx_problem> up(new sfx_problem());
+  p = up.get();
+  p->device = desc->device;
+  p->params = desc->params;
+  p->epsilon = desc->epsilon;
+  p->ordering = desc->ordering;
+  analyze_problem(*desc, p->a);
+  {
+    Analysis& a = p->a;
+    const BlockMatrix& sys = a.schur ? a.sp.S : a.H;
+    std::vector<int> sys2ref;
+    if (desc->ordering == SFX_ORDERING_METIS_SCALAR) {
+      std::vector<int> int2ref(a.N);
+      for (int r = 0; r < a.N; ++r) int2ref[a.ref2int[r]] = r;
+      sys2ref.assign(int2ref.begin(), int2ref.begin() + sys.node_off[sys.n_nodes]);
+    }
+    build_front_plan(sys, desc->ordering, sys2ref, a.fp);
+  }
+  CUDA_OK(cudaStreamCreateWithFlags(&p->st, cudaStreamNonBlocking));
+  upload_structures(p);
+  CUDA_OK(cudaStreamSynchronize(p->st));
+  *out = up.release();
+  p = nullptr;
+  SFX_API_END(p)
+}
+
+void sfx_problem_destroy(sfx_problem* p) {
+  if (!p) return;
+  cudaSetDevice(p->device);
+  delete p;
+}
+
+sfx_status sfx_update_params(sfx_problem* p, const sfx_params* params) {
+  SFX_API_BEGIN
+  SFX_CHECK(p && params, SFX_ERR_INVALID_ARG, "null argument");
+  p->params = *params;
+  SFX_API_END(p)
+}
+
+sfx_status sfx_set_values(sfx_problem* p, const double* values, int64_t n) {
+  SFX_API_BEGIN
+  SFX_CHECK(p && values, SFX_ERR_INVALID_ARG, "null argument");
+  SFX_CHECK(n == p->a.n_values, SFX_ERR_INVALID_ARG, "values length mismatch");
+  CUDA_OK(cudaSetDevice(p->device));
+  CUDA_OK(cudaMemcpyAsync(p->d_cur_values, values, sizeof(double) * n, cudaMemcpyHostToDevice, p->st));
+  CUDA_OK(cudaStreamSynchronize(p->st));
+  p->values_set = true;
+  SFX_API_END(p)
+}
+
+sfx_status sfx_optimize(sfx_problem* p, int32_t num_iterations, sfx_stats* stats) {
+  SFX_API_BEGIN
+  SFX_CHECK(p, SFX_ERR_INVALID_ARG, "null problem");
+  SFX_CHECK(p->values_set, SFX_ERR_INVALID_ARG, "sfx_set_values must be called first");
+  if (num_iterations < 0) num_iterations = p->params.iterations;
+  SFX_CHECK(num_iterations > 0, SFX_ERR_INVALID_ARG, "num_iterations must be positive");
+  SFX_CHECK(num_iterations <= kMaxIterations, SFX_ERR_INVALID_ARG, "num_iterations exceeds stats capacity");
+  CUDA_OK(cudaSetDevice(p->device));
+  Analysis& a = p->a;
+  const int64_t launches0 = g_launches;
+  // Reset(values): all three state blocks hold the full values buffer; optimized keys are
+  // overwritten by retract (levenberg_marquardt_solver.h:163-182, state ResetValues)
+  reset_ctrl(p);
+  for (int b = 0; b < 3; ++b) launch_copy_values(p->st, p->sp.values[b], p->d_cur_values, a.n_values);
+  // events
+  const size_t need = (size_t)num_iterations * (PH_COUNT + 1) + 8;
+  while (p->ev.size() < need) {
+    cudaEvent_t e;
+    CUDA_OK(cudaEventCreate(&e));
+    p->ev.push_back(e);
+  }
+  p->ev_phase.clear();
+  size_t evi = 0;
+  auto mark = [&](int phase) {
+    CUDA_OK(cudaEventRecord(p->ev[evi++], p->st));
+    p->ev_phase.push_back(phase);
+  };
+  std::vector<size_t> iter_end_ev;
+  mark(-1);
+  int enq = 0;
+  for (int i = 0; i < num_iterations; ++i) {
+    if (i >= 2) {  // bound the run-ahead; the device always has >= 1 iteration queued
+      CUDA_OK(cudaEventSynchronize(p->ev[iter_end_ev[i - 2]]));
+      if (*(volatile int*)p->h_done) break;
+    }
+    launch_lm_begin(p->st, p->d_ctrl);
+    if (i == 0) {
+      enqueue_linearize(p, /*mode=*/0);
+      launch_lm_after_first_linearize(p->st, p->d_ctrl);
+      mark(PH_LIN);
+    }
+    enqueue_solve(p, mark);
+    launch_retract(p->st, p->d_ctrl, p->sp, p->d_key_type, p->d_key_voff, p->d_key_sdim, p->d_key_tdim,
+                   p->d_key_itoff, a.n_keys, p->d_upd);
+    mark(PH_UPDATE);
+    enqueue_linearize(p, /*mode=*/1);
+    mark(PH_LIN);
+    launch_step_reduce(p->st, p->d_ctrl, p->sp, p->d_upd, p->d_dvec, p->d_last, a.N, p->d_partials);
+    launch_lm_end(p->st, p->d_ctrl, p->d_upd, p->d_last, a.N, p->d_done);
+    mark(PH_UPDATE);
+    iter_end_ev.push_back(evi - 1);
+    enq++;
+  }
+  CUDA_OK(cudaMemcpyAsync(p->h_ctrl, p->d_ctrl, sizeof(Ctrl), cudaMemcpyDeviceToHost, p->st));
+  CUDA_OK(cudaStreamSynchronize(p->st));
+  {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) throw Error(SFX_ERR_CUDA, std::string("kernel failure: ") + cudaGetErrorString(e));
+  }
+  const Ctrl& c = *p->h_ctrl;
+  sfx_stats s{};
+  s.status = c.done ? c.done : 2;  // HIT_ITERATION_LIMIT
+  s.failure_reason = c.done == 3 ? c.failure_reason : 0;
+  s.best_index = c.best_index;
+  s.n_iterations = c.n_iters;
+  p->last_stats = s;
+  if (stats) *stats = s;
+  // timings
+  sfx_timings tm{};
+  double acc[PH_COUNT] = {0, 0, 0, 0, 0};
+  for (size_t i = 1; i < evi; ++i) {
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, p->ev[i - 1], p->ev[i]) == cudaSuccess && p->ev_phase[i] >= 0)
+      acc[p->ev_phase[i]] += ms;
+  }
+  float tot = 0;
+  cudaEventElapsedTime(&tot, p->ev[0], p->ev[evi - 1]);
+  tm.total_ms = tot;
+  tm.linearize_ms = acc[PH_LIN];
+  tm.schur_ms = acc[PH_SCHUR];
+  tm.factorize_ms = acc[PH_FACTOR];
+  tm.solve_ms = acc[PH_SOLVE];
+  tm.update_ms = acc[PH_UPDATE];
+  tm.iterations_run = c.n_iters > 0 ? c.n_iters - 1 : 0;
+  tm.n_linearize = tm.iterations_run + 1;
+  tm.n_factorize = tm.iterations_run;
+  tm.kernel_launches = (int32_t)(g_launches - launches0);
+  p->tm = tm;
+  SFX_API_END(p)
+}
+
+sfx_status sfx_get_best_values(sfx_problem* p, double* values, int64_t n) {
+  SFX_API_BEGIN
+  SFX_CHECK(p && values, SFX_ERR_INVALID_ARG, "null argument");
+  SFX_CHECK(n == p->a.n_values, SFX_ERR_INVALID_ARG, "values length mismatch");
+  SFX_CHECK(p->h_ctrl->best_valid, SFX_ERR_INVALID_ARG, "SYM_ASSERT: state_.BestIsValid()");
+  CUDA_OK(cudaSetDevice(p->device));
+  CUDA_OK(cudaMemcpyAsync(values, p->sp.values[p->h_ctrl->best_idx], sizeof(double) * n, cudaMemcpyDeviceToHost,
+                          p->st));
+  CUDA_OK(cudaStreamSynchronize(p->st));
+  SFX_API_END(p)
+}
+
+sfx_status sfx_get_iterations(sfx_problem* p, sfx_iteration* buf, int32_t capacity, int32_t* n) {
+  SFX_API_BEGIN
+  SFX_CHECK(p && n, SFX_ERR_INVALID_ARG, "null argument");
+  *n = p->h_ctrl->n_iters;
+  for (int i = 0; i < std::min(capacity, *n); ++i) buf[i] = p->h_ctrl->iters[i];
+  SFX_API_END(p)
+}
+
+sfx_status sfx_get_dims(sfx_problem* p, int32_t* N, int32_t* M, int64_t* nnz) {
+  SFX_API_BEGIN
+  SFX_CHECK(p, SFX_ERR_INVALID_ARG, "null problem");
+  if (N) *N = p->a.N;
+  if (M) *M = p->a.M;
+  if (nnz) {
+    build_csc(p->a);
+    *nnz = p->a.nnz;
+  }
+  SFX_API_END(p)
+}
+
+sfx_status sfx_get_hessian_pattern(sfx_problem* p, int32_t* outer, int32_t* inner) {
+  SFX_API_BEGIN
+  SFX_CHECK(p && outer && inner, SFX_ERR_INVALID_ARG, "null argument");
+  build_csc(p->a);
+  std::copy(p->a.csc_outer.begin(), p->a.csc_outer.end(), outer);
+  std::copy(p->a.csc_inner.begin(), p->a.csc_inner.end(), inner);
+  SFX_API_END(p)
+}
+
+sfx_status sfx_linearize(sfx_problem* p, double* residual, double* rhs, double* hessian_values) {
+  SFX_API_BEGIN
+  SFX_CHECK(p, SFX_ERR_INVALID_ARG, "null problem");
+  SFX_CHECK(p->values_set, SFX_ERR_INVALID_ARG, "sfx_set_values must be called first");
+  CUDA_OK(cudaSetDevice(p->device));
+  reset_ctrl(p);
+  launch_copy_values(p->st, p->sp.values[0], p->d_cur_values, p->a.n_values);
+  enqueue_linearize(p, 0);
+  export_linearization(p, 0, residual, rhs, hessian_values);
+  SFX_API_END(p)
+}
+
+sfx_status sfx_get_best_linearization(sfx_problem* p, double* residual, double* rhs, double* hessian_values) {
+  SFX_API_BEGIN
+  SFX_CHECK(p, SFX_ERR_INVALID_ARG, "null problem");
+  const Ctrl& c = *p->h_ctrl;
+  SFX_CHECK(c.best_valid && c.lin_valid[c.best_idx], SFX_ERR_INVALID_ARG,
+            "SYM_ASSERT: state_.BestIsValid() && Best().GetLinearization().IsInitialized()");
+  CUDA_OK(cudaSetDevice(p->device));
+  export_linearization(p, c.best_idx, residual, rhs, hessian_values);
+  SFX_API_END(p)
+}
+
+sfx_status sfx_solve_step(sfx_problem* p, double lambda, double* update) {
+  SFX_API_BEGIN
+  SFX_CHECK(p && update, SFX_ERR_INVALID_ARG, "null argument");
+  SFX_CHECK(p->values_set, SFX_ERR_INVALID_ARG, "sfx_set_values must be called first");
+  CUDA_OK(cudaSetDevice(p->device));
+  reset_ctrl(p);
+  p->h_ctrl->lambda = lambda;
+  CUDA_OK(cudaMemcpyAsync(p->d_ctrl, p->h_ctrl, offsetof(Ctrl, iters), cudaMemcpyHostToDevice, p->st));
+  launch_copy_values(p->st, p->sp.values[0], p->d_cur_values, p->a.n_values);
+  enqueue_linearize(p, 0);
+  enqueue_solve(p, [](int) {});
+  launch_permute_vec(p->st, p->d_upd, p->d_ref2int, p->a.N, p->d_y);
+  CUDA_OK(cudaMemcpyAsync(update, p->d_y, sizeof(double) * p->a.N, cudaMemcpyDeviceToHost, p->st));
+  CUDA_OK(cudaStreamSynchronize(p->st));
+  SFX_API_END(p)
+}
+
+sfx_status sfx_get_ordering(sfx_problem* p, int32_t* perm, int32_t capacity, int32_t* n) {
+  SFX_API_BEGIN
+  SFX_CHECK(p && n, SFX_ERR_INVALID_ARG, "null argument");
+  // elimination scalar position -> reference scalar index of the factored system
+  const Analysis& a = p->a;
+  std::vector<int> int2ref(a.N);
+  for (int r = 0; r < a.N; ++r) int2ref[a.ref2int[r]] = r;
+  *n = a.fp.n;
+  for (int i = 0; i < std::min(capacity, *n); ++i) perm[i] = int2ref[a.fp.scalar_perm[i]];
+  SFX_API_END(p)
+}
+
+sfx_status sfx_get_timings(sfx_problem* p, sfx_timings* out) {
+  SFX_API_BEGIN
+  SFX_CHECK(p && out, SFX_ERR_INVALID_ARG, "null argument");
+  *out = p->tm;
+  SFX_API_END(p)
+}
+
+sfx_status sfx_get_info(sfx_problem* p, int64_t* out, int32_t capacity) {
+  SFX_API_BEGIN
+  SFX_CHECK(p && out, SFX_ERR_INVALID_ARG, "null argument");
+  const Analysis& a = p->a;
+  int64_t v[SFX_INFO_COUNT] = {0};
+  v[SFX_INFO_N] = a.N;
+  v[SFX_INFO_M] = a.M;
+  v[SFX_INFO_NNZ_H] = a.csc_built ? a.nnz : -1;
+  v[SFX_INFO_NUM_NODES] = (int64_t)a.nodes.size();
+  v[SFX_INFO_REDUCED_DIM] = a.fp.n;
+  v[SFX_INFO_NNZ_L] = a.fp.nnz_L;
+  v[SFX_INFO_NUM_SUPERNODES] = a.fp.n_fronts;
+  v[SFX_INFO_NUM_LEVELS] = a.fp.n_levels;
+  v[SFX_INFO_FACTOR_FLOPS] = (int64_t)a.fp.flops;
+  v[SFX_INFO_S_BLOCKS] = a.schur ? (int64_t)a.sp.S.row_idx.size() : 0;
+  v[SFX_INFO_SCHUR_PAIRS] = a.schur ? (int64_t)a.sp.m_lm.size() : 0;
+  v[SFX_INFO_MAX_FRONT] = a.fp.max_front;
+  v[SFX_INFO_DEVICE_BYTES] = p->pool.bytes;
+  for (int i = 0; i < std::min<int>(capacity, SFX_INFO_COUNT); ++i) out[i] = v[i];
+  SFX_API_END(p)
+}
+
+sfx_status sfx_comm_unique_id(char id_out[128]) {
+  (void)id_out;
+  g_create_err = "multi-GPU communicator not built yet";
+  return SFX_ERR_UNSUPPORTED;
+}
+sfx_status sfx_comm_create(const char id[128], int32_t rank, int32_t world, int32_t device, sfx_comm** out) {
+  (void)id;
+  (void)rank;
+  (void)world;
+  (void)device;
+  (void)out;
+  g_create_err = "multi-GPU communicator not built yet";
+  return SFX_ERR_UNSUPPORTED;
+}
+void sfx_comm_destroy(sfx_comm* c) { (void)c; }
+
+}  // extern "C"

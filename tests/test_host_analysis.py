@@ -1,0 +1,97 @@
+"""
+CPU tests of the product's host logic (no GPU): the C-ABI library loads and exports every symbol of
+include/sfx.h, and the structural analysis (index maps, CSC layout, Schur match lists, multifrontal
+plan) replayed in numpy reproduces the oracle's H / rhs / residual / LM step.
+"""
+import ctypes as C
+import re
+import os
+
+import numpy as np
+import pytest
+
+from symforce_b200 import capi, desc as D, problems as P
+from tests import host_emulation as E
+from tests import oracle_capi as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = capi.load()
+    header = open(os.path.join(ROOT, "include", "sfx.h")).read()
+    declared = set(re.findall(r"\b(sfx_[a-z_0-9]+)\s*\(", header))
+    declared -= {"sfx_status"}
+    assert declared == set(capi.EXPORTS), declared ^ set(capi.EXPORTS)
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_create_without_gpu_fails_loudly():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError, match="no CUDA device|CUDA"):
+        capi.SfxProblem(P.pose_smoothing())
+
+
+PROBLEMS = {
+    "pose_smoothing": lambda: P.pose_smoothing(),
+    "rotation_smoothing": lambda: P.rotation_smoothing(),
+    "frozen_keys": lambda: P.frozen_keys(),
+    "robot3d": lambda: P.robot_3d_localization(),
+    "bal_tiny_schur": lambda: P.bal_problem("tiny", solver=D.SOLVER_SCHUR),
+    "bal_tiny_chol": lambda: P.bal_problem("tiny", solver=D.SOLVER_CHOLESKY),
+    "bal_tiny_natural": lambda: _with_ordering(P.bal_problem("tiny", solver=D.SOLVER_SCHUR), D.ORDERING_NATURAL),
+    "bal_tiny_block": lambda: _with_ordering(P.bal_problem("tiny", solver=D.SOLVER_CHOLESKY), D.ORDERING_METIS_BLOCK),
+    "pose_graph_small": lambda: P.pose_graph_problem(n_poses=60, n_loops=15),
+}
+
+
+def _with_ordering(p, o):
+    p.ordering = o
+    return p
+
+
+@pytest.mark.parametrize("name", list(PROBLEMS))
+def test_host_maps_reproduce_oracle(name):
+    prob = PROBLEMS[name]()
+    A = capi.analysis_json(prob)
+    o = O.OracleProblem(prob)
+    N, M, nnz = o.dims()
+    assert (A["N"], A["M"]) == (N, M)
+    outer, inner = o.hessian_pattern()
+    assert np.array_equal(outer, np.array(A["csc_outer"]))
+    assert np.array_equal(inner, np.array(A["csc_inner"]))
+    lam = 0.37
+    upd, (res, rhs, H) = E.emulate_solve_step(prob, A, lam)
+    res_o, rhs_o, H_o = o.linearize()
+    scale = max(1.0, np.abs(H_o).max())
+    assert np.allclose(res, res_o, rtol=0, atol=1e-12 * max(1.0, np.abs(res_o).max()))
+    assert np.allclose(rhs, rhs_o, rtol=0, atol=1e-11 * max(1.0, np.abs(rhs_o).max()))
+    assert np.allclose(H, H_o, rtol=0, atol=1e-12 * scale)
+    upd_o = o.solve_step(lam)
+    assert np.allclose(upd, upd_o, rtol=1e-8, atol=1e-9 * max(1e-3, np.abs(upd_o).max()))
+
+
+def test_bal_nodes_merge_pose_and_intrinsics():
+    prob = P.bal_problem("tiny", solver=D.SOLVER_SCHUR)
+    A = capi.analysis_json(prob)
+    n_cams = prob.meta["n_cams"]
+    kn = A["key_node"]
+    for j in range(n_cams):
+        assert kn[j] == kn[n_cams + j]  # c_j and i_j share a node
+    assert A["H"]["node_dim"][: n_cams] == [9] * n_cams
+    assert A["schur_plan"]["n_landmarks"] == prob.meta["n_pts"]
+
+
+def test_unoptimized_key_is_an_error():
+    prob = P.pose_smoothing()
+    # add an optimized key no factor touches
+    vals = np.concatenate([prob.values, [0, 0, 0, 1, 0, 0, 0]])
+    keys = np.concatenate([prob.keys, [[D.TYPE_POSE3, len(prob.values), 7, 6]]])
+    bad = D.Problem(vals, keys, prob.batches)
+    with pytest.raises(RuntimeError, match="not optimized by any factor"):
+        capi.analysis_json(bad)
+    with pytest.raises(RuntimeError, match="not optimized by any factor"):
+        O.OracleProblem(bad)

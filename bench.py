@@ -1,0 +1,282 @@
+#!/usr/bin/env python
+"""
+bench.py -- LM iterations/sec (linearize + Schur + Cholesky) on synthetic BAL, the metric of
+BASELINE.json, measured on the CUDA path through the C ABI (symforce_b200/lib/libsfx.so).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload final|ladybug|...] [--impl reference]
+
+One "step" = one Levenberg-Marquardt iteration (damp -> Schur -> factorize -> solve -> retract ->
+relinearize -> accept/reject) of sym::Optimizer on the workload.
+  value : K iterations inside ONE sfx_optimize call, inputs already resident in HBM, timed on the
+          device with CUDA events on the library's stream.
+  e2e   : K calls of the reference-facing API the way the reference's own benchmark drives it
+          (`Optimize(values, 1, ...)`, symforce/benchmarks/robot_3d_localization/
+          robot_3d_localization_benchmark.cc:88-93): per step a host->device copy of the Values
+          buffer from pinned host memory, one LM iteration, and the device->host read of the result.
+  --impl reference : the reference's own CPU algorithm (oracle/, a restatement pinned to the
+          reference's KATs -- the reference C++ cannot be built here), single
+          thread like the reference, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "LM iterations/sec (linearize+Schur+Cholesky) on synthetic BAL"
+UNIT = "iterations/s"
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="sfx", choices=["sfx", "reference"])
+    ap.add_argument("--workload", default="final")
+    ap.add_argument("--cpu-baseline", type=int, default=1, help="0: skip the cpu_baseline leg")
+    ap.add_argument("--cpu-workload", default=None)
+    return ap.parse_args()
+
+
+def workload_config(name):
+    from symforce_b200 import problems as P
+
+    s = P.BAL_SHAPES[name]
+    return {
+        "workload": f"synthetic BAL {name}-shape: {s['n_cams']} cams / {s['n_pts']} pts / {s['n_obs']} obs, "
+                    f"Snavely reprojection + Schur + multifrontal Cholesky, DYNAMIC lambda",
+        "n_cams": s["n_cams"], "n_pts": s["n_pts"], "n_obs": s["n_obs"],
+        "l2": "inputs larger than L2 (block Hessian > 126 MB)" if s["n_obs"] * 27 * 8 > 126e6
+              else "working set fits L2; L2 flushed between timed calls",
+    }
+
+
+def never_exit_params():
+    """Reference BAL params (DYNAMIC lambda) with early exit disabled so exactly K iterations run."""
+    from symforce_b200 import desc as D
+
+    p = D.default_params()
+    p.lambda_update_type = D.LAMBDA_DYNAMIC
+    p.early_exit_min_reduction = 0.0
+    p.early_exit_min_absolute_error = -1.0
+    p.lambda_upper_bound = 1e300
+    p.iterations = 1000
+    return p
+
+
+class ClockSampler:
+    def __init__(self, device=0):
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = False
+        self.device = device
+        self.proc = None
+
+    def start(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.th = threading.Thread(target=self._run, daemon=True)
+        self.th.start()
+
+    def _run(self):
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.proc.stdout:
+            parts = [x.strip() for x in line.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                self.samples.append(float(parts[0]))
+                self.max_mhz = float(parts[1])
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    self.reasons.add(n)
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def cpu_baseline(workload, max_seconds=40.0):
+    """The oracle (CPU restatement of the reference algorithm, 1 thread like the reference) on a
+    bounded sample of the workload: setup excluded, LM iterations timed."""
+    from symforce_b200 import desc as D, problems as P
+    from tests import oracle_capi as O
+
+    prob = P.bal_problem(workload, solver=D.SOLVER_SCHUR, params=never_exit_params())
+    t0 = time.time()
+    o = O.OracleProblem(prob)
+    o.optimize(1)  # warm-up iteration: index maps, METIS, symbolic factorization (excluded)
+    setup_s = time.time() - t0
+    o.reset_timings()
+    iters = 0
+    t0 = time.time()
+    while True:
+        o.optimize(1)
+        iters += 1
+        el = time.time() - t0
+        if el > max_seconds / 2 or iters >= 20:
+            break
+    el = time.time() - t0
+    tm = o.timings()
+    return {
+        "value": iters / el, "unit": UNIT, "cores": 1, "kind": "port",
+        "sample": f"{iters} x Optimize(values, 1) LM iterations of the {workload}-shape problem (Schur + simplicial "
+                  f"LDLT on S), setup {setup_s:.1f}s excluded; per iteration linearize "
+                  f"{tm['linearize_s'] / max(tm['n_linearize'], 1) * 1e3:.1f} ms, factorize "
+                  f"{tm['factorize_s'] / max(tm['n_factorize'], 1) * 1e3:.1f} ms",
+        "host_cores_available": os.cpu_count(),
+    }
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = args.cpu_workload or args.workload
+    cb = cpu_baseline(wl, max_seconds=60.0)
+    cfg = workload_config(wl)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / cb["value"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+        "cpu_baseline": cb,
+        "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import torch
+    import torch.distributed as dist
+
+    from symforce_b200 import capi, desc as D, problems as P
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+
+    K, W = args.steps, max(args.warmup, 3)
+    shape = P.BAL_SHAPES[args.workload]
+    # multi-GPU: replicas of the full problem per rank until landmark sharding lands
+    prob = P.bal_problem(args.workload, solver=D.SOLVER_SCHUR, params=never_exit_params())
+    t0 = time.time()
+    gpu = capi.SfxProblem(prob, device=local_rank)
+    setup_s = time.time() - t0
+    info = gpu.info()
+
+    pinned = torch.empty(prob.values.shape[0], dtype=torch.float64).pin_memory()
+    pinned.numpy()[:] = prob.values
+    out_pinned = torch.empty(prob.values.shape[0], dtype=torch.float64).pin_memory()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # warm-up
+    gpu.set_values(pinned.numpy())
+    gpu.optimize(W)
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    # ---- device-resident: K iterations in one call ---------------------------------------------
+    gpu.set_values(pinned.numpy())
+    barrier()
+    st = gpu.optimize(K)
+    barrier()
+    tm = gpu.timings()
+    iters_run = tm["iterations_run"]
+    assert iters_run == K, f"expected {K} iterations, ran {iters_run} (status {st.status})"
+    dev_ms = tm["total_ms"]
+    # ---- e2e: host buffers, one iteration per call -----------------------------------------------
+    lib = gpu.lib
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(K):
+        gpu.set_values(pinned.numpy())
+        gpu.optimize(1)
+        vals = gpu.best_values()
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    clocks = sampler.stop()
+
+    t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_s = float(t[0]), float(t[1])
+    value = world * K / (dev_ms * 1e-3)
+    e2e = world * K / e2e_s
+
+    if rank == 0:
+        n_obs, n_cams, n_pts = shape["n_obs"], shape["n_cams"], shape["n_pts"]
+        lin_bytes = 256 * n_obs + 512 * n_cams + 96 * n_pts
+        lin_ms = tm["linearize_ms"] / max(tm["n_linearize"], 1)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = peaks.get("hbm_gbs", 6650.0)
+        achieved = lin_bytes / (lin_ms * 1e-3) / 1e9
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
+            "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": dict(workload_config(args.workload), parallelism=f"replicas x{world}" if world > 1 else "1 GPU",
+                           reduced_dim=info["reduced_dim"], nnz_L=info["nnz_L"], supernodes=info["num_supernodes"],
+                           levels=info["num_levels"], max_front=info["max_front"], setup_s=round(setup_s, 2)),
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(prob.values.nbytes),
+                    "d2h_bytes_per_step": int(prob.values.nbytes)},
+            "gpu_launches": int(tm["kernel_launches"]),
+            "clocks": clocks,
+            "phases_ms_per_iteration": {
+                "linearize": tm["linearize_ms"] / max(tm["n_linearize"], 1),
+                "schur": tm["schur_ms"] / K, "factorize": tm["factorize_ms"] / K, "solve": tm["solve_ms"] / K,
+                "update": tm["update_ms"] / K},
+            "roofline": {"kernel": "linearize_kernel<snavely> (+zero, error reduce)", "bound": "hbm",
+                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": None,
+                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"},
+        }
+        if args.cpu_baseline:
+            try:
+                line["cpu_baseline"] = cpu_baseline(args.cpu_workload or args.workload)
+            except Exception as e:  # the checker must not break the bench line
+                line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "port",
+                                        "sample": f"failed: {e}"}
+        print(json.dumps(line))
+    gpu.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

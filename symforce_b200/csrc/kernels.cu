@@ -757,27 +757,31 @@ __global__ void __launch_bounds__(kFrontThreads) front_solve_bwd_kernel(const Ct
 }
 
 void launch_front_solve_fwd(cudaStream_t st, const Ctrl* ctrl, const FrontDev& fd, const double* rhs_static,
-                            StatePtrs sp, int use_state_rhs, int lvl_begin, int lvl_count) {
-  // dynamic smem sized by the largest front; set by the driver through cudaFuncSetAttribute
-  extern int g_solve_smem;
-  front_solve_fwd_kernel<<<lvl_count, kFrontThreads, g_solve_smem, st>>>(ctrl, fd, rhs_static, sp, use_state_rhs,
+                            StatePtrs sp, int use_state_rhs, int lvl_begin, int lvl_count, int smem_bytes) {
+  front_solve_fwd_kernel<<<lvl_count, kFrontThreads, smem_bytes, st>>>(ctrl, fd, rhs_static, sp, use_state_rhs,
                                                                         lvl_begin); ++g_launches;
 }
-void launch_front_solve_bwd(cudaStream_t st, const Ctrl* ctrl, const FrontDev& fd, int lvl_begin, int lvl_count) {
-  extern int g_solve_smem;
-  front_solve_bwd_kernel<<<lvl_count, kFrontThreads, g_solve_smem, st>>>(ctrl, fd, lvl_begin); ++g_launches;
+void launch_front_solve_bwd(cudaStream_t st, const Ctrl* ctrl, const FrontDev& fd, int lvl_begin, int lvl_count,
+                            int smem_bytes) {
+  front_solve_bwd_kernel<<<lvl_count, kFrontThreads, smem_bytes, st>>>(ctrl, fd, lvl_begin); ++g_launches;
 }
-int g_solve_smem = 0;
-
+// opt in to large dynamic shared memory (process-wide maxima; launches pass their own size)
 cudaError_t configure_front_kernels(int smem_m_max, int max_front) {
-  cudaError_t e = cudaFuncSetAttribute(front_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       smem_m_max * smem_m_max * (int)sizeof(double));
-  if (e != cudaSuccess) return e;
-  g_solve_smem = max_front * (int)sizeof(double);
-  if (g_solve_smem > 48 * 1024) {
-    e = cudaFuncSetAttribute(front_solve_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_solve_smem);
+  static int cur_factor = 0, cur_solve = 48 * 1024;
+  cudaError_t e = cudaSuccess;
+  const int need_f = smem_m_max * smem_m_max * (int)sizeof(double);
+  if (need_f > cur_factor) {
+    e = cudaFuncSetAttribute(front_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, need_f);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(front_solve_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, g_solve_smem);
+    cur_factor = need_f;
+  }
+  const int need_s = max_front * (int)sizeof(double);
+  if (need_s > cur_solve) {
+    e = cudaFuncSetAttribute(front_solve_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, need_s);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(front_solve_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, need_s);
+    if (e != cudaSuccess) return e;
+    cur_solve = need_s;
   }
   return e;
 }

@@ -103,8 +103,9 @@ void launch_front_factor(cudaStream_t st, Ctrl* ctrl, const FrontDev& fd, const 
                          StatePtrs sp, int use_state_H, const double* dvec, int lvl_begin, int lvl_count,
                          int smem_m_max);
 void launch_front_solve_fwd(cudaStream_t st, const Ctrl* ctrl, const FrontDev& fd, const double* rhs_static,
-                            StatePtrs sp, int use_state_rhs, int lvl_begin, int lvl_count);
-void launch_front_solve_bwd(cudaStream_t st, const Ctrl* ctrl, const FrontDev& fd, int lvl_begin, int lvl_count);
+                            StatePtrs sp, int use_state_rhs, int lvl_begin, int lvl_count, int smem_bytes);
+void launch_front_solve_bwd(cudaStream_t st, const Ctrl* ctrl, const FrontDev& fd, int lvl_begin, int lvl_count,
+                            int smem_bytes);
 void launch_unpermute(cudaStream_t st, const Ctrl* ctrl, const FrontDev& fd, double* out, double scale);
 void launch_retract(cudaStream_t st, const Ctrl* ctrl, StatePtrs sp, const int32_t* key_type, const int32_t* key_voff,
                     const int32_t* key_sdim, const int32_t* key_tdim, const int32_t* key_itoff, int n_keys,

@@ -282,9 +282,10 @@ void enqueue_solve(sfx_problem* p, const std::function<void(int)>& mark) {
   mark(PH_FACTOR);
   for (int l = 0; l < f.n_levels; ++l)
     launch_front_solve_fwd(p->st, p->d_ctrl, p->fd, a.schur ? p->sd.rhs_red : nullptr, p->sp, a.schur ? 0 : 1,
-                           f.level_ptr[l], f.level_ptr[l + 1] - f.level_ptr[l]);
+                           f.level_ptr[l], f.level_ptr[l + 1] - f.level_ptr[l], p->lvl_max_m[l] * 8);
   for (int l = f.n_levels - 1; l >= 0; --l)
-    launch_front_solve_bwd(p->st, p->d_ctrl, p->fd, f.level_ptr[l], f.level_ptr[l + 1] - f.level_ptr[l]);
+    launch_front_solve_bwd(p->st, p->d_ctrl, p->fd, f.level_ptr[l], f.level_ptr[l + 1] - f.level_ptr[l],
+                           p->lvl_max_m[l] * 8);
   if (a.schur) {
     launch_unpermute(p->st, p->d_ctrl, p->fd, p->d_y, 1.0);
     launch_schur_back(p->st, p->d_ctrl, p->sp, p->sd, p->d_y, p->d_upd);
@@ -295,10 +296,8 @@ void enqueue_solve(sfx_problem* p, const std::function<void(int)>& mark) {
 }
 
 void ensure_csc(sfx_problem* p) {
-  if (!p->a.csc_built) {
-    build_csc(p->a);
-    p->d_csc_src = p->pool.upload(p->a.csc_src);
-  }
+  build_csc(p->a);
+  if (!p->d_csc_src) p->d_csc_src = p->pool.upload(p->a.csc_src);
   if (p->export_cap < p->a.nnz) {
     p->d_export = p->pool.alloc<double>(p->a.nnz);
     p->export_cap = p->a.nnz;

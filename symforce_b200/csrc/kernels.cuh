@@ -90,6 +90,44 @@ struct FrontDev {
   double* ywork;    // n (elimination order)
 };
 
+// ---- large fronts: tile-DAG Cholesky (chol_large.cu) ---------------------------------------------
+struct LargeFront {
+  int64_t off;       // offset of the front in FrontDev::fronts
+  int64_t linv_off;  // offset of this front's L_kk^-1 tiles (wt * 64*64 doubles)
+  int m, w;
+  int wt, nt;        // pivot tiles, total tiles
+  int cnt_off;       // offset of the nt*nt tile version counters
+  int front;         // front id
+};
+struct LargeTask {
+  int lf;
+  short type, k, i, j;  // type: 0 POTRF(k), 1 TRSM(i,k), 2 UPDATE(i,j,k)
+};
+struct LargeJob {
+  int lf, type, idx, c0, c1;  // type 0: copy idx; 1: child front idx, columns [c0,c1); 2: damping rows [c0,c1)
+};
+struct LargeLevel {
+  int lf0, n_lf;   // range of large fronts of this level
+  int t0, t1;      // task range
+  int j0, j1;      // assembly job range
+  int max_m;
+};
+struct LargeDev {
+  const LargeFront* lf;
+  const LargeTask* tasks;
+  const LargeJob* jobs;
+  int* counters;
+  int* queue;  // one head per level
+  double* linv;
+};
+void launch_large_level(cudaStream_t st, Ctrl* ctrl, const FrontDev& fd, const LargeDev& ld, const LargeLevel& lv,
+                        int level, const double* sys_static, StatePtrs sp, int use_state_H, const double* dvec);
+void launch_large_solve_fwd(cudaStream_t st, const Ctrl* ctrl, const FrontDev& fd, const LargeDev& ld,
+                            const LargeLevel& lv, const double* rhs_static, StatePtrs sp, int use_state_rhs);
+void launch_large_solve_bwd(cudaStream_t st, const Ctrl* ctrl, const FrontDev& fd, const LargeDev& ld,
+                            const LargeLevel& lv);
+cudaError_t configure_large_kernels();
+
 // launchers (all asynchronous on `st`)
 void launch_zero_lin(cudaStream_t st, const Ctrl* ctrl, StatePtrs sp, int mode, int64_t n_h, int n_rhs);
 void launch_linearize(cudaStream_t st, const Ctrl* ctrl, StatePtrs sp, int mode, const LinBatch& b, double* partials);

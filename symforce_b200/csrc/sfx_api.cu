@@ -80,7 +80,12 @@ struct sfx_problem {
   std::vector<LinBatch> lin;
   SchurDev sd{};
   FrontDev fd{};
-  std::vector<int> lvl_max_m;
+  std::vector<int> lvl_max_m;      // largest SMALL front per level
+  std::vector<int> lvl_small_cnt;  // small fronts per level (listed first in level_fronts)
+  std::vector<LargeLevel> lvl_large;
+  LargeDev ld{};
+  int64_t n_counters = 0;
+  int small_max_m = 64;  // fronts with more rows go to the tile-DAG path
   int smem_cap_m = 168;
   // csc export
   int32_t* d_csc_src = nullptr;
@@ -232,15 +237,103 @@ void upload_structures(sfx_problem* p) {
       cp[i] = FrontCopy{c.src, c.rows, c.cols, c.src_ld, c.dst_row, c.dst_col, c.transposed, c.lower_only, 0};
     }
     d.copies = P.upload(cp);
-    d.level_fronts = up32(f.level_fronts);
     d.scalar_perm = up32(f.scalar_perm);
     d.fronts = P.alloc<double>(f.front_values);
     d.twork = P.alloc<double>(f.solve_ws);
     d.ywork = P.alloc<double>(f.n);
+    // ---- split every level into small fronts (one CTA each, in shared memory) and large fronts
+    //      (tile-DAG kernel); small ones first in level_fronts
+    if (const char* e = getenv("SFX_SMALL_MAX")) p->small_max_m = std::min(atoi(e), p->smem_cap_m);
+    const int T = 64;
+    std::vector<int> lvl_fronts(f.level_fronts);
     p->lvl_max_m.assign(f.n_levels, 0);
-    for (int s = 0; s < f.n_fronts; ++s)
-      p->lvl_max_m[f.f_level[s]] = std::max(p->lvl_max_m[f.f_level[s]], f.f_w[s] + f.f_u[s]);
+    p->lvl_small_cnt.assign(f.n_levels, 0);
+    p->lvl_large.assign(f.n_levels, LargeLevel{});
+    std::vector<LargeFront> lfs;
+    std::vector<LargeTask> tasks;
+    std::vector<LargeJob> jobs;
+    int64_t linv_off = 0, cnt_off = 0;
+    for (int l = 0; l < f.n_levels; ++l) {
+      int* b = lvl_fronts.data() + f.level_ptr[l];
+      int* e = lvl_fronts.data() + f.level_ptr[l + 1];
+      auto is_small = [&](int s) { return f.f_w[s] + f.f_u[s] <= p->small_max_m; };
+      int* mid = std::stable_partition(b, e, is_small);
+      p->lvl_small_cnt[l] = (int)(mid - b);
+      for (int* q = b; q < mid; ++q) p->lvl_max_m[l] = std::max(p->lvl_max_m[l], f.f_w[*q] + f.f_u[*q]);
+      LargeLevel& lv = p->lvl_large[l];
+      lv.lf0 = (int)lfs.size();
+      lv.n_lf = (int)(e - mid);
+      lv.t0 = (int)tasks.size();
+      lv.j0 = (int)jobs.size();
+      lv.max_m = 0;
+      int max_wt = 0;
+      for (int* q = mid; q < e; ++q) {
+        const int s = *q;
+        LargeFront x{};
+        x.off = f.f_off[s];
+        x.m = f.f_w[s] + f.f_u[s];
+        x.w = f.f_w[s];
+        x.wt = (x.w + T - 1) / T;
+        x.nt = x.wt + (f.f_u[s] + T - 1) / T;
+        x.linv_off = linv_off;
+        x.cnt_off = (int)cnt_off;
+        x.front = s;
+        linv_off += (int64_t)x.wt * T * T;
+        cnt_off += (int64_t)x.nt * x.nt;
+        SFX_CHECK(cnt_off < (int64_t)INT32_MAX, SFX_ERR_UNSUPPORTED, "too many tiles");
+        lv.max_m = std::max(lv.max_m, x.m);
+        max_wt = std::max(max_wt, x.wt);
+        const int li = (int)lfs.size();
+        lfs.push_back(x);
+        // assembly jobs
+        for (int c = f.f_copy_ptr[s]; c < f.f_copy_ptr[s + 1]; ++c) jobs.push_back(LargeJob{li, 0, c, 0, 0});
+        for (int r = 0; r < x.w; r += 1024) jobs.push_back(LargeJob{li, 2, 0, r, std::min(x.w, r + 1024)});
+        for (int ci = f.f_child_ptr[s]; ci < f.f_child_ptr[s + 1]; ++ci) {
+          const int c = f.f_child[ci];
+          const int uc = f.f_u[c];
+          int c0 = 0;
+          while (c0 < uc) {
+            int c1 = c0;
+            int64_t el = 0;
+            while (c1 < uc && el < 4096) {
+              el += uc - c1;
+              ++c1;
+            }
+            jobs.push_back(LargeJob{li, 1, c, c0, c1});
+            c0 = c1;
+          }
+        }
+      }
+      // tasks, ordered so that every dependency precedes its consumer (see chol_large.cu)
+      for (int k = 0; k < max_wt; ++k)
+        for (int li = lv.lf0; li < lv.lf0 + lv.n_lf; ++li) {
+          const LargeFront& x = lfs[li];
+          if (k >= x.wt) continue;
+          tasks.push_back(LargeTask{li, 0, (short)k, (short)k, (short)k});
+          if (k + 1 < x.nt) {
+            tasks.push_back(LargeTask{li, 1, (short)k, (short)(k + 1), (short)k});
+            tasks.push_back(LargeTask{li, 2, (short)k, (short)(k + 1), (short)(k + 1)});
+          }
+          for (int i = k + 2; i < x.nt; ++i) tasks.push_back(LargeTask{li, 1, (short)k, (short)i, (short)k});
+          for (int j = k + 1; j < x.nt; ++j)
+            for (int i = j; i < x.nt; ++i) {
+              if (i == k + 1 && j == k + 1) continue;
+              tasks.push_back(LargeTask{li, 2, (short)k, (short)i, (short)j});
+            }
+        }
+      lv.t1 = (int)tasks.size();
+      lv.j1 = (int)jobs.size();
+    }
+    d.level_fronts = up32(lvl_fronts);
+    p->ld.lf = P.upload(lfs);
+    p->ld.tasks = P.upload(tasks);
+    p->ld.jobs = P.upload(jobs);
+    p->n_counters = cnt_off;
+    p->ld.counters = P.alloc<int>(cnt_off);
+    p->ld.queue = P.alloc<int>(f.n_levels);
+    p->ld.linv = P.alloc<double>(linv_off);
     CUDA_OK(configure_front_kernels(p->smem_cap_m, f.max_front));
+    CUDA_OK(configure_large_kernels());
   }
 }
 
@@ -273,19 +366,32 @@ void enqueue_solve(sfx_problem* p, const std::function<void(int)>& mark) {
   if (a.schur) launch_schur(p->st, p->d_ctrl, p->sp, p->sd, p->d_dvec);
   mark(PH_SCHUR);
   const FrontPlan& f = a.fp;
+  const double* sys = a.schur ? p->sd.S : nullptr;
+  const int use_H = a.schur ? 0 : 1;
+  const double* dv = a.schur ? nullptr : p->d_dvec;
+  if (p->n_counters > 0) {
+    CUDA_OK(cudaMemsetAsync(p->ld.counters, 0, sizeof(int) * p->n_counters, p->st));
+    CUDA_OK(cudaMemsetAsync(p->ld.queue, 0, sizeof(int) * f.n_levels, p->st));
+  }
   for (int l = 0; l < f.n_levels; ++l) {
-    const int cnt = f.level_ptr[l + 1] - f.level_ptr[l];
-    const int sm = std::min(p->lvl_max_m[l], p->smem_cap_m);
-    launch_front_factor(p->st, p->d_ctrl, p->fd, a.schur ? p->sd.S : nullptr, p->sp, a.schur ? 0 : 1,
-                        a.schur ? nullptr : p->d_dvec, f.level_ptr[l], cnt, sm);
+    if (p->lvl_small_cnt[l] > 0)
+      launch_front_factor(p->st, p->d_ctrl, p->fd, sys, p->sp, use_H, dv, f.level_ptr[l], p->lvl_small_cnt[l],
+                          p->lvl_max_m[l]);
+    launch_large_level(p->st, p->d_ctrl, p->fd, p->ld, p->lvl_large[l], l, sys, p->sp, use_H, dv);
   }
   mark(PH_FACTOR);
-  for (int l = 0; l < f.n_levels; ++l)
-    launch_front_solve_fwd(p->st, p->d_ctrl, p->fd, a.schur ? p->sd.rhs_red : nullptr, p->sp, a.schur ? 0 : 1,
-                           f.level_ptr[l], f.level_ptr[l + 1] - f.level_ptr[l], p->lvl_max_m[l] * 8);
-  for (int l = f.n_levels - 1; l >= 0; --l)
-    launch_front_solve_bwd(p->st, p->d_ctrl, p->fd, f.level_ptr[l], f.level_ptr[l + 1] - f.level_ptr[l],
-                           p->lvl_max_m[l] * 8);
+  const double* rhs_s = a.schur ? p->sd.rhs_red : nullptr;
+  for (int l = 0; l < f.n_levels; ++l) {
+    if (p->lvl_small_cnt[l] > 0)
+      launch_front_solve_fwd(p->st, p->d_ctrl, p->fd, rhs_s, p->sp, use_H, f.level_ptr[l], p->lvl_small_cnt[l],
+                             p->lvl_max_m[l] * 8);
+    launch_large_solve_fwd(p->st, p->d_ctrl, p->fd, p->ld, p->lvl_large[l], rhs_s, p->sp, use_H);
+  }
+  for (int l = f.n_levels - 1; l >= 0; --l) {
+    if (p->lvl_small_cnt[l] > 0)
+      launch_front_solve_bwd(p->st, p->d_ctrl, p->fd, f.level_ptr[l], p->lvl_small_cnt[l], p->lvl_max_m[l] * 8);
+    launch_large_solve_bwd(p->st, p->d_ctrl, p->fd, p->ld, p->lvl_large[l]);
+  }
   if (a.schur) {
     launch_unpermute(p->st, p->d_ctrl, p->fd, p->d_y, 1.0);
     launch_schur_back(p->st, p->d_ctrl, p->sp, p->sd, p->d_y, p->d_upd);

@@ -108,7 +108,15 @@ __global__ void __launch_bounds__(kLargeThreads) large_factor_kernel(Ctrl* ctrl,
       const int s0 = tile_start(lf, k), nb = tile_size(lf, k);
       load_tile(As, F + s0 + (size_t)s0 * m, m, nb, nb, true);
       __syncthreads();
-      for (int c = 0; c < nb; ++c) {
+      // Cholesky of the tile fused with the forward substitution L X = I (X = L^-1 in Bs, layout
+      // X[r + c*kLd]): per column one pivot, one scaling, one rank-1 update of both A and X.
+      double* X = Bs;
+      {
+        const int r = tid & 63;
+        for (int c = tid >> 6; c < kT; c += kLargeThreads / 64) X[r + c * kLd] = (r == c) ? 1.0 : 0.0;
+      }
+      __syncthreads();
+      for (int c = 0; c < kT; ++c) {
         if (tid == 0) {
           double d = As[c + c * kLd];
           if (!(d > 0.0)) {
@@ -118,36 +126,25 @@ __global__ void __launch_bounds__(kLargeThreads) large_factor_kernel(Ctrl* ctrl,
           As[c + c * kLd] = sqrt(d);
         }
         __syncthreads();
-        const double piv = As[c + c * kLd];
-        if (tid > c && tid < kT) As[tid + c * kLd] /= piv;
+        const double pinv = 1.0 / As[c + c * kLd];
+        if (tid > c && tid < kT) As[tid + c * kLd] *= pinv;        // column c of L
+        if (tid >= 64 && tid < 64 + c + 1) X[c + (tid - 64) * kLd] *= pinv;  // row c of X (cols 0..c)
         __syncthreads();
         {
           const int r = tid & 63;
           if (r > c) {
             const double lrc = As[r + c * kLd];
             for (int cc = c + 1 + (tid >> 6); cc <= r; cc += kLargeThreads / 64) As[r + cc * kLd] -= lrc * As[cc + c * kLd];
+            for (int cc = (tid >> 6); cc <= c; cc += kLargeThreads / 64) X[r + cc * kLd] -= lrc * X[c + cc * kLd];
           }
         }
         __syncthreads();
       }
-      // L^-1 (lower), one column per thread, scratch layout X[r + c*65] inside Bs
-      double* X = Bs;
-      if (tid < kT) {
-        const int c = tid;
-        for (int r = 0; r < c; ++r) X[r + c * 65] = 0.0;
-        X[c + c * 65] = 1.0 / As[c + c * kLd];
-        for (int r = c + 1; r < kT; ++r) {
-          double s = 0.0;
-          for (int q = c; q < r; ++q) s += As[r + q * kLd] * X[q + c * 65];
-          X[r + c * 65] = -s / As[r + r * kLd];
-        }
-      }
-      __syncthreads();
       double* linv = ld.linv + lf.linv_off + (size_t)k * kT * kT;
       {
         const int r = tid & 63;
         for (int c = tid >> 6; c < kT; c += kLargeThreads / 64) {
-          linv[r + c * kT] = X[r + c * 65];
+          linv[r + c * kT] = X[r + c * kLd];
           if (r < nb && c < nb && r >= c) F[(s0 + r) + (size_t)(s0 + c) * m] = As[r + c * kLd];
         }
       }
@@ -189,8 +186,9 @@ __global__ void __launch_bounds__(kLargeThreads) large_factor_kernel(Ctrl* ctrl,
       for (int rb = 0; rb < 2; ++rb)
 #pragma unroll
         for (int cb = 0; cb < 4; ++cb) acc[rb][cb][0] = acc[rb][cb][1] = 0.0;
-      tile_gemm(As, Bs, acc);
       double* C = F + ri + (size_t)cj * m;
+      // all C loads first (independent, L2 latency overlapped), then subtract and store
+      double cin[2][4][2];
 #pragma unroll
       for (int rb = 0; rb < 2; ++rb)
 #pragma unroll
@@ -199,10 +197,18 @@ __global__ void __launch_bounds__(kLargeThreads) large_factor_kernel(Ctrl* ctrl,
           for (int e = 0; e < 2; ++e) {
             const int r = wr * 16 + rb * 8 + g;
             const int c = wc * 32 + cb * 8 + tq * 2 + e;
-            if (r < ni && c < nj) {
-              double* p = C + r + (size_t)c * m;
-              *p = trsm ? acc[rb][cb][e] : (__ldcg(p) - acc[rb][cb][e]);
-            }
+            cin[rb][cb][e] = (!trsm && r < ni && c < nj) ? __ldcg(C + r + (size_t)c * m) : 0.0;
+          }
+      tile_gemm(As, Bs, acc);
+#pragma unroll
+      for (int rb = 0; rb < 2; ++rb)
+#pragma unroll
+        for (int cb = 0; cb < 4; ++cb)
+#pragma unroll
+          for (int e = 0; e < 2; ++e) {
+            const int r = wr * 16 + rb * 8 + g;
+            const int c = wc * 32 + cb * 8 + tq * 2 + e;
+            if (r < ni && c < nj) C[r + (size_t)c * m] = trsm ? acc[rb][cb][e] : cin[rb][cb][e] - acc[rb][cb][e];
           }
       __syncthreads();
       if (tid == 0) {

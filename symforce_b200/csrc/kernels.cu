@@ -246,6 +246,185 @@ __global__ void __launch_bounds__(kLinThreads) linearize_kernel(const Ctrl* __re
   if (threadIdx.x == 0) partials[b.partial_base + blockIdx.x] = tot;
 }
 
+// ---- K1, BAL fast path ---------------------------------------------------------------------------
+// Snavely factors whose camera pose + intrinsics are one 9-dim node and whose point is a 3-dim
+// node.  Slots are camera-major, so a warp almost always works on ONE camera: its 45 + 9 camera
+// block/rhs values are summed across the warp with a transpose-reduce (62 shuffles per 32 values,
+// every lane ends up owning one total) and leave the SM as 54 atomics per warp instead of 1728.
+// The 3x9 point-camera block of every observation is owned by that observation: it is staged in
+// shared memory and written as one contiguous 6912-byte run per warp.  Point blocks go out as
+// fp64 RED atomics (9 per observation).
+__device__ __forceinline__ double transpose_reduce32(double (&v)[32]) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int o = 16, n = 16; o >= 1; o >>= 1, n >>= 1) {
+    const bool up = (lane & o) != 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i)
+      if (i < n) {
+        const double lo = v[i], hi = v[i + n];
+        const double send = up ? lo : hi;
+        const double keep = up ? hi : lo;
+        v[i] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+      }
+  }
+  return v[0];  // total of value index: bit-reversed-free mapping, see value_of_lane()
+}
+// which of the 32 input values a lane owns after transpose_reduce32
+__device__ __forceinline__ int value_of_lane(int lane) {
+  return ((lane & 16) ? 16 : 0) + ((lane & 8) ? 8 : 0) + ((lane & 4) ? 4 : 0) + ((lane & 2) ? 2 : 0) + (lane & 1);
+}
+
+constexpr int kBalThreads = 128;
+__global__ void __launch_bounds__(kBalThreads) linearize_bal_kernel(const Ctrl* __restrict__ ctrl, StatePtrs sp,
+                                                                    LinBatch b, int mode,
+                                                                    double* __restrict__ partials) {
+  __shared__ double stage[kBalThreads / 32][32 * 27];
+  if (ctrl->done) return;
+  const int blk = sel_block(ctrl, mode);
+  if (mode == 0 && ctrl->lin_valid[blk]) return;
+  const double* __restrict__ values = sp.values[blk];
+  double* __restrict__ H = sp.H[blk];
+  double* __restrict__ rhs = sp.rhs[blk];
+  double* __restrict__ resid = sp.res[blk];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int s = blockIdx.x * kBalThreads + threadIdx.x;
+  const bool valid = s < b.n;
+  const int sc = valid ? s : b.n - 1;
+  double res[2], J[24];
+  {
+    const double* a0 = values + __ldg(b.arg_off + sc);
+    const double* a1 = values + __ldg(b.arg_off + (size_t)b.n + sc);
+    const double* a2 = values + __ldg(b.arg_off + (size_t)2 * b.n + sc);
+    const double* a3 = values + __ldg(b.arg_off + (size_t)3 * b.n + sc);
+    sfx_factor_snavely(a0, a1, a2, a3, nullptr, res, J);
+  }
+  if (!valid) {
+    res[0] = res[1] = 0.0;
+#pragma unroll
+    for (int i = 0; i < 24; ++i) J[i] = 0.0;
+  }
+  double err = res[0] * res[0] + res[1] * res[1];
+  if (valid) {
+    const int ro = __ldg(b.res_off + s);
+    resid[ro] = res[0];
+    resid[ro + 1] = res[1];
+  }
+  const int cam_rhs = __ldg(b.rhs_off + sc);
+  const int pt_rhs = __ldg(b.rhs_off + (size_t)b.n + sc);
+  const int cam_diag = __ldg(b.diag_off + sc);
+  const int pt_diag = __ldg(b.diag_off + (size_t)b.n + sc);
+  const uint32_t eo = __ldg(b.off_off + sc);
+  // ---- camera block: 45 lower entries (column-major packed) + 9 rhs ------------------------------
+  const int key0 = __shfl_sync(0xffffffffu, cam_diag, 0);
+  const bool uniform = __all_sync(0xffffffffu, !valid || cam_diag == key0);
+  if (uniform) {
+    double v[32];
+    // batch 0: packed entries 0..31
+    {
+      int idx = 0;
+#pragma unroll
+      for (int c = 0; c < 9; ++c)
+#pragma unroll
+        for (int r = c; r < 9; ++r) {
+          if (idx < 32) v[idx] = J[2 * r] * J[2 * c] + J[2 * r + 1] * J[2 * c + 1];
+          ++idx;
+        }
+    }
+    const double t0 = transpose_reduce32(v);
+    // batch 1: packed entries 32..44, then rhs 0..8 (22 values), rest zero
+    {
+      int idx = 0;
+#pragma unroll
+      for (int c = 0; c < 9; ++c)
+#pragma unroll
+        for (int r = c; r < 9; ++r) {
+          if (idx >= 32) v[idx - 32] = J[2 * r] * J[2 * c] + J[2 * r + 1] * J[2 * c + 1];
+          ++idx;
+        }
+#pragma unroll
+      for (int r = 0; r < 9; ++r) v[13 + r] = J[2 * r] * res[0] + J[2 * r + 1] * res[1];
+#pragma unroll
+      for (int i = 22; i < 32; ++i) v[i] = 0.0;
+    }
+    const double t1 = transpose_reduce32(v);
+    const int vi = value_of_lane(lane);
+    // packed index -> (r, c)
+    {
+      int idx = vi, c = 0;
+      while (idx >= 9 - c) {
+        idx -= 9 - c;
+        ++c;
+      }
+      atomicAdd(H + key0 + (c + idx) + c * 9, t0);
+    }
+    if (vi < 13) {
+      int idx = vi + 32, c = 0;
+      while (idx >= 9 - c) {
+        idx -= 9 - c;
+        ++c;
+      }
+      atomicAdd(H + key0 + (c + idx) + c * 9, t1);
+    }
+    {
+      const int rb = __shfl_sync(0xffffffffu, cam_rhs, 0);
+      if (vi >= 13 && vi < 22) atomicAdd(rhs + rb + (vi - 13), t1);
+    }
+  } else if (valid) {
+#pragma unroll
+    for (int c = 0; c < 9; ++c)
+#pragma unroll
+      for (int r = c; r < 9; ++r)
+        atomicAdd(H + cam_diag + r + c * 9, J[2 * r] * J[2 * c] + J[2 * r + 1] * J[2 * c + 1]);
+#pragma unroll
+    for (int r = 0; r < 9; ++r) atomicAdd(rhs + cam_rhs + r, J[2 * r] * res[0] + J[2 * r + 1] * res[1]);
+  }
+  // ---- point block ---------------------------------------------------------------------------------
+  if (valid) {
+#pragma unroll
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int r = c; r < 3; ++r)
+        atomicAdd(H + pt_diag + r + c * 3,
+                  J[2 * (9 + r)] * J[2 * (9 + c)] + J[2 * (9 + r) + 1] * J[2 * (9 + c) + 1]);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) atomicAdd(rhs + pt_rhs + r, J[2 * (9 + r)] * res[0] + J[2 * (9 + r) + 1] * res[1]);
+  }
+  // ---- E block (point rows x camera cols), owned by the observation --------------------------------
+  {
+    const uint32_t off = eo & 0x3fffffffu;
+    const bool excl = (eo >> 31) != 0;
+    const uint32_t off0 = __shfl_sync(0xffffffffu, off, 0);
+    const bool contiguous = __all_sync(0xffffffffu, valid && excl && off == off0 + 27u * lane);
+    if (contiguous) {
+      double* st = stage[warp];
+#pragma unroll
+      for (int c = 0; c < 9; ++c)
+#pragma unroll
+        for (int a = 0; a < 3; ++a)
+          st[lane * 27 + a + 3 * c] = J[2 * (9 + a)] * J[2 * c] + J[2 * (9 + a) + 1] * J[2 * c + 1];
+      __syncwarp();
+      double* dst = H + off0;
+#pragma unroll
+      for (int i = 0; i < 27; ++i) dst[i * 32 + lane] = st[i * 32 + lane];
+    } else if (valid) {
+      double* dst = H + off;
+#pragma unroll
+      for (int c = 0; c < 9; ++c)
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+          const double v = J[2 * (9 + a)] * J[2 * c] + J[2 * (9 + a) + 1] * J[2 * c + 1];
+          if (excl)
+            dst[a + 3 * c] = v;
+          else
+            atomicAdd(dst + a + 3 * c, v);
+        }
+    }
+  }
+  const double tot = block_sum<kBalThreads>(err);
+  if (threadIdx.x == 0) partials[b.partial_base + blockIdx.x] = tot;
+}
+
 __global__ void zero_lin_kernel(const Ctrl* __restrict__ ctrl, StatePtrs sp, int mode, int64_t n_h, int n_rhs) {
   if (ctrl->done) return;
   const int blk = sel_block(ctrl, mode);
@@ -281,6 +460,10 @@ void launch_zero_lin(cudaStream_t st, const Ctrl* ctrl, StatePtrs sp, int mode, 
 
 void launch_linearize(cudaStream_t st, const Ctrl* ctrl, StatePtrs sp, int mode, const LinBatch& b, double* partials) {
   const int grid = (b.n + kLinThreads - 1) / kLinThreads;
+  if (b.bal_fast) {
+    linearize_bal_kernel<<<grid, kBalThreads, 0, st>>>(ctrl, sp, b, mode, partials); ++g_launches;
+    return;
+  }
   switch (b.kind) {
 #define SFX_CASE(ID) \
   case ID: linearize_kernel<ID><<<grid, kLinThreads, 0, st>>>(ctrl, sp, b, mode, partials); ++g_launches; break;
@@ -427,15 +610,22 @@ __global__ void schur_cinv_kernel(const Ctrl* __restrict__ ctrl, StatePtrs sp, S
   for (int r = 0; r < 3; ++r) sd.tl[(size_t)l * 3 + r] = Ci[r][0] * w[0] + Ci[r][1] * w[1] + Ci[r][2] * w[2];
 }
 
-// One warp per S block: S_IJ = B_IJ (+ D on the diagonal) - sum_matches E_I^T C^-1 E_J.
+// One warp per work item = (S block, chunk of <= 32 matches): partial = sum_matches E_I^T C^-1 E_J.
+// Items are sorted by block column, so concurrently running warps touch a narrow band of cameras
+// and the E blocks are served from L2.  Blocks with one chunk are stored directly
+// (S_IJ = B_IJ + D - partial); longer match lists are split and combined with fp64 RED atomics on
+// the zeroed S.
 constexpr int kSchurWarps = 4;
 __global__ void __launch_bounds__(kSchurWarps * 32) schur_s_kernel(const Ctrl* __restrict__ ctrl, StatePtrs sp,
                                                                    SchurDev sd, const double* __restrict__ dvec) {
   if (ctrl->done) return;
   __shared__ double sh[kSchurWarps][3 * 16 * 2 + 3 * 16 + 9];
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x * kSchurWarps + wid;
-  if (b >= sd.n_sblocks) return;
+  const int item = blockIdx.x * kSchurWarps + wid;
+  if (item >= sd.n_items) return;
+  const int b = sd.item_blk[item];
+  const int m0 = sd.item_m0[item], m1 = m0 + sd.item_cnt[item];
+  const int first = sd.item_flags[item] & 1, single = (sd.item_flags[item] >> 1) & 1;
   const double* H = sp.H[ctrl->init_idx];
   const int I = sd.s_row[b], J = sd.s_col[b];
   const int dI = sd.node_dim[I], dJ = sd.node_dim[J];
@@ -447,8 +637,7 @@ __global__ void __launch_bounds__(kSchurWarps * 32) schur_s_kernel(const Ctrl* _
   double acc[8];
 #pragma unroll
   for (int k = 0; k < 8; ++k) acc[k] = 0.0;
-  const int64_t m0 = sd.s_m_ptr[b], m1 = sd.s_m_ptr[b + 1];
-  for (int64_t m = m0; m < m1; ++m) {
+  for (int m = m0; m < m1; ++m) {
     const int l = sd.m_lm[m];
     const int dl = sd.lm_dim[l];
     const double* ei = H + sd.m_eoff_i[m];
@@ -458,7 +647,6 @@ __global__ void __launch_bounds__(kSchurWarps * 32) schur_s_kernel(const Ctrl* _
     for (int t = lane; t < dl * dJ; t += 32) EJ[t] = ej[t];
     if (lane < 9) Cs[lane] = sd.cinv[(size_t)l * 9 + lane];
     __syncwarp();
-    // G = Cinv * EJ  (dl x dJ)
     for (int t = lane; t < dl * dJ; t += 32) {
       const int a = t % dl, c = t / dl;
       double v = 0;
@@ -486,11 +674,22 @@ __global__ void __launch_bounds__(kSchurWarps * 32) schur_s_kernel(const Ctrl* _
     if (e < ne) {
       const int r = e % dI, c = e / dI;
       double v = -acc[k];
-      if (bsrc >= 0) v += H[bsrc + e];
-      if (I == J && r == c) v += dvec[toI + r];
-      out[e] = v;
+      if (first) {
+        if (bsrc >= 0) v += H[bsrc + e];
+        if (I == J && r == c) v += dvec[toI + r];
+      }
+      if (single)
+        out[e] = v;
+      else
+        atomicAdd(out + e, v);
     }
   }
+}
+
+__global__ void zero_kernel(const Ctrl* __restrict__ ctrl, double* __restrict__ p, int64_t n) {
+  if (ctrl->done) return;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = 0.0;
 }
 
 // reduced rhs: v_I - sum_l E_{l,I}^T (C_l^-1 w_l); one warp per reduced node
@@ -556,7 +755,12 @@ __global__ void schur_back_kernel(const Ctrl* __restrict__ ctrl, StatePtrs sp, S
 
 void launch_schur(cudaStream_t st, const Ctrl* ctrl, StatePtrs sp, const SchurDev& sd, const double* dvec) {
   schur_cinv_kernel<<<(sd.n_landmarks + 127) / 128, 128, 0, st>>>(ctrl, sp, sd, dvec); ++g_launches;
-  schur_s_kernel<<<(sd.n_sblocks + kSchurWarps - 1) / kSchurWarps, kSchurWarps * 32, 0, st>>>(ctrl, sp, sd, dvec); ++g_launches;
+  {
+    int zg = (int)((sd.s_values + 255) / 256);
+    if (zg > 148 * 8) zg = 148 * 8;
+    zero_kernel<<<zg, 256, 0, st>>>(ctrl, sd.S, sd.s_values); ++g_launches;
+  }
+  schur_s_kernel<<<(sd.n_items + kSchurWarps - 1) / kSchurWarps, kSchurWarps * 32, 0, st>>>(ctrl, sp, sd, dvec); ++g_launches;
   schur_rhs_kernel<<<(sd.n_reduced_nodes + 3) / 4, 128, 0, st>>>(ctrl, sp, sd); ++g_launches;
 }
 
@@ -934,7 +1138,6 @@ __global__ void lm_after_first_kernel(Ctrl* c) {
 // everything after Relinearize in Iterate() (…tcc:239-343)
 __global__ void lm_end_kernel(Ctrl* c, const double* __restrict__ upd, double* __restrict__ last_upd, int N,
                               int* host_done) {
-  __shared__ int s_accept;
   if (c->done) return;
   if (threadIdx.x == 0) {
     const sfx_params& p = c->p;
@@ -1002,22 +1205,29 @@ __global__ void lm_end_kernel(Ctrl* c, const double* __restrict__ upd, double* _
     it.update_angle_change = angle;
     it.update_accepted = accept ? 1 : 0;
     c->n_iters++;
-    s_accept = accept ? 1 : 0;
     if (status) {
       if (status != 3) c->failure_reason = 0;
       c->done = status;
       *host_done = status;
     }
   }
-  __syncthreads();
-  if (s_accept)
-    for (int i = threadIdx.x; i < N; i += blockDim.x) last_upd[i] = upd[i];
+}
+
+// last_update_ = update_ when the step was accepted (the entry just written says so)
+__global__ void save_last_update_kernel(const Ctrl* __restrict__ c, const double* __restrict__ upd,
+                                        double* __restrict__ last_upd, int N) {
+  if (c->n_iters < 1 || !c->iters[c->n_iters - 1].update_accepted) return;
+  if (!c->p.enable_bold_updates) return;  // last_update_ is only read by the bold-update rule
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) last_upd[i] = upd[i];
 }
 
 void launch_lm_begin(cudaStream_t st, Ctrl* ctrl) { lm_begin_kernel<<<1, 1, 0, st>>>(ctrl); ++g_launches; }
 void launch_lm_after_first_linearize(cudaStream_t st, Ctrl* ctrl) { lm_after_first_kernel<<<1, 1, 0, st>>>(ctrl); ++g_launches; }
 void launch_lm_end(cudaStream_t st, Ctrl* ctrl, const double* upd, double* last_upd, int N, int* host_done) {
-  lm_end_kernel<<<1, 1024, 0, st>>>(ctrl, upd, last_upd, N, host_done); ++g_launches;
+  lm_end_kernel<<<1, 32, 0, st>>>(ctrl, upd, last_upd, N, host_done); ++g_launches;
+  int grid = (N + 255) / 256;
+  if (grid > 296) grid = 296;
+  save_last_update_kernel<<<grid, 256, 0, st>>>(ctrl, upd, last_upd, N); ++g_launches;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -53,6 +53,7 @@ struct LinBatch {
   int group_dim[3];
   int n_groups;
   int partial_base;  // offset of this batch's per-CTA partial sums
+  int bal_fast;      // Snavely batch with (pose+intrinsics) 9-node and 3-dim point node: linearize_bal_kernel
 };
 
 struct SchurDev {
@@ -66,6 +67,10 @@ struct SchurDev {
   const int32_t* s_b_src;
   const int64_t* s_m_ptr;
   const int32_t *m_eoff_i, *m_eoff_j, *m_lm;
+  // work items of schur_s_kernel: (block, first match, count, flags: bit0 first chunk, bit1 only chunk)
+  int n_items;
+  const int32_t *item_blk, *item_m0, *item_cnt, *item_flags;
+  int64_t s_values;
   const int32_t *r_ptr, *r_eoff, *r_lm;
   double* cinv;   // [n_landmarks][9]
   double* tl;     // [n_landmarks][3]

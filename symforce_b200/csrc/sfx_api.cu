@@ -146,6 +146,20 @@ void upload_structures(sfx_problem* p) {
       lb.group_dim[i] = i < bp.n_groups ? bp.group_dim[i] : 0;
     }
     lb.n_groups = bp.n_groups;
+    // BAL fast path: camera pose + intrinsics merged into one 9-dim node, point node of dim 3,
+    // every point-camera block stored untransposed (landmark nodes trail the camera nodes)
+    lb.bal_fast = 0;
+    if (bp.kind == SFX_KIND_SNAVELY && bp.n_groups == 2 && bp.key_group[0] == 0 && bp.key_group[1] == 0 &&
+        bp.key_group[2] == 1 && bp.key_sub[0] == 0 && bp.key_sub[1] == 6 && bp.key_sub[2] == 0 &&
+        bp.group_dim[0] == 9 && bp.group_dim[1] == 3 && !getenv("SFX_NO_BAL_FAST")) {
+      bool ok = true;
+      for (uint32_t v : bp.off_off)
+        if (v & kOffTransposed) {
+          ok = false;
+          break;
+        }
+      lb.bal_fast = ok ? 1 : 0;
+    }
     lb.partial_base = partial_base;
     partial_base += (bp.n + 127) / 128;
     p->lin.push_back(lb);
@@ -205,6 +219,28 @@ void upload_structures(sfx_problem* p) {
     d.m_eoff_i = P.upload(s.m_eoff_i);
     d.m_eoff_j = P.upload(s.m_eoff_j);
     d.m_lm = P.upload(s.m_lm);
+    {
+      const int chunk = getenv("SFX_SCHUR_CHUNK") ? atoi(getenv("SFX_SCHUR_CHUNK")) : 32;
+      std::vector<int32_t> ib, im, ic, ifl;
+      SFX_CHECK(s.m_lm.size() < (size_t)INT32_MAX, SFX_ERR_UNSUPPORTED, "too many Schur matches");
+      for (int b = 0; b < d.n_sblocks; ++b) {
+        const int64_t m0 = s.s_m_ptr[b], m1 = s.s_m_ptr[b + 1];
+        const int64_t n = m1 - m0;
+        const int nch = n == 0 ? 1 : (int)((n + chunk - 1) / chunk);
+        for (int c = 0; c < nch; ++c) {
+          ib.push_back(b);
+          im.push_back((int32_t)(m0 + (int64_t)c * chunk));
+          ic.push_back((int32_t)std::min<int64_t>(chunk, n - (int64_t)c * chunk));
+          ifl.push_back((c == 0 ? 1 : 0) | (nch == 1 ? 2 : 0));
+        }
+      }
+      d.n_items = (int)ib.size();
+      d.item_blk = P.upload(ib);
+      d.item_m0 = P.upload(im);
+      d.item_cnt = P.upload(ic);
+      d.item_flags = P.upload(ifl);
+      d.s_values = s.S.n_values;
+    }
     d.r_ptr = P.upload(s.r_ptr);
     d.r_eoff = P.upload(s.r_eoff);
     d.r_lm = P.upload(s.r_lm);

@@ -187,19 +187,21 @@ __global__ void __launch_bounds__(kLargeThreads) large_factor_kernel(Ctrl* ctrl,
 #pragma unroll
         for (int cb = 0; cb < 4; ++cb) acc[rb][cb][0] = acc[rb][cb][1] = 0.0;
       double* C = F + ri + (size_t)cj * m;
-      // all C loads first (independent, L2 latency overlapped), then subtract and store
-      double cin[2][4][2];
-#pragma unroll
-      for (int rb = 0; rb < 2; ++rb)
-#pragma unroll
-        for (int cb = 0; cb < 4; ++cb)
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int r = wr * 16 + rb * 8 + g;
-            const int c = wc * 32 + cb * 8 + tq * 2 + e;
-            cin[rb][cb][e] = (!trsm && r < ni && c < nj) ? __ldcg(C + r + (size_t)c * m) : 0.0;
-          }
       tile_gemm(As, Bs, acc);
+      // C tile: all loads first (independent, one L2 latency), then subtract and store
+      if (!trsm) {
+#pragma unroll
+        for (int rb = 0; rb < 2; ++rb)
+#pragma unroll
+          for (int cb = 0; cb < 4; ++cb)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int r = wr * 16 + rb * 8 + g;
+              const int c = wc * 32 + cb * 8 + tq * 2 + e;
+              const double cin = (r < ni && c < nj) ? __ldcg(C + r + (size_t)c * m) : 0.0;
+              acc[rb][cb][e] = cin - acc[rb][cb][e];
+            }
+      }
 #pragma unroll
       for (int rb = 0; rb < 2; ++rb)
 #pragma unroll
@@ -208,7 +210,7 @@ __global__ void __launch_bounds__(kLargeThreads) large_factor_kernel(Ctrl* ctrl,
           for (int e = 0; e < 2; ++e) {
             const int r = wr * 16 + rb * 8 + g;
             const int c = wc * 32 + cb * 8 + tq * 2 + e;
-            if (r < ni && c < nj) C[r + (size_t)c * m] = trsm ? acc[rb][cb][e] : cin[rb][cb][e] - acc[rb][cb][e];
+            if (r < ni && c < nj) C[r + (size_t)c * m] = acc[rb][cb][e];
           }
       __syncthreads();
       if (tid == 0) {
@@ -290,98 +292,178 @@ cudaError_t configure_large_kernels() {
                               (int)(2 * kT * kLd * sizeof(double)));
 }
 
-// ---- triangular solves on large fronts (one CTA per front, panels of 64 with L_kk^-1) ------------
+// ---- triangular solves on large fronts -------------------------------------------------------------
+// P cooperating CTAs per front; tile-row i of the front is owned by CTA i % P.  The dependency
+// chain over the pivot tiles runs through global flags (forward) / per-tile contribution counters
+// (backward) with ld.acquire / st.release; every L tile is read exactly once, spread over P SMs.
+// All CTAs of a launch are co-resident (grid <= #SMs), which the spin-waits rely on.
+__device__ __forceinline__ void tile_gemv(const double* __restrict__ Lt, int ldm, int nr, int nc,
+                                          const double* __restrict__ x, double* red, double* out_sub) {
+  // out_sub[r] -= sum_c Lt[r + c*ldm] * x[c]; 256 threads: r = tid & 63, 4 column groups
+  const int r = threadIdx.x & 63, gq = threadIdx.x >> 6;
+  double v = 0.0;
+  if (r < nr)
+    for (int c = gq; c < nc; c += 4) v += __ldcg(Lt + r + (size_t)c * ldm) * x[c];
+  red[gq * 64 + r] = v;
+  __syncthreads();
+  if (threadIdx.x < 64 && r < nr) out_sub[r] -= red[r] + red[64 + r] + red[128 + r] + red[192 + r];
+  __syncthreads();
+}
+__device__ __forceinline__ void tile_gemv_t(const double* __restrict__ Lt, int ldm, int nr, int nc,
+                                            const double* __restrict__ x, double* __restrict__ out) {
+  // out[c] = sum_r Lt[r + c*ldm] * x[r]; one warp per column (8 warps)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int c = warp; c < nc; c += 8) {
+    double v = 0.0;
+    for (int r = lane; r < nr; r += 32) v += __ldcg(Lt + r + (size_t)c * ldm) * x[r];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    if (lane == 0) out[c] = v;
+  }
+}
+
 __global__ void __launch_bounds__(256) large_solve_fwd_kernel(const Ctrl* __restrict__ ctrl, FrontDev fd, LargeDev ld,
                                                                const double* __restrict__ rhs_static, StatePtrs sp,
-                                                               int use_state_rhs, int lf0) {
-  extern __shared__ double f[];  // m + 64
+                                                               int use_state_rhs, int lf0, int P) {
+  extern __shared__ double smf[];  // own: ceil(nt/P)*64 | y: 64 | red: 256
   if (ctrl->done) return;
-  const LargeFront lf = ld.lf[lf0 + blockIdx.x];
-  const int s = lf.front;
-  const int w = lf.w, m = lf.m, u = m - w;
-  double* ytmp = f + m;
+  const LargeFront lf = ld.lf[lf0 + blockIdx.x / P];
+  const int p = blockIdx.x % P;
+  const int s = lf.front, w = lf.w, m = lf.m, nt = lf.nt, wt = lf.wt;
+  const int n_own = (nt - p + P - 1) / P;
+  double* own = smf;
+  double* yk = own + (size_t)((nt + P - 1) / P) * kT;
+  double* red = yk + kT;
   const double* rhs = use_state_rhs ? sp.rhs[ctrl->init_idx] : rhs_static;
   const double* L = fd.fronts + lf.off;
-  const int tid = threadIdx.x, nt = blockDim.x;
-  for (int r = tid; r < m; r += nt) f[r] = r < w ? rhs[fd.scalar_perm[fd.f_piv[s] + r]] : 0.0;
+  int* flag = ld.sflags + lf.flag_off;
+  const int tid = threadIdx.x;
+  // ---- assemble the owned part of the front right-hand side
+  for (int q = tid; q < n_own * kT; q += 256) {
+    const int i = p + (q / kT) * P, r = q % kT;
+    const int row = tile_start(lf, i) + r;
+    double v = 0.0;
+    if (r < tile_size(lf, i) && row < w) v = rhs[fd.scalar_perm[fd.f_piv[s] + row]];
+    own[q] = v;
+  }
   __syncthreads();
   for (int ci = fd.f_child_ptr[s]; ci < fd.f_child_ptr[s + 1]; ++ci) {
     const int c = fd.f_child[ci];
     const int uc = fd.f_u[c];
     const double* t = fd.twork + fd.f_toff[c];
     const int32_t* rel = fd.f_rel + fd.f_rows_ptr[c];
-    for (int q = tid; q < uc; q += nt) f[rel[q]] += t[q];
-    __syncthreads();
-  }
-  for (int kt = 0; kt < lf.wt; ++kt) {
-    const int c0 = kt * kT, nb = min(kT, w - c0);
-    const double* linv = ld.linv + lf.linv_off + (size_t)kt * kT * kT;
-    if (tid < nb) {
-      double v = 0.0;
-      for (int q = 0; q <= tid; ++q) v += linv[tid + q * kT] * f[c0 + q];
-      ytmp[tid] = v;
-    }
-    __syncthreads();
-    if (tid < nb) f[c0 + tid] = ytmp[tid];
-    for (int r = c0 + nb + tid; r < m; r += nt) {
-      double v = f[r];
-      for (int q = 0; q < nb; ++q) v -= L[r + (size_t)(c0 + q) * m] * ytmp[q];
-      f[r] = v;
+    for (int q = tid; q < uc; q += 256) {
+      const int row = rel[q];
+      const int i = row < w ? row / kT : wt + (row - w) / kT;
+      if (i % P == p) own[(i / P) * kT + (row - tile_start(lf, i))] += t[q];  // rows of one child are distinct
     }
     __syncthreads();
   }
-  for (int q = tid; q < u; q += nt) fd.twork[fd.f_toff[s] + q] = f[w + q];
-  for (int r = tid; r < w; r += nt) fd.ywork[fd.f_piv[s] + r] = f[r];
+  // ---- forward substitution over the pivot tiles
+  for (int k = 0; k < wt; ++k) {
+    const int nb = tile_size(lf, k);
+    double* ypub = fd.ywork + fd.f_piv[s] + k * kT;
+    if (k % P == p) {
+      const double* linv = ld.linv + lf.linv_off + (size_t)k * kT * kT;
+      const double* fk = own + (k / P) * kT;
+      if (tid < nb) {
+        double v = 0.0;
+        for (int q = 0; q <= tid; ++q) v += linv[tid + q * kT] * fk[q];
+        yk[tid] = v;
+        ypub[tid] = v;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        __threadfence();
+        st_release(flag + k, 1);
+      }
+    } else {
+      if (tid == 0)
+        while (ld_acquire(flag + k) == 0) __nanosleep(20);
+      __syncthreads();
+      if (tid < nb) yk[tid] = __ldcg(ypub + tid);
+      __syncthreads();
+    }
+    const int ck = k * kT;
+    for (int i = k + 1 + ((p - (k + 1)) % P + P) % P; i < nt; i += P)
+      tile_gemv(L + tile_start(lf, i) + (size_t)ck * m, m, tile_size(lf, i), nb, yk, red, own + (i / P) * kT);
+  }
+  // ---- update part -> twork (pivot part was published tile by tile)
+  for (int q = tid; q < n_own * kT; q += 256) {
+    const int i = p + (q / kT) * P, r = q % kT;
+    if (i >= wt && r < tile_size(lf, i)) fd.twork[fd.f_toff[s] + (tile_start(lf, i) - w) + r] = own[q];
+  }
 }
 
 __global__ void __launch_bounds__(256) large_solve_bwd_kernel(const Ctrl* __restrict__ ctrl, FrontDev fd, LargeDev ld,
-                                                               int lf0) {
-  extern __shared__ double f[];  // m + 64
+                                                               int lf0, int P) {
+  extern __shared__ double smf[];  // x: 64 | g: 64 | tmp: 64
   if (ctrl->done) return;
-  const LargeFront lf = ld.lf[lf0 + blockIdx.x];
-  const int s = lf.front;
-  const int w = lf.w, m = lf.m;
-  double* gt = f + m;
+  const LargeFront lf = ld.lf[lf0 + blockIdx.x / P];
+  const int p = blockIdx.x % P;
+  const int s = lf.front, w = lf.w, m = lf.m, nt = lf.nt, wt = lf.wt;
+  double* xi = smf;
+  double* g = xi + kT;
   const double* L = fd.fronts + lf.off;
-  const int tid = threadIdx.x, nt = blockDim.x;
-  const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+  int* cntb = ld.sflags + lf.flag_off + wt;  // contributions received per pivot tile
+  double* contrib = ld.contrib + lf.contrib_off;
+  const int tid = threadIdx.x;
   const int32_t* rows = fd.f_rows + fd.f_rows_ptr[s];
-  for (int r = tid; r < m; r += nt) f[r] = r < w ? fd.ywork[fd.f_piv[s] + r] : fd.ywork[rows[r - w]];
-  __syncthreads();
-  for (int kt = lf.wt - 1; kt >= 0; --kt) {
-    const int c0 = kt * kT, nb = min(kT, w - c0);
-    // g_c = y_c - sum_{r >= c0+nb} L[r, c0+c] x_r   (one warp per column)
-    for (int c = warp; c < nb; c += nw) {
-      double v = 0.0;
-      for (int r = c0 + nb + lane; r < m; r += 32) v += L[r + (size_t)(c0 + c) * m] * f[r];
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-      if (lane == 0) gt[c] = f[c0 + c] - v;
+  // owned tile rows, from the bottom up
+  int i = nt - 1 - (((nt - 1 - p) % P) + P) % P;
+  for (; i >= 0; i -= P) {
+    const int ni = tile_size(lf, i), ri = tile_start(lf, i);
+    if (i >= wt) {
+      // update rows: x known from the ancestors
+      if (tid < ni) xi[tid] = fd.ywork[rows[ri - w + tid]];
+      __syncthreads();
+    } else {
+      // pivot tile i: wait for all contributions of rows below, then x_i = L_ii^-T (y_i - sum)
+      if (tid == 0)
+        while (ld_acquire(cntb + i) < nt - 1 - i) __nanosleep(20);
+      __syncthreads();
+      if (tid < ni) {
+        double v = fd.ywork[fd.f_piv[s] + ri + tid];
+        for (int r = nt - 1; r > i; --r) v -= __ldcg(contrib + ((size_t)i * nt + r) * kT + tid);
+        g[tid] = v;
+      }
+      __syncthreads();
+      const double* linv = ld.linv + lf.linv_off + (size_t)i * kT * kT;
+      if (tid < ni) {
+        double v = 0.0;
+        for (int r = tid; r < ni; ++r) v += linv[r + tid * kT] * g[r];
+        xi[tid] = v;
+        fd.ywork[fd.f_piv[s] + ri + tid] = v;
+      }
+      __syncthreads();
     }
-    __syncthreads();
-    // x = L_kk^-T g
-    const double* linv = ld.linv + lf.linv_off + (size_t)kt * kT * kT;
-    if (tid < nb) {
-      double v = 0.0;
-      for (int r = tid; r < nb; ++r) v += linv[r + tid * kT] * gt[r];
-      f[c0 + tid] = v;
+    // contributions of row i to the pivot tiles k < min(i, wt), nearest first
+    for (int k = min(i, wt) - 1; k >= 0; --k) {
+      double* out = contrib + ((size_t)k * nt + i) * kT;
+      tile_gemv_t(L + ri + (size_t)(k * kT) * m, m, ni, tile_size(lf, k), xi, out);
+      __syncthreads();
+      if (tid == 0) {
+        __threadfence();
+        atomicAdd(cntb + k, 1);
+      }
     }
-    __syncthreads();
   }
-  for (int r = tid; r < w; r += nt) fd.ywork[fd.f_piv[s] + r] = f[r];
 }
 
 void launch_large_solve_fwd(cudaStream_t st, const Ctrl* ctrl, const FrontDev& fd, const LargeDev& ld,
                             const LargeLevel& lv, const double* rhs_static, StatePtrs sp, int use_state_rhs) {
   if (lv.n_lf == 0) return;
-  const size_t smem = (size_t)(lv.max_m + 64) * sizeof(double);
-  large_solve_fwd_kernel<<<lv.n_lf, 256, smem, st>>>(ctrl, fd, ld, rhs_static, sp, use_state_rhs, lv.lf0); ++g_launches;
+  const int P = lv.solve_p;
+  const size_t smem = (size_t)(((lv.max_nt + P - 1) / P) * kT + kT + 256) * sizeof(double);
+  large_solve_fwd_kernel<<<lv.n_lf * P, 256, smem, st>>>(ctrl, fd, ld, rhs_static, sp, use_state_rhs, lv.lf0, P);
+  ++g_launches;
 }
 void launch_large_solve_bwd(cudaStream_t st, const Ctrl* ctrl, const FrontDev& fd, const LargeDev& ld,
                             const LargeLevel& lv) {
   if (lv.n_lf == 0) return;
-  const size_t smem = (size_t)(lv.max_m + 64) * sizeof(double);
-  large_solve_bwd_kernel<<<lv.n_lf, 256, smem, st>>>(ctrl, fd, ld, lv.lf0); ++g_launches;
+  const int P = lv.solve_p;
+  large_solve_bwd_kernel<<<lv.n_lf * P, 256, 3 * kT * sizeof(double), st>>>(ctrl, fd, ld, lv.lf0, P);
+  ++g_launches;
 }
 
 }  // namespace sfx

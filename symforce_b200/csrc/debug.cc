@@ -137,3 +137,34 @@ extern "C" int sfx_debug_analysis_json(const sfx_problem_desc* d, char** out) {
     return 1;
   }
 }
+
+// Per-front summary (level, w, u) of the multifrontal plan as text; cheap even for large problems.
+extern "C" int sfx_debug_front_summary(const sfx_problem_desc* d, char** out) {
+  using namespace sfx;
+  static thread_local std::string buf;
+  try {
+    Analysis a;
+    analyze_problem(*d, a);
+    const BlockMatrix& sys = a.schur ? a.sp.S : a.H;
+    std::vector<int> sys2ref;
+    if (d->ordering == SFX_ORDERING_METIS_SCALAR) {
+      std::vector<int> int2ref(a.N);
+      for (int r = 0; r < a.N; ++r) int2ref[a.ref2int[r]] = r;
+      sys2ref.assign(int2ref.begin(), int2ref.begin() + sys.node_off[sys.n_nodes]);
+    }
+    build_front_plan(sys, d->ordering, sys2ref, a.fp);
+    std::ostringstream o;
+    o << "n=" << a.fp.n << " fronts=" << a.fp.n_fronts << " levels=" << a.fp.n_levels << " nnzL=" << a.fp.nnz_L
+      << " flops=" << a.fp.flops << " sblocks=" << (a.schur ? a.sp.S.row_idx.size() : 0)
+      << " matches=" << (a.schur ? a.sp.m_lm.size() : 0) << "\n";
+    for (int s = 0; s < a.fp.n_fronts; ++s)
+      o << a.fp.f_level[s] << " " << a.fp.f_w[s] << " " << a.fp.f_u[s] << " " << a.fp.f_parent[s] << "\n";
+    buf = o.str();
+    *out = const_cast<char*>(buf.c_str());
+    return 0;
+  } catch (const std::exception& e) {
+    buf = e.what();
+    *out = const_cast<char*>(buf.c_str());
+    return 1;
+  }
+}

@@ -103,6 +103,9 @@ struct LargeFront {
   int wt, nt;        // pivot tiles, total tiles
   int cnt_off;       // offset of the nt*nt tile version counters
   int front;         // front id
+  int flag_off;      // solve flags: [wt] forward published, [wt] backward contribution counters
+  int pad;
+  int64_t contrib_off;  // backward-solve contribution slots: wt * nt * 64 doubles
 };
 struct LargeTask {
   int lf;
@@ -116,6 +119,8 @@ struct LargeLevel {
   int t0, t1;      // task range
   int j0, j1;      // assembly job range
   int max_m;
+  int max_nt;
+  int solve_p;     // CTAs per front in the cooperative solves (grid = n_lf * solve_p <= #SMs)
 };
 struct LargeDev {
   const LargeFront* lf;
@@ -124,6 +129,8 @@ struct LargeDev {
   int* counters;
   int* queue;  // one head per level
   double* linv;
+  int* sflags;      // solve flags / counters (zeroed before every solve)
+  double* contrib;  // backward-solve contribution slots
 };
 void launch_large_level(cudaStream_t st, Ctrl* ctrl, const FrontDev& fd, const LargeDev& ld, const LargeLevel& lv,
                         int level, const double* sys_static, StatePtrs sp, int use_state_H, const double* dvec);

@@ -84,7 +84,7 @@ struct sfx_problem {
   std::vector<int> lvl_small_cnt;  // small fronts per level (listed first in level_fronts)
   std::vector<LargeLevel> lvl_large;
   LargeDev ld{};
-  int64_t n_counters = 0;
+  int64_t n_counters = 0, n_sflags = 0;
   int small_max_m = 64;  // fronts with more rows go to the tile-DAG path
   int smem_cap_m = 168;
   // csc export
@@ -288,7 +288,7 @@ void upload_structures(sfx_problem* p) {
     std::vector<LargeFront> lfs;
     std::vector<LargeTask> tasks;
     std::vector<LargeJob> jobs;
-    int64_t linv_off = 0, cnt_off = 0;
+    int64_t linv_off = 0, cnt_off = 0, flag_off = 0, contrib_off = 0;
     for (int l = 0; l < f.n_levels; ++l) {
       int* b = lvl_fronts.data() + f.level_ptr[l];
       int* e = lvl_fronts.data() + f.level_ptr[l + 1];
@@ -302,6 +302,7 @@ void upload_structures(sfx_problem* p) {
       lv.t0 = (int)tasks.size();
       lv.j0 = (int)jobs.size();
       lv.max_m = 0;
+      lv.max_nt = 0;
       int max_wt = 0;
       for (int* q = mid; q < e; ++q) {
         const int s = *q;
@@ -314,6 +315,11 @@ void upload_structures(sfx_problem* p) {
         x.linv_off = linv_off;
         x.cnt_off = (int)cnt_off;
         x.front = s;
+        x.flag_off = (int)flag_off;
+        x.contrib_off = contrib_off;
+        flag_off += 2 * x.wt;
+        contrib_off += (int64_t)x.wt * x.nt * T;
+        lv.max_nt = std::max(lv.max_nt, x.nt);
         linv_off += (int64_t)x.wt * T * T;
         cnt_off += (int64_t)x.nt * x.nt;
         SFX_CHECK(cnt_off < (int64_t)INT32_MAX, SFX_ERR_UNSUPPORTED, "too many tiles");
@@ -340,25 +346,49 @@ void upload_structures(sfx_problem* p) {
           }
         }
       }
-      // tasks, ordered so that every dependency precedes its consumer (see chol_large.cu)
-      for (int k = 0; k < max_wt; ++k)
-        for (int li = lv.lf0; li < lv.lf0 + lv.n_lf; ++li) {
+      // tasks: per front in an order that keeps every dependency earlier in the list (see
+      // chol_large.cu), then merged round-robin across the fronts of the level so that the window
+      // of tasks in flight always spans all fronts (one front's critical path hides behind the
+      // others' trailing updates)
+      {
+        std::vector<std::vector<LargeTask>> per(lv.n_lf);
+        for (int q = 0; q < lv.n_lf; ++q) {
+          const int li = lv.lf0 + q;
           const LargeFront& x = lfs[li];
-          if (k >= x.wt) continue;
-          tasks.push_back(LargeTask{li, 0, (short)k, (short)k, (short)k});
-          if (k + 1 < x.nt) {
-            tasks.push_back(LargeTask{li, 1, (short)k, (short)(k + 1), (short)k});
-            tasks.push_back(LargeTask{li, 2, (short)k, (short)(k + 1), (short)(k + 1)});
-          }
-          for (int i = k + 2; i < x.nt; ++i) tasks.push_back(LargeTask{li, 1, (short)k, (short)i, (short)k});
-          for (int j = k + 1; j < x.nt; ++j)
-            for (int i = j; i < x.nt; ++i) {
-              if (i == k + 1 && j == k + 1) continue;
-              tasks.push_back(LargeTask{li, 2, (short)k, (short)i, (short)j});
+          auto& tl = per[q];
+          for (int k = 0; k < x.wt; ++k) {
+            tl.push_back(LargeTask{li, 0, (short)k, (short)k, (short)k});
+            if (k + 1 < x.nt) {
+              tl.push_back(LargeTask{li, 1, (short)k, (short)(k + 1), (short)k});
+              tl.push_back(LargeTask{li, 2, (short)k, (short)(k + 1), (short)(k + 1)});
             }
+            for (int i = k + 2; i < x.nt; ++i) tl.push_back(LargeTask{li, 1, (short)k, (short)i, (short)k});
+            for (int j = k + 1; j < x.nt; ++j)
+              for (int i = j; i < x.nt; ++i) {
+                if (i == k + 1 && j == k + 1) continue;
+                tl.push_back(LargeTask{li, 2, (short)k, (short)i, (short)j});
+              }
+          }
         }
+        // proportional round-robin: fronts advance at a rate proportional to their task count
+        std::vector<size_t> pos(lv.n_lf, 0);
+        size_t total = 0, longest = 0;
+        for (auto& tl : per) {
+          total += tl.size();
+          longest = std::max(longest, tl.size());
+        }
+        for (size_t step = 0; step < longest; ++step)
+          for (int q = 0; q < lv.n_lf; ++q) {
+            const size_t upto = (size_t)((double)(step + 1) * per[q].size() / longest);
+            while (pos[q] < upto && pos[q] < per[q].size()) tasks.push_back(per[q][pos[q]++]);
+          }
+        for (int q = 0; q < lv.n_lf; ++q)
+          while (pos[q] < per[q].size()) tasks.push_back(per[q][pos[q]++]);
+        (void)total;
+      }
       lv.t1 = (int)tasks.size();
       lv.j1 = (int)jobs.size();
+      lv.solve_p = lv.n_lf > 0 ? std::max(1, std::min(lv.max_nt, 144 / lv.n_lf)) : 1;
     }
     d.level_fronts = up32(lvl_fronts);
     p->ld.lf = P.upload(lfs);
@@ -368,6 +398,9 @@ void upload_structures(sfx_problem* p) {
     p->ld.counters = P.alloc<int>(cnt_off);
     p->ld.queue = P.alloc<int>(f.n_levels);
     p->ld.linv = P.alloc<double>(linv_off);
+    p->n_sflags = flag_off;
+    p->ld.sflags = P.alloc<int>(flag_off);
+    p->ld.contrib = P.alloc<double>(contrib_off);
     CUDA_OK(configure_front_kernels(p->smem_cap_m, f.max_front));
     CUDA_OK(configure_large_kernels());
   }
@@ -416,6 +449,7 @@ void enqueue_solve(sfx_problem* p, const std::function<void(int)>& mark) {
     launch_large_level(p->st, p->d_ctrl, p->fd, p->ld, p->lvl_large[l], l, sys, p->sp, use_H, dv);
   }
   mark(PH_FACTOR);
+  if (p->n_sflags > 0) CUDA_OK(cudaMemsetAsync(p->ld.sflags, 0, sizeof(int) * p->n_sflags, p->st));
   const double* rhs_s = a.schur ? p->sd.rhs_red : nullptr;
   for (int l = 0; l < f.n_levels; ++l) {
     if (p->lvl_small_cnt[l] > 0)

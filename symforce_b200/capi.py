@@ -41,15 +41,45 @@ def load():
     return _lib
 
 
-def analysis_json(problem: D.Problem):
-    """Host-only structural analysis (no CUDA), for the CPU test-suite."""
+def analysis_json(problem: D.Problem, rank=0, world=1):
+    """Host-only structural analysis (no CUDA), for the CPU test-suite.  world > 1 analyses the
+    shard of `rank` (a dummy non-NULL communicator pointer enables sharding; it is never used)."""
     lib = load()
-    d, keep = problem.desc()
+    d, keep = problem.desc(rank=rank, world=world, comm=(1 if world > 1 else None))
     out = C.c_char_p()
     rc = lib.sfx_debug_analysis_json(C.byref(d), C.byref(out))
     if rc != 0:
         raise RuntimeError("analysis failed: " + out.value.decode())
     return json.loads(out.value.decode())
+
+
+class Comm:
+    """One NCCL communicator per rank (sfx_comm_*); the unique id travels over torch.distributed."""
+
+    def __init__(self, rank, world, device):
+        import torch
+        import torch.distributed as dist
+
+        self.lib = load()
+        ident = C.create_string_buffer(128)
+        if rank == 0:
+            rc = self.lib.sfx_comm_unique_id(ident)
+            if rc != 0:
+                raise RuntimeError("sfx_comm_unique_id failed: " + self.lib.sfx_last_error(None).decode())
+        t = torch.tensor(list(ident.raw), dtype=torch.uint8, device=f"cuda:{device}")
+        dist.broadcast(t, src=0)
+        ident = C.create_string_buffer(bytes(t.cpu().tolist()), 128)
+        h = C.c_void_p()
+        rc = self.lib.sfx_comm_create(ident, C.c_int32(rank), C.c_int32(world), C.c_int32(device), C.byref(h))
+        if rc != 0:
+            raise RuntimeError("sfx_comm_create failed: " + self.lib.sfx_last_error(None).decode())
+        self.h = h
+        self.rank, self.world, self.device = rank, world, device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.sfx_comm_destroy(self.h)
+            self.h = None
 
 
 class SfxProblem(D._LibProblem):
@@ -59,7 +89,7 @@ class SfxProblem(D._LibProblem):
         self.lib = load()
         self.problem = problem
         self.n_values = problem.values.shape[0]
-        d, keep = problem.desc(device=device, rank=rank, world=world, comm=comm)
+        d, keep = problem.desc(device=device, rank=rank, world=world, comm=(comm.h if comm is not None else None))
         self._keep = keep
         h = C.c_void_p()
         rc = self.lib.sfx_problem_create(C.byref(d), C.byref(h))

@@ -7,6 +7,7 @@
 #include <cstring>
 #include <map>
 #include <numeric>
+#include <type_traits>
 #include <unordered_map>
 
 #include "sfx_internal.h"
@@ -222,6 +223,61 @@ void analyze_problem(const sfx_problem_desc& d, Analysis& a) {
     plan_factors[plan].push_back(fref[fi]);
   }
 
+  // ---- multi-GPU: landmark ranges and factor ownership -----------------------------
+  // Landmarks are split into `world` contiguous ranges balanced on the Schur work k(k+1)/2; a
+  // factor belongs to the rank of its landmark (factors without landmark: rank 0).  Structure
+  // (blocks, S pattern, front plan) is built from ALL factors so that it is identical on every
+  // rank; only the slots, landmarks and matches of this rank are kept for the device.
+  a.rank = d.comm ? d.rank : 0;
+  a.world = d.comm ? d.world : 1;
+  SFX_CHECK(a.world >= 1 && a.rank >= 0 && a.rank < a.world, SFX_ERR_INVALID_ARG, "rank/world");
+  SFX_CHECK(a.world == 1 || a.schur, SFX_ERR_UNSUPPORTED,
+            "multi-GPU sharding needs the Schur solver (pose-graph problems run as replicas)");
+  std::vector<int> lm_rank_begin(a.world + 1, nk);
+  if (a.schur) {
+    double total_cost = 0;
+    for (int k = first_lm_key; k < nk; ++k) total_cost += 0.5 * cnt[k] * (cnt[k] + 1.0) + cnt[k];
+    double acc_cost = 0;
+    int r = 0;
+    lm_rank_begin[0] = first_lm_key;
+    for (int k = first_lm_key; k < nk; ++k) {
+      while (r + 1 < a.world && acc_cost >= total_cost * (r + 1) / a.world) lm_rank_begin[++r] = k;
+      acc_cost += 0.5 * cnt[k] * (cnt[k] + 1.0) + cnt[k];
+    }
+    while (r + 1 < a.world) lm_rank_begin[++r] = nk;
+    lm_rank_begin[a.world] = nk;
+  }
+  auto owner_of = [&](const FactorRef& fr) -> int {
+    if (a.world == 1) return 0;
+    const sfx_factor_batch& fb = d.batches[fr.batch];
+    const sfx_kind_meta& km = SFX_KIND_META[fb.kind];
+    for (int o = 0; o < km.n_opt; ++o) {
+      int key = fb.opt_keys[(int64_t)o * fb.n + fr.idx];
+      if (key >= first_lm_key) {
+        int r = (int)(std::upper_bound(lm_rank_begin.begin(), lm_rank_begin.end(), key) - lm_rank_begin.begin()) - 1;
+        return std::min(std::max(r, 0), a.world - 1);
+      }
+    }
+    return 0;
+  };
+  std::vector<std::vector<int>> plan_rank_begin(plan_factors.size(), std::vector<int>(a.world + 1, 0));
+  if (a.world > 1)
+    for (size_t pl = 0; pl < plan_factors.size(); ++pl) {
+      auto& v = plan_factors[pl];
+      std::vector<int> own(v.size());
+      for (size_t i = 0; i < v.size(); ++i) own[i] = owner_of(v[i]);
+      std::vector<size_t> idx(v.size());
+      std::iota(idx.begin(), idx.end(), (size_t)0);
+      std::stable_sort(idx.begin(), idx.end(), [&](size_t x, size_t y) { return own[x] < own[y]; });
+      std::vector<FactorRef> sorted(v.size());
+      for (size_t i = 0; i < v.size(); ++i) {
+        sorted[i] = v[idx[i]];
+        plan_rank_begin[pl][own[idx[i]] + 1]++;
+      }
+      for (int r = 0; r < a.world; ++r) plan_rank_begin[pl][r + 1] += plan_rank_begin[pl][r];
+      v.swap(sorted);
+    }
+
   // ---- Hessian blocks ---------------------------------------------------------------------------
   // contributions to off-diagonal blocks: (col node, row node) keyed, with (plan, slot, pair)
   struct Contrib {
@@ -340,24 +396,39 @@ void analyze_problem(const sfx_problem_desc& d, Analysis& a) {
                 "Submatrix C of A is not block diagonal, cannot use a Schur complement solver");
     }
   }
-  // value offsets: [diag blocks | shared off-diag blocks] accumulated, then exclusive blocks in
-  // (plan, slot, pair) order so that a thread's stores are contiguous
+  // value offsets: [reduced diag | all reduced-reduced off-diag] (= B, summed across ranks in the
+  // multi-GPU path) | landmark diag | shared landmark-reduced blocks || exclusive blocks in
+  // (plan, slot, pair) order so that a thread's stores are contiguous.  Everything before `||`
+  // is zeroed before each linearization.
   int64_t off = 0;
-  for (int j = 0; j < nn; ++j) {
+  for (int j = 0; j < first_lm_node; ++j) {
     H.blk_off[H.col_ptr[j]] = off;
     off += (int64_t)a.nodes[j].dim * a.nodes[j].dim;
   }
-  for (size_t b = 0; b < blk_key.size(); ++b)
-    if (blk_cnt[b] > 1) {
-      int col = (int)(blk_key[b] >> 32), row = (int)(blk_key[b] & 0xffffffffu);
+  for (size_t b = 0; b < blk_key.size(); ++b) {
+    int col = (int)(blk_key[b] >> 32), row = (int)(blk_key[b] & 0xffffffffu);
+    if (row < first_lm_node) {
       H.blk_off[offdiag_id[b]] = off;
       off += (int64_t)a.nodes[row].dim * a.nodes[col].dim;
     }
+  }
+  a.b_values = off;
+  for (int j = first_lm_node; j < nn; ++j) {
+    H.blk_off[H.col_ptr[j]] = off;
+    off += (int64_t)a.nodes[j].dim * a.nodes[j].dim;
+  }
+  for (size_t b = 0; b < blk_key.size(); ++b) {
+    int col = (int)(blk_key[b] >> 32), row = (int)(blk_key[b] & 0xffffffffu);
+    if (row >= first_lm_node && blk_cnt[b] > 1) {
+      H.blk_off[offdiag_id[b]] = off;
+      off += (int64_t)a.nodes[row].dim * a.nodes[col].dim;
+    }
+  }
   a.h_accum_values = off;
   for (size_t c = 0; c < contribs.size(); ++c) {  // contribs are in (plan, slot, pair) order
     int b = contrib_blk[c];
-    if (blk_cnt[b] == 1) {
-      int col = (int)(blk_key[b] >> 32), row = (int)(blk_key[b] & 0xffffffffu);
+    int col = (int)(blk_key[b] >> 32), row = (int)(blk_key[b] & 0xffffffffu);
+    if (row >= first_lm_node && blk_cnt[b] == 1) {
       H.blk_off[offdiag_id[b]] = off;
       off += (int64_t)a.nodes[row].dim * a.nodes[col].dim;
     }
@@ -374,13 +445,6 @@ void analyze_problem(const sfx_problem_desc& d, Analysis& a) {
     if (ct.transposed) v |= kOffTransposed;
     bp.off_off[(size_t)ct.pair * bp.n + ct.slot] = v;
   }
-  for (auto& bp : a.batches) {
-    for (int g = 0; g < bp.n_groups; ++g)
-      for (int s = 0; s < bp.n; ++s) {
-        // node of this group: recover from rhs_off (toff) -> search; cheaper: use diag offsets by node
-        // (filled below through a toff->node map)
-      }
-  }
   {
     std::unordered_map<int, int> toff2node;
     toff2node.reserve(nn * 2);
@@ -389,6 +453,28 @@ void analyze_problem(const sfx_problem_desc& d, Analysis& a) {
       for (size_t i = 0; i < bp.rhs_off.size(); ++i)
         bp.diag_off[i] = (int32_t)H.blk_off[H.col_ptr[toff2node[bp.rhs_off[i]]]];
   }
+  // keep only this rank's slots (contiguous thanks to the owner-sorted slot order)
+  if (a.world > 1)
+    for (size_t pl = 0; pl < a.batches.size(); ++pl) {
+      BatchPlan& bp = a.batches[pl];
+      const int s0 = plan_rank_begin[pl][a.rank], s1 = plan_rank_begin[pl][a.rank + 1];
+      const int n = bp.n, m = s1 - s0;
+      auto trim = [&](auto& v, int rows) {
+        typename std::remove_reference<decltype(v)>::type w((size_t)rows * m);
+        for (int r = 0; r < rows; ++r)
+          for (int q = 0; q < m; ++q) w[(size_t)r * m + q] = v[(size_t)r * n + s0 + q];
+        v.swap(w);
+      };
+      trim(bp.arg_off, bp.n_used_args);
+      trim(bp.res_off, 1);
+      trim(bp.rhs_off, bp.n_groups);
+      trim(bp.diag_off, bp.n_groups);
+      trim(bp.off_off, bp.n_groups * (bp.n_groups - 1) / 2);
+      trim(bp.factor_index, 1);
+      bp.n = m;
+    }
+  a.batches.erase(std::remove_if(a.batches.begin(), a.batches.end(), [](const BatchPlan& b) { return b.n == 0; }),
+                  a.batches.end());
   a.diag_pos.resize(a.N);
   for (int i = 0; i < nn; ++i) {
     const int dmn = a.nodes[i].dim;
@@ -399,62 +485,79 @@ void analyze_problem(const sfx_problem_desc& d, Analysis& a) {
   if (a.schur) {
     SchurPlan& sp = a.sp;
     sp.first_lm_node = first_lm_node;
-    sp.n_landmarks = nn - first_lm_node;
+    sp.n_landmarks_total = nn - first_lm_node;
+    // landmark nodes of this rank: [lm0, lm1) relative to first_lm_node
+    const int lm0 = a.keys[std::min(lm_rank_begin[a.rank], nk - 1)].node - first_lm_node +
+                    (lm_rank_begin[a.rank] >= nk ? 1 : 0);
+    const int lm1 = lm_rank_begin[a.rank + 1] >= nk ? sp.n_landmarks_total
+                                                    : a.keys[lm_rank_begin[a.rank + 1]].node - first_lm_node;
+    sp.lm_begin = lm0;
+    sp.n_landmarks = std::max(0, lm1 - lm0);
     sp.reduced_dim = a.nodes[first_lm_node].toff;
-    const int nl = sp.n_landmarks, nr = first_lm_node;
+    const int nl = sp.n_landmarks, nr = first_lm_node, nlt = sp.n_landmarks_total;
     sp.lm_dim.resize(nl);
     sp.lm_cdiag_off.resize(nl);
     sp.lm_toff.resize(nl);
-    sp.lm_e_ptr.assign(nl + 1, 0);
     for (int l = 0; l < nl; ++l) {
-      int node = first_lm_node + l;
+      int node = first_lm_node + lm0 + l;
       sp.lm_dim[l] = a.nodes[node].dim;
       sp.lm_cdiag_off[l] = (int32_t)H.blk_off[H.col_ptr[node]];
       sp.lm_toff[l] = a.nodes[node].toff;
     }
-    // E blocks: blocks (row = landmark node, col = reduced node)
+    // E blocks of ALL landmarks (for the S pattern): blocks (row = landmark node, col = reduced node)
+    std::vector<int32_t> all_ptr(nlt + 1, 0), all_off, all_node;
     for (int j = 0; j < nr; ++j)
       for (int p = H.col_ptr[j] + 1; p < H.col_ptr[j + 1]; ++p)
-        if (H.row_idx[p] >= first_lm_node) sp.lm_e_ptr[H.row_idx[p] - first_lm_node + 1]++;
-    for (int l = 0; l < nl; ++l) sp.lm_e_ptr[l + 1] += sp.lm_e_ptr[l];
-    sp.lm_e_off.resize(sp.lm_e_ptr[nl]);
-    sp.lm_e_node.resize(sp.lm_e_ptr[nl]);
+        if (H.row_idx[p] >= first_lm_node) all_ptr[H.row_idx[p] - first_lm_node + 1]++;
+    for (int l = 0; l < nlt; ++l) all_ptr[l + 1] += all_ptr[l];
+    all_off.resize(all_ptr[nlt]);
+    all_node.resize(all_ptr[nlt]);
     {
-      std::vector<int> fill(sp.lm_e_ptr.begin(), sp.lm_e_ptr.end() - 1);
+      std::vector<int> fill(all_ptr.begin(), all_ptr.end() - 1);
       for (int j = 0; j < nr; ++j)  // increasing j -> each landmark's list sorted by node
         for (int p = H.col_ptr[j] + 1; p < H.col_ptr[j + 1]; ++p)
           if (H.row_idx[p] >= first_lm_node) {
             int l = H.row_idx[p] - first_lm_node;
-            sp.lm_e_off[fill[l]] = (int32_t)H.blk_off[p];
-            sp.lm_e_node[fill[l]] = j;
+            all_off[fill[l]] = (int32_t)H.blk_off[p];
+            all_node[fill[l]] = j;
             fill[l]++;
           }
     }
-    // reduced rhs lists (per reduced node: E blocks of its column)
+    sp.lm_e_ptr.assign(nl + 1, 0);
+    for (int l = 0; l < nl; ++l) sp.lm_e_ptr[l + 1] = sp.lm_e_ptr[l] + (all_ptr[lm0 + l + 1] - all_ptr[lm0 + l]);
+    sp.lm_e_off.assign(all_off.begin() + all_ptr[lm0], all_off.begin() + all_ptr[lm0 + nl]);
+    sp.lm_e_node.assign(all_node.begin() + all_ptr[lm0], all_node.begin() + all_ptr[lm0 + nl]);
+    // reduced rhs lists (per reduced node: E blocks of its column that belong to own landmarks)
     sp.r_ptr.assign(nr + 1, 0);
     for (int j = 0; j < nr; ++j) {
       int c = 0;
-      for (int p = H.col_ptr[j] + 1; p < H.col_ptr[j + 1]; ++p)
-        if (H.row_idx[p] >= first_lm_node) c++;
+      for (int p = H.col_ptr[j] + 1; p < H.col_ptr[j + 1]; ++p) {
+        int l = H.row_idx[p] - first_lm_node - lm0;
+        if (H.row_idx[p] >= first_lm_node && l >= 0 && l < nl) c++;
+      }
       sp.r_ptr[j + 1] = sp.r_ptr[j] + c;
     }
     sp.r_eoff.resize(sp.r_ptr[nr]);
     sp.r_lm.resize(sp.r_ptr[nr]);
     for (int j = 0; j < nr; ++j) {
       int q = sp.r_ptr[j];
-      for (int p = H.col_ptr[j] + 1; p < H.col_ptr[j + 1]; ++p)
-        if (H.row_idx[p] >= first_lm_node) {
+      for (int p = H.col_ptr[j] + 1; p < H.col_ptr[j + 1]; ++p) {
+        int l = H.row_idx[p] - first_lm_node - lm0;
+        if (H.row_idx[p] >= first_lm_node && l >= 0 && l < nl) {
           sp.r_eoff[q] = (int32_t)H.blk_off[p];
-          sp.r_lm[q] = H.row_idx[p] - first_lm_node;
+          sp.r_lm[q] = l;
           q++;
         }
+      }
     }
-    // S pattern: B blocks + all pairs (I >= J) of reduced nodes adjacent to a common landmark
+    // S pattern: B blocks + all pairs (I >= J) of reduced nodes adjacent to a common landmark (ANY
+    // rank's landmark, so the pattern is the same everywhere); matches only for own landmarks
     struct Match {
       uint64_t key;  // (col J << 32) | row I
       int32_t ei, ej, lm;
     };
     std::vector<Match> matches;
+    std::vector<uint64_t> skeys;
     {
       int64_t cnt_m = 0;
       for (int l = 0; l < nl; ++l) {
@@ -463,15 +566,23 @@ void analyze_problem(const sfx_problem_desc& d, Analysis& a) {
       }
       matches.reserve(cnt_m);
     }
-    for (int l = 0; l < nl; ++l)
-      for (int q = sp.lm_e_ptr[l]; q < sp.lm_e_ptr[l + 1]; ++q)
-        for (int p = q; p < sp.lm_e_ptr[l + 1]; ++p)  // node[p] >= node[q]
-          matches.push_back(Match{((uint64_t)sp.lm_e_node[q] << 32) | (uint32_t)sp.lm_e_node[p], sp.lm_e_off[p],
-                                  sp.lm_e_off[q], l});
+    for (int l = 0; l < nlt; ++l) {
+      const bool own = l >= lm0 && l < lm0 + nl;
+      for (int q = all_ptr[l]; q < all_ptr[l + 1]; ++q)
+        for (int p = q; p < all_ptr[l + 1]; ++p) {  // node[p] >= node[q]
+          const uint64_t key = ((uint64_t)all_node[q] << 32) | (uint32_t)all_node[p];
+          if (own)
+            matches.push_back(Match{key, all_off[p], all_off[q], l - lm0});
+          else
+            skeys.push_back(key);
+        }
+      if (!own && skeys.size() > (size_t)(1 << 24)) {  // keep the temporary bounded
+        std::sort(skeys.begin(), skeys.end());
+        skeys.erase(std::unique(skeys.begin(), skeys.end()), skeys.end());
+      }
+    }
     std::stable_sort(matches.begin(), matches.end(), [](const Match& x, const Match& y) { return x.key < y.key; });
     // merged column structure
-    std::vector<uint64_t> skeys;
-    skeys.reserve(matches.size() / 4 + nr);
     for (int j = 0; j < nr; ++j)
       for (int p = H.col_ptr[j]; p < H.col_ptr[j + 1]; ++p)
         if (H.row_idx[p] < first_lm_node) skeys.push_back(((uint64_t)j << 32) | (uint32_t)H.row_idx[p]);

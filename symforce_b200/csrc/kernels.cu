@@ -444,10 +444,69 @@ __global__ void finish_error_kernel(Ctrl* ctrl, const double* __restrict__ parti
   double v = 0;
   for (int i = threadIdx.x; i < n; i += 1024) v += partials[i];
   const double tot = block_sum<1024>(v);
-  if (threadIdx.x == 0) {
-    ctrl->err[blk] = 0.5 * tot;
-    ctrl->lin_valid[blk] = 1;
+  if (threadIdx.x == 0) ctrl->red[0] = 0.5 * tot;  // this rank's part; committed by commit_error_kernel
+}
+
+// err[target] = (all-reduced) red[0]; marks the linearization valid
+__global__ void commit_error_kernel(Ctrl* ctrl, int mode) {
+  if (ctrl->done) return;
+  const int blk = sel_block(ctrl, mode);
+  if (mode == 0 && ctrl->lin_valid[blk]) return;
+  ctrl->err[blk] = ctrl->red[0];
+  ctrl->lin_valid[blk] = 1;
+}
+
+// multi-GPU: pack [B blocks | reduced rhs | red[0]] of the target block into a staging buffer for
+// one ncclAllReduce, and unpack afterwards
+__global__ void pack_b_kernel(Ctrl* ctrl, StatePtrs sp, int mode, int64_t nb, int nr, double* __restrict__ stage,
+                              int unpack) {
+  if (ctrl->done) return;
+  const int blk = sel_block(ctrl, mode);
+  if (mode == 0 && ctrl->lin_valid[blk]) return;
+  double* H = sp.H[blk];
+  double* rhs = sp.rhs[blk];
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  for (int64_t i = tid; i < nb; i += stride) {
+    if (unpack)
+      H[i] = stage[i];
+    else
+      stage[i] = H[i];
   }
+  for (int64_t i = tid; i < nr; i += stride) {
+    if (unpack)
+      rhs[i] = stage[nb + i];
+    else
+      stage[nb + i] = rhs[i];
+  }
+  if (tid == 0) {
+    if (unpack)
+      ctrl->red[0] = stage[nb + nr];
+    else
+      stage[nb + nr] = ctrl->red[0];
+  }
+}
+void launch_pack_b(cudaStream_t st, Ctrl* ctrl, StatePtrs sp, int mode, int64_t nb, int nr, double* stage, int unpack) {
+  int grid = (int)((nb + nr + 255) / 256);
+  if (grid > 148 * 4) grid = 148 * 4;
+  if (grid < 1) grid = 1;
+  pack_b_kernel<<<grid, 256, 0, st>>>(ctrl, sp, mode, nb, nr, stage, unpack); ++g_launches;
+}
+void launch_commit_error(cudaStream_t st, Ctrl* ctrl, int mode) {
+  commit_error_kernel<<<1, 1, 0, st>>>(ctrl, mode); ++g_launches;
+}
+
+// stage[i] = mask[i] ? v[i] : 0  (gather of the sharded landmark values at the end of Optimize)
+__global__ void mask_values_kernel(const double* __restrict__ v, const unsigned char* __restrict__ mask, int64_t n,
+                                   double* __restrict__ out) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = mask[i] ? v[i] : 0.0;
+}
+void launch_mask_values(cudaStream_t st, const double* v, const unsigned char* mask, int64_t n, double* out) {
+  int grid = (int)((n + 255) / 256);
+  if (grid > 148 * 8) grid = 148 * 8;
+  if (grid < 1) grid = 1;
+  mask_values_kernel<<<grid, 256, 0, st>>>(v, mask, n, out); ++g_launches;
 }
 
 void launch_zero_lin(cudaStream_t st, const Ctrl* ctrl, StatePtrs sp, int mode, int64_t n_h, int n_rhs) {
@@ -618,6 +677,7 @@ __global__ void schur_cinv_kernel(const Ctrl* __restrict__ ctrl, StatePtrs sp, S
 constexpr int kSchurWarps = 4;
 __global__ void __launch_bounds__(kSchurWarps * 32) schur_s_kernel(const Ctrl* __restrict__ ctrl, StatePtrs sp,
                                                                    SchurDev sd, const double* __restrict__ dvec) {
+  // sd.add_b == 0 (ranks > 0 of a sharded run): B and the damping are contributed by rank 0 only
   if (ctrl->done) return;
   __shared__ double sh[kSchurWarps][3 * 16 * 2 + 3 * 16 + 9];
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -625,7 +685,7 @@ __global__ void __launch_bounds__(kSchurWarps * 32) schur_s_kernel(const Ctrl* _
   if (item >= sd.n_items) return;
   const int b = sd.item_blk[item];
   const int m0 = sd.item_m0[item], m1 = m0 + sd.item_cnt[item];
-  const int first = sd.item_flags[item] & 1, single = (sd.item_flags[item] >> 1) & 1;
+  const int first = (sd.item_flags[item] & 1) && sd.add_b, single = (sd.item_flags[item] >> 1) & 1;
   const double* H = sp.H[ctrl->init_idx];
   const int I = sd.s_row[b], J = sd.s_col[b];
   const int dI = sd.node_dim[I], dJ = sd.node_dim[J];
@@ -719,7 +779,7 @@ __global__ void __launch_bounds__(128) schur_rhs_kernel(const Ctrl* __restrict__
   acc += __shfl_xor_sync(0xffffffffu, acc, 16);
   if (half == 0 && r < dI) {
     const int to = sd.node_toff[I];
-    sd.rhs_red[to + r] = rhs[to + r] - acc;
+    sd.rhs_red[to + r] = (sd.add_b ? rhs[to + r] : 0.0) - acc;
   }
 }
 
@@ -1064,11 +1124,11 @@ constexpr int kRedBlocks = 296;
 __global__ void __launch_bounds__(256) step_reduce_kernel(const Ctrl* __restrict__ ctrl, StatePtrs sp,
                                                           const double* __restrict__ upd, const double* __restrict__ dvec,
                                                           const double* __restrict__ last, int N,
-                                                          double* __restrict__ partials) {
+                                                          double* __restrict__ partials, int i0) {
   if (ctrl->done) return;
   const double* rhs = sp.rhs[ctrl->init_idx];
   double a = 0, b = 0, c = 0, d = 0;
-  for (int i = blockIdx.x * 256 + threadIdx.x; i < N; i += gridDim.x * 256) {
+  for (int i = i0 + blockIdx.x * 256 + threadIdx.x; i < N; i += gridDim.x * 256) {
     const double u = upd[i];
     a += u * (rhs[i] - dvec[i] * u);
     const double l = last[i];
@@ -1095,10 +1155,10 @@ __global__ void step_reduce_final_kernel(Ctrl* ctrl, const double* __restrict__ 
   ctrl->red[1 + q] = v;
 }
 void launch_step_reduce(cudaStream_t st, Ctrl* ctrl, StatePtrs sp, const double* upd, const double* dvec,
-                        const double* last_upd, int N, double* partials) {
+                        const double* last_upd, int N, double* partials, int i0) {
   int nb = (N + 255) / 256;
   if (nb > kRedBlocks) nb = kRedBlocks;
-  step_reduce_kernel<<<nb, 256, 0, st>>>(ctrl, sp, upd, dvec, last_upd, N, partials); ++g_launches;
+  step_reduce_kernel<<<nb, 256, 0, st>>>(ctrl, sp, upd, dvec, last_upd, N, partials, i0); ++g_launches;
   step_reduce_final_kernel<<<1, 4, 0, st>>>(ctrl, partials, nb); ++g_launches;
 }
 

@@ -58,6 +58,7 @@ struct LinBatch {
 
 struct SchurDev {
   int n_landmarks, n_reduced_nodes, reduced_dim;
+  int add_b;  // 1: this rank adds B, damping and the camera rhs (rank 0 / single GPU)
   const int32_t *lm_dim, *lm_cdiag_off, *lm_toff, *lm_e_ptr, *lm_e_off, *lm_e_node;
   const int32_t* node_toff;   // reduced node -> internal tangent offset
   const int32_t* node_dim;
@@ -161,7 +162,10 @@ void launch_retract(cudaStream_t st, const Ctrl* ctrl, StatePtrs sp, const int32
                     const int32_t* key_sdim, const int32_t* key_tdim, const int32_t* key_itoff, int n_keys,
                     const double* upd);
 void launch_step_reduce(cudaStream_t st, Ctrl* ctrl, StatePtrs sp, const double* upd, const double* dvec,
-                        const double* last_upd, int N, double* partials);
+                        const double* last_upd, int N, double* partials, int i0);
+void launch_pack_b(cudaStream_t st, Ctrl* ctrl, StatePtrs sp, int mode, int64_t nb, int nr, double* stage, int unpack);
+void launch_commit_error(cudaStream_t st, Ctrl* ctrl, int mode);
+void launch_mask_values(cudaStream_t st, const double* v, const unsigned char* mask, int64_t n, double* out);
 void launch_lm_begin(cudaStream_t st, Ctrl* ctrl);
 void launch_lm_after_first_linearize(cudaStream_t st, Ctrl* ctrl);
 void launch_lm_end(cudaStream_t st, Ctrl* ctrl, const double* upd, double* last_upd, int N, int* host_done);

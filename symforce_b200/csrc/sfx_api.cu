@@ -1,5 +1,7 @@
 // libsfx: problem object, device residency, LM driver and the C ABI of include/sfx.h.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>
 
 #include <algorithm>
 #include <chrono>
@@ -51,11 +53,61 @@ struct DevPool {
 
 enum Phase { PH_LIN = 0, PH_SCHUR, PH_FACTOR, PH_SOLVE, PH_UPDATE, PH_COUNT };
 
+// NCCL is resolved at run time (dlopen) so that libsfx.so has no link-time dependency on it and
+// shares the copy torch already loaded in a torchrun process.
+struct NcclApi {
+  void* h = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Reduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi& nccl() {
+  static NcclApi api;
+  if (!api.h) {
+    const char* names[] = {"libnccl.so.2", "libnccl.so"};
+    for (const char* n : names) {
+      api.h = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+      if (api.h) break;
+    }
+    if (!api.h) throw Error(SFX_ERR_NCCL, "cannot dlopen libnccl.so.2");
+    auto sym = [&](const char* n) {
+      void* f = dlsym(api.h, n);
+      if (!f) throw Error(SFX_ERR_NCCL, std::string("NCCL symbol missing: ") + n);
+      return f;
+    };
+    api.GetUniqueId = (decltype(api.GetUniqueId))sym("ncclGetUniqueId");
+    api.CommInitRank = (decltype(api.CommInitRank))sym("ncclCommInitRank");
+    api.CommDestroy = (decltype(api.CommDestroy))sym("ncclCommDestroy");
+    api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
+    api.Reduce = (decltype(api.Reduce))sym("ncclReduce");
+    api.Broadcast = (decltype(api.Broadcast))sym("ncclBroadcast");
+    api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
+  }
+  return api;
+}
+#define NCCL_OK(expr)                                                                          \
+  do {                                                                                         \
+    ncclResult_t r__ = (expr);                                                                 \
+    if (r__ != ncclSuccess) throw Error(SFX_ERR_NCCL, std::string(#expr) + ": " + nccl().GetErrorString(r__)); \
+  } while (0)
+
 }  // namespace sfx
 
 using namespace sfx;
 
+struct sfx_comm {
+  ncclComm_t comm = nullptr;
+  int rank = 0, world = 1, device = 0;
+};
+
 struct sfx_problem {
+  sfx_comm* comm = nullptr;  // not owned
+  double* d_stage = nullptr;        // multi-GPU staging: [B | reduced rhs | err] / masked values
+  unsigned char* d_vmask = nullptr; // which entries of the values buffer this rank contributes
   Analysis a;
   sfx_params params;
   double epsilon = 0;
@@ -180,18 +232,31 @@ void upload_structures(sfx_problem* p) {
   p->d_last = P.alloc<double>(a.N);
   p->d_y = P.alloc<double>(a.N);
   CUDA_OK(cudaMemset(p->d_last, 0, sizeof(double) * a.N));
+  CUDA_OK(cudaMemset(p->d_upd, 0, sizeof(double) * a.N));  // entries of other ranks' landmarks stay 0
+  if (a.world > 1) {
+    p->d_stage = P.alloc<double>(std::max<int64_t>(a.n_values, a.b_values + a.sp.reduced_dim + 1));
+    std::vector<unsigned char> mask(a.n_values, a.rank == 0 ? 1 : 0);
+    const int first_lm_key = (int)a.keys.size() - a.sp.n_landmarks_total;
+    for (int k = first_lm_key; k < (int)a.keys.size(); ++k) {
+      const int l = a.keys[k].node - a.sp.first_lm_node - a.sp.lm_begin;
+      const unsigned char own = (l >= 0 && l < a.sp.n_landmarks) ? 1 : 0;
+      for (int q = 0; q < a.keys[k].sdim; ++q) mask[a.keys[k].voff + q] = own;
+    }
+    p->d_vmask = P.upload(mask);
+  }
   CUDA_OK(cudaMemset(p->d_maxdiag, 0, sizeof(double) * a.N));
   p->d_ctrl = P.alloc<Ctrl>(1);
   CUDA_OK(cudaMallocHost(&p->h_ctrl, sizeof(Ctrl)));
-  CUDA_OK(cudaHostAlloc(&p->h_done, sizeof(int), cudaHostAllocMapped));
+  CUDA_OK(cudaHostAlloc(&p->h_done, sizeof(int) * (kMaxIterations + 2), cudaHostAllocMapped));
   CUDA_OK(cudaHostGetDevicePointer(&p->d_done, p->h_done, 0));
-  *p->h_done = 0;
+  std::memset(p->h_done, 0, sizeof(int) * (kMaxIterations + 2));
 
   // Schur
   if (a.schur) {
     SchurPlan& s = a.sp;
     SchurDev& d = p->sd;
     d.n_landmarks = s.n_landmarks;
+    d.add_b = a.rank == 0 ? 1 : 0;
     d.n_reduced_nodes = s.first_lm_node;
     d.reduced_dim = s.reduced_dim;
     d.lm_dim = P.upload(s.lm_dim);
@@ -419,13 +484,22 @@ void reset_ctrl(sfx_problem* p) {
   c->free_idx = 2;
   c->iteration = -1;
   CUDA_OK(cudaMemcpyAsync(p->d_ctrl, c, offsetof(Ctrl, iters), cudaMemcpyHostToDevice, p->st));
-  *p->h_done = 0;
+  std::memset(p->h_done, 0, sizeof(int) * (kMaxIterations + 2));
 }
 
 void enqueue_linearize(sfx_problem* p, int mode) {
   launch_zero_lin(p->st, p->d_ctrl, p->sp, mode, p->a.h_accum_values, p->a.N);
   for (auto& lb : p->lin) launch_linearize(p->st, p->d_ctrl, p->sp, mode, lb, p->d_partials);
   launch_finish_error(p->st, p->d_ctrl, mode, p->d_partials, p->n_partials);
+  if (p->a.world > 1) {
+    // one all-reduce per linearization: B blocks, camera rhs and the error partial
+    const int64_t nb = p->a.b_values;
+    const int nr = p->a.sp.reduced_dim;
+    launch_pack_b(p->st, p->d_ctrl, p->sp, mode, nb, nr, p->d_stage, 0);
+    NCCL_OK(nccl().AllReduce(p->d_stage, p->d_stage, (size_t)(nb + nr + 1), ncclDouble, ncclSum, p->comm->comm, p->st));
+    launch_pack_b(p->st, p->d_ctrl, p->sp, mode, nb, nr, p->d_stage, 1);
+  }
+  launch_commit_error(p->st, p->d_ctrl, mode);
 }
 
 // damping + [Schur] + factorize + solve -> d_upd (internal order) = -H_damped^-1 rhs
@@ -433,8 +507,23 @@ void enqueue_solve(sfx_problem* p, const std::function<void(int)>& mark) {
   Analysis& a = p->a;
   launch_damping(p->st, p->d_ctrl, p->sp, p->d_diag_pos, a.N, p->d_dvec, p->d_maxdiag);
   if (a.schur) launch_schur(p->st, p->d_ctrl, p->sp, p->sd, p->d_dvec);
+  const bool mg = a.world > 1;
+  if (mg) {
+    // the block-sparse S (identical pattern on every rank) and the reduced rhs are summed onto rank 0
+    NCCL_OK(nccl().Reduce(p->sd.S, p->sd.S, (size_t)a.sp.S.n_values, ncclDouble, ncclSum, 0, p->comm->comm, p->st));
+    NCCL_OK(nccl().Reduce(p->sd.rhs_red, p->sd.rhs_red, (size_t)a.sp.reduced_dim, ncclDouble, ncclSum, 0,
+                          p->comm->comm, p->st));
+  }
   mark(PH_SCHUR);
   const FrontPlan& f = a.fp;
+  if (mg && a.rank != 0) {
+    // rank 0 factors and solves; everyone receives the camera step
+    mark(PH_FACTOR);
+    NCCL_OK(nccl().Broadcast(p->d_y, p->d_y, (size_t)a.sp.reduced_dim, ncclDouble, 0, p->comm->comm, p->st));
+    launch_schur_back(p->st, p->d_ctrl, p->sp, p->sd, p->d_y, p->d_upd);
+    mark(PH_SOLVE);
+    return;
+  }
   const double* sys = a.schur ? p->sd.S : nullptr;
   const int use_H = a.schur ? 0 : 1;
   const double* dv = a.schur ? nullptr : p->d_dvec;
@@ -464,6 +553,7 @@ void enqueue_solve(sfx_problem* p, const std::function<void(int)>& mark) {
   }
   if (a.schur) {
     launch_unpermute(p->st, p->d_ctrl, p->fd, p->d_y, 1.0);
+    if (mg) NCCL_OK(nccl().Broadcast(p->d_y, p->d_y, (size_t)a.sp.reduced_dim, ncclDouble, 0, p->comm->comm, p->st));
     launch_schur_back(p->st, p->d_ctrl, p->sp, p->sd, p->d_y, p->d_upd);
   } else {
     launch_unpermute(p->st, p->d_ctrl, p->fd, p->d_upd, -1.0);
@@ -558,6 +648,12 @@ sfx_status sfx_problem_create(const sfx_problem_desc* desc, sfx_problem** out) {
   p->params = desc->params;
   p->epsilon = desc->epsilon;
   p->ordering = desc->ordering;
+  p->comm = (sfx_comm*)desc->comm;
+  if (p->comm) {
+    SFX_CHECK(p->comm->rank == desc->rank && p->comm->world == desc->world, SFX_ERR_INVALID_ARG,
+              "rank/world of the descriptor and the communicator differ");
+    SFX_CHECK(p->comm->device == desc->device, SFX_ERR_INVALID_ARG, "communicator was created for another device");
+  }
   analyze_problem(*desc, p->a);
   {
     Analysis& a = p->a;
@@ -634,8 +730,10 @@ sfx_status sfx_optimize(sfx_problem* p, int32_t num_iterations, sfx_stats* stats
   int enq = 0;
   for (int i = 0; i < num_iterations; ++i) {
     if (i >= 2) {  // bound the run-ahead; the device always has >= 1 iteration queued
+      // the status slot of iteration i-2 is written exactly once, by that iteration: every rank of a
+      // sharded run reads the same value here and enqueues the same collectives
       CUDA_OK(cudaEventSynchronize(p->ev[iter_end_ev[i - 2]]));
-      if (*(volatile int*)p->h_done) break;
+      if (((volatile int*)p->h_done)[i - 2]) break;
     }
     launch_lm_begin(p->st, p->d_ctrl);
     if (i == 0) {
@@ -649,8 +747,13 @@ sfx_status sfx_optimize(sfx_problem* p, int32_t num_iterations, sfx_stats* stats
     mark(PH_UPDATE);
     enqueue_linearize(p, /*mode=*/1);
     mark(PH_LIN);
-    launch_step_reduce(p->st, p->d_ctrl, p->sp, p->d_upd, p->d_dvec, p->d_last, a.N, p->d_partials);
-    launch_lm_end(p->st, p->d_ctrl, p->d_upd, p->d_last, a.N, p->d_done);
+    launch_step_reduce(p->st, p->d_ctrl, p->sp, p->d_upd, p->d_dvec, p->d_last, a.N, p->d_partials,
+                       (a.world > 1 && a.rank != 0) ? a.sp.reduced_dim : 0);
+    if (a.world > 1) {
+      double* red = (double*)((char*)p->d_ctrl + offsetof(Ctrl, red)) + 1;
+      NCCL_OK(nccl().AllReduce(red, red, 4, ncclDouble, ncclSum, p->comm->comm, p->st));
+    }
+    launch_lm_end(p->st, p->d_ctrl, p->d_upd, p->d_last, a.N, p->d_done + i);
     mark(PH_UPDATE);
     iter_end_ev.push_back(evi - 1);
     enq++;
@@ -699,8 +802,14 @@ sfx_status sfx_get_best_values(sfx_problem* p, double* values, int64_t n) {
   SFX_CHECK(n == p->a.n_values, SFX_ERR_INVALID_ARG, "values length mismatch");
   SFX_CHECK(p->h_ctrl->best_valid, SFX_ERR_INVALID_ARG, "SYM_ASSERT: state_.BestIsValid()");
   CUDA_OK(cudaSetDevice(p->device));
-  CUDA_OK(cudaMemcpyAsync(values, p->sp.values[p->h_ctrl->best_idx], sizeof(double) * n, cudaMemcpyDeviceToHost,
-                          p->st));
+  const double* src = p->sp.values[p->h_ctrl->best_idx];
+  if (p->a.world > 1) {
+    // every rank holds the cameras and its own landmarks: masked all-reduce assembles the full buffer
+    launch_mask_values(p->st, src, p->d_vmask, n, p->d_stage);
+    NCCL_OK(nccl().AllReduce(p->d_stage, p->d_stage, (size_t)n, ncclDouble, ncclSum, p->comm->comm, p->st));
+    src = p->d_stage;
+  }
+  CUDA_OK(cudaMemcpyAsync(values, src, sizeof(double) * n, cudaMemcpyDeviceToHost, p->st));
   CUDA_OK(cudaStreamSynchronize(p->st));
   SFX_API_END(p)
 }
@@ -816,19 +925,36 @@ sfx_status sfx_get_info(sfx_problem* p, int64_t* out, int32_t capacity) {
 }
 
 sfx_status sfx_comm_unique_id(char id_out[128]) {
-  (void)id_out;
-  g_create_err = "multi-GPU communicator not built yet";
-  return SFX_ERR_UNSUPPORTED;
+  sfx_problem* p = nullptr;
+  SFX_API_BEGIN
+  SFX_CHECK(id_out, SFX_ERR_INVALID_ARG, "null argument");
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId size");
+  ncclUniqueId id;
+  NCCL_OK(nccl().GetUniqueId(&id));
+  std::memcpy(id_out, &id, 128);
+  SFX_API_END(p)
 }
+
 sfx_status sfx_comm_create(const char id[128], int32_t rank, int32_t world, int32_t device, sfx_comm** out) {
-  (void)id;
-  (void)rank;
-  (void)world;
-  (void)device;
-  (void)out;
-  g_create_err = "multi-GPU communicator not built yet";
-  return SFX_ERR_UNSUPPORTED;
+  sfx_problem* p = nullptr;
+  SFX_API_BEGIN
+  SFX_CHECK(id && out && world >= 1 && rank >= 0 && rank < world, SFX_ERR_INVALID_ARG, "bad communicator arguments");
+  CUDA_OK(cudaSetDevice(device));
+  ncclUniqueId uid;
+  std::memcpy(&uid, id, 128);
+  std::unique_ptr<sfx_comm> c(new sfx_comm());
+  c->rank = rank;
+  c->world = world;
+  c->device = device;
+  NCCL_OK(nccl().CommInitRank(&c->comm, world, uid, rank));
+  *out = c.release();
+  SFX_API_END(p)
 }
-void sfx_comm_destroy(sfx_comm* c) { (void)c; }
+
+void sfx_comm_destroy(sfx_comm* c) {
+  if (!c) return;
+  if (c->comm) nccl().CommDestroy(c->comm);
+  delete c;
+}
 
 }  // extern "C"

@@ -81,7 +81,9 @@ constexpr uint32_t kOffTransposed = 0x40000000u; // node(g) < node(h): write the
 constexpr uint32_t kOffMask = 0x3fffffffu;
 
 struct SchurPlan {
-  int n_landmarks = 0;
+  int n_landmarks = 0;        // landmarks of THIS rank
+  int n_landmarks_total = 0;
+  int lm_begin = 0;           // first own landmark (relative to first_lm_node)
   int first_lm_node = 0;
   int reduced_dim = 0;  // scalar dim of the reduced system
   // per landmark
@@ -145,6 +147,8 @@ struct Analysis {
   std::vector<int> ref2int;   // reference tangent index -> internal tangent index
   BlockMatrix H;
   int64_t h_accum_values = 0; // prefix of H values that is accumulated (must be zeroed)
+  int64_t b_values = 0;       // prefix holding every block among reduced nodes (B); summed across ranks
+  int rank = 0, world = 1;
   std::vector<int32_t> diag_pos;  // per internal scalar: H value offset of its diagonal entry
   std::vector<BatchPlan> batches;
   bool schur = false;

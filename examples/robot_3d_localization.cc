@@ -1,0 +1,70 @@
+// robot_3d_localization on the GPU path, written against the sym:: API exactly like the reference
+// example (symforce/examples/robot_3d_localization/run_dynamic_size.cc:25-105, common.h:24-62).
+#include <cstdio>
+
+#include <sym/sym.h>
+
+#include "robot3d_data.inc"
+
+namespace Keys {
+static const sym::Key WORLD_T_BODY = 'w';
+static const sym::Key WORLD_T_LANDMARK = 'W';
+static const sym::Key ODOMETRY_DIAGONAL_SIGMAS = 'o';
+static const sym::Key ODOMETRY_RELATIVE_POSE_MEASUREMENTS = 'O';
+static const sym::Key MATCHING_SIGMA = 'm';
+static const sym::Key BODY_T_LANDMARK_MEASUREMENTS = 'b';
+static const sym::Key EPSILON = 'e';
+}  // namespace Keys
+
+static sym::Factord CreateMatchingFactor(int i, int j) {
+  return sym::Factord::Hessian(sym::MatchingFactor<double>,
+                               {Keys::WORLD_T_BODY.WithSuper(i), Keys::WORLD_T_LANDMARK.WithSuper(j),
+                                {Keys::BODY_T_LANDMARK_MEASUREMENTS.Letter(), i, j}, Keys::MATCHING_SIGMA},
+                               {Keys::WORLD_T_BODY.WithSuper(i)});
+}
+static sym::Factord CreateOdometryFactor(int i) {
+  return sym::Factord::Hessian(
+      sym::OdometryFactor<double>,
+      {Keys::WORLD_T_BODY.WithSuper(i), Keys::WORLD_T_BODY.WithSuper(i + 1),
+       Keys::ODOMETRY_RELATIVE_POSE_MEASUREMENTS.WithSuper(i), Keys::ODOMETRY_DIAGONAL_SIGMAS, Keys::EPSILON},
+      {Keys::WORLD_T_BODY.WithSuper(i), Keys::WORLD_T_BODY.WithSuper(i + 1)});
+}
+
+int main() {
+  sym::Valuesd values;
+  for (int i = 0; i < kNumPoses; i++) values.Set(Keys::WORLD_T_BODY.WithSuper(i), sym::Pose3d());
+  for (int i = 0; i < kNumLandmarks; i++)
+    values.Set(Keys::WORLD_T_LANDMARK.WithSuper(i), sym::Vector3d::FromData(kLandmarks + 3 * i));
+  values.Set(Keys::ODOMETRY_DIAGONAL_SIGMAS, sym::Vector6d(0.05, 0.05, 0.05, 0.2, 0.2, 0.2));
+  for (int i = 0; i < kNumPoses - 1; i++)
+    values.Set(Keys::ODOMETRY_RELATIVE_POSE_MEASUREMENTS.WithSuper(i), sym::Pose3d(sym::Vector7d::FromData(kOdometry + 7 * i)));
+  values.Set(Keys::MATCHING_SIGMA, 0.1);
+  for (int i = 0; i < kNumPoses; i++)
+    for (int j = 0; j < kNumLandmarks; j++)
+      values.Set({Keys::BODY_T_LANDMARK_MEASUREMENTS.Letter(), i, j},
+                 sym::Vector3d::FromData(kBodyTLandmark + 3 * (i * kNumLandmarks + j)));
+  values.Set(Keys::EPSILON, sym::kDefaultEpsilond);
+
+  std::vector<sym::Factord> factors;
+  for (int i = 0; i < kNumPoses; i++)
+    for (int j = 0; j < kNumLandmarks; j++) factors.push_back(CreateMatchingFactor(i, j));
+  for (int i = 0; i < kNumPoses - 1; i++) factors.push_back(CreateOdometryFactor(i));
+
+  sym::optimizer_params_t params = sym::DefaultOptimizerParams();
+  params.initial_lambda = 1e4;
+  params.lambda_down_factor = 1 / 2.;
+  sym::Optimizer<double> optimizer(params, factors, "Robot3DScanMatchingOptimizerDynamic");
+  const auto stats = optimizer.Optimize(values);
+
+  const auto& first_iter = stats.iterations.front();
+  const auto& last_iter = stats.iterations.back();
+  const auto& best_iter = stats.iterations[stats.best_index];
+  std::printf("Iterations: %d\nLambda: %.6g\nInitial error: %.10f\nFinal error: %.10f\nStatus: %d\n", last_iter.iteration,
+              last_iter.current_lambda, first_iter.new_error, best_iter.new_error, static_cast<int>(stats.status));
+  for (int i = 0; i < kNumPoses; i++) {
+    const auto p = values.At<sym::Pose3d>(Keys::WORLD_T_BODY.WithSuper(i));
+    std::printf("Pose %d: t = [%.6f %.6f %.6f]\n", i, p.Data()[4], p.Data()[5], p.Data()[6]);
+  }
+  // same acceptance check as test/symforce_examples_robot_3d_localization_test.py:49-51
+  return (stats.status == sym::optimization_status_t::SUCCESS && best_iter.new_error < 140) ? 0 : 1;
+}

@@ -1,0 +1,887 @@
+// sym:: header layer -- the reference's C++ surface for the sparse LM path, lowered onto the C ABI
+// of include/sfx.h (libsfx.so: CUDA sm_100a).  Same class / function names, argument meaning and
+// error behaviour as the reference for THIS path:
+//   sym::Key                         symforce/opt/key.h:26-103
+//   sym::Values<Scalar>              symforce/opt/values.h:31-324   (Set / At / Has / CreateIndex / Data ...)
+//   sym::Factor<Scalar>::Hessian     symforce/opt/factor.h:231-234  (function-pointer flavour)
+//   sym::optimizer_params_t, DefaultOptimizerParams()   lcmtypes/symforce.lcm:134-200, opt/optimizer.cc:8-56
+//   sym::OptimizationStats           symforce/opt/optimization_stats.h:22-94
+//   sym::Optimizer<Scalar>           symforce/opt/optimizer.h:72-325
+//   sym::Optimize(params, factors, values, eps)          symforce/opt/optimizer.h:334-340
+// What is different, by design: factors must be generated functions with a device implementation
+// (all of their inputs are Values keys); anything else is a std::runtime_error at Factor creation --
+// there is no CPU fallback.  `Optimize()` moves Values::Data() to the GPU, runs the whole LM loop
+// there and copies the best values + per-iteration stats back.
+#pragma once
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <limits>
+#include <map>
+#include <memory>
+#include <optional>
+#include <sstream>
+#include <stdexcept>
+#include <string>
+#include <unordered_map>
+#include <utility>
+#include <vector>
+
+#include "../sfx.h"
+#include "mini_eigen.h"
+
+// SYM_ASSERT -> std::runtime_error (symforce/opt/assert.h:40-92)
+#define SYM_ASSERT(expr, ...)                                                                   \
+  do {                                                                                          \
+    if (!(expr)) {                                                                              \
+      std::ostringstream o__;                                                                   \
+      o__ << "SYM_ASSERT: " #expr "\n    --> " << __func__ << "\n    --> " << __FILE__ << ":" << __LINE__; \
+      throw std::runtime_error(o__.str());                                                      \
+    }                                                                                           \
+  } while (0)
+
+namespace sym {
+
+template <typename Scalar>
+constexpr Scalar kDefaultEpsilon = Scalar(10) * std::numeric_limits<Scalar>::epsilon();  // sym/util/epsilon.h:31
+constexpr double kDefaultEpsilond = kDefaultEpsilon<double>;
+
+template <typename S>
+using Vector1 = Eigen::Matrix<S, 1, 1>;
+template <typename S>
+using Vector2 = Eigen::Matrix<S, 2, 1>;
+template <typename S>
+using Vector3 = Eigen::Matrix<S, 3, 1>;
+template <typename S>
+using Vector4 = Eigen::Matrix<S, 4, 1>;
+template <typename S>
+using Vector6 = Eigen::Matrix<S, 6, 1>;
+template <typename S>
+using Vector7 = Eigen::Matrix<S, 7, 1>;
+template <typename S>
+using Matrix33 = Eigen::Matrix<S, 3, 3>;
+template <typename S>
+using Matrix66 = Eigen::Matrix<S, 6, 6>;
+using Vector3d = Vector3<double>;
+using Vector6d = Vector6<double>;
+using Vector7d = Vector7<double>;
+using Matrix66d = Matrix66<double>;
+
+// ------------------------------------------------------------------------------------------------
+// Key (symforce/opt/key.h)
+// ------------------------------------------------------------------------------------------------
+class Key {
+ public:
+  using subscript_t = std::int64_t;
+  using superscript_t = std::int64_t;
+  static constexpr char kInvalidLetter = static_cast<char>(0);
+  static constexpr subscript_t kInvalidSub = std::numeric_limits<subscript_t>::min();
+  static constexpr superscript_t kInvalidSuper = std::numeric_limits<superscript_t>::min();
+
+  constexpr Key(const char letter, const subscript_t sub = kInvalidSub, const superscript_t super = kInvalidSuper)
+      : letter_(letter), sub_(sub), super_(super) {}
+  constexpr Key() = default;
+  constexpr char Letter() const { return letter_; }
+  constexpr subscript_t Sub() const { return sub_; }
+  constexpr superscript_t Super() const { return super_; }
+  constexpr Key WithLetter(const char letter) const { return Key(letter, sub_, super_); }
+  constexpr Key WithSub(const subscript_t sub) const { return Key(letter_, sub, super_); }
+  constexpr Key WithSuper(const superscript_t super) const { return Key(letter_, sub_, super); }
+  constexpr bool operator==(const Key& o) const { return letter_ == o.letter_ && sub_ == o.sub_ && super_ == o.super_; }
+  constexpr bool operator!=(const Key& o) const { return !(*this == o); }
+  // symforce/opt/key.cc:18-21
+  static bool LexicalLessThan(const Key& a, const Key& b) {
+    return std::make_tuple(a.Letter(), a.Sub(), a.Super()) < std::make_tuple(b.Letter(), b.Sub(), b.Super());
+  }
+  std::string str() const {
+    if (letter_ == kInvalidLetter) return "NULLKEY";
+    std::ostringstream os;
+    os << letter_;
+    if (sub_ != kInvalidSub) os << '_' << (sub_ < 0 ? "n" : "") << std::llabs(sub_);
+    if (super_ != kInvalidSuper) os << '_' << (super_ < 0 ? "n" : "") << std::llabs(super_);
+    return os.str();
+  }
+
+ private:
+  char letter_{kInvalidLetter};
+  subscript_t sub_{kInvalidSub};
+  superscript_t super_{kInvalidSuper};
+};
+struct KeyHash {
+  std::size_t operator()(const Key& k) const {
+    std::size_t h = std::hash<char>()(k.Letter());
+    h ^= std::hash<std::int64_t>()(k.Sub()) + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2);
+    h ^= std::hash<std::int64_t>()(k.Super()) + 0x9e3779b97f4a7c15ull + (h << 6) + (h >> 2);
+    return h;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Geo types needed by the path (storage + retract semantics live on the device; these are the
+// host-side value types of gen/cpp/sym/{rot3,pose3,linear_camera_cal}.h)
+// ------------------------------------------------------------------------------------------------
+template <typename Scalar>
+class Rot3 {
+ public:
+  using DataVec = Eigen::Matrix<Scalar, 4, 1>;
+  Rot3() { data_[3] = 1; }
+  explicit Rot3(const DataVec& d, bool normalize = true) : data_(d) {
+    if (normalize) Normalize();
+  }
+  static Rot3 Identity() { return Rot3(); }
+  // gen/cpp/sym/ops/rot3/lie_group_ops.cc:15-37
+  static Rot3 FromTangent(const Vector3<Scalar>& v, Scalar epsilon = kDefaultEpsilon<Scalar>) {
+    const Scalar t0 = std::sqrt(epsilon * epsilon + v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+    const Scalar t1 = Scalar(0.5) * t0, s = std::sin(t1) / t0;
+    DataVec d;
+    d[0] = s * v[0];
+    d[1] = s * v[1];
+    d[2] = s * v[2];
+    d[3] = std::cos(t1);
+    return Rot3(d);
+  }
+  Rot3 Compose(const Rot3& b) const {
+    const DataVec& a = data_;
+    DataVec r;
+    r[0] = a[3] * b.data_[0] + a[0] * b.data_[3] + a[1] * b.data_[2] - a[2] * b.data_[1];
+    r[1] = a[3] * b.data_[1] - a[0] * b.data_[2] + a[1] * b.data_[3] + a[2] * b.data_[0];
+    r[2] = a[3] * b.data_[2] + a[0] * b.data_[1] - a[1] * b.data_[0] + a[2] * b.data_[3];
+    r[3] = a[3] * b.data_[3] - a[0] * b.data_[0] - a[1] * b.data_[1] - a[2] * b.data_[2];
+    return Rot3(r);
+  }
+  Rot3 Retract(const Vector3<Scalar>& v, Scalar epsilon = kDefaultEpsilon<Scalar>) const {
+    return Compose(Rot3(FromTangent(v, epsilon).Data(), false));
+  }
+  Vector3<Scalar> Rotate(const Vector3<Scalar>& p) const {
+    const Scalar x = data_[0], y = data_[1], z = data_[2], w = data_[3];
+    const Scalar tx = 2 * (y * p[2] - z * p[1]), ty = 2 * (z * p[0] - x * p[2]), tz = 2 * (x * p[1] - y * p[0]);
+    Vector3<Scalar> r;
+    r[0] = p[0] + w * tx + (y * tz - z * ty);
+    r[1] = p[1] + w * ty + (z * tx - x * tz);
+    r[2] = p[2] + w * tz + (x * ty - y * tx);
+    return r;
+  }
+  const DataVec& Data() const { return data_; }
+
+ private:
+  void Normalize() {
+    const Scalar n2 = data_[0] * data_[0] + data_[1] * data_[1] + data_[2] * data_[2] + data_[3] * data_[3];
+    if (n2 > 0) {
+      const Scalar n = std::sqrt(n2);
+      for (int i = 0; i < 4; ++i) data_[i] /= n;
+    }
+  }
+  DataVec data_;
+};
+
+template <typename Scalar>
+class Pose3 {
+ public:
+  using DataVec = Eigen::Matrix<Scalar, 7, 1>;
+  Pose3() { data_[3] = 1; }
+  explicit Pose3(const DataVec& d, bool normalize = true) : data_(d) {
+    if (normalize) {
+      typename Rot3<Scalar>::DataVec q;
+      for (int i = 0; i < 4; ++i) q[i] = d[i];
+      Rot3<Scalar> r(q, true);
+      for (int i = 0; i < 4; ++i) data_[i] = r.Data()[i];
+    }
+  }
+  Pose3(const Rot3<Scalar>& R, const Vector3<Scalar>& t) {
+    for (int i = 0; i < 4; ++i) data_[i] = R.Data()[i];
+    for (int i = 0; i < 3; ++i) data_[4 + i] = t[i];
+  }
+  static Pose3 Identity() { return Pose3(); }
+  Rot3<Scalar> Rotation() const {
+    typename Rot3<Scalar>::DataVec q;
+    for (int i = 0; i < 4; ++i) q[i] = data_[i];
+    return Rot3<Scalar>(q, false);
+  }
+  Vector3<Scalar> Position() const {
+    Vector3<Scalar> t;
+    for (int i = 0; i < 3; ++i) t[i] = data_[4 + i];
+    return t;
+  }
+  // gen/cpp/sym/ops/pose3/lie_group_ops.cc:70-103: rotation retracts on the right, translation adds
+  Pose3 Retract(const Vector6<Scalar>& v, Scalar epsilon = kDefaultEpsilon<Scalar>) const {
+    Vector3<Scalar> w, t = Position();
+    for (int i = 0; i < 3; ++i) {
+      w[i] = v[i];
+      t[i] += v[3 + i];
+    }
+    return Pose3(Rotation().Retract(w, epsilon), t);
+  }
+  const DataVec& Data() const { return data_; }
+
+ private:
+  DataVec data_;
+};
+
+template <typename Scalar>
+class LinearCameraCal {
+ public:
+  using DataVec = Eigen::Matrix<Scalar, 4, 1>;
+  LinearCameraCal(const Vector2<Scalar>& focal, const Vector2<Scalar>& principal) {
+    data_[0] = focal[0];
+    data_[1] = focal[1];
+    data_[2] = principal[0];
+    data_[3] = principal[1];
+  }
+  explicit LinearCameraCal(const DataVec& d) : data_(d) {}
+  const DataVec& Data() const { return data_; }
+
+ private:
+  DataVec data_;
+};
+using Rot3d = Rot3<double>;
+using Pose3d = Pose3<double>;
+using LinearCameraCald = LinearCameraCal<double>;
+
+// ------------------------------------------------------------------------------------------------
+// Values (symforce/opt/values.h): flat insertion-ordered data + key -> index entry
+// ------------------------------------------------------------------------------------------------
+enum class type_t : int32_t { INVALID = 0, SCALAR, ROT3, POSE3, VECTOR, MATRIX, CAMERA_CAL };
+
+struct index_entry_t {
+  Key key;
+  type_t type{type_t::INVALID};
+  int32_t offset{0};
+  int32_t storage_dim{0};
+  int32_t tangent_dim{0};
+};
+struct index_t {
+  int32_t storage_dim{0};
+  int32_t tangent_dim{0};
+  std::vector<index_entry_t> entries;
+};
+
+namespace internal {
+template <typename T, typename = void>
+struct StorageTraits;  // storage pointer / dims / type of a value type
+template <>
+struct StorageTraits<double> {
+  static constexpr int kStorage = 1, kTangent = 1;
+  static constexpr type_t kType = type_t::SCALAR;
+  static const double* Ptr(const double& v) { return &v; }
+  static double From(const double* p) { return *p; }
+};
+template <typename S>
+struct StorageTraits<Rot3<S>> {
+  static constexpr int kStorage = 4, kTangent = 3;
+  static constexpr type_t kType = type_t::ROT3;
+  static const S* Ptr(const Rot3<S>& v) { return v.Data().data(); }
+  static Rot3<S> From(const S* p) { return Rot3<S>(Rot3<S>::DataVec::FromData(p), false); }
+};
+template <typename S>
+struct StorageTraits<Pose3<S>> {
+  static constexpr int kStorage = 7, kTangent = 6;
+  static constexpr type_t kType = type_t::POSE3;
+  static const S* Ptr(const Pose3<S>& v) { return v.Data().data(); }
+  static Pose3<S> From(const S* p) { return Pose3<S>(Pose3<S>::DataVec::FromData(p), false); }
+};
+template <typename S>
+struct StorageTraits<LinearCameraCal<S>> {
+  static constexpr int kStorage = 4, kTangent = 4;
+  static constexpr type_t kType = type_t::CAMERA_CAL;
+  static const S* Ptr(const LinearCameraCal<S>& v) { return v.Data().data(); }
+  static LinearCameraCal<S> From(const S* p) { return LinearCameraCal<S>(LinearCameraCal<S>::DataVec::FromData(p)); }
+};
+template <typename S, int R, int C>
+struct StorageTraits<Eigen::Matrix<S, R, C>> {
+  static constexpr int kStorage = R * C, kTangent = R * C;
+  static constexpr type_t kType = (C == 1) ? type_t::VECTOR : type_t::MATRIX;
+  static const S* Ptr(const Eigen::Matrix<S, R, C>& v) { return v.data(); }
+  static Eigen::Matrix<S, R, C> From(const S* p) { return Eigen::Matrix<S, R, C>::FromData(p); }
+};
+}  // namespace internal
+
+template <typename Scalar>
+class Values {
+ public:
+  using MapType = std::unordered_map<Key, index_entry_t, KeyHash>;
+
+  bool Has(const Key& key) const { return map_.find(key) != map_.end(); }
+
+  // Values::Set (values.tcc:60-100): new key appends, existing key overwrites (type must match)
+  template <typename T>
+  bool Set(const Key& key, const T& value) {
+    using Tr = internal::StorageTraits<T>;
+    auto it = map_.find(key);
+    if (it == map_.end()) {
+      index_entry_t e;
+      e.key = key;
+      e.type = Tr::kType;
+      e.offset = static_cast<int32_t>(data_.size());
+      e.storage_dim = Tr::kStorage;
+      e.tangent_dim = Tr::kTangent;
+      map_[key] = e;
+      data_.insert(data_.end(), Tr::Ptr(value), Tr::Ptr(value) + Tr::kStorage);
+      return true;
+    }
+    if (it->second.type != Tr::kType || it->second.storage_dim != Tr::kStorage)
+      throw std::runtime_error("Trying to set key " + key.str() + " with a different type than it was created with");
+    std::copy(Tr::Ptr(value), Tr::Ptr(value) + Tr::kStorage, data_.begin() + it->second.offset);
+    return false;
+  }
+  bool Set(const Key& key, const int value) { return Set<double>(key, static_cast<double>(value)); }
+
+  // Values::At (values.tcc:27-58): "Key not found" / type mismatch are std::runtime_error
+  template <typename T>
+  T At(const Key& key) const {
+    using Tr = internal::StorageTraits<T>;
+    const index_entry_t& e = IndexEntryAt(key);
+    if (e.type != Tr::kType || e.storage_dim != Tr::kStorage)
+      throw std::runtime_error("Mismatched types; index entry for key " + key.str() + " has a different type");
+    return Tr::From(data_.data() + e.offset);
+  }
+  const index_entry_t& IndexEntryAt(const Key& key) const {
+    auto it = map_.find(key);
+    if (it == map_.end()) throw std::runtime_error("Key not found: " + key.str());
+    return it->second;
+  }
+  // values.cc:210-234
+  index_t CreateIndex(const std::vector<Key>& keys) const {
+    index_t index;
+    for (const Key& key : keys) {
+      auto it = map_.find(key);
+      if (it == map_.end()) throw std::runtime_error("Tried to create index for key " + key.str() + " not in values");
+      index.entries.push_back(it->second);
+      index.storage_dim += it->second.storage_dim;
+      index.tangent_dim += it->second.tangent_dim;
+    }
+    return index;
+  }
+  size_t NumEntries() const { return map_.size(); }
+  const std::vector<Scalar>& Data() const { return data_; }
+  Scalar* DataPointer() { return data_.data(); }
+  const MapType& Items() const { return map_; }
+
+ private:
+  MapType map_;
+  std::vector<Scalar> data_;
+};
+using Valuesd = Values<double>;
+
+// ------------------------------------------------------------------------------------------------
+// Params / stats (lcmtypes/symforce.lcm)
+// ------------------------------------------------------------------------------------------------
+enum class lambda_update_type_t : int32_t { INVALID = 0, STATIC = 1, DYNAMIC = 2 };
+enum class optimization_status_t : int32_t { INVALID = 0, SUCCESS = 1, HIT_ITERATION_LIMIT = 2, FAILED = 3 };
+enum class levenberg_marquardt_solver_failure_reason_t : int32_t {
+  INVALID = 0,
+  LAMBDA_OUT_OF_BOUNDS = 1,
+  INITIAL_ERROR_NOT_FINITE = 2
+};
+
+struct optimizer_params_t {
+  bool verbose{false};
+  bool debug_stats{false};
+  bool check_derivatives{false};
+  bool include_jacobians{false};
+  bool debug_checks{false};
+  double initial_lambda{1.0};
+  double lambda_lower_bound{0.0};
+  double lambda_upper_bound{1000000.0};
+  lambda_update_type_t lambda_update_type{lambda_update_type_t::STATIC};
+  double lambda_up_factor{4.0};
+  double lambda_down_factor{0.25};
+  double dynamic_lambda_update_beta{2.0};
+  double dynamic_lambda_update_gamma{3.0};
+  int32_t dynamic_lambda_update_p{3};
+  bool use_diagonal_damping{false};
+  bool use_unit_damping{true};
+  bool keep_max_diagonal_damping{false};
+  double diagonal_damping_min{1e-6};
+  int32_t iterations{50};
+  double early_exit_min_reduction{1e-6};
+  double early_exit_min_absolute_error{0.0};
+  bool enable_bold_updates{false};
+};
+inline optimizer_params_t DefaultOptimizerParams() { return optimizer_params_t{}; }  // optimizer.cc:8-56
+
+struct optimization_iteration_t {
+  int16_t iteration{0};
+  double current_lambda{0};
+  double new_error_linear{0};
+  double new_error{0};
+  double relative_reduction{0};
+  bool update_accepted{false};
+  double update_angle_change{0};
+};
+
+// Linearization container (symforce/opt/linearization.h:27-77) with the CSC pieces the reference's
+// Eigen::SparseMatrix exposes (valuePtr / innerIndexPtr / outerIndexPtr / nonZeros / rows / cols)
+struct SparseMatrixCsc {
+  int rows_{0}, cols_{0};
+  std::vector<int32_t> outer, inner;
+  std::vector<double> values;
+  int rows() const { return rows_; }
+  int cols() const { return cols_; }
+  int64_t nonZeros() const { return static_cast<int64_t>(values.size()); }
+  const double* valuePtr() const { return values.data(); }
+  const int32_t* innerIndexPtr() const { return inner.data(); }
+  const int32_t* outerIndexPtr() const { return outer.data(); }
+};
+struct SparseLinearization {
+  std::vector<double> residual;
+  SparseMatrixCsc hessian_lower;
+  std::vector<double> rhs;
+  double Error() const {
+    double s = 0;
+    for (double r : residual) s += r * r;
+    return 0.5 * s;
+  }
+};
+
+struct OptimizationStats {
+  std::vector<optimization_iteration_t> iterations;
+  int32_t best_index{0};
+  optimization_status_t status{optimization_status_t::INVALID};
+  int32_t failure_reason{0};
+  std::optional<SparseLinearization> best_linearization{};
+};
+
+// ------------------------------------------------------------------------------------------------
+// Generated factor functions with a device implementation.  Host-side they are only *identities*:
+// Factor::Hessian recognises them by address.  When the reference's generated headers are also
+// included (real Eigen build) these are the same entities (matching redeclarations); otherwise the
+// definitions below stand in and refuse to run on the host.
+// ------------------------------------------------------------------------------------------------
+namespace internal {
+[[noreturn]] inline void DeviceOnly(const char* name) {
+  throw std::runtime_error(std::string(name) + " is evaluated on the GPU by sym::Optimizer; there is no host implementation");
+}
+}  // namespace internal
+
+#ifndef SFX_HAVE_REFERENCE_FACTOR_HEADERS
+template <typename Scalar>
+void SnavelyReprojectionFactor(const Pose3<Scalar>&, const Eigen::Matrix<Scalar, 3, 1>&, const Eigen::Matrix<Scalar, 3, 1>&,
+                               const Eigen::Matrix<Scalar, 2, 1>&, const Scalar, Eigen::Matrix<Scalar, 2, 1>* const = nullptr,
+                               Eigen::Matrix<Scalar, 2, 12>* const = nullptr, Eigen::Matrix<Scalar, 12, 12>* const = nullptr,
+                               Eigen::Matrix<Scalar, 12, 1>* const = nullptr) {
+  internal::DeviceOnly("SnavelyReprojectionFactor");
+}
+template <typename Scalar>
+void BetweenFactorPose3(const Pose3<Scalar>&, const Pose3<Scalar>&, const Pose3<Scalar>&, const Eigen::Matrix<Scalar, 6, 6>&,
+                        const Scalar, Eigen::Matrix<Scalar, 6, 1>* const = nullptr,
+                        Eigen::Matrix<Scalar, 6, 12>* const = nullptr, Eigen::Matrix<Scalar, 12, 12>* const = nullptr,
+                        Eigen::Matrix<Scalar, 12, 1>* const = nullptr) {
+  internal::DeviceOnly("BetweenFactorPose3");
+}
+template <typename Scalar>
+void PriorFactorPose3(const Pose3<Scalar>&, const Pose3<Scalar>&, const Eigen::Matrix<Scalar, 6, 6>&, const Scalar,
+                      Eigen::Matrix<Scalar, 6, 1>* const = nullptr, Eigen::Matrix<Scalar, 6, 6>* const = nullptr,
+                      Eigen::Matrix<Scalar, 6, 6>* const = nullptr, Eigen::Matrix<Scalar, 6, 1>* const = nullptr) {
+  internal::DeviceOnly("PriorFactorPose3");
+}
+template <typename Scalar>
+void MatchingFactor(const Pose3<Scalar>&, const Eigen::Matrix<Scalar, 3, 1>&, const Eigen::Matrix<Scalar, 3, 1>&,
+                    const Scalar, Eigen::Matrix<Scalar, 3, 1>* const = nullptr, Eigen::Matrix<Scalar, 3, 6>* const = nullptr,
+                    Eigen::Matrix<Scalar, 6, 6>* const = nullptr, Eigen::Matrix<Scalar, 6, 1>* const = nullptr) {
+  internal::DeviceOnly("MatchingFactor");
+}
+template <typename Scalar>
+void OdometryFactor(const Pose3<Scalar>&, const Pose3<Scalar>&, const Pose3<Scalar>&, const Eigen::Matrix<Scalar, 6, 1>&,
+                    const Scalar, Eigen::Matrix<Scalar, 6, 1>* const = nullptr, Eigen::Matrix<Scalar, 6, 12>* const = nullptr,
+                    Eigen::Matrix<Scalar, 12, 12>* const = nullptr, Eigen::Matrix<Scalar, 12, 1>* const = nullptr) {
+  internal::DeviceOnly("OdometryFactor");
+}
+template <typename Scalar>
+void InverseRangeLandmarkLinearGncFactor(const Pose3<Scalar>&, const LinearCameraCal<Scalar>&, const Pose3<Scalar>&,
+                                         const LinearCameraCal<Scalar>&, const Scalar, const Eigen::Matrix<Scalar, 2, 1>&,
+                                         const Eigen::Matrix<Scalar, 2, 1>&, const Scalar, const Scalar, const Scalar,
+                                         const Scalar, Eigen::Matrix<Scalar, 2, 1>* const = nullptr,
+                                         Eigen::Matrix<Scalar, 2, 13>* const = nullptr,
+                                         Eigen::Matrix<Scalar, 13, 13>* const = nullptr,
+                                         Eigen::Matrix<Scalar, 13, 1>* const = nullptr) {
+  internal::DeviceOnly("InverseRangeLandmarkLinearGncFactor");
+}
+template <typename Scalar>
+void InverseRangeLandmarkPriorFactor(const Scalar, const Scalar, const Scalar, const Scalar, const Scalar,
+                                     Eigen::Matrix<Scalar, 1, 1>* const = nullptr, Eigen::Matrix<Scalar, 1, 1>* const = nullptr,
+                                     Eigen::Matrix<Scalar, 1, 1>* const = nullptr, Eigen::Matrix<Scalar, 1, 1>* const = nullptr) {
+  internal::DeviceOnly("InverseRangeLandmarkPriorFactor");
+}
+template <typename Scalar>
+void BetweenFactorRot3(const Rot3<Scalar>&, const Rot3<Scalar>&, const Rot3<Scalar>&, const Eigen::Matrix<Scalar, 3, 3>&,
+                       const Scalar, Eigen::Matrix<Scalar, 3, 1>* const = nullptr, Eigen::Matrix<Scalar, 3, 6>* const = nullptr,
+                       Eigen::Matrix<Scalar, 6, 6>* const = nullptr, Eigen::Matrix<Scalar, 6, 1>* const = nullptr) {
+  internal::DeviceOnly("BetweenFactorRot3");
+}
+template <typename Scalar>
+void PriorFactorRot3(const Rot3<Scalar>&, const Rot3<Scalar>&, const Eigen::Matrix<Scalar, 3, 3>&, const Scalar,
+                     Eigen::Matrix<Scalar, 3, 1>* const = nullptr, Eigen::Matrix<Scalar, 3, 3>* const = nullptr,
+                     Eigen::Matrix<Scalar, 3, 3>* const = nullptr, Eigen::Matrix<Scalar, 3, 1>* const = nullptr) {
+  internal::DeviceOnly("PriorFactorRot3");
+}
+#endif
+
+// ------------------------------------------------------------------------------------------------
+// Factor (symforce/opt/factor.h)
+// ------------------------------------------------------------------------------------------------
+namespace internal {
+struct KindInfo {
+  int kind, n_args, n_opt;
+  int opt_args[3];
+};
+inline const std::unordered_map<const void*, KindInfo>& KindRegistry() {
+  static const std::unordered_map<const void*, KindInfo> reg = [] {
+    std::unordered_map<const void*, KindInfo> r;
+    auto add = [&](const void* f, KindInfo k) { r[f] = k; };
+    add(reinterpret_cast<const void*>(&SnavelyReprojectionFactor<double>), {SFX_KIND_SNAVELY, 5, 3, {0, 1, 2}});
+    add(reinterpret_cast<const void*>(&BetweenFactorPose3<double>), {SFX_KIND_BETWEEN_POSE3, 5, 2, {0, 1, -1}});
+    add(reinterpret_cast<const void*>(&PriorFactorPose3<double>), {SFX_KIND_PRIOR_POSE3, 4, 1, {0, -1, -1}});
+    add(reinterpret_cast<const void*>(&MatchingFactor<double>), {SFX_KIND_MATCHING, 4, 1, {0, -1, -1}});
+    add(reinterpret_cast<const void*>(&OdometryFactor<double>), {SFX_KIND_ODOMETRY, 5, 2, {0, 1, -1}});
+    add(reinterpret_cast<const void*>(&InverseRangeLandmarkLinearGncFactor<double>),
+        {SFX_KIND_IRL_LINEAR_GNC, 11, 3, {0, 2, 4}});
+    add(reinterpret_cast<const void*>(&InverseRangeLandmarkPriorFactor<double>), {SFX_KIND_IRL_PRIOR, 5, 1, {0, -1, -1}});
+    add(reinterpret_cast<const void*>(&BetweenFactorRot3<double>), {SFX_KIND_BETWEEN_ROT3, 5, 2, {0, 1, -1}});
+    add(reinterpret_cast<const void*>(&PriorFactorRot3<double>), {SFX_KIND_PRIOR_ROT3, 4, 1, {0, -1, -1}});
+    return r;
+  }();
+  return reg;
+}
+}  // namespace internal
+
+template <typename Scalar>
+class Factor {
+ public:
+  // Factor::Hessian(func, keys_to_func, keys_to_optimize) (factor.h:231-234).  `func` must be one
+  // of the generated functions with a device implementation (recognised by address).
+  template <typename Functor>
+  static Factor Hessian(Functor&& func, const std::vector<Key>& keys_to_func,
+                        const std::vector<Key>& keys_to_optimize = {}, bool /*requires_jacobian*/ = false) {
+    const void* addr = AddressOf(std::forward<Functor>(func));
+    const auto& reg = internal::KindRegistry();
+    auto it = addr ? reg.find(addr) : reg.end();
+    if (it == reg.end())
+      throw std::runtime_error(
+          "sym::Factor: this functor has no GPU implementation (only generated factor functions whose inputs are all "
+          "Values keys run on the device; there is no CPU fallback)");
+    Factor f;
+    f.kind_ = it->second.kind;
+    if (static_cast<int>(keys_to_func.size()) != it->second.n_args)
+      throw std::runtime_error("SYM_ASSERT: keys_to_func.size() == number of function arguments");
+    f.keys_ = keys_to_func;
+    // keys_to_optimize empty == all keys are optimized (factor.h:190-192); for generated
+    // linearization functions that means the arguments the derivative is taken with respect to
+    if (keys_to_optimize.empty()) {
+      for (int o = 0; o < it->second.n_opt; ++o) f.keys_to_optimize_.push_back(keys_to_func[it->second.opt_args[o]]);
+    } else {
+      f.keys_to_optimize_ = keys_to_optimize;
+    }
+    if (static_cast<int>(f.keys_to_optimize_.size()) != it->second.n_opt)
+      throw std::runtime_error("SYM_ASSERT: keys_to_optimize must list the linearized arguments of the function");
+    for (int o = 0; o < it->second.n_opt; ++o)
+      if (!(f.keys_to_optimize_[o] == keys_to_func[it->second.opt_args[o]]))
+        throw std::runtime_error("SYM_ASSERT: keys_to_optimize must be the linearized arguments, in argument order");
+    return f;
+  }
+  const std::vector<Key>& AllKeys() const { return keys_; }
+  const std::vector<Key>& OptimizedKeys() const { return keys_to_optimize_; }
+  int Kind() const { return kind_; }
+
+ private:
+  // functions (and pointers to functions) decay to a function pointer; anything else has no address
+  template <typename F>
+  static const void* AddressOf(F&& f) {
+    using D = typename std::decay<F>::type;
+    if constexpr (std::is_pointer<D>::value && std::is_function<typename std::remove_pointer<D>::type>::value)
+      return reinterpret_cast<const void*>(static_cast<D>(f));
+    else
+      return nullptr;
+  }
+  int kind_{-1};
+  std::vector<Key> keys_, keys_to_optimize_;
+};
+using Factord = Factor<double>;
+
+// ComputeKeysToOptimize (factor.h:424-449): union of optimized keys, LexicalLessThan order
+template <typename Scalar>
+std::vector<Key> ComputeKeysToOptimize(const std::vector<Factor<Scalar>>& factors) {
+  std::vector<Key> keys;
+  std::unordered_map<Key, bool, KeyHash> seen;
+  for (const auto& f : factors)
+    for (const Key& k : f.OptimizedKeys())
+      if (!seen.count(k)) {
+        seen[k] = true;
+        keys.push_back(k);
+      }
+  std::sort(keys.begin(), keys.end(), Key::LexicalLessThan);
+  return keys;
+}
+
+// Extension point for the GPU path: which linear solver the LM loop uses.
+struct GpuSolverOptions {
+  enum Solver { AUTO, CHOLESKY, SCHUR };
+  Solver solver = AUTO;        // AUTO: Schur when a trailing run of <=3-dim vector keys is pairwise
+                               // unconnected (the block-diagonal C of sparse_schur_solver.h:20-31)
+  int schur_num_keys = 0;      // SCHUR: number of trailing keys to eliminate
+  int ordering = SFX_ORDERING_METIS_SCALAR;
+  int device = 0;
+};
+
+// ------------------------------------------------------------------------------------------------
+// Optimizer (symforce/opt/optimizer.h:72-325)
+// ------------------------------------------------------------------------------------------------
+template <typename ScalarType>
+class Optimizer {
+ public:
+  using Scalar = ScalarType;
+  using Stats = OptimizationStats;
+  static_assert(std::is_same<Scalar, double>::value, "the GPU path computes in fp64");
+
+  Optimizer(const optimizer_params_t& params, std::vector<Factor<Scalar>> factors,
+            const std::string& name = "sym::Optimize", std::vector<Key> keys = {},
+            const Scalar epsilon = kDefaultEpsilon<Scalar>, const GpuSolverOptions& gpu = GpuSolverOptions())
+      : params_(params), factors_(std::move(factors)), name_(name), keys_(std::move(keys)), epsilon_(epsilon), gpu_(gpu) {
+    if (keys_.empty()) keys_ = ComputeKeysToOptimize(factors_);
+    SYM_ASSERT(!factors_.empty());
+    SYM_ASSERT(!keys_.empty());
+  }
+  Optimizer(const Optimizer&) = delete;
+  Optimizer& operator=(const Optimizer&) = delete;
+  ~Optimizer() {
+    if (handle_) sfx_problem_destroy(handle_);
+  }
+
+  // Optimize(values, num_iterations, populate_best_linearization) (optimizer.tcc:79-89)
+  Stats Optimize(Values<Scalar>& values, int num_iterations = -1, bool populate_best_linearization = false) {
+    Stats stats;
+    Optimize(values, num_iterations, populate_best_linearization, stats);
+    return stats;
+  }
+  void Optimize(Values<Scalar>& values, int num_iterations, bool populate_best_linearization, Stats& stats) {
+    Initialize(values);
+    Check(sfx_set_values(handle_, values.Data().data(), static_cast<int64_t>(values.Data().size())));
+    sfx_stats st{};
+    Check(sfx_optimize(handle_, num_iterations, &st));
+    std::vector<sfx_iteration> its(st.n_iterations);
+    int32_t n = 0;
+    Check(sfx_get_iterations(handle_, its.data(), st.n_iterations, &n));
+    stats.iterations.clear();
+    for (const auto& it : its) {
+      optimization_iteration_t o;
+      o.iteration = static_cast<int16_t>(it.iteration);
+      o.current_lambda = it.current_lambda;
+      o.new_error_linear = it.new_error_linear;
+      o.new_error = it.new_error;
+      o.relative_reduction = it.relative_reduction;
+      o.update_accepted = it.update_accepted != 0;
+      o.update_angle_change = it.update_angle_change;
+      stats.iterations.push_back(o);
+    }
+    stats.best_index = st.best_index;
+    stats.status = static_cast<optimization_status_t>(st.status);
+    stats.failure_reason = st.failure_reason;
+    // values = nonlinear_solver.GetBestValues() (internal/optimizer_utils.h:69)
+    Check(sfx_get_best_values(handle_, values.DataPointer(), static_cast<int64_t>(values.Data().size())));
+    if (populate_best_linearization) {
+      SparseLinearization lin;
+      FillPattern(lin);
+      Check(sfx_get_best_linearization(handle_, lin.residual.data(), lin.rhs.data(), lin.hessian_lower.values.data()));
+      stats.best_linearization = std::move(lin);
+    } else {
+      stats.best_linearization.reset();
+    }
+  }
+
+  // Linearize(values) (optimizer.h:177)
+  SparseLinearization Linearize(const Values<Scalar>& values) {
+    Initialize(values);
+    Check(sfx_set_values(handle_, values.Data().data(), static_cast<int64_t>(values.Data().size())));
+    SparseLinearization lin;
+    FillPattern(lin);
+    Check(sfx_linearize(handle_, lin.residual.data(), lin.rhs.data(), lin.hessian_lower.values.data()));
+    return lin;
+  }
+
+  const std::vector<Key>& Keys() const { return keys_; }
+  const std::vector<Factor<Scalar>>& Factors() const { return factors_; }
+  const optimizer_params_t& Params() const { return params_; }
+  void UpdateParams(const optimizer_params_t& params) {
+    params_ = params;
+    if (handle_) {
+      sfx_params p = ToC(params_);
+      Check(sfx_update_params(handle_, &p));
+    }
+  }
+  sfx_problem* Handle() { return handle_; }
+
+ private:
+  static sfx_params ToC(const optimizer_params_t& q) {
+    sfx_params p{};
+    p.verbose = q.verbose;
+    p.debug_stats = q.debug_stats;
+    p.check_derivatives = q.check_derivatives;
+    p.include_jacobians = q.include_jacobians;
+    p.debug_checks = q.debug_checks;
+    p.initial_lambda = q.initial_lambda;
+    p.lambda_lower_bound = q.lambda_lower_bound;
+    p.lambda_upper_bound = q.lambda_upper_bound;
+    p.lambda_update_type = static_cast<int32_t>(q.lambda_update_type);
+    p.lambda_up_factor = q.lambda_up_factor;
+    p.lambda_down_factor = q.lambda_down_factor;
+    p.dynamic_lambda_update_beta = q.dynamic_lambda_update_beta;
+    p.dynamic_lambda_update_gamma = q.dynamic_lambda_update_gamma;
+    p.dynamic_lambda_update_p = q.dynamic_lambda_update_p;
+    p.use_diagonal_damping = q.use_diagonal_damping;
+    p.use_unit_damping = q.use_unit_damping;
+    p.keep_max_diagonal_damping = q.keep_max_diagonal_damping;
+    p.diagonal_damping_min = q.diagonal_damping_min;
+    p.iterations = q.iterations;
+    p.early_exit_min_reduction = q.early_exit_min_reduction;
+    p.early_exit_min_absolute_error = q.early_exit_min_absolute_error;
+    p.enable_bold_updates = q.enable_bold_updates;
+    return p;
+  }
+  void Check(sfx_status s) const {
+    if (s != SFX_OK) throw std::runtime_error(std::string("sym::Optimizer<") + name_ + ">: " + sfx_last_error(handle_));
+  }
+  static int DeviceType(type_t t) {
+    switch (t) {
+      case type_t::ROT3: return SFX_TYPE_ROT3;
+      case type_t::POSE3: return SFX_TYPE_POSE3;
+      default: return SFX_TYPE_VECTOR;
+    }
+  }
+  // Lazy first-call initialisation like Optimizer::Initialize (optimizer.tcc:273-278): index the
+  // keys, lower every factor to argument offsets, create the device problem.
+  void Initialize(const Values<Scalar>& values) {
+    if (handle_) {
+      SYM_ASSERT(static_cast<int64_t>(values.Data().size()) == n_values_);
+      return;
+    }
+    std::unordered_map<Key, int, KeyHash> key_index;
+    std::vector<sfx_key_entry> kentries;
+    for (size_t i = 0; i < keys_.size(); ++i) {
+      const index_entry_t& e = values.IndexEntryAt(keys_[i]);
+      kentries.push_back(sfx_key_entry{DeviceType(e.type), e.offset, e.storage_dim, e.tangent_dim});
+      key_index[keys_[i]] = static_cast<int>(i);
+    }
+    struct Batch {
+      int n_args = 0, n_opt = 0;
+      std::vector<std::vector<int32_t>> args, opt;
+      std::vector<int32_t> fidx;
+    };
+    std::map<int, Batch> batches;
+    for (size_t fi = 0; fi < factors_.size(); ++fi) {
+      const Factor<Scalar>& f = factors_[fi];
+      Batch& b = batches[f.Kind()];
+      if (b.args.empty()) {
+        b.n_args = static_cast<int>(f.AllKeys().size());
+        b.n_opt = static_cast<int>(f.OptimizedKeys().size());
+        b.args.resize(b.n_args);
+        b.opt.resize(b.n_opt);
+      }
+      for (int a = 0; a < b.n_args; ++a) b.args[a].push_back(values.IndexEntryAt(f.AllKeys()[a]).offset);
+      for (int o = 0; o < b.n_opt; ++o) {
+        auto it = key_index.find(f.OptimizedKeys()[o]);
+        b.opt[o].push_back(it == key_index.end() ? -1 : it->second);
+      }
+      b.fidx.push_back(static_cast<int32_t>(fi));
+    }
+    std::vector<std::vector<int32_t>> flat_args, flat_opt;
+    std::vector<sfx_factor_batch> fb;
+    for (auto& kv : batches) {
+      Batch& b = kv.second;
+      std::vector<int32_t> fa, fo;
+      for (auto& v : b.args) fa.insert(fa.end(), v.begin(), v.end());
+      for (auto& v : b.opt) fo.insert(fo.end(), v.begin(), v.end());
+      flat_args.push_back(std::move(fa));
+      flat_opt.push_back(std::move(fo));
+    }
+    size_t bi = 0;
+    for (auto& kv : batches) {
+      sfx_factor_batch x{};
+      x.kind = kv.first;
+      x.n = static_cast<int32_t>(kv.second.fidx.size());
+      x.arg_offsets = flat_args[bi].data();
+      x.opt_keys = flat_opt[bi].data();
+      x.factor_index = kv.second.fidx.data();
+      fb.push_back(x);
+      ++bi;
+    }
+    sfx_problem_desc d{};
+    d.abi_version = SFX_ABI_VERSION;
+    d.params = ToC(params_);
+    d.epsilon = epsilon_;
+    d.n_values = static_cast<int64_t>(values.Data().size());
+    d.n_keys = static_cast<int32_t>(kentries.size());
+    d.keys = kentries.data();
+    d.n_batches = static_cast<int32_t>(fb.size());
+    d.batches = fb.data();
+    d.n_factors = static_cast<int32_t>(factors_.size());
+    d.ordering = gpu_.ordering;
+    d.device = gpu_.device;
+    d.rank = 0;
+    d.world = 1;
+    d.comm = nullptr;
+    int schur_keys = 0;
+    if (gpu_.solver == GpuSolverOptions::SCHUR) schur_keys = gpu_.schur_num_keys;
+    if (gpu_.solver == GpuSolverOptions::AUTO) schur_keys = AutoSchurKeys(values, key_index);
+    d.solver = schur_keys > 0 ? SFX_SOLVER_SCHUR : SFX_SOLVER_CHOLESKY;
+    d.schur_num_keys = schur_keys;
+    sfx_problem* h = nullptr;
+    sfx_status s = sfx_problem_create(&d, &h);
+    if (s != SFX_OK) throw std::runtime_error(std::string("sym::Optimizer<") + name_ + ">: " + sfx_last_error(nullptr));
+    handle_ = h;
+    n_values_ = d.n_values;
+  }
+  // Longest trailing run of keys (in keys_ order) that are vectors of dim <= 3 and never share a
+  // factor with each other: eliminating them per block is exactly SparseSchurSolver's C.
+  int AutoSchurKeys(const Values<Scalar>& values, const std::unordered_map<Key, int, KeyHash>& key_index) const {
+    const int nk = static_cast<int>(keys_.size());
+    int first = nk;
+    while (first > 0) {
+      const index_entry_t& e = values.IndexEntryAt(keys_[first - 1]);
+      if ((e.type == type_t::VECTOR || e.type == type_t::SCALAR) && e.tangent_dim <= 3)
+        --first;
+      else
+        break;
+    }
+    if (first == 0 || first == nk) return 0;
+    for (const auto& f : factors_) {
+      int lm = 0;
+      for (const Key& k : f.OptimizedKeys()) {
+        auto it = key_index.find(k);
+        if (it != key_index.end() && it->second >= first) ++lm;
+      }
+      if (lm > 1) return 0;
+    }
+    return (nk - first) >= nk / 2 ? nk - first : 0;
+  }
+  void FillPattern(SparseLinearization& lin) {
+    int32_t N = 0, M = 0;
+    int64_t nnz = 0;
+    Check(sfx_get_dims(handle_, &N, &M, &nnz));
+    lin.residual.resize(M);
+    lin.rhs.resize(N);
+    lin.hessian_lower.rows_ = lin.hessian_lower.cols_ = N;
+    lin.hessian_lower.outer.resize(N + 1);
+    lin.hessian_lower.inner.resize(nnz);
+    lin.hessian_lower.values.resize(nnz);
+    Check(sfx_get_hessian_pattern(handle_, lin.hessian_lower.outer.data(), lin.hessian_lower.inner.data()));
+  }
+
+  optimizer_params_t params_;
+  std::vector<Factor<Scalar>> factors_;
+  std::string name_;
+  std::vector<Key> keys_;
+  Scalar epsilon_;
+  GpuSolverOptions gpu_;
+  sfx_problem* handle_{nullptr};
+  int64_t n_values_{0};
+};
+using Optimizerd = Optimizer<double>;
+
+// sym::Optimize (optimizer.h:334-340)
+template <typename Scalar>
+OptimizationStats Optimize(const optimizer_params_t& params, std::vector<Factor<Scalar>> factors, Values<Scalar>& values,
+                           const Scalar epsilon = kDefaultEpsilon<Scalar>) {
+  Optimizer<Scalar> optimizer(params, std::move(factors), "sym::Optimize", {}, epsilon);
+  return optimizer.Optimize(values);
+}
+
+}  // namespace sym

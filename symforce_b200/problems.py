@@ -456,3 +456,115 @@ def pose_graph_problem(n_poses=100000, n_loops=20000, seed=0x51A4, params=None, 
     prob = D.Problem(vb.data(), keys, [between, prior], params=p, ordering=ordering)
     prob.meta = dict(n_poses=n_poses, n_edges=int(ne))
     return prob
+
+
+# ------------------------------------------------------------------------------------------------
+# BA example shape (config A): 2 views, 20 inverse-range landmarks, view 0 fixed
+# ------------------------------------------------------------------------------------------------
+def ba_example(seed=42, num_landmarks=20, params=None):
+    """
+    The bundle_adjustment example's problem structure (symforce/examples/bundle_adjustment/
+    run_bundle_adjustment.cc:20-125, build_example_state.cc:25-140, example_utils/
+    bundle_adjustment_util.h:119-136): keys v/c/T/s/l/P/S/m/M/W/u/C/e, relative-pose priors
+    (BetweenFactorPose3) in both directions, an InverseRangeLandmarkPriorFactor and an
+    InverseRangeLandmarkLinearGncFactor per landmark, VIEW 0 not optimized.  Inputs are drawn with
+    numpy (the reference uses libstdc++'s RNG stream, which numpy cannot reproduce), so parity for
+    this config is oracle-vs-GPU on these inputs plus the reference's acceptance check
+    (final error < 10, SUCCESS).
+    """
+    rng = np.random.default_rng(seed)
+    eps = 1e-10
+    fx = fy = 740.0
+    cx, cy = 639.5, 359.5
+    q0 = quat_exp(rng.normal(0, 0.3, (1, 3)))[0]
+    t0 = rng.normal(0, 1, 3)
+    pert = np.array([0.1, -0.2, 0.1, 2.1, 0.4, -0.2]) * rng.normal(0, 0.3)
+    q1 = quat_mul(q0, quat_exp(pert[None, :3])[0])
+    q1 /= np.linalg.norm(q1)
+    t1 = t0 + pert[3:]
+    noise = 0.1 * rng.normal(0, 1, 6) * 0.3
+    q1n = quat_mul(q1, quat_exp(noise[None, :3])[0])
+    q1n /= np.linalg.norm(q1n)
+    t1n = t1 + noise[3:]
+    # correspondences: grid pixels in the source view, inverse ranges 1/U(2.5, 30)
+    gx, gy = np.meshgrid(np.arange(100, 1200, 100), np.arange(100, 700, 100))
+    grid = np.stack([gx.reshape(-1), gy.reshape(-1)], 1).astype(float)
+    src = grid[rng.permutation(grid.shape[0])[:num_landmarks]]
+    inv_range = 1.0 / rng.uniform(2.5, 30, num_landmarks)
+    ray = np.stack([(src[:, 0] - cx) / fx, (src[:, 1] - cy) / fy, np.ones(num_landmarks)], 1)
+    ray /= np.linalg.norm(ray, axis=1, keepdims=True)
+    p_cam0 = ray / inv_range[:, None]
+    p_w = quat_rotate(np.tile(q0, (num_landmarks, 1)), p_cam0) + t0
+    q1_inv = q1 * np.array([-1, -1, -1, 1.0])
+    p_cam1 = quat_rotate(np.tile(q1_inv, (num_landmarks, 1)), p_w - t1)
+    tgt = np.stack([fx * p_cam1[:, 0] / p_cam1[:, 2] + cx, fy * p_cam1[:, 1] / p_cam1[:, 2] + cy], 1)
+    tgt += 1.0 * rng.normal(0, 1, tgt.shape)
+    range_pert = np.clip(1 + rng.normal(0, 0.5, num_landmarks), 0.5, 2.0)
+    lm_init = 1.0 / ((1.0 / inv_range) * range_pert)
+    # relative pose prior 0->1: between(view0, view1) (+) noise
+    q0_inv = q0 * np.array([-1, -1, -1, 1.0])
+    q01 = quat_mul(q0_inv, q1)
+    t01 = quat_rotate(q0_inv[None, :], (t1 - t0)[None, :])[0]
+    pn = 0.3 * rng.normal(0, 1, 6) * 0.1
+    q01 = quat_mul(q01, quat_exp(pn[None, :3])[0])
+    q01 /= np.linalg.norm(q01)
+    t01 = t01 + pn[3:]
+
+    vb = ValuesBuilder()
+    e_off = vb.add([eps])
+    scale_off = vb.add([10.0])
+    mu_off = vb.add([0.0])
+    v0 = vb.add(np.concatenate([q0, t0]))
+    c0 = vb.add([fx, fy, cx, cy])
+    v1 = vb.add(np.concatenate([q1n, t1n]))
+    c1 = vb.add([fx, fy, cx, cy])
+    ident = [0, 0, 0, 1, 0, 0, 0]
+    T = {}
+    S = {}
+    for i in range(2):
+        for j in range(2):
+            T[i, j] = vb.add(ident)
+            S[i, j] = vb.add(np.zeros(36))
+    vals_T01 = np.concatenate([q01, t01])
+    vb.chunks[-4 * 2 + 2] = vals_T01  # (0,1) pose prior
+    vb.chunks[-4 * 2 + 3] = (np.eye(6) / 0.3).reshape(-1, order="F")
+    lm = vb.add_many(lm_init[:, None])
+    src_off = vb.add_many(src)
+    tgt_off = vb.add_many(tgt)
+    w_off = vb.add_many(np.ones((num_landmarks, 1)))
+    prior_off = vb.add_many(inv_range[:, None])
+    sig_off = vb.add_many(np.full((num_landmarks, 1), 100.0))
+    # optimized keys, lexical: l_0.. ('l' < 'v'), then v_1
+    keys = [(D.TYPE_VECTOR, int(lm[i]), 1, 1) for i in range(num_landmarks)] + [(D.TYPE_POSE3, int(v1), 7, 6)]
+    kv1 = num_landmarks
+    view_off = {0: v0, 1: v1}
+    view_key = {0: -1, 1: kv1}
+    pairs = [(0, 1), (1, 0)]
+    between = (
+        D.KIND_BETWEEN_POSE3,
+        np.array([[view_off[i] for i, _ in pairs], [view_off[j] for _, j in pairs], [T[p] for p in pairs],
+                  [S[p] for p in pairs], [e_off] * 2]),
+        np.array([[view_key[i] for i, _ in pairs], [view_key[j] for _, j in pairs]]),
+        np.array([0, 1]),
+    )
+    n = num_landmarks
+    prior = (
+        D.KIND_IRL_PRIOR,
+        np.array([lm, prior_off, w_off, sig_off, np.full(n, e_off)]),
+        np.array([np.arange(n)]),
+        2 + np.arange(n),
+    )
+    gnc = (
+        D.KIND_IRL_LINEAR_GNC,
+        np.array([np.full(n, v0), np.full(n, c0), np.full(n, v1), np.full(n, c1), lm, src_off, tgt_off, w_off,
+                  np.full(n, mu_off), np.full(n, scale_off), np.full(n, e_off)]),
+        np.array([np.full(n, -1), np.full(n, kv1), np.arange(n)]),
+        2 + n + np.arange(n),
+    )
+    if params is None:
+        params = D.default_params()
+        params.iterations = 50
+        params.lambda_up_factor = 10.0
+        params.lambda_down_factor = 0.1
+        params.lambda_lower_bound = 1e-8
+    return D.Problem(vb.data(), keys, [between, prior, gnc], params=params, epsilon=eps)

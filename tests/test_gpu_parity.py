@@ -33,6 +33,7 @@ PROBLEMS = {
     "rotation_smoothing": lambda: P.rotation_smoothing(_params(iterations=50, early_exit_min_reduction=1e-4)),
     "frozen_keys": lambda: P.frozen_keys(_params(iterations=50, early_exit_min_reduction=1e-4)),
     "robot3d": lambda: P.robot_3d_localization(),
+    "ba_example": lambda: P.ba_example(),
     "bal_tiny_schur": lambda: P.bal_problem("tiny", solver=D.SOLVER_SCHUR),
     "bal_small_schur": lambda: P.bal_problem("small", solver=D.SOLVER_SCHUR),
     "bal_small_chol": lambda: P.bal_problem("small", solver=D.SOLVER_CHOLESKY),
@@ -164,3 +165,38 @@ def test_bal_properties_at_scale():
     assert its[ss.best_index].new_error < 0.02 * its[0].new_error
     gs.close()
     gc.close()
+
+
+def test_ba_example_acceptance(solved):
+    """symforce/examples/bundle_adjustment/run_bundle_adjustment.cc:180-181: error < 10 and SUCCESS
+    (GNC + inverse-range prior factors, view 0 fixed)."""
+    prob, gpu, _ = solved("ba_example")
+    gpu.set_values(prob.values)
+    st = gpu.optimize()
+    its = gpu.iterations()
+    assert st.status == D.STATUS_SUCCESS
+    assert its[st.best_index].new_error < 10
+
+
+def test_cpp_examples_through_sym_layer():
+    """The C++17 callers of include/sym/sym.h (examples/) reproduce the Python/C-ABI results."""
+    import os
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    subprocess.check_call(["make", "-s", "-C", os.path.join(root, "examples")])
+    out = subprocess.run([os.path.join(root, "examples", "_build", "robot_3d_localization")], capture_output=True,
+                         text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    init = float(re.search(r"Initial error: ([0-9.eE+-]+)", out.stdout).group(1))
+    final = float(re.search(r"Final error: ([0-9.eE+-]+)", out.stdout).group(1))
+    assert init == pytest.approx(463700.5576620833, rel=1e-8)
+    g = capi.SfxProblem(P.robot_3d_localization())
+    st = g.optimize()
+    assert final == pytest.approx(g.iterations()[st.best_index].new_error, rel=1e-9)
+    g.close()
+    out = subprocess.run([os.path.join(root, "examples", "_build", "bundle_adjustment_in_the_large"), "--synthetic",
+                          "12", "400", "5"], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    errs = [float(x) for x in re.findall(r"error: ([0-9.eE+-]+),", out.stdout)]
+    assert errs[-1] < 0.05 * errs[0]

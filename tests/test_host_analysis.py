@@ -40,6 +40,7 @@ PROBLEMS = {
     "rotation_smoothing": lambda: P.rotation_smoothing(),
     "frozen_keys": lambda: P.frozen_keys(),
     "robot3d": lambda: P.robot_3d_localization(),
+    "ba_example": lambda: P.ba_example(),
     "bal_tiny_schur": lambda: P.bal_problem("tiny", solver=D.SOLVER_SCHUR),
     "bal_tiny_chol": lambda: P.bal_problem("tiny", solver=D.SOLVER_CHOLESKY),
     "bal_tiny_natural": lambda: _with_ordering(P.bal_problem("tiny", solver=D.SOLVER_SCHUR), D.ORDERING_NATURAL),

@@ -695,34 +695,67 @@ __global__ void __launch_bounds__(kSchurWarps * 32) schur_s_kernel(const Ctrl* _
   double* G = EJ + 48;
   double* Cs = G + 48;
   double acc[8];
+  int er[8], ec[8];  // (row, col) of the S-block elements this lane owns (hoisted out of the match loop)
 #pragma unroll
-  for (int k = 0; k < 8; ++k) acc[k] = 0.0;
+  for (int k = 0; k < 8; ++k) {
+    acc[k] = 0.0;
+    const int e = lane + 32 * k;
+    er[k] = e % dI;
+    ec[k] = e / dI;
+  }
+  const int nslots = (ne + 31) >> 5;
+  // landmark dims are uniform inside a problem in practice; the generic loop bounds stay runtime
   for (int m = m0; m < m1; ++m) {
     const int l = sd.m_lm[m];
     const int dl = sd.lm_dim[l];
-    const double* ei = H + sd.m_eoff_i[m];
-    const double* ej = H + sd.m_eoff_j[m];
+    const double* __restrict__ ei = H + sd.m_eoff_i[m];
+    const double* __restrict__ ej = H + sd.m_eoff_j[m];
+    // issue all global loads of this match first
+    double vi0 = 0, vi1 = 0, vj0 = 0, vj1 = 0, vc = 0;
+    const int ni = dl * dI, nj = dl * dJ;
+    if (lane < ni) vi0 = ei[lane];
+    if (lane + 32 < ni) vi1 = ei[lane + 32];
+    if (lane < nj) vj0 = ej[lane];
+    if (lane + 32 < nj) vj1 = ej[lane + 32];
+    if (lane < 9) vc = sd.cinv[(size_t)l * 9 + lane];
     __syncwarp();
-    for (int t = lane; t < dl * dI; t += 32) EI[t] = ei[t];
-    for (int t = lane; t < dl * dJ; t += 32) EJ[t] = ej[t];
-    if (lane < 9) Cs[lane] = sd.cinv[(size_t)l * 9 + lane];
+    if (lane < ni) EI[lane] = vi0;
+    if (lane + 32 < ni) EI[lane + 32] = vi1;
+    if (lane < nj) EJ[lane] = vj0;
+    if (lane + 32 < nj) EJ[lane + 32] = vj1;
+    if (lane < 9) Cs[lane] = vc;
     __syncwarp();
-    for (int t = lane; t < dl * dJ; t += 32) {
-      const int a = t % dl, c = t / dl;
-      double v = 0;
-      for (int q = 0; q < dl; ++q) v += Cs[a + q * 3] * EJ[q + c * dl];
-      G[t] = v;
+    // G = Cinv * EJ  (dl x dJ), element t = a + dl*c
+    if (dl == 3) {
+      for (int t = lane; t < nj; t += 32) {
+        const int c = t / 3, a = t - 3 * c;
+        G[t] = Cs[a] * EJ[3 * c] + Cs[a + 3] * EJ[3 * c + 1] + Cs[a + 6] * EJ[3 * c + 2];
+      }
+    } else {
+      for (int t = lane; t < nj; t += 32) {
+        const int a = t % dl, c = t / dl;
+        double v = 0;
+        for (int q = 0; q < dl; ++q) v += Cs[a + q * 3] * EJ[q + c * dl];
+        G[t] = v;
+      }
     }
     __syncwarp();
+    if (dl == 3) {
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int e = lane + 32 * k;
-      if (e < ne) {
-        const int r = e % dI, c = e / dI;
-        double v = 0;
-        for (int q = 0; q < dl; ++q) v += EI[q + r * dl] * G[q + c * dl];
-        acc[k] += v;
-      }
+      for (int k = 0; k < 8; ++k)
+        if (k < nslots && lane + 32 * k < ne) {
+          const double* a = EI + 3 * er[k];
+          const double* g = G + 3 * ec[k];
+          acc[k] += a[0] * g[0] + a[1] * g[1] + a[2] * g[2];
+        }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        if (k < nslots && lane + 32 * k < ne) {
+          double v = 0;
+          for (int q = 0; q < dl; ++q) v += EI[q + er[k] * dl] * G[q + ec[k] * dl];
+          acc[k] += v;
+        }
     }
   }
   double* out = sd.S + sd.s_off[b];
@@ -732,7 +765,7 @@ __global__ void __launch_bounds__(kSchurWarps * 32) schur_s_kernel(const Ctrl* _
   for (int k = 0; k < 8; ++k) {
     const int e = lane + 32 * k;
     if (e < ne) {
-      const int r = e % dI, c = e / dI;
+      const int r = er[k], c = ec[k];
       double v = -acc[k];
       if (first) {
         if (bsrc >= 0) v += H[bsrc + e];

@@ -368,50 +368,62 @@ def bal_problem(shape="ladybug", solver=D.SOLVER_SCHUR, params=None, seed_struct
 # Synthetic pose graph
 # ------------------------------------------------------------------------------------------------
 def pose_graph_problem(n_poses=100000, n_loops=20000, seed=0x51A4, params=None, ordering=D.ORDERING_METIS_SCALAR):
+    """
+    Synthetic Pose3 pose-graph SLAM (config E): a Manhattan-world trajectory (1 m steps, 90-degree
+    turns, confined to a square region so that places are revisited), odometry edges (i, i+1) and
+    `n_loops` loop closures between poses that are spatial neighbours (<= 5 m) but far apart in time;
+    measurements = true relative pose (+) N(0, diag(0.01^2 rad, 0.05^2 m)); sqrt_info =
+    diag(100,100,100,20,20,20) stored as one Matrix66 Values key per edge; one PriorFactorPose3 on P_0;
+    initial guess = odometry dead reckoning.
+    """
     rng = np.random.default_rng(seed)
-    # truth: random walk, 1 m forward along body x, yaw noise
-    yaw_step = rng.normal(0, 0.1, n_poses)
-    pitch_step = rng.normal(0, 0.02, n_poses)
-    q = np.empty((n_poses, 4))
-    t = np.empty((n_poses, 3))
-    q[0] = [0, 0, 0, 1]
-    t[0] = 0
-    dqs = quat_exp(np.stack([np.zeros(n_poses), pitch_step, yaw_step], axis=1))
-    for i in range(1, n_poses):
-        q[i] = quat_mul(q[i - 1], dqs[i])
-        q[i] /= np.linalg.norm(q[i])
-        t[i] = t[i - 1] + quat_rotate(q[i - 1], np.array([1.0, 0.0, 0.0]))
-    # edges: odometry + loop closures to spatial neighbours within 5 m (grid hash), fallback random
-    ea = [np.arange(n_poses - 1)]
-    eb = [np.arange(1, n_poses)]
-    cell = np.floor(t / 5.0).astype(np.int64)
-    keyc = cell[:, 0] * 73856093 ^ cell[:, 1] * 19349663 ^ cell[:, 2] * 83492791
+    side = max(8, int(np.sqrt(n_poses) * 0.9))  # region size in metres: cells get revisited
+    pos = np.zeros((n_poses, 2), dtype=np.int64)
+    head = np.zeros(n_poses, dtype=np.int64)  # heading in quarter turns
+    dirs = np.array([[1, 0], [0, 1], [-1, 0], [0, -1]])
+    turn = rng.choice([0, 0, 0, 0, 0, 0, 1, 3], size=n_poses)
+    x, y, h = side // 2, side // 2, 0
+    for i in range(n_poses):
+        pos[i] = (x, y)
+        head[i] = h
+        h = (h + turn[i]) % 4
+        nx, ny = x + dirs[h][0], y + dirs[h][1]
+        tries = 0
+        while not (0 <= nx < side and 0 <= ny < side) and tries < 4:
+            h = (h + 1) % 4
+            nx, ny = x + dirs[h][0], y + dirs[h][1]
+            tries += 1
+        x, y = nx, ny
+    theta = head * (np.pi / 2)
+    q = np.stack([np.zeros(n_poses), np.zeros(n_poses), np.sin(theta / 2), np.cos(theta / 2)], axis=1)
+    t = np.stack([pos[:, 0].astype(float), pos[:, 1].astype(float), np.zeros(n_poses)], axis=1)
+    # loop closures: spatial neighbours through a cell hash (5 m cells), far apart in time
+    min_sep = min(100, max(1, n_poses // 4))
+    cell = (pos // 5)
+    keyc = cell[:, 0] * 100003 + cell[:, 1]
     order = np.argsort(keyc, kind="stable")
     sorted_keys = keyc[order]
-    starts = np.searchsorted(sorted_keys, sorted_keys, side="left")
-    ends = np.searchsorted(sorted_keys, sorted_keys, side="right")
-    inv = np.empty(n_poses, dtype=np.int64)
-    inv[order] = np.arange(n_poses)
-    src = rng.integers(0, n_poses, n_loops)
-    min_sep = min(100, max(1, n_poses // 4))
     la, lb = [], []
+    src = rng.permutation(n_poses)
+    seen = set()
     for i in src:
-        pos = inv[i]
-        lo, hi = starts[pos], ends[pos]
+        if len(la) >= n_loops:
+            break
+        lo = np.searchsorted(sorted_keys, keyc[i], side="left")
+        hi = np.searchsorted(sorted_keys, keyc[i], side="right")
         cand = order[lo:hi]
         cand = cand[np.abs(cand - i) > min_sep]
-        if cand.shape[0] > 0:
-            j = int(cand[rng.integers(0, cand.shape[0])])
-        else:
-            j = int(rng.integers(0, n_poses))
-            while abs(j - i) <= min_sep:
-                j = int(rng.integers(0, n_poses))
-        la.append(min(i, j))
-        lb.append(max(i, j))
-    ea.append(np.array(la, dtype=np.int64))
-    eb.append(np.array(lb, dtype=np.int64))
-    ea = np.concatenate(ea)
-    eb = np.concatenate(eb)
+        if cand.shape[0] == 0:
+            continue
+        j = int(cand[rng.integers(0, cand.shape[0])])
+        a, b = (int(i), j) if i < j else (j, int(i))
+        if (a, b) in seen:
+            continue
+        seen.add((a, b))
+        la.append(a)
+        lb.append(b)
+    ea = np.concatenate([np.arange(n_poses - 1), np.array(la, dtype=np.int64)])
+    eb = np.concatenate([np.arange(1, n_poses), np.array(lb, dtype=np.int64)])
     ne = ea.shape[0]
     # measurements: a_T_b = a^-1 b (+) noise
     qa_inv = q[ea] * np.array([-1, -1, -1, 1.0])
@@ -428,9 +440,17 @@ def pose_graph_problem(n_poses=100000, n_loops=20000, seed=0x51A4, params=None, 
     q0[0] = q[0]
     t0[0] = t[0]
     for i in range(1, n_poses):
-        q0[i] = quat_mul(q0[i - 1], q_meas[i - 1])
-        q0[i] /= np.linalg.norm(q0[i])
-        t0[i] = t0[i - 1] + quat_rotate(q0[i - 1], t_meas[i - 1])
+        a = q0[i - 1]
+        b = q_meas[i - 1]
+        qq = np.array([a[3] * b[0] + a[0] * b[3] + a[1] * b[2] - a[2] * b[1],
+                       a[3] * b[1] - a[0] * b[2] + a[1] * b[3] + a[2] * b[0],
+                       a[3] * b[2] + a[0] * b[1] - a[1] * b[0] + a[2] * b[3],
+                       a[3] * b[3] - a[0] * b[0] - a[1] * b[1] - a[2] * b[2]])
+        q0[i] = qq / np.sqrt(qq @ qq)
+        v = t_meas[i - 1]
+        qv = a[:3]
+        tt = 2.0 * np.cross(qv, v)
+        t0[i] = t0[i - 1] + v + a[3] * tt + np.cross(qv, tt)
     vb = ValuesBuilder()
     pose_off = vb.add_many(np.concatenate([q0, t0], axis=1))
     sqrt_info = np.diag([100, 100, 100, 20, 20, 20.0]).reshape(-1, order="F")
@@ -454,7 +474,7 @@ def pose_graph_problem(n_poses=100000, n_loops=20000, seed=0x51A4, params=None, 
     )
     p = params if params is not None else D.default_params()
     prob = D.Problem(vb.data(), keys, [between, prior], params=p, ordering=ordering)
-    prob.meta = dict(n_poses=n_poses, n_edges=int(ne))
+    prob.meta = dict(n_poses=n_poses, n_edges=int(ne), n_loops=len(la))
     return prob
 
 

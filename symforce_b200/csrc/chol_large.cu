@@ -77,17 +77,164 @@ __device__ __forceinline__ void tile_gemm(const double* As, const double* Bs, do
   }
 }
 
+// 64x64 Cholesky + inverse of the factor, register blocked: thread (trow, tcol) = (tid & 15, tid >> 4)
+// owns the 4x4 sub-block rows 4*trow.., cols 4*tcol.. of both A (-> L) and X (-> L^-1).  Per
+// column: the diagonal owner publishes 1/sqrt(d); the 16 owners of column c scale it and publish
+// it, the 16 owners of row c of X do the same; everyone applies the rank-1 update to its registers.
+// Two barriers per column (buffers alternate by column parity).
+struct PotrfSmem {
+  double col[2][kT];
+  double xrow[2][kT];
+  double pinv[2];
+};
+__device__ __forceinline__ void potrf_inverse_64(double (&a)[4][4], double (&x)[4][4], PotrfSmem& ps, int* fail) {
+  const int tid = threadIdx.x;
+  const int trow = tid & 15, tcol = tid >> 4;
+#pragma unroll 1
+  for (int c = 0; c < kT; ++c) {
+    const int par = c & 1, cb = c >> 2, ci = c & 3;
+    if (trow == cb && tcol == cb) {
+      double d = 0.0;
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (i == ci) d = a[i][i];
+      if (!(d > 0.0)) {
+        *fail = 1;
+        d = __longlong_as_double(0x7ff8000000000000LL);
+      }
+      const double sd = sqrt(d);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        if (i == ci) a[i][i] = sd;
+      ps.pinv[par] = 1.0 / sd;
+    }
+    __syncthreads();
+    const double pinv = ps.pinv[par];
+    if (tcol == cb) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int row = 4 * trow + i;
+        double v = 0.0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (j == ci) {
+            if (row > c) a[i][j] *= pinv;
+            v = row > c ? a[i][j] : 0.0;
+          }
+        ps.col[par][row] = v;
+      }
+    }
+    if (trow == cb) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        double v = 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (i == ci) {
+            x[i][j] *= pinv;
+            v = x[i][j];
+          }
+        ps.xrow[par][4 * tcol + j] = v;
+      }
+    }
+    __syncthreads();
+    double lr[4], lc[4], xr[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) lr[i] = ps.col[par][4 * trow + i];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      lc[j] = ps.col[par][4 * tcol + j];
+      xr[j] = ps.xrow[par][4 * tcol + j];
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        a[i][j] -= lr[i] * lc[j];
+        x[i][j] -= lr[i] * xr[j];
+      }
+  }
+  __syncthreads();
+}
+
+// tile(i, jt) <- (trsm ? 0 : tile(i, jt)) -/+ A * B^T with A, B already in shared memory
+__device__ __forceinline__ void gemm_store(double* F, int m, const LargeFront& lf, int i, int jt, const double* As,
+                                           const double* Bs, bool trsm, double* keep /* optional smem copy */) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wr = warp & 3, wc = warp >> 2;
+  const int g = lane >> 2, tq = lane & 3;
+  const int ri = tile_start(lf, i), ni = tile_size(lf, i);
+  const int cj = tile_start(lf, jt), nj = tile_size(lf, jt);
+  double acc[2][4][2];
+#pragma unroll
+  for (int rb = 0; rb < 2; ++rb)
+#pragma unroll
+    for (int cb = 0; cb < 4; ++cb) acc[rb][cb][0] = acc[rb][cb][1] = 0.0;
+  double* C = F + ri + (size_t)cj * m;
+  tile_gemm(As, Bs, acc);
+  if (!trsm) {
+#pragma unroll
+    for (int rb = 0; rb < 2; ++rb)
+#pragma unroll
+      for (int cb = 0; cb < 4; ++cb)
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int r = wr * 16 + rb * 8 + g;
+          const int c = wc * 32 + cb * 8 + tq * 2 + e;
+          const double cin = (r < ni && c < nj) ? __ldcg(C + r + (size_t)c * m) : 0.0;
+          acc[rb][cb][e] = cin - acc[rb][cb][e];
+        }
+  }
+  if (keep != nullptr) __syncthreads();  // everyone finished reading As/Bs before `keep` (may alias) is written
+#pragma unroll
+  for (int rb = 0; rb < 2; ++rb)
+#pragma unroll
+    for (int cb = 0; cb < 4; ++cb)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int r = wr * 16 + rb * 8 + g;
+        const int c = wc * 32 + cb * 8 + tq * 2 + e;
+        const bool in = r < ni && c < nj;
+        if (in) C[r + (size_t)c * m] = acc[rb][cb][e];
+        if (keep != nullptr) keep[r + c * kLd] = in ? acc[rb][cb][e] : 0.0;
+      }
+}
+
+__device__ __forceinline__ void publish(int* flag, int v) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    st_release(flag, v);
+  }
+}
+__device__ __forceinline__ void wait_eq(const int* flag, int v) {
+  if (threadIdx.x == 0)
+    while (ld_acquire(flag) != v) __nanosleep(32);
+  __syncthreads();
+}
+__device__ __forceinline__ void wait_ge(const int* flag, int v) {
+  if (threadIdx.x == 0)
+    while (ld_acquire(flag) < v) __nanosleep(32);
+  __syncthreads();
+}
+
+__device__ unsigned long long* g_trace = nullptr;  // debug: [task][4] = claim, deps ready, done (ns), smid
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+void set_factor_trace(unsigned long long* buf) { cudaMemcpyToSymbol(g_trace, &buf, sizeof(buf)); }
+
 __global__ void __launch_bounds__(kLargeThreads) large_factor_kernel(Ctrl* ctrl, FrontDev fd, LargeDev ld, int t0,
                                                                      int t1, int level) {
   extern __shared__ double sm[];
   double* As = sm;
   double* Bs = sm + kT * kLd;
   __shared__ int s_task;
+  __shared__ PotrfSmem ps;
   if (ctrl->done) return;
   const int tid = threadIdx.x;
-  const int lane = tid & 31, warp = tid >> 5;
-  const int wr = warp & 3, wc = warp >> 2;
-  const int g = lane >> 2, tq = lane & 3;
   for (;;) {
     if (tid == 0) s_task = t0 + atomicAdd(&ld.queue[level], 1);
     __syncthreads();
@@ -100,123 +247,76 @@ __global__ void __launch_bounds__(kLargeThreads) large_factor_kernel(Ctrl* ctrl,
     const int m = lf.m, nt = lf.nt;
     int* cnt = ld.counters + lf.cnt_off;
     const int k = task.k, i = task.i, j = task.j;
-    if (task.type == 0) {
-      // ---------------- POTRF(k) ----------------
-      if (tid == 0)
-        while (ld_acquire(cnt + k * nt + k) != k) __nanosleep(40);
-      __syncthreads();
+    if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 0] = gtime();
+    if (task.type == 3) {
+      // ---------------- DIAG(k): POTRF(k), then TRSM(k+1,k) and UPDATE(k+1,k+1,k) on the critical path
+      wait_eq(cnt + k * nt + k, k);
+      if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 1] = gtime();
       const int s0 = tile_start(lf, k), nb = tile_size(lf, k);
-      load_tile(As, F + s0 + (size_t)s0 * m, m, nb, nb, true);
-      __syncthreads();
-      // Cholesky of the tile fused with the forward substitution L X = I (X = L^-1 in Bs, layout
-      // X[r + c*kLd]): per column one pivot, one scaling, one rank-1 update of both A and X.
-      double* X = Bs;
-      {
-        const int r = tid & 63;
-        for (int c = tid >> 6; c < kT; c += kLargeThreads / 64) X[r + c * kLd] = (r == c) ? 1.0 : 0.0;
-      }
-      __syncthreads();
-      for (int c = 0; c < kT; ++c) {
-        if (tid == 0) {
-          double d = As[c + c * kLd];
-          if (!(d > 0.0)) {
-            ctrl->chol_fail = 1;
-            d = __longlong_as_double(0x7ff8000000000000LL);
-          }
-          As[c + c * kLd] = sqrt(d);
+      const int trow = tid & 15, tcol = tid >> 4;
+      double a[4][4], x[4][4];
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii) {
+          const int r = 4 * trow + ii, c = 4 * tcol + jj;
+          double v = (r == c) ? 1.0 : 0.0;  // identity padding outside the nb x nb tile
+          if (r < nb && c < nb) v = (r >= c) ? __ldcg(F + (s0 + r) + (size_t)(s0 + c) * m) : 0.0;
+          a[ii][jj] = v;
+          x[ii][jj] = (r == c) ? 1.0 : 0.0;
         }
-        __syncthreads();
-        const double pinv = 1.0 / As[c + c * kLd];
-        if (tid > c && tid < kT) As[tid + c * kLd] *= pinv;        // column c of L
-        if (tid >= 64 && tid < 64 + c + 1) X[c + (tid - 64) * kLd] *= pinv;  // row c of X (cols 0..c)
-        __syncthreads();
-        {
-          const int r = tid & 63;
-          if (r > c) {
-            const double lrc = As[r + c * kLd];
-            for (int cc = c + 1 + (tid >> 6); cc <= r; cc += kLargeThreads / 64) As[r + cc * kLd] -= lrc * As[cc + c * kLd];
-            for (int cc = (tid >> 6); cc <= c; cc += kLargeThreads / 64) X[r + cc * kLd] -= lrc * X[c + cc * kLd];
-          }
-        }
-        __syncthreads();
-      }
+      potrf_inverse_64(a, x, ps, &ctrl->chol_fail);
       double* linv = ld.linv + lf.linv_off + (size_t)k * kT * kT;
-      {
-        const int r = tid & 63;
-        for (int c = tid >> 6; c < kT; c += kLargeThreads / 64) {
-          linv[r + c * kT] = X[r + c * kLd];
-          if (r < nb && c < nb && r >= c) F[(s0 + r) + (size_t)(s0 + c) * m] = As[r + c * kLd];
+#pragma unroll
+      for (int jj = 0; jj < 4; ++jj)
+#pragma unroll
+        for (int ii = 0; ii < 4; ++ii) {
+          const int r = 4 * trow + ii, c = 4 * tcol + jj;
+          const double xv = r >= c ? x[ii][jj] : 0.0;
+          linv[r + c * kT] = xv;
+          Bs[r + c * kLd] = xv;
+          if (r < nb && c < nb && r >= c) F[(s0 + r) + (size_t)(s0 + c) * m] = a[ii][jj];
         }
+      publish(cnt + k * nt + k, k + 1);
+      if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 3] = gtime();  // POTRF published
+      if (k + 1 < nt) {
+        // TRSM(k+1, k) with L_kk^-1 still in shared memory
+        wait_eq(cnt + (k + 1) * nt + k, k);
+        load_tile(As, F + tile_start(lf, k + 1) + (size_t)s0 * m, m, tile_size(lf, k + 1), nb, false);
+        __syncthreads();
+        gemm_store(F, m, lf, k + 1, k, As, Bs, true, As);  // result kept in As
+        publish(cnt + (k + 1) * nt + k, k + 1);
+        // UPDATE(k+1, k+1, k)
+        wait_eq(cnt + (k + 1) * nt + (k + 1), k);
+        gemm_store(F, m, lf, k + 1, k + 1, As, As, false, nullptr);
+        publish(cnt + (k + 1) * nt + (k + 1), k + 1);
       }
-      __syncthreads();
-      if (tid == 0) {
-        __threadfence();
-        st_release(cnt + k * nt + k, k + 1);
-      }
+      if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 2] = gtime();
     } else {
       // ---------------- TRSM(i,k) / UPDATE(i,j,k) ----------------
       const bool trsm = task.type == 1;
       if (tid == 0) {
         if (trsm) {
-          while (ld_acquire(cnt + k * nt + k) < k + 1) __nanosleep(40);
-          while (ld_acquire(cnt + i * nt + k) != k) __nanosleep(40);
+          while (ld_acquire(cnt + k * nt + k) < k + 1) __nanosleep(32);
+          while (ld_acquire(cnt + i * nt + k) != k) __nanosleep(32);
         } else {
-          while (ld_acquire(cnt + i * nt + k) < k + 1) __nanosleep(40);
-          while (ld_acquire(cnt + j * nt + k) < k + 1) __nanosleep(40);
-          while (ld_acquire(cnt + i * nt + j) != k) __nanosleep(40);
+          while (ld_acquire(cnt + i * nt + k) < k + 1) __nanosleep(32);
+          while (ld_acquire(cnt + j * nt + k) < k + 1) __nanosleep(32);
+          while (ld_acquire(cnt + i * nt + j) != k) __nanosleep(32);
         }
       }
       __syncthreads();
-      const int ri = tile_start(lf, i), ni = tile_size(lf, i);
+      if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 1] = gtime();
       const int ck = tile_start(lf, k), nk = tile_size(lf, k);
-      load_tile(As, F + ri + (size_t)ck * m, m, ni, nk, false);
-      int cj, nj;
-      if (trsm) {
-        cj = ck;
-        nj = nk;
+      load_tile(As, F + tile_start(lf, i) + (size_t)ck * m, m, tile_size(lf, i), nk, false);
+      if (trsm)
         load_tile(Bs, ld.linv + lf.linv_off + (size_t)k * kT * kT, kT, kT, kT, false);
-      } else {
-        cj = tile_start(lf, j);
-        nj = tile_size(lf, j);
-        load_tile(Bs, F + cj + (size_t)ck * m, m, nj, nk, false);
-      }
+      else
+        load_tile(Bs, F + tile_start(lf, j) + (size_t)ck * m, m, tile_size(lf, j), nk, false);
       __syncthreads();
-      double acc[2][4][2];
-#pragma unroll
-      for (int rb = 0; rb < 2; ++rb)
-#pragma unroll
-        for (int cb = 0; cb < 4; ++cb) acc[rb][cb][0] = acc[rb][cb][1] = 0.0;
-      double* C = F + ri + (size_t)cj * m;
-      tile_gemm(As, Bs, acc);
-      // C tile: all loads first (independent, one L2 latency), then subtract and store
-      if (!trsm) {
-#pragma unroll
-        for (int rb = 0; rb < 2; ++rb)
-#pragma unroll
-          for (int cb = 0; cb < 4; ++cb)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) {
-              const int r = wr * 16 + rb * 8 + g;
-              const int c = wc * 32 + cb * 8 + tq * 2 + e;
-              const double cin = (r < ni && c < nj) ? __ldcg(C + r + (size_t)c * m) : 0.0;
-              acc[rb][cb][e] = cin - acc[rb][cb][e];
-            }
-      }
-#pragma unroll
-      for (int rb = 0; rb < 2; ++rb)
-#pragma unroll
-        for (int cb = 0; cb < 4; ++cb)
-#pragma unroll
-          for (int e = 0; e < 2; ++e) {
-            const int r = wr * 16 + rb * 8 + g;
-            const int c = wc * 32 + cb * 8 + tq * 2 + e;
-            if (r < ni && c < nj) C[r + (size_t)c * m] = acc[rb][cb][e];
-          }
-      __syncthreads();
-      if (tid == 0) {
-        __threadfence();
-        st_release(cnt + i * nt + (trsm ? k : j), k + 1);
-      }
+      gemm_store(F, m, lf, i, trsm ? k : j, As, Bs, trsm, nullptr);
+      publish(cnt + i * nt + (trsm ? k : j), k + 1);
+      if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 2] = gtime();
     }
   }
 }

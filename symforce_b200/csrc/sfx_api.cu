@@ -20,6 +20,7 @@
 namespace sfx {
 
 extern int64_t g_launches;
+void set_factor_trace(unsigned long long* buf);
 
 #define CUDA_OK(expr)                                                                                   \
   do {                                                                                                  \
@@ -421,17 +422,24 @@ void upload_structures(sfx_problem* p) {
           const int li = lv.lf0 + q;
           const LargeFront& x = lfs[li];
           auto& tl = per[q];
+          // DIAG(k) = POTRF(k) + TRSM(k+1,k) + UPDATE(k+1,k+1,k) fused on one CTA (type 3); the three
+          // tasks the NEXT diagonal step waits for follow immediately, then DIAG(k+1) is hoisted in
+          // front of the bulk of step k (one step of look-ahead along the critical path)
+          auto T = [&](int i, int k) { tl.push_back(LargeTask{li, 1, (short)k, (short)i, (short)k}); };
+          auto U = [&](int i, int j, int k) { tl.push_back(LargeTask{li, 2, (short)k, (short)i, (short)j}); };
+          tl.push_back(LargeTask{li, 3, 0, 0, 0});
           for (int k = 0; k < x.wt; ++k) {
-            tl.push_back(LargeTask{li, 0, (short)k, (short)k, (short)k});
-            if (k + 1 < x.nt) {
-              tl.push_back(LargeTask{li, 1, (short)k, (short)(k + 1), (short)k});
-              tl.push_back(LargeTask{li, 2, (short)k, (short)(k + 1), (short)(k + 1)});
+            if (k + 2 < x.nt) {
+              T(k + 2, k);
+              U(k + 2, k + 1, k);
+              U(k + 2, k + 2, k);
             }
-            for (int i = k + 2; i < x.nt; ++i) tl.push_back(LargeTask{li, 1, (short)k, (short)i, (short)k});
+            if (k + 1 < x.wt) tl.push_back(LargeTask{li, 3, (short)(k + 1), (short)(k + 1), (short)(k + 1)});
+            for (int i = k + 3; i < x.nt; ++i) T(i, k);
             for (int j = k + 1; j < x.nt; ++j)
               for (int i = j; i < x.nt; ++i) {
-                if (i == k + 1 && j == k + 1) continue;
-                tl.push_back(LargeTask{li, 2, (short)k, (short)i, (short)j});
+                if (i <= k + 2 && j <= k + 2) continue;  // done by DIAG(k) / the priority tasks
+                U(i, j, k);
               }
           }
         }
@@ -899,6 +907,34 @@ sfx_status sfx_get_timings(sfx_problem* p, sfx_timings* out) {
   SFX_API_BEGIN
   SFX_CHECK(p && out, SFX_ERR_INVALID_ARG, "null argument");
   *out = p->tm;
+  SFX_API_END(p)
+}
+
+// debug: trace the tile-DAG tasks of the next factorizations (buffer of n_tasks*4 u64, device)
+sfx_status sfx_debug_trace_tasks(sfx_problem* p, unsigned long long* host_out, int32_t* n_tasks, int16_t* task_info) {
+  SFX_API_BEGIN
+  static unsigned long long* dbuf = nullptr;
+  static int64_t ntask = 0;
+  if (!host_out) {  // arm
+    ntask = 0;
+    for (auto& lv : p->lvl_large) ntask = std::max<int64_t>(ntask, lv.t1);
+    CUDA_OK(cudaMalloc(&dbuf, sizeof(unsigned long long) * 4 * ntask));
+    CUDA_OK(cudaMemset(dbuf, 0, sizeof(unsigned long long) * 4 * ntask));
+    sfx::set_factor_trace(dbuf);
+    *n_tasks = (int32_t)ntask;
+  } else {
+    CUDA_OK(cudaMemcpy(host_out, dbuf, sizeof(unsigned long long) * 4 * ntask, cudaMemcpyDeviceToHost));
+    std::vector<LargeTask> tk(ntask);
+    CUDA_OK(cudaMemcpy(tk.data(), p->ld.tasks, sizeof(LargeTask) * ntask, cudaMemcpyDeviceToHost));
+    for (int64_t i = 0; i < ntask; ++i) {
+      task_info[i * 5 + 0] = (int16_t)tk[i].lf;
+      task_info[i * 5 + 1] = tk[i].type;
+      task_info[i * 5 + 2] = tk[i].k;
+      task_info[i * 5 + 3] = tk[i].i;
+      task_info[i * 5 + 4] = tk[i].j;
+    }
+    sfx::set_factor_trace(nullptr);
+  }
   SFX_API_END(p)
 }
 

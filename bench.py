@@ -56,7 +56,7 @@ def workload_config(name):
                     f"Snavely reprojection + Schur + multifrontal Cholesky, DYNAMIC lambda",
         "n_cams": s["n_cams"], "n_pts": s["n_pts"], "n_obs": s["n_obs"],
         "l2": "inputs larger than L2 (block Hessian > 126 MB)" if s["n_obs"] * 27 * 8 > 126e6
-              else "working set fits L2; L2 flushed between timed calls",
+              else "working set fits L2 and is NOT flushed (parity/debug workload, not the headline)",
     }
 
 
@@ -118,33 +118,38 @@ class ClockSampler:
 
 
 def cpu_baseline(workload, max_seconds=40.0):
-    """The oracle (CPU restatement of the reference algorithm, 1 thread like the reference) on a
-    bounded sample of the workload: setup excluded, LM iterations timed."""
+    """The oracle (CPU restatement of the reference algorithm, 1 thread like the reference's
+    symforce/opt) on a bounded sample of the workload: LM iterations driven like the reference
+    benchmark (`Optimize(values, 1)`), timed by the oracle's own phase timers; index building,
+    METIS and symbolic factorization (first call) are excluded, like the GPU side's setup."""
     from symforce_b200 import desc as D, problems as P
     from tests import oracle_capi as O
 
     prob = P.bal_problem(workload, solver=D.SOLVER_SCHUR, params=never_exit_params())
     t0 = time.time()
     o = O.OracleProblem(prob)
-    o.optimize(1)  # warm-up iteration: index maps, METIS, symbolic factorization (excluded)
-    setup_s = time.time() - t0
-    o.reset_timings()
     iters = 0
-    t0 = time.time()
+    per_iter = []
     while True:
+        o.reset_timings()
         o.optimize(1)
+        tm = o.timings()
+        # one LM iteration = 1 linearize + 1 factorize + 1 solve (the first call linearizes twice)
+        per_iter.append(tm["linearize_s"] / max(tm["n_linearize"], 1) + tm["factorize_s"] / max(tm["n_factorize"], 1)
+                        + tm["solve_s"] / max(tm["n_factorize"], 1))
         iters += 1
-        el = time.time() - t0
-        if el > max_seconds / 2 or iters >= 20:
+        if sum(per_iter) > max_seconds / 2 or iters >= 20:
             break
-    el = time.time() - t0
-    tm = o.timings()
+    wall = time.time() - t0
+    it_s = float(np.mean(per_iter))
     return {
-        "value": iters / el, "unit": UNIT, "cores": 1, "kind": "port",
-        "sample": f"{iters} x Optimize(values, 1) LM iterations of the {workload}-shape problem (Schur + simplicial "
-                  f"LDLT on S), setup {setup_s:.1f}s excluded; per iteration linearize "
-                  f"{tm['linearize_s'] / max(tm['n_linearize'], 1) * 1e3:.1f} ms, factorize "
-                  f"{tm['factorize_s'] / max(tm['n_factorize'], 1) * 1e3:.1f} ms",
+        "value": 1.0 / it_s, "unit": UNIT, "cores": 1, "kind": "port",
+        "sample": f"{iters} LM iteration(s) of the {workload}-shape problem on the CPU oracle (Schur + simplicial LDLT on S, "
+                  f"single thread like the reference): {it_s * 1e3:.1f} ms per iteration = linearize "
+                  f"{tm['linearize_s'] / max(tm['n_linearize'], 1) * 1e3:.1f} + factorize "
+                  f"{tm['factorize_s'] / max(tm['n_factorize'], 1) * 1e3:.1f} + solve "
+                  f"{tm['solve_s'] / max(tm['n_factorize'], 1) * 1e3:.1f} ms; one-off setup (index maps, METIS, symbolic) "
+                  f"excluded; whole leg took {wall:.0f} s",
         "host_cores_available": os.cpu_count(),
     }
 
@@ -239,36 +244,59 @@ def main():
 
     if rank == 0:
         n_obs, n_cams, n_pts = shape["n_obs"], shape["n_cams"], shape["n_pts"]
-        lin_bytes = 256 * n_obs + 512 * n_cams + 96 * n_pts
-        lin_ms = tm["linearize_ms"] / max(tm["n_linearize"], 1)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        peak = peaks.get("hbm_gbs", 6650.0)
-        achieved = lin_bytes / (lin_ms * 1e-3) / 1e9
+        hbm = peaks.get("hbm_gbs", 6650.0)
+        hbm_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"
+        traffic = {}
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload, {})
+        except Exception:
+            pass
+        ph = {
+            "linearize": tm["linearize_ms"] / max(tm["n_linearize"], 1),
+            "schur": tm["schur_ms"] / K, "factorize": tm["factorize_ms"] / K, "solve": tm["solve_ms"] / K,
+            "update": tm["update_ms"] / K}
+        # algorithmic work per launch (DESIGN.md section 3 / SURVEY.md 8d)
+        lin_bytes = 256 * n_obs + 512 * n_cams + 96 * n_pts
+        schur_bytes = 216 * n_obs + 72 * n_pts + 432 * n_cams + 8 * 81 * info["s_blocks"]
+        fac_flops = float(info["factor_flops"])
+        fp64_peak = 40.0  # TFLOP/s nominal B200 FP64 (DMMA); MEASURED_PEAKS.json has no FP64 figure
+        rl_lin = {"kernel": "linearize_bal_kernel (+zero, error reduce)", "bound": "hbm",
+                  "achieved": lin_bytes / (ph["linearize"] * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                  "traffic": traffic.get("linearize_bal_kernel"), "peak_source": hbm_src}
+        rl_lin["frac"] = rl_lin["achieved"] / hbm
+        rl_schur = {"kernel": "schur_cinv/s/rhs kernels", "bound": "hbm",
+                    "achieved": schur_bytes / (ph["schur"] * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                    "traffic": traffic.get("schur_s_kernel"), "peak_source": hbm_src}
+        rl_schur["frac"] = rl_schur["achieved"] / hbm
+        rl_fac = {"kernel": "large_factor_kernel (tile-DAG supernodal Cholesky, DMMA m8n8k4)", "bound": "tensor",
+                  "achieved": fac_flops / (ph["factorize"] * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+                  "traffic": traffic.get("large_factor_kernel"),
+                  "peak_source": "nominal B200 FP64 tensor 40 TFLOP/s (no FP64 number in MEASURED_PEAKS.json)"}
+        rl_fac["frac"] = rl_fac["achieved"] / fp64_peak
+        dominant = max(("factorize", rl_fac), ("schur", rl_schur), ("linearize", rl_lin), key=lambda kv: ph[kv[0]])[1]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak" if world == 1 else "strong",
             "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": dict(workload_config(args.workload), parallelism=f"landmarks+observations sharded over {world} GPUs, NCCL reduce of S" if world > 1
+            "config": dict(workload_config(args.workload),
+                           parallelism=f"landmarks+observations sharded over {world} GPUs, NCCL reduce of S" if world > 1
                            else "1 GPU",
                            reduced_dim=info["reduced_dim"], nnz_L=info["nnz_L"], supernodes=info["num_supernodes"],
-                           levels=info["num_levels"], max_front=info["max_front"], setup_s=round(setup_s, 2)),
+                           levels=info["num_levels"], max_front=info["max_front"], factor_gflop=fac_flops / 1e9,
+                           setup_s=round(setup_s, 2)),
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(prob.values.nbytes),
                     "d2h_bytes_per_step": int(prob.values.nbytes)},
             "gpu_launches": int(tm["kernel_launches"]),
             "clocks": clocks,
-            "phases_ms_per_iteration": {
-                "linearize": tm["linearize_ms"] / max(tm["n_linearize"], 1),
-                "schur": tm["schur_ms"] / K, "factorize": tm["factorize_ms"] / K, "solve": tm["solve_ms"] / K,
-                "update": tm["update_ms"] / K},
-            "roofline": {"kernel": "linearize_kernel<snavely> (+zero, error reduce)", "bound": "hbm",
-                         "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None,
-                         "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"},
+            "phases_ms_per_iteration": ph,
+            "roofline": dominant,
+            "roofline_linearize": rl_lin, "roofline_schur": rl_schur, "roofline_factorize": rl_fac,
         }
         if args.cpu_baseline:
             try:

@@ -846,12 +846,208 @@ __global__ void schur_back_kernel(const Ctrl* __restrict__ ctrl, StatePtrs sp, S
   }
 }
 
+// ---- K3 fast path: landmarks of dim 3, reduced nodes of dim <= 16 -----------------------------------
+// (1) schur_g_rhs_kernel: one pass over the E blocks in camera-major order: G = C^-1 E is written
+//     next to E (same offsets, second buffer) and the reduced rhs  v_I - sum E^T (C^-1 w)  is
+//     accumulated (warp-level sum when the 32 blocks of a warp share the camera);
+// (2) schur_s_dmma_kernel: S_IJ -= sum_matches E_I^T G_J as FP64 tensor-core products
+//     (mma.sync.m8n8k4.f64, k = landmark dim padded to 4): per match 4 scalar loads + <= 4 DMMA per lane;
+// (3) schur_back_fast_kernel: per E block  s_l += E y_I  (RED atomics, 3 per block), then
+//     z_l = t_l - C^-1 s_l per landmark.
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+__global__ void schur_rhs_init_kernel(const Ctrl* __restrict__ ctrl, StatePtrs sp, SchurDev sd) {
+  if (ctrl->done) return;
+  const double* rhs = sp.rhs[ctrl->init_idx];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < sd.reduced_dim) sd.rhs_red[i] = sd.add_b ? rhs[i] : 0.0;
+  for (int q = i; q < sd.n_landmarks * 3; q += gridDim.x * blockDim.x) sd.sl[q] = 0.0;
+}
+
+constexpr int kGThreads = 128;
+__global__ void __launch_bounds__(kGThreads) schur_g_rhs_kernel(const Ctrl* __restrict__ ctrl, StatePtrs sp,
+                                                                SchurDev sd) {
+  if (ctrl->done) return;
+  const int q = blockIdx.x * kGThreads + threadIdx.x;
+  const bool valid = q < sd.n_entries;
+  const int qc = valid ? q : sd.n_entries - 1;
+  const double* __restrict__ H = sp.H[ctrl->init_idx];
+  const int I = sd.r_node[qc];
+  const int l = sd.r_lm[qc];
+  const int eoff = sd.r_eoff[qc];
+  const int dI = sd.node_dim[I];
+  const double* ci = sd.cinv + (size_t)l * 9;
+  const double c00 = ci[0], c10 = ci[1], c20 = ci[2], c11 = ci[4], c21 = ci[5], c22 = ci[8];
+  const double t0 = sd.tl[(size_t)l * 3], t1 = sd.tl[(size_t)l * 3 + 1], t2 = sd.tl[(size_t)l * 3 + 2];
+  const double* e = H + eoff;
+  double* g = sd.G + eoff;
+  double r[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) {
+    r[c] = 0.0;
+    if (c < dI && valid) {
+      const double e0 = e[3 * c], e1 = e[3 * c + 1], e2 = e[3 * c + 2];
+      g[3 * c] = c00 * e0 + c10 * e1 + c20 * e2;
+      g[3 * c + 1] = c10 * e0 + c11 * e1 + c21 * e2;
+      g[3 * c + 2] = c20 * e0 + c21 * e1 + c22 * e2;
+      r[c] = e0 * t0 + e1 * t1 + e2 * t2;
+    }
+  }
+  // reduced rhs: warp-level sum when the whole warp works on one camera
+  const int I0 = __shfl_sync(0xffffffffu, I, 0);
+  const bool uniform = __all_sync(0xffffffffu, I == I0);
+  const int lane = threadIdx.x & 31;
+  const int to = sd.node_toff[I];
+  if (uniform) {
+#pragma unroll
+    for (int c = 0; c < 16; ++c)
+      if (c < dI) {
+        double v = r[c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == c) atomicAdd(sd.rhs_red + to + c, -v);
+      }
+  } else if (valid) {
+#pragma unroll
+    for (int c = 0; c < 16; ++c)
+      if (c < dI) atomicAdd(sd.rhs_red + to + c, -r[c]);
+  }
+}
+
+__global__ void __launch_bounds__(kSchurWarps * 32) schur_s_dmma_kernel(const Ctrl* __restrict__ ctrl, StatePtrs sp,
+                                                                        SchurDev sd, const double* __restrict__ dvec) {
+  if (ctrl->done) return;
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * kSchurWarps + wid;
+  if (item >= sd.n_items) return;
+  const int b = sd.item_blk[item];
+  const int m0 = sd.item_m0[item], m1 = m0 + sd.item_cnt[item];
+  const int first = (sd.item_flags[item] & 1) && sd.add_b, single = (sd.item_flags[item] >> 1) & 1;
+  const double* __restrict__ H = sp.H[ctrl->init_idx];
+  const double* __restrict__ G = sd.G;
+  const int I = sd.s_row[b], J = sd.s_col[b];
+  const int dI = sd.node_dim[I], dJ = sd.node_dim[J];
+  const int g = lane >> 2, tq = lane & 3;
+  // fragment element offsets inside a 3 x d block (column-major, ld 3); -1: padding
+  const int a0 = (tq < 3 && g < dI) ? tq + 3 * g : -1;
+  const int a1 = (tq < 3 && g + 8 < dI) ? tq + 3 * (g + 8) : -1;
+  const int b0 = (tq < 3 && g < dJ) ? tq + 3 * g : -1;
+  const int b1 = (tq < 3 && g + 8 < dJ) ? tq + 3 * (g + 8) : -1;
+  const bool two_r = dI > 8, two_c = dJ > 8;
+  double acc[2][2][2] = {{{0, 0}, {0, 0}}, {{0, 0}, {0, 0}}};
+  // software pipeline: loads of match m+1 are in flight while the MMAs of match m issue
+  double fa0 = 0, fa1 = 0, fb0 = 0, fb1 = 0;
+  if (m0 < m1) {
+    const double* ei = H + sd.m_eoff_i[m0];
+    const double* gj = G + sd.m_eoff_j[m0];
+    fa0 = a0 >= 0 ? ei[a0] : 0.0;
+    fa1 = a1 >= 0 ? ei[a1] : 0.0;
+    fb0 = b0 >= 0 ? gj[b0] : 0.0;
+    fb1 = b1 >= 0 ? gj[b1] : 0.0;
+  }
+  for (int m = m0; m < m1; ++m) {
+    const double ca0 = fa0, ca1 = fa1, cb0 = fb0, cb1 = fb1;
+    if (m + 1 < m1) {
+      const double* ei = H + sd.m_eoff_i[m + 1];
+      const double* gj = G + sd.m_eoff_j[m + 1];
+      fa0 = a0 >= 0 ? ei[a0] : 0.0;
+      fa1 = a1 >= 0 ? ei[a1] : 0.0;
+      fb0 = b0 >= 0 ? gj[b0] : 0.0;
+      fb1 = b1 >= 0 ? gj[b1] : 0.0;
+    }
+    dmma884(acc[0][0][0], acc[0][0][1], ca0, cb0);
+    if (two_c) dmma884(acc[0][1][0], acc[0][1][1], ca0, cb1);
+    if (two_r) {
+      dmma884(acc[1][0][0], acc[1][0][1], ca1, cb0);
+      if (two_c) dmma884(acc[1][1][0], acc[1][1][1], ca1, cb1);
+    }
+  }
+  double* out = sd.S + sd.s_off[b];
+  const int bsrc = sd.s_b_src[b];
+  const int toI = sd.node_toff[I];
+#pragma unroll
+  for (int rb = 0; rb < 2; ++rb)
+#pragma unroll
+    for (int cb = 0; cb < 2; ++cb)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int r = rb * 8 + g, c = cb * 8 + tq * 2 + e;
+        if (r < dI && c < dJ) {
+          const int idx = r + c * dI;
+          double v = -acc[rb][cb][e];
+          if (first) {
+            if (bsrc >= 0) v += H[bsrc + idx];
+            if (I == J && r == c) v += dvec[toI + r];
+          }
+          if (single)
+            out[idx] = v;
+          else
+            atomicAdd(out + idx, v);
+        }
+      }
+}
+
+// s_l += E y_I per E block (camera-major), then z_l = t_l - C^-1 s_l per landmark
+__global__ void __launch_bounds__(kGThreads) schur_back_accum_kernel(const Ctrl* __restrict__ ctrl, StatePtrs sp,
+                                                                     SchurDev sd, const double* __restrict__ y) {
+  if (ctrl->done) return;
+  const int q = blockIdx.x * kGThreads + threadIdx.x;
+  if (q >= sd.n_entries) return;
+  const double* __restrict__ H = sp.H[ctrl->init_idx];
+  const int I = sd.r_node[q];
+  const int l = sd.r_lm[q];
+  const int dI = sd.node_dim[I];
+  const double* e = H + sd.r_eoff[q];
+  const double* yi = y + sd.node_toff[I];
+  double s0 = 0, s1 = 0, s2 = 0;
+#pragma unroll
+  for (int c = 0; c < 16; ++c)
+    if (c < dI) {
+      const double yc = yi[c];
+      s0 += e[3 * c] * yc;
+      s1 += e[3 * c + 1] * yc;
+      s2 += e[3 * c + 2] * yc;
+    }
+  atomicAdd(sd.sl + (size_t)l * 3, s0);
+  atomicAdd(sd.sl + (size_t)l * 3 + 1, s1);
+  atomicAdd(sd.sl + (size_t)l * 3 + 2, s2);
+}
+__global__ void schur_back_final_kernel(const Ctrl* __restrict__ ctrl, SchurDev sd, const double* __restrict__ y,
+                                        double* __restrict__ upd) {
+  if (ctrl->done) return;
+  const int l = blockIdx.x * blockDim.x + threadIdx.x;
+  const int stride = gridDim.x * blockDim.x;
+  for (int i = l; i < sd.reduced_dim; i += stride) upd[i] = -y[i];
+  if (l >= sd.n_landmarks) return;
+  const double* Ci = sd.cinv + (size_t)l * 9;
+  const double* t = sd.tl + (size_t)l * 3;
+  const double* s = sd.sl + (size_t)l * 3;
+  const int to = sd.lm_toff[l];
+#pragma unroll
+  for (int a = 0; a < 3; ++a) upd[to + a] = -(t[a] - (Ci[a] * s[0] + Ci[a + 3] * s[1] + Ci[a + 6] * s[2]));
+}
+
 void launch_schur(cudaStream_t st, const Ctrl* ctrl, StatePtrs sp, const SchurDev& sd, const double* dvec) {
   schur_cinv_kernel<<<(sd.n_landmarks + 127) / 128, 128, 0, st>>>(ctrl, sp, sd, dvec); ++g_launches;
   {
     int zg = (int)((sd.s_values + 255) / 256);
     if (zg > 148 * 8) zg = 148 * 8;
     zero_kernel<<<zg, 256, 0, st>>>(ctrl, sd.S, sd.s_values); ++g_launches;
+  }
+  if (sd.fast3) {
+    int n0 = sd.reduced_dim > sd.n_landmarks * 3 ? sd.reduced_dim : sd.n_landmarks * 3;
+    int ig = (n0 + 255) / 256;
+    if (ig > 148 * 8) ig = 148 * 8;
+    if (ig * 256 < sd.reduced_dim) ig = (sd.reduced_dim + 255) / 256;
+    schur_rhs_init_kernel<<<ig, 256, 0, st>>>(ctrl, sp, sd); ++g_launches;
+    schur_g_rhs_kernel<<<(sd.n_entries + kGThreads - 1) / kGThreads, kGThreads, 0, st>>>(ctrl, sp, sd); ++g_launches;
+    schur_s_dmma_kernel<<<(sd.n_items + kSchurWarps - 1) / kSchurWarps, kSchurWarps * 32, 0, st>>>(ctrl, sp, sd, dvec);
+    ++g_launches;
+    return;
   }
   schur_s_kernel<<<(sd.n_items + kSchurWarps - 1) / kSchurWarps, kSchurWarps * 32, 0, st>>>(ctrl, sp, sd, dvec); ++g_launches;
   schur_rhs_kernel<<<(sd.n_reduced_nodes + 3) / 4, 128, 0, st>>>(ctrl, sp, sd); ++g_launches;
@@ -860,6 +1056,12 @@ void launch_schur(cudaStream_t st, const Ctrl* ctrl, StatePtrs sp, const SchurDe
 void launch_schur_back(cudaStream_t st, const Ctrl* ctrl, StatePtrs sp, const SchurDev& sd, const double* y,
                        double* upd) {
   int n = sd.n_landmarks > sd.reduced_dim ? sd.n_landmarks : sd.reduced_dim;
+  if (sd.fast3) {
+    schur_back_accum_kernel<<<(sd.n_entries + kGThreads - 1) / kGThreads, kGThreads, 0, st>>>(ctrl, sp, sd, y);
+    ++g_launches;
+    schur_back_final_kernel<<<(n + 127) / 128, 128, 0, st>>>(ctrl, sd, y, upd); ++g_launches;
+    return;
+  }
   schur_back_kernel<<<(n + 127) / 128, 128, 0, st>>>(ctrl, sp, sd, y, upd); ++g_launches;
 }
 

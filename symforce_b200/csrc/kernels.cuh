@@ -73,6 +73,11 @@ struct SchurDev {
   const int32_t *item_blk, *item_m0, *item_cnt, *item_flags;
   int64_t s_values;
   const int32_t *r_ptr, *r_eoff, *r_lm;
+  // fast path (all landmarks dim 3, reduced nodes dim <= 16): entry -> reduced node, G = C^-1 E buffer
+  int fast3, n_entries;
+  const int32_t* r_node;
+  double* G;   // same offsets as the E blocks in H
+  double* sl;  // [n_landmarks][3] back-substitution accumulators
   double* cinv;   // [n_landmarks][9]
   double* tl;     // [n_landmarks][3]
   double* S;      // S values

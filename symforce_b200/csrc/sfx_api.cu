@@ -314,6 +314,19 @@ void upload_structures(sfx_problem* p) {
     d.tl = P.alloc<double>((size_t)s.n_landmarks * 3);
     d.S = P.alloc<double>(s.S.n_values);
     d.rhs_red = P.alloc<double>(s.reduced_dim);
+    {
+      bool fast = !getenv("SFX_NO_SCHUR_FAST");
+      for (int l = 0; l < s.n_landmarks && fast; ++l) fast = s.lm_dim[l] == 3;
+      for (int i = 0; i < s.first_lm_node && fast; ++i) fast = a.nodes[i].dim <= 16;
+      d.fast3 = fast ? 1 : 0;
+      d.n_entries = (int)s.r_eoff.size();
+      std::vector<int32_t> rnode(s.r_eoff.size());
+      for (int j = 0; j < s.first_lm_node; ++j)
+        for (int q = s.r_ptr[j]; q < s.r_ptr[j + 1]; ++q) rnode[q] = j;
+      d.r_node = P.upload(rnode);
+      d.G = fast ? P.alloc<double>(a.H.n_values) : nullptr;
+      d.sl = P.alloc<double>((size_t)s.n_landmarks * 3);
+    }
   }
   // fronts
   {

@@ -230,7 +230,7 @@ def main():
     for _ in range(K):
         gpu.set_values(pinned.numpy())
         gpu.optimize(1)
-        vals = gpu.best_values()
+        vals = gpu.best_values(out=out_pinned.numpy())
     barrier()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop()

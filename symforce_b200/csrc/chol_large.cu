@@ -77,40 +77,32 @@ __device__ __forceinline__ void tile_gemm(const double* As, const double* Bs, do
   }
 }
 
-// 64x64 Cholesky + inverse of the factor, register blocked: thread (trow, tcol) = (tid & 15, tid >> 4)
-// owns the 4x4 sub-block rows 4*trow.., cols 4*tcol.. of both A (-> L) and X (-> L^-1).  Per
-// column: the diagonal owner publishes 1/sqrt(d); the 16 owners of column c scale it and publish
-// it, the 16 owners of row c of X do the same; everyone applies the rank-1 update to its registers.
-// Two barriers per column (buffers alternate by column parity).
+// 64x64 Cholesky, register blocked: thread (trow, tcol) = (tid & 15, tid >> 4) owns the 4x4
+// sub-block rows 4*trow.., cols 4*tcol.. of A (-> L).  Per column: the 16 owners of column c scale
+// it by the pivot's reciprocal square root and publish it; everyone below the pivot applies the
+// rank-1 update to its registers; the owner of the next pivot prepares rsqrt right after its own
+// update.  Two barriers per column (buffers alternate by column parity).
 struct PotrfSmem {
   double col[2][kT];
-  double xrow[2][kT];
   double pinv[2];
 };
-__device__ __forceinline__ void potrf_inverse_64(double (&a)[4][4], double (&x)[4][4], PotrfSmem& ps, int* fail) {
+__device__ __forceinline__ void potrf_64(double (&a)[4][4], PotrfSmem& ps, int* fail) {
   const int tid = threadIdx.x;
   const int trow = tid & 15, tcol = tid >> 4;
+  if (trow == 0 && tcol == 0) {
+    double d = a[0][0];
+    if (!(d > 0.0)) {
+      *fail = 1;
+      d = __longlong_as_double(0x7ff8000000000000LL);
+    }
+    ps.pinv[0] = rsqrt(d);
+  }
+  __syncthreads();
 #pragma unroll 1
   for (int c = 0; c < kT; ++c) {
     const int par = c & 1, cb = c >> 2, ci = c & 3;
-    if (trow == cb && tcol == cb) {
-      double d = 0.0;
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if (i == ci) d = a[i][i];
-      if (!(d > 0.0)) {
-        *fail = 1;
-        d = __longlong_as_double(0x7ff8000000000000LL);
-      }
-      const double sd = sqrt(d);
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        if (i == ci) a[i][i] = sd;
-      ps.pinv[par] = 1.0 / sd;
-    }
-    __syncthreads();
-    const double pinv = ps.pinv[par];
     if (tcol == cb) {
+      const double pinv = ps.pinv[par];
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
         const int row = 4 * trow + i;
@@ -118,41 +110,112 @@ __device__ __forceinline__ void potrf_inverse_64(double (&a)[4][4], double (&x)[
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           if (j == ci) {
-            if (row > c) a[i][j] *= pinv;
+            if (row >= c) a[i][j] *= pinv;
             v = row > c ? a[i][j] : 0.0;
           }
         ps.col[par][row] = v;
       }
     }
-    if (trow == cb) {
+    __syncthreads();
+    if (trow >= cb && tcol >= cb) {  // only the trailing lower-right part changes
+      double lr[4], lc[4];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        double v = 0.0;
+      for (int i = 0; i < 4; ++i) lr[i] = ps.col[par][4 * trow + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) lc[j] = ps.col[par][4 * tcol + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) a[i][j] -= lr[i] * lc[j];
+      const int cn = c + 1;
+      if (cn < kT && trow == (cn >> 2) && tcol == (cn >> 2)) {
+        double d = 0.0;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-          if (i == ci) {
-            x[i][j] *= pinv;
-            v = x[i][j];
-          }
-        ps.xrow[par][4 * tcol + j] = v;
+          if (i == (cn & 3)) d = a[i][i];
+        if (!(d > 0.0)) {
+          *fail = 1;
+          d = __longlong_as_double(0x7ff8000000000000LL);
+        }
+        ps.pinv[cn & 1] = rsqrt(d);
       }
     }
     __syncthreads();
-    double lr[4], lc[4], xr[4];
+  }
+}
+
+// ---- X = L^-1 for the 64x64 lower-triangular tile in shared memory, blocked by 16 ------------------
+// diagonal 16x16 blocks by forward substitution (one warp each, one column per lane, registers);
+// off-diagonal blocks level by level with FP64 tensor-core products:
+//   X_ij = -X_ii * sum_{k=j}^{i-1} L_ik X_kj
+// acc += A(16x16) * B(16x16), both column-major in shared memory (one warp)
+__device__ __forceinline__ void warp_gemm16(const double* A, const double* B, double (&acc)[2][2][2]) {
+  const int lane = threadIdx.x & 31;
+  const int g = lane >> 2, tq = lane & 3;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) lr[i] = ps.col[par][4 * trow + i];
+  for (int kk = 0; kk < 16; kk += 4) {
+    const double a0 = A[g + (kk + tq) * kLd], a1 = A[8 + g + (kk + tq) * kLd];
+    const double b0 = B[(kk + tq) + g * kLd], b1 = B[(kk + tq) + (8 + g) * kLd];
+    mma884(acc[0][0][0], acc[0][0][1], a0, b0);
+    mma884(acc[0][1][0], acc[0][1][1], a0, b1);
+    mma884(acc[1][0][0], acc[1][0][1], a1, b0);
+    mma884(acc[1][1][0], acc[1][1][1], a1, b1);
+  }
+}
+__device__ __forceinline__ void warp_store16(double* C, const double (&acc)[2][2][2], double scale) {
+  const int lane = threadIdx.x & 31;
+  const int g = lane >> 2, tq = lane & 3;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      lc[j] = ps.col[par][4 * tcol + j];
-      xr[j] = ps.xrow[par][4 * tcol + j];
+  for (int rb = 0; rb < 2; ++rb)
+#pragma unroll
+    for (int cb = 0; cb < 2; ++cb)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) C[(rb * 8 + g) + (cb * 8 + tq * 2 + e) * kLd] = scale * acc[rb][cb][e];
+}
+// Ls: L (lower, zero above the diagonal), Xs: output (full tile written, zero above the diagonal)
+__device__ void tri_inverse_64(const double* Ls, double* Xs) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // zero X
+  for (int e = tid; e < kT * kT; e += kLargeThreads) Xs[(e & 63) + (e >> 6) * kLd] = 0.0;
+  __syncthreads();
+  // diagonal blocks: warp w < 4, lane j < 16 solves L_ww x = e_j
+  if (warp < 4 && lane < 16) {
+    const double* Lb = Ls + 16 * warp + 16 * warp * kLd;
+    double x[16];
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+      double v = (r == lane) ? 1.0 : 0.0;
+#pragma unroll
+      for (int q = 0; q < 16; ++q)
+        if (q < r) v -= Lb[r + q * kLd] * x[q];
+      x[r] = v / Lb[r + r * kLd];
     }
+    double* Xb = Xs + 16 * warp + (16 * warp + lane) * kLd;
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        a[i][j] -= lr[i] * lc[j];
-        x[i][j] -= lr[i] * xr[j];
-      }
+    for (int r = 0; r < 16; ++r) Xb[r] = (r >= lane) ? x[r] : 0.0;
+  }
+  __syncthreads();
+  // off-diagonal blocks, distance d = i - j; scratch for T = sum L_ik X_kj is the (unused) mirror block (j, i)
+#pragma unroll 1
+  for (int d = 1; d < 4; ++d) {
+    if (warp < 4 - d) {
+      const int j = warp, i = warp + d;
+      double acc[2][2][2] = {{{0, 0}, {0, 0}}, {{0, 0}, {0, 0}}};
+      for (int k = j; k < i; ++k) warp_gemm16(Ls + 16 * i + 16 * k * kLd, Xs + 16 * k + 16 * j * kLd, acc);
+      double* T = Xs + 16 * j + 16 * i * kLd;
+      warp_store16(T, acc, 1.0);
+      __syncwarp();
+      double acc2[2][2][2] = {{{0, 0}, {0, 0}}, {{0, 0}, {0, 0}}};
+      warp_gemm16(Xs + 16 * i + 16 * i * kLd, T, acc2);
+      __syncwarp();
+      warp_store16(Xs + 16 * i + 16 * j * kLd, acc2, -1.0);
+    }
+    __syncthreads();
+  }
+  // clear the scratch (upper blocks)
+  for (int e = tid; e < kT * kT; e += kLargeThreads) {
+    const int r = e & 63, c = e >> 6;
+    if ((r >> 4) < (c >> 4)) Xs[r + c * kLd] = 0.0;
   }
   __syncthreads();
 }
@@ -218,15 +281,17 @@ __device__ __forceinline__ void wait_ge(const int* flag, int v) {
   __syncthreads();
 }
 
-__device__ unsigned long long* g_trace = nullptr;  // debug: [task][4] = claim, deps ready, done (ns), smid
+__device__ unsigned long long* g_trace = nullptr;
+__device__ unsigned long long g_diag_stamps[8 * 512];  // debug: fine-grained DIAG phases  // debug: [task][4] = claim, deps ready, done (ns), smid
 __device__ __forceinline__ unsigned long long gtime() {
   unsigned long long t;
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
 void set_factor_trace(unsigned long long* buf) { cudaMemcpyToSymbol(g_trace, &buf, sizeof(buf)); }
+void get_diag_stamps(unsigned long long* out) { cudaMemcpyFromSymbol(out, g_diag_stamps, sizeof(unsigned long long) * 8 * 512); }
 
-__global__ void __launch_bounds__(kLargeThreads) large_factor_kernel(Ctrl* ctrl, FrontDev fd, LargeDev ld, int t0,
+__global__ void __launch_bounds__(kLargeThreads, 2) large_factor_kernel(Ctrl* ctrl, FrontDev fd, LargeDev ld, int t0,
                                                                      int t1, int level) {
   extern __shared__ double sm[];
   double* As = sm;
@@ -254,7 +319,7 @@ __global__ void __launch_bounds__(kLargeThreads) large_factor_kernel(Ctrl* ctrl,
       if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 1] = gtime();
       const int s0 = tile_start(lf, k), nb = tile_size(lf, k);
       const int trow = tid & 15, tcol = tid >> 4;
-      double a[4][4], x[4][4];
+      double a[4][4];
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj)
 #pragma unroll
@@ -263,20 +328,27 @@ __global__ void __launch_bounds__(kLargeThreads) large_factor_kernel(Ctrl* ctrl,
           double v = (r == c) ? 1.0 : 0.0;  // identity padding outside the nb x nb tile
           if (r < nb && c < nb) v = (r >= c) ? __ldcg(F + (s0 + r) + (size_t)(s0 + c) * m) : 0.0;
           a[ii][jj] = v;
-          x[ii][jj] = (r == c) ? 1.0 : 0.0;
         }
-      potrf_inverse_64(a, x, ps, &ctrl->chol_fail);
-      double* linv = ld.linv + lf.linv_off + (size_t)k * kT * kT;
+      if (g_trace && tid == 0 && k < 512) g_diag_stamps[k * 8 + 0] = gtime();
+      potrf_64(a, ps, &ctrl->chol_fail);
+      if (g_trace && tid == 0 && k < 512) g_diag_stamps[k * 8 + 1] = gtime();
 #pragma unroll
       for (int jj = 0; jj < 4; ++jj)
 #pragma unroll
         for (int ii = 0; ii < 4; ++ii) {
           const int r = 4 * trow + ii, c = 4 * tcol + jj;
-          const double xv = r >= c ? x[ii][jj] : 0.0;
-          linv[r + c * kT] = xv;
-          Bs[r + c * kLd] = xv;
+          As[r + c * kLd] = r >= c ? a[ii][jj] : 0.0;
           if (r < nb && c < nb && r >= c) F[(s0 + r) + (size_t)(s0 + c) * m] = a[ii][jj];
         }
+      __syncthreads();
+      if (g_trace && tid == 0 && k < 512) g_diag_stamps[k * 8 + 2] = gtime();
+      tri_inverse_64(As, Bs);
+      if (g_trace && tid == 0 && k < 512) g_diag_stamps[k * 8 + 3] = gtime();
+      double* linv = ld.linv + lf.linv_off + (size_t)k * kT * kT;
+      {
+        const int r = tid & 63;
+        for (int c = tid >> 6; c < kT; c += kLargeThreads / 64) linv[r + c * kT] = Bs[r + c * kLd];
+      }
       publish(cnt + k * nt + k, k + 1);
       if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 3] = gtime();  // POTRF published
       if (k + 1 < nt) {

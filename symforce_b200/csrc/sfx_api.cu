@@ -21,6 +21,7 @@ namespace sfx {
 
 extern int64_t g_launches;
 void set_factor_trace(unsigned long long* buf);
+void get_diag_stamps(unsigned long long* out);
 
 #define CUDA_OK(expr)                                                                                   \
   do {                                                                                                  \
@@ -924,6 +925,10 @@ sfx_status sfx_get_timings(sfx_problem* p, sfx_timings* out) {
 }
 
 // debug: trace the tile-DAG tasks of the next factorizations (buffer of n_tasks*4 u64, device)
+sfx_status sfx_debug_diag_stamps(unsigned long long* out) {
+  sfx::get_diag_stamps(out);
+  return SFX_OK;
+}
 sfx_status sfx_debug_trace_tasks(sfx_problem* p, unsigned long long* host_out, int32_t* n_tasks, int16_t* task_info) {
   SFX_API_BEGIN
   static unsigned long long* dbuf = nullptr;

@@ -262,8 +262,11 @@ class _LibProblem:
         self._check(self._fn("optimize")(self.h, C.c_int32(num_iterations), C.byref(st)), "optimize")
         return st
 
-    def best_values(self):
-        out = np.empty(self.n_values, dtype=np.float64)
+    def best_values(self, out=None):
+        """values = GetBestValues(); `out` (float64, contiguous, e.g. a pinned buffer) avoids the allocation."""
+        if out is None:
+            out = np.empty(self.n_values, dtype=np.float64)
+        assert out.dtype == np.float64 and out.flags["C_CONTIGUOUS"] and out.shape[0] == self.n_values
         self._check(self._fn("get_best_values")(self.h, out.ctypes.data_as(C.POINTER(C.c_double)),
                                                 C.c_int64(out.shape[0])), "get_best_values")
         return out

@@ -28,3 +28,10 @@ lf = np.bincount(info[m, 0]).argmax()
 mm = m & (info[:, 0] == lf)
 order = np.argsort(info[mm, 2])
 print("front", lf, "DIAG ready times (us) by k:", np.round(ready[mm][order][:12], 1), "done:", np.round(done[mm][order][:12], 1))
+
+st = np.zeros((512, 8), dtype=np.uint64)
+g.lib.sfx_debug_diag_stamps(st.ctypes.data_as(C.POINTER(C.c_uint64)))
+st = st.astype(np.int64)
+v = st[:40]
+print("DIAG phases (us, last writer per k): potrf", np.round(np.mean((v[:, 1] - v[:, 0]) / 1e3), 2), "store+sync",
+      np.round(np.mean((v[:, 2] - v[:, 1]) / 1e3), 2), "inverse", np.round(np.mean((v[:, 3] - v[:, 2]) / 1e3), 2))

@@ -77,68 +77,64 @@ __device__ __forceinline__ void tile_gemm(const double* As, const double* Bs, do
   }
 }
 
-// 64x64 Cholesky, register blocked: thread (trow, tcol) = (tid & 15, tid >> 4) owns the 4x4
-// sub-block rows 4*trow.., cols 4*tcol.. of A (-> L).  Per column: the 16 owners of column c scale
-// it by the pivot's reciprocal square root and publish it; everyone below the pivot applies the
-// rank-1 update to its registers; the owner of the next pivot prepares rsqrt right after its own
-// update.  Two barriers per column (buffers alternate by column parity).
-struct PotrfSmem {
-  double col[2][kT];
-  double pinv[2];
-};
-__device__ __forceinline__ void potrf_64(double (&a)[4][4], PotrfSmem& ps, int* fail) {
-  const int tid = threadIdx.x;
-  const int trow = tid & 15, tcol = tid >> 4;
-  if (trow == 0 && tcol == 0) {
-    double d = a[0][0];
-    if (!(d > 0.0)) {
-      *fail = 1;
-      d = __longlong_as_double(0x7ff8000000000000LL);
-    }
-    ps.pinv[0] = rsqrt(d);
-  }
-  __syncthreads();
+// 64x64 Cholesky of the tile in shared memory (lower part valid, ld = kLd), panels of 8 columns.
+// A panel is factored by ONE warp with shuffles only (lane l holds rows l and l+32 of the panel in
+// registers; per column: broadcast the pivot, rsqrt on every lane, scale, rank-1 update inside the
+// panel with the pivot row's entries broadcast from their owner lane) -- no block barrier inside the
+// 8-column chain.  The other warps join for the rank-8 trailing update; two barriers per panel.
+constexpr int kPW = 8;
+__device__ __forceinline__ void potrf_64_panels(double* As, int* fail) {
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 #pragma unroll 1
-  for (int c = 0; c < kT; ++c) {
-    const int par = c & 1, cb = c >> 2, ci = c & 3;
-    if (tcol == cb) {
-      const double pinv = ps.pinv[par];
+  for (int p = 0; p < kT / kPW; ++p) {
+    const int c0 = p * kPW;
+    if (warp == (p & 7)) {
+      double a0[kPW], a1[kPW];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int row = 4 * trow + i;
-        double v = 0.0;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (j == ci) {
-            if (row >= c) a[i][j] *= pinv;
-            v = row > c ? a[i][j] : 0.0;
-          }
-        ps.col[par][row] = v;
+      for (int j = 0; j < kPW; ++j) {
+        a0[j] = As[lane + (c0 + j) * kLd];
+        a1[j] = As[lane + 32 + (c0 + j) * kLd];
       }
-    }
-    __syncthreads();
-    if (trow >= cb && tcol >= cb) {  // only the trailing lower-right part changes
-      double lr[4], lc[4];
+      const bool hi = c0 >= 32;  // pivot rows of this panel live in slot 1 (rows 32..63)
 #pragma unroll
-      for (int i = 0; i < 4; ++i) lr[i] = ps.col[par][4 * trow + i];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) lc[j] = ps.col[par][4 * tcol + j];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) a[i][j] -= lr[i] * lc[j];
-      const int cn = c + 1;
-      if (cn < kT && trow == (cn >> 2) && tcol == (cn >> 2)) {
-        double d = 0.0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-          if (i == (cn & 3)) d = a[i][i];
+      for (int j = 0; j < kPW; ++j) {
+        const int c = c0 + j;
+        double d = __shfl_sync(0xffffffffu, hi ? a1[j] : a0[j], c & 31);
         if (!(d > 0.0)) {
           *fail = 1;
           d = __longlong_as_double(0x7ff8000000000000LL);
         }
-        ps.pinv[cn & 1] = rsqrt(d);
+        const double pinv = rsqrt(d);
+        if (lane >= c) a0[j] *= pinv;       // rows lane (< 32)
+        if (lane + 32 >= c) a1[j] *= pinv;  // rows lane + 32
+#pragma unroll
+        for (int jj = j + 1; jj < kPW; ++jj) {
+          const int rr = c0 + jj;  // pivot-panel row whose entry in column c multiplies column jj
+          const double l = __shfl_sync(0xffffffffu, hi ? a1[j] : a0[j], rr & 31);
+          if (lane > c) a0[jj] -= a0[j] * l;
+          if (lane + 32 > c) a1[jj] -= a1[j] * l;
+        }
       }
+#pragma unroll
+      for (int j = 0; j < kPW; ++j) {
+        As[lane + (c0 + j) * kLd] = lane >= c0 + j ? a0[j] : 0.0;
+        As[lane + 32 + (c0 + j) * kLd] = lane + 32 >= c0 + j ? a1[j] : 0.0;
+      }
+    }
+    __syncthreads();
+    // trailing update: A[r][cc] -= sum_j L[r][c0+j] L[cc][c0+j] for cc >= c0 + 8, r >= cc
+    {
+      const int r = tid & 63;
+      double lr[kPW];
+#pragma unroll
+      for (int j = 0; j < kPW; ++j) lr[j] = As[r + (c0 + j) * kLd];
+      for (int cc = c0 + kPW + (tid >> 6); cc < kT; cc += kLargeThreads / 64)
+        if (r >= cc) {
+          double v = As[r + cc * kLd];
+#pragma unroll
+          for (int j = 0; j < kPW; ++j) v -= lr[j] * As[cc + (c0 + j) * kLd];
+          As[r + cc * kLd] = v;
+        }
     }
     __syncthreads();
   }
@@ -297,7 +293,6 @@ __global__ void __launch_bounds__(kLargeThreads, 2) large_factor_kernel(Ctrl* ct
   double* As = sm;
   double* Bs = sm + kT * kLd;
   __shared__ int s_task;
-  __shared__ PotrfSmem ps;
   if (ctrl->done) return;
   const int tid = threadIdx.x;
   for (;;) {
@@ -318,28 +313,18 @@ __global__ void __launch_bounds__(kLargeThreads, 2) large_factor_kernel(Ctrl* ct
       wait_eq(cnt + k * nt + k, k);
       if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 1] = gtime();
       const int s0 = tile_start(lf, k), nb = tile_size(lf, k);
-      const int trow = tid & 15, tcol = tid >> 4;
-      double a[4][4];
-#pragma unroll
-      for (int jj = 0; jj < 4; ++jj)
-#pragma unroll
-        for (int ii = 0; ii < 4; ++ii) {
-          const int r = 4 * trow + ii, c = 4 * tcol + jj;
-          double v = (r == c) ? 1.0 : 0.0;  // identity padding outside the nb x nb tile
-          if (r < nb && c < nb) v = (r >= c) ? __ldcg(F + (s0 + r) + (size_t)(s0 + c) * m) : 0.0;
-          a[ii][jj] = v;
-        }
+      load_tile(As, F + s0 + (size_t)s0 * m, m, nb, nb, true);
+      __syncthreads();
       if (g_trace && tid == 0 && k < 512) g_diag_stamps[k * 8 + 0] = gtime();
-      potrf_64(a, ps, &ctrl->chol_fail);
+      potrf_64_panels(As, &ctrl->chol_fail);
       if (g_trace && tid == 0 && k < 512) g_diag_stamps[k * 8 + 1] = gtime();
-#pragma unroll
-      for (int jj = 0; jj < 4; ++jj)
-#pragma unroll
-        for (int ii = 0; ii < 4; ++ii) {
-          const int r = 4 * trow + ii, c = 4 * tcol + jj;
-          As[r + c * kLd] = r >= c ? a[ii][jj] : 0.0;
-          if (r < nb && c < nb && r >= c) F[(s0 + r) + (size_t)(s0 + c) * m] = a[ii][jj];
+      {
+        const int r = tid & 63;
+        for (int c = tid >> 6; c < kT; c += kLargeThreads / 64) {
+          if (r < c) As[r + c * kLd] = 0.0;  // the inverse and the TRSM read the full tile
+          if (r < nb && c < nb && r >= c) F[(s0 + r) + (size_t)(s0 + c) * m] = As[r + c * kLd];
         }
+      }
       __syncthreads();
       if (g_trace && tid == 0 && k < 512) g_diag_stamps[k * 8 + 2] = gtime();
       tri_inverse_64(As, Bs);

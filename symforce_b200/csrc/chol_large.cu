@@ -11,6 +11,7 @@
 // (ld.acquire / st.release), so the diagonal critical path overlaps the trailing updates without
 // kernel-launch boundaries.  Tile data is read with ld.global.cg (L2 is the coherence point).
 #include <cstdio>
+#include <cstdlib>
 
 #include "kernels.cuh"
 
@@ -444,10 +445,6 @@ void launch_large_level(cudaStream_t st, Ctrl* ctrl, const FrontDev& fd, const L
   large_factor_kernel<<<grid, kLargeThreads, smem, st>>>(ctrl, fd, ld, lv.t0, lv.t1, level); ++g_launches;
 }
 
-cudaError_t configure_large_kernels() {
-  return cudaFuncSetAttribute(large_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                              (int)(2 * kT * kLd * sizeof(double)));
-}
 
 // ---- triangular solves on large fronts -------------------------------------------------------------
 // P cooperating CTAs per front; tile-row i of the front is owned by CTA i % P.  The dependency
@@ -607,20 +604,339 @@ __global__ void __launch_bounds__(256) large_solve_bwd_kernel(const Ctrl* __rest
   }
 }
 
+
+// ---- v2 solves: every L / L_kk^-1 tile a CTA will touch is known up front (the sequence depends only
+// on the front geometry), so tiles stream into a 4-stage shared-memory ring with cp.async while the
+// CTA waits on the dependency flags; the chain step is then flag latency + one smem mat-vec.
+constexpr int kSStages = 4;
+constexpr int kSLd = 65;  // conflict-free for both T*x (lanes over rows) and T^T*x (lanes over columns)
+__device__ __forceinline__ void cp_async8(double* smem, const double* g) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void issue_tile(double* T, const double* __restrict__ G, int ldg, int nr, int nc) {
+  const int r = threadIdx.x & 63;
+  if (r < nr)
+    for (int c = threadIdx.x >> 6; c < nc; c += kLargeThreads / 64) cp_async8(T + r + c * kSLd, G + r + (size_t)c * ldg);
+}
+struct SolveItem {
+  int kind, i, k;  // kind 0: L_kk^-1 tile of pivot tile k (i == k); 1: L tile (i, k)
+};
+// forward order of CTA p: for k = 0..wt-1: [L_kk^-1 if k % P == p], then the owned tile rows i > k
+struct FwdIter {
+  int k, i, phase;
+  __device__ void init() { k = 0; i = 0; phase = 0; }
+  __device__ bool next(const LargeFront& lf, int p, int P, SolveItem& it) {
+    for (;;) {
+      if (k >= lf.wt) return false;
+      if (phase == 0) {
+        phase = 1;
+        i = k + 1 + (((p - (k + 1)) % P) + P) % P;
+        if (k % P == p) {
+          it = SolveItem{0, k, k};
+          return true;
+        }
+      }
+      if (i < lf.nt) {
+        it = SolveItem{1, i, k};
+        i += P;
+        return true;
+      }
+      ++k;
+      phase = 0;
+    }
+  }
+};
+// backward order of CTA p: owned tile rows from the bottom up: [L_ii^-1 if i < wt], then tiles (i, k), k descending
+struct BwdIter {
+  int i, k, phase;
+  __device__ void init(const LargeFront& lf, int p, int P) {
+    i = lf.nt - 1 - (((lf.nt - 1 - p) % P) + P) % P;
+    k = 0;
+    phase = 0;
+  }
+  __device__ bool next(const LargeFront& lf, int P, SolveItem& it) {
+    for (;;) {
+      if (i < 0) return false;
+      if (phase == 0) {
+        phase = 1;
+        k = min(i, lf.wt) - 1;
+        if (i < lf.wt) {
+          it = SolveItem{0, i, i};
+          return true;
+        }
+      }
+      if (k >= 0) {
+        it = SolveItem{1, i, k};
+        --k;
+        return true;
+      }
+      i -= P;
+      phase = 0;
+    }
+  }
+};
+__device__ __forceinline__ void issue_item(double* T, const SolveItem& it, const LargeFront& lf, const double* L,
+                                           const double* linv) {
+  if (it.kind == 0)
+    issue_tile(T, linv + (size_t)it.k * kT * kT, kT, kT, kT);
+  else
+    issue_tile(T, L + tile_start(lf, it.i) + (size_t)(it.k * kT) * lf.m, lf.m, tile_size(lf, it.i), tile_size(lf, it.k));
+}
+// red[gq*64 + r] = sum_{c = gq, gq+4, ..} T[r][c] * x[c]       (r < nr, c < nc)
+__device__ __forceinline__ void smem_gemv_part(const double* T, int nr, int nc, const double* x, double* red) {
+  const int r = threadIdx.x & 63, gq = threadIdx.x >> 6;
+  double v = 0.0;
+  if (r < nr) {
+#pragma unroll 4
+    for (int c = gq; c < nc; c += 4) v += T[r + c * kSLd] * x[c];
+  }
+  red[gq * 64 + r] = v;
+}
+// red[gq*64 + c] = sum_{r = gq, gq+4, ..} T[r][c] * x[r]
+__device__ __forceinline__ void smem_gemv_t_part(const double* T, int nr, int nc, const double* x, double* red) {
+  const int c = threadIdx.x & 63, gq = threadIdx.x >> 6;
+  double v = 0.0;
+  if (c < nc) {
+#pragma unroll 4
+    for (int r = gq; r < nr; r += 4) v += T[r + c * kSLd] * x[r];
+  }
+  red[gq * 64 + c] = v;
+}
+
+__global__ void __launch_bounds__(kLargeThreads, 1)
+    large_solve_fwd2_kernel(const Ctrl* __restrict__ ctrl, FrontDev fd, LargeDev ld, const double* __restrict__ rhs_static,
+                            StatePtrs sp, int use_state_rhs, int lf0, int P) {
+  extern __shared__ double smf[];  // stages | own: ceil(nt/P)*64 | y: 64 | red: 256
+  if (ctrl->done) return;
+  const LargeFront lf = ld.lf[lf0 + blockIdx.x / P];
+  const int p = blockIdx.x % P;
+  const int s = lf.front, w = lf.w, m = lf.m, nt = lf.nt, wt = lf.wt;
+  const int n_own = (nt - p + P - 1) / P;
+  double* stages = smf;
+  double* own = stages + kSStages * kT * kSLd;
+  double* yk = own + (size_t)((nt + P - 1) / P) * kT;
+  double* red = yk + kT;
+  const double* rhs = use_state_rhs ? sp.rhs[ctrl->init_idx] : rhs_static;
+  const double* L = fd.fronts + lf.off;
+  const double* linv = ld.linv + lf.linv_off;
+  int* flag = ld.sflags + lf.flag_off;
+  const int tid = threadIdx.x;
+  // ---- start streaming the tiles of this CTA's sequence
+  FwdIter prod, cons;
+  prod.init();
+  cons.init();
+  SolveItem it;
+  for (int st = 0; st < kSStages - 1; ++st) {
+    if (prod.next(lf, p, P, it)) issue_item(stages + st * kT * kSLd, it, lf, L, linv);
+    cp_async_commit();
+  }
+  // ---- assemble the owned part of the front right-hand side
+  for (int q = tid; q < n_own * kT; q += kLargeThreads) {
+    const int i = p + (q / kT) * P, r = q % kT;
+    const int row = tile_start(lf, i) + r;
+    double v = 0.0;
+    if (r < tile_size(lf, i) && row < w) v = rhs[fd.scalar_perm[fd.f_piv[s] + row]];
+    own[q] = v;
+  }
+  __syncthreads();
+  for (int ci = fd.f_child_ptr[s]; ci < fd.f_child_ptr[s + 1]; ++ci) {
+    const int c = fd.f_child[ci];
+    const int uc = fd.f_u[c];
+    const double* t = fd.twork + fd.f_toff[c];
+    const int32_t* rel = fd.f_rel + fd.f_rows_ptr[c];
+    for (int q = tid; q < uc; q += kLargeThreads) {
+      const int row = rel[q];
+      const int i = row < w ? row / kT : wt + (row - w) / kT;
+      if (i % P == p) own[(i / P) * kT + (row - tile_start(lf, i))] += t[q];  // rows of one child are distinct
+    }
+    __syncthreads();
+  }
+  // ---- forward substitution
+  int cur_k = -1, n = 0;
+  while (cons.next(lf, p, P, it)) {
+    {
+      SolveItem nx;
+      if (prod.next(lf, p, P, nx)) issue_item(stages + ((n + kSStages - 1) % kSStages) * kT * kSLd, nx, lf, L, linv);
+      cp_async_commit();
+    }
+    const double* T = stages + (n % kSStages) * kT * kSLd;
+    const int k = it.k;
+    if (it.kind == 1 && k != cur_k) {
+      // y_k of another CTA: wait for its flag (tiles keep streaming in meanwhile)
+      if (tid == 0)
+        while (ld_acquire(flag + k) == 0) __nanosleep(20);
+      __syncthreads();
+      if (tid < kT) yk[tid] = tid < tile_size(lf, k) ? __ldcg(fd.ywork + fd.f_piv[s] + k * kT + tid) : 0.0;
+      cur_k = k;
+    }
+    cp_async_wait<kSStages - 1>();
+    __syncthreads();
+    if (it.kind == 0) {
+      // y_k = L_kk^-1 f_k, published for the other CTAs
+      const int nb = tile_size(lf, k);
+      smem_gemv_part(T, kT, kT, own + (k / P) * kT, red);
+      __syncthreads();
+      if (tid < kT) {
+        const double v = red[tid] + red[64 + tid] + red[128 + tid] + red[192 + tid];
+        yk[tid] = tid < nb ? v : 0.0;
+        if (tid < nb) fd.ywork[fd.f_piv[s] + k * kT + tid] = v;
+      }
+      __syncthreads();
+      if (tid == 0) {
+        __threadfence();
+        st_release(flag + k, 1);
+      }
+      cur_k = k;
+    } else {
+      const int i = it.i;
+      const int ni = tile_size(lf, i);
+      smem_gemv_part(T, ni, tile_size(lf, k), yk, red);
+      __syncthreads();
+      if (tid < ni) own[(i / P) * kT + tid] -= red[tid] + red[64 + tid] + red[128 + tid] + red[192 + tid];
+      __syncthreads();
+    }
+    ++n;
+  }
+  cp_async_wait<0>();
+  // ---- update part -> twork (pivot part was published tile by tile)
+  for (int q = tid; q < n_own * kT; q += kLargeThreads) {
+    const int i = p + (q / kT) * P, r = q % kT;
+    if (i >= wt && r < tile_size(lf, i)) fd.twork[fd.f_toff[s] + (tile_start(lf, i) - w) + r] = own[q];
+  }
+}
+
+__global__ void __launch_bounds__(kLargeThreads, 1)
+    large_solve_bwd2_kernel(const Ctrl* __restrict__ ctrl, FrontDev fd, LargeDev ld, int lf0, int P) {
+  extern __shared__ double smf[];  // stages | x: 64 | g: 64 | red: 256
+  if (ctrl->done) return;
+  const LargeFront lf = ld.lf[lf0 + blockIdx.x / P];
+  const int p = blockIdx.x % P;
+  const int s = lf.front, w = lf.w, nt = lf.nt, wt = lf.wt;
+  double* stages = smf;
+  double* xi = stages + kSStages * kT * kSLd;
+  double* g = xi + kT;
+  double* red = g + kT;
+  const double* L = fd.fronts + lf.off;
+  const double* linv = ld.linv + lf.linv_off;
+  int* cntb = ld.sflags + lf.flag_off + wt;  // contributions received per pivot tile
+  double* contrib = ld.contrib + lf.contrib_off;
+  const int tid = threadIdx.x;
+  const int32_t* rows = fd.f_rows + fd.f_rows_ptr[s];
+  BwdIter prod, cons;
+  prod.init(lf, p, P);
+  cons.init(lf, p, P);
+  SolveItem it;
+  for (int st = 0; st < kSStages - 1; ++st) {
+    if (prod.next(lf, P, it)) issue_item(stages + st * kT * kSLd, it, lf, L, linv);
+    cp_async_commit();
+  }
+  int cur_i = -1, n = 0;
+  while (cons.next(lf, P, it)) {
+    {
+      SolveItem nx;
+      if (prod.next(lf, P, nx)) issue_item(stages + ((n + kSStages - 1) % kSStages) * kT * kSLd, nx, lf, L, linv);
+      cp_async_commit();
+    }
+    const double* T = stages + (n % kSStages) * kT * kSLd;
+    const int i = it.i;
+    const int ni = tile_size(lf, i), ri = tile_start(lf, i);
+    if (it.kind == 0) {
+      // pivot tile i: all contributions of the rows below, then x_i = L_ii^-T (y_i - sum)
+      if (tid == 0)
+        while (ld_acquire(cntb + i) < nt - 1 - i) __nanosleep(20);
+      __syncthreads();
+      {
+        const int t = tid & 63, gq = tid >> 6;
+        double v = 0.0;
+        if (t < ni) {
+#pragma unroll 4
+          for (int r = i + 1 + gq; r < nt; r += 4) v += __ldcg(contrib + ((size_t)i * nt + r) * kT + t);
+        }
+        red[gq * 64 + t] = v;
+      }
+      __syncthreads();
+      if (tid < kT)
+        g[tid] = tid < ni ? fd.ywork[fd.f_piv[s] + ri + tid] - (red[tid] + red[64 + tid] + red[128 + tid] + red[192 + tid]) : 0.0;
+      cp_async_wait<kSStages - 1>();
+      __syncthreads();
+      smem_gemv_t_part(T, kT, kT, g, red);
+      __syncthreads();
+      if (tid < kT) {
+        const double v = red[tid] + red[64 + tid] + red[128 + tid] + red[192 + tid];
+        xi[tid] = tid < ni ? v : 0.0;
+        if (tid < ni) fd.ywork[fd.f_piv[s] + ri + tid] = v;
+      }
+      __syncthreads();
+      cur_i = i;
+    } else {
+      if (i != cur_i) {
+        // update rows: x known from the ancestors
+        if (tid < kT) xi[tid] = tid < ni ? fd.ywork[rows[ri - w + tid]] : 0.0;
+        cur_i = i;
+      }
+      cp_async_wait<kSStages - 1>();
+      __syncthreads();
+      const int k = it.k;
+      const int nk = tile_size(lf, k);
+      smem_gemv_t_part(T, ni, nk, xi, red);
+      __syncthreads();
+      if (tid < nk) contrib[((size_t)k * nt + i) * kT + tid] = red[tid] + red[64 + tid] + red[128 + tid] + red[192 + tid];
+      __syncthreads();
+      if (tid == 0) {
+        __threadfence();
+        atomicAdd(cntb + k, 1);
+      }
+    }
+    ++n;
+  }
+  cp_async_wait<0>();
+}
+
+static bool solve_v1() {
+  static const bool v = getenv("SFX_SOLVE_V1") != nullptr;
+  return v;
+}
+
 void launch_large_solve_fwd(cudaStream_t st, const Ctrl* ctrl, const FrontDev& fd, const LargeDev& ld,
                             const LargeLevel& lv, const double* rhs_static, StatePtrs sp, int use_state_rhs) {
   if (lv.n_lf == 0) return;
   const int P = lv.solve_p;
   const size_t smem = (size_t)(((lv.max_nt + P - 1) / P) * kT + kT + 256) * sizeof(double);
-  large_solve_fwd_kernel<<<lv.n_lf * P, 256, smem, st>>>(ctrl, fd, ld, rhs_static, sp, use_state_rhs, lv.lf0, P);
+  if (solve_v1()) {
+    large_solve_fwd_kernel<<<lv.n_lf * P, 256, smem, st>>>(ctrl, fd, ld, rhs_static, sp, use_state_rhs, lv.lf0, P);
+  } else {
+    const size_t smem2 = smem + (size_t)kSStages * kT * kSLd * sizeof(double);
+    large_solve_fwd2_kernel<<<lv.n_lf * P, kLargeThreads, smem2, st>>>(ctrl, fd, ld, rhs_static, sp, use_state_rhs,
+                                                                       lv.lf0, P);
+  }
   ++g_launches;
 }
 void launch_large_solve_bwd(cudaStream_t st, const Ctrl* ctrl, const FrontDev& fd, const LargeDev& ld,
                             const LargeLevel& lv) {
   if (lv.n_lf == 0) return;
   const int P = lv.solve_p;
-  large_solve_bwd_kernel<<<lv.n_lf * P, 256, 3 * kT * sizeof(double), st>>>(ctrl, fd, ld, lv.lf0, P);
+  if (solve_v1()) {
+    large_solve_bwd_kernel<<<lv.n_lf * P, 256, 3 * kT * sizeof(double), st>>>(ctrl, fd, ld, lv.lf0, P);
+  } else {
+    const size_t smem2 = (size_t)(kSStages * kT * kSLd + 2 * kT + 256) * sizeof(double);
+    large_solve_bwd2_kernel<<<lv.n_lf * P, kLargeThreads, smem2, st>>>(ctrl, fd, ld, lv.lf0, P);
+  }
   ++g_launches;
+}
+
+cudaError_t configure_large_kernels() {
+  cudaError_t e = cudaFuncSetAttribute(large_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)(2 * kT * kLd * sizeof(double)));
+  if (e != cudaSuccess) return e;
+  e = cudaFuncSetAttribute(large_solve_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+  if (e != cudaSuccess) return e;
+  return cudaFuncSetAttribute(large_solve_bwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
 }
 
 }  // namespace sfx

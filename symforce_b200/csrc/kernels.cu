@@ -276,6 +276,9 @@ __device__ __forceinline__ int value_of_lane(int lane) {
 }
 
 constexpr int kBalThreads = 128;
+// SKIP (timing experiments only, results invalid when != 0): bit0 camera block, bit1 point block,
+// bit2 E block, bit3 factor arithmetic
+template <int SKIP>
 __global__ void __launch_bounds__(kBalThreads) linearize_bal_kernel(const Ctrl* __restrict__ ctrl, StatePtrs sp,
                                                                     LinBatch b, int mode,
                                                                     double* __restrict__ partials) {
@@ -297,7 +300,14 @@ __global__ void __launch_bounds__(kBalThreads) linearize_bal_kernel(const Ctrl* 
     const double* a1 = values + __ldg(b.arg_off + (size_t)b.n + sc);
     const double* a2 = values + __ldg(b.arg_off + (size_t)2 * b.n + sc);
     const double* a3 = values + __ldg(b.arg_off + (size_t)3 * b.n + sc);
-    sfx_factor_snavely(a0, a1, a2, a3, nullptr, res, J);
+    if (SKIP & 8) {
+      res[0] = a0[0] + a1[0] + a2[0] + a3[0];
+      res[1] = a0[6] + a1[2] + a2[2] + a3[1];
+#pragma unroll
+      for (int i = 0; i < 24; ++i) J[i] = res[i & 1] * (i + 1);
+    } else {
+      sfx_factor_snavely(a0, a1, a2, a3, nullptr, res, J);
+    }
   }
   if (!valid) {
     res[0] = res[1] = 0.0;
@@ -318,7 +328,8 @@ __global__ void __launch_bounds__(kBalThreads) linearize_bal_kernel(const Ctrl* 
   // ---- camera block: 45 lower entries (column-major packed) + 9 rhs ------------------------------
   const int key0 = __shfl_sync(0xffffffffu, cam_diag, 0);
   const bool uniform = __all_sync(0xffffffffu, !valid || cam_diag == key0);
-  if (uniform) {
+  if (SKIP & 1) {
+  } else if (uniform) {
     double v[32];
     // batch 0: packed entries 0..31
     {
@@ -380,7 +391,7 @@ __global__ void __launch_bounds__(kBalThreads) linearize_bal_kernel(const Ctrl* 
     for (int r = 0; r < 9; ++r) atomicAdd(rhs + cam_rhs + r, J[2 * r] * res[0] + J[2 * r + 1] * res[1]);
   }
   // ---- point block ---------------------------------------------------------------------------------
-  if (valid) {
+  if (valid && !(SKIP & 2)) {
 #pragma unroll
     for (int c = 0; c < 3; ++c)
 #pragma unroll
@@ -391,7 +402,7 @@ __global__ void __launch_bounds__(kBalThreads) linearize_bal_kernel(const Ctrl* 
     for (int r = 0; r < 3; ++r) atomicAdd(rhs + pt_rhs + r, J[2 * (9 + r)] * res[0] + J[2 * (9 + r) + 1] * res[1]);
   }
   // ---- E block (point rows x camera cols), owned by the observation --------------------------------
-  {
+  if (!(SKIP & 4)) {
     const uint32_t off = eo & 0x3fffffffu;
     const bool excl = (eo >> 31) != 0;
     const uint32_t off0 = __shfl_sync(0xffffffffu, off, 0);
@@ -517,10 +528,23 @@ void launch_zero_lin(cudaStream_t st, const Ctrl* ctrl, StatePtrs sp, int mode, 
   zero_lin_kernel<<<grid, 256, 0, st>>>(ctrl, sp, mode, n_h, n_rhs); ++g_launches;
 }
 
+int g_lin_skip = 0;  // debug (sfx_debug_time_linearize): parts of linearize_bal_kernel to leave out
 void launch_linearize(cudaStream_t st, const Ctrl* ctrl, StatePtrs sp, int mode, const LinBatch& b, double* partials) {
   const int grid = (b.n + kLinThreads - 1) / kLinThreads;
   if (b.bal_fast) {
-    linearize_bal_kernel<<<grid, kBalThreads, 0, st>>>(ctrl, sp, b, mode, partials); ++g_launches;
+    switch (g_lin_skip) {
+#define SFX_SKIP_CASE(V) \
+  case V: linearize_bal_kernel<V><<<grid, kBalThreads, 0, st>>>(ctrl, sp, b, mode, partials); break;
+      SFX_SKIP_CASE(1)
+      SFX_SKIP_CASE(2)
+      SFX_SKIP_CASE(4)
+      SFX_SKIP_CASE(7)
+      SFX_SKIP_CASE(8)
+      SFX_SKIP_CASE(15)
+#undef SFX_SKIP_CASE
+      default: linearize_bal_kernel<0><<<grid, kBalThreads, 0, st>>>(ctrl, sp, b, mode, partials); break;
+    }
+    ++g_launches;
     return;
   }
   switch (b.kind) {
@@ -667,6 +691,24 @@ __global__ void schur_cinv_kernel(const Ctrl* __restrict__ ctrl, StatePtrs sp, S
     if (r < d) w[r] = rhs[to + r];
 #pragma unroll
   for (int r = 0; r < 3; ++r) sd.tl[(size_t)l * 3 + r] = Ci[r][0] * w[0] + Ci[r][1] * w[1] + Ci[r][2] * w[2];
+  if (sd.wl != nullptr) {
+    // fast path: whitening factor L^-1 (C + D = L L^T) and u = L^-1 w, so that
+    // E^T C^-1 E = (L^-1 E)^T (L^-1 E) and E^T C^-1 w = (L^-1 E)^T u
+    const double i00 = 1.0 / L[0][0], i11 = 1.0 / L[1][1], i22 = 1.0 / L[2][2];
+    const double i10 = -L[1][0] * i00 * i11;
+    const double i21 = -L[2][1] * i11 * i22;
+    const double i20 = -(L[2][0] * i00 + L[2][1] * i10) * i22;
+    double* o = sd.wl + (size_t)l * 9;
+    o[0] = i00;
+    o[1] = i10;
+    o[2] = i11;
+    o[3] = i20;
+    o[4] = i21;
+    o[5] = i22;
+    o[6] = i00 * w[0];
+    o[7] = i10 * w[0] + i11 * w[1];
+    o[8] = i20 * w[0] + i21 * w[1] + i22 * w[2];
+  }
 }
 
 // One warp per work item = (S block, chunk of <= 32 matches): partial = sum_matches E_I^T C^-1 E_J.
@@ -991,6 +1033,222 @@ __global__ void __launch_bounds__(kSchurWarps * 32) schur_s_dmma_kernel(const Ct
       }
 }
 
+// ---- K3 fast path, v2 ------------------------------------------------------------------------------
+// (1) schur_w_rhs_kernel: W = L^-1 E (whitened point-camera blocks, written to the second buffer at the
+//     offsets of E) and the reduced rhs v_I - sum W^T u.  A warp's 32 blocks are one contiguous run in
+//     camera-major order: they are read and written coalesced through shared memory.
+// (2) schur_s2_kernel: S_IJ -= sum_matches W_I^T W_J with the matches stacked along k: one
+//     mma.sync.m8n8k4.f64 step covers 4/3 matches (no k padding); a 9 x 9 block takes 3 DMMAs per step
+//     (the 9th row x 9th column corner is one FMA per lane + a 4-lane reduction at the end).  Match
+//     offsets are loaded once per 32 matches (one coalesced load) and broadcast with shuffles; the
+//     loads of the next four k-steps (16 per lane) are in flight while the current four issue.
+constexpr int kWThreads = 128;
+__global__ void __launch_bounds__(kWThreads) schur_w_rhs_kernel(const Ctrl* __restrict__ ctrl, StatePtrs sp,
+                                                                SchurDev sd) {
+  __shared__ double stage[kWThreads / 32][32 * 27];
+  if (ctrl->done) return;
+  const int q = blockIdx.x * kWThreads + threadIdx.x;
+  const bool valid = q < sd.n_entries;
+  const int qc = valid ? q : sd.n_entries - 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const double* __restrict__ H = sp.H[ctrl->init_idx];
+  const int I = __ldg(sd.r_node + qc);
+  const int l = __ldg(sd.r_lm + qc);
+  const int eoff = __ldg(sd.r_eoff + qc);
+  const int dI = __ldg(sd.node_dim + I);
+  const double* wl = sd.wl + (size_t)l * 9;
+  const double i00 = wl[0], i10 = wl[1], i11 = wl[2], i20 = wl[3], i21 = wl[4], i22 = wl[5];
+  const double u0 = wl[6], u1 = wl[7], u2 = wl[8];
+  const int I0 = __shfl_sync(0xffffffffu, I, 0);
+  const bool uniform = __all_sync(0xffffffffu, I == I0);
+  const int eoff0 = __shfl_sync(0xffffffffu, eoff, 0);
+  const int n = 3 * dI;
+  const bool staged = uniform && dI == 9 && __all_sync(0xffffffffu, valid && eoff == eoff0 + n * lane);
+  double r[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) r[c] = 0.0;
+  if (staged) {
+    double* st = stage[warp];
+    const double* src = H + eoff0;
+    {
+      double t[27];
+#pragma unroll
+      for (int i = 0; i < 27; ++i) t[i] = src[i * 32 + lane];
+#pragma unroll
+      for (int i = 0; i < 27; ++i) st[i * 32 + lane] = t[i];
+    }
+    __syncwarp();
+    double* e = st + lane * 27;
+#pragma unroll
+    for (int c = 0; c < 9; ++c) {
+      {
+        const double e0 = e[3 * c], e1 = e[3 * c + 1], e2 = e[3 * c + 2];
+        const double w0 = i00 * e0, w1 = i10 * e0 + i11 * e1, w2 = i20 * e0 + i21 * e1 + i22 * e2;
+        e[3 * c] = w0;
+        e[3 * c + 1] = w1;
+        e[3 * c + 2] = w2;
+        r[c] = w0 * u0 + w1 * u1 + w2 * u2;
+      }
+    }
+    __syncwarp();
+    double* dst = sd.G + eoff0;
+#pragma unroll
+    for (int i = 0; i < 27; ++i) dst[i * 32 + lane] = st[i * 32 + lane];
+  } else {
+    const double* e = H + eoff;
+    double* g = sd.G + eoff;
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+      r[c] = 0.0;
+      if (c < dI && valid) {
+        const double e0 = e[3 * c], e1 = e[3 * c + 1], e2 = e[3 * c + 2];
+        const double w0 = i00 * e0, w1 = i10 * e0 + i11 * e1, w2 = i20 * e0 + i21 * e1 + i22 * e2;
+        g[3 * c] = w0;
+        g[3 * c + 1] = w1;
+        g[3 * c + 2] = w2;
+        r[c] = w0 * u0 + w1 * u1 + w2 * u2;
+      }
+    }
+  }
+  const int to = sd.node_toff[I];
+  if (uniform) {
+#pragma unroll
+    for (int c = 0; c < 16; ++c)
+      if (c < dI && (c < 9 || !staged)) {
+        double v = r[c];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == c) atomicAdd(sd.rhs_red + to + c, -v);
+      }
+  } else if (valid) {
+#pragma unroll
+    for (int c = 0; c < 16; ++c)
+      if (c < dI) atomicAdd(sd.rhs_red + to + c, -r[c]);
+  }
+}
+
+struct alignas(16) SItem2 {
+  int32_t m0, cnt;
+  int32_t flags;  // bit0 first chunk of the block, bit1 only chunk, bits 8..15 dI, bits 16..23 dJ, bit 24: I == J
+  int32_t toI;
+  int64_t s_off;
+  int32_t bsrc, pad;
+};
+static_assert(sizeof(SItem2) == 32, "SItem2 layout");
+
+__global__ void __launch_bounds__(kSchurWarps * 32, 4) schur_s2_kernel(const Ctrl* __restrict__ ctrl, StatePtrs sp,
+                                                                      SchurDev sd, const double* __restrict__ dvec) {
+  if (ctrl->done) return;
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int item = blockIdx.x * kSchurWarps + wid;
+  if (item >= sd.n_items) return;
+  SItem2 it;
+  {
+    const int4* ip = reinterpret_cast<const int4*>(sd.items2) + (size_t)item * 2;
+    const int4 a = __ldg(ip), b = __ldg(ip + 1);
+    it.m0 = a.x;
+    it.cnt = a.y;
+    it.flags = a.z;
+    it.toI = a.w;
+    it.s_off = ((int64_t)(uint32_t)b.x) | ((int64_t)b.y << 32);
+    it.bsrc = b.z;
+  }
+  const double* __restrict__ W = sd.G;
+  const double* __restrict__ zp = sd.zeros;
+  const int dI = (it.flags >> 8) & 0xff, dJ = (it.flags >> 16) & 0xff;
+  const int g = lane >> 2, tq = lane & 3;
+  const bool two_r = dI > 8, two_c = dJ > 8;
+  const bool corner_fma = dI == 9 && dJ == 9;
+  // element offsets of this lane's fragment rows inside a 3 x d block; rows/cols >= d are padding
+  const bool va0 = g < dI, va1 = g + 8 < dI, vb0 = g < dJ, vb1 = g + 8 < dJ;
+  const int ra0 = 3 * g, ra1 = 3 * (g + 8);
+  double acc[2][2][2] = {{{0, 0}, {0, 0}}, {{0, 0}, {0, 0}}};
+  double corner = 0.0;
+  for (int base = 0; base < it.cnt; base += 32) {
+    const int nm = min(32, it.cnt - base);
+    int oi = 0, oj = 0;
+    if (lane < nm) {
+      oi = __ldg(sd.m_eoff_i + it.m0 + base + lane);
+      oj = __ldg(sd.m_eoff_j + it.m0 + base + lane);
+    }
+    const int K = 3 * nm;
+    const int nsteps = (K + 3) >> 2;
+    double fa0[2][4], fa1[2][4], fb0[2][4], fb1[2][4];
+    auto load_group = [&](int s0, int buf) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int kk = 4 * (s0 + u) + tq;
+        const bool ok = kk < K;
+        const int mm = (kk * 43) >> 7;  // kk / 3 for kk < 128
+        const int a = kk - 3 * mm;
+        const int offI = __shfl_sync(0xffffffffu, oi, mm & 31);
+        const int offJ = __shfl_sync(0xffffffffu, oj, mm & 31);
+        const double* pa = W + offI + a;
+        const double* pb = W + offJ + a;
+        // padding lanes read a zero from `zp`: the select is on the address, so nothing consumes the
+        // loaded value before the MMA and the loads of a group stay in flight together
+        fa0[buf][u] = __ldg((ok && va0) ? pa + ra0 : zp);
+        fb0[buf][u] = __ldg((ok && vb0) ? pb + ra0 : zp);
+        fa1[buf][u] = __ldg((ok && va1) ? pa + ra1 : zp);
+        fb1[buf][u] = __ldg((ok && vb1) ? pb + ra1 : zp);
+      }
+    };
+    auto mma_group = [&](int buf) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        dmma884(acc[0][0][0], acc[0][0][1], fa0[buf][u], fb0[buf][u]);
+        if (two_c) dmma884(acc[0][1][0], acc[0][1][1], fa0[buf][u], fb1[buf][u]);
+        if (two_r) {
+          dmma884(acc[1][0][0], acc[1][0][1], fa1[buf][u], fb0[buf][u]);
+          if (corner_fma)
+            corner += fa1[buf][u] * fb1[buf][u];
+          else if (two_c)
+            dmma884(acc[1][1][0], acc[1][1][1], fa1[buf][u], fb1[buf][u]);
+        }
+      }
+    };
+    load_group(0, 0);
+    for (int s0 = 0; s0 < nsteps; s0 += 8) {
+      if (s0 + 4 < nsteps) load_group(s0 + 4, 1);
+      mma_group(0);
+      if (s0 + 4 < nsteps) {
+        if (s0 + 8 < nsteps) load_group(s0 + 8, 0);
+        mma_group(1);
+      }
+    }
+  }
+  if (corner_fma) {
+    // lanes g == 0 hold the k-partials of entry (8, 8)
+    corner += __shfl_xor_sync(0xffffffffu, corner, 1);
+    corner += __shfl_xor_sync(0xffffffffu, corner, 2);
+    if (lane == 0) acc[1][1][0] = corner;
+  }
+  const double* __restrict__ H = sp.H[ctrl->init_idx];
+  double* out = sd.S + it.s_off;
+  const int first = (it.flags & 1) && sd.add_b, single = (it.flags >> 1) & 1;
+  const bool diag = (it.flags >> 24) & 1;
+#pragma unroll
+  for (int rb = 0; rb < 2; ++rb)
+#pragma unroll
+    for (int cb = 0; cb < 2; ++cb)
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        const int r = rb * 8 + g, c = cb * 8 + tq * 2 + e;
+        if (r < dI && c < dJ) {
+          const int idx = r + c * dI;
+          double v = -acc[rb][cb][e];
+          if (first) {
+            if (it.bsrc >= 0) v += H[it.bsrc + idx];
+            if (diag && r == c) v += dvec[it.toI + r];
+          }
+          if (single)
+            out[idx] = v;
+          else
+            atomicAdd(out + idx, v);
+        }
+      }
+}
+
 // s_l += E y_I per E block (camera-major), then z_l = t_l - C^-1 s_l per landmark
 __global__ void __launch_bounds__(kGThreads) schur_back_accum_kernel(const Ctrl* __restrict__ ctrl, StatePtrs sp,
                                                                      SchurDev sd, const double* __restrict__ y) {
@@ -1044,6 +1302,12 @@ void launch_schur(cudaStream_t st, const Ctrl* ctrl, StatePtrs sp, const SchurDe
     if (ig > 148 * 8) ig = 148 * 8;
     if (ig * 256 < sd.reduced_dim) ig = (sd.reduced_dim + 255) / 256;
     schur_rhs_init_kernel<<<ig, 256, 0, st>>>(ctrl, sp, sd); ++g_launches;
+    if (sd.wl != nullptr) {
+      schur_w_rhs_kernel<<<(sd.n_entries + kWThreads - 1) / kWThreads, kWThreads, 0, st>>>(ctrl, sp, sd); ++g_launches;
+      schur_s2_kernel<<<(sd.n_items + kSchurWarps - 1) / kSchurWarps, kSchurWarps * 32, 0, st>>>(ctrl, sp, sd, dvec);
+      ++g_launches;
+      return;
+    }
     schur_g_rhs_kernel<<<(sd.n_entries + kGThreads - 1) / kGThreads, kGThreads, 0, st>>>(ctrl, sp, sd); ++g_launches;
     schur_s_dmma_kernel<<<(sd.n_items + kSchurWarps - 1) / kSchurWarps, kSchurWarps * 32, 0, st>>>(ctrl, sp, sd, dvec);
     ++g_launches;

@@ -76,7 +76,10 @@ struct SchurDev {
   // fast path (all landmarks dim 3, reduced nodes dim <= 16): entry -> reduced node, G = C^-1 E buffer
   int fast3, n_entries;
   const int32_t* r_node;
-  double* G;   // same offsets as the E blocks in H
+  double* G;   // same offsets as the E blocks in H (v1: C^-1 E; v2: W = L^-1 E)
+  double* wl;  // v2: [n_landmarks][9] = L^-1 (i00 i10 i11 i20 i21 i22), u = L^-1 w; nullptr selects v1
+  const double* zeros;  // 8 zero doubles (padding lanes of the DMMA fragments load from here)
+  const void* items2;  // v2: packed 32-byte item headers (SItem2 in kernels.cu)
   double* sl;  // [n_landmarks][3] back-substitution accumulators
   double* cinv;   // [n_landmarks][9]
   double* tl;     // [n_landmarks][3]

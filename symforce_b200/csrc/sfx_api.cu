@@ -20,6 +20,7 @@
 namespace sfx {
 
 extern int64_t g_launches;
+extern int g_lin_skip;
 void set_factor_trace(unsigned long long* buf);
 void get_diag_stamps(unsigned long long* out);
 
@@ -301,6 +302,26 @@ void upload_structures(sfx_problem* p) {
           ifl.push_back((c == 0 ? 1 : 0) | (nch == 1 ? 2 : 0));
         }
       }
+      {
+        // packed headers for schur_s2_kernel
+        std::vector<int32_t> hdr(ib.size() * 8);
+        for (size_t q = 0; q < ib.size(); ++q) {
+          const int b = ib[q];
+          const int I = srow[b], J = scol[b];
+          const int dI = a.nodes[I].dim, dJ = a.nodes[J].dim;
+          const int64_t so = s.S.blk_off[b];
+          int32_t* h = &hdr[q * 8];
+          h[0] = im[q];
+          h[1] = ic[q];
+          h[2] = ifl[q] | (dI << 8) | (dJ << 16) | ((I == J ? 1 : 0) << 24);
+          h[3] = a.nodes[I].toff;
+          h[4] = (int32_t)(uint32_t)(so & 0xffffffffll);
+          h[5] = (int32_t)(so >> 32);
+          h[6] = s.s_b_src[b];
+          h[7] = 0;
+        }
+        d.items2 = P.upload(hdr);
+      }
       d.n_items = (int)ib.size();
       d.item_blk = P.upload(ib);
       d.item_m0 = P.upload(im);
@@ -326,6 +347,8 @@ void upload_structures(sfx_problem* p) {
         for (int q = s.r_ptr[j]; q < s.r_ptr[j + 1]; ++q) rnode[q] = j;
       d.r_node = P.upload(rnode);
       d.G = fast ? P.alloc<double>(a.H.n_values) : nullptr;
+      d.wl = (fast && !getenv("SFX_SCHUR_V1")) ? P.alloc<double>((size_t)s.n_landmarks * 9) : nullptr;
+      d.zeros = P.upload(std::vector<double>(8, 0.0));
       d.sl = P.alloc<double>((size_t)s.n_landmarks * 3);
     }
   }
@@ -921,6 +944,32 @@ sfx_status sfx_get_timings(sfx_problem* p, sfx_timings* out) {
   SFX_API_BEGIN
   SFX_CHECK(p && out, SFX_ERR_INVALID_ARG, "null argument");
   *out = p->tm;
+  SFX_API_END(p)
+}
+
+// debug: average time of `reps` linearizations of state block 0 (zero + kernels + error reduce), with
+// parts of the BAL kernel left out when skip != 0 (timing experiment; leaves an invalid linearization)
+sfx_status sfx_debug_time_linearize(sfx_problem* p, int32_t skip, int32_t reps, float* ms) {
+  SFX_API_BEGIN
+  SFX_CHECK(p && ms && reps > 0, SFX_ERR_INVALID_ARG, "bad argument");
+  CUDA_OK(cudaSetDevice(p->device));
+  reset_ctrl(p);
+  for (int b = 0; b < 3; ++b) launch_copy_values(p->st, p->sp.values[b], p->d_cur_values, p->a.n_values);
+  cudaEvent_t e0, e1;
+  CUDA_OK(cudaEventCreate(&e0));
+  CUDA_OK(cudaEventCreate(&e1));
+  sfx::g_lin_skip = skip;
+  enqueue_linearize(p, 1);
+  CUDA_OK(cudaEventRecord(e0, p->st));
+  for (int r = 0; r < reps; ++r) enqueue_linearize(p, 1);
+  CUDA_OK(cudaEventRecord(e1, p->st));
+  sfx::g_lin_skip = 0;
+  CUDA_OK(cudaStreamSynchronize(p->st));
+  float t = 0;
+  CUDA_OK(cudaEventElapsedTime(&t, e0, e1));
+  *ms = t / reps;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
   SFX_API_END(p)
 }
 

@@ -278,6 +278,51 @@ __device__ __forceinline__ void wait_ge(const int* flag, int v) {
   __syncthreads();
 }
 
+// ---- range updates: tile(i,j) -= sum_{kk in [k,k1)} L(i,kk) L(j,kk)^T with the accumulator in registers.
+// The operand tiles are consumed as 64 x 32 half tiles, double buffered in shared memory; the next
+// half tile pair is loaded into registers (ld.global.cg: tiles are produced by other CTAs of the same
+// launch, and tile boundaries are not sector aligned, so L1 must not be involved) while the tensor
+// cores work on the current one.
+constexpr int kHalf = 32;
+constexpr int kHalfDoubles = kHalf * kLd;
+constexpr int kHalfPerThread = kT * kHalf / kLargeThreads;  // 8
+__device__ __forceinline__ void load_half(double (&v)[kHalfPerThread], const double* F, int m, const LargeFront& lf,
+                                          int t, int kk, int c0) {
+  const int nr = tile_size(lf, t), nc = tile_size(lf, kk);
+  const double* G = F + tile_start(lf, t) + (size_t)(kk * kT + c0) * m;
+  const int r = threadIdx.x & 63;
+#pragma unroll
+  for (int q = 0; q < kHalfPerThread; ++q) {
+    const int c = (threadIdx.x >> 6) + q * (kLargeThreads / 64);
+    v[q] = (r < nr && c0 + c < nc) ? __ldcg(G + r + (size_t)c * m) : 0.0;
+  }
+}
+__device__ __forceinline__ void store_half(double* S, const double (&v)[kHalfPerThread]) {
+  const int r = threadIdx.x & 63;
+#pragma unroll
+  for (int q = 0; q < kHalfPerThread; ++q) S[r + ((threadIdx.x >> 6) + q * (kLargeThreads / 64)) * kLd] = v[q];
+}
+// acc += A * B^T over a 32-deep half tile pair
+__device__ __forceinline__ void half_gemm(const double* As, const double* Bs, double (&acc)[2][4][2]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int wr = warp & 3, wc = warp >> 2;
+  const int g = lane >> 2, tq = lane & 3;
+  const double* ap = As + (wr * 16 + g) + tq * kLd;
+  const double* bp = Bs + (wc * 32 + g) + tq * kLd;
+#pragma unroll
+  for (int kk = 0; kk < kHalf; kk += 4) {
+    double a[2], b[4];
+#pragma unroll
+    for (int rb = 0; rb < 2; ++rb) a[rb] = ap[rb * 8 + kk * kLd];
+#pragma unroll
+    for (int cb = 0; cb < 4; ++cb) b[cb] = bp[cb * 8 + kk * kLd];
+#pragma unroll
+    for (int rb = 0; rb < 2; ++rb)
+#pragma unroll
+      for (int cb = 0; cb < 4; ++cb) mma884(acc[rb][cb][0], acc[rb][cb][1], a[rb], b[cb]);
+  }
+}
+
 __device__ unsigned long long* g_trace = nullptr;
 __device__ unsigned long long g_diag_stamps[8 * 512];  // debug: fine-grained DIAG phases  // debug: [task][4] = claim, deps ready, done (ns), smid
 __device__ __forceinline__ unsigned long long gtime() {
@@ -350,6 +395,70 @@ __global__ void __launch_bounds__(kLargeThreads, 2) large_factor_kernel(Ctrl* ct
         publish(cnt + (k + 1) * nt + (k + 1), k + 1);
       }
       if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 2] = gtime();
+    } else if (task.type == 4) {
+      // ---------------- UPDATE(i, j, [k, k1)) ----------------
+      const int k1 = task.k1;
+      const int nh = 2 * (k1 - k);
+      double acc[2][4][2];
+#pragma unroll
+      for (int rb = 0; rb < 2; ++rb)
+#pragma unroll
+        for (int cb = 0; cb < 4; ++cb) acc[rb][cb][0] = acc[rb][cb][1] = 0.0;
+      double ra[kHalfPerThread], rb_[kHalfPerThread];
+      auto fetch = [&](int h) {
+        const int kk = k + (h >> 1);
+        if ((h & 1) == 0) {
+          // operands of step kk must be final
+          if (tid == 0) {
+            while (ld_acquire(cnt + i * nt + kk) < kk + 1) __nanosleep(32);
+            while (ld_acquire(cnt + j * nt + kk) < kk + 1) __nanosleep(32);
+          }
+          __syncthreads();
+        }
+        load_half(ra, F, m, lf, i, kk, (h & 1) * kHalf);
+        load_half(rb_, F, m, lf, j, kk, (h & 1) * kHalf);
+      };
+      fetch(0);
+      if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 1] = gtime();
+      store_half(sm, ra);
+      store_half(sm + kHalfDoubles, rb_);
+      __syncthreads();
+      for (int h = 0; h < nh; ++h) {
+        double* cur = sm + (h & 1) * 2 * kHalfDoubles;
+        double* nxt = sm + ((h + 1) & 1) * 2 * kHalfDoubles;
+        if (h + 1 < nh) fetch(h + 1);
+        half_gemm(cur, cur + kHalfDoubles, acc);
+        if (h + 1 < nh) {
+          store_half(nxt, ra);
+          store_half(nxt + kHalfDoubles, rb_);
+        }
+        __syncthreads();
+      }
+      // C tile: all earlier updates applied
+      wait_eq(cnt + i * nt + j, k);
+      {
+        const int lane = tid & 31, warp = tid >> 5;
+        const int wr = warp & 3, wc = warp >> 2;
+        const int g = lane >> 2, tq = lane & 3;
+        const int ri = tile_start(lf, i), ni = tile_size(lf, i);
+        const int cj = tile_start(lf, j), nj = tile_size(lf, j);
+        double* C = F + ri + (size_t)cj * m;
+#pragma unroll
+        for (int rb = 0; rb < 2; ++rb)
+#pragma unroll
+          for (int cb = 0; cb < 4; ++cb)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int r = wr * 16 + rb * 8 + g;
+              const int c = wc * 32 + cb * 8 + tq * 2 + e;
+              if (r < ni && c < nj) {
+                double* pc = C + r + (size_t)c * m;
+                *pc = __ldcg(pc) - acc[rb][cb][e];
+              }
+            }
+      }
+      publish(cnt + i * nt + j, k1);
+      if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 2] = gtime();
     } else {
       // ---------------- TRSM(i,k) / UPDATE(i,j,k) ----------------
       const bool trsm = task.type == 1;
@@ -380,12 +489,22 @@ __global__ void __launch_bounds__(kLargeThreads, 2) large_factor_kernel(Ctrl* ct
 }
 
 // ---- assembly of large fronts ---------------------------------------------------------------------
-__global__ void large_zero_kernel(const Ctrl* __restrict__ ctrl, FrontDev fd, LargeDev ld, int lf0) {
+// zeroes the lower-triangular tiles of every large front (column c from the top of its diagonal tile:
+// rows >= c - 63 covers it wherever the tile boundary lies); nothing reads above the diagonal tiles
+__global__ void __launch_bounds__(256) large_zero_kernel(const Ctrl* __restrict__ ctrl, FrontDev fd, LargeDev ld) {
   if (ctrl->done) return;
-  const LargeFront lf = ld.lf[lf0 + blockIdx.y];
+  const LargeFront lf = ld.lf[blockIdx.y];
   double* F = fd.fronts + lf.off;
-  const int64_t n = (int64_t)lf.m * lf.m;
-  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < n; e += (int64_t)gridDim.x * blockDim.x) F[e] = 0.0;
+  const int m = lf.m;
+  for (int c = blockIdx.x; c < m; c += gridDim.x) {
+    double* col = F + (size_t)c * m;
+    for (int r = max(0, c - 63) + threadIdx.x; r < m; r += 256) col[r] = 0.0;
+  }
+}
+void launch_large_zero(cudaStream_t st, const Ctrl* ctrl, const FrontDev& fd, const LargeDev& ld, int n_lf) {
+  if (n_lf == 0) return;
+  dim3 zg(148, n_lf);
+  large_zero_kernel<<<zg, 256, 0, st>>>(ctrl, fd, ld); ++g_launches;
 }
 
 // one warp per job: system-matrix block copy, damping, or a column range of a child's update matrix
@@ -424,6 +543,7 @@ __global__ void __launch_bounds__(256) large_assemble_kernel(const Ctrl* __restr
     const int32_t* rel = fd.f_rel + fd.f_rows_ptr[c];
     for (int jc = job.c0; jc < job.c1; ++jc) {
       const int dj = rel[jc];
+#pragma unroll 4
       for (int ic = jc + lane; ic < uc; ic += 32) atomicAdd(F + rel[ic] + (size_t)dj * m, U[ic + (size_t)jc * mc]);
     }
   }
@@ -432,8 +552,6 @@ __global__ void __launch_bounds__(256) large_assemble_kernel(const Ctrl* __restr
 void launch_large_level(cudaStream_t st, Ctrl* ctrl, const FrontDev& fd, const LargeDev& ld, const LargeLevel& lv,
                         int level, const double* sys_static, StatePtrs sp, int use_state_H, const double* dvec) {
   if (lv.n_lf == 0) return;
-  dim3 zg(96, lv.n_lf);
-  large_zero_kernel<<<zg, 256, 0, st>>>(ctrl, fd, ld, lv.lf0); ++g_launches;
   const int nj = lv.j1 - lv.j0;
   if (nj > 0) {
     large_assemble_kernel<<<(nj + 7) / 8, 256, 0, st>>>(ctrl, fd, ld, sys_static, sp, use_state_H, dvec, lv.j0, lv.j1);

@@ -391,7 +391,26 @@ __global__ void __launch_bounds__(kBalThreads) linearize_bal_kernel(const Ctrl* 
     for (int r = 0; r < 9; ++r) atomicAdd(rhs + cam_rhs + r, J[2 * r] * res[0] + J[2 * r + 1] * res[1]);
   }
   // ---- point block ---------------------------------------------------------------------------------
-  if (valid && !(SKIP & 2)) {
+  if (b.pbuf != nullptr && !(SKIP & 2)) {
+    // per-observation contribution (6 lower entries + 3 rhs) written coalesced; summed per point by
+    // bal_point_finalize_kernel (no atomics on the 12 scattered point values of every observation)
+    double* st = stage[warp];
+    {
+      int q = 0;
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int r = c; r < 3; ++r)
+          st[lane * 9 + q++] = J[2 * (9 + r)] * J[2 * (9 + c)] + J[2 * (9 + r) + 1] * J[2 * (9 + c) + 1];
+#pragma unroll
+      for (int r = 0; r < 3; ++r) st[lane * 9 + 6 + r] = J[2 * (9 + r)] * res[0] + J[2 * (9 + r) + 1] * res[1];
+    }
+    __syncwarp();
+    double* dst = b.pbuf + (size_t)(blockIdx.x * kBalThreads + warp * 32) * 9;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) dst[i * 32 + lane] = st[i * 32 + lane];
+    __syncwarp();
+  } else if (valid && !(SKIP & 2)) {
 #pragma unroll
     for (int c = 0; c < 3; ++c)
 #pragma unroll
@@ -434,6 +453,37 @@ __global__ void __launch_bounds__(kBalThreads) linearize_bal_kernel(const Ctrl* 
   }
   const double tot = block_sum<kBalThreads>(err);
   if (threadIdx.x == 0) partials[b.partial_base + blockIdx.x] = tot;
+}
+
+// sums the per-observation point contributions of linearize_bal_kernel in slot order (deterministic)
+// and adds the total to the point's diagonal block and rhs
+__global__ void __launch_bounds__(128) bal_point_finalize_kernel(const Ctrl* __restrict__ ctrl, StatePtrs sp, LinBatch b,
+                                                                 int mode) {
+  if (ctrl->done) return;
+  const int blk = sel_block(ctrl, mode);
+  if (mode == 0 && ctrl->lin_valid[blk]) return;
+  const int pt = blockIdx.x * blockDim.x + threadIdx.x;
+  if (pt >= b.n_pf) return;
+  double a[9];
+#pragma unroll
+  for (int i = 0; i < 9; ++i) a[i] = 0.0;
+  const int q1 = __ldg(b.pf_ptr + pt + 1);
+  for (int q = __ldg(b.pf_ptr + pt); q < q1; ++q) {
+    const double* __restrict__ src = b.pbuf + (size_t)__ldg(b.pf_slot + q) * 9;
+#pragma unroll
+    for (int i = 0; i < 9; ++i) a[i] += src[i];
+  }
+  double* Hd = sp.H[blk] + __ldg(b.pf_diag + pt);
+  double* rh = sp.rhs[blk] + __ldg(b.pf_rhs + pt);
+  atomicAdd(Hd + 0, a[0]);
+  atomicAdd(Hd + 1, a[1]);
+  atomicAdd(Hd + 2, a[2]);
+  atomicAdd(Hd + 4, a[3]);
+  atomicAdd(Hd + 5, a[4]);
+  atomicAdd(Hd + 8, a[5]);
+  atomicAdd(rh + 0, a[6]);
+  atomicAdd(rh + 1, a[7]);
+  atomicAdd(rh + 2, a[8]);
 }
 
 __global__ void zero_lin_kernel(const Ctrl* __restrict__ ctrl, StatePtrs sp, int mode, int64_t n_h, int n_rhs) {
@@ -545,6 +595,9 @@ void launch_linearize(cudaStream_t st, const Ctrl* ctrl, StatePtrs sp, int mode,
       default: linearize_bal_kernel<0><<<grid, kBalThreads, 0, st>>>(ctrl, sp, b, mode, partials); break;
     }
     ++g_launches;
+    if (b.pbuf != nullptr && !(g_lin_skip & 2)) {
+      bal_point_finalize_kernel<<<(b.n_pf + 127) / 128, 128, 0, st>>>(ctrl, sp, b, mode); ++g_launches;
+    }
     return;
   }
   switch (b.kind) {
@@ -1249,6 +1302,138 @@ __global__ void __launch_bounds__(kSchurWarps * 32, 4) schur_s2_kernel(const Ctr
       }
 }
 
+// (2b) schur_s9_kernel: persistent kernel for the BAL shape (every reduced node has dim 9).  Items are
+//      chunks of <= 64 matches whose offsets are stored padded (64 slots per item; unused slots point
+//      at a block of zeros behind W), so an item is addressed by its id alone: the 16-byte header and
+//      the offsets of the NEXT item are prefetched while the current one runs.  The 9 x 9 product is
+//      split into the 8 x 8 core (ONE mma.sync.m8n8k4.f64 per k-step of 4/3 matches) and the border
+//      row 8 / column 8 / corner, which are three FMAs per lane on operands the lane already holds,
+//      reduced over the four k-lanes at the end.  Offsets sit in a per-warp shared-memory table; the 16
+//      loads of the next four k-steps are in flight while the current four issue.
+constexpr int kS9Warps = 4;
+__global__ void __launch_bounds__(kS9Warps * 32, 4) schur_s9_kernel(const Ctrl* __restrict__ ctrl, StatePtrs sp,
+                                                                   SchurDev sd, const double* __restrict__ dvec) {
+  __shared__ int32_t offs[kS9Warps][2][128];  // [buffer][0..63: row operand, 64..127: column operand]
+  if (ctrl->done) return;
+  const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nw = gridDim.x * kS9Warps;
+  int item = blockIdx.x * kS9Warps + wid;
+  if (item >= sd.n_items) return;
+  const double* __restrict__ W = sd.G;
+  const double* __restrict__ H = sp.H[ctrl->init_idx];
+  const int4* __restrict__ hdr = reinterpret_cast<const int4*>(sd.items3);
+  const int g = lane >> 2, tq = lane & 3;
+  const double* __restrict__ Wg = W + 3 * g;
+  double fa0[2][4], fb0[2][4], fa8[2][4], fb8[2][4];
+  auto load_group = [&](const int32_t* tab, int s0, int buf) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int kk = 4 * (s0 + u) + tq;
+      const int mm = (kk * 171) >> 9;  // kk / 3 for kk < 512
+      const int a = kk - 3 * mm;
+      const int oi = tab[mm] + a, oj = tab[64 + mm] + a;
+      fa0[buf][u] = __ldg(Wg + oi);
+      fb0[buf][u] = __ldg(Wg + oj);
+      fa8[buf][u] = __ldg(W + oi + 24);
+      fb8[buf][u] = __ldg(W + oj + 24);
+    }
+  };
+  int4 h = __ldg(hdr + item);
+  int cb = 0;
+  {
+    const int32_t* pi = sd.pm_i + (size_t)item * 64;
+    const int32_t* pj = sd.pm_j + (size_t)item * 64;
+    int32_t* tab = offs[wid][0];
+    tab[lane] = __ldg(pi + lane);
+    tab[32 + lane] = __ldg(pi + 32 + lane);
+    tab[64 + lane] = __ldg(pj + lane);
+    tab[96 + lane] = __ldg(pj + 32 + lane);
+    __syncwarp();
+  }
+  load_group(offs[wid][0], 0, 0);
+  for (;;) {
+    const int nitem = item + nw;
+    const bool more = nitem < sd.n_items;
+    int4 hn = make_int4(0, 0, 0, 0);
+    int na = 0, nb = 0, nc = 0, nd = 0;
+    if (more) {
+      hn = __ldg(hdr + nitem);
+      const int32_t* pi = sd.pm_i + (size_t)nitem * 64;
+      const int32_t* pj = sd.pm_j + (size_t)nitem * 64;
+      na = __ldg(pi + lane);
+      nb = __ldg(pi + 32 + lane);
+      nc = __ldg(pj + lane);
+      nd = __ldg(pj + 32 + lane);
+    }
+    const int32_t* tab = offs[wid][cb];
+    const int cnt = (h.w >> 25) & 0x7f;
+    const int nsteps = (3 * cnt + 3) >> 2;
+    double acc0 = 0.0, acc1 = 0.0, row8 = 0.0, col8 = 0.0, corner = 0.0;
+    auto mma_group = [&](int buf) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        dmma884(acc0, acc1, fa0[buf][u], fb0[buf][u]);
+        row8 += fa8[buf][u] * fb0[buf][u];
+        col8 += fa0[buf][u] * fb8[buf][u];
+        corner += fa8[buf][u] * fb8[buf][u];
+      }
+    };
+    for (int s0 = 0; s0 < nsteps; s0 += 8) {
+      if (s0 + 4 < nsteps) load_group(tab, s0 + 4, 1);
+      mma_group(0);
+      if (s0 + 4 < nsteps) {
+        if (s0 + 8 < nsteps) load_group(tab, s0 + 8, 0);
+        mma_group(1);
+      }
+    }
+    if (more) {
+      // offsets of the next item -> the other table; its first loads fly during the epilogue
+      int32_t* nt = offs[wid][cb ^ 1];
+      nt[lane] = na;
+      nt[32 + lane] = nb;
+      nt[64 + lane] = nc;
+      nt[96 + lane] = nd;
+      __syncwarp();
+      load_group(nt, 0, 0);
+    }
+    row8 += __shfl_xor_sync(0xffffffffu, row8, 1);
+    row8 += __shfl_xor_sync(0xffffffffu, row8, 2);
+    col8 += __shfl_xor_sync(0xffffffffu, col8, 1);
+    col8 += __shfl_xor_sync(0xffffffffu, col8, 2);
+    corner += __shfl_xor_sync(0xffffffffu, corner, 1);
+    corner += __shfl_xor_sync(0xffffffffu, corner, 2);
+    {
+      const int64_t s_off = ((int64_t)(uint32_t)h.x) | ((int64_t)h.y << 32);
+      double* out = sd.S + s_off;
+      const int bsrc = h.z;
+      const bool first = (h.w & 1) && sd.add_b, single = (h.w >> 1) & 1;
+      const bool diag = (h.w >> 24) & 1;
+      const int toI = (first && diag) ? __ldg(sd.item_toI + item) : 0;
+      auto emit = [&](int r, int c, double a) {
+        const int idx = r + c * 9;
+        double v = -a;
+        if (first) {
+          if (bsrc >= 0) v += H[bsrc + idx];
+          if (diag && r == c) v += dvec[toI + r];
+        }
+        if (single)
+          out[idx] = v;
+        else
+          atomicAdd(out + idx, v);
+      };
+      emit(g, 2 * tq, acc0);
+      emit(g, 2 * tq + 1, acc1);
+      if (tq == 0) emit(8, g, row8);
+      if (tq == 1) emit(g, 8, col8);
+      if (lane == 2) emit(8, 8, corner);
+    }
+    if (!more) break;
+    item = nitem;
+    h = hn;
+    cb ^= 1;
+  }
+}
+
 // s_l += E y_I per E block (camera-major), then z_l = t_l - C^-1 s_l per landmark
 __global__ void __launch_bounds__(kGThreads) schur_back_accum_kernel(const Ctrl* __restrict__ ctrl, StatePtrs sp,
                                                                      SchurDev sd, const double* __restrict__ y) {
@@ -1304,6 +1489,12 @@ void launch_schur(cudaStream_t st, const Ctrl* ctrl, StatePtrs sp, const SchurDe
     schur_rhs_init_kernel<<<ig, 256, 0, st>>>(ctrl, sp, sd); ++g_launches;
     if (sd.wl != nullptr) {
       schur_w_rhs_kernel<<<(sd.n_entries + kWThreads - 1) / kWThreads, kWThreads, 0, st>>>(ctrl, sp, sd); ++g_launches;
+      if (sd.items3 != nullptr) {
+        int grid = 148 * 4;
+        if (grid * kS9Warps > sd.n_items) grid = (sd.n_items + kS9Warps - 1) / kS9Warps;
+        schur_s9_kernel<<<grid, kS9Warps * 32, 0, st>>>(ctrl, sp, sd, dvec); ++g_launches;
+        return;
+      }
       schur_s2_kernel<<<(sd.n_items + kSchurWarps - 1) / kSchurWarps, kSchurWarps * 32, 0, st>>>(ctrl, sp, sd, dvec);
       ++g_launches;
       return;

@@ -54,6 +54,10 @@ struct LinBatch {
   int n_groups;
   int partial_base;  // offset of this batch's per-CTA partial sums
   int bal_fast;      // Snavely batch with (pose+intrinsics) 9-node and 3-dim point node: linearize_bal_kernel
+  // bal_fast: per-observation point contributions [slots rounded up to 128][9] and the point -> slots lists
+  double* pbuf;      // nullptr: point blocks are accumulated with atomics instead
+  const int32_t *pf_ptr, *pf_slot, *pf_diag, *pf_rhs;
+  int n_pf;
 };
 
 struct SchurDev {
@@ -79,6 +83,9 @@ struct SchurDev {
   double* G;   // same offsets as the E blocks in H (v1: C^-1 E; v2: W = L^-1 E)
   double* wl;  // v2: [n_landmarks][9] = L^-1 (i00 i10 i11 i20 i21 i22), u = L^-1 w; nullptr selects v1
   const double* zeros;  // 8 zero doubles (padding lanes of the DMMA fragments load from here)
+  const void* items3;  // s9: 16-byte headers {s_off lo, s_off hi, bsrc, flags|dI<<8|dJ<<16|diag<<24|cnt<<25}; nullptr: use items2
+  const int32_t *pm_i, *pm_j;  // s9: match offsets, 64 slots per item, unused slots -> zero block behind W
+  const int32_t* item_toI;     // v3: tangent offset of the row node (damping of diagonal blocks)
   const void* items2;  // v2: packed 32-byte item headers (SItem2 in kernels.cu)
   double* sl;  // [n_landmarks][3] back-substitution accumulators
   double* cinv;   // [n_landmarks][9]
@@ -118,7 +125,8 @@ struct LargeFront {
 };
 struct LargeTask {
   int lf;
-  short type, k, i, j;  // type: 0 POTRF(k), 1 TRSM(i,k), 2 UPDATE(i,j,k)
+  short type, k, i, j;  // type: 1 TRSM(i,k), 2 UPDATE(i,j,k), 3 DIAG(k), 4 UPDATE(i,j,[k,k1))
+  short k1, pad;
 };
 struct LargeJob {
   int lf, type, idx, c0, c1;  // type 0: copy idx; 1: child front idx, columns [c0,c1); 2: damping rows [c0,c1)
@@ -147,6 +155,7 @@ void launch_large_solve_fwd(cudaStream_t st, const Ctrl* ctrl, const FrontDev& f
                             const LargeLevel& lv, const double* rhs_static, StatePtrs sp, int use_state_rhs);
 void launch_large_solve_bwd(cudaStream_t st, const Ctrl* ctrl, const FrontDev& fd, const LargeDev& ld,
                             const LargeLevel& lv);
+void launch_large_zero(cudaStream_t st, const Ctrl* ctrl, const FrontDev& fd, const LargeDev& ld, int n_lf);
 cudaError_t configure_large_kernels();
 
 // launchers (all asynchronous on `st`)

@@ -119,6 +119,9 @@ struct sfx_problem {
   std::string err;
   DevPool pool;
   cudaStream_t st = nullptr;
+  cudaStream_t st2 = nullptr;  // side stream: front zeroing overlaps damping + Schur
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  int n_large_fronts = 0;
   Ctrl* d_ctrl = nullptr;
   Ctrl* h_ctrl = nullptr;  // pinned
   int* h_done = nullptr;   // pinned + mapped
@@ -156,6 +159,9 @@ struct sfx_problem {
   ~sfx_problem() {
     for (auto e : ev) cudaEventDestroy(e);
     if (st) cudaStreamDestroy(st);
+    if (st2) cudaStreamDestroy(st2);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
     if (h_ctrl) cudaFreeHost(h_ctrl);
     if (h_done) cudaFreeHost(h_done);
   }
@@ -164,6 +170,127 @@ struct sfx_problem {
 static thread_local std::string g_create_err;
 
 namespace {
+
+// Tile task list of one large front (see chol_large.cu for the task types).
+void build_front_tasks(const LargeFront& x, int li, int Kc, std::vector<LargeTask>& tl) {
+  const int wt = x.wt, nt = x.nt;
+  // Tile (i, j), i >= j, needs the updates k in [0, min(j, wt)).  Those with k >= i - 2 are on or
+  // next to the critical path and stay single-step tasks: DIAG(k) = POTRF(k) + TRSM(k+1,k) +
+  // UPDATE(k+1,k+1,k) fused on one CTA, and the priority tasks TRSM(k+2,k), UPDATE(k+2,k+1,k),
+  // UPDATE(k+2,k+2,k), with DIAG(k+1) hoisted in front of the bulk of step k.  All other
+  // updates are range tasks UPDATE(i,j,[a,e)) with the accumulator kept in registers: cut at
+  // multiples of Kc (panel boundaries) and at e = min(j, i-2, wt), emitted once TRSM(.,e-1) is.
+  auto T = [&](int i, int k) { tl.push_back(LargeTask{li, 1, (short)k, (short)i, (short)k, 0, 0}); };
+  auto U = [&](int i, int j, int k) { tl.push_back(LargeTask{li, 2, (short)k, (short)i, (short)j, 0, 0}); };
+  auto R = [&](int i, int j, int a, int e) {
+    if (e - a == 1)
+      U(i, j, a);
+    else
+      tl.push_back(LargeTask{li, 4, (short)a, (short)i, (short)j, (short)e, 0});
+  };
+  auto cend = [&](int i, int j) { return std::min(std::min(j, i - 2), wt); };  // end of the coarse range
+  struct Def {
+    int need, i, j, a, e;
+  };
+  std::vector<Def> deferred;
+  size_t dpos = 0;
+  int d_steps_left = 0;
+  tl.push_back(LargeTask{li, 3, 0, 0, 0, 0, 0});
+  for (int k = 0; k < wt; ++k) {
+    if (k + 2 < nt) {
+      T(k + 2, k);
+      U(k + 2, k + 1, k);
+      U(k + 2, k + 2, k);
+    }
+    if (k + 1 < wt) tl.push_back(LargeTask{li, 3, (short)(k + 1), (short)(k + 1), (short)(k + 1), 0, 0});
+    for (int i = k + 3; i < nt; ++i) T(i, k);
+    // deferred range tasks of the last panel boundary: everything needed by this step, plus a share
+    if (dpos < deferred.size()) {
+      size_t upto = dpos + (deferred.size() - dpos + d_steps_left - 1) / std::max(1, d_steps_left);
+      while (upto < deferred.size() && deferred[upto].need <= k) ++upto;  // sorted by need
+      for (; dpos < upto; ++dpos) R(deferred[dpos].i, deferred[dpos].j, deferred[dpos].a, deferred[dpos].e);
+      if (d_steps_left > 1) --d_steps_left;
+    }
+    const int a0 = (k / Kc) * Kc;
+    const int e = k + 1;
+    // final pieces: column k+1 (rows >= k+3) and row k+3
+    if (k + 1 < nt)
+      for (int i = k + 3; i < nt; ++i)
+        if (cend(i, k + 1) == e) R(i, k + 1, a0, e);
+    if (k + 3 < nt)
+      for (int j = k + 2; j <= k + 3; ++j)
+        if (cend(k + 3, j) == e) R(k + 3, j, a0, e);
+    // panel boundary (or last pivot step): one piece [a0, e) for every other tile that has not
+    // reached the end of its coarse range (at the last step these are final pieces)
+    const bool last = k == wt - 1;
+    if (e % Kc == 0 || last) {
+      std::vector<Def> batch;
+      for (int j = k + 2; j < nt; ++j)
+        for (int i = std::max(j, k + 4); i < nt; ++i) batch.push_back(Def{std::min(j - 1, i - 3), i, j, a0, e});
+      // anything still deferred from the previous boundary goes first (same tiles, earlier pieces)
+      for (; dpos < deferred.size(); ++dpos)
+        R(deferred[dpos].i, deferred[dpos].j, deferred[dpos].a, deferred[dpos].e);
+      deferred.clear();
+      dpos = 0;
+      if (last) {
+        for (auto& d : batch) R(d.i, d.j, d.a, d.e);
+      } else {
+        std::stable_sort(batch.begin(), batch.end(), [](const Def& p, const Def& q) { return p.need < q.need; });
+        deferred.swap(batch);
+        d_steps_left = Kc;
+      }
+    }
+  }
+  for (; dpos < deferred.size(); ++dpos) R(deferred[dpos].i, deferred[dpos].j, deferred[dpos].a, deferred[dpos].e);
+}
+
+// Replays one front's task list sequentially against the tile version counters: every wait condition
+// of chol_large.cu must already hold when its task comes up (so in-order claiming cannot deadlock) and
+// every tile must end up final.
+void verify_task_list(const LargeFront& x, const std::vector<LargeTask>& tl) {
+  const int nt = x.nt, wt = x.wt;
+  std::vector<int> cnt((size_t)nt * nt, 0);
+  auto C = [&](int i, int j) -> int& { return cnt[(size_t)i * nt + j]; };
+  auto fail = [&](const LargeTask& t, const char* why) {
+    throw Error(SFX_ERR_INVALID_ARG, std::string("internal: tile task list invalid (") + why + ") type " +
+                                         std::to_string(t.type) + " k " + std::to_string(t.k) + " i " +
+                                         std::to_string(t.i) + " j " + std::to_string(t.j) + " k1 " + std::to_string(t.k1));
+  };
+  for (const LargeTask& t : tl) {
+    const int k = t.k, i = t.i, j = t.j;
+    if (t.type == 3) {
+      if (C(k, k) != k) fail(t, "diag not ready");
+      C(k, k) = k + 1;
+      if (k + 1 < nt) {
+        if (C(k + 1, k) != k) fail(t, "diag trsm");
+        C(k + 1, k) = k + 1;
+        if (C(k + 1, k + 1) != k) fail(t, "diag update");
+        C(k + 1, k + 1) = k + 1;
+      }
+    } else if (t.type == 1) {
+      if (C(k, k) < k + 1 || C(i, k) != k) fail(t, "trsm");
+      C(i, k) = k + 1;
+    } else if (t.type == 2) {
+      if (C(i, k) < k + 1 || C(j, k) < k + 1 || C(i, j) != k) fail(t, "update");
+      C(i, j) = k + 1;
+    } else if (t.type == 4) {
+      for (int kk = k; kk < t.k1; ++kk)
+        if (C(i, kk) < kk + 1 || C(j, kk) < kk + 1) fail(t, "range operands");
+      if (C(i, j) != k) fail(t, "range target");
+      C(i, j) = t.k1;
+    } else {
+      fail(t, "type");
+    }
+  }
+  for (int j = 0; j < nt; ++j)
+    for (int i = j; i < nt; ++i) {
+      const int want = j < wt ? j + 1 : wt;
+      if (C(i, j) != want)
+        throw Error(SFX_ERR_INVALID_ARG, "internal: tile (" + std::to_string(i) + "," + std::to_string(j) +
+                                             ") ends at version " + std::to_string(C(i, j)) + ", expected " +
+                                             std::to_string(want));
+    }
+}
 
 void upload_structures(sfx_problem* p) {
   Analysis& a = p->a;
@@ -214,6 +341,28 @@ void upload_structures(sfx_problem* p) {
           break;
         }
       lb.bal_fast = ok ? 1 : 0;
+      if (ok && !getenv("SFX_POINT_ATOMICS")) {
+        // point -> observation slots (points identified by the offset of their diagonal block)
+        std::vector<int32_t> order(bp.n);
+        for (int i = 0; i < bp.n; ++i) order[i] = i;
+        const int32_t* pd = bp.diag_off.data() + bp.n;
+        const int32_t* pr = bp.rhs_off.data() + bp.n;
+        std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return pd[x] < pd[y]; });
+        std::vector<int32_t> ptr, diag, rhs;
+        for (int i = 0; i < bp.n; ++i)
+          if (i == 0 || pd[order[i]] != pd[order[i - 1]]) {
+            ptr.push_back(i);
+            diag.push_back(pd[order[i]]);
+            rhs.push_back(pr[order[i]]);
+          }
+        ptr.push_back(bp.n);
+        lb.n_pf = (int)diag.size();
+        lb.pf_ptr = P.upload(ptr);
+        lb.pf_slot = P.upload(order);
+        lb.pf_diag = P.upload(diag);
+        lb.pf_rhs = P.upload(rhs);
+        lb.pbuf = P.alloc<double>((size_t)((bp.n + 127) / 128) * 128 * 9);
+      }
     }
     lb.partial_base = partial_base;
     partial_base += (bp.n + 127) / 128;
@@ -288,7 +437,12 @@ void upload_structures(sfx_problem* p) {
     d.m_eoff_j = P.upload(s.m_eoff_j);
     d.m_lm = P.upload(s.m_lm);
     {
-      const int chunk = getenv("SFX_SCHUR_CHUNK") ? atoi(getenv("SFX_SCHUR_CHUNK")) : 32;
+      bool v3 = !getenv("SFX_SCHUR_V2") && !getenv("SFX_SCHUR_V1") && !getenv("SFX_NO_SCHUR_FAST");
+      for (int l = 0; l < s.n_landmarks && v3; ++l) v3 = s.lm_dim[l] == 3;
+      for (int i = 0; i < s.first_lm_node && v3; ++i) v3 = a.nodes[i].dim == 9;  // schur_s9_kernel: BAL shape only
+      SFX_CHECK(a.H.n_values + 64 < (int64_t)INT32_MAX, SFX_ERR_UNSUPPORTED, "Hessian too large for int32 offsets");
+      const int32_t zero_block = (int32_t)a.H.n_values;  // 32 zero doubles behind the W buffer
+      const int chunk = v3 ? 64 : getenv("SFX_SCHUR_CHUNK") ? atoi(getenv("SFX_SCHUR_CHUNK")) : 64;
       std::vector<int32_t> ib, im, ic, ifl;
       SFX_CHECK(s.m_lm.size() < (size_t)INT32_MAX, SFX_ERR_UNSUPPORTED, "too many Schur matches");
       for (int b = 0; b < d.n_sblocks; ++b) {
@@ -321,6 +475,27 @@ void upload_structures(sfx_problem* p) {
           h[7] = 0;
         }
         d.items2 = P.upload(hdr);
+        if (v3) {
+          // padded per-item match offsets + 16-byte headers for the persistent kernel
+          std::vector<int32_t> h3(ib.size() * 4), pmi(ib.size() * 64, zero_block), pmj(ib.size() * 64, zero_block),
+              toI(ib.size());
+          for (size_t q = 0; q < ib.size(); ++q) {
+            const int32_t* h = &hdr[q * 8];
+            h3[q * 4 + 0] = h[4];
+            h3[q * 4 + 1] = h[5];
+            h3[q * 4 + 2] = h[6];
+            h3[q * 4 + 3] = h[2] | (ic[q] << 25);
+            toI[q] = h[3];
+            for (int c = 0; c < ic[q]; ++c) {
+              pmi[q * 64 + c] = s.m_eoff_i[im[q] + c];
+              pmj[q * 64 + c] = s.m_eoff_j[im[q] + c];
+            }
+          }
+          d.items3 = P.upload(h3);
+          d.pm_i = P.upload(pmi);
+          d.pm_j = P.upload(pmj);
+          d.item_toI = P.upload(toI);
+        }
       }
       d.n_items = (int)ib.size();
       d.item_blk = P.upload(ib);
@@ -346,7 +521,8 @@ void upload_structures(sfx_problem* p) {
       for (int j = 0; j < s.first_lm_node; ++j)
         for (int q = s.r_ptr[j]; q < s.r_ptr[j + 1]; ++q) rnode[q] = j;
       d.r_node = P.upload(rnode);
-      d.G = fast ? P.alloc<double>(a.H.n_values) : nullptr;
+      d.G = fast ? P.alloc<double>(a.H.n_values + 32) : nullptr;
+      if (fast) CUDA_OK(cudaMemset(d.G + a.H.n_values, 0, 32 * sizeof(double)));
       d.wl = (fast && !getenv("SFX_SCHUR_V1")) ? P.alloc<double>((size_t)s.n_landmarks * 9) : nullptr;
       d.zeros = P.upload(std::vector<double>(8, 0.0));
       d.sl = P.alloc<double>((size_t)s.n_landmarks * 3);
@@ -440,7 +616,7 @@ void upload_structures(sfx_problem* p) {
           while (c0 < uc) {
             int c1 = c0;
             int64_t el = 0;
-            while (c1 < uc && el < 4096) {
+            while (c1 < uc && el < 1024) {
               el += uc - c1;
               ++c1;
             }
@@ -450,57 +626,45 @@ void upload_structures(sfx_problem* p) {
         }
       }
       // tasks: per front in an order that keeps every dependency earlier in the list (see
-      // chol_large.cu), then merged round-robin across the fronts of the level so that the window
-      // of tasks in flight always spans all fronts (one front's critical path hides behind the
-      // others' trailing updates)
+      // chol_large.cu), then merged across the fronts of the level in proportion to their work so that
+      // the window of tasks in flight always spans all fronts (one front's critical path hides behind
+      // the others' trailing updates)
       {
+        static const int Kc = getenv("SFX_KC") ? std::max(1, atoi(getenv("SFX_KC"))) : 4;
         std::vector<std::vector<LargeTask>> per(lv.n_lf);
         for (int q = 0; q < lv.n_lf; ++q) {
-          const int li = lv.lf0 + q;
-          const LargeFront& x = lfs[li];
-          auto& tl = per[q];
-          // DIAG(k) = POTRF(k) + TRSM(k+1,k) + UPDATE(k+1,k+1,k) fused on one CTA (type 3); the three
-          // tasks the NEXT diagonal step waits for follow immediately, then DIAG(k+1) is hoisted in
-          // front of the bulk of step k (one step of look-ahead along the critical path)
-          auto T = [&](int i, int k) { tl.push_back(LargeTask{li, 1, (short)k, (short)i, (short)k}); };
-          auto U = [&](int i, int j, int k) { tl.push_back(LargeTask{li, 2, (short)k, (short)i, (short)j}); };
-          tl.push_back(LargeTask{li, 3, 0, 0, 0});
-          for (int k = 0; k < x.wt; ++k) {
-            if (k + 2 < x.nt) {
-              T(k + 2, k);
-              U(k + 2, k + 1, k);
-              U(k + 2, k + 2, k);
-            }
-            if (k + 1 < x.wt) tl.push_back(LargeTask{li, 3, (short)(k + 1), (short)(k + 1), (short)(k + 1)});
-            for (int i = k + 3; i < x.nt; ++i) T(i, k);
-            for (int j = k + 1; j < x.nt; ++j)
-              for (int i = j; i < x.nt; ++i) {
-                if (i <= k + 2 && j <= k + 2) continue;  // done by DIAG(k) / the priority tasks
-                U(i, j, k);
-              }
-          }
+          build_front_tasks(lfs[lv.lf0 + q], lv.lf0 + q, Kc, per[q]);
+          verify_task_list(lfs[lv.lf0 + q], per[q]);
         }
-        // proportional round-robin: fronts advance at a rate proportional to their task count
+        // proportional merge by cumulative cost
+        auto cost = [](const LargeTask& t) { return t.type == 4 ? (double)(t.k1 - t.k) : t.type == 3 ? 3.0 : 1.0; };
+        std::vector<double> tot(lv.n_lf, 0.0);
+        double longest = 0;
+        for (int q = 0; q < lv.n_lf; ++q) {
+          for (auto& t : per[q]) tot[q] += cost(t);
+          longest = std::max(longest, tot[q]);
+        }
         std::vector<size_t> pos(lv.n_lf, 0);
-        size_t total = 0, longest = 0;
-        for (auto& tl : per) {
-          total += tl.size();
-          longest = std::max(longest, tl.size());
-        }
-        for (size_t step = 0; step < longest; ++step)
+        std::vector<double> done(lv.n_lf, 0.0);
+        const int nsteps = 4096;
+        for (int step = 1; step <= nsteps; ++step)
           for (int q = 0; q < lv.n_lf; ++q) {
-            const size_t upto = (size_t)((double)(step + 1) * per[q].size() / longest);
-            while (pos[q] < upto && pos[q] < per[q].size()) tasks.push_back(per[q][pos[q]++]);
+            const double upto = tot[q] * step / nsteps;
+            while (pos[q] < per[q].size() && done[q] < upto) {
+              done[q] += cost(per[q][pos[q]]);
+              tasks.push_back(per[q][pos[q]++]);
+            }
           }
         for (int q = 0; q < lv.n_lf; ++q)
           while (pos[q] < per[q].size()) tasks.push_back(per[q][pos[q]++]);
-        (void)total;
+        (void)longest;
       }
       lv.t1 = (int)tasks.size();
       lv.j1 = (int)jobs.size();
       lv.solve_p = lv.n_lf > 0 ? std::max(1, std::min(lv.max_nt, 144 / lv.n_lf)) : 1;
     }
     d.level_fronts = up32(lvl_fronts);
+    p->n_large_fronts = (int)lfs.size();
     p->ld.lf = P.upload(lfs);
     p->ld.tasks = P.upload(tasks);
     p->ld.jobs = P.upload(jobs);
@@ -550,6 +714,15 @@ void enqueue_linearize(sfx_problem* p, int mode) {
 // damping + [Schur] + factorize + solve -> d_upd (internal order) = -H_damped^-1 rhs
 void enqueue_solve(sfx_problem* p, const std::function<void(int)>& mark) {
   Analysis& a = p->a;
+  const bool factors_here = !(a.world > 1 && a.rank != 0);
+  if (factors_here && p->n_large_fronts > 0) {
+    // the large fronts are zeroed on a side stream while damping and the Schur complement run (the
+    // previous solve, the last reader of the fronts, precedes the fork event on the main stream)
+    CUDA_OK(cudaEventRecord(p->ev_fork, p->st));
+    CUDA_OK(cudaStreamWaitEvent(p->st2, p->ev_fork, 0));
+    launch_large_zero(p->st2, p->d_ctrl, p->fd, p->ld, p->n_large_fronts);
+    CUDA_OK(cudaEventRecord(p->ev_join, p->st2));
+  }
   launch_damping(p->st, p->d_ctrl, p->sp, p->d_diag_pos, a.N, p->d_dvec, p->d_maxdiag);
   if (a.schur) launch_schur(p->st, p->d_ctrl, p->sp, p->sd, p->d_dvec);
   const bool mg = a.world > 1;
@@ -572,6 +745,7 @@ void enqueue_solve(sfx_problem* p, const std::function<void(int)>& mark) {
   const double* sys = a.schur ? p->sd.S : nullptr;
   const int use_H = a.schur ? 0 : 1;
   const double* dv = a.schur ? nullptr : p->d_dvec;
+  if (p->n_large_fronts > 0) CUDA_OK(cudaStreamWaitEvent(p->st, p->ev_join, 0));
   if (p->n_counters > 0) {
     CUDA_OK(cudaMemsetAsync(p->ld.counters, 0, sizeof(int) * p->n_counters, p->st));
     CUDA_OK(cudaMemsetAsync(p->ld.queue, 0, sizeof(int) * f.n_levels, p->st));
@@ -712,6 +886,9 @@ sfx_status sfx_problem_create(const sfx_problem_desc* desc, sfx_problem** out) {
     build_front_plan(sys, desc->ordering, sys2ref, a.fp);
   }
   CUDA_OK(cudaStreamCreateWithFlags(&p->st, cudaStreamNonBlocking));
+  CUDA_OK(cudaStreamCreateWithFlags(&p->st2, cudaStreamNonBlocking));
+  CUDA_OK(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
+  CUDA_OK(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
   upload_structures(p);
   CUDA_OK(cudaStreamSynchronize(p->st));
   *out = up.release();
@@ -945,6 +1122,23 @@ sfx_status sfx_get_timings(sfx_problem* p, sfx_timings* out) {
   SFX_CHECK(p && out, SFX_ERR_INVALID_ARG, "null argument");
   *out = p->tm;
   SFX_API_END(p)
+}
+
+// debug (host only): build and verify the tile task list of a front with `wt` pivot tiles out of `nt`;
+// returns the number of tasks, or -1 with sfx_last_error(NULL) set
+int32_t sfx_debug_verify_tasks(int32_t wt, int32_t nt, int32_t kc) {
+  try {
+    LargeFront x{};
+    x.wt = wt;
+    x.nt = nt;
+    std::vector<LargeTask> tl;
+    build_front_tasks(x, 0, kc, tl);
+    verify_task_list(x, tl);
+    return (int32_t)tl.size();
+  } catch (const std::exception& e) {
+    g_create_err = e.what();
+    return -1;
+  }
 }
 
 // debug: average time of `reps` linearizations of state block 0 (zero + kernels + error reduce), with

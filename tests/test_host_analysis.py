@@ -96,3 +96,19 @@ def test_unoptimized_key_is_an_error():
         capi.analysis_json(bad)
     with pytest.raises(RuntimeError, match="not optimized by any factor"):
         O.OracleProblem(bad)
+
+
+def test_tile_task_lists_are_dependency_ordered():
+    """The tile-DAG task generator (sfx_api.cu: build_front_tasks) is replayed sequentially against the
+    tile version counters for many front shapes and panel widths: every wait condition of
+    chol_large.cu must hold when its task comes up and every tile must end up final."""
+    from symforce_b200 import capi
+
+    lib = capi.load()
+    for kc in (1, 2, 3, 4, 6, 8):
+        for wt in range(1, 14):
+            for nt in range(wt, wt + 14):
+                n = lib.sfx_debug_verify_tasks(wt, nt, kc)
+                assert n > 0, (kc, wt, nt, lib.sfx_last_error(None).decode())
+    # the range tasks cut the task count of the final-shape level-1 fronts by ~3x
+    assert lib.sfx_debug_verify_tasks(18, 41, 4) < lib.sfx_debug_verify_tasks(18, 41, 1) // 2

@@ -323,6 +323,131 @@ __device__ __forceinline__ void half_gemm(const double* As, const double* Bs, do
   }
 }
 
+// ---- v2 critical path: panel Cholesky / panel substitution without shuffles or explicit inverses -----
+// C(8x8 tile (rb, cb) of Cs) -= X[rb rows][c0..c0+8) * Y[cb rows][c0..c0+8)^T   (one warp, two DMMA k-steps)
+__device__ __forceinline__ void rank8_tile(double* Cs, const double* Xs, const double* Ys, int rb, int cb, int c0) {
+  const int lane = threadIdx.x & 31;
+  const int g = lane >> 2, tq = lane & 3;
+  double* cp = Cs + (rb * 8 + g) + (cb * 8 + 2 * tq) * kLd;
+  double d0 = cp[0], d1 = cp[kLd];
+  const double* xp = Xs + (rb * 8 + g) + (c0 + tq) * kLd;
+  const double* yp = Ys + (cb * 8 + g) + (c0 + tq) * kLd;
+  mma884(d0, d1, -xp[0], yp[0]);
+  mma884(d0, d1, -xp[4 * kLd], yp[4 * kLd]);
+  cp[0] = d0;
+  cp[kLd] = d1;
+}
+
+// 64x64 Cholesky of the tile in shared memory (lower part valid, ld = kLd) in panels of 8 columns.
+// Panel step: every row thread (tid < 64, row >= c0) reads the 8x8 diagonal block (broadcast), factors
+// it redundantly in registers and solves its own row against it -- no cross-lane traffic inside the
+// 8-column chain; then all 8 warps apply the rank-8 update to the trailing tiles with DMMA.
+// rinv[c] = 1 / L[c][c] is left in shared memory for the substitution TRSM.
+__device__ void potrf_64_v2(double* As, double* s_rinv, int* fail) {
+  const int tid = threadIdx.x, warp = tid >> 5;
+#pragma unroll 1
+  for (int p = 0; p < 8; ++p) {
+    const int c0 = 8 * p;
+    if (tid < kT && tid >= c0) {
+      double D[8][8], a[8], ri[8], x[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int i = j; i < 8; ++i) D[i][j] = As[(c0 + i) + (c0 + j) * kLd];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] = As[tid + (c0 + j) * kLd];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        double d = D[j][j];
+        if (!(d > 0.0)) {
+          *fail = 1;
+          d = __longlong_as_double(0x7ff8000000000000LL);
+        }
+        ri[j] = rsqrt(d);
+#pragma unroll
+        for (int i = j + 1; i < 8; ++i) D[i][j] *= ri[j];
+#pragma unroll
+        for (int jj = j + 1; jj < 8; ++jj)
+#pragma unroll
+          for (int i = jj; i < 8; ++i) D[i][jj] -= D[i][j] * D[jj][j];
+      }
+      const int jr = tid - c0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        double v = a[j];
+#pragma unroll
+        for (int c = 0; c < j; ++c) v -= x[c] * D[j][c];
+        x[j] = v * ri[j];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) As[tid + (c0 + j) * kLd] = jr >= j ? x[j] : 0.0;
+      if (jr == 0) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s_rinv[c0 + j] = ri[j];
+      }
+    }
+    __syncthreads();
+    if (p < 7) {
+      int t = 0;
+      for (int cb = p + 1; cb < 8; ++cb)
+        for (int rb = cb; rb < 8; ++rb, ++t)
+          if ((t & 7) == warp) rank8_tile(As, As, As, rb, cb, c0);
+    }
+    __syncthreads();
+  }
+}
+
+// X <- X * L^-T for the 64x64 tile X (Xs) and the lower-triangular L (Ls, identity padded), by panels:
+// per panel every row thread substitutes its 8 entries against the 8x8 diagonal block of L, then the
+// trailing columns get the rank-8 update with DMMA.  No L^-1 needed.
+__device__ void trsm_subst_64(double* Xs, const double* Ls, const double* s_rinv) {
+  const int tid = threadIdx.x, warp = tid >> 5;
+#pragma unroll 1
+  for (int p = 0; p < 8; ++p) {
+    const int c0 = 8 * p;
+    if (tid < kT) {
+      double Lb[8][8], a[8], x[8];
+#pragma unroll
+      for (int j = 1; j < 8; ++j)
+#pragma unroll
+        for (int c = 0; c < j; ++c) Lb[j][c] = Ls[(c0 + j) + (c0 + c) * kLd];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) a[j] = Xs[tid + (c0 + j) * kLd];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        double v = a[j];
+#pragma unroll
+        for (int c = 0; c < j; ++c) v -= x[c] * Lb[j][c];
+        x[j] = v * s_rinv[c0 + j];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) Xs[tid + (c0 + j) * kLd] = x[j];
+    }
+    __syncthreads();
+    if (p < 7) {
+      int t = 0;
+      for (int cb = p + 1; cb < 8; ++cb)
+        for (int rb = 0; rb < 8; ++rb, ++t)
+          if ((t & 7) == warp) rank8_tile(Xs, Xs, Ls, rb, cb, c0);
+    }
+    __syncthreads();
+  }
+}
+
+// smem <- the final L_kk of pivot tile k from the front (strictly upper part zero, identity padding)
+__device__ __forceinline__ void load_L(double* S, const double* __restrict__ F, int m, int s0, int nb) {
+  const int r = threadIdx.x & 63;
+  for (int c = threadIdx.x >> 6; c < kT; c += kLargeThreads / 64) {
+    double v = 0.0;
+    if (r < nb && c < nb) {
+      if (r >= c) v = __ldcg(F + (s0 + r) + (size_t)(s0 + c) * m);
+    } else if (r == c) {
+      v = 1.0;
+    }
+    S[r + c * kLd] = v;
+  }
+}
+
 __device__ unsigned long long* g_trace = nullptr;
 __device__ unsigned long long g_diag_stamps[8 * 512];  // debug: fine-grained DIAG phases  // debug: [task][4] = claim, deps ready, done (ns), smid
 __device__ __forceinline__ unsigned long long gtime() {
@@ -339,6 +464,7 @@ __global__ void __launch_bounds__(kLargeThreads, 2) large_factor_kernel(Ctrl* ct
   double* As = sm;
   double* Bs = sm + kT * kLd;
   __shared__ int s_task;
+  __shared__ double s_rinv[kT];
   if (ctrl->done) return;
   const int tid = threadIdx.x;
   for (;;) {
@@ -356,44 +482,88 @@ __global__ void __launch_bounds__(kLargeThreads, 2) large_factor_kernel(Ctrl* ct
     if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 0] = gtime();
     if (task.type == 3) {
       // ---------------- DIAG(k): POTRF(k), then TRSM(k+1,k) and UPDATE(k+1,k+1,k) on the critical path
+      __shared__ int s_pre;
+      double* rinv_g = ld.rinv + lf.linv_off / kT + (size_t)k * kT;
+      // tile (k+1, k) is usually ready before the diagonal tile: fetch it first if so
+      if (tid == 0) s_pre = (k + 1 < nt) && ld_acquire(cnt + (k + 1) * nt + k) == k;
       wait_eq(cnt + k * nt + k, k);
       if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 1] = gtime();
       const int s0 = tile_start(lf, k), nb = tile_size(lf, k);
+      const bool pre = s_pre != 0;
       load_tile(As, F + s0 + (size_t)s0 * m, m, nb, nb, true);
+      if (pre) load_tile(Bs, F + tile_start(lf, k + 1) + (size_t)s0 * m, m, tile_size(lf, k + 1), nb, false);
       __syncthreads();
       if (g_trace && tid == 0 && k < 512) g_diag_stamps[k * 8 + 0] = gtime();
-      potrf_64_panels(As, &ctrl->chol_fail);
+      potrf_64_v2(As, s_rinv, &ctrl->chol_fail);
       if (g_trace && tid == 0 && k < 512) g_diag_stamps[k * 8 + 1] = gtime();
       {
         const int r = tid & 63;
-        for (int c = tid >> 6; c < kT; c += kLargeThreads / 64) {
-          if (r < c) As[r + c * kLd] = 0.0;  // the inverse and the TRSM read the full tile
+        for (int c = tid >> 6; c < kT; c += kLargeThreads / 64)
           if (r < nb && c < nb && r >= c) F[(s0 + r) + (size_t)(s0 + c) * m] = As[r + c * kLd];
-        }
+        if (tid < kT) rinv_g[tid] = tid < nb ? s_rinv[tid] : 1.0;
+        if (tid < kT && tid >= nb) s_rinv[tid] = 1.0;
       }
-      __syncthreads();
+      publish(cnt + k * nt + k, k + 1);
       if (g_trace && tid == 0 && k < 512) g_diag_stamps[k * 8 + 2] = gtime();
+      if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 3] = gtime();  // POTRF published
+      if (k + 1 < nt) {
+        // TRSM(k+1, k) by substitution against L_kk still in shared memory
+        if (!pre) {
+          wait_eq(cnt + (k + 1) * nt + k, k);
+          load_tile(Bs, F + tile_start(lf, k + 1) + (size_t)s0 * m, m, tile_size(lf, k + 1), nb, false);
+          __syncthreads();
+        }
+        trsm_subst_64(Bs, As, s_rinv);
+        {
+          const int r = tid & 63;
+          const int ri = tile_start(lf, k + 1), ni = tile_size(lf, k + 1);
+          for (int c = tid >> 6; c < nb; c += kLargeThreads / 64)
+            if (r < ni) F[(ri + r) + (size_t)(s0 + c) * m] = Bs[r + c * kLd];
+        }
+        publish(cnt + (k + 1) * nt + k, k + 1);
+        if (g_trace && tid == 0 && k < 512) g_diag_stamps[k * 8 + 3] = gtime();
+        // UPDATE(k+1, k+1, k)
+        wait_eq(cnt + (k + 1) * nt + (k + 1), k);
+        gemm_store(F, m, lf, k + 1, k + 1, Bs, Bs, false, nullptr);
+        publish(cnt + (k + 1) * nt + (k + 1), k + 1);
+      }
+      if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 2] = gtime();
+    } else if (task.type == 5) {
+      // ---------------- INV(k): L_kk^-1 for the triangular solves (off the critical path) ----------------
+      wait_ge(cnt + k * nt + k, k + 1);
+      if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 1] = gtime();
+      const int s0 = tile_start(lf, k), nb = tile_size(lf, k);
+      load_L(As, F, m, s0, nb);
+      __syncthreads();
       tri_inverse_64(As, Bs);
-      if (g_trace && tid == 0 && k < 512) g_diag_stamps[k * 8 + 3] = gtime();
       double* linv = ld.linv + lf.linv_off + (size_t)k * kT * kT;
       {
         const int r = tid & 63;
         for (int c = tid >> 6; c < kT; c += kLargeThreads / 64) linv[r + c * kT] = Bs[r + c * kLd];
       }
-      publish(cnt + k * nt + k, k + 1);
-      if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 3] = gtime();  // POTRF published
-      if (k + 1 < nt) {
-        // TRSM(k+1, k) with L_kk^-1 still in shared memory
-        wait_eq(cnt + (k + 1) * nt + k, k);
-        load_tile(As, F + tile_start(lf, k + 1) + (size_t)s0 * m, m, tile_size(lf, k + 1), nb, false);
-        __syncthreads();
-        gemm_store(F, m, lf, k + 1, k, As, Bs, true, As);  // result kept in As
-        publish(cnt + (k + 1) * nt + k, k + 1);
-        // UPDATE(k+1, k+1, k)
-        wait_eq(cnt + (k + 1) * nt + (k + 1), k);
-        gemm_store(F, m, lf, k + 1, k + 1, As, As, false, nullptr);
-        publish(cnt + (k + 1) * nt + (k + 1), k + 1);
+      __syncthreads();
+      if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 2] = gtime();
+    } else if (task.type == 1) {
+      // ---------------- TRSM(i,k) by substitution ----------------
+      if (tid == 0) {
+        while (ld_acquire(cnt + k * nt + k) < k + 1) __nanosleep(32);
+        while (ld_acquire(cnt + i * nt + k) != k) __nanosleep(32);
       }
+      __syncthreads();
+      if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 1] = gtime();
+      const int s0 = tile_start(lf, k), nb = tile_size(lf, k);
+      const int ri = tile_start(lf, i), ni = tile_size(lf, i);
+      load_L(As, F, m, s0, nb);
+      load_tile(Bs, F + ri + (size_t)s0 * m, m, ni, nb, false);
+      if (tid < kT) s_rinv[tid] = __ldcg(ld.rinv + lf.linv_off / kT + (size_t)k * kT + tid);
+      __syncthreads();
+      trsm_subst_64(Bs, As, s_rinv);
+      {
+        const int r = tid & 63;
+        for (int c = tid >> 6; c < nb; c += kLargeThreads / 64)
+          if (r < ni) F[(ri + r) + (size_t)(s0 + c) * m] = Bs[r + c * kLd];
+      }
+      publish(cnt + i * nt + k, k + 1);
       if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 2] = gtime();
     } else if (task.type == 4) {
       // ---------------- UPDATE(i, j, [k, k1)) ----------------
@@ -460,8 +630,8 @@ __global__ void __launch_bounds__(kLargeThreads, 2) large_factor_kernel(Ctrl* ct
       publish(cnt + i * nt + j, k1);
       if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 2] = gtime();
     } else {
-      // ---------------- TRSM(i,k) / UPDATE(i,j,k) ----------------
-      const bool trsm = task.type == 1;
+      // ---------------- UPDATE(i,j,k) ----------------
+      const bool trsm = false;
       if (tid == 0) {
         if (trsm) {
           while (ld_acquire(cnt + k * nt + k) < k + 1) __nanosleep(32);

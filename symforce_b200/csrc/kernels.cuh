@@ -125,7 +125,7 @@ struct LargeFront {
 };
 struct LargeTask {
   int lf;
-  short type, k, i, j;  // type: 1 TRSM(i,k), 2 UPDATE(i,j,k), 3 DIAG(k), 4 UPDATE(i,j,[k,k1))
+  short type, k, i, j;  // type: 1 TRSM(i,k), 2 UPDATE(i,j,k), 3 DIAG(k), 4 UPDATE(i,j,[k,k1)), 5 INV(k)
   short k1, pad;
 };
 struct LargeJob {
@@ -146,6 +146,7 @@ struct LargeDev {
   int* counters;
   int* queue;  // one head per level
   double* linv;
+  double* rinv;     // 1 / diag(L_kk) per pivot tile (64 each), written by DIAG, read by the substitution TRSMs
   int* sflags;      // solve flags / counters (zeroed before every solve)
   double* contrib;  // backward-solve contribution slots
 };

@@ -204,6 +204,7 @@ void build_front_tasks(const LargeFront& x, int li, int Kc, std::vector<LargeTas
     }
     if (k + 1 < wt) tl.push_back(LargeTask{li, 3, (short)(k + 1), (short)(k + 1), (short)(k + 1), 0, 0});
     for (int i = k + 3; i < nt; ++i) T(i, k);
+    tl.push_back(LargeTask{li, 5, (short)k, (short)k, (short)k, 0, 0});  // INV(k): L_kk^-1 for the solves
     // deferred range tasks of the last panel boundary: everything needed by this step, plus a share
     if (dpos < deferred.size()) {
       size_t upto = dpos + (deferred.size() - dpos + d_steps_left - 1) / std::max(1, d_steps_left);
@@ -267,6 +268,8 @@ void verify_task_list(const LargeFront& x, const std::vector<LargeTask>& tl) {
         if (C(k + 1, k + 1) != k) fail(t, "diag update");
         C(k + 1, k + 1) = k + 1;
       }
+    } else if (t.type == 5) {
+      if (C(k, k) < k + 1) fail(t, "inv");
     } else if (t.type == 1) {
       if (C(k, k) < k + 1 || C(i, k) != k) fail(t, "trsm");
       C(i, k) = k + 1;
@@ -672,6 +675,7 @@ void upload_structures(sfx_problem* p) {
     p->ld.counters = P.alloc<int>(cnt_off);
     p->ld.queue = P.alloc<int>(f.n_levels);
     p->ld.linv = P.alloc<double>(linv_off);
+    p->ld.rinv = P.alloc<double>(linv_off / T + T);
     p->n_sflags = flag_off;
     p->ld.sflags = P.alloc<int>(flag_off);
     p->ld.contrib = P.alloc<double>(contrib_off);

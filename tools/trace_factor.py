@@ -18,7 +18,7 @@ t = buf.astype(np.int64)
 ok = t[:, 0] > 0
 t0 = t[ok, 0].min()
 claim, ready, done, potrf = (t[:, 0] - t0) / 1e3, (t[:, 1] - t0) / 1e3, (t[:, 2] - t0) / 1e3, (t[:, 3] - t0) / 1e3
-for ty, name in [(3, "DIAG"), (1, "TRSM"), (2, "UPDATE")]:
+for ty, name in [(3, "DIAG"), (1, "TRSM"), (2, "UPDATE"), (4, "RANGE"), (5, "INV")]:
     m = ok & (info[:, 1] == ty)
     print(f"{name}: n={m.sum()} wait(claim->ready) mean {np.mean(ready[m]-claim[m]):.1f} us  exec(ready->done) mean {np.mean(done[m]-ready[m]):.1f} us  p90 {np.percentile(done[m]-ready[m],90):.1f}")
 m = ok & (info[:, 1] == 3)
@@ -34,4 +34,12 @@ g.lib.sfx_debug_diag_stamps(st.ctypes.data_as(C.POINTER(C.c_uint64)))
 st = st.astype(np.int64)
 v = st[:40]
 print("DIAG phases (us, last writer per k): potrf", np.round(np.mean((v[:, 1] - v[:, 0]) / 1e3), 2), "store+sync",
-      np.round(np.mean((v[:, 2] - v[:, 1]) / 1e3), 2), "inverse", np.round(np.mean((v[:, 3] - v[:, 2]) / 1e3), 2))
+      np.round(np.mean((v[:, 2] - v[:, 1]) / 1e3), 2), "trsm(k+1,k)", np.round(np.mean((v[:, 3] - v[:, 2]) / 1e3), 2))
+
+# per large front: span, number of tasks, busy time
+for lf in np.unique(info[ok, 0]):
+    mm = ok & (info[:, 0] == lf)
+    md = mm & (info[:, 1] == 3)
+    print(f"front {lf}: tasks {mm.sum()} diag {md.sum()} span {claim[mm].min():.0f}..{done[mm].max():.0f} us  "
+          f"busy(sum exec) {np.sum(done[mm]-ready[mm])/1e3:.2f} ms  wait(sum) {np.sum(ready[mm]-claim[mm])/1e3:.2f} ms  "
+          f"diag exec {np.mean(done[md]-ready[md]):.1f} us, diag step {(np.diff(np.sort(ready[md])).mean() if md.sum()>1 else 0):.1f} us")

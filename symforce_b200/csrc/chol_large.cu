@@ -341,21 +341,25 @@ __device__ __forceinline__ void rank8_tile(double* Cs, const double* Xs, const d
 // 64x64 Cholesky of the tile in shared memory (lower part valid, ld = kLd) in panels of 8 columns.
 // Panel step: every row thread (tid < 64, row >= c0) reads the 8x8 diagonal block (broadcast), factors
 // it redundantly in registers and solves its own row against it -- no cross-lane traffic inside the
-// 8-column chain; then all 8 warps apply the rank-8 update to the trailing tiles with DMMA.
-// rinv[c] = 1 / L[c][c] is left in shared memory for the substitution TRSM.
-__device__ void potrf_64_v2(double* As, double* s_rinv, int* fail) {
+// 8-column chain; eight threads of a third warp do the same factorization and produce the columns of
+// the inverse of the 8x8 block (s_binv[p], column-major 8x8, used by the TRSMs as a DMMA operand);
+// then all 8 warps apply the rank-8 update to the trailing tiles with DMMA.
+__device__ void potrf_64_v2(double* As, double* s_binv, int* fail) {
   const int tid = threadIdx.x, warp = tid >> 5;
 #pragma unroll 1
   for (int p = 0; p < 8; ++p) {
     const int c0 = 8 * p;
-    if (tid < kT && tid >= c0) {
-      double D[8][8], a[8], ri[8], x[8];
+    const bool row_thread = tid < kT && tid >= c0;
+    const bool inv_thread = tid >= kT && tid < kT + 8;
+    if (row_thread || inv_thread) {
+      double D[8][8], ri[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j)
 #pragma unroll
         for (int i = j; i < 8; ++i) D[i][j] = As[(c0 + i) + (c0 + j) * kLd];
+      double a[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) a[j] = As[tid + (c0 + j) * kLd];
+      for (int j = 0; j < 8; ++j) a[j] = row_thread ? As[tid + (c0 + j) * kLd] : 0.0;
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         double d = D[j][j];
@@ -371,19 +375,31 @@ __device__ void potrf_64_v2(double* As, double* s_rinv, int* fail) {
 #pragma unroll
           for (int i = jj; i < 8; ++i) D[i][jj] -= D[i][j] * D[jj][j];
       }
-      const int jr = tid - c0;
+      if (row_thread) {
+        const int jr = tid - c0;
+        double x[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        double v = a[j];
+        for (int j = 0; j < 8; ++j) {
+          double v = a[j];
 #pragma unroll
-        for (int c = 0; c < j; ++c) v -= x[c] * D[j][c];
-        x[j] = v * ri[j];
-      }
+          for (int c = 0; c < j; ++c) v -= x[c] * D[j][c];
+          x[j] = v * ri[j];
+        }
 #pragma unroll
-      for (int j = 0; j < 8; ++j) As[tid + (c0 + j) * kLd] = jr >= j ? x[j] : 0.0;
-      if (jr == 0) {
+        for (int j = 0; j < 8; ++j) As[tid + (c0 + j) * kLd] = jr >= j ? x[j] : 0.0;
+      } else {
+        // column e of the inverse of the 8x8 block: y = L^-1 e_e by forward substitution
+        const int e = tid - kT;
+        double y[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) s_rinv[c0 + j] = ri[j];
+        for (int i = 0; i < 8; ++i) {
+          double v = (i == e) ? 1.0 : 0.0;
+#pragma unroll
+          for (int c = 0; c < i; ++c) v -= D[i][c] * y[c];
+          y[i] = (i >= e) ? v * ri[i] : 0.0;
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) s_binv[p * 64 + i + 8 * e] = y[i];
       }
     }
     __syncthreads();
@@ -397,41 +413,70 @@ __device__ void potrf_64_v2(double* As, double* s_rinv, int* fail) {
   }
 }
 
-// X <- X * L^-T for the 64x64 tile X (Xs) and the lower-triangular L (Ls, identity padded), by panels:
-// per panel every row thread substitutes its 8 entries against the 8x8 diagonal block of L, then the
-// trailing columns get the rank-8 update with DMMA.  No L^-1 needed.
-__device__ void trsm_subst_64(double* Xs, const double* Ls, const double* s_rinv) {
-  const int tid = threadIdx.x, warp = tid >> 5;
-#pragma unroll 1
+// X <- X * L^-T for a 64x64 tile, one warp per 8-row strip held in registers as DMMA accumulator
+// fragments xf[cb] = X[8w + g][8cb + 2tq + {0,1}]; rows are independent, so there is no barrier.  Per panel p:
+//   X_p <- X_p * inv(L_pp)^T        (2 DMMA; inv(L_pp) from s_binv, X_p re-laid out as an A operand by shuffles)
+//   X_cb -= X_p * L[cb, p]^T, cb > p (2 DMMA each, independent)
+__device__ __forceinline__ void frag_to_a(const double (&c)[2], double& a0, double& a1) {
+  // accumulator layout (row g: cols 2tq, 2tq+1) -> A operand layout (row g: col tq, col 4 + tq)
+  const int lane = threadIdx.x & 31;
+  const int g4 = lane & ~3, tq = lane & 3;
+  const double lo0 = __shfl_sync(0xffffffffu, c[0], g4 + (tq >> 1));
+  const double hi0 = __shfl_sync(0xffffffffu, c[1], g4 + (tq >> 1));
+  const double lo1 = __shfl_sync(0xffffffffu, c[0], g4 + 2 + (tq >> 1));
+  const double hi1 = __shfl_sync(0xffffffffu, c[1], g4 + 2 + (tq >> 1));
+  a0 = (tq & 1) ? hi0 : lo0;
+  a1 = (tq & 1) ? hi1 : lo1;
+}
+__device__ __forceinline__ void trsm_frag_64(double (&xf)[8][2], const double* Ls, const double* s_binv) {
+  const int lane = threadIdx.x & 31;
+  const int g = lane >> 2, tq = lane & 3;
+#pragma unroll
   for (int p = 0; p < 8; ++p) {
     const int c0 = 8 * p;
-    if (tid < kT) {
-      double Lb[8][8], a[8], x[8];
-#pragma unroll
-      for (int j = 1; j < 8; ++j)
-#pragma unroll
-        for (int c = 0; c < j; ++c) Lb[j][c] = Ls[(c0 + j) + (c0 + c) * kLd];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) a[j] = Xs[tid + (c0 + j) * kLd];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        double v = a[j];
-#pragma unroll
-        for (int c = 0; c < j; ++c) v -= x[c] * Lb[j][c];
-        x[j] = v * s_rinv[c0 + j];
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) Xs[tid + (c0 + j) * kLd] = x[j];
-    }
-    __syncthreads();
+    double a0, a1;
+    frag_to_a(xf[p], a0, a1);
+    double d0 = 0.0, d1 = 0.0;
+    mma884(d0, d1, a0, s_binv[p * 64 + g + 8 * tq]);
+    mma884(d0, d1, a1, s_binv[p * 64 + g + 8 * (4 + tq)]);
+    xf[p][0] = d0;
+    xf[p][1] = d1;
     if (p < 7) {
-      int t = 0;
-      for (int cb = p + 1; cb < 8; ++cb)
-        for (int rb = 0; rb < 8; ++rb, ++t)
-          if ((t & 7) == warp) rank8_tile(Xs, Xs, Ls, rb, cb, c0);
+      frag_to_a(xf[p], a0, a1);
+      a0 = -a0;
+      a1 = -a1;
+#pragma unroll
+      for (int cb = p + 1; cb < 8; ++cb) {
+        const double* lp = Ls + (cb * 8 + g) + (c0 + tq) * kLd;
+        mma884(xf[cb][0], xf[cb][1], a0, lp[0]);
+        mma884(xf[cb][0], xf[cb][1], a1, lp[4 * kLd]);
+      }
     }
-    __syncthreads();
   }
+}
+// fragments of warp w's strip <-> the 64 x 64 tile at G (global, ld ldg; rows < nr, cols < nc valid)
+__device__ __forceinline__ void load_frag(double (&xf)[8][2], const double* __restrict__ G, int ldg, int nr, int nc) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r = warp * 8 + (lane >> 2), tq = lane & 3;
+#pragma unroll
+  for (int cb = 0; cb < 8; ++cb)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int c = cb * 8 + 2 * tq + e;
+      xf[cb][e] = (r < nr && c < nc) ? __ldcg(G + r + (size_t)c * ldg) : 0.0;
+    }
+}
+__device__ __forceinline__ void store_frag(const double (&xf)[8][2], double* G, int ldg, int nr, int nc, double* keep) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int r = warp * 8 + (lane >> 2), tq = lane & 3;
+#pragma unroll
+  for (int cb = 0; cb < 8; ++cb)
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int c = cb * 8 + 2 * tq + e;
+      if (r < nr && c < nc) G[r + (size_t)c * ldg] = xf[cb][e];
+      if (keep != nullptr) keep[r + c * kLd] = xf[cb][e];
+    }
 }
 
 // smem <- the final L_kk of pivot tile k from the front (strictly upper part zero, identity padding)
@@ -464,7 +509,7 @@ __global__ void __launch_bounds__(kLargeThreads, 2) large_factor_kernel(Ctrl* ct
   double* As = sm;
   double* Bs = sm + kT * kLd;
   __shared__ int s_task;
-  __shared__ double s_rinv[kT];
+  __shared__ double s_binv[512];  // inverses of the eight 8x8 diagonal blocks of the current L_kk
   if (ctrl->done) return;
   const int tid = threadIdx.x;
   for (;;) {
@@ -482,44 +527,33 @@ __global__ void __launch_bounds__(kLargeThreads, 2) large_factor_kernel(Ctrl* ct
     if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 0] = gtime();
     if (task.type == 3) {
       // ---------------- DIAG(k): POTRF(k), then TRSM(k+1,k) and UPDATE(k+1,k+1,k) on the critical path
-      __shared__ int s_pre;
-      double* rinv_g = ld.rinv + lf.linv_off / kT + (size_t)k * kT;
-      // tile (k+1, k) is usually ready before the diagonal tile: fetch it first if so
-      if (tid == 0) s_pre = (k + 1 < nt) && ld_acquire(cnt + (k + 1) * nt + k) == k;
+      double* binv_g = ld.binv + lf.linv_off / 8 + (size_t)k * 512;
       wait_eq(cnt + k * nt + k, k);
       if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 1] = gtime();
       const int s0 = tile_start(lf, k), nb = tile_size(lf, k);
-      const bool pre = s_pre != 0;
       load_tile(As, F + s0 + (size_t)s0 * m, m, nb, nb, true);
-      if (pre) load_tile(Bs, F + tile_start(lf, k + 1) + (size_t)s0 * m, m, tile_size(lf, k + 1), nb, false);
       __syncthreads();
       if (g_trace && tid == 0 && k < 512) g_diag_stamps[k * 8 + 0] = gtime();
-      potrf_64_v2(As, s_rinv, &ctrl->chol_fail);
+      potrf_64_v2(As, s_binv, &ctrl->chol_fail);
       if (g_trace && tid == 0 && k < 512) g_diag_stamps[k * 8 + 1] = gtime();
       {
         const int r = tid & 63;
         for (int c = tid >> 6; c < kT; c += kLargeThreads / 64)
           if (r < nb && c < nb && r >= c) F[(s0 + r) + (size_t)(s0 + c) * m] = As[r + c * kLd];
-        if (tid < kT) rinv_g[tid] = tid < nb ? s_rinv[tid] : 1.0;
-        if (tid < kT && tid >= nb) s_rinv[tid] = 1.0;
+        binv_g[tid] = s_binv[tid];
+        binv_g[tid + 256] = s_binv[tid + 256];
       }
       publish(cnt + k * nt + k, k + 1);
       if (g_trace && tid == 0 && k < 512) g_diag_stamps[k * 8 + 2] = gtime();
       if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 3] = gtime();  // POTRF published
       if (k + 1 < nt) {
-        // TRSM(k+1, k) by substitution against L_kk still in shared memory
-        if (!pre) {
-          wait_eq(cnt + (k + 1) * nt + k, k);
-          load_tile(Bs, F + tile_start(lf, k + 1) + (size_t)s0 * m, m, tile_size(lf, k + 1), nb, false);
-          __syncthreads();
-        }
-        trsm_subst_64(Bs, As, s_rinv);
-        {
-          const int r = tid & 63;
-          const int ri = tile_start(lf, k + 1), ni = tile_size(lf, k + 1);
-          for (int c = tid >> 6; c < nb; c += kLargeThreads / 64)
-            if (r < ni) F[(ri + r) + (size_t)(s0 + c) * m] = Bs[r + c * kLd];
-        }
+        // TRSM(k+1, k) against L_kk still in shared memory; result to the front and to Bs for the SYRK
+        wait_eq(cnt + (k + 1) * nt + k, k);
+        const int ri = tile_start(lf, k + 1), ni = tile_size(lf, k + 1);
+        double xf[8][2];
+        load_frag(xf, F + ri + (size_t)s0 * m, m, ni, nb);
+        trsm_frag_64(xf, As, s_binv);
+        store_frag(xf, F + ri + (size_t)s0 * m, m, ni, nb, Bs);
         publish(cnt + (k + 1) * nt + k, k + 1);
         if (g_trace && tid == 0 && k < 512) g_diag_stamps[k * 8 + 3] = gtime();
         // UPDATE(k+1, k+1, k)
@@ -544,7 +578,7 @@ __global__ void __launch_bounds__(kLargeThreads, 2) large_factor_kernel(Ctrl* ct
       __syncthreads();
       if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 2] = gtime();
     } else if (task.type == 1) {
-      // ---------------- TRSM(i,k) by substitution ----------------
+      // ---------------- TRSM(i,k): strip-per-warp substitution in registers ----------------
       if (tid == 0) {
         while (ld_acquire(cnt + k * nt + k) < k + 1) __nanosleep(32);
         while (ld_acquire(cnt + i * nt + k) != k) __nanosleep(32);
@@ -553,16 +587,17 @@ __global__ void __launch_bounds__(kLargeThreads, 2) large_factor_kernel(Ctrl* ct
       if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 1] = gtime();
       const int s0 = tile_start(lf, k), nb = tile_size(lf, k);
       const int ri = tile_start(lf, i), ni = tile_size(lf, i);
+      double xf[8][2];
+      load_frag(xf, F + ri + (size_t)s0 * m, m, ni, nb);
       load_L(As, F, m, s0, nb);
-      load_tile(Bs, F + ri + (size_t)s0 * m, m, ni, nb, false);
-      if (tid < kT) s_rinv[tid] = __ldcg(ld.rinv + lf.linv_off / kT + (size_t)k * kT + tid);
-      __syncthreads();
-      trsm_subst_64(Bs, As, s_rinv);
       {
-        const int r = tid & 63;
-        for (int c = tid >> 6; c < nb; c += kLargeThreads / 64)
-          if (r < ni) F[(ri + r) + (size_t)(s0 + c) * m] = Bs[r + c * kLd];
+        const double* binv_g = ld.binv + lf.linv_off / 8 + (size_t)k * 512;
+        s_binv[tid] = __ldcg(binv_g + tid);
+        s_binv[tid + 256] = __ldcg(binv_g + tid + 256);
       }
+      __syncthreads();
+      trsm_frag_64(xf, As, s_binv);
+      store_frag(xf, F + ri + (size_t)s0 * m, m, ni, nb, nullptr);
       publish(cnt + i * nt + k, k + 1);
       if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 2] = gtime();
     } else if (task.type == 4) {

@@ -146,7 +146,7 @@ struct LargeDev {
   int* counters;
   int* queue;  // one head per level
   double* linv;
-  double* rinv;     // 1 / diag(L_kk) per pivot tile (64 each), written by DIAG, read by the substitution TRSMs
+  double* binv;     // inverses of the eight 8x8 diagonal blocks of every L_kk (512 doubles per pivot tile): DIAG -> TRSMs
   int* sflags;      // solve flags / counters (zeroed before every solve)
   double* contrib;  // backward-solve contribution slots
 };

@@ -675,7 +675,7 @@ void upload_structures(sfx_problem* p) {
     p->ld.counters = P.alloc<int>(cnt_off);
     p->ld.queue = P.alloc<int>(f.n_levels);
     p->ld.linv = P.alloc<double>(linv_off);
-    p->ld.rinv = P.alloc<double>(linv_off / T + T);
+    p->ld.binv = P.alloc<double>(linv_off / 8 + 512);
     p->n_sflags = flag_off;
     p->ld.sflags = P.alloc<int>(flag_off);
     p->ld.contrib = P.alloc<double>(contrib_off);

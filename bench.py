@@ -264,19 +264,27 @@ def main():
         lin_bytes = 256 * n_obs + 512 * n_cams + 96 * n_pts
         schur_bytes = 216 * n_obs + 72 * n_pts + 432 * n_cams + 8 * 81 * info["s_blocks"]
         fac_flops = float(info["factor_flops"])
-        fp64_peak = 40.0  # TFLOP/s nominal B200 FP64 (DMMA); MEASURED_PEAKS.json has no FP64 figure
-        rl_lin = {"kernel": "linearize_bal_kernel (+zero, error reduce)", "bound": "hbm",
+        # MEASURED_PEAKS.json has no FP64 figure: the DMMA peak was measured once on this pool's B200 with
+        # tools/micro/fp64_peak.cu (profiles/fp64_peak.json); nominal 40 TFLOP/s otherwise
+        fp64_peak, fp64_src = 40.0, "nominal B200 FP64 tensor 40 TFLOP/s (no FP64 number in MEASURED_PEAKS.json)"
+        try:
+            fp = json.load(open(os.path.join(ROOT, "profiles", "fp64_peak.json")))
+            fp64_peak = float(fp["dmma_tflops"])
+            fp64_src = "profiles/fp64_peak.json: mma.sync.m8n8k4.f64 peak measured with tools/micro/fp64_peak.cu"
+        except Exception:
+            pass
+        rl_lin = {"kernel": "linearize_bal_kernel (+zero, point finalize, error reduce)", "bound": "hbm",
                   "achieved": lin_bytes / (ph["linearize"] * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
-                  "traffic": traffic.get("linearize_bal_kernel"), "peak_source": hbm_src}
+                  "traffic": traffic.get("linearize"), "peak_source": hbm_src}
         rl_lin["frac"] = rl_lin["achieved"] / hbm
-        rl_schur = {"kernel": "schur_cinv/s/rhs kernels", "bound": "hbm",
+        rl_schur = {"kernel": "schur_cinv + schur_w_rhs + schur_s9 kernels", "bound": "hbm",
                     "achieved": schur_bytes / (ph["schur"] * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
-                    "traffic": traffic.get("schur_s_kernel"), "peak_source": hbm_src}
+                    "traffic": traffic.get("schur"), "peak_source": hbm_src}
         rl_schur["frac"] = rl_schur["achieved"] / hbm
         rl_fac = {"kernel": "large_factor_kernel (tile-DAG supernodal Cholesky, DMMA m8n8k4)", "bound": "tensor",
                   "achieved": fac_flops / (ph["factorize"] * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
                   "traffic": traffic.get("large_factor_kernel"),
-                  "peak_source": "nominal B200 FP64 tensor 40 TFLOP/s (no FP64 number in MEASURED_PEAKS.json)"}
+                  "peak_source": fp64_src}
         rl_fac["frac"] = rl_fac["achieved"] / fp64_peak
         dominant = max(("factorize", rl_fac), ("schur", rl_schur), ("linearize", rl_lin), key=lambda kv: ph[kv[0]])[1]
         line = {

@@ -475,15 +475,28 @@ __global__ void __launch_bounds__(128) bal_point_finalize_kernel(const Ctrl* __r
   }
   double* Hd = sp.H[blk] + __ldg(b.pf_diag + pt);
   double* rh = sp.rhs[blk] + __ldg(b.pf_rhs + pt);
-  atomicAdd(Hd + 0, a[0]);
-  atomicAdd(Hd + 1, a[1]);
-  atomicAdd(Hd + 2, a[2]);
-  atomicAdd(Hd + 4, a[3]);
-  atomicAdd(Hd + 5, a[4]);
-  atomicAdd(Hd + 8, a[5]);
-  atomicAdd(rh + 0, a[6]);
-  atomicAdd(rh + 1, a[7]);
-  atomicAdd(rh + 2, a[8]);
+  if (b.pf_exclusive) {
+    // no other batch touches these point blocks (zeroed before): plain stores
+    Hd[0] = a[0];
+    Hd[1] = a[1];
+    Hd[2] = a[2];
+    Hd[4] = a[3];
+    Hd[5] = a[4];
+    Hd[8] = a[5];
+    rh[0] = a[6];
+    rh[1] = a[7];
+    rh[2] = a[8];
+  } else {
+    atomicAdd(Hd + 0, a[0]);
+    atomicAdd(Hd + 1, a[1]);
+    atomicAdd(Hd + 2, a[2]);
+    atomicAdd(Hd + 4, a[3]);
+    atomicAdd(Hd + 5, a[4]);
+    atomicAdd(Hd + 8, a[5]);
+    atomicAdd(rh + 0, a[6]);
+    atomicAdd(rh + 1, a[7]);
+    atomicAdd(rh + 2, a[8]);
+  }
 }
 
 __global__ void zero_lin_kernel(const Ctrl* __restrict__ ctrl, StatePtrs sp, int mode, int64_t n_h, int n_rhs) {

@@ -58,6 +58,7 @@ struct LinBatch {
   double* pbuf;      // nullptr: point blocks are accumulated with atomics instead
   const int32_t *pf_ptr, *pf_slot, *pf_diag, *pf_rhs;
   int n_pf;
+  int pf_exclusive;  // the point blocks receive contributions from this batch only
 };
 
 struct SchurDev {

@@ -360,6 +360,7 @@ void upload_structures(sfx_problem* p) {
           }
         ptr.push_back(bp.n);
         lb.n_pf = (int)diag.size();
+        lb.pf_exclusive = a.batches.size() == 1 ? 1 : 0;
         lb.pf_ptr = P.upload(ptr);
         lb.pf_slot = P.upload(order);
         lb.pf_diag = P.upload(diag);
@@ -633,7 +634,7 @@ void upload_structures(sfx_problem* p) {
       // the window of tasks in flight always spans all fronts (one front's critical path hides behind
       // the others' trailing updates)
       {
-        static const int Kc = getenv("SFX_KC") ? std::max(1, atoi(getenv("SFX_KC"))) : 4;
+        static const int Kc = getenv("SFX_KC") ? std::max(1, atoi(getenv("SFX_KC"))) : 6;
         std::vector<std::vector<LargeTask>> per(lv.n_lf);
         for (int q = 0; q < lv.n_lf; ++q) {
           build_front_tasks(lfs[lv.lf0 + q], lv.lf0 + q, Kc, per[q]);

@@ -1,0 +1,7 @@
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/mgpu_check.py 2>&1 | tail -4
+python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29513 bench.py --gpus 2 --steps 10 --warmup 3 --cpu-baseline 0 2>&1 | tail -1 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print('2gpu', d['ms_per_step'], d['phases_ms_per_iteration'], d['e2e'])"
+python bench.py --steps 10 --warmup 3 --cpu-baseline 0 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print('1gpu', d['ms_per_step'], d['phases_ms_per_iteration'], d['e2e'])"

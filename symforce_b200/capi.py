@@ -12,7 +12,7 @@ import numpy as np
 from . import desc as D
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libsfx.so")
+LIB_PATH = os.environ.get("SFX_LIB") or os.path.join(_HERE, "lib", "libsfx.so")  # SFX_LIB: experiment builds
 
 EXPORTS = [
     "sfx_default_params", "sfx_problem_create", "sfx_problem_destroy", "sfx_last_error", "sfx_update_params",

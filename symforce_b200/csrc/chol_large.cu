@@ -342,8 +342,9 @@ __device__ __forceinline__ void rank8_tile(double* Cs, const double* Xs, const d
 // Panel step: every row thread (tid < 64, row >= c0) reads the 8x8 diagonal block (broadcast), factors
 // it redundantly in registers and solves its own row against it -- no cross-lane traffic inside the
 // 8-column chain; eight threads of a third warp do the same factorization and produce the columns of
-// the inverse of the 8x8 block (s_binv[p], column-major 8x8, used by the TRSMs as a DMMA operand);
-// then all 8 warps apply the rank-8 update to the trailing tiles with DMMA.
+// the inverse of the 8x8 block (s_binv[p], column-major 8x8, used by the TRSMs as a DMMA operand).
+// The rank-8 trailing update (DMMA) is split: the next panel's tile column right away, all other
+// tile columns by warps 3..7 while warps 0..2 are in the next panel's column chain.
 __device__ void potrf_64_v2(double* As, double* s_binv, int* fail) {
   const int tid = threadIdx.x, warp = tid >> 5;
 #pragma unroll 1
@@ -402,13 +403,17 @@ __device__ void potrf_64_v2(double* As, double* s_binv, int* fail) {
         for (int i = 0; i < 8; ++i) s_binv[p * 64 + i + 8 * e] = y[i];
       }
     }
-    __syncthreads();
-    if (p < 7) {
+    else if (warp >= 3 && p >= 1 && p <= 6) {
+      // meanwhile warps 3..7 finish the trailing update of the PREVIOUS panel (tile columns >= p + 1;
+      // tile column p, the one this panel factors, was updated right after the previous panel)
       int t = 0;
       for (int cb = p + 1; cb < 8; ++cb)
         for (int rb = cb; rb < 8; ++rb, ++t)
-          if ((t & 7) == warp) rank8_tile(As, As, As, rb, cb, c0);
+          if (t % 5 == warp - 3) rank8_tile(As, As, As, rb, cb, c0 - 8);
     }
+    __syncthreads();
+    // rank-8 update of the next panel's tile column only (one tile per warp); the rest overlaps the next panel
+    if (p < 7 && p + 1 + warp < 8) rank8_tile(As, As, As, p + 1 + warp, p + 1, c0);
     __syncthreads();
   }
 }
@@ -527,11 +532,16 @@ __global__ void __launch_bounds__(kLargeThreads, 2) large_factor_kernel(Ctrl* ct
     if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 0] = gtime();
     if (task.type == 3) {
       // ---------------- DIAG(k): POTRF(k), then TRSM(k+1,k) and UPDATE(k+1,k+1,k) on the critical path
+      __shared__ int s_pre;
       double* binv_g = ld.binv + lf.linv_off / 8 + (size_t)k * 512;
+      // tile (k+1, k) is usually ready before the diagonal tile: fetch it now (into Bs) if so
+      if (tid == 0) s_pre = (k + 1 < nt) && ld_acquire(cnt + (k + 1) * nt + k) == k;
       wait_eq(cnt + k * nt + k, k);
       if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 1] = gtime();
       const int s0 = tile_start(lf, k), nb = tile_size(lf, k);
+      const bool pre = s_pre != 0;
       load_tile(As, F + s0 + (size_t)s0 * m, m, nb, nb, true);
+      if (pre) load_tile(Bs, F + tile_start(lf, k + 1) + (size_t)s0 * m, m, tile_size(lf, k + 1), nb, false);
       __syncthreads();
       if (g_trace && tid == 0 && k < 512) g_diag_stamps[k * 8 + 0] = gtime();
       potrf_64_v2(As, s_binv, &ctrl->chol_fail);
@@ -548,10 +558,19 @@ __global__ void __launch_bounds__(kLargeThreads, 2) large_factor_kernel(Ctrl* ct
       if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 3] = gtime();  // POTRF published
       if (k + 1 < nt) {
         // TRSM(k+1, k) against L_kk still in shared memory; result to the front and to Bs for the SYRK
-        wait_eq(cnt + (k + 1) * nt + k, k);
         const int ri = tile_start(lf, k + 1), ni = tile_size(lf, k + 1);
         double xf[8][2];
-        load_frag(xf, F + ri + (size_t)s0 * m, m, ni, nb);
+        if (pre) {
+          const int lane = tid & 31, warp = tid >> 5;
+          const int r = warp * 8 + (lane >> 2), tq = lane & 3;
+#pragma unroll
+          for (int cb = 0; cb < 8; ++cb)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) xf[cb][e] = Bs[r + (cb * 8 + 2 * tq + e) * kLd];
+        } else {
+          wait_eq(cnt + (k + 1) * nt + k, k);
+          load_frag(xf, F + ri + (size_t)s0 * m, m, ni, nb);
+        }
         trsm_frag_64(xf, As, s_binv);
         store_frag(xf, F + ri + (size_t)s0 * m, m, ni, nb, Bs);
         publish(cnt + (k + 1) * nt + k, k + 1);
@@ -716,7 +735,7 @@ void launch_large_zero(cudaStream_t st, const Ctrl* ctrl, const FrontDev& fd, co
 __global__ void __launch_bounds__(256) large_assemble_kernel(const Ctrl* __restrict__ ctrl, FrontDev fd, LargeDev ld,
                                                               const double* __restrict__ sys_static, StatePtrs sp,
                                                               int use_state_H, const double* __restrict__ dvec, int j0,
-                                                              int j1) {
+                                                              int j1, int plain) {
   if (ctrl->done) return;
   const int lane = threadIdx.x & 31;
   const int job_id = j0 + blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -735,7 +754,10 @@ __global__ void __launch_bounds__(256) large_assemble_kernel(const Ctrl* __restr
       const double v = sys[c.src + r + (int64_t)cc * c.src_ld];
       double* dst = c.transposed ? F + (c.dst_row + cc) + (size_t)(c.dst_col + r) * m
                                  : F + (c.dst_row + r) + (size_t)(c.dst_col + cc) * m;
-      atomicAdd(dst, v);
+      if (plain)
+        *dst = v;
+      else
+        atomicAdd(dst, v);
     }
   } else if (job.type == 2) {
     if (dvec != nullptr)
@@ -754,12 +776,26 @@ __global__ void __launch_bounds__(256) large_assemble_kernel(const Ctrl* __restr
   }
 }
 
+void launch_large_preassemble(cudaStream_t st, const Ctrl* ctrl, const FrontDev& fd, const LargeDev& ld,
+                              const double* sys_static, StatePtrs sp, int use_state_H, const double* dvec, int pre_j0,
+                              int pre_j1, int damp_j0, int damp_j1) {
+  if (pre_j1 > pre_j0) {
+    large_assemble_kernel<<<(pre_j1 - pre_j0 + 7) / 8, 256, 0, st>>>(ctrl, fd, ld, sys_static, sp, use_state_H, dvec,
+                                                                    pre_j0, pre_j1, 1);
+    ++g_launches;
+  }
+  if (dvec != nullptr && damp_j1 > damp_j0) {
+    large_assemble_kernel<<<(damp_j1 - damp_j0 + 7) / 8, 256, 0, st>>>(ctrl, fd, ld, sys_static, sp, use_state_H, dvec,
+                                                                      damp_j0, damp_j1, 0);
+    ++g_launches;
+  }
+}
 void launch_large_level(cudaStream_t st, Ctrl* ctrl, const FrontDev& fd, const LargeDev& ld, const LargeLevel& lv,
                         int level, const double* sys_static, StatePtrs sp, int use_state_H, const double* dvec) {
   if (lv.n_lf == 0) return;
   const int nj = lv.j1 - lv.j0;
   if (nj > 0) {
-    large_assemble_kernel<<<(nj + 7) / 8, 256, 0, st>>>(ctrl, fd, ld, sys_static, sp, use_state_H, dvec, lv.j0, lv.j1);
+    large_assemble_kernel<<<(nj + 7) / 8, 256, 0, st>>>(ctrl, fd, ld, sys_static, sp, use_state_H, dvec, lv.j0, lv.j1, 0);
     ++g_launches;
   }
   const int ntask = lv.t1 - lv.t0;

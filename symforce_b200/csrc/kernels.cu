@@ -276,10 +276,13 @@ __device__ __forceinline__ int value_of_lane(int lane) {
 }
 
 constexpr int kBalThreads = 128;
+#ifndef SFX_BAL_MINB
+#define SFX_BAL_MINB 5  // 96 registers, 68 B of spills: 0.83 -> 0.80 ms at final-shape (6: 80 registers, slower)
+#endif
 // SKIP (timing experiments only, results invalid when != 0): bit0 camera block, bit1 point block,
 // bit2 E block, bit3 factor arithmetic
 template <int SKIP>
-__global__ void __launch_bounds__(kBalThreads) linearize_bal_kernel(const Ctrl* __restrict__ ctrl, StatePtrs sp,
+__global__ void __launch_bounds__(kBalThreads, SFX_BAL_MINB) linearize_bal_kernel(const Ctrl* __restrict__ ctrl, StatePtrs sp,
                                                                     LinBatch b, int mode,
                                                                     double* __restrict__ partials) {
   __shared__ double stage[kBalThreads / 32][32 * 27];

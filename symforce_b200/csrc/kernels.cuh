@@ -157,6 +157,9 @@ void launch_large_solve_fwd(cudaStream_t st, const Ctrl* ctrl, const FrontDev& f
                             const LargeLevel& lv, const double* rhs_static, StatePtrs sp, int use_state_rhs);
 void launch_large_solve_bwd(cudaStream_t st, const Ctrl* ctrl, const FrontDev& fd, const LargeDev& ld,
                             const LargeLevel& lv);
+void launch_large_preassemble(cudaStream_t st, const Ctrl* ctrl, const FrontDev& fd, const LargeDev& ld,
+                              const double* sys_static, StatePtrs sp, int use_state_H, const double* dvec, int pre_j0,
+                              int pre_j1, int damp_j0, int damp_j1);
 void launch_large_zero(cudaStream_t st, const Ctrl* ctrl, const FrontDev& fd, const LargeDev& ld, int n_lf);
 cudaError_t configure_large_kernels();
 

@@ -122,6 +122,7 @@ struct sfx_problem {
   cudaStream_t st2 = nullptr;  // side stream: front zeroing overlaps damping + Schur
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int n_large_fronts = 0;
+  int pre_j0 = 0, pre_j1 = 0, damp_j0 = 0, damp_j1 = 0;  // assembly jobs run before level 0 (copies, damping)
   Ctrl* d_ctrl = nullptr;
   Ctrl* h_ctrl = nullptr;  // pinned
   int* h_done = nullptr;   // pinned + mapped
@@ -360,7 +361,7 @@ void upload_structures(sfx_problem* p) {
           }
         ptr.push_back(bp.n);
         lb.n_pf = (int)diag.size();
-        lb.pf_exclusive = a.batches.size() == 1 ? 1 : 0;
+        lb.pf_exclusive = (a.batches.size() == 1 && getenv("SFX_PF_STORES")) ? 1 : 0;  // measured: plain stores are ~4% slower than REDs here
         lb.pf_ptr = P.upload(ptr);
         lb.pf_slot = P.upload(order);
         lb.pf_diag = P.upload(diag);
@@ -570,7 +571,7 @@ void upload_structures(sfx_problem* p) {
     p->lvl_large.assign(f.n_levels, LargeLevel{});
     std::vector<LargeFront> lfs;
     std::vector<LargeTask> tasks;
-    std::vector<LargeJob> jobs;
+    std::vector<LargeJob> jobs, pre_jobs, damp_jobs;
     int64_t linv_off = 0, cnt_off = 0, flag_off = 0, contrib_off = 0;
     for (int l = 0; l < f.n_levels; ++l) {
       int* b = lvl_fronts.data() + f.level_ptr[l];
@@ -611,8 +612,11 @@ void upload_structures(sfx_problem* p) {
         const int li = (int)lfs.size();
         lfs.push_back(x);
         // assembly jobs
-        for (int c = f.f_copy_ptr[s]; c < f.f_copy_ptr[s + 1]; ++c) jobs.push_back(LargeJob{li, 0, c, 0, 0});
-        for (int r = 0; r < x.w; r += 1024) jobs.push_back(LargeJob{li, 2, 0, r, std::min(x.w, r + 1024)});
+        // system-matrix block copies and damping do not depend on the children: they run for all levels
+        // at once before level 0 (copies as plain stores: every entry has one source block); only the
+        // extend-add of the children stays between the levels
+        for (int c = f.f_copy_ptr[s]; c < f.f_copy_ptr[s + 1]; ++c) pre_jobs.push_back(LargeJob{li, 0, c, 0, 0});
+        for (int r = 0; r < x.w; r += 1024) damp_jobs.push_back(LargeJob{li, 2, 0, r, std::min(x.w, r + 1024)});
         for (int ci = f.f_child_ptr[s]; ci < f.f_child_ptr[s + 1]; ++ci) {
           const int c = f.f_child[ci];
           const int uc = f.f_u[c];
@@ -671,6 +675,11 @@ void upload_structures(sfx_problem* p) {
     p->n_large_fronts = (int)lfs.size();
     p->ld.lf = P.upload(lfs);
     p->ld.tasks = P.upload(tasks);
+    p->pre_j0 = (int)jobs.size();
+    jobs.insert(jobs.end(), pre_jobs.begin(), pre_jobs.end());
+    p->pre_j1 = p->damp_j0 = (int)jobs.size();
+    jobs.insert(jobs.end(), damp_jobs.begin(), damp_jobs.end());
+    p->damp_j1 = (int)jobs.size();
     p->ld.jobs = P.upload(jobs);
     p->n_counters = cnt_off;
     p->ld.counters = P.alloc<int>(cnt_off);
@@ -755,6 +764,8 @@ void enqueue_solve(sfx_problem* p, const std::function<void(int)>& mark) {
     CUDA_OK(cudaMemsetAsync(p->ld.counters, 0, sizeof(int) * p->n_counters, p->st));
     CUDA_OK(cudaMemsetAsync(p->ld.queue, 0, sizeof(int) * f.n_levels, p->st));
   }
+  launch_large_preassemble(p->st, p->d_ctrl, p->fd, p->ld, sys, p->sp, use_H, dv, p->pre_j0, p->pre_j1, p->damp_j0,
+                           p->damp_j1);
   for (int l = 0; l < f.n_levels; ++l) {
     if (p->lvl_small_cnt[l] > 0)
       launch_front_factor(p->st, p->d_ctrl, p->fd, sys, p->sp, use_H, dv, f.level_ptr[l], p->lvl_small_cnt[l],

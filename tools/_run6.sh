@@ -1,10 +1,7 @@
 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-for cfg in "A:SFX_KC=6"; do
-  name=${cfg%%:*}; envs=${cfg#*:}
-  env $envs python bench.py --cpu-baseline 0 --steps 10 --warmup 3 > gpurun_out/r_$name.json 2> gpurun_out/r_$name.err
-  python -c "
+python bench.py --cpu-baseline 0 --steps 10 --warmup 3 > gpurun_out/r_A.json 2> gpurun_out/r_A.err
+python -c "
 import json
-d=json.load(open('gpurun_out/r_$name.json')); print('$cfg', d['ms_per_step'], d['phases_ms_per_iteration'])
-" || tail -5 gpurun_out/r_$name.err
-done
-SFX_KC=6 python tools/trace_factor.py final 2>&1 | tail -40
+d=json.load(open('gpurun_out/r_A.json')); print(d['ms_per_step'], d['phases_ms_per_iteration'], d['e2e']['value'])
+" || tail -5 gpurun_out/r_A.err
+python tools/trace_factor.py final 2>&1 | tail -34

@@ -983,6 +983,24 @@ __device__ __forceinline__ void issue_tile(double* T, const double* __restrict__
   if (r < nr)
     for (int c = threadIdx.x >> 6; c < nc; c += kLargeThreads / 64) cp_async8(T + r + c * kSLd, G + r + (size_t)c * ldg);
 }
+// "LL" slots for values that cross CTAs inside one solve launch: a double travels as {lo, epoch, hi, epoch}
+// in one 16-byte store; each 8-byte half validates itself, so the reader needs no separate flag
+// round trip and the writer no fence.  epoch != 0 changes with every solve (slots start zeroed).
+__device__ __forceinline__ void ll_store(uint4* p, double v, unsigned epoch) {
+  const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(p), "r"((unsigned)b), "r"(epoch),
+               "r"((unsigned)(b >> 32)), "r"(epoch)
+               : "memory");
+}
+__device__ __forceinline__ double ll_load(const uint4* p, unsigned epoch) {
+  unsigned lo, f1, hi, f2;
+  for (;;) {
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(lo), "=r"(f1), "=r"(hi), "=r"(f2) : "l"(p) : "memory");
+    if (f1 == epoch && f2 == epoch) break;
+    __nanosleep(20);
+  }
+  return __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+}
 struct SolveItem {
   int kind, i, k;  // kind 0: L_kk^-1 tile of pivot tile k (i == k); 1: L tile (i, k)
 };
@@ -1070,7 +1088,7 @@ __device__ __forceinline__ void smem_gemv_t_part(const double* T, int nr, int nc
 
 __global__ void __launch_bounds__(kLargeThreads, 1)
     large_solve_fwd2_kernel(const Ctrl* __restrict__ ctrl, FrontDev fd, LargeDev ld, const double* __restrict__ rhs_static,
-                            StatePtrs sp, int use_state_rhs, int lf0, int P) {
+                            StatePtrs sp, int use_state_rhs, int lf0, int P, unsigned epoch) {
   extern __shared__ double smf[];  // stages | own: ceil(nt/P)*64 | y: 64 | red: 256
   if (ctrl->done) return;
   const LargeFront lf = ld.lf[lf0 + blockIdx.x / P];
@@ -1084,7 +1102,6 @@ __global__ void __launch_bounds__(kLargeThreads, 1)
   const double* rhs = use_state_rhs ? sp.rhs[ctrl->init_idx] : rhs_static;
   const double* L = fd.fronts + lf.off;
   const double* linv = ld.linv + lf.linv_off;
-  int* flag = ld.sflags + lf.flag_off;
   const int tid = threadIdx.x;
   // ---- start streaming the tiles of this CTA's sequence
   FwdIter prod, cons;
@@ -1127,11 +1144,8 @@ __global__ void __launch_bounds__(kLargeThreads, 1)
     const double* T = stages + (n % kSStages) * kT * kSLd;
     const int k = it.k;
     if (it.kind == 1 && k != cur_k) {
-      // y_k of another CTA: wait for its flag (tiles keep streaming in meanwhile)
-      if (tid == 0)
-        while (ld_acquire(flag + k) == 0) __nanosleep(20);
-      __syncthreads();
-      if (tid < kT) yk[tid] = tid < tile_size(lf, k) ? __ldcg(fd.ywork + fd.f_piv[s] + k * kT + tid) : 0.0;
+      // y_k of another CTA: every thread polls its own LL slot (tiles keep streaming in meanwhile)
+      if (tid < kT) yk[tid] = tid < tile_size(lf, k) ? ll_load(ld.ll_y + fd.f_piv[s] + k * kT + tid, epoch) : 0.0;
       cur_k = k;
     }
     cp_async_wait<kSStages - 1>();
@@ -1144,13 +1158,12 @@ __global__ void __launch_bounds__(kLargeThreads, 1)
       if (tid < kT) {
         const double v = red[tid] + red[64 + tid] + red[128 + tid] + red[192 + tid];
         yk[tid] = tid < nb ? v : 0.0;
-        if (tid < nb) fd.ywork[fd.f_piv[s] + k * kT + tid] = v;
+        if (tid < nb) {
+          fd.ywork[fd.f_piv[s] + k * kT + tid] = v;
+          ll_store(ld.ll_y + fd.f_piv[s] + k * kT + tid, v, epoch);
+        }
       }
       __syncthreads();
-      if (tid == 0) {
-        __threadfence();
-        st_release(flag + k, 1);
-      }
       cur_k = k;
     } else {
       const int i = it.i;
@@ -1171,7 +1184,7 @@ __global__ void __launch_bounds__(kLargeThreads, 1)
 }
 
 __global__ void __launch_bounds__(kLargeThreads, 1)
-    large_solve_bwd2_kernel(const Ctrl* __restrict__ ctrl, FrontDev fd, LargeDev ld, int lf0, int P) {
+    large_solve_bwd2_kernel(const Ctrl* __restrict__ ctrl, FrontDev fd, LargeDev ld, int lf0, int P, unsigned epoch) {
   extern __shared__ double smf[];  // stages | x: 64 | g: 64 | red: 256
   if (ctrl->done) return;
   const LargeFront lf = ld.lf[lf0 + blockIdx.x / P];
@@ -1183,8 +1196,7 @@ __global__ void __launch_bounds__(kLargeThreads, 1)
   double* red = g + kT;
   const double* L = fd.fronts + lf.off;
   const double* linv = ld.linv + lf.linv_off;
-  int* cntb = ld.sflags + lf.flag_off + wt;  // contributions received per pivot tile
-  double* contrib = ld.contrib + lf.contrib_off;
+  uint4* contrib = ld.ll_contrib + lf.contrib_off;  // LL slots [pivot tile][row tile][64]
   const int tid = threadIdx.x;
   const int32_t* rows = fd.f_rows + fd.f_rows_ptr[s];
   BwdIter prod, cons;
@@ -1206,16 +1218,12 @@ __global__ void __launch_bounds__(kLargeThreads, 1)
     const int i = it.i;
     const int ni = tile_size(lf, i), ri = tile_start(lf, i);
     if (it.kind == 0) {
-      // pivot tile i: all contributions of the rows below, then x_i = L_ii^-T (y_i - sum)
-      if (tid == 0)
-        while (ld_acquire(cntb + i) < nt - 1 - i) __nanosleep(20);
-      __syncthreads();
+      // pivot tile i: all contributions of the rows below (polled in their LL slots), then x_i = L_ii^-T (y_i - sum)
       {
         const int t = tid & 63, gq = tid >> 6;
         double v = 0.0;
         if (t < ni) {
-#pragma unroll 4
-          for (int r = i + 1 + gq; r < nt; r += 4) v += __ldcg(contrib + ((size_t)i * nt + r) * kT + t);
+          for (int r = i + 1 + gq; r < nt; r += 4) v += ll_load(contrib + ((size_t)i * nt + r) * kT + t, epoch);
         }
         red[gq * 64 + t] = v;
       }
@@ -1245,12 +1253,9 @@ __global__ void __launch_bounds__(kLargeThreads, 1)
       const int nk = tile_size(lf, k);
       smem_gemv_t_part(T, ni, nk, xi, red);
       __syncthreads();
-      if (tid < nk) contrib[((size_t)k * nt + i) * kT + tid] = red[tid] + red[64 + tid] + red[128 + tid] + red[192 + tid];
+      if (tid < nk)
+        ll_store(contrib + ((size_t)k * nt + i) * kT + tid, red[tid] + red[64 + tid] + red[128 + tid] + red[192 + tid], epoch);
       __syncthreads();
-      if (tid == 0) {
-        __threadfence();
-        atomicAdd(cntb + k, 1);
-      }
     }
     ++n;
   }
@@ -1263,7 +1268,8 @@ static bool solve_v1() {
 }
 
 void launch_large_solve_fwd(cudaStream_t st, const Ctrl* ctrl, const FrontDev& fd, const LargeDev& ld,
-                            const LargeLevel& lv, const double* rhs_static, StatePtrs sp, int use_state_rhs) {
+                            const LargeLevel& lv, const double* rhs_static, StatePtrs sp, int use_state_rhs,
+                            unsigned epoch) {
   if (lv.n_lf == 0) return;
   const int P = lv.solve_p;
   const size_t smem = (size_t)(((lv.max_nt + P - 1) / P) * kT + kT + 256) * sizeof(double);
@@ -1272,19 +1278,19 @@ void launch_large_solve_fwd(cudaStream_t st, const Ctrl* ctrl, const FrontDev& f
   } else {
     const size_t smem2 = smem + (size_t)kSStages * kT * kSLd * sizeof(double);
     large_solve_fwd2_kernel<<<lv.n_lf * P, kLargeThreads, smem2, st>>>(ctrl, fd, ld, rhs_static, sp, use_state_rhs,
-                                                                       lv.lf0, P);
+                                                                       lv.lf0, P, epoch);
   }
   ++g_launches;
 }
 void launch_large_solve_bwd(cudaStream_t st, const Ctrl* ctrl, const FrontDev& fd, const LargeDev& ld,
-                            const LargeLevel& lv) {
+                            const LargeLevel& lv, unsigned epoch) {
   if (lv.n_lf == 0) return;
   const int P = lv.solve_p;
   if (solve_v1()) {
     large_solve_bwd_kernel<<<lv.n_lf * P, 256, 3 * kT * sizeof(double), st>>>(ctrl, fd, ld, lv.lf0, P);
   } else {
     const size_t smem2 = (size_t)(kSStages * kT * kSLd + 2 * kT + 256) * sizeof(double);
-    large_solve_bwd2_kernel<<<lv.n_lf * P, kLargeThreads, smem2, st>>>(ctrl, fd, ld, lv.lf0, P);
+    large_solve_bwd2_kernel<<<lv.n_lf * P, kLargeThreads, smem2, st>>>(ctrl, fd, ld, lv.lf0, P, epoch);
   }
   ++g_launches;
 }

@@ -149,14 +149,17 @@ struct LargeDev {
   double* linv;
   double* binv;     // inverses of the eight 8x8 diagonal blocks of every L_kk (512 doubles per pivot tile): DIAG -> TRSMs
   int* sflags;      // solve flags / counters (zeroed before every solve)
-  double* contrib;  // backward-solve contribution slots
+  double* contrib;  // backward-solve contribution slots (v1 solves)
+  uint4* ll_y;       // v2 solves: LL slots of the forward solution (elimination order)
+  uint4* ll_contrib; // v2 solves: LL slots of the backward contributions (same indexing as contrib)
 };
 void launch_large_level(cudaStream_t st, Ctrl* ctrl, const FrontDev& fd, const LargeDev& ld, const LargeLevel& lv,
                         int level, const double* sys_static, StatePtrs sp, int use_state_H, const double* dvec);
 void launch_large_solve_fwd(cudaStream_t st, const Ctrl* ctrl, const FrontDev& fd, const LargeDev& ld,
-                            const LargeLevel& lv, const double* rhs_static, StatePtrs sp, int use_state_rhs);
+                            const LargeLevel& lv, const double* rhs_static, StatePtrs sp, int use_state_rhs,
+                            unsigned epoch);
 void launch_large_solve_bwd(cudaStream_t st, const Ctrl* ctrl, const FrontDev& fd, const LargeDev& ld,
-                            const LargeLevel& lv);
+                            const LargeLevel& lv, unsigned epoch);
 void launch_large_preassemble(cudaStream_t st, const Ctrl* ctrl, const FrontDev& fd, const LargeDev& ld,
                               const double* sys_static, StatePtrs sp, int use_state_H, const double* dvec, int pre_j0,
                               int pre_j1, int damp_j0, int damp_j1);

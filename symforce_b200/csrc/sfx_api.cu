@@ -122,6 +122,7 @@ struct sfx_problem {
   cudaStream_t st2 = nullptr;  // side stream: front zeroing overlaps damping + Schur
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int n_large_fronts = 0;
+  unsigned solve_epoch = 0;
   int pre_j0 = 0, pre_j1 = 0, damp_j0 = 0, damp_j1 = 0;  // assembly jobs run before level 0 (copies, damping)
   Ctrl* d_ctrl = nullptr;
   Ctrl* h_ctrl = nullptr;  // pinned
@@ -689,6 +690,10 @@ void upload_structures(sfx_problem* p) {
     p->n_sflags = flag_off;
     p->ld.sflags = P.alloc<int>(flag_off);
     p->ld.contrib = P.alloc<double>(contrib_off);
+    p->ld.ll_y = P.alloc<uint4>(f.n);
+    p->ld.ll_contrib = P.alloc<uint4>(contrib_off);
+    CUDA_OK(cudaMemset(p->ld.ll_y, 0, sizeof(uint4) * std::max<int64_t>(f.n, 1)));
+    CUDA_OK(cudaMemset(p->ld.ll_contrib, 0, sizeof(uint4) * std::max<int64_t>(contrib_off, 1)));
     CUDA_OK(configure_front_kernels(p->smem_cap_m, f.max_front));
     CUDA_OK(configure_large_kernels());
   }
@@ -774,17 +779,18 @@ void enqueue_solve(sfx_problem* p, const std::function<void(int)>& mark) {
   }
   mark(PH_FACTOR);
   if (p->n_sflags > 0) CUDA_OK(cudaMemsetAsync(p->ld.sflags, 0, sizeof(int) * p->n_sflags, p->st));
+  if (++p->solve_epoch == 0) p->solve_epoch = 1;  // LL slots of the v2 solves: 0 means "never written"
   const double* rhs_s = a.schur ? p->sd.rhs_red : nullptr;
   for (int l = 0; l < f.n_levels; ++l) {
     if (p->lvl_small_cnt[l] > 0)
       launch_front_solve_fwd(p->st, p->d_ctrl, p->fd, rhs_s, p->sp, use_H, f.level_ptr[l], p->lvl_small_cnt[l],
                              p->lvl_max_m[l] * 8);
-    launch_large_solve_fwd(p->st, p->d_ctrl, p->fd, p->ld, p->lvl_large[l], rhs_s, p->sp, use_H);
+    launch_large_solve_fwd(p->st, p->d_ctrl, p->fd, p->ld, p->lvl_large[l], rhs_s, p->sp, use_H, p->solve_epoch);
   }
   for (int l = f.n_levels - 1; l >= 0; --l) {
     if (p->lvl_small_cnt[l] > 0)
       launch_front_solve_bwd(p->st, p->d_ctrl, p->fd, f.level_ptr[l], p->lvl_small_cnt[l], p->lvl_max_m[l] * 8);
-    launch_large_solve_bwd(p->st, p->d_ctrl, p->fd, p->ld, p->lvl_large[l]);
+    launch_large_solve_bwd(p->st, p->d_ctrl, p->fd, p->ld, p->lvl_large[l], p->solve_epoch);
   }
   if (a.schur) {
     launch_unpermute(p->st, p->d_ctrl, p->fd, p->d_y, 1.0);

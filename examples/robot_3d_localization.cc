@@ -65,6 +65,20 @@ int main() {
     const auto p = values.At<sym::Pose3d>(Keys::WORLD_T_BODY.WithSuper(i));
     std::printf("Pose %d: t = [%.6f %.6f %.6f]\n", i, p.Data()[4], p.Data()[5], p.Data()[6]);
   }
+  // marginal covariances of every optimized key at the optimum (Optimizer::ComputeAllCovariances), and of the
+  // first pose alone with everything else eliminated... the other poses are 6-dim, so that split is not
+  // block diagonal: the full inverse is the path for this problem
+  {
+    const auto lin = optimizer.Linearize(values);
+    std::unordered_map<sym::Key, sym::MatrixX<double>, sym::KeyHash> covs;
+    optimizer.ComputeAllCovariances(lin, covs);
+    for (int i = 0; i < kNumPoses; i++) {
+      const auto& c = covs.at(Keys::WORLD_T_BODY.WithSuper(i));
+      double tr = 0;
+      for (int d = 0; d < c.rows(); d++) tr += c(d, d);
+      std::printf("Covariance trace %d: %.12e\n", i, tr);
+    }
+  }
   // same acceptance check as test/symforce_examples_robot_3d_localization_test.py:49-51
   return (stats.status == sym::optimization_status_t::SUCCESS && best_iter.new_error < 140) ? 0 : 1;
 }

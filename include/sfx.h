@@ -35,7 +35,8 @@ typedef enum {
   SFX_ERR_UNSUPPORTED = 3, /* factor kind / key type that has no device implementation */
   SFX_ERR_STRUCTURE = 4,   /* e.g. "Key ... is in the state vector but is not optimized by any
                               factor" (symforce/opt/linearizer.cc:277-284), non block-diagonal C */
-  SFX_ERR_NCCL = 5
+  SFX_ERR_NCCL = 5,
+  SFX_ERR_NUMERICAL = 6    /* Eigen::NumericalIssue of ComputeCovariances (optimizer.h:214-217) */
 } sfx_status;
 
 /* Storage/tangent semantics of an optimized key; subset of sym::type_t
@@ -232,6 +233,20 @@ sfx_status sfx_linearize(sfx_problem* p, double* residual, double* rhs, double* 
 /* stats.best_linearization (populate_best_linearization, internal/optimizer_utils.h:71-76) */
 sfx_status sfx_get_best_linearization(sfx_problem* p, double* residual, double* rhs,
                                       double* hessian_values);
+
+/* Optimizer::ComputeCovariances(linearization, keys, ..., c_is_block_diagonal = true)
+ * (symforce/opt/optimizer.tcc:177-199 -> internal/covariance_utils.h:124-147 ->
+ * SparseSchurSolver::Factorize + SInvInPlace, sparse_schur_solver.tcc:101-138,165-170) for a problem
+ * created with the Schur solver: `keys` are the keys in front of the eliminated landmarks,
+ * block_dim = their tangent dimension, covariance = (B - E (C + eps I)^-1 E^T)^-1, column-major
+ * block_dim x block_dim in keys_ order.  For a problem created with the Cholesky solver:
+ * Optimizer::ComputeFullCovariance / ComputeAllCovariances (optimizer.tcc:113-121, 201-206 ->
+ * LevenbergMarquardtSolver::ComputeCovariance, levenberg_marquardt_solver.tcc:345-356):
+ * block_dim = N, covariance = (H + eps I)^-1.  hessian_values: Linearization::hessian_lower values
+ * in the CSC order of sfx_get_hessian_pattern, or NULL for the best linearization of the last
+ * sfx_optimize.  Other blocks: SFX_ERR_UNSUPPORTED; a non-positive pivot: SFX_ERR_NUMERICAL. */
+sfx_status sfx_compute_covariance(sfx_problem* p, const double* hessian_values, int32_t block_dim,
+                                  double* covariance);
 
 /* Parity hook for one linear solve: DampHessian + Factorize + Solve of
  * LevenbergMarquardtSolver::Iterate (levenberg_marquardt_solver.tcc:195-218) at the

@@ -433,6 +433,45 @@ struct SparseLinearization {
   }
 };
 
+// Dynamic dense matrix (column-major) for covariance blocks: Eigen::MatrixXd when real Eigen is used
+#if defined(SFX_USE_EIGEN)
+template <typename Scalar>
+using MatrixX = Eigen::Matrix<Scalar, Eigen::Dynamic, Eigen::Dynamic>;
+using ComputationInfo = Eigen::ComputationInfo;
+constexpr ComputationInfo kSuccess = Eigen::Success;
+constexpr ComputationInfo kNumericalIssue = Eigen::NumericalIssue;
+#else
+template <typename Scalar>
+class MatrixX {
+ public:
+  MatrixX() = default;
+  MatrixX(int r, int c) : r_(r), c_(c), d_(static_cast<size_t>(r) * c, Scalar(0)) {}
+  void resize(int r, int c) {
+    r_ = r;
+    c_ = c;
+    d_.assign(static_cast<size_t>(r) * c, Scalar(0));
+  }
+  int rows() const { return r_; }
+  int cols() const { return c_; }
+  Scalar& operator()(int r, int c) { return d_[r + static_cast<size_t>(c) * r_]; }
+  const Scalar& operator()(int r, int c) const { return d_[r + static_cast<size_t>(c) * r_]; }
+  Scalar* data() { return d_.data(); }
+  const Scalar* data() const { return d_.data(); }
+  // covariance_block.block(offset, offset, dim, dim) of SplitCovariancesByKey (covariance_utils.h:180-181)
+  MatrixX block(int r0, int c0, int nr, int nc) const {
+    MatrixX m(nr, nc);
+    for (int c = 0; c < nc; ++c)
+      for (int r = 0; r < nr; ++r) m(r, c) = (*this)(r0 + r, c0 + c);
+    return m;
+  }
+
+ private:
+  int r_{0}, c_{0};
+  std::vector<Scalar> d_;
+};
+enum ComputationInfo { kSuccess = 0, kNumericalIssue = 1, kNoConvergence = 2, kInvalidInput = 3 };  // Eigen::ComputationInfo
+#endif
+
 struct OptimizationStats {
   std::vector<optimization_iteration_t> iterations;
   int32_t best_index{0};
@@ -644,6 +683,7 @@ class Optimizer {
   Optimizer& operator=(const Optimizer&) = delete;
   ~Optimizer() {
     if (handle_) sfx_problem_destroy(handle_);
+    if (cov_handle_) sfx_problem_destroy(cov_handle_);
   }
 
   // Optimize(values, num_iterations, populate_best_linearization) (optimizer.tcc:79-89)
@@ -697,6 +737,79 @@ class Optimizer {
     return lin;
   }
 
+  // ComputeAllCovariances (optimizer.tcc:113-121): (H + eps I)^-1 split by key
+  void ComputeAllCovariances(const SparseLinearization& linearization,
+                             std::unordered_map<Key, MatrixX<Scalar>, KeyHash>& covariances_by_key) {
+    MatrixX<Scalar> cov;
+    ComputeFullCovariance(linearization, cov);
+    SplitCovariancesByKey(cov, keys_, covariances_by_key);
+  }
+
+  // ComputeCovariances (optimizer.tcc:177-199): marginal covariance of `keys`, which must be the first
+  // keys of Keys() in order; every later key is eliminated with the Schur complement.  The GPU path has
+  // the block-diagonal-C solver only (c_is_block_diagonal = true: each eliminated key is a vector of
+  // dim <= 3 that shares no factor with another eliminated key).
+  ComputationInfo ComputeCovariances(const SparseLinearization& linearization, const std::vector<Key>& keys,
+                                     std::unordered_map<Key, MatrixX<Scalar>, KeyHash>& covariances_by_key,
+                                     const bool c_is_block_diagonal = true) {
+    SYM_ASSERT(IsInitialized());
+    SYM_ASSERT(!keys.empty() && keys.size() <= keys_.size());
+    for (size_t i = 0; i < keys.size(); ++i) SYM_ASSERT(keys[i] == keys_[i]);  // CheckKeyOrderMatchesLinearizerKeysStart
+    if (keys.size() == keys_.size()) {
+      ComputeAllCovariances(linearization, covariances_by_key);
+      return kSuccess;
+    }
+    if (!c_is_block_diagonal)
+      throw std::runtime_error("sym::Optimizer::ComputeCovariances: the GPU path only has the block-diagonal C solver");
+    int block_dim = 0;
+    for (size_t i = 0; i < keys.size(); ++i) block_dim += kentries_[i].tangent_dim;
+    const int n_elim = static_cast<int>(keys_.size() - keys.size());
+    sfx_problem* h = handle_;
+    if (!(solver_ == SFX_SOLVER_SCHUR && schur_keys_ == n_elim)) {
+      // the LM solve uses another split (or none): a sibling problem with the same structure and the
+      // requested Schur split, built once (the reference builds a SparseSchurSolver per call, covariance_utils.h:141-145)
+      if (cov_handle_ && cov_schur_keys_ != n_elim) {
+        sfx_problem_destroy(cov_handle_);
+        cov_handle_ = nullptr;
+      }
+      if (!cov_handle_) {
+        cov_handle_ = Create(SFX_SOLVER_SCHUR, n_elim);
+        cov_schur_keys_ = n_elim;
+      }
+      h = cov_handle_;
+    }
+    MatrixX<Scalar> cov(block_dim, block_dim);
+    const sfx_status st = sfx_compute_covariance(h, linearization.hessian_lower.values.data(), block_dim, cov.data());
+    if (st == SFX_ERR_NUMERICAL) return kNumericalIssue;
+    if (st != SFX_OK) throw std::runtime_error(std::string("sym::Optimizer<") + name_ + ">: " + sfx_last_error(h));
+    SplitCovariancesByKey(cov, keys, covariances_by_key);
+    return kSuccess;
+  }
+
+  // ComputeFullCovariance (optimizer.tcc:201-206 -> LevenbergMarquardtSolver::ComputeCovariance)
+  void ComputeFullCovariance(const SparseLinearization& linearization, MatrixX<Scalar>& covariance) {
+    SYM_ASSERT(IsInitialized());
+    int N = 0;
+    for (const auto& e : kentries_) N += e.tangent_dim;
+    sfx_problem* h = handle_;
+    if (solver_ != SFX_SOLVER_CHOLESKY) {
+      // the full inverse needs the factorization of the whole H: sibling problem without Schur elimination
+      if (cov_handle_ && cov_schur_keys_ != 0) {
+        sfx_problem_destroy(cov_handle_);
+        cov_handle_ = nullptr;
+      }
+      if (!cov_handle_) {
+        cov_handle_ = Create(SFX_SOLVER_CHOLESKY, 0);
+        cov_schur_keys_ = 0;
+      }
+      h = cov_handle_;
+    }
+    covariance.resize(N, N);
+    const sfx_status st = sfx_compute_covariance(h, linearization.hessian_lower.values.data(), N, covariance.data());
+    if (st != SFX_OK) throw std::runtime_error(std::string("sym::Optimizer<") + name_ + ">: " + sfx_last_error(h));
+  }
+
+  bool IsInitialized() const { return handle_ != nullptr; }
   const std::vector<Key>& Keys() const { return keys_; }
   const std::vector<Factor<Scalar>>& Factors() const { return factors_; }
   const optimizer_params_t& Params() const { return params_; }
@@ -754,10 +867,10 @@ class Optimizer {
       return;
     }
     std::unordered_map<Key, int, KeyHash> key_index;
-    std::vector<sfx_key_entry> kentries;
+    kentries_.clear();
     for (size_t i = 0; i < keys_.size(); ++i) {
       const index_entry_t& e = values.IndexEntryAt(keys_[i]);
-      kentries.push_back(sfx_key_entry{DeviceType(e.type), e.offset, e.storage_dim, e.tangent_dim});
+      kentries_.push_back(sfx_key_entry{DeviceType(e.type), e.offset, e.storage_dim, e.tangent_dim});
       key_index[keys_[i]] = static_cast<int>(i);
     }
     struct Batch {
@@ -782,34 +895,48 @@ class Optimizer {
       }
       b.fidx.push_back(static_cast<int32_t>(fi));
     }
-    std::vector<std::vector<int32_t>> flat_args, flat_opt;
-    std::vector<sfx_factor_batch> fb;
+    batch_kind_.clear();
+    flat_args_.clear();
+    flat_opt_.clear();
+    batch_fidx_.clear();
     for (auto& kv : batches) {
       Batch& b = kv.second;
       std::vector<int32_t> fa, fo;
       for (auto& v : b.args) fa.insert(fa.end(), v.begin(), v.end());
       for (auto& v : b.opt) fo.insert(fo.end(), v.begin(), v.end());
-      flat_args.push_back(std::move(fa));
-      flat_opt.push_back(std::move(fo));
+      batch_kind_.push_back(kv.first);
+      flat_args_.push_back(std::move(fa));
+      flat_opt_.push_back(std::move(fo));
+      batch_fidx_.push_back(std::move(b.fidx));
     }
-    size_t bi = 0;
-    for (auto& kv : batches) {
+    n_values_ = static_cast<int64_t>(values.Data().size());
+    int schur_keys = 0;
+    if (gpu_.solver == GpuSolverOptions::SCHUR) schur_keys = gpu_.schur_num_keys;
+    if (gpu_.solver == GpuSolverOptions::AUTO) schur_keys = AutoSchurKeys(values, key_index);
+    solver_ = schur_keys > 0 ? SFX_SOLVER_SCHUR : SFX_SOLVER_CHOLESKY;
+    schur_keys_ = schur_keys;
+    handle_ = Create(solver_, schur_keys_);
+  }
+  // Device problem for the indexed factor graph with the given linear solver (the LM problem, or the
+  // sibling ComputeCovariances needs when it eliminates a different set of keys).
+  sfx_problem* Create(int solver, int schur_keys) {
+    std::vector<sfx_factor_batch> fb;
+    for (size_t bi = 0; bi < batch_kind_.size(); ++bi) {
       sfx_factor_batch x{};
-      x.kind = kv.first;
-      x.n = static_cast<int32_t>(kv.second.fidx.size());
-      x.arg_offsets = flat_args[bi].data();
-      x.opt_keys = flat_opt[bi].data();
-      x.factor_index = kv.second.fidx.data();
+      x.kind = batch_kind_[bi];
+      x.n = static_cast<int32_t>(batch_fidx_[bi].size());
+      x.arg_offsets = flat_args_[bi].data();
+      x.opt_keys = flat_opt_[bi].data();
+      x.factor_index = batch_fidx_[bi].data();
       fb.push_back(x);
-      ++bi;
     }
     sfx_problem_desc d{};
     d.abi_version = SFX_ABI_VERSION;
     d.params = ToC(params_);
     d.epsilon = epsilon_;
-    d.n_values = static_cast<int64_t>(values.Data().size());
-    d.n_keys = static_cast<int32_t>(kentries.size());
-    d.keys = kentries.data();
+    d.n_values = n_values_;
+    d.n_keys = static_cast<int32_t>(kentries_.size());
+    d.keys = kentries_.data();
     d.n_batches = static_cast<int32_t>(fb.size());
     d.batches = fb.data();
     d.n_factors = static_cast<int32_t>(factors_.size());
@@ -818,16 +945,23 @@ class Optimizer {
     d.rank = 0;
     d.world = 1;
     d.comm = nullptr;
-    int schur_keys = 0;
-    if (gpu_.solver == GpuSolverOptions::SCHUR) schur_keys = gpu_.schur_num_keys;
-    if (gpu_.solver == GpuSolverOptions::AUTO) schur_keys = AutoSchurKeys(values, key_index);
-    d.solver = schur_keys > 0 ? SFX_SOLVER_SCHUR : SFX_SOLVER_CHOLESKY;
+    d.solver = solver;
     d.schur_num_keys = schur_keys;
     sfx_problem* h = nullptr;
     sfx_status s = sfx_problem_create(&d, &h);
     if (s != SFX_OK) throw std::runtime_error(std::string("sym::Optimizer<") + name_ + ">: " + sfx_last_error(nullptr));
-    handle_ = h;
-    n_values_ = d.n_values;
+    return h;
+  }
+  // internal::SplitCovariancesByKey (covariance_utils.h:172-191)
+  void SplitCovariancesByKey(const MatrixX<Scalar>& covariance_block, const std::vector<Key>& keys,
+                             std::unordered_map<Key, MatrixX<Scalar>, KeyHash>& covariances_by_key) const {
+    int offset = 0;
+    for (size_t i = 0; i < keys.size(); ++i) {
+      const int dim = kentries_[i].tangent_dim;
+      covariances_by_key[keys[i]] = covariance_block.block(offset, offset, dim, dim);
+      offset += dim;
+    }
+    SYM_ASSERT(covariances_by_key.size() == keys.size());
   }
   // Longest trailing run of keys (in keys_ order) that are vectors of dim <= 3 and never share a
   // factor with each other: eliminating them per block is exactly SparseSchurSolver's C.
@@ -873,6 +1007,13 @@ class Optimizer {
   GpuSolverOptions gpu_;
   sfx_problem* handle_{nullptr};
   int64_t n_values_{0};
+  // the indexed problem (kept so that ComputeCovariances can build a sibling with another Schur split)
+  std::vector<sfx_key_entry> kentries_;
+  std::vector<int> batch_kind_;
+  std::vector<std::vector<int32_t>> flat_args_, flat_opt_, batch_fidx_;
+  int solver_{SFX_SOLVER_CHOLESKY}, schur_keys_{0};
+  sfx_problem* cov_handle_{nullptr};
+  int cov_schur_keys_{-1};
 };
 using Optimizerd = Optimizer<double>;
 

@@ -18,7 +18,7 @@ EXPORTS = [
     "sfx_default_params", "sfx_problem_create", "sfx_problem_destroy", "sfx_last_error", "sfx_update_params",
     "sfx_set_values", "sfx_optimize", "sfx_get_best_values", "sfx_get_iterations", "sfx_get_dims",
     "sfx_get_hessian_pattern", "sfx_linearize", "sfx_get_best_linearization", "sfx_solve_step",
-    "sfx_get_ordering", "sfx_get_timings", "sfx_get_info", "sfx_comm_unique_id", "sfx_comm_create",
+    "sfx_compute_covariance", "sfx_get_ordering", "sfx_get_timings", "sfx_get_info", "sfx_comm_unique_id", "sfx_comm_create",
     "sfx_comm_destroy",
 ]
 
@@ -110,6 +110,18 @@ class SfxProblem(D._LibProblem):
         out = (C.c_int64 * len(INFO_NAMES))()
         self._check(self.lib.sfx_get_info(self.h, out, C.c_int32(len(INFO_NAMES))), "get_info")
         return dict(zip(INFO_NAMES, list(out)))
+
+    def compute_covariance(self, block_dim, hessian_values=None):
+        """Optimizer::ComputeCovariances / ComputeFullCovariance: dense block_dim x block_dim covariance in keys_
+        order, from the given Linearization::hessian_lower values (CSC order) or the best linearization."""
+        cov = np.empty((block_dim, block_dim), dtype=np.float64, order="F")
+        hv = None
+        if hessian_values is not None:
+            hessian_values = np.ascontiguousarray(hessian_values, dtype=np.float64)
+            hv = hessian_values.ctypes.data_as(C.POINTER(C.c_double))
+        self._check(self.lib.sfx_compute_covariance(self.h, hv, C.c_int32(block_dim),
+                                                    cov.ctypes.data_as(C.POINTER(C.c_double))), "compute_covariance")
+        return cov
 
     def close(self):
         if getattr(self, "h", None):

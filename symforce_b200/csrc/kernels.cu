@@ -2021,6 +2021,23 @@ void launch_export_csc(cudaStream_t st, const double* Hvals, const int32_t* csc_
   export_csc_kernel<<<grid, 256, 0, st>>>(Hvals, csc_src, nnz, out); ++g_launches;
 }
 // out[ref] = in[ref2int[ref]]
+__global__ void import_csc_kernel(const double* __restrict__ in, const int32_t* __restrict__ src, int64_t nnz,
+                                  double* __restrict__ Hv) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < nnz; i += stride) Hv[src[i]] = in[i];
+}
+void launch_import_csc(cudaStream_t st, const double* in, const int32_t* csc_src, int64_t nnz, double* Hvals) {
+  int grid = (int)((nnz + 255) / 256);
+  if (grid > 148 * 8) grid = 148 * 8;
+  if (grid < 1) grid = 1;
+  import_csc_kernel<<<grid, 256, 0, st>>>(in, csc_src, nnz, Hvals); ++g_launches;
+}
+__global__ void set_unit_kernel(double* v, int j, int prev) {
+  if (prev >= 0) v[prev] = 0.0;
+  v[j] = 1.0;
+}
+void launch_set_unit(cudaStream_t st, double* v, int j, int prev) { set_unit_kernel<<<1, 1, 0, st>>>(v, j, prev); ++g_launches; }
+
 __global__ void permute_vec_kernel(const double* __restrict__ in, const int32_t* __restrict__ ref2int, int N,
                                    double* __restrict__ out) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;

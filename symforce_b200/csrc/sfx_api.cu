@@ -730,18 +730,64 @@ void enqueue_linearize(sfx_problem* p, int mode) {
   launch_commit_error(p->st, p->d_ctrl, mode);
 }
 
+// zeroes the large fronts on the side stream (joined by enqueue_factorize); the previous solve, the
+// last reader of the fronts, precedes the fork event on the main stream
+void enqueue_zero_fork(sfx_problem* p) {
+  if (p->n_large_fronts == 0) return;
+  CUDA_OK(cudaEventRecord(p->ev_fork, p->st));
+  CUDA_OK(cudaStreamWaitEvent(p->st2, p->ev_fork, 0));
+  launch_large_zero(p->st2, p->d_ctrl, p->fd, p->ld, p->n_large_fronts);
+  CUDA_OK(cudaEventRecord(p->ev_join, p->st2));
+}
+
+// multifrontal Cholesky of the damped system: S (Schur problems; damping already inside) or
+// H[init_idx] + diag(d_dvec)
+void enqueue_factorize(sfx_problem* p) {
+  Analysis& a = p->a;
+  const FrontPlan& f = a.fp;
+  const double* sys = a.schur ? p->sd.S : nullptr;
+  const int use_H = a.schur ? 0 : 1;
+  const double* dv = a.schur ? nullptr : p->d_dvec;
+  if (p->n_large_fronts > 0) CUDA_OK(cudaStreamWaitEvent(p->st, p->ev_join, 0));
+  if (p->n_counters > 0) {
+    CUDA_OK(cudaMemsetAsync(p->ld.counters, 0, sizeof(int) * p->n_counters, p->st));
+    CUDA_OK(cudaMemsetAsync(p->ld.queue, 0, sizeof(int) * f.n_levels, p->st));
+  }
+  launch_large_preassemble(p->st, p->d_ctrl, p->fd, p->ld, sys, p->sp, use_H, dv, p->pre_j0, p->pre_j1, p->damp_j0,
+                           p->damp_j1);
+  for (int l = 0; l < f.n_levels; ++l) {
+    if (p->lvl_small_cnt[l] > 0)
+      launch_front_factor(p->st, p->d_ctrl, p->fd, sys, p->sp, use_H, dv, f.level_ptr[l], p->lvl_small_cnt[l],
+                          p->lvl_max_m[l]);
+    launch_large_level(p->st, p->d_ctrl, p->fd, p->ld, p->lvl_large[l], l, sys, p->sp, use_H, dv);
+  }
+}
+
+// forward + backward substitution with the current factor; rhs in system scalar order (rhs_static, or
+// the rhs of state block init_idx); the solution is left in fd.ywork (elimination order)
+void enqueue_tri_solves(sfx_problem* p, const double* rhs_static, int use_state_rhs) {
+  const FrontPlan& f = p->a.fp;
+  if (p->n_sflags > 0) CUDA_OK(cudaMemsetAsync(p->ld.sflags, 0, sizeof(int) * p->n_sflags, p->st));
+  if (++p->solve_epoch == 0) p->solve_epoch = 1;  // LL slots of the v2 solves: 0 means "never written"
+  for (int l = 0; l < f.n_levels; ++l) {
+    if (p->lvl_small_cnt[l] > 0)
+      launch_front_solve_fwd(p->st, p->d_ctrl, p->fd, rhs_static, p->sp, use_state_rhs, f.level_ptr[l],
+                             p->lvl_small_cnt[l], p->lvl_max_m[l] * 8);
+    launch_large_solve_fwd(p->st, p->d_ctrl, p->fd, p->ld, p->lvl_large[l], rhs_static, p->sp, use_state_rhs,
+                           p->solve_epoch);
+  }
+  for (int l = f.n_levels - 1; l >= 0; --l) {
+    if (p->lvl_small_cnt[l] > 0)
+      launch_front_solve_bwd(p->st, p->d_ctrl, p->fd, f.level_ptr[l], p->lvl_small_cnt[l], p->lvl_max_m[l] * 8);
+    launch_large_solve_bwd(p->st, p->d_ctrl, p->fd, p->ld, p->lvl_large[l], p->solve_epoch);
+  }
+}
+
 // damping + [Schur] + factorize + solve -> d_upd (internal order) = -H_damped^-1 rhs
 void enqueue_solve(sfx_problem* p, const std::function<void(int)>& mark) {
   Analysis& a = p->a;
   const bool factors_here = !(a.world > 1 && a.rank != 0);
-  if (factors_here && p->n_large_fronts > 0) {
-    // the large fronts are zeroed on a side stream while damping and the Schur complement run (the
-    // previous solve, the last reader of the fronts, precedes the fork event on the main stream)
-    CUDA_OK(cudaEventRecord(p->ev_fork, p->st));
-    CUDA_OK(cudaStreamWaitEvent(p->st2, p->ev_fork, 0));
-    launch_large_zero(p->st2, p->d_ctrl, p->fd, p->ld, p->n_large_fronts);
-    CUDA_OK(cudaEventRecord(p->ev_join, p->st2));
-  }
+  if (factors_here) enqueue_zero_fork(p);  // overlaps damping and the Schur complement
   launch_damping(p->st, p->d_ctrl, p->sp, p->d_diag_pos, a.N, p->d_dvec, p->d_maxdiag);
   if (a.schur) launch_schur(p->st, p->d_ctrl, p->sp, p->sd, p->d_dvec);
   const bool mg = a.world > 1;
@@ -761,37 +807,10 @@ void enqueue_solve(sfx_problem* p, const std::function<void(int)>& mark) {
     mark(PH_SOLVE);
     return;
   }
-  const double* sys = a.schur ? p->sd.S : nullptr;
-  const int use_H = a.schur ? 0 : 1;
-  const double* dv = a.schur ? nullptr : p->d_dvec;
-  if (p->n_large_fronts > 0) CUDA_OK(cudaStreamWaitEvent(p->st, p->ev_join, 0));
-  if (p->n_counters > 0) {
-    CUDA_OK(cudaMemsetAsync(p->ld.counters, 0, sizeof(int) * p->n_counters, p->st));
-    CUDA_OK(cudaMemsetAsync(p->ld.queue, 0, sizeof(int) * f.n_levels, p->st));
-  }
-  launch_large_preassemble(p->st, p->d_ctrl, p->fd, p->ld, sys, p->sp, use_H, dv, p->pre_j0, p->pre_j1, p->damp_j0,
-                           p->damp_j1);
-  for (int l = 0; l < f.n_levels; ++l) {
-    if (p->lvl_small_cnt[l] > 0)
-      launch_front_factor(p->st, p->d_ctrl, p->fd, sys, p->sp, use_H, dv, f.level_ptr[l], p->lvl_small_cnt[l],
-                          p->lvl_max_m[l]);
-    launch_large_level(p->st, p->d_ctrl, p->fd, p->ld, p->lvl_large[l], l, sys, p->sp, use_H, dv);
-  }
+  (void)f;
+  enqueue_factorize(p);
   mark(PH_FACTOR);
-  if (p->n_sflags > 0) CUDA_OK(cudaMemsetAsync(p->ld.sflags, 0, sizeof(int) * p->n_sflags, p->st));
-  if (++p->solve_epoch == 0) p->solve_epoch = 1;  // LL slots of the v2 solves: 0 means "never written"
-  const double* rhs_s = a.schur ? p->sd.rhs_red : nullptr;
-  for (int l = 0; l < f.n_levels; ++l) {
-    if (p->lvl_small_cnt[l] > 0)
-      launch_front_solve_fwd(p->st, p->d_ctrl, p->fd, rhs_s, p->sp, use_H, f.level_ptr[l], p->lvl_small_cnt[l],
-                             p->lvl_max_m[l] * 8);
-    launch_large_solve_fwd(p->st, p->d_ctrl, p->fd, p->ld, p->lvl_large[l], rhs_s, p->sp, use_H, p->solve_epoch);
-  }
-  for (int l = f.n_levels - 1; l >= 0; --l) {
-    if (p->lvl_small_cnt[l] > 0)
-      launch_front_solve_bwd(p->st, p->d_ctrl, p->fd, f.level_ptr[l], p->lvl_small_cnt[l], p->lvl_max_m[l] * 8);
-    launch_large_solve_bwd(p->st, p->d_ctrl, p->fd, p->ld, p->lvl_large[l], p->solve_epoch);
-  }
+  enqueue_tri_solves(p, a.schur ? p->sd.rhs_red : nullptr, a.schur ? 0 : 1);
   if (a.schur) {
     launch_unpermute(p->st, p->d_ctrl, p->fd, p->d_y, 1.0);
     if (mg) NCCL_OK(nccl().Broadcast(p->d_y, p->d_y, (size_t)a.sp.reduced_dim, ncclDouble, 0, p->comm->comm, p->st));
@@ -1107,6 +1126,82 @@ sfx_status sfx_get_best_linearization(sfx_problem* p, double* residual, double* 
             "SYM_ASSERT: state_.BestIsValid() && Best().GetLinearization().IsInitialized()");
   CUDA_OK(cudaSetDevice(p->device));
   export_linearization(p, c.best_idx, residual, rhs, hessian_values);
+  SFX_API_END(p)
+}
+
+sfx_status sfx_compute_covariance(sfx_problem* p, const double* hessian_values, int32_t block_dim,
+                                  double* covariance) {
+  SFX_API_BEGIN
+  SFX_CHECK(p && covariance, SFX_ERR_INVALID_ARG, "null argument");
+  Analysis& a = p->a;
+  SFX_CHECK(a.world == 1, SFX_ERR_UNSUPPORTED, "covariances are computed on one GPU");
+  const int sys_dim = a.schur ? a.sp.reduced_dim : a.N;
+  SFX_CHECK(block_dim == sys_dim, SFX_ERR_UNSUPPORTED,
+            "covariance block must be the block the linear solver factors: all keys before the Schur-eliminated "
+            "landmarks, or every key of a problem solved without Schur elimination");
+  CUDA_OK(cudaSetDevice(p->device));
+  Ctrl* c = p->h_ctrl;
+  int blk;
+  if (hessian_values != nullptr) {
+    // a caller-provided Linearization::hessian_lower: scattered into a state block that is not Best
+    blk = c->best_valid ? (c->best_idx + 1) % 3 : 0;
+    ensure_csc(p);
+    CUDA_OK(cudaMemcpyAsync(p->d_export, hessian_values, sizeof(double) * a.nnz, cudaMemcpyHostToDevice, p->st));
+    CUDA_OK(cudaMemsetAsync(p->sp.H[blk], 0, sizeof(double) * a.H.n_values, p->st));
+    launch_import_csc(p->st, p->d_export, p->d_csc_src, a.nnz, p->sp.H[blk]);
+    c->lin_valid[blk] = 0;
+  } else {
+    SFX_CHECK(c->best_valid && c->lin_valid[c->best_idx], SFX_ERR_INVALID_ARG,
+              "SYM_ASSERT: state_.BestIsValid() && Best().GetLinearization().IsInitialized()");
+    blk = c->best_idx;
+  }
+  // run the solver kernels on that block: they select it through ctrl->init_idx and stop on ctrl->done
+  const int saved_init = c->init_idx, saved_done = c->done, saved_fail = c->chol_fail;
+  c->init_idx = blk;
+  c->done = 0;
+  c->chol_fail = 0;
+  CUDA_OK(cudaMemcpyAsync(p->d_ctrl, c, offsetof(Ctrl, iters), cudaMemcpyHostToDevice, p->st));
+  // damping of internal/covariance_utils.h:131-135 (epsilon on C only) resp.
+  // LevenbergMarquardtSolver::ComputeCovariance (levenberg_marquardt_solver.tcc:345-356: epsilon everywhere)
+  {
+    std::vector<double> dv(a.N, p->epsilon);
+    if (a.schur) std::fill(dv.begin(), dv.begin() + sys_dim, 0.0);
+    CUDA_OK(cudaMemcpyAsync(p->d_dvec, dv.data(), sizeof(double) * a.N, cudaMemcpyHostToDevice, p->st));
+    CUDA_OK(cudaStreamSynchronize(p->st));
+  }
+  enqueue_zero_fork(p);
+  if (a.schur) launch_schur(p->st, p->d_ctrl, p->sp, p->sd, p->d_dvec);
+  enqueue_factorize(p);
+  // S^-1 = solves against the identity (SparseSchurSolver::SInvInPlace, sparse_schur_solver.tcc:165-170), column by column
+  double *d_unit = nullptr, *d_cov = nullptr;
+  CUDA_OK(cudaMalloc(&d_unit, sizeof(double) * sys_dim));
+  if (cudaMalloc(&d_cov, sizeof(double) * (size_t)sys_dim * sys_dim) != cudaSuccess) {
+    cudaFree(d_unit);
+    throw Error(SFX_ERR_CUDA, "out of device memory for the covariance block");
+  }
+  CUDA_OK(cudaMemsetAsync(d_unit, 0, sizeof(double) * sys_dim, p->st));
+  for (int j = 0; j < sys_dim; ++j) {
+    launch_set_unit(p->st, d_unit, j, j > 0 ? j - 1 : -1);
+    enqueue_tri_solves(p, d_unit, 0);
+    launch_unpermute(p->st, p->d_ctrl, p->fd, d_cov + (size_t)j * sys_dim, 1.0);
+  }
+  std::vector<double> cov_int((size_t)sys_dim * sys_dim);
+  CUDA_OK(cudaMemcpyAsync(cov_int.data(), d_cov, sizeof(double) * cov_int.size(), cudaMemcpyDeviceToHost, p->st));
+  int fail = 0;
+  CUDA_OK(cudaMemcpyAsync(&fail, (char*)p->d_ctrl + offsetof(Ctrl, chol_fail), sizeof(int), cudaMemcpyDeviceToHost, p->st));
+  // restore the control block
+  c->init_idx = saved_init;
+  c->done = saved_done;
+  c->chol_fail = saved_fail;
+  CUDA_OK(cudaMemcpyAsync(p->d_ctrl, c, offsetof(Ctrl, iters), cudaMemcpyHostToDevice, p->st));
+  CUDA_OK(cudaStreamSynchronize(p->st));
+  cudaFree(d_unit);
+  cudaFree(d_cov);
+  SFX_CHECK(!fail, SFX_ERR_NUMERICAL, "the matrix to invert is not positive definite");
+  // internal tangent order -> keys_ order
+  for (int cj = 0; cj < sys_dim; ++cj)
+    for (int ri = 0; ri < sys_dim; ++ri)
+      covariance[ri + (size_t)cj * sys_dim] = cov_int[a.ref2int[ri] + (size_t)a.ref2int[cj] * sys_dim];
   SFX_API_END(p)
 }
 

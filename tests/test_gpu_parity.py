@@ -194,7 +194,17 @@ def test_cpp_examples_through_sym_layer():
     g = capi.SfxProblem(P.robot_3d_localization())
     st = g.optimize()
     assert final == pytest.approx(g.iterations()[st.best_index].new_error, rel=1e-9)
+    # Optimizer::ComputeAllCovariances through the sym:: layer == the C ABI on the best linearization
+    traces = [float(x) for x in re.findall(r"Covariance trace \d+: ([0-9.eE+-]+)", out.stdout)]
+    N, _, _ = g.dims()
+    cov = g.compute_covariance(N)
+    want = [float(np.trace(cov[6 * i:6 * i + 6, 6 * i:6 * i + 6])) for i in range(N // 6)]
+    assert len(traces) == len(want) and np.allclose(traces, want, rtol=1e-6)
     g.close()
+    # ComputeCovariances on every code path (own Schur solver, sibling problem, full inverse) agree
+    out = subprocess.run([os.path.join(root, "examples", "_build", "covariance_check")], capture_output=True, text=True,
+                         timeout=120)
+    assert out.returncode == 0 and "COVARIANCE_OK" in out.stdout, out.stdout + out.stderr
     out = subprocess.run([os.path.join(root, "examples", "_build", "bundle_adjustment_in_the_large"), "--synthetic",
                           "12", "400", "5"], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stdout + out.stderr

@@ -213,6 +213,12 @@ sfx_status sfx_optimize(sfx_problem* p, int32_t num_iterations, sfx_stats* stats
 /* values = nonlinear_solver.GetBestValues() (internal/optimizer_utils.h:69) */
 sfx_status sfx_get_best_values(sfx_problem* p, double* values, int64_t n);
 
+/* Values::Update(index, other) (symforce/opt/values.cc:269-275) with other = GetBestValues(): overwrites only the
+ * storage of the optimized keys in `values`, which must be the buffer last given to sfx_set_values (every other
+ * entry of the best values is identical to it by construction: only optimized keys are retracted).  Moves
+ * 8 * (optimized storage) bytes over PCIe instead of the whole buffer; *bytes_copied (may be NULL) reports it. */
+sfx_status sfx_update_best_values(sfx_problem* p, double* values, int64_t n, int64_t* bytes_copied);
+
 /* stats.iterations (symforce/opt/optimization_stats.h:30) */
 sfx_status sfx_get_iterations(sfx_problem* p, sfx_iteration* buf, int32_t capacity, int32_t* n);
 

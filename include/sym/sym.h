@@ -716,7 +716,8 @@ class Optimizer {
     stats.status = static_cast<optimization_status_t>(st.status);
     stats.failure_reason = st.failure_reason;
     // values = nonlinear_solver.GetBestValues() (internal/optimizer_utils.h:69)
-    Check(sfx_get_best_values(handle_, values.DataPointer(), static_cast<int64_t>(values.Data().size())));
+    // (only the optimized keys changed: Values::Update semantics move a fraction of the buffer over PCIe)
+    Check(sfx_update_best_values(handle_, values.DataPointer(), static_cast<int64_t>(values.Data().size()), nullptr));
     if (populate_best_linearization) {
       SparseLinearization lin;
       FillPattern(lin);

@@ -16,7 +16,7 @@ LIB_PATH = os.environ.get("SFX_LIB") or os.path.join(_HERE, "lib", "libsfx.so") 
 
 EXPORTS = [
     "sfx_default_params", "sfx_problem_create", "sfx_problem_destroy", "sfx_last_error", "sfx_update_params",
-    "sfx_set_values", "sfx_optimize", "sfx_get_best_values", "sfx_get_iterations", "sfx_get_dims",
+    "sfx_set_values", "sfx_optimize", "sfx_get_best_values", "sfx_update_best_values", "sfx_get_iterations", "sfx_get_dims",
     "sfx_get_hessian_pattern", "sfx_linearize", "sfx_get_best_linearization", "sfx_solve_step",
     "sfx_compute_covariance", "sfx_get_ordering", "sfx_get_timings", "sfx_get_info", "sfx_comm_unique_id", "sfx_comm_create",
     "sfx_comm_destroy",
@@ -110,6 +110,15 @@ class SfxProblem(D._LibProblem):
         out = (C.c_int64 * len(INFO_NAMES))()
         self._check(self.lib.sfx_get_info(self.h, out, C.c_int32(len(INFO_NAMES))), "get_info")
         return dict(zip(INFO_NAMES, list(out)))
+
+    def update_best_values(self, values):
+        """Values::Update with the best values: overwrites the optimized keys' storage in `values` (the buffer that was
+        given to set_values); returns the number of bytes moved device -> host."""
+        assert values.dtype == np.float64 and values.flags["C_CONTIGUOUS"] and values.shape[0] == self.n_values
+        nb = C.c_int64(0)
+        self._check(self.lib.sfx_update_best_values(self.h, values.ctypes.data_as(C.POINTER(C.c_double)),
+                                                    C.c_int64(values.shape[0]), C.byref(nb)), "update_best_values")
+        return nb.value
 
     def compute_covariance(self, block_dim, hessian_values=None):
         """Optimizer::ComputeCovariances / ComputeFullCovariance: dense block_dim x block_dim covariance in keys_

@@ -123,6 +123,7 @@ struct sfx_problem {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int n_large_fronts = 0;
   unsigned solve_epoch = 0;
+  std::vector<std::pair<int64_t, int64_t>> opt_ranges;  // merged storage ranges of the optimized keys
   int pre_j0 = 0, pre_j1 = 0, damp_j0 = 0, damp_j1 = 0;  // assembly jobs run before level 0 (copies, damping)
   Ctrl* d_ctrl = nullptr;
   Ctrl* h_ctrl = nullptr;  // pinned
@@ -300,6 +301,19 @@ void verify_task_list(const LargeFront& x, const std::vector<LargeTask>& tl) {
 void upload_structures(sfx_problem* p) {
   Analysis& a = p->a;
   DevPool& P = p->pool;
+  {
+    // storage ranges of the optimized keys, merged (BAL: cameras and points are a handful of runs); used by
+    // sfx_update_best_values
+    std::vector<std::pair<int64_t, int64_t>> r;
+    for (const auto& k : a.keys) r.emplace_back((int64_t)k.voff, (int64_t)k.voff + k.sdim);
+    std::sort(r.begin(), r.end());
+    for (const auto& x : r) {
+      if (!p->opt_ranges.empty() && x.first <= p->opt_ranges.back().second)
+        p->opt_ranges.back().second = std::max(p->opt_ranges.back().second, x.second);
+      else
+        p->opt_ranges.push_back(x);
+    }
+  }
   // keys
   std::vector<int32_t> kt, kv, ks, kd, ki;
   for (auto& k : a.keys) {
@@ -1074,6 +1088,30 @@ sfx_status sfx_get_best_values(sfx_problem* p, double* values, int64_t n) {
   }
   CUDA_OK(cudaMemcpyAsync(values, src, sizeof(double) * n, cudaMemcpyDeviceToHost, p->st));
   CUDA_OK(cudaStreamSynchronize(p->st));
+  SFX_API_END(p)
+}
+
+sfx_status sfx_update_best_values(sfx_problem* p, double* values, int64_t n, int64_t* bytes_copied) {
+  SFX_API_BEGIN
+  SFX_CHECK(p && values, SFX_ERR_INVALID_ARG, "null argument");
+  SFX_CHECK(n == p->a.n_values, SFX_ERR_INVALID_ARG, "values length mismatch");
+  SFX_CHECK(p->h_ctrl->best_valid, SFX_ERR_INVALID_ARG, "SYM_ASSERT: state_.BestIsValid()");
+  CUDA_OK(cudaSetDevice(p->device));
+  Analysis& a = p->a;
+  if (a.world > 1 || p->opt_ranges.size() > 256) {
+    // scattered keys (or sharded landmarks): the full buffer is cheaper than thousands of small copies
+    if (bytes_copied) *bytes_copied = (int64_t)sizeof(double) * n;
+    return sfx_get_best_values(p, values, n);
+  }
+  const double* src = p->sp.values[p->h_ctrl->best_idx];
+  int64_t total = 0;
+  for (const auto& x : p->opt_ranges) {
+    CUDA_OK(cudaMemcpyAsync(values + x.first, src + x.first, sizeof(double) * (x.second - x.first),
+                            cudaMemcpyDeviceToHost, p->st));
+    total += (int64_t)sizeof(double) * (x.second - x.first);
+  }
+  CUDA_OK(cudaStreamSynchronize(p->st));
+  if (bytes_copied) *bytes_copied = total;
   SFX_API_END(p)
 }
 

@@ -140,6 +140,21 @@ def test_reference_kats_on_gpu(solved):
     assert its[st.best_index].new_error < 140
 
 
+@pytest.mark.parametrize("name", ["robot3d", "bal_small_schur", "frozen_keys", "ba_example"])
+def test_update_best_values_equals_full_copy(name):
+    """sfx_update_best_values (Values::Update semantics: only the optimized keys travel back) leaves the caller's
+    buffer identical to the full GetBestValues() copy."""
+    prob = PROBLEMS[name]()
+    g = capi.SfxProblem(prob)
+    g.optimize()
+    full = g.best_values()
+    buf = np.array(prob.values, dtype=np.float64, copy=True)
+    nbytes = g.update_best_values(buf)
+    assert np.array_equal(buf, full)
+    assert 0 < nbytes <= full.nbytes
+    g.close()
+
+
 def test_status_codes(solved):
     prob = P.pose_smoothing(_params(iterations=2))
     g = capi.SfxProblem(prob)

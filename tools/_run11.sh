@@ -1,0 +1,4 @@
+python -m pytest tests -m gpu -x -q 2>&1 | tail -4
+python bench.py --cpu-baseline 0 --steps 10 --warmup 3 | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print(d['ms_per_step'], d['phases_ms_per_iteration'], d['e2e'])"

@@ -276,6 +276,9 @@ __device__ __forceinline__ int value_of_lane(int lane) {
 }
 
 constexpr int kBalThreads = 128;
+// per-observation point contribution: 6 + 3 doubles (padding to 10 for aligned 16-byte gather loads was measured:
+// slower, 0.84 vs 0.81 ms per linearization at Final-shape)
+constexpr int kPbufStride = 9;
 #ifndef SFX_BAL_MINB
 #define SFX_BAL_MINB 5  // 96 registers, 68 B of spills: 0.83 -> 0.80 ms at final-shape (6: 80 registers, slower)
 #endif
@@ -404,14 +407,15 @@ __global__ void __launch_bounds__(kBalThreads, SFX_BAL_MINB) linearize_bal_kerne
       for (int c = 0; c < 3; ++c)
 #pragma unroll
         for (int r = c; r < 3; ++r)
-          st[lane * 9 + q++] = J[2 * (9 + r)] * J[2 * (9 + c)] + J[2 * (9 + r) + 1] * J[2 * (9 + c) + 1];
+          st[lane * kPbufStride + q++] = J[2 * (9 + r)] * J[2 * (9 + c)] + J[2 * (9 + r) + 1] * J[2 * (9 + c) + 1];
 #pragma unroll
-      for (int r = 0; r < 3; ++r) st[lane * 9 + 6 + r] = J[2 * (9 + r)] * res[0] + J[2 * (9 + r) + 1] * res[1];
+      for (int r = 0; r < 3; ++r)
+        st[lane * kPbufStride + 6 + r] = J[2 * (9 + r)] * res[0] + J[2 * (9 + r) + 1] * res[1];
     }
     __syncwarp();
-    double* dst = b.pbuf + (size_t)(blockIdx.x * kBalThreads + warp * 32) * 9;
+    double* dst = b.pbuf + (size_t)(blockIdx.x * kBalThreads + warp * 32) * kPbufStride;
 #pragma unroll
-    for (int i = 0; i < 9; ++i) dst[i * 32 + lane] = st[i * 32 + lane];
+    for (int i = 0; i < kPbufStride; ++i) dst[i * 32 + lane] = st[i * 32 + lane];
     __syncwarp();
   } else if (valid && !(SKIP & 2)) {
 #pragma unroll
@@ -472,7 +476,7 @@ __global__ void __launch_bounds__(128) bal_point_finalize_kernel(const Ctrl* __r
   for (int i = 0; i < 9; ++i) a[i] = 0.0;
   const int q1 = __ldg(b.pf_ptr + pt + 1);
   for (int q = __ldg(b.pf_ptr + pt); q < q1; ++q) {
-    const double* __restrict__ src = b.pbuf + (size_t)__ldg(b.pf_slot + q) * 9;
+    const double* __restrict__ src = b.pbuf + (size_t)__ldg(b.pf_slot + q) * kPbufStride;
 #pragma unroll
     for (int i = 0; i < 9; ++i) a[i] += src[i];
   }
@@ -1453,24 +1457,54 @@ __global__ void __launch_bounds__(kS9Warps * 32, 4) schur_s9_kernel(const Ctrl* 
 // s_l += E y_I per E block (camera-major), then z_l = t_l - C^-1 s_l per landmark
 __global__ void __launch_bounds__(kGThreads) schur_back_accum_kernel(const Ctrl* __restrict__ ctrl, StatePtrs sp,
                                                                      SchurDev sd, const double* __restrict__ y) {
+  __shared__ double stage[kGThreads / 32][32 * 27];
   if (ctrl->done) return;
   const int q = blockIdx.x * kGThreads + threadIdx.x;
-  if (q >= sd.n_entries) return;
+  const bool valid = q < sd.n_entries;
+  const int qc = valid ? q : sd.n_entries - 1;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const double* __restrict__ H = sp.H[ctrl->init_idx];
-  const int I = sd.r_node[q];
-  const int l = sd.r_lm[q];
-  const int dI = sd.node_dim[I];
-  const double* e = H + sd.r_eoff[q];
+  const int I = __ldg(sd.r_node + qc);
+  const int l = __ldg(sd.r_lm + qc);
+  const int dI = __ldg(sd.node_dim + I);
+  const int eoff = __ldg(sd.r_eoff + qc);
   const double* yi = y + sd.node_toff[I];
   double s0 = 0, s1 = 0, s2 = 0;
+  // a warp's 32 blocks are one contiguous run in camera-major order: read them coalesced through shared memory
+  const int I0 = __shfl_sync(0xffffffffu, I, 0);
+  const int eoff0 = __shfl_sync(0xffffffffu, eoff, 0);
+  const bool staged = __all_sync(0xffffffffu, valid && I == I0 && dI == 9 && eoff == eoff0 + 27 * lane);
+  if (staged) {
+    double* st = stage[warp];
+    const double* src = H + eoff0;
+    {
+      double t[27];
 #pragma unroll
-  for (int c = 0; c < 16; ++c)
-    if (c < dI) {
+      for (int i = 0; i < 27; ++i) t[i] = src[i * 32 + lane];
+#pragma unroll
+      for (int i = 0; i < 27; ++i) st[i * 32 + lane] = t[i];
+    }
+    __syncwarp();
+    const double* e = st + lane * 27;
+#pragma unroll
+    for (int c = 0; c < 9; ++c) {
       const double yc = yi[c];
       s0 += e[3 * c] * yc;
       s1 += e[3 * c + 1] * yc;
       s2 += e[3 * c + 2] * yc;
     }
+  } else if (valid) {
+    const double* e = H + eoff;
+#pragma unroll
+    for (int c = 0; c < 16; ++c)
+      if (c < dI) {
+        const double yc = yi[c];
+        s0 += e[3 * c] * yc;
+        s1 += e[3 * c + 1] * yc;
+        s2 += e[3 * c + 2] * yc;
+      }
+  }
+  if (!valid) return;
   atomicAdd(sd.sl + (size_t)l * 3, s0);
   atomicAdd(sd.sl + (size_t)l * 3 + 1, s1);
   atomicAdd(sd.sl + (size_t)l * 3 + 2, s2);

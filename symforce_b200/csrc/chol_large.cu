@@ -1262,10 +1262,7 @@ __global__ void __launch_bounds__(kLargeThreads, 1)
   cp_async_wait<0>();
 }
 
-static bool solve_v1() {
-  static const bool v = getenv("SFX_SOLVE_V1") != nullptr;
-  return v;
-}
+static bool solve_v1() { return getenv("SFX_SOLVE_V1") != nullptr; }  // read per launch: tests toggle it
 
 void launch_large_solve_fwd(cudaStream_t st, const Ctrl* ctrl, const FrontDev& fd, const LargeDev& ld,
                             const LargeLevel& lv, const double* rhs_static, StatePtrs sp, int use_state_rhs,

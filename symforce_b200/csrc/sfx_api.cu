@@ -653,7 +653,7 @@ void upload_structures(sfx_problem* p) {
       // the window of tasks in flight always spans all fronts (one front's critical path hides behind
       // the others' trailing updates)
       {
-        static const int Kc = getenv("SFX_KC") ? std::max(1, atoi(getenv("SFX_KC"))) : 6;
+        const int Kc = getenv("SFX_KC") ? std::max(1, atoi(getenv("SFX_KC"))) : 6;
         std::vector<std::vector<LargeTask>> per(lv.n_lf);
         for (int q = 0; q < lv.n_lf; ++q) {
           // (shorter panels for narrow fronts were measured: slightly slower, 4.87 vs 4.82 ms at Final-shape)

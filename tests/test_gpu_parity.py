@@ -155,6 +155,32 @@ def test_update_best_values_equals_full_copy(name):
     g.close()
 
 
+@pytest.mark.parametrize("env", ["SFX_SCHUR_V2", "SFX_SCHUR_V1", "SFX_NO_SCHUR_FAST", "SFX_POINT_ATOMICS", "SFX_SOLVE_V1",
+                                 "SFX_NO_BAL_FAST", "SFX_KC=1", "SFX_KC=3"])
+def test_alternative_kernel_paths_match_default(env):
+    """Every alternative device path kept in the library (generic-dimension Schur kernels, first-generation solves,
+    atomics instead of the per-point sum, other panel widths of the tile-DAG Cholesky) reproduces the default path's
+    iteration history on a BAL problem whose reduced system is large enough for the tile-DAG kernels."""
+    import os
+    prob = P.bal_problem("ladybug", solver=D.SOLVER_SCHUR)
+    g = capi.SfxProblem(prob)
+    g.optimize()
+    want = [(it.new_error, it.update_accepted) for it in g.iterations()]
+    g.close()
+    k, _, v = env.partition("=")
+    os.environ[k] = v or "1"
+    try:
+        g = capi.SfxProblem(prob)
+        g.optimize()
+        got = [(it.new_error, it.update_accepted) for it in g.iterations()]
+        g.close()
+    finally:
+        del os.environ[k]
+    assert len(got) == len(want)
+    for (e1, a1), (e0, a0) in zip(got, want):
+        assert a1 == a0 and abs(e1 - e0) <= COST_TOL * abs(e0)
+
+
 def test_status_codes(solved):
     prob = P.pose_smoothing(_params(iterations=2))
     g = capi.SfxProblem(prob)

@@ -2,6 +2,7 @@
 // example (symforce/examples/bundle_adjustment_in_the_large/bundle_adjustment_in_the_large.cc:27-140).
 //   bal_example <problem.txt>                     read a BAL file (https://grail.cs.washington.edu/projects/bal/)
 //   bal_example --synthetic <cams> <pts> <obs/pt>  generate a BAL-shaped problem (datasets are not in this image)
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
@@ -116,6 +117,10 @@ static Problem SyntheticProblem(int cams, int pts, int per_pt) {
 }
 
 int main(int argc, char** argv) {
+  const auto t_start = std::chrono::steady_clock::now();
+  auto seconds_since = [](std::chrono::steady_clock::time_point t0) {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  };
   Problem problem;
   if (argc == 5 && std::string(argv[1]) == "--synthetic")
     problem = SyntheticProblem(std::atoi(argv[2]), std::atoi(argv[3]), std::atoi(argv[4]));
@@ -131,8 +136,18 @@ int main(int argc, char** argv) {
   auto params = sym::DefaultOptimizerParams();
   params.lambda_update_type = sym::lambda_update_type_t::DYNAMIC;
   // keys c.., i.., p.. (lexical): the trailing points are eliminated by the GPU Schur path (AUTO)
+  const double build_s = seconds_since(t_start);
   sym::Optimizerd optimizer{params, std::move(problem.factors)};
+  const auto t_opt = std::chrono::steady_clock::now();
   const auto stats = optimizer.Optimize(optimized_values);
+  const double optimize_s = seconds_since(t_opt);
+  sfx_timings tm{};
+  sfx_get_timings(optimizer.Handle(), &tm);
+  // host-side ingestion (factor / Values construction), first-call initialisation (indexing, structural analysis,
+  // METIS, symbolic factorization, upload) and the device time of the LM iterations themselves
+  std::printf("Timing: build problem %.2f s, Optimize() wall %.2f s (first call includes Initialize), device %.1f ms for %d "
+              "iterations = %.2f ms/iteration\n",
+              build_s, optimize_s, tm.total_ms, tm.iterations_run, tm.iterations_run ? tm.total_ms / tm.iterations_run : 0.0);
   for (const auto& it : stats.iterations)
     std::printf("[iter %4d] lambda: %.3e, error: %.9e, rel reduction: %.5e, accepted: %d\n", it.iteration,
                 it.current_lambda, it.new_error, it.relative_reduction, (int)it.update_accepted);

@@ -213,6 +213,15 @@ sfx_status sfx_optimize(sfx_problem* p, int32_t num_iterations, sfx_stats* stats
 /* values = nonlinear_solver.GetBestValues() (internal/optimizer_utils.h:69) */
 sfx_status sfx_get_best_values(sfx_problem* p, double* values, int64_t n);
 
+/* GncOptimizer::Optimize outer loop (symforce/opt/gnc_optimizer.h:53-130, OptimizeContinue :133-142):
+ * sfx_optimize_continue = LevenbergMarquardtSolver::ResetState(values) (levenberg_marquardt_solver.h:178-183) with
+ * the values last given to sfx_set_values + IterateToConvergence for up to num_iterations more iterations: lambda,
+ * nu, the iteration counter and the iteration records continue from the preceding sfx_optimize[_continue] (stats
+ * report the accumulated records).  sfx_relax_damping_to_initial = RelaxDampingToInitial (:171-174).  The caller
+ * changes the convexity parameter in its Values and the early-exit threshold with sfx_update_params in between. */
+sfx_status sfx_optimize_continue(sfx_problem* p, int32_t num_iterations, sfx_stats* stats);
+sfx_status sfx_relax_damping_to_initial(sfx_problem* p);
+
 /* Values::Update(index, other) (symforce/opt/values.cc:269-275) with other = GetBestValues(): overwrites only the
  * storage of the optimized keys in `values`, which must be the buffer last given to sfx_set_values (every other
  * entry of the best values is identical to it by construction: only optimized keys are retracted).  Moves

@@ -681,7 +681,7 @@ class Optimizer {
   }
   Optimizer(const Optimizer&) = delete;
   Optimizer& operator=(const Optimizer&) = delete;
-  ~Optimizer() {
+  virtual ~Optimizer() {
     if (handle_) sfx_problem_destroy(handle_);
     if (cov_handle_) sfx_problem_destroy(cov_handle_);
   }
@@ -692,11 +692,19 @@ class Optimizer {
     Optimize(values, num_iterations, populate_best_linearization, stats);
     return stats;
   }
-  void Optimize(Values<Scalar>& values, int num_iterations, bool populate_best_linearization, Stats& stats) {
+  virtual void Optimize(Values<Scalar>& values, int num_iterations, bool populate_best_linearization, Stats& stats) {
+    OptimizeImpl(values, num_iterations, populate_best_linearization, stats, /*continue_previous=*/false);
+  }
+
+ protected:
+  // OptimizeImpl (internal/optimizer_utils.h:78-101), or -- continue_previous -- GncOptimizer::OptimizeContinue
+  // (gnc_optimizer.h:133-142): ResetState(values) + IterateToConvergence, stats keep accumulating
+  void OptimizeImpl(Values<Scalar>& values, int num_iterations, bool populate_best_linearization, Stats& stats,
+                    bool continue_previous) {
     Initialize(values);
     Check(sfx_set_values(handle_, values.Data().data(), static_cast<int64_t>(values.Data().size())));
     sfx_stats st{};
-    Check(sfx_optimize(handle_, num_iterations, &st));
+    Check(continue_previous ? sfx_optimize_continue(handle_, num_iterations, &st) : sfx_optimize(handle_, num_iterations, &st));
     std::vector<sfx_iteration> its(st.n_iterations);
     int32_t n = 0;
     Check(sfx_get_iterations(handle_, its.data(), st.n_iterations, &n));
@@ -727,6 +735,9 @@ class Optimizer {
       stats.best_linearization.reset();
     }
   }
+  void RelaxDampingToInitial() { Check(sfx_relax_damping_to_initial(handle_)); }
+
+ public:
 
   // Linearize(values) (optimizer.h:177)
   SparseLinearization Linearize(const Values<Scalar>& values) {
@@ -976,15 +987,24 @@ class Optimizer {
       else
         break;
     }
-    if (first == 0 || first == nk) return 0;
+    if (first == nk) return 0;
+    // shrink the run until no factor touches two of its keys (BAL: intrinsics and points are both small vectors
+    // and meet in every factor; the run must start behind the last intrinsics key)
     for (const auto& f : factors_) {
-      int lm = 0;
+      int largest = -1, second = -1;
       for (const Key& k : f.OptimizedKeys()) {
         auto it = key_index.find(k);
-        if (it != key_index.end() && it->second >= first) ++lm;
+        if (it == key_index.end() || it->second < first) continue;
+        if (it->second > largest) {
+          second = largest;
+          largest = it->second;
+        } else if (it->second > second) {
+          second = it->second;
+        }
       }
-      if (lm > 1) return 0;
+      if (second >= 0) first = std::max(first, second + 1);
     }
+    if (first == 0 || first >= nk) return 0;
     return (nk - first) >= nk / 2 ? nk - first : 0;
   }
   void FillPattern(SparseLinearization& lin) {
@@ -1017,6 +1037,63 @@ class Optimizer {
   int cov_schur_keys_{-1};
 };
 using Optimizerd = Optimizer<double>;
+
+// optimizer_gnc_params_t (lcmtypes/symforce.lcm:203-226)
+struct optimizer_gnc_params_t {
+  double gnc_update_min_reduction{0};
+  double mu_initial{0};
+  double mu_step{0};
+  double mu_max{0};
+};
+
+// GncOptimizer (symforce/opt/gnc_optimizer.h:15-148): optimizes to convergence with the convex cost, then steps
+// the convexity parameter mu (a scalar in the Values) towards mu_max, relaxing the damping and continuing the
+// optimization after every step.  The iteration budget is the total over all stages.
+template <typename BaseOptimizerType>
+class GncOptimizer : public BaseOptimizerType {
+ public:
+  using BaseOptimizer = BaseOptimizerType;
+  using Scalar = typename BaseOptimizer::Scalar;
+
+  template <typename... OptimizerArgs>
+  GncOptimizer(const optimizer_params_t& optimizer_params, const optimizer_gnc_params_t& gnc_params,
+               const Key& gnc_mu_key, OptimizerArgs&&... args)
+      : BaseOptimizer(optimizer_params, std::forward<OptimizerArgs>(args)...),
+        gnc_params_(gnc_params),
+        gnc_mu_key_(gnc_mu_key) {}
+
+  using BaseOptimizerType::Optimize;
+  void Optimize(Values<Scalar>& values, int num_iterations, bool populate_best_linearization,
+                typename BaseOptimizer::Stats& stats) override {
+    if (num_iterations < 0) num_iterations = this->Params().iterations;
+    bool updating_gnc = gnc_params_.mu_initial < gnc_params_.mu_max && gnc_params_.mu_step > 0.0;
+    values.template Set<Scalar>(gnc_mu_key_, static_cast<Scalar>(gnc_params_.mu_initial));
+    optimizer_params_t optimizer_params = this->Params();
+    const double early_exit_min_reduction = optimizer_params.early_exit_min_reduction;
+    if (updating_gnc) optimizer_params.early_exit_min_reduction = gnc_params_.gnc_update_min_reduction;
+    this->UpdateParams(optimizer_params);
+    this->OptimizeImpl(values, num_iterations, populate_best_linearization, stats, false);
+    while (static_cast<int>(stats.iterations.size()) < num_iterations) {
+      if (stats.status != optimization_status_t::SUCCESS) return;  // the previous stage did not converge
+      if (!updating_gnc) return;
+      values.template Set<Scalar>(gnc_mu_key_,
+                                  values.template At<Scalar>(gnc_mu_key_) + static_cast<Scalar>(gnc_params_.mu_step));
+      this->RelaxDampingToInitial();
+      if (values.template At<Scalar>(gnc_mu_key_) >= gnc_params_.mu_max) {
+        values.template Set<Scalar>(gnc_mu_key_, static_cast<Scalar>(gnc_params_.mu_max));
+        optimizer_params.early_exit_min_reduction = early_exit_min_reduction;
+        this->UpdateParams(optimizer_params);
+        updating_gnc = false;
+      }
+      this->OptimizeImpl(values, num_iterations - static_cast<int>(stats.iterations.size()),
+                         populate_best_linearization, stats, true);
+    }
+  }
+
+ private:
+  optimizer_gnc_params_t gnc_params_;
+  Key gnc_mu_key_;
+};
 
 // sym::Optimize (optimizer.h:334-340)
 template <typename Scalar>

@@ -738,6 +738,8 @@ struct Problem {
   void solve(const Csc& A, std::vector<double>& x);
   int iterate();
   void optimize(int num_iterations);
+  void optimize_continue(int num_iterations);
+  void run_iterations(int num_iterations);
 };
 
 void Problem::build(const sfx_problem_desc& d) {
@@ -1168,6 +1170,33 @@ void Problem::optimize(int num_iterations) {
   best_valid = false;
   iters.clear();
   stats = sfx_stats{};
+  run_iterations(num_iterations);
+  tm.total += now_s() - t0;
+}
+
+// OptimizeContinue (symforce/opt/gnc_optimizer.h:133-142): nonlinear_solver_.ResetState(values)
+// (levenberg_marquardt_solver.h:178-183: have_max_diagonal_ = have_last_update_ = false, state_.Reset(values):
+// internal/levenberg_marquardt_state.h:81-89, 250-261) then IterateToConvergence; lambda, nu, the iteration
+// counter and the stats keep accumulating.
+void Problem::optimize_continue(int num_iterations) {
+  ORC_ASSERT(num_iterations > 0, "num_iterations must be positive");
+  double t0 = now_s();
+  have_max_diag = false;
+  have_last_update = false;
+  New().values = cur_values;
+  for (auto& b : blocks) {
+    b.lin.initialized = false;
+    b.have_err = false;
+  }
+  best_valid = false;
+  stats.status = 0;
+  stats.failure_reason = 0;
+  run_iterations(num_iterations);
+  tm.total += now_s() - t0;
+}
+
+// IterateToConvergenceImpl (symforce/opt/internal/optimizer_utils.h:36-73)
+void Problem::run_iterations(int num_iterations) {
   int i;
   for (i = 0; i < num_iterations; ++i) {
     int st = iterate();
@@ -1182,7 +1211,6 @@ void Problem::optimize(int num_iterations) {
     stats.failure_reason = 0;
   }
   stats.n_iterations = (int)iters.size();
-  tm.total += now_s() - t0;
   tm.iters += std::min(i + 1, num_iterations);
 }
 
@@ -1241,6 +1269,22 @@ int orc_optimize(void* p, int num_iterations, sfx_stats* stats) {
     Problem* P = (Problem*)p;
     P->optimize(num_iterations);
     if (stats) *stats = P->stats;
+  });
+}
+
+int orc_optimize_continue(void* p, int num_iterations, sfx_stats* stats) {
+  ORC_TRY(p, {
+    ((Problem*)p)->optimize_continue(num_iterations);
+    if (stats) *stats = ((Problem*)p)->stats;
+  });
+}
+
+// RelaxDampingToInitial (levenberg_marquardt_solver.h:171-174)
+int orc_relax_damping_to_initial(void* p) {
+  ORC_TRY(p, {
+    Problem* q = (Problem*)p;
+    q->lambda = std::min(q->lambda, q->p.initial_lambda);
+    q->nu = q->p.dynamic_lambda_update_beta;
   });
 }
 

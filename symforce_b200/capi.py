@@ -16,7 +16,8 @@ LIB_PATH = os.environ.get("SFX_LIB") or os.path.join(_HERE, "lib", "libsfx.so") 
 
 EXPORTS = [
     "sfx_default_params", "sfx_problem_create", "sfx_problem_destroy", "sfx_last_error", "sfx_update_params",
-    "sfx_set_values", "sfx_optimize", "sfx_get_best_values", "sfx_update_best_values", "sfx_get_iterations", "sfx_get_dims",
+    "sfx_set_values", "sfx_optimize", "sfx_optimize_continue", "sfx_relax_damping_to_initial", "sfx_get_best_values",
+    "sfx_update_best_values", "sfx_get_iterations", "sfx_get_dims",
     "sfx_get_hessian_pattern", "sfx_linearize", "sfx_get_best_linearization", "sfx_solve_step",
     "sfx_compute_covariance", "sfx_get_ordering", "sfx_get_timings", "sfx_get_info", "sfx_comm_unique_id", "sfx_comm_create",
     "sfx_comm_destroy",

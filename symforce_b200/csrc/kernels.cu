@@ -1914,12 +1914,13 @@ __global__ void lm_begin_kernel(Ctrl* c) {
 // after the first linearization of Init: SetBestToInit + stats[-1] (…tcc:151-186)
 __global__ void lm_after_first_kernel(Ctrl* c) {
   if (c->done) return;
-  if (c->iteration != 0) return;
+  // SetBestToInit after EvaluateFirst: on the first Iterate after every Reset / ResetState (…tcc:151-155)
   c->best_valid = 1;
   if (c->best_idx != c->init_idx) {
     if (c->best_idx != c->new_idx) c->free_idx = c->best_idx;
     c->best_idx = c->init_idx;
   }
+  if (c->iteration != 0) return;  // FirstIterationStats only when the iteration counter was reset (…tcc:158-186)
   sfx_iteration& it = c->iters[0];
   it.iteration = -1;
   it.update_accepted = 0;

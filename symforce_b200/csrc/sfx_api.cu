@@ -123,6 +123,7 @@ struct sfx_problem {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int n_large_fronts = 0;
   unsigned solve_epoch = 0;
+  bool can_continue = false;  // the control block is the one the last sfx_optimize[_continue] left
   std::vector<std::pair<int64_t, int64_t>> opt_ranges;  // merged storage ranges of the optimized keys
   int pre_j0 = 0, pre_j1 = 0, damp_j0 = 0, damp_j1 = 0;  // assembly jobs run before level 0 (copies, damping)
   Ctrl* d_ctrl = nullptr;
@@ -716,6 +717,7 @@ void upload_structures(sfx_problem* p) {
 
 void reset_ctrl(sfx_problem* p) {
   Ctrl* c = p->h_ctrl;
+  p->can_continue = false;
   std::memset(c, 0, offsetof(Ctrl, iters));
   c->p = p->params;
   c->epsilon = p->epsilon;
@@ -726,6 +728,23 @@ void reset_ctrl(sfx_problem* p) {
   c->best_idx = 0;
   c->free_idx = 2;
   c->iteration = -1;
+  CUDA_OK(cudaMemcpyAsync(p->d_ctrl, c, offsetof(Ctrl, iters), cudaMemcpyHostToDevice, p->st));
+  std::memset(p->h_done, 0, sizeof(int) * (kMaxIterations + 2));
+}
+
+// LevenbergMarquardtSolver::ResetState (levenberg_marquardt_solver.h:178-183) on top of the control block left
+// by the previous Optimize: linearizations and Best become invalid, max-diagonal / last-update memories are
+// dropped; lambda, nu, the iteration counter, the iteration records and the state-block indices stay.
+void reset_ctrl_continue(sfx_problem* p) {
+  Ctrl* c = p->h_ctrl;
+  c->p = p->params;
+  c->have_max_diag = 0;
+  c->have_last_update = 0;
+  c->lin_valid[0] = c->lin_valid[1] = c->lin_valid[2] = 0;
+  c->best_valid = 0;
+  c->done = 0;
+  c->failure_reason = 0;
+  c->chol_fail = 0;
   CUDA_OK(cudaMemcpyAsync(p->d_ctrl, c, offsetof(Ctrl, iters), cudaMemcpyHostToDevice, p->st));
   std::memset(p->h_done, 0, sizeof(int) * (kMaxIterations + 2));
 }
@@ -976,7 +995,7 @@ sfx_status sfx_set_values(sfx_problem* p, const double* values, int64_t n) {
   SFX_API_END(p)
 }
 
-sfx_status sfx_optimize(sfx_problem* p, int32_t num_iterations, sfx_stats* stats) {
+static sfx_status optimize_impl(sfx_problem* p, int32_t num_iterations, sfx_stats* stats, bool cont) {
   SFX_API_BEGIN
   SFX_CHECK(p, SFX_ERR_INVALID_ARG, "null problem");
   SFX_CHECK(p->values_set, SFX_ERR_INVALID_ARG, "sfx_set_values must be called first");
@@ -986,9 +1005,17 @@ sfx_status sfx_optimize(sfx_problem* p, int32_t num_iterations, sfx_stats* stats
   CUDA_OK(cudaSetDevice(p->device));
   Analysis& a = p->a;
   const int64_t launches0 = g_launches;
-  // Reset(values): all three state blocks hold the full values buffer; optimized keys are
-  // overwritten by retract (levenberg_marquardt_solver.h:163-182, state ResetValues)
-  reset_ctrl(p);
+  if (cont) {
+    SFX_CHECK(p->can_continue, SFX_ERR_INVALID_ARG,
+              "sfx_optimize_continue must directly follow sfx_optimize / sfx_optimize_continue (SYM_ASSERT: IsInitialized())");
+    SFX_CHECK(p->h_ctrl->n_iters + num_iterations <= kMaxIterations, SFX_ERR_INVALID_ARG,
+              "num_iterations exceeds stats capacity");
+    reset_ctrl_continue(p);
+  } else {
+    // Reset(values): all three state blocks hold the full values buffer; optimized keys are
+    // overwritten by retract (levenberg_marquardt_solver.h:163-182, state ResetValues)
+    reset_ctrl(p);
+  }
   for (int b = 0; b < 3; ++b) launch_copy_values(p->st, p->sp.values[b], p->d_cur_values, a.n_values);
   // events
   const size_t need = (size_t)num_iterations * (PH_COUNT + 1) + 8;
@@ -1071,6 +1098,25 @@ sfx_status sfx_optimize(sfx_problem* p, int32_t num_iterations, sfx_stats* stats
   tm.n_factorize = tm.iterations_run;
   tm.kernel_launches = (int32_t)(g_launches - launches0);
   p->tm = tm;
+  p->can_continue = true;
+  SFX_API_END(p)
+}
+
+sfx_status sfx_optimize(sfx_problem* p, int32_t num_iterations, sfx_stats* stats) {
+  return optimize_impl(p, num_iterations, stats, false);
+}
+
+sfx_status sfx_optimize_continue(sfx_problem* p, int32_t num_iterations, sfx_stats* stats) {
+  return optimize_impl(p, num_iterations, stats, true);
+}
+
+sfx_status sfx_relax_damping_to_initial(sfx_problem* p) {
+  SFX_API_BEGIN
+  SFX_CHECK(p, SFX_ERR_INVALID_ARG, "null problem");
+  SFX_CHECK(p->can_continue, SFX_ERR_INVALID_ARG, "no optimization to continue (SYM_ASSERT: IsInitialized())");
+  Ctrl* c = p->h_ctrl;  // uploaded by the next sfx_optimize_continue
+  c->lambda = std::min(c->lambda, p->params.initial_lambda);
+  c->nu = p->params.dynamic_lambda_update_beta;
   SFX_API_END(p)
 }
 

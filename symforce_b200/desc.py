@@ -262,6 +262,15 @@ class _LibProblem:
         self._check(self._fn("optimize")(self.h, C.c_int32(num_iterations), C.byref(st)), "optimize")
         return st
 
+    def optimize_continue(self, num_iterations):
+        """OptimizeContinue of gnc_optimizer.h:133-142: ResetState(values last set) + IterateToConvergence."""
+        st = Stats()
+        self._check(self._fn("optimize_continue")(self.h, C.c_int32(num_iterations), C.byref(st)), "optimize_continue")
+        return st
+
+    def relax_damping_to_initial(self):
+        self._check(self._fn("relax_damping_to_initial")(self.h), "relax_damping_to_initial")
+
     def best_values(self, out=None):
         """values = GetBestValues(); `out` (float64, contiguous, e.g. a pinned buffer) avoids the allocation."""
         if out is None:

@@ -587,4 +587,6 @@ def ba_example(seed=42, num_landmarks=20, params=None):
         params.lambda_up_factor = 10.0
         params.lambda_down_factor = 0.1
         params.lambda_lower_bound = 1e-8
-    return D.Problem(vb.data(), keys, [between, prior, gnc], params=params, epsilon=eps)
+    prob = D.Problem(vb.data(), keys, [between, prior, gnc], params=params, epsilon=eps)
+    prob.meta = dict(mu_off=int(mu_off), scale_off=int(scale_off), num_landmarks=num_landmarks)
+    return prob

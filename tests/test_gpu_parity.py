@@ -246,6 +246,10 @@ def test_cpp_examples_through_sym_layer():
     out = subprocess.run([os.path.join(root, "examples", "_build", "covariance_check")], capture_output=True, text=True,
                          timeout=120)
     assert out.returncode == 0 and "COVARIANCE_OK" in out.stdout, out.stdout + out.stderr
+    # config A through the sym:: layer: sym::Optimizer like the reference example, and sym::GncOptimizer
+    out = subprocess.run([os.path.join(root, "examples", "_build", "bundle_adjustment")], capture_output=True, text=True,
+                         timeout=120)
+    assert out.returncode == 0 and "GNC_OK" in out.stdout, out.stdout + out.stderr
     out = subprocess.run([os.path.join(root, "examples", "_build", "bundle_adjustment_in_the_large"), "--synthetic",
                           "12", "400", "5"], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stdout + out.stderr

@@ -1145,12 +1145,22 @@ sfx_status sfx_update_best_values(sfx_problem* p, double* values, int64_t n, int
   SFX_CHECK(p->h_ctrl->best_valid, SFX_ERR_INVALID_ARG, "SYM_ASSERT: state_.BestIsValid()");
   CUDA_OK(cudaSetDevice(p->device));
   Analysis& a = p->a;
-  if (a.world > 1 || p->opt_ranges.size() > 256) {
-    // scattered keys (or sharded landmarks): the full buffer is cheaper than thousands of small copies
+  if (p->opt_ranges.size() > 256) {
+    // scattered keys: the full buffer is cheaper than thousands of small copies
     if (bytes_copied) *bytes_copied = (int64_t)sizeof(double) * n;
     return sfx_get_best_values(p, values, n);
   }
   const double* src = p->sp.values[p->h_ctrl->best_idx];
+  if (a.world > 1) {
+    // every rank holds the cameras and its own landmarks: a masked all-reduce per optimized range assembles them
+    for (const auto& x : p->opt_ranges) {
+      const int64_t len = x.second - x.first;
+      launch_mask_values(p->st, src + x.first, p->d_vmask + x.first, len, p->d_stage + x.first);
+      NCCL_OK(nccl().AllReduce(p->d_stage + x.first, p->d_stage + x.first, (size_t)len, ncclDouble, ncclSum,
+                               p->comm->comm, p->st));
+    }
+    src = p->d_stage;
+  }
   int64_t total = 0;
   for (const auto& x : p->opt_ranges) {
     CUDA_OK(cudaMemcpyAsync(values + x.first, src + x.first, sizeof(double) * (x.second - x.first),

@@ -219,7 +219,8 @@ void build_front_plan(const BlockMatrix& A, int ordering, const std::vector<int>
         const double mp = wp + up;
         const double zeros = wc * (mp - uc);  // rows of the parent front absent from the child
         const double merged = (wc + wp) * (wc + wp + up);
-        bool ok = zeros <= 0.0 || (wc + wp <= 48 && zeros <= 0.35 * merged) || zeros <= 0.08 * merged;
+        static const double relax_big = getenv("SFX_RELAX") ? atof(getenv("SFX_RELAX")) : 0.08;  // experiment knob
+        bool ok = zeros <= 0.0 || (wc + wp <= 48 && zeros <= 0.35 * merged) || zeros <= relax_big * merged;
         if (!ok) break;
         // merge c into s
         alive[c] = 0;

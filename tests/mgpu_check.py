@@ -29,6 +29,9 @@ for name in ["small", "ladybug"]:
     st = g.optimize()
     its = g.iterations()
     vals = g.best_values()
+    upd = np.array(prob.values, dtype=np.float64, copy=True)
+    g.update_best_values(upd)  # Values::Update semantics must assemble the same buffer on every rank
+    assert np.array_equal(upd, vals), "update_best_values != best_values on rank %d" % rank
     if rank == 0:
         g1 = capi.SfxProblem(prob, device=local)
         st1 = g1.optimize()

@@ -212,8 +212,10 @@ def main():
     gpu.set_values(pinned.numpy())
     gpu.optimize(W)
 
+    # clocks are sampled by rank 0 only: N concurrent nvidia-smi pollers contend for the driver and for host cores
     sampler = ClockSampler(local_rank)
-    sampler.start()
+    if rank == 0:
+        sampler.start()
     # ---- device-resident: K iterations in one call ---------------------------------------------
     gpu.set_values(pinned.numpy())
     barrier()
@@ -228,12 +230,23 @@ def main():
     barrier()
     t0 = time.perf_counter()
     d2h_bytes = 0
+    diag = [0.0, 0.0, 0.0]
     for _ in range(K):
+        ta = time.perf_counter()
         gpu.set_values(pinned.numpy())
+        tb = time.perf_counter()
         gpu.optimize(1)
+        tc = time.perf_counter()
         # the result lands in the caller's Values buffer like sym::Optimizer::Optimize(values) does it:
         # Values::Update semantics, only the optimized keys travel back
         d2h_bytes = gpu.update_best_values(pinned.numpy())
+        td = time.perf_counter()
+        diag[0] += tb - ta
+        diag[1] += tc - tb
+        diag[2] += td - tc
+    if os.environ.get("SFX_E2E_DIAG"):
+        print(f"[e2e rank {rank}] per step: set_values {diag[0] / K * 1e3:.2f} ms, optimize(1) {diag[1] / K * 1e3:.2f} ms, "
+              f"update_best_values {diag[2] / K * 1e3:.2f} ms", file=sys.stderr, flush=True)
     barrier()
     e2e_s = time.perf_counter() - t0
     clocks = sampler.stop()

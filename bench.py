@@ -12,7 +12,8 @@ relinearize -> accept/reject) of sym::Optimizer on the workload.
   e2e   : K calls of the reference-facing API the way the reference's own benchmark drives it
           (`Optimize(values, 1, ...)`, symforce/benchmarks/robot_3d_localization/
           robot_3d_localization_benchmark.cc:88-93): per step a host->device copy of the Values
-          buffer from pinned host memory, one LM iteration, and the device->host read of the result.
+          buffer from pinned host memory, one LM iteration, and the device->host read of the result
+          into the same buffer (Values::Update semantics: the optimized keys' storage).
   --impl reference : the reference's own CPU algorithm (oracle/, a restatement pinned to the
           reference's KATs -- the reference C++ cannot be built here), single
           thread like the reference, on a bounded sample of the same workload.

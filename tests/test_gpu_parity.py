@@ -189,6 +189,25 @@ def test_status_codes(solved):
     g.close()
 
 
+def test_failure_statuses_match_oracle():
+    """optimization_status_t::FAILED / INITIAL_ERROR_NOT_FINITE (lcmtypes/symforce.lcm:279-299), decided on the device like
+    every other LM decision: the GPU reports what the CPU restatement reports."""
+    # INITIAL_ERROR_NOT_FINITE (levenberg_marquardt_solver.tcc:178-185): a NaN measurement
+    prob = P.bal_problem("tiny", solver=D.SOLVER_SCHUR)
+    bad = np.array(prob.values, dtype=np.float64, copy=True)
+    bad[-3] = np.nan  # a pixel coordinate / constant at the end of the buffer
+    g, o = capi.SfxProblem(prob), O.OracleProblem(prob)
+    g.set_values(bad)
+    o.set_values(bad)
+    sg, so = g.optimize(), o.optimize()
+    assert so.status == D.STATUS_FAILED and so.failure_reason == 2
+    assert (sg.status, sg.failure_reason, sg.n_iterations) == (so.status, so.failure_reason, so.n_iterations)
+    # the problem object stays usable
+    g.set_values(prob.values)
+    assert g.optimize().status == D.STATUS_SUCCESS
+    g.close()
+
+
 def test_bal_properties_at_scale():
     """Size-independent properties on a mid-size BAL problem (no oracle): monotone accepted errors,
     gradient norm reduced, Schur path == full Cholesky path."""

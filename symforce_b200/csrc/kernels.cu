@@ -1116,7 +1116,10 @@ __global__ void __launch_bounds__(kSchurWarps * 32) schur_s_dmma_kernel(const Ct
 //     offsets are loaded once per 32 matches (one coalesced load) and broadcast with shuffles; the
 //     loads of the next four k-steps (16 per lane) are in flight while the current four issue.
 constexpr int kWThreads = 128;
-__global__ void __launch_bounds__(kWThreads) schur_w_rhs_kernel(const Ctrl* __restrict__ ctrl, StatePtrs sp,
+#ifndef SFX_W_MINB
+#define SFX_W_MINB 5
+#endif
+__global__ void __launch_bounds__(kWThreads, SFX_W_MINB) schur_w_rhs_kernel(const Ctrl* __restrict__ ctrl, StatePtrs sp,
                                                                 SchurDev sd) {
   __shared__ double stage[kWThreads / 32][32 * 27];
   if (ctrl->done) return;
@@ -1331,7 +1334,10 @@ __global__ void __launch_bounds__(kSchurWarps * 32, 4) schur_s2_kernel(const Ctr
 //      reduced over the four k-lanes at the end.  Offsets sit in a per-warp shared-memory table; the 16
 //      loads of the next four k-steps are in flight while the current four issue.
 constexpr int kS9Warps = 4;
-__global__ void __launch_bounds__(kS9Warps * 32, 4) schur_s9_kernel(const Ctrl* __restrict__ ctrl, StatePtrs sp,
+#ifndef SFX_S9_MINB
+#define SFX_S9_MINB 4
+#endif
+__global__ void __launch_bounds__(kS9Warps * 32, SFX_S9_MINB) schur_s9_kernel(const Ctrl* __restrict__ ctrl, StatePtrs sp,
                                                                    SchurDev sd, const double* __restrict__ dvec) {
   __shared__ int32_t offs[kS9Warps][2][128];  // [buffer][0..63: row operand, 64..127: column operand]
   if (ctrl->done) return;
@@ -1540,7 +1546,7 @@ void launch_schur(cudaStream_t st, const Ctrl* ctrl, StatePtrs sp, const SchurDe
     if (sd.wl != nullptr) {
       schur_w_rhs_kernel<<<(sd.n_entries + kWThreads - 1) / kWThreads, kWThreads, 0, st>>>(ctrl, sp, sd); ++g_launches;
       if (sd.items3 != nullptr) {
-        int grid = 148 * 4;
+        int grid = 148 * SFX_S9_MINB;
         if (grid * kS9Warps > sd.n_items) grid = (sd.n_items + kS9Warps - 1) / kS9Warps;
         schur_s9_kernel<<<grid, kS9Warps * 32, 0, st>>>(ctrl, sp, sd, dvec); ++g_launches;
         return;

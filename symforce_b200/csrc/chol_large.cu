@@ -1223,7 +1223,32 @@ __global__ void __launch_bounds__(kLargeThreads, 1)
         const int t = tid & 63, gq = tid >> 6;
         double v = 0.0;
         if (t < ni) {
-          for (int r = i + 1 + gq; r < nt; r += 4) v += ll_load(contrib + ((size_t)i * nt + r) * kT + t, epoch);
+          // four slots per round trip: the loads are issued together (most contributions arrived long ago); a slot
+          // whose epoch is not there yet is polled afterwards
+          for (int r0 = i + 1 + gq; r0 < nt; r0 += 16) {
+            unsigned lo[4], f1[4], hi[4], f2[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int r = r0 + 4 * u;
+              if (r < nt) {
+                const uint4* q = contrib + ((size_t)i * nt + r) * kT + t;
+                asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];"
+                             : "=r"(lo[u]), "=r"(f1[u]), "=r"(hi[u]), "=r"(f2[u])
+                             : "l"(q)
+                             : "memory");
+              }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const int r = r0 + 4 * u;
+              if (r < nt) {
+                if (f1[u] == epoch && f2[u] == epoch)
+                  v += __longlong_as_double((long long)(((unsigned long long)hi[u] << 32) | lo[u]));
+                else
+                  v += ll_load(contrib + ((size_t)i * nt + r) * kT + t, epoch);
+              }
+            }
+          }
         }
         red[gq * 64 + t] = v;
       }

@@ -213,6 +213,13 @@ sfx_status sfx_optimize(sfx_problem* p, int32_t num_iterations, sfx_stats* stats
 /* values = nonlinear_solver.GetBestValues() (internal/optimizer_utils.h:69) */
 sfx_status sfx_get_best_values(sfx_problem* p, double* values, int64_t n);
 
+/* optimizer_params_t::debug_stats (lcmtypes/symforce.lcm:236-246, levenberg_marquardt_solver.tcc:166-171,245-250):
+ * optimization_iteration_t::values (the data of the Values buffer, whose index the caller already has) and
+ * ::residual of iteration record `record` (0 = the record of iteration -1) of the last sfx_optimize[_continue],
+ * which must have run with debug_stats set.  Either output may be NULL.  Costs iterations x (Values + residual)
+ * of device memory; single GPU.  (jacobian_values / include_jacobians are not produced: the path never forms J.) */
+sfx_status sfx_get_iteration_debug(sfx_problem* p, int32_t record, double* values, double* residual);
+
 /* GncOptimizer::Optimize outer loop (symforce/opt/gnc_optimizer.h:53-130, OptimizeContinue :133-142):
  * sfx_optimize_continue = LevenbergMarquardtSolver::ResetState(values) (levenberg_marquardt_solver.h:178-183) with
  * the values last given to sfx_set_values + IterateToConvergence for up to num_iterations more iterations: lambda,

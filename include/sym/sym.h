@@ -407,6 +407,8 @@ struct optimization_iteration_t {
   double relative_reduction{0};
   bool update_accepted{false};
   double update_angle_change{0};
+  // debug_stats only (symforce.lcm:236-246): the data of the Values buffer and the residual of this record
+  std::vector<double> values, residual;
 };
 
 // Linearization container (symforce/opt/linearization.h:27-77) with the CSC pieces the reference's
@@ -719,6 +721,17 @@ class Optimizer {
       o.update_accepted = it.update_accepted != 0;
       o.update_angle_change = it.update_angle_change;
       stats.iterations.push_back(o);
+    }
+    if (params_.debug_stats) {
+      int32_t N = 0, M = 0;
+      int64_t nnz = 0;
+      Check(sfx_get_dims(handle_, &N, &M, &nnz));
+      for (size_t i = 0; i < stats.iterations.size(); ++i) {
+        stats.iterations[i].values.resize(values.Data().size());
+        stats.iterations[i].residual.resize(M);
+        Check(sfx_get_iteration_debug(handle_, static_cast<int32_t>(i), stats.iterations[i].values.data(),
+                                      stats.iterations[i].residual.data()));
+      }
     }
     stats.best_index = st.best_index;
     stats.status = static_cast<optimization_status_t>(st.status);

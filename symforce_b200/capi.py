@@ -17,7 +17,7 @@ LIB_PATH = os.environ.get("SFX_LIB") or os.path.join(_HERE, "lib", "libsfx.so") 
 EXPORTS = [
     "sfx_default_params", "sfx_problem_create", "sfx_problem_destroy", "sfx_last_error", "sfx_update_params",
     "sfx_set_values", "sfx_optimize", "sfx_optimize_continue", "sfx_relax_damping_to_initial", "sfx_get_best_values",
-    "sfx_update_best_values", "sfx_get_iterations", "sfx_get_dims",
+    "sfx_update_best_values", "sfx_get_iteration_debug", "sfx_get_iterations", "sfx_get_dims",
     "sfx_get_hessian_pattern", "sfx_linearize", "sfx_get_best_linearization", "sfx_solve_step",
     "sfx_compute_covariance", "sfx_get_ordering", "sfx_get_timings", "sfx_get_info", "sfx_comm_unique_id", "sfx_comm_create",
     "sfx_comm_destroy",
@@ -120,6 +120,16 @@ class SfxProblem(D._LibProblem):
         self._check(self.lib.sfx_update_best_values(self.h, values.ctypes.data_as(C.POINTER(C.c_double)),
                                                     C.c_int64(values.shape[0]), C.byref(nb)), "update_best_values")
         return nb.value
+
+    def iteration_debug(self, record):
+        """debug_stats payload of an iteration record: (values data, residual)."""
+        _, M, _ = self.dims()
+        v = np.empty(self.n_values)
+        r = np.empty(M)
+        p = C.POINTER(C.c_double)
+        self._check(self.lib.sfx_get_iteration_debug(self.h, C.c_int32(record), v.ctypes.data_as(p), r.ctypes.data_as(p)),
+                    "get_iteration_debug")
+        return v, r
 
     def compute_covariance(self, block_dim, hessian_values=None):
         """Optimizer::ComputeCovariances / ComputeFullCovariance: dense block_dim x block_dim covariance in keys_

@@ -123,6 +123,10 @@ struct sfx_problem {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   int n_large_fronts = 0;
   unsigned solve_epoch = 0;
+  // debug_stats: per-record snapshots of values / residual (allocated on first use)
+  double *dbg_values = nullptr, *dbg_res = nullptr;
+  int dbg_cap = 0;
+  bool dbg_valid = false;
   bool can_continue = false;  // the control block is the one the last sfx_optimize[_continue] left
   std::vector<std::pair<int64_t, int64_t>> opt_ranges;  // merged storage ranges of the optimized keys
   int pre_j0 = 0, pre_j1 = 0, damp_j0 = 0, damp_j1 = 0;  // assembly jobs run before level 0 (copies, damping)
@@ -164,6 +168,8 @@ struct sfx_problem {
     for (auto e : ev) cudaEventDestroy(e);
     if (st) cudaStreamDestroy(st);
     if (st2) cudaStreamDestroy(st2);
+    if (dbg_values) cudaFree(dbg_values);
+    if (dbg_res) cudaFree(dbg_res);
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
     if (h_ctrl) cudaFreeHost(h_ctrl);
@@ -1005,6 +1011,33 @@ static sfx_status optimize_impl(sfx_problem* p, int32_t num_iterations, sfx_stat
   CUDA_OK(cudaSetDevice(p->device));
   Analysis& a = p->a;
   const int64_t launches0 = g_launches;
+  // debug_stats (optimizer_params_t, lcmtypes/symforce.lcm): keep values and residual of every record
+  const bool dbg = p->params.debug_stats != 0;
+  if (dbg) {
+    SFX_CHECK(a.world == 1, SFX_ERR_UNSUPPORTED, "debug_stats snapshots are single-GPU only");
+    const int need = (cont ? p->h_ctrl->n_iters : 0) + num_iterations + 1;
+    if (need > p->dbg_cap) {
+      double *nv = nullptr, *nr = nullptr;
+      if (cudaMalloc(&nv, sizeof(double) * (size_t)need * a.n_values) != cudaSuccess ||
+          cudaMalloc(&nr, sizeof(double) * (size_t)need * std::max(a.M, 1)) != cudaSuccess) {
+        if (nv) cudaFree(nv);
+        throw Error(SFX_ERR_CUDA, "out of device memory for the debug_stats snapshots (iterations x Values)");
+      }
+      if (cont && p->dbg_valid) {  // keep the records of the stages before
+        CUDA_OK(cudaMemcpyAsync(nv, p->dbg_values, sizeof(double) * (size_t)p->h_ctrl->n_iters * a.n_values,
+                                cudaMemcpyDeviceToDevice, p->st));
+        CUDA_OK(cudaMemcpyAsync(nr, p->dbg_res, sizeof(double) * (size_t)p->h_ctrl->n_iters * a.M, cudaMemcpyDeviceToDevice,
+                                p->st));
+        CUDA_OK(cudaStreamSynchronize(p->st));
+      }
+      if (p->dbg_values) cudaFree(p->dbg_values);
+      if (p->dbg_res) cudaFree(p->dbg_res);
+      p->dbg_values = nv;
+      p->dbg_res = nr;
+      p->dbg_cap = need;
+    }
+  }
+  p->dbg_valid = dbg && (cont ? p->dbg_valid || p->h_ctrl->n_iters == 0 : true);
   if (cont) {
     SFX_CHECK(p->can_continue, SFX_ERR_INVALID_ARG,
               "sfx_optimize_continue must directly follow sfx_optimize / sfx_optimize_continue (SYM_ASSERT: IsInitialized())");
@@ -1044,6 +1077,7 @@ static sfx_status optimize_impl(sfx_problem* p, int32_t num_iterations, sfx_stat
     if (i == 0) {
       enqueue_linearize(p, /*mode=*/0);
       launch_lm_after_first_linearize(p->st, p->d_ctrl);
+      if (dbg) launch_debug_snapshot(p->st, p->d_ctrl, p->sp, 1, a.n_values, a.M, p->dbg_cap, p->dbg_values, p->dbg_res);
       mark(PH_LIN);
     }
     enqueue_solve(p, mark);
@@ -1051,6 +1085,7 @@ static sfx_status optimize_impl(sfx_problem* p, int32_t num_iterations, sfx_stat
                    p->d_key_itoff, a.n_keys, p->d_upd);
     mark(PH_UPDATE);
     enqueue_linearize(p, /*mode=*/1);
+    if (dbg) launch_debug_snapshot(p->st, p->d_ctrl, p->sp, 0, a.n_values, a.M, p->dbg_cap, p->dbg_values, p->dbg_res);
     mark(PH_LIN);
     launch_step_reduce(p->st, p->d_ctrl, p->sp, p->d_upd, p->d_dvec, p->d_last, a.N, p->d_partials,
                        (a.world > 1 && a.rank != 0) ? a.sp.reduced_dim : 0);
@@ -1169,6 +1204,22 @@ sfx_status sfx_update_best_values(sfx_problem* p, double* values, int64_t n, int
   }
   CUDA_OK(cudaStreamSynchronize(p->st));
   if (bytes_copied) *bytes_copied = total;
+  SFX_API_END(p)
+}
+
+sfx_status sfx_get_iteration_debug(sfx_problem* p, int32_t record, double* values, double* residual) {
+  SFX_API_BEGIN
+  SFX_CHECK(p, SFX_ERR_INVALID_ARG, "null problem");
+  SFX_CHECK(p->dbg_valid, SFX_ERR_INVALID_ARG, "the last optimization did not run with optimizer_params_t::debug_stats");
+  SFX_CHECK(record >= 0 && record < p->h_ctrl->n_iters && record < p->dbg_cap, SFX_ERR_INVALID_ARG, "no such iteration record");
+  CUDA_OK(cudaSetDevice(p->device));
+  const Analysis& a = p->a;
+  if (values)
+    CUDA_OK(cudaMemcpyAsync(values, p->dbg_values + (size_t)record * a.n_values, sizeof(double) * a.n_values,
+                            cudaMemcpyDeviceToHost, p->st));
+  if (residual)
+    CUDA_OK(cudaMemcpyAsync(residual, p->dbg_res + (size_t)record * a.M, sizeof(double) * a.M, cudaMemcpyDeviceToHost, p->st));
+  CUDA_OK(cudaStreamSynchronize(p->st));
   SFX_API_END(p)
 }
 

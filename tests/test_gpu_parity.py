@@ -274,3 +274,37 @@ def test_cpp_examples_through_sym_layer():
     assert out.returncode == 0, out.stdout + out.stderr
     errs = [float(x) for x in re.findall(r"error: ([0-9.eE+-]+),", out.stdout)]
     assert errs[-1] < 0.05 * errs[0]
+
+
+@pytest.mark.parametrize("name", ["robot3d", "bal_small_schur"])
+def test_debug_stats_payloads(name):
+    """optimizer_params_t::debug_stats: optimization_iteration_t::values / residual of every record
+    (levenberg_marquardt_solver.tcc:166-171, 245-250), kept on the device and read through sfx_get_iteration_debug."""
+    prob = PROBLEMS[name]()
+    prob.params.debug_stats = 1
+    g = capi.SfxProblem(prob)
+    st = g.optimize()
+    its = g.iterations()
+    v0, r0 = g.iteration_debug(0)
+    assert np.array_equal(v0, prob.values)  # the record of iteration -1 holds the initial values
+    for i, it in enumerate(its):
+        v, r = g.iteration_debug(i)
+        assert 0.5 * float(r @ r) == pytest.approx(it.new_error, rel=1e-12)
+    vb, _ = g.iteration_debug(st.best_index)
+    assert np.array_equal(vb, g.best_values())
+    # the residual of a record is the residual at that record's values
+    k = len(its) // 2
+    vk, rk = g.iteration_debug(k)
+    g.set_values(vk)
+    res, _, _ = g.linearize()
+    assert np.allclose(res, rk, rtol=0, atol=1e-12 * max(1.0, np.abs(rk).max()))
+    with pytest.raises(RuntimeError, match="rc=1"):  # linearize() was not an optimization with debug_stats
+        g.iteration_debug(len(its))
+    g.close()
+    # without debug_stats there is nothing to read
+    prob.params.debug_stats = 0
+    g = capi.SfxProblem(prob)
+    g.optimize()
+    with pytest.raises(RuntimeError, match="rc=1"):
+        g.iteration_debug(0)
+    g.close()

@@ -791,7 +791,8 @@ void launch_large_preassemble(cudaStream_t st, const Ctrl* ctrl, const FrontDev&
   }
 }
 void launch_large_level(cudaStream_t st, Ctrl* ctrl, const FrontDev& fd, const LargeDev& ld, const LargeLevel& lv,
-                        int level, const double* sys_static, StatePtrs sp, int use_state_H, const double* dvec) {
+                        int level, const double* sys_static, StatePtrs sp, int use_state_H, const double* dvec,
+                        int grid_cap) {
   if (lv.n_lf == 0) return;
   const int nj = lv.j1 - lv.j0;
   if (nj > 0) {
@@ -800,6 +801,9 @@ void launch_large_level(cudaStream_t st, Ctrl* ctrl, const FrontDev& fd, const L
   }
   const int ntask = lv.t1 - lv.t0;
   int grid = ntask < 148 * 3 ? ntask : 148 * 3;
+  // single-front levels are bound by the diagonal chain, not by throughput: one CTA per SM is as fast as two
+  // (measured) and leaves room for the forward-substitution CTAs that overlap them
+  if (grid_cap > 0 && grid > grid_cap) grid = grid_cap;
   const size_t smem = 2 * kT * kLd * sizeof(double);
   large_factor_kernel<<<grid, kLargeThreads, smem, st>>>(ctrl, fd, ld, lv.t0, lv.t1, level); ++g_launches;
 }

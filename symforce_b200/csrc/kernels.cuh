@@ -154,7 +154,8 @@ struct LargeDev {
   uint4* ll_contrib; // v2 solves: LL slots of the backward contributions (same indexing as contrib)
 };
 void launch_large_level(cudaStream_t st, Ctrl* ctrl, const FrontDev& fd, const LargeDev& ld, const LargeLevel& lv,
-                        int level, const double* sys_static, StatePtrs sp, int use_state_H, const double* dvec);
+                        int level, const double* sys_static, StatePtrs sp, int use_state_H, const double* dvec,
+                        int grid_cap);
 void launch_large_solve_fwd(cudaStream_t st, const Ctrl* ctrl, const FrontDev& fd, const LargeDev& ld,
                             const LargeLevel& lv, const double* rhs_static, StatePtrs sp, int use_state_rhs,
                             unsigned epoch);

@@ -120,7 +120,7 @@ struct sfx_problem {
   DevPool pool;
   cudaStream_t st = nullptr;
   cudaStream_t st2 = nullptr;  // side stream: front zeroing overlaps damping + Schur
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fork2 = nullptr, ev_join2 = nullptr;
   int n_large_fronts = 0;
   unsigned solve_epoch = 0;
   // debug_stats: per-record snapshots of values / residual (allocated on first use)
@@ -172,6 +172,8 @@ struct sfx_problem {
     if (dbg_res) cudaFree(dbg_res);
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
+    if (ev_fork2) cudaEventDestroy(ev_fork2);
+    if (ev_join2) cudaEventDestroy(ev_join2);
     if (h_ctrl) cudaFreeHost(h_ctrl);
     if (h_done) cudaFreeHost(h_done);
   }
@@ -782,7 +784,38 @@ void enqueue_zero_fork(sfx_problem* p) {
 
 // multifrontal Cholesky of the damped system: S (Schur problems; damping already inside) or
 // H[init_idx] + diag(d_dvec)
-void enqueue_factorize(sfx_problem* p) {
+// First level of the chain-bound top of the elimination tree: every level from there up is one large front and no
+// small ones (0 = none).  While those levels factor (their diagonal chain leaves most SMs idle, and one CTA per SM
+// is as fast as two), the forward substitution of everything below can already run on the side stream.
+int chain_top_level(const sfx_problem* p) {
+  const FrontPlan& f = p->a.fp;
+  // measured at Final-shape: the solve phase drops 1.01 -> 0.86 ms but the chain-bound levels slow down by the same
+  // amount (the substitution CTAs share SMs with the diagonal-chain CTAs), so this stays opt-in
+  if (!getenv("SFX_SOLVE_OVERLAP") || getenv("SFX_SOLVE_V1")) return 0;
+  int T = f.n_levels;
+  while (T > 0 && p->lvl_large[T - 1].n_lf == 1 && p->lvl_small_cnt[T - 1] == 0) --T;
+  if (T >= f.n_levels || T == 0) return 0;
+  return T;
+}
+
+void begin_tri_solves(sfx_problem* p) {
+  if (p->n_sflags > 0) CUDA_OK(cudaMemsetAsync(p->ld.sflags, 0, sizeof(int) * p->n_sflags, p->st));
+  if (++p->solve_epoch == 0) p->solve_epoch = 1;  // LL slots of the v2 solves: 0 means "never written"
+}
+
+void enqueue_fwd_levels(sfx_problem* p, cudaStream_t st, int l0, int l1, const double* rhs_static, int use_state_rhs) {
+  const FrontPlan& f = p->a.fp;
+  for (int l = l0; l < l1; ++l) {
+    if (p->lvl_small_cnt[l] > 0)
+      launch_front_solve_fwd(st, p->d_ctrl, p->fd, rhs_static, p->sp, use_state_rhs, f.level_ptr[l],
+                             p->lvl_small_cnt[l], p->lvl_max_m[l] * 8);
+    launch_large_solve_fwd(st, p->d_ctrl, p->fd, p->ld, p->lvl_large[l], rhs_static, p->sp, use_state_rhs, p->solve_epoch);
+  }
+}
+
+// overlap_T > 0: begins the triangular solves too -- the forward substitution of the levels below overlap_T runs on
+// the side stream while the levels from overlap_T up factor (with one CTA per SM); joined before returning
+void enqueue_factorize(sfx_problem* p, int overlap_T = 0, const double* rhs_static = nullptr, int use_state_rhs = 0) {
   Analysis& a = p->a;
   const FrontPlan& f = a.fp;
   const double* sys = a.schur ? p->sd.S : nullptr;
@@ -796,26 +829,29 @@ void enqueue_factorize(sfx_problem* p) {
   launch_large_preassemble(p->st, p->d_ctrl, p->fd, p->ld, sys, p->sp, use_H, dv, p->pre_j0, p->pre_j1, p->damp_j0,
                            p->damp_j1);
   for (int l = 0; l < f.n_levels; ++l) {
+    if (overlap_T > 0 && l == overlap_T) {
+      begin_tri_solves(p);
+      CUDA_OK(cudaEventRecord(p->ev_fork2, p->st));
+      CUDA_OK(cudaStreamWaitEvent(p->st2, p->ev_fork2, 0));
+      enqueue_fwd_levels(p, p->st2, 0, overlap_T, rhs_static, use_state_rhs);
+      CUDA_OK(cudaEventRecord(p->ev_join2, p->st2));
+    }
     if (p->lvl_small_cnt[l] > 0)
       launch_front_factor(p->st, p->d_ctrl, p->fd, sys, p->sp, use_H, dv, f.level_ptr[l], p->lvl_small_cnt[l],
                           p->lvl_max_m[l]);
-    launch_large_level(p->st, p->d_ctrl, p->fd, p->ld, p->lvl_large[l], l, sys, p->sp, use_H, dv);
+    launch_large_level(p->st, p->d_ctrl, p->fd, p->ld, p->lvl_large[l], l, sys, p->sp, use_H, dv,
+                       (overlap_T > 0 && l >= overlap_T) ? 148 : 0);
   }
+  if (overlap_T > 0) CUDA_OK(cudaStreamWaitEvent(p->st, p->ev_join2, 0));
 }
 
 // forward + backward substitution with the current factor; rhs in system scalar order (rhs_static, or
 // the rhs of state block init_idx); the solution is left in fd.ywork (elimination order)
-void enqueue_tri_solves(sfx_problem* p, const double* rhs_static, int use_state_rhs) {
+// fwd_done_below > 0: the forward substitution of the levels below was already enqueued by enqueue_factorize
+void enqueue_tri_solves(sfx_problem* p, const double* rhs_static, int use_state_rhs, int fwd_done_below = 0) {
   const FrontPlan& f = p->a.fp;
-  if (p->n_sflags > 0) CUDA_OK(cudaMemsetAsync(p->ld.sflags, 0, sizeof(int) * p->n_sflags, p->st));
-  if (++p->solve_epoch == 0) p->solve_epoch = 1;  // LL slots of the v2 solves: 0 means "never written"
-  for (int l = 0; l < f.n_levels; ++l) {
-    if (p->lvl_small_cnt[l] > 0)
-      launch_front_solve_fwd(p->st, p->d_ctrl, p->fd, rhs_static, p->sp, use_state_rhs, f.level_ptr[l],
-                             p->lvl_small_cnt[l], p->lvl_max_m[l] * 8);
-    launch_large_solve_fwd(p->st, p->d_ctrl, p->fd, p->ld, p->lvl_large[l], rhs_static, p->sp, use_state_rhs,
-                           p->solve_epoch);
-  }
+  if (fwd_done_below == 0) begin_tri_solves(p);
+  enqueue_fwd_levels(p, p->st, fwd_done_below, f.n_levels, rhs_static, use_state_rhs);
   for (int l = f.n_levels - 1; l >= 0; --l) {
     if (p->lvl_small_cnt[l] > 0)
       launch_front_solve_bwd(p->st, p->d_ctrl, p->fd, f.level_ptr[l], p->lvl_small_cnt[l], p->lvl_max_m[l] * 8);
@@ -848,9 +884,10 @@ void enqueue_solve(sfx_problem* p, const std::function<void(int)>& mark) {
     return;
   }
   (void)f;
-  enqueue_factorize(p);
+  const int T = chain_top_level(p);
+  enqueue_factorize(p, T, a.schur ? p->sd.rhs_red : nullptr, a.schur ? 0 : 1);
   mark(PH_FACTOR);
-  enqueue_tri_solves(p, a.schur ? p->sd.rhs_red : nullptr, a.schur ? 0 : 1);
+  enqueue_tri_solves(p, a.schur ? p->sd.rhs_red : nullptr, a.schur ? 0 : 1, T);
   if (a.schur) {
     launch_unpermute(p->st, p->d_ctrl, p->fd, p->d_y, 1.0);
     if (mg) NCCL_OK(nccl().Broadcast(p->d_y, p->d_y, (size_t)a.sp.reduced_dim, ncclDouble, 0, p->comm->comm, p->st));
@@ -970,6 +1007,8 @@ sfx_status sfx_problem_create(const sfx_problem_desc* desc, sfx_problem** out) {
   CUDA_OK(cudaStreamCreateWithFlags(&p->st2, cudaStreamNonBlocking));
   CUDA_OK(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
+  CUDA_OK(cudaEventCreateWithFlags(&p->ev_fork2, cudaEventDisableTiming));
+  CUDA_OK(cudaEventCreateWithFlags(&p->ev_join2, cudaEventDisableTiming));
   upload_structures(p);
   CUDA_OK(cudaStreamSynchronize(p->st));
   *out = up.release();

@@ -21,6 +21,16 @@
 
 namespace sfx {
 
+// Streams that are far larger than L2 and not re-read soon (E blocks, per-observation point contributions) are
+// written / read with the evict-first hint so they do not push the reused data (camera values, W, point blocks) out
+#ifdef SFX_NO_STREAM_HINTS
+#define SFX_ST_STREAM(p, v) (*(p) = (v))
+#define SFX_LD_STREAM(p) (*(p))
+#else
+#define SFX_ST_STREAM(p, v) __stcs((p), (v))
+#define SFX_LD_STREAM(p) __ldcs(p)
+#endif
+
 int64_t g_launches = 0;  // kernels launched by this library (bench.py reports it)
 
 // ------------------------------------------------------------------------------------------------
@@ -415,7 +425,7 @@ __global__ void __launch_bounds__(kBalThreads, SFX_BAL_MINB) linearize_bal_kerne
     __syncwarp();
     double* dst = b.pbuf + (size_t)(blockIdx.x * kBalThreads + warp * 32) * kPbufStride;
 #pragma unroll
-    for (int i = 0; i < kPbufStride; ++i) dst[i * 32 + lane] = st[i * 32 + lane];
+    for (int i = 0; i < kPbufStride; ++i) SFX_ST_STREAM(dst + i * 32 + lane, st[i * 32 + lane]);
     __syncwarp();
   } else if (valid && !(SKIP & 2)) {
 #pragma unroll
@@ -443,7 +453,7 @@ __global__ void __launch_bounds__(kBalThreads, SFX_BAL_MINB) linearize_bal_kerne
       __syncwarp();
       double* dst = H + off0;
 #pragma unroll
-      for (int i = 0; i < 27; ++i) dst[i * 32 + lane] = st[i * 32 + lane];
+      for (int i = 0; i < 27; ++i) SFX_ST_STREAM(dst + i * 32 + lane, st[i * 32 + lane]);
     } else if (valid) {
       double* dst = H + off;
 #pragma unroll
@@ -1149,7 +1159,7 @@ __global__ void __launch_bounds__(kWThreads, SFX_W_MINB) schur_w_rhs_kernel(cons
     {
       double t[27];
 #pragma unroll
-      for (int i = 0; i < 27; ++i) t[i] = src[i * 32 + lane];
+      for (int i = 0; i < 27; ++i) t[i] = SFX_LD_STREAM(src + i * 32 + lane);
 #pragma unroll
       for (int i = 0; i < 27; ++i) st[i * 32 + lane] = t[i];
     }
@@ -1486,7 +1496,7 @@ __global__ void __launch_bounds__(kGThreads) schur_back_accum_kernel(const Ctrl*
     {
       double t[27];
 #pragma unroll
-      for (int i = 0; i < 27; ++i) t[i] = src[i * 32 + lane];
+      for (int i = 0; i < 27; ++i) t[i] = SFX_LD_STREAM(src + i * 32 + lane);
 #pragma unroll
       for (int i = 0; i < 27; ++i) st[i * 32 + lane] = t[i];
     }

@@ -3,7 +3,7 @@
 bench.py -- LM iterations/sec (linearize + Schur + Cholesky) on synthetic BAL, the metric of
 BASELINE.json, measured on the CUDA path through the C ABI (symforce_b200/lib/libsfx.so).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload final|ladybug|...] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload final|ladybug|pose_graph|...] [--impl reference]
 
 One "step" = one Levenberg-Marquardt iteration (damp -> Schur -> factorize -> solve -> retract ->
 relinearize -> accept/reject) of sym::Optimizer on the workload.
@@ -48,9 +48,29 @@ def parse_args():
     return ap.parse_args()
 
 
+POSE_GRAPH = dict(n_poses=100000, n_loops=20000)  # BASELINE.json configs[4]
+
+
+def make_problem(name):
+    """BAL shapes (Schur path) or `pose_graph` (config E: 100k Pose3 poses, SparseCholeskySolver path, 1 GPU)."""
+    from symforce_b200 import desc as D, problems as P
+
+    if name == "pose_graph":
+        return P.pose_graph_problem(POSE_GRAPH["n_poses"], POSE_GRAPH["n_loops"], params=never_exit_params())
+    return P.bal_problem(name, solver=D.SOLVER_SCHUR, params=never_exit_params())
+
+
 def workload_config(name):
     from symforce_b200 import problems as P
 
+    if name == "pose_graph":
+        return {
+            "workload": f"synthetic Pose3 pose graph: {POSE_GRAPH['n_poses']} poses, {POSE_GRAPH['n_poses'] - 1} odometry + "
+                        f"{POSE_GRAPH['n_loops']} loop-closure BetweenFactorPose3 + 1 PriorFactorPose3, multifrontal "
+                        f"Cholesky on the full Hessian (N = 600,000), DYNAMIC lambda",
+            "n_poses": POSE_GRAPH["n_poses"], "n_loops": POSE_GRAPH["n_loops"],
+            "l2": "inputs larger than L2 (fronts + Hessian ~ 1.8 GB)",
+        }
     s = P.BAL_SHAPES[name]
     return {
         "workload": f"synthetic BAL {name}-shape: {s['n_cams']} cams / {s['n_pts']} pts / {s['n_obs']} obs, "
@@ -126,7 +146,7 @@ def cpu_baseline(workload, max_seconds=40.0):
     from symforce_b200 import desc as D, problems as P
     from tests import oracle_capi as O
 
-    prob = P.bal_problem(workload, solver=D.SOLVER_SCHUR, params=never_exit_params())
+    prob = make_problem(workload)
     t0 = time.time()
     o = O.OracleProblem(prob)
     iters = 0
@@ -145,7 +165,8 @@ def cpu_baseline(workload, max_seconds=40.0):
     it_s = float(np.mean(per_iter))
     return {
         "value": 1.0 / it_s, "unit": UNIT, "cores": 1, "kind": "port",
-        "sample": f"{iters} LM iteration(s) of the {workload}-shape problem on the CPU oracle (Schur + simplicial LDLT on S, "
+        "sample": f"{iters} LM iteration(s) of the {workload} problem on the CPU oracle ("
+                  f"{'simplicial LDLT on H' if workload == 'pose_graph' else 'Schur + simplicial LDLT on S'}, "
                   f"single thread like the reference): {it_s * 1e3:.1f} ms per iteration = linearize "
                   f"{tm['linearize_s'] / max(tm['n_linearize'], 1) * 1e3:.1f} + factorize "
                   f"{tm['factorize_s'] / max(tm['n_factorize'], 1) * 1e3:.1f} + solve "
@@ -190,10 +211,12 @@ def main():
     torch.cuda.set_device(local_rank)
 
     K, W = args.steps, max(args.warmup, 3)
-    shape = P.BAL_SHAPES[args.workload]
+    is_pg = args.workload == "pose_graph"
+    assert not (is_pg and world > 1), "pose graphs are single-GPU (replicas only, SURVEY.md 8e)"
+    shape = None if is_pg else P.BAL_SHAPES[args.workload]
     # multi-GPU: every rank is given the same problem; libsfx shards landmarks + their observations
     # over the ranks and sums the reduced camera system with one NCCL reduce per iteration
-    prob = P.bal_problem(args.workload, solver=D.SOLVER_SCHUR, params=never_exit_params())
+    prob = make_problem(args.workload)
     comm = capi.Comm(rank, world, local_rank) if world > 1 else None
     t0 = time.time()
     gpu = capi.SfxProblem(prob, device=local_rank, rank=rank, world=world, comm=comm)
@@ -260,7 +283,7 @@ def main():
     e2e = K / e2e_s
 
     if rank == 0:
-        n_obs, n_cams, n_pts = shape["n_obs"], shape["n_cams"], shape["n_pts"]
+        n_obs, n_cams, n_pts = (shape["n_obs"], shape["n_cams"], shape["n_pts"]) if shape else (0, 0, 0)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -279,6 +302,8 @@ def main():
             "update": tm["update_ms"] / K}
         # algorithmic work per launch (DESIGN.md section 3 / SURVEY.md 8d)
         lin_bytes = 256 * n_obs + 512 * n_cams + 96 * n_pts
+        if is_pg:  # 688 B per between edge + 272 B per pose
+            lin_bytes = 688 * (POSE_GRAPH["n_poses"] - 1 + POSE_GRAPH["n_loops"]) + 272 * POSE_GRAPH["n_poses"]
         schur_bytes = 216 * n_obs + 72 * n_pts + 432 * n_cams + 8 * 81 * info["s_blocks"]
         fac_flops = float(info["factor_flops"])
         # MEASURED_PEAKS.json has no FP64 figure: the DMMA peak was measured once on this pool's B200 with
@@ -290,7 +315,8 @@ def main():
             fp64_src = "profiles/fp64_peak.json: mma.sync.m8n8k4.f64 peak measured with tools/micro/fp64_peak.cu"
         except Exception:
             pass
-        rl_lin = {"kernel": "linearize_bal_kernel (+zero, point finalize, error reduce)", "bound": "hbm",
+        rl_lin = {"kernel": "linearize_kernel<between/prior> (+zero, error reduce)" if is_pg else
+                            "linearize_bal_kernel (+zero, point finalize, error reduce)", "bound": "hbm",
                   "achieved": lin_bytes / (ph["linearize"] * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                   "traffic": traffic.get("linearize"), "peak_source": hbm_src}
         rl_lin["frac"] = rl_lin["achieved"] / hbm
@@ -298,12 +324,15 @@ def main():
                     "achieved": schur_bytes / (ph["schur"] * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                     "traffic": traffic.get("schur"), "peak_source": hbm_src}
         rl_schur["frac"] = rl_schur["achieved"] / hbm
+        if is_pg:
+            rl_schur = None  # no Schur elimination on this path
         rl_fac = {"kernel": "large_factor_kernel (tile-DAG supernodal Cholesky, DMMA m8n8k4)", "bound": "tensor",
                   "achieved": fac_flops / (ph["factorize"] * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
                   "traffic": traffic.get("large_factor_kernel"),
                   "peak_source": fp64_src}
         rl_fac["frac"] = rl_fac["achieved"] / fp64_peak
-        dominant = max(("factorize", rl_fac), ("schur", rl_schur), ("linearize", rl_lin), key=lambda kv: ph[kv[0]])[1]
+        dominant = max([kv for kv in (("factorize", rl_fac), ("schur", rl_schur), ("linearize", rl_lin)) if kv[1]],
+                       key=lambda kv: ph[kv[0]])[1]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak" if world == 1 else "strong",

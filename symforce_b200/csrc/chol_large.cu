@@ -715,20 +715,24 @@ __global__ void __launch_bounds__(kLargeThreads, 2) large_factor_kernel(Ctrl* ct
 // ---- assembly of large fronts ---------------------------------------------------------------------
 // zeroes the lower-triangular tiles of every large front (column c from the top of its diagonal tile:
 // rows >= c - 63 covers it wherever the tile boundary lies); nothing reads above the diagonal tiles
-__global__ void __launch_bounds__(256) large_zero_kernel(const Ctrl* __restrict__ ctrl, FrontDev fd, LargeDev ld) {
+__global__ void __launch_bounds__(256) large_zero_kernel(const Ctrl* __restrict__ ctrl, FrontDev fd, LargeDev ld, int n_jobs) {
   if (ctrl->done) return;
-  const LargeFront lf = ld.lf[blockIdx.y];
-  double* F = fd.fronts + lf.off;
-  const int m = lf.m;
-  for (int c = blockIdx.x; c < m; c += gridDim.x) {
-    double* col = F + (size_t)c * m;
-    for (int r = max(0, c - 63) + threadIdx.x; r < m; r += 256) col[r] = 0.0;
+  // one job = a run of columns of one front with ~8k entries below the top of their diagonal tiles
+  for (int jb = blockIdx.x; jb < n_jobs; jb += gridDim.x) {
+    const int4 job = ld.zero_jobs[jb];  // {large front, first column, end column, -}
+    const LargeFront lf = ld.lf[job.x];
+    const int m = lf.m;
+    double* F = fd.fronts + lf.off;
+    for (int c = job.y; c < job.z; ++c) {
+      double* col = F + (size_t)c * m;
+      for (int r = max(0, c - 63) + threadIdx.x; r < m; r += 256) col[r] = 0.0;
+    }
   }
 }
-void launch_large_zero(cudaStream_t st, const Ctrl* ctrl, const FrontDev& fd, const LargeDev& ld, int n_lf) {
-  if (n_lf == 0) return;
-  dim3 zg(148, n_lf);
-  large_zero_kernel<<<zg, 256, 0, st>>>(ctrl, fd, ld); ++g_launches;
+void launch_large_zero(cudaStream_t st, const Ctrl* ctrl, const FrontDev& fd, const LargeDev& ld, int n_jobs) {
+  if (n_jobs == 0) return;
+  const int grid = n_jobs < 148 * 8 ? n_jobs : 148 * 8;
+  large_zero_kernel<<<grid, 256, 0, st>>>(ctrl, fd, ld, n_jobs); ++g_launches;
 }
 
 // one warp per job: system-matrix block copy, damping, or a column range of a child's update matrix

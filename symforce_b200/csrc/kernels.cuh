@@ -147,6 +147,7 @@ struct LargeDev {
   int* counters;
   int* queue;  // one head per level
   double* linv;
+  const int4* zero_jobs;  // large_zero_kernel: {large front, first column, end column, 0}
   double* binv;     // inverses of the eight 8x8 diagonal blocks of every L_kk (512 doubles per pivot tile): DIAG -> TRSMs
   int* sflags;      // solve flags / counters (zeroed before every solve)
   double* contrib;  // backward-solve contribution slots (v1 solves)
@@ -164,7 +165,7 @@ void launch_large_solve_bwd(cudaStream_t st, const Ctrl* ctrl, const FrontDev& f
 void launch_large_preassemble(cudaStream_t st, const Ctrl* ctrl, const FrontDev& fd, const LargeDev& ld,
                               const double* sys_static, StatePtrs sp, int use_state_H, const double* dvec, int pre_j0,
                               int pre_j1, int damp_j0, int damp_j1);
-void launch_large_zero(cudaStream_t st, const Ctrl* ctrl, const FrontDev& fd, const LargeDev& ld, int n_lf);
+void launch_large_zero(cudaStream_t st, const Ctrl* ctrl, const FrontDev& fd, const LargeDev& ld, int n_jobs);
 cudaError_t configure_large_kernels();
 
 // launchers (all asynchronous on `st`)

@@ -122,6 +122,7 @@ struct sfx_problem {
   cudaStream_t st2 = nullptr;  // side stream: front zeroing overlaps damping + Schur
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fork2 = nullptr, ev_join2 = nullptr;
   int n_large_fronts = 0;
+  int n_zero_jobs = 0;
   unsigned solve_epoch = 0;
   // debug_stats: per-record snapshots of values / residual (allocated on first use)
   double *dbg_values = nullptr, *dbg_res = nullptr;
@@ -698,6 +699,26 @@ void upload_structures(sfx_problem* p) {
     }
     d.level_fronts = up32(lvl_fronts);
     p->n_large_fronts = (int)lfs.size();
+    {
+      // zeroing jobs: runs of columns with ~8k entries each (small fronts: one job; the 2844-row root: ~500)
+      std::vector<int4> zj;
+      for (size_t q = 0; q < lfs.size(); ++q) {
+        const int m = lfs[q].m;
+        int c0 = 0;
+        while (c0 < m) {
+          int c1 = c0;
+          int64_t el = 0;
+          while (c1 < m && el < 8192) {
+            el += m - std::max(0, c1 - 63);
+            ++c1;
+          }
+          zj.push_back(make_int4((int)q, c0, c1, 0));
+          c0 = c1;
+        }
+      }
+      p->n_zero_jobs = (int)zj.size();
+      p->ld.zero_jobs = P.upload(zj);
+    }
     p->ld.lf = P.upload(lfs);
     p->ld.tasks = P.upload(tasks);
     p->pre_j0 = (int)jobs.size();
@@ -778,7 +799,7 @@ void enqueue_zero_fork(sfx_problem* p) {
   if (p->n_large_fronts == 0) return;
   CUDA_OK(cudaEventRecord(p->ev_fork, p->st));
   CUDA_OK(cudaStreamWaitEvent(p->st2, p->ev_fork, 0));
-  launch_large_zero(p->st2, p->d_ctrl, p->fd, p->ld, p->n_large_fronts);
+  launch_large_zero(p->st2, p->d_ctrl, p->fd, p->ld, p->n_zero_jobs);
   CUDA_OK(cudaEventRecord(p->ev_join, p->st2));
 }
 

@@ -186,7 +186,7 @@ def run_reference(args):
     line = {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / cb["value"], "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
         "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -335,7 +335,7 @@ def main():
                        key=lambda kv: ph[kv[0]])[1]
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
-            "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "weak" if world == 1 else "strong",
+            "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "strong",  # one fixed problem sharded over N GPUs
             "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
             "config": dict(workload_config(args.workload),

@@ -1697,12 +1697,16 @@ __global__ void __launch_bounds__(kFrontThreads) front_factor_kernel(Ctrl* ctrl,
   }
 }
 
+// Threads per CTA of the one-CTA-per-front kernels: levels of tiny fronts (pose-graph leaves: 6 pivots, a few dozen
+// rows) run more fronts per SM with 64 or 128 threads than with 256 mostly idle ones
+static int small_front_threads(int max_m) { return max_m <= 32 ? 64 : max_m <= 64 ? 128 : kFrontThreads; }
+
 void launch_front_factor(cudaStream_t st, Ctrl* ctrl, const FrontDev& fd, const double* sysvals_static, StatePtrs sp,
                          int use_state_H, const double* dvec, int lvl_begin, int lvl_count, int smem_m_max) {
   // smem_m_max: fronts with m <= smem_m_max are factored in shared memory (chosen per launch)
   const size_t smem = (size_t)smem_m_max * smem_m_max * sizeof(double);
-  front_factor_kernel<<<lvl_count, kFrontThreads, smem, st>>>(ctrl, fd, sysvals_static, sp, use_state_H, dvec,
-                                                              lvl_begin, smem_m_max); ++g_launches;
+  front_factor_kernel<<<lvl_count, small_front_threads(smem_m_max), smem, st>>>(ctrl, fd, sysvals_static, sp, use_state_H,
+                                                                                dvec, lvl_begin, smem_m_max); ++g_launches;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1778,12 +1782,14 @@ __global__ void __launch_bounds__(kFrontThreads) front_solve_bwd_kernel(const Ct
 
 void launch_front_solve_fwd(cudaStream_t st, const Ctrl* ctrl, const FrontDev& fd, const double* rhs_static,
                             StatePtrs sp, int use_state_rhs, int lvl_begin, int lvl_count, int smem_bytes) {
-  front_solve_fwd_kernel<<<lvl_count, kFrontThreads, smem_bytes, st>>>(ctrl, fd, rhs_static, sp, use_state_rhs,
-                                                                        lvl_begin); ++g_launches;
+  front_solve_fwd_kernel<<<lvl_count, small_front_threads(smem_bytes / 8), smem_bytes, st>>>(
+      ctrl, fd, rhs_static, sp, use_state_rhs, lvl_begin);
+  ++g_launches;
 }
 void launch_front_solve_bwd(cudaStream_t st, const Ctrl* ctrl, const FrontDev& fd, int lvl_begin, int lvl_count,
                             int smem_bytes) {
-  front_solve_bwd_kernel<<<lvl_count, kFrontThreads, smem_bytes, st>>>(ctrl, fd, lvl_begin); ++g_launches;
+  front_solve_bwd_kernel<<<lvl_count, small_front_threads(smem_bytes / 8), smem_bytes, st>>>(ctrl, fd, lvl_begin);
+  ++g_launches;
 }
 // opt in to large dynamic shared memory (process-wide maxima; launches pass their own size)
 cudaError_t configure_front_kernels(int smem_m_max, int max_front) {

@@ -8,6 +8,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <exception>
+#include <thread>
 #include <map>
 #include <numeric>
 #include <type_traits>
@@ -68,6 +70,33 @@ static void stable_order_by_key(const std::vector<uint64_t>& keys, std::vector<u
     }
     order.swap(tmp);
   }
+}
+
+// fn(begin, end) over [0, n) on up to 8 host threads (the per-slot index building of a 5 M-factor problem is bound by
+// cache misses on the caller's arrays); exceptions thrown by a chunk are rethrown on the calling thread
+template <typename Fn>
+static void parallel_chunks(int64_t n, const Fn& fn) {
+  const int64_t min_chunk = 1 << 16;
+  int nt = (int)std::min<int64_t>(std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency())),
+                                  (n + min_chunk - 1) / min_chunk);
+  if (getenv("SFX_HOST_THREADS")) nt = std::max(1, atoi(getenv("SFX_HOST_THREADS")));
+  if (nt <= 1) {
+    fn((int64_t)0, n);
+    return;
+  }
+  std::vector<std::thread> th;
+  std::vector<std::exception_ptr> err(nt);
+  for (int t = 0; t < nt; ++t)
+    th.emplace_back([&, t] {
+      try {
+        fn(n * t / nt, n * (t + 1) / nt);
+      } catch (...) {
+        err[t] = std::current_exception();
+      }
+    });
+  for (auto& x : th) x.join();
+  for (auto& e : err)
+    if (e) std::rethrow_exception(e);
 }
 
 static inline uint64_t mix64(uint64_t x) {
@@ -364,36 +393,47 @@ void analyze_problem(const sfx_problem_desc& d, Analysis& a) {
     bp.diag_off.resize((size_t)ng * n);
     bp.off_off.resize((size_t)npairs * n);
     bp.factor_index.resize(n);
-    for (int s = 0; s < n; ++s) {
-      const FactorRef& fr = plan_factors[pl][s];
+    // group dims from the first slot (checked against every slot below)
+    if (n > 0) {
+      const FactorRef& fr = plan_factors[pl][0];
       const sfx_factor_batch& fb = d.batches[fr.batch];
-      const int f = fr.idx;
-      const int fi = fb.factor_index[f];
-      bp.factor_index[s] = fi;
-      bp.res_off[s] = res_off_of_factor[fi];
-      for (int u = 0; u < bp.n_used_args; ++u)
-        bp.arg_off[(size_t)u * n + s] = fb.arg_offsets[(int64_t)bp.used_args[u] * fb.n + f];
-      int gnode[kMaxGroups];
       for (int o = 0; o < km.n_opt; ++o)
-        if (pk.grp[o] >= 0) gnode[pk.grp[o]] = a.keys[fb.opt_keys[(int64_t)o * fb.n + f]].node;
-      for (int g = 0; g < ng; ++g) {
-        if (s == 0) bp.group_dim[g] = a.nodes[gnode[g]].dim;
-        SFX_CHECK(bp.group_dim[g] == a.nodes[gnode[g]].dim, SFX_ERR_STRUCTURE, "non-uniform node dims inside a batch");
-        bp.rhs_off[(size_t)g * n + s] = a.nodes[gnode[g]].toff;
-      }
-      int pair = 0;
-      for (int g = 1; g < ng; ++g)
-        for (int h = 0; h < g; ++h, ++pair) {
-          int I = gnode[g], J = gnode[h];
-          uint32_t tr = 0;
-          if (I < J) {
-            std::swap(I, J);
-            tr = 1;
-          }
-          contribs.push_back(Contrib{((uint64_t)J << 32) | (uint32_t)I, (int)pl, s, pair, tr});
-        }
+        if (pk.grp[o] >= 0) bp.group_dim[pk.grp[o]] = a.nodes[a.keys[fb.opt_keys[(int64_t)o * fb.n + fr.idx]].node].dim;
     }
+    const size_t c_base = contribs.size();
+    contribs.resize(c_base + (size_t)n * npairs);  // (plan, slot, pair) order, filled by the chunks below
+    parallel_chunks(n, [&](int64_t s_begin, int64_t s_end) {
+      for (int s = (int)s_begin; s < (int)s_end; ++s) {
+        const FactorRef& fr = plan_factors[pl][s];
+        const sfx_factor_batch& fb = d.batches[fr.batch];
+        const int f = fr.idx;
+        const int fi = fb.factor_index[f];
+        bp.factor_index[s] = fi;
+        bp.res_off[s] = res_off_of_factor[fi];
+        for (int u = 0; u < bp.n_used_args; ++u)
+          bp.arg_off[(size_t)u * n + s] = fb.arg_offsets[(int64_t)bp.used_args[u] * fb.n + f];
+        int gnode[kMaxGroups];
+        for (int o = 0; o < km.n_opt; ++o)
+          if (pk.grp[o] >= 0) gnode[pk.grp[o]] = a.keys[fb.opt_keys[(int64_t)o * fb.n + f]].node;
+        for (int g = 0; g < ng; ++g) {
+          SFX_CHECK(bp.group_dim[g] == a.nodes[gnode[g]].dim, SFX_ERR_STRUCTURE, "non-uniform node dims inside a batch");
+          bp.rhs_off[(size_t)g * n + s] = a.nodes[gnode[g]].toff;
+        }
+        int pair = 0;
+        for (int g = 1; g < ng; ++g)
+          for (int h = 0; h < g; ++h, ++pair) {
+            int I = gnode[g], J = gnode[h];
+            uint32_t tr = 0;
+            if (I < J) {
+              std::swap(I, J);
+              tr = 1;
+            }
+            contribs[c_base + (size_t)s * npairs + pair] = Contrib{((uint64_t)J << 32) | (uint32_t)I, (int)pl, s, pair, tr};
+          }
+      }
+    });
   }
+  clk.lap("  contribs built");
   // sort contributions by block; stable so that slot order is kept inside a block
   std::vector<uint32_t> order;
   {
@@ -401,6 +441,7 @@ void analyze_problem(const sfx_problem_desc& d, Analysis& a) {
     for (size_t i = 0; i < contribs.size(); ++i) ck[i] = contribs[i].key;
     stable_order_by_key(ck, order);
   }
+  clk.lap("  contribs sorted");
   // unique blocks with contributor counts
   std::vector<uint64_t> blk_key;
   std::vector<int> blk_cnt;
@@ -414,6 +455,7 @@ void analyze_problem(const sfx_problem_desc& d, Analysis& a) {
     blk_cnt.back()++;
     contrib_blk[order[i]] = (int)blk_key.size() - 1;
   }
+  clk.lap("  unique blocks");
   // Block matrix structure: per column, diagonal first then sorted off-diagonal rows
   BlockMatrix& H = a.H;
   H.n_nodes = nn;
@@ -451,6 +493,7 @@ void analyze_problem(const sfx_problem_desc& d, Analysis& a) {
                 "Submatrix C of A is not block diagonal, cannot use a Schur complement solver");
     }
   }
+  clk.lap("  block matrix");
   // value offsets: [reduced diag | all reduced-reduced off-diag] (= B, summed across ranks in the
   // multi-GPU path) | landmark diag | shared landmark-reduced blocks || exclusive blocks in
   // (plan, slot, pair) order so that a thread's stores are contiguous.  Everything before `||`
@@ -502,8 +545,7 @@ void analyze_problem(const sfx_problem_desc& d, Analysis& a) {
     bp.off_off[(size_t)ct.pair * bp.n + ct.slot] = v;
   }
   {
-    std::unordered_map<int, int> toff2node;
-    toff2node.reserve(nn * 2);
+    std::vector<int> toff2node(a.N + 1, -1);  // tangent offset of a node -> node
     for (int i = 0; i < nn; ++i) toff2node[a.nodes[i].toff] = i;
     for (auto& bp : a.batches)
       for (size_t i = 0; i < bp.rhs_off.size(); ++i)
@@ -584,6 +626,7 @@ void analyze_problem(const sfx_problem_desc& d, Analysis& a) {
     for (int l = 0; l < nl; ++l) sp.lm_e_ptr[l + 1] = sp.lm_e_ptr[l] + (all_ptr[lm0 + l + 1] - all_ptr[lm0 + l]);
     sp.lm_e_off.assign(all_off.begin() + all_ptr[lm0], all_off.begin() + all_ptr[lm0 + nl]);
     sp.lm_e_node.assign(all_node.begin() + all_ptr[lm0], all_node.begin() + all_ptr[lm0 + nl]);
+  clk.lap("  E lists");
     // reduced rhs lists (per reduced node: E blocks of its column that belong to own landmarks)
     sp.r_ptr.assign(nr + 1, 0);
     for (int j = 0; j < nr; ++j) {
@@ -607,6 +650,7 @@ void analyze_problem(const sfx_problem_desc& d, Analysis& a) {
         }
       }
     }
+  clk.lap("  rhs lists");
     // S pattern: B blocks + all pairs (I >= J) of reduced nodes adjacent to a common landmark (ANY
     // rank's landmark, so the pattern is the same everywhere); matches only for own landmarks
     struct Match {
@@ -638,16 +682,22 @@ void analyze_problem(const sfx_problem_desc& d, Analysis& a) {
         skeys.erase(std::unique(skeys.begin(), skeys.end()), skeys.end());
       }
     }
+    clk.lap("  matches built");
     {
+      // stable sort by (column J, row I): two counting passes over the nr node buckets (row first, then column)
       SFX_CHECK(matches.size() < (size_t)UINT32_MAX, SFX_ERR_UNSUPPORTED, "too many Schur matches");
-      std::vector<uint64_t> mk(matches.size());
-      for (size_t i = 0; i < matches.size(); ++i) mk[i] = matches[i].key;
-      std::vector<uint32_t> mo;
-      stable_order_by_key(mk, mo);
       std::vector<Match> sorted(matches.size());
-      for (size_t i = 0; i < mo.size(); ++i) sorted[i] = matches[mo[i]];
-      matches.swap(sorted);
+      std::vector<size_t> start(nr + 1);
+      for (int pass = 0; pass < 2; ++pass) {
+        const int shift = pass == 0 ? 0 : 32;
+        std::fill(start.begin(), start.end(), 0);
+        for (const Match& m : matches) start[((m.key >> shift) & 0xffffffffu) + 1]++;
+        for (int j = 0; j < nr; ++j) start[j + 1] += start[j];
+        for (const Match& m : matches) sorted[start[(m.key >> shift) & 0xffffffffu]++] = m;
+        matches.swap(sorted);  // after the second pass `matches` is sorted by (column, row), ties in landmark order
+      }
     }
+  clk.lap("  matches built+sorted");
     // merged column structure
     for (int j = 0; j < nr; ++j)
       for (int p = H.col_ptr[j]; p < H.col_ptr[j + 1]; ++p)
@@ -662,6 +712,7 @@ void analyze_problem(const sfx_problem_desc& d, Analysis& a) {
     }
     std::sort(skeys.begin(), skeys.end());
     skeys.erase(std::unique(skeys.begin(), skeys.end()), skeys.end());
+  clk.lap("  skeys");
     BlockMatrix& S = sp.S;
     S.n_nodes = nr;
     S.node_dim.assign(H.node_dim.begin(), H.node_dim.begin() + nr);
@@ -683,6 +734,7 @@ void analyze_problem(const sfx_problem_desc& d, Analysis& a) {
     for (int j = 0; j < nr; ++j)
       for (int p = H.col_ptr[j]; p < H.col_ptr[j + 1]; ++p)
         if (H.row_idx[p] < first_lm_node) sp.s_b_src[S.find(H.row_idx[p], j)] = (int32_t)H.blk_off[p];
+  clk.lap("  S structure");
     sp.s_m_ptr.assign(skeys.size() + 1, 0);
     sp.m_eoff_i.resize(matches.size());
     sp.m_eoff_j.resize(matches.size());

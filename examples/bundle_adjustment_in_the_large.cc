@@ -6,6 +6,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
+#include <algorithm>
 #include <array>
 #include <random>
 #include <string>
@@ -85,13 +86,27 @@ static Problem SyntheticProblem(int cams, int pts, int per_pt) {
   for (int j = 0; j < pts; j++) truth_pt.emplace_back(10 * u(gen), 10 * u(gen), 20 + 10 * u(gen));
   int obs = 0;
   std::vector<std::array<int, 2>> pairs;
-  for (int c = 0; c < cams; c++)
-    for (int j = 0; j < pts; j++) {
-      const int centre = (int)((long long)j * cams / pts);
-      int d = std::abs(c - centre);
-      d = std::min(d, cams - d);
-      if (d <= per_pt / 2) pairs.push_back({c, j});
+  // camera-major list of (camera, point) with |camera - centre(point)| <= per_pt / 2 on the ring of cameras, points in
+  // ascending order per camera; built from per-centre buckets (O(observations), not O(cameras x points))
+  {
+    std::vector<std::vector<int>> by_centre(cams);
+    for (int j = 0; j < pts; j++) by_centre[(int)((long long)j * cams / pts)].push_back(j);
+    const int half = per_pt / 2;
+    for (int c = 0; c < cams; c++) {
+      std::vector<int> mine;
+      for (int dd = -half; dd <= half; dd++) {
+        const int centre = ((c + dd) % cams + cams) % cams;
+        int d = std::abs(c - centre);
+        d = std::min(d, cams - d);
+        if (d > half) continue;  // (tiny rings: the same centre must not be taken twice)
+        bool dup = false;
+        for (int e = -half; e < dd; e++) dup = dup || (((c + e) % cams + cams) % cams) == centre;
+        if (!dup) mine.insert(mine.end(), by_centre[centre].begin(), by_centre[centre].end());
+      }
+      std::sort(mine.begin(), mine.end());
+      for (int j : mine) pairs.push_back({c, j});
     }
+  }
   for (auto& cj : pairs) {
     const int c = cj[0], j = cj[1];
     const Eigen::Vector3d pc = truth_pose[c].Rotation().Rotate(truth_pt[j]);

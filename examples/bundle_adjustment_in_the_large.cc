@@ -147,11 +147,13 @@ int main(int argc, char** argv) {
   }
   std::printf("Created problem with %d cameras, %d points, %d observations\n", problem.num_cameras, problem.num_points,
               problem.num_observations);
+  std::fflush(stdout);
   sym::Valuesd optimized_values = problem.values;
   auto params = sym::DefaultOptimizerParams();
   params.lambda_update_type = sym::lambda_update_type_t::DYNAMIC;
   // keys c.., i.., p.. (lexical): the trailing points are eliminated by the GPU Schur path (AUTO)
   const double build_s = seconds_since(t_start);
+  std::fprintf(stderr, "[host] factor list + Values built in %.2f s\n", build_s);
   sym::Optimizerd optimizer{params, std::move(problem.factors)};
   const auto t_opt = std::chrono::steady_clock::now();
   const auto stats = optimizer.Optimize(optimized_values);

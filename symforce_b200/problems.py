@@ -257,6 +257,8 @@ def bal_structure(n_cams, n_pts, n_obs, window, seed=0xBA1):
     while diff != 0:
         step = 1 if diff > 0 else -1
         cand = np.flatnonzero((k + step >= 0) & (k + step <= slots - 2))
+        if cand.shape[0] == 0:
+            raise ValueError("n_obs=%d cannot be realised with %d points and tracks of 2..%d cameras" % (n_obs, n_pts, slots))
         pick = rng.choice(cand, size=min(abs(diff), cand.shape[0]), replace=False)
         k[pick] += step
         diff = int(n_extra - k.sum())

@@ -75,6 +75,37 @@ def test_host_maps_reproduce_oracle(name):
     assert np.allclose(upd, upd_o, rtol=1e-8, atol=1e-9 * max(1e-3, np.abs(upd_o).max()))
 
 
+@pytest.mark.parametrize("seed", range(6))
+def test_host_maps_random_bal_shapes(seed, monkeypatch):
+    """Ragged BAL structures (random camera / point counts and track lengths, windows wider than the camera ring) through
+    the same host-vs-oracle replay, with the per-slot index building forced onto several host threads."""
+    rng = np.random.default_rng(1000 + seed)
+    n_cams = int(rng.integers(3, 12))
+    n_pts = int(rng.integers(4 * n_cams, 70))
+    window = int(rng.integers(1, n_cams + 3))
+    slots = 2 * min(window, (n_cams - 1) // 2) + 1  # longest track P.bal_structure can draw
+    n_obs = int(rng.integers(2 * n_pts, slots * n_pts + 1))
+    monkeypatch.setenv("SFX_HOST_THREADS", str(int(rng.integers(1, 5))))
+    solver = D.SOLVER_SCHUR if seed % 2 == 0 else D.SOLVER_CHOLESKY
+    for structure_seed in range(seed, seed + 600, 100):  # every camera must be observed at least once
+        prob = P.bal_problem(n_cams=n_cams, n_pts=n_pts, n_obs=n_obs, window=window, solver=solver,
+                             seed_structure=structure_seed)
+        if len(np.unique(prob.meta["cam"])) == n_cams:
+            break
+    else:
+        pytest.fail("no structure seed observes every camera")
+    A = capi.analysis_json(prob)
+    o = O.OracleProblem(prob)
+    outer, inner = o.hessian_pattern()
+    assert np.array_equal(outer, np.array(A["csc_outer"])) and np.array_equal(inner, np.array(A["csc_inner"]))
+    upd, (res, rhs, H) = E.emulate_solve_step(prob, A, 0.5)
+    res_o, rhs_o, H_o = o.linearize()
+    assert np.allclose(H, H_o, rtol=0, atol=1e-12 * max(1.0, np.abs(H_o).max()))
+    assert np.allclose(rhs, rhs_o, rtol=0, atol=1e-11 * max(1.0, np.abs(rhs_o).max()))
+    upd_o = o.solve_step(0.5)
+    assert np.allclose(upd, upd_o, rtol=1e-8, atol=1e-9 * max(1e-3, np.abs(upd_o).max()))
+
+
 def test_bal_nodes_merge_pose_and_intrinsics():
     prob = P.bal_problem("tiny", solver=D.SOLVER_SCHUR)
     A = capi.analysis_json(prob)

@@ -4,6 +4,7 @@
 //   keys -> nodes, block-sparse Hessian layout in HBM, per-factor scatter indices,
 //   Schur match lists, CSC export map (reference layout of Linearization::hessian_lower).
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -11,6 +12,7 @@
 #include <exception>
 #include <thread>
 #include <map>
+#include <memory>
 #include <numeric>
 #include <type_traits>
 #include <unordered_map>
@@ -42,15 +44,14 @@ int BlockMatrix::find(int row, int col) const {
 // order[] = stable ascending order of keys[]: LSD radix sort with 16-bit digits (digits on which all keys agree are
 // skipped).  Replaces std::stable_sort with an indirect comparator on the 5 M contributions / 16.6 M Schur matches of
 // a Final-shape BAL problem (2.9 s -> 0.5 s of the host analysis).
-static void stable_order_by_key(const std::vector<uint64_t>& keys, std::vector<uint32_t>& order) {
-  const size_t n = keys.size();
+static void stable_order_by_key(const uint64_t* keys, size_t n, std::vector<uint32_t>& order) {
   order.resize(n);
   std::iota(order.begin(), order.end(), 0u);
-  if (n < 2) return;
+  if (n < 2 || std::is_sorted(keys, keys + n)) return;  // BAL files list observations by (camera, point)
   uint64_t all_or = 0, all_and = ~0ull;
-  for (uint64_t k : keys) {
-    all_or |= k;
-    all_and &= k;
+  for (size_t i = 0; i < n; ++i) {
+    all_or |= keys[i];
+    all_and &= keys[i];
   }
   std::vector<uint32_t> tmp(n);
   std::vector<size_t> cnt(1 << 16);
@@ -72,32 +73,65 @@ static void stable_order_by_key(const std::vector<uint64_t>& keys, std::vector<u
   }
 }
 
-// fn(begin, end) over [0, n) on up to 8 host threads (the per-slot index building of a 5 M-factor problem is bound by
-// cache misses on the caller's arrays); exceptions thrown by a chunk are rethrown on the calling thread
-template <typename Fn>
-static void parallel_chunks(int64_t n, const Fn& fn) {
-  const int64_t min_chunk = 1 << 16;
+// Host threads for `n` work items of which a thread should get at least `min_chunk`: up to 8 (the index building of a
+// 5 M-factor problem is bound by cache misses on the caller's arrays), SFX_HOST_THREADS overrides.
+static int host_threads(int64_t n, int64_t min_chunk) {
   int nt = (int)std::min<int64_t>(std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency())),
                                   (n + min_chunk - 1) / min_chunk);
-  if (getenv("SFX_HOST_THREADS")) nt = std::max(1, atoi(getenv("SFX_HOST_THREADS")));
+  if (getenv("SFX_HOST_THREADS")) nt = atoi(getenv("SFX_HOST_THREADS"));
+  return std::max(1, nt);
+}
+
+// fn(t) for t in [0, nt) on nt threads (the caller's thread runs t = 0); exceptions thrown by a thread are rethrown
+// on the calling thread
+template <typename Fn>
+static void run_threads(int nt, const Fn& fn) {
   if (nt <= 1) {
-    fn((int64_t)0, n);
+    fn(0);
     return;
   }
   std::vector<std::thread> th;
   std::vector<std::exception_ptr> err(nt);
-  for (int t = 0; t < nt; ++t)
-    th.emplace_back([&, t] {
-      try {
-        fn(n * t / nt, n * (t + 1) / nt);
-      } catch (...) {
-        err[t] = std::current_exception();
-      }
-    });
+  auto body = [&](int t) {
+    try {
+      fn(t);
+    } catch (...) {
+      err[t] = std::current_exception();
+    }
+  };
+  for (int t = 1; t < nt; ++t) th.emplace_back(body, t);
+  body(0);
   for (auto& x : th) x.join();
   for (auto& e : err)
     if (e) std::rethrow_exception(e);
 }
+
+// fn(begin, end) over contiguous chunks of [0, n)
+template <typename Fn>
+static void parallel_chunks(int64_t n, const Fn& fn) {
+  const int nt = host_threads(n, 1 << 16);
+  run_threads(nt, [&](int t) { fn(n * t / nt, n * (t + 1) / nt); });
+}
+
+// Uninitialised array of a trivial type: std::vector would zero-fill hundreds of MB on one thread before the host
+// threads overwrite every element (and take the page faults in parallel)
+template <typename T>
+struct RawBuf {
+  static_assert(std::is_trivially_copyable<T>::value, "RawBuf holds trivial types");
+  std::unique_ptr<T[]> p;
+  size_t n = 0;
+  RawBuf() = default;
+  explicit RawBuf(size_t n_) : p(new T[n_]), n(n_) {}
+  T* data() { return p.get(); }
+  const T* data() const { return p.get(); }
+  size_t size() const { return n; }
+  T& operator[](size_t i) { return p[i]; }
+  const T& operator[](size_t i) const { return p[i]; }
+  void reset() {
+    p.reset();
+    n = 0;
+  }
+};
 
 static inline uint64_t mix64(uint64_t x) {
   x += 0x9e3779b97f4a7c15ull;
@@ -158,29 +192,33 @@ void analyze_problem(const sfx_problem_desc& d, Analysis& a) {
   }
   SFX_CHECK(total == d.n_factors, SFX_ERR_INVALID_ARG, "n_factors != sum of batch sizes");
 
+  // per key: order-independent signature of the set of factors that optimize it (sums of hashes, accumulated with
+  // relaxed atomic adds from all host threads: integer addition commutes, so the result does not depend on the schedule)
   std::vector<uint64_t> h1(nk, 0), h2(nk, 0);
   std::vector<int> cnt(nk, 0);
   for (int b = 0; b < d.n_batches; ++b) {
     const sfx_factor_batch& fb = d.batches[b];
     const sfx_kind_meta& km = SFX_KIND_META[fb.kind];
-    for (int o = 0; o < km.n_opt; ++o)
-      for (int f = 0; f < fb.n; ++f) {
-        int key = fb.opt_keys[(int64_t)o * fb.n + f];
-        if (key < 0) continue;
-        SFX_CHECK(key < nk, SFX_ERR_INVALID_ARG, "opt key index out of range");
-        SFX_CHECK(a.keys[key].tdim == km.opt_dims[o], SFX_ERR_INVALID_ARG, "tangent dim of key does not match factor");
-        uint64_t fi = (uint64_t)fb.factor_index[f];
-        h1[key] += mix64(fi);
-        h2[key] += mix64(fi ^ 0x5bd1e995deadbeefull);
-        cnt[key]++;
-      }
-    for (int ar = 0; ar < km.n_args; ++ar)
-      if (km.arg_used[ar])
-        for (int f = 0; f < fb.n; ++f) {
-          int off = fb.arg_offsets[(int64_t)ar * fb.n + f];
-          SFX_CHECK(off >= 0 && (int64_t)off + km.arg_dims[ar] <= d.n_values, SFX_ERR_INVALID_ARG,
-                    "factor argument outside the values buffer");
+    parallel_chunks(fb.n, [&](int64_t f0, int64_t f1) {
+      for (int o = 0; o < km.n_opt; ++o)
+        for (int64_t f = f0; f < f1; ++f) {
+          int key = fb.opt_keys[(int64_t)o * fb.n + f];
+          if (key < 0) continue;
+          SFX_CHECK(key < nk, SFX_ERR_INVALID_ARG, "opt key index out of range");
+          SFX_CHECK(a.keys[key].tdim == km.opt_dims[o], SFX_ERR_INVALID_ARG, "tangent dim of key does not match factor");
+          uint64_t fi = (uint64_t)fb.factor_index[f];
+          __atomic_fetch_add(&h1[key], mix64(fi), __ATOMIC_RELAXED);
+          __atomic_fetch_add(&h2[key], mix64(fi ^ 0x5bd1e995deadbeefull), __ATOMIC_RELAXED);
+          __atomic_fetch_add(&cnt[key], 1, __ATOMIC_RELAXED);
         }
+      for (int ar = 0; ar < km.n_args; ++ar)
+        if (km.arg_used[ar])
+          for (int64_t f = f0; f < f1; ++f) {
+            int off = fb.arg_offsets[(int64_t)ar * fb.n + f];
+            SFX_CHECK(off >= 0 && (int64_t)off + km.arg_dims[ar] <= d.n_values, SFX_ERR_INVALID_ARG,
+                      "factor argument outside the values buffer");
+          }
+    });
   }
   for (int k = 0; k < nk; ++k)
     if (cnt[k] == 0)
@@ -243,7 +281,6 @@ void analyze_problem(const sfx_problem_desc& d, Analysis& a) {
              std::tie(o.kind, o.grp[0], o.grp[1], o.grp[2], o.sub[0], o.sub[1], o.sub[2]);
     }
   };
-  std::map<PatternKey, int> pat2plan;
   std::vector<std::vector<FactorRef>> plan_factors;
   std::vector<PatternKey> plan_pat;
   // residual offsets in caller order
@@ -256,11 +293,11 @@ void analyze_problem(const sfx_problem_desc& d, Analysis& a) {
     }
     a.M = r;
   }
-  for (int fi = 0; fi < d.n_factors; ++fi) {
+  // pattern of one factor: which of its optimized keys fall into the same node (group) and where inside it
+  auto pattern_of = [&](int fi, PatternKey& pk) {
     const sfx_factor_batch& fb = d.batches[fref[fi].batch];
     const sfx_kind_meta& km = SFX_KIND_META[fb.kind];
     const int f = fref[fi].idx;
-    PatternKey pk;
     pk.kind = fb.kind;
     int nodes_seen[SFX_MAX_OPT];
     int ng = 0;
@@ -290,17 +327,41 @@ void analyze_problem(const sfx_problem_desc& d, Analysis& a) {
       pk.grp[o] = g;
       pk.sub[o] = a.keys[key].sub;
     }
-    auto it = pat2plan.find(pk);
-    int plan;
-    if (it == pat2plan.end()) {
-      plan = (int)plan_factors.size();
-      pat2plan[pk] = plan;
-      plan_factors.emplace_back();
-      plan_pat.push_back(pk);
-    } else {
-      plan = it->second;
+  };
+  // (1) packed pattern of every factor, on all host threads (the key -> node lookups miss the cache);
+  // (2) serial pass in caller order: plans are numbered by first appearance, slots keep the caller's order
+  static_assert(SFX_MAX_OPT == 3 && kMaxNodeDim <= 255 && SFX_NUM_KINDS <= 255, "pattern packing");
+  RawBuf<uint64_t> fpat(d.n_factors);
+  parallel_chunks(d.n_factors, [&](int64_t f0, int64_t f1) {
+    PatternKey pk;
+    for (int64_t fi = f0; fi < f1; ++fi) {
+      pattern_of((int)fi, pk);
+      uint64_t v = (uint64_t)pk.kind;
+      for (int o = 0; o < SFX_MAX_OPT; ++o) v = (v << 11) | ((uint64_t)(pk.grp[o] + 2) << 8) | (uint64_t)pk.sub[o];
+      fpat[fi] = v;
     }
-    plan_factors[plan].push_back(fref[fi]);
+  });
+  {
+    std::map<uint64_t, int> packed2plan;
+    uint64_t last_pat = ~0ull;
+    int last_plan = -1;
+    for (int fi = 0; fi < d.n_factors; ++fi) {
+      if (fpat[fi] != last_pat) {
+        last_pat = fpat[fi];
+        auto it = packed2plan.find(last_pat);
+        if (it == packed2plan.end()) {
+          last_plan = (int)plan_factors.size();
+          packed2plan[last_pat] = last_plan;
+          plan_factors.emplace_back();
+          PatternKey pk;
+          pattern_of(fi, pk);
+          plan_pat.push_back(pk);
+        } else {
+          last_plan = it->second;
+        }
+      }
+      plan_factors[last_plan].push_back(fref[fi]);
+    }
   }
 
   clk.lap("batch plans");
@@ -345,16 +406,16 @@ void analyze_problem(const sfx_problem_desc& d, Analysis& a) {
   if (a.world > 1)
     for (size_t pl = 0; pl < plan_factors.size(); ++pl) {
       auto& v = plan_factors[pl];
-      std::vector<int> own(v.size());
-      for (size_t i = 0; i < v.size(); ++i) own[i] = owner_of(v[i]);
-      std::vector<size_t> idx(v.size());
-      std::iota(idx.begin(), idx.end(), (size_t)0);
-      std::stable_sort(idx.begin(), idx.end(), [&](size_t x, size_t y) { return own[x] < own[y]; });
+      RawBuf<int> own(v.size());
+      parallel_chunks((int64_t)v.size(), [&](int64_t i0, int64_t i1) {
+        for (int64_t i = i0; i < i1; ++i) own[i] = owner_of(v[i]);
+      });
+      // stable counting sort of the slots by owner rank
+      for (size_t i = 0; i < v.size(); ++i) plan_rank_begin[pl][own[i] + 1]++;
+      std::vector<size_t> cursor(a.world, 0);
+      for (int r = 1; r < a.world; ++r) cursor[r] = cursor[r - 1] + plan_rank_begin[pl][r];
       std::vector<FactorRef> sorted(v.size());
-      for (size_t i = 0; i < v.size(); ++i) {
-        sorted[i] = v[idx[i]];
-        plan_rank_begin[pl][own[idx[i]] + 1]++;
-      }
+      for (size_t i = 0; i < v.size(); ++i) sorted[cursor[own[i]]++] = v[i];
       for (int r = 0; r < a.world; ++r) plan_rank_begin[pl][r + 1] += plan_rank_begin[pl][r];
       v.swap(sorted);
     }
@@ -367,7 +428,14 @@ void analyze_problem(const sfx_problem_desc& d, Analysis& a) {
     int plan, slot, pair;
     uint32_t transposed;
   };
-  std::vector<Contrib> contribs;
+  size_t n_contribs = 0;
+  for (size_t pl = 0; pl < plan_factors.size(); ++pl) {
+    int ng = 0;
+    for (int o = 0; o < SFX_MAX_OPT; ++o) ng = std::max(ng, plan_pat[pl].grp[o] + 1);
+    n_contribs += plan_factors[pl].size() * (size_t)(ng * (ng - 1) / 2);
+  }
+  RawBuf<Contrib> contribs(n_contribs);  // (plan, slot, pair) order, filled by the chunks below
+  size_t c_next = 0;
   a.batches.assign(plan_factors.size(), BatchPlan{});
   for (size_t pl = 0; pl < plan_factors.size(); ++pl) {
     BatchPlan& bp = a.batches[pl];
@@ -400,8 +468,9 @@ void analyze_problem(const sfx_problem_desc& d, Analysis& a) {
       for (int o = 0; o < km.n_opt; ++o)
         if (pk.grp[o] >= 0) bp.group_dim[pk.grp[o]] = a.nodes[a.keys[fb.opt_keys[(int64_t)o * fb.n + fr.idx]].node].dim;
     }
-    const size_t c_base = contribs.size();
-    contribs.resize(c_base + (size_t)n * npairs);  // (plan, slot, pair) order, filled by the chunks below
+    const size_t c_base = c_next;
+    c_next += (size_t)n * npairs;
+    SFX_CHECK(c_next <= n_contribs, SFX_ERR_STRUCTURE, "contribution count");
     parallel_chunks(n, [&](int64_t s_begin, int64_t s_end) {
       for (int s = (int)s_begin; s < (int)s_end; ++s) {
         const FactorRef& fr = plan_factors[pl][s];
@@ -437,15 +506,17 @@ void analyze_problem(const sfx_problem_desc& d, Analysis& a) {
   // sort contributions by block; stable so that slot order is kept inside a block
   std::vector<uint32_t> order;
   {
-    std::vector<uint64_t> ck(contribs.size());
-    for (size_t i = 0; i < contribs.size(); ++i) ck[i] = contribs[i].key;
-    stable_order_by_key(ck, order);
+    RawBuf<uint64_t> ck(contribs.size());
+    parallel_chunks((int64_t)contribs.size(), [&](int64_t c0, int64_t c1) {
+      for (int64_t i = c0; i < c1; ++i) ck[i] = contribs[i].key;
+    });
+    stable_order_by_key(ck.data(), ck.size(), order);
   }
   clk.lap("  contribs sorted");
   // unique blocks with contributor counts
   std::vector<uint64_t> blk_key;
   std::vector<int> blk_cnt;
-  std::vector<int> contrib_blk(contribs.size());
+  RawBuf<int> contrib_blk(contribs.size());
   for (size_t i = 0; i < order.size(); ++i) {
     const Contrib& c = contribs[order[i]];
     if (blk_key.empty() || blk_key.back() != c.key) {
@@ -535,21 +606,24 @@ void analyze_problem(const sfx_problem_desc& d, Analysis& a) {
   SFX_CHECK(off < (int64_t)kOffMask, SFX_ERR_UNSUPPORTED, "Hessian has more than 2^30 block values");
   clk.lap("Hessian blocks");
   // fill per-factor scatter indices
-  for (size_t c = 0; c < contribs.size(); ++c) {
-    const Contrib& ct = contribs[c];
-    BatchPlan& bp = a.batches[ct.plan];
-    int b = contrib_blk[c];
-    uint32_t v = (uint32_t)H.blk_off[offdiag_id[b]];
-    if (blk_cnt[b] == 1) v |= kOffExclusive;
-    if (ct.transposed) v |= kOffTransposed;
-    bp.off_off[(size_t)ct.pair * bp.n + ct.slot] = v;
-  }
+  parallel_chunks((int64_t)contribs.size(), [&](int64_t c0, int64_t c1) {
+    for (int64_t c = c0; c < c1; ++c) {
+      const Contrib& ct = contribs[c];
+      BatchPlan& bp = a.batches[ct.plan];
+      int b = contrib_blk[c];
+      uint32_t v = (uint32_t)H.blk_off[offdiag_id[b]];
+      if (blk_cnt[b] == 1) v |= kOffExclusive;
+      if (ct.transposed) v |= kOffTransposed;
+      bp.off_off[(size_t)ct.pair * bp.n + ct.slot] = v;
+    }
+  });
   {
     std::vector<int> toff2node(a.N + 1, -1);  // tangent offset of a node -> node
     for (int i = 0; i < nn; ++i) toff2node[a.nodes[i].toff] = i;
     for (auto& bp : a.batches)
-      for (size_t i = 0; i < bp.rhs_off.size(); ++i)
-        bp.diag_off[i] = (int32_t)H.blk_off[H.col_ptr[toff2node[bp.rhs_off[i]]]];
+      parallel_chunks((int64_t)bp.rhs_off.size(), [&](int64_t i0, int64_t i1) {
+        for (int64_t i = i0; i < i1; ++i) bp.diag_off[i] = (int32_t)H.blk_off[H.col_ptr[toff2node[bp.rhs_off[i]]]];
+      });
   }
   // keep only this rank's slots (contiguous thanks to the owner-sorted slot order)
   if (a.world > 1)
@@ -604,23 +678,41 @@ void analyze_problem(const sfx_problem_desc& d, Analysis& a) {
       sp.lm_toff[l] = a.nodes[node].toff;
     }
     // E blocks of ALL landmarks (for the S pattern): blocks (row = landmark node, col = reduced node)
+    // Every host thread takes a contiguous range of landmarks and, in each column, the (sorted) rows inside it: the
+    // per-landmark lists are written without conflicts and come out ordered by reduced node.
     std::vector<int32_t> all_ptr(nlt + 1, 0), all_off, all_node;
-    for (int j = 0; j < nr; ++j)
-      for (int p = H.col_ptr[j] + 1; p < H.col_ptr[j + 1]; ++p)
-        if (H.row_idx[p] >= first_lm_node) all_ptr[H.row_idx[p] - first_lm_node + 1]++;
+    const int nt_e = host_threads(H.col_ptr[nr], 1 << 18);
+    auto lm_rows_of = [&](int t, int j, int& p0, int& p1) {  // blocks of column j whose row is a landmark of thread t
+      const int* rb = H.row_idx.data() + H.col_ptr[j] + 1;
+      const int* re = H.row_idx.data() + H.col_ptr[j + 1];
+      const int lo = first_lm_node + (int)((int64_t)nlt * t / nt_e), hi = first_lm_node + (int)((int64_t)nlt * (t + 1) / nt_e);
+      p0 = (int)(std::lower_bound(rb, re, lo) - H.row_idx.data());
+      p1 = (int)(std::lower_bound(rb, re, hi) - H.row_idx.data());
+    };
+    run_threads(nt_e, [&](int t) {
+      for (int j = 0; j < nr; ++j) {
+        int p0, p1;
+        lm_rows_of(t, j, p0, p1);
+        for (int p = p0; p < p1; ++p) all_ptr[H.row_idx[p] - first_lm_node + 1]++;
+      }
+    });
     for (int l = 0; l < nlt; ++l) all_ptr[l + 1] += all_ptr[l];
     all_off.resize(all_ptr[nlt]);
     all_node.resize(all_ptr[nlt]);
     {
       std::vector<int> fill(all_ptr.begin(), all_ptr.end() - 1);
-      for (int j = 0; j < nr; ++j)  // increasing j -> each landmark's list sorted by node
-        for (int p = H.col_ptr[j] + 1; p < H.col_ptr[j + 1]; ++p)
-          if (H.row_idx[p] >= first_lm_node) {
-            int l = H.row_idx[p] - first_lm_node;
+      run_threads(nt_e, [&](int t) {
+        for (int j = 0; j < nr; ++j) {  // increasing j -> each landmark's list sorted by node
+          int p0, p1;
+          lm_rows_of(t, j, p0, p1);
+          for (int p = p0; p < p1; ++p) {
+            const int l = H.row_idx[p] - first_lm_node;
             all_off[fill[l]] = (int32_t)H.blk_off[p];
             all_node[fill[l]] = j;
             fill[l]++;
           }
+        }
+      });
     }
     sp.lm_e_ptr.assign(nl + 1, 0);
     for (int l = 0; l < nl; ++l) sp.lm_e_ptr[l + 1] = sp.lm_e_ptr[l] + (all_ptr[lm0 + l + 1] - all_ptr[lm0 + l]);
@@ -652,67 +744,138 @@ void analyze_problem(const sfx_problem_desc& d, Analysis& a) {
     }
   clk.lap("  rhs lists");
     // S pattern: B blocks + all pairs (I >= J) of reduced nodes adjacent to a common landmark (ANY
-    // rank's landmark, so the pattern is the same everywhere); matches only for own landmarks
-    struct Match {
-      uint64_t key;  // (col J << 32) | row I
-      int32_t ei, ej, lm;
+    // rank's landmark, so the pattern is the same everywhere); matches only for own landmarks.
+    // Match order: by S block (column J, then row I), inside a block by landmark.  Built without a global sort:
+    // (1) per-thread counts of the matches each column receives, (2) every thread scatters the matches of its
+    // landmark range into the column buckets (thread ranges are in landmark order, so a bucket stays landmark-ordered),
+    // (3) each column is counting-sorted by row on its own (cache resident; columns are handed out dynamically) and
+    // written straight into the final arrays.
+    struct ColMatch {
+      int32_t row, ei, ej, lm;
     };
-    std::vector<Match> matches;
     std::vector<uint64_t> skeys;
-    {
-      int64_t cnt_m = 0;
-      for (int l = 0; l < nl; ++l) {
-        int64_t k = sp.lm_e_ptr[l + 1] - sp.lm_e_ptr[l];
-        cnt_m += k * (k + 1) / 2;
-      }
-      matches.reserve(cnt_m);
-    }
-    for (int l = 0; l < nlt; ++l) {
-      const bool own = l >= lm0 && l < lm0 + nl;
-      for (int q = all_ptr[l]; q < all_ptr[l + 1]; ++q)
-        for (int p = q; p < all_ptr[l + 1]; ++p) {  // node[p] >= node[q]
-          const uint64_t key = ((uint64_t)all_node[q] << 32) | (uint32_t)all_node[p];
-          if (own)
-            matches.push_back(Match{key, all_off[p], all_off[q], l - lm0});
-          else
-            skeys.push_back(key);
+    if (nl < nlt) {  // other ranks' landmarks only contribute to the pattern
+      const int64_t n_words = ((int64_t)nr * nr + 63) / 64;
+      if (n_words <= (int64_t)(1 << 23)) {
+        // nr x nr bitmap (<= 64 MB) of the (column, row) pairs, set with relaxed atomic ORs from all host threads
+        std::vector<uint64_t> bits((size_t)n_words, 0);
+        const int nt_p = host_threads(all_ptr[nlt], 1 << 16);
+        run_threads(nt_p, [&](int t) {
+          for (int l = (int)((int64_t)nlt * t / nt_p); l < (int)((int64_t)nlt * (t + 1) / nt_p); ++l) {
+            if (l >= lm0 && l < lm0 + nl) continue;
+            for (int q = all_ptr[l]; q < all_ptr[l + 1]; ++q)
+              for (int p = q; p < all_ptr[l + 1]; ++p) {
+                const int64_t bit = (int64_t)all_node[q] * nr + all_node[p];
+                const uint64_t m = 1ull << (bit & 63);
+                if (!(__atomic_load_n(&bits[bit >> 6], __ATOMIC_RELAXED) & m))
+                  __atomic_fetch_or(&bits[bit >> 6], m, __ATOMIC_RELAXED);
+              }
+          }
+        });
+        for (int64_t w = 0; w < n_words; ++w)
+          for (uint64_t x = bits[w]; x; x &= x - 1) {
+            const int64_t bit = w * 64 + __builtin_ctzll(x);
+            skeys.push_back(((uint64_t)(bit / nr) << 32) | (uint32_t)(bit % nr));
+          }
+      } else {
+        for (int l = 0; l < nlt; ++l) {
+          if (l >= lm0 && l < lm0 + nl) continue;
+          for (int q = all_ptr[l]; q < all_ptr[l + 1]; ++q)
+            for (int p = q; p < all_ptr[l + 1]; ++p) skeys.push_back(((uint64_t)all_node[q] << 32) | (uint32_t)all_node[p]);
+          if (skeys.size() > (size_t)(1 << 24)) {  // keep the temporary bounded
+            std::sort(skeys.begin(), skeys.end());
+            skeys.erase(std::unique(skeys.begin(), skeys.end()), skeys.end());
+          }
         }
-      if (!own && skeys.size() > (size_t)(1 << 24)) {  // keep the temporary bounded
-        std::sort(skeys.begin(), skeys.end());
-        skeys.erase(std::unique(skeys.begin(), skeys.end()), skeys.end());
       }
     }
-    clk.lap("  matches built");
+    std::vector<int64_t> m_prefix(nl + 1, 0);  // matches of own landmarks [0, l)
+    for (int l = 0; l < nl; ++l) {
+      const int64_t k = sp.lm_e_ptr[l + 1] - sp.lm_e_ptr[l];
+      m_prefix[l + 1] = m_prefix[l] + k * (k + 1) / 2;
+    }
+    const int64_t n_matches = m_prefix[nl];
+    SFX_CHECK(n_matches < (int64_t)UINT32_MAX, SFX_ERR_UNSUPPORTED, "too many Schur matches");
+    const int nt = host_threads(n_matches, 1 << 18);
+    std::vector<int> t_begin(nt + 1, nl);  // landmark ranges with equal numbers of matches
+    for (int t = 0; t <= nt; ++t)
+      t_begin[t] = (int)(std::lower_bound(m_prefix.begin(), m_prefix.end(), n_matches * t / nt) - m_prefix.begin());
+    t_begin[0] = 0;
+    t_begin[nt] = nl;
+    std::vector<std::vector<int64_t>> t_cnt(nt, std::vector<int64_t>(nr, 0));
+    run_threads(nt, [&](int t) {
+      auto& c = t_cnt[t];
+      for (int l = t_begin[t]; l < t_begin[t + 1]; ++l) {
+        const int e0 = all_ptr[lm0 + l], e1 = all_ptr[lm0 + l + 1];
+        for (int q = e0; q < e1; ++q) c[all_node[q]] += e1 - q;
+      }
+    });
+    std::vector<int64_t> col_start(nr + 1, 0);
+    for (int j = 0; j < nr; ++j) {
+      int64_t run = col_start[j];
+      for (int t = 0; t < nt; ++t) {
+        const int64_t c = t_cnt[t][j];
+        t_cnt[t][j] = run;  // becomes this thread's write cursor in column j
+        run += c;
+      }
+      col_start[j + 1] = run;
+    }
+    RawBuf<ColMatch> bucket((size_t)n_matches);
+    run_threads(nt, [&](int t) {
+      auto& cur = t_cnt[t];
+      for (int l = t_begin[t]; l < t_begin[t + 1]; ++l) {
+        const int e0 = all_ptr[lm0 + l], e1 = all_ptr[lm0 + l + 1];
+        for (int q = e0; q < e1; ++q) {
+          ColMatch* dst = bucket.data() + cur[all_node[q]];
+          for (int p = q; p < e1; ++p) *dst++ = ColMatch{all_node[p], all_off[p], all_off[q], l};  // node[p] >= node[q]
+          cur[all_node[q]] += e1 - q;
+        }
+      }
+    });
+    clk.lap("  matches bucketed");
+    sp.m_eoff_i.resize((size_t)n_matches);
+    sp.m_eoff_j.resize((size_t)n_matches);
+    sp.m_lm.resize((size_t)n_matches);
+    // per column: the S blocks that receive matches (row, count), in row order
+    std::vector<std::vector<std::pair<int32_t, int32_t>>> col_runs(nr);
     {
-      // stable sort by (column J, row I): two counting passes over the nr node buckets (row first, then column)
-      SFX_CHECK(matches.size() < (size_t)UINT32_MAX, SFX_ERR_UNSUPPORTED, "too many Schur matches");
-      std::vector<Match> sorted(matches.size());
-      std::vector<size_t> start(nr + 1);
-      for (int pass = 0; pass < 2; ++pass) {
-        const int shift = pass == 0 ? 0 : 32;
-        std::fill(start.begin(), start.end(), 0);
-        for (const Match& m : matches) start[((m.key >> shift) & 0xffffffffu) + 1]++;
-        for (int j = 0; j < nr; ++j) start[j + 1] += start[j];
-        for (const Match& m : matches) sorted[start[(m.key >> shift) & 0xffffffffu]++] = m;
-        matches.swap(sorted);  // after the second pass `matches` is sorted by (column, row), ties in landmark order
-      }
+      std::atomic<int> next_col{0};
+      run_threads(nt, [&](int) {
+        std::vector<int32_t> start(nr + 1);
+        for (;;) {
+          const int j = next_col.fetch_add(1, std::memory_order_relaxed);
+          if (j >= nr) break;
+          const int64_t b0 = col_start[j], b1 = col_start[j + 1];
+          if (b0 == b1) continue;
+          SFX_CHECK(b1 - b0 < (int64_t)INT32_MAX, SFX_ERR_UNSUPPORTED, "too many Schur matches in one column");
+          std::fill(start.begin(), start.end(), 0);
+          for (int64_t i = b0; i < b1; ++i) start[bucket[i].row + 1]++;
+          auto& runs = col_runs[j];
+          for (int r = 0; r < nr; ++r) {
+            if (start[r + 1]) runs.emplace_back(r, start[r + 1]);
+            start[r + 1] += start[r];
+          }
+          for (int64_t i = b0; i < b1; ++i) {  // stable: landmark order is kept inside a block
+            const ColMatch& m = bucket[i];
+            const int64_t o = b0 + start[m.row]++;
+            sp.m_eoff_i[o] = m.ei;
+            sp.m_eoff_j[o] = m.ej;
+            sp.m_lm[o] = m.lm;
+          }
+        }
+      });
     }
-  clk.lap("  matches built+sorted");
+    bucket.reset();
+    clk.lap("  matches sorted");
     // merged column structure
     for (int j = 0; j < nr; ++j)
       for (int p = H.col_ptr[j]; p < H.col_ptr[j + 1]; ++p)
         if (H.row_idx[p] < first_lm_node) skeys.push_back(((uint64_t)j << 32) | (uint32_t)H.row_idx[p]);
-    {
-      uint64_t last = ~0ull;
-      for (const Match& m : matches)
-        if (m.key != last) {
-          skeys.push_back(m.key);
-          last = m.key;
-        }
-    }
+    for (int j = 0; j < nr; ++j)
+      for (const auto& rc : col_runs[j]) skeys.push_back(((uint64_t)j << 32) | (uint32_t)rc.first);
     std::sort(skeys.begin(), skeys.end());
     skeys.erase(std::unique(skeys.begin(), skeys.end()), skeys.end());
-  clk.lap("  skeys");
+    clk.lap("  skeys");
     BlockMatrix& S = sp.S;
     S.n_nodes = nr;
     S.node_dim.assign(H.node_dim.begin(), H.node_dim.begin() + nr);
@@ -734,20 +897,16 @@ void analyze_problem(const sfx_problem_desc& d, Analysis& a) {
     for (int j = 0; j < nr; ++j)
       for (int p = H.col_ptr[j]; p < H.col_ptr[j + 1]; ++p)
         if (H.row_idx[p] < first_lm_node) sp.s_b_src[S.find(H.row_idx[p], j)] = (int32_t)H.blk_off[p];
-  clk.lap("  S structure");
+    clk.lap("  S structure");
     sp.s_m_ptr.assign(skeys.size() + 1, 0);
-    sp.m_eoff_i.resize(matches.size());
-    sp.m_eoff_j.resize(matches.size());
-    sp.m_lm.resize(matches.size());
     {
       size_t b = 0;
-      for (size_t i = 0; i < matches.size(); ++i) {
-        while (skeys[b] != matches[i].key) ++b;
-        sp.s_m_ptr[b + 1]++;
-        sp.m_eoff_i[i] = matches[i].ei;
-        sp.m_eoff_j[i] = matches[i].ej;
-        sp.m_lm[i] = matches[i].lm;
-      }
+      for (int j = 0; j < nr; ++j)
+        for (const auto& rc : col_runs[j]) {
+          const uint64_t key = ((uint64_t)j << 32) | (uint32_t)rc.first;
+          while (skeys[b] != key) ++b;
+          sp.s_m_ptr[b + 1] = rc.second;
+        }
       for (size_t q = 0; q < skeys.size(); ++q) sp.s_m_ptr[q + 1] += sp.s_m_ptr[q];
     }
   }

@@ -1,6 +1,7 @@
 // Host-only introspection of the structural analysis (no CUDA calls): lets the CPU test-suite
 // replay the index maps, Schur match lists and the multifrontal plan in numpy and check them
 // against the oracle before any kernel runs.  Small problems only (JSON text).
+#include <cstring>
 #include <sstream>
 
 #include "sfx_internal.h"
@@ -128,6 +129,93 @@ extern "C" int sfx_debug_analysis_json(const sfx_problem_desc* d, char** out) {
         << c.dst_col << ',' << c.transposed << ',' << c.lower_only << ']';
     }
     o << "]}}";
+    buf = o.str();
+    *out = const_cast<char*>(buf.c_str());
+    return 0;
+  } catch (const std::exception& e) {
+    buf = e.what();
+    *out = const_cast<char*>(buf.c_str());
+    return 1;
+  }
+}
+
+// 64-bit digests of every array of the analysis (no plan of the fronts), one "name hash size" line each: lets a change of
+// the host analysis be checked for identical output on problems far too large for the JSON dump (tools/analysis_digest.py).
+namespace {
+template <typename T>
+void digest(std::ostringstream& o, const std::string& name, const std::vector<T>& v) {
+  uint64_t h = 0xcbf29ce484222325ull;
+  const unsigned char* p = reinterpret_cast<const unsigned char*>(v.data());
+  const size_t nb = v.size() * sizeof(T);
+  size_t i = 0;
+  for (; i + 8 <= nb; i += 8) {
+    uint64_t w;
+    memcpy(&w, p + i, 8);
+    h = (h ^ w) * 0x100000001b3ull;
+    h ^= h >> 29;
+  }
+  for (; i < nb; ++i) h = (h ^ p[i]) * 0x100000001b3ull;
+  o << name << ' ' << std::hex << h << std::dec << ' ' << v.size() << "\n";
+}
+void digest_bm(std::ostringstream& o, const std::string& name, const sfx::BlockMatrix& B) {
+  digest(o, name + ".node_dim", B.node_dim);
+  digest(o, name + ".node_off", B.node_off);
+  digest(o, name + ".col_ptr", B.col_ptr);
+  digest(o, name + ".row_idx", B.row_idx);
+  digest(o, name + ".blk_off", B.blk_off);
+  o << name << ".n_values " << (long long)B.n_values << "\n";
+}
+}  // namespace
+
+extern "C" int sfx_debug_analysis_digest(const sfx_problem_desc* d, char** out) {
+  using namespace sfx;
+  static thread_local std::string buf;
+  try {
+    Analysis a;
+    analyze_problem(*d, a);
+    std::ostringstream o;
+    o << "N " << a.N << " M " << a.M << " b_values " << (long long)a.b_values << " h_accum_values "
+      << (long long)a.h_accum_values << "\n";
+    std::vector<int> v1, v2;
+    for (auto& k : a.keys) {
+      v1.push_back(k.node);
+      v2.push_back(k.sub);
+    }
+    digest(o, "key_node", v1);
+    digest(o, "key_sub", v2);
+    digest(o, "ref2int", a.ref2int);
+    digest(o, "diag_pos", a.diag_pos);
+    digest_bm(o, "H", a.H);
+    for (size_t b = 0; b < a.batches.size(); ++b) {
+      const BatchPlan& bp = a.batches[b];
+      const std::string n = "batch" + std::to_string(b);
+      o << n << " kind " << bp.kind << " n " << bp.n << " groups " << bp.n_groups << "\n";
+      digest(o, n + ".arg_off", bp.arg_off);
+      digest(o, n + ".res_off", bp.res_off);
+      digest(o, n + ".rhs_off", bp.rhs_off);
+      digest(o, n + ".diag_off", bp.diag_off);
+      digest(o, n + ".off_off", bp.off_off);
+      digest(o, n + ".factor_index", bp.factor_index);
+    }
+    if (a.schur) {
+      const SchurPlan& s = a.sp;
+      o << "schur n_landmarks " << s.n_landmarks << " lm_begin " << s.lm_begin << " reduced_dim " << s.reduced_dim << "\n";
+      digest(o, "lm_dim", s.lm_dim);
+      digest(o, "lm_cdiag_off", s.lm_cdiag_off);
+      digest(o, "lm_toff", s.lm_toff);
+      digest(o, "lm_e_ptr", s.lm_e_ptr);
+      digest(o, "lm_e_off", s.lm_e_off);
+      digest(o, "lm_e_node", s.lm_e_node);
+      digest_bm(o, "S", s.S);
+      digest(o, "s_b_src", s.s_b_src);
+      digest(o, "s_m_ptr", s.s_m_ptr);
+      digest(o, "m_eoff_i", s.m_eoff_i);
+      digest(o, "m_eoff_j", s.m_eoff_j);
+      digest(o, "m_lm", s.m_lm);
+      digest(o, "r_ptr", s.r_ptr);
+      digest(o, "r_eoff", s.r_eoff);
+      digest(o, "r_lm", s.r_lm);
+    }
     buf = o.str();
     *out = const_cast<char*>(buf.c_str());
     return 0;

@@ -154,7 +154,9 @@ int main(int argc, char** argv) {
   // keys c.., i.., p.. (lexical): the trailing points are eliminated by the GPU Schur path (AUTO)
   const double build_s = seconds_since(t_start);
   std::fprintf(stderr, "[host] factor list + Values built in %.2f s\n", build_s);
+  const auto t_ctor = std::chrono::steady_clock::now();
   sym::Optimizerd optimizer{params, std::move(problem.factors)};
+  std::fprintf(stderr, "[host] Optimizer constructed (keys to optimize collected and ordered) in %.2f s\n", seconds_since(t_ctor));
   const auto t_opt = std::chrono::steady_clock::now();
   const auto stats = optimizer.Optimize(optimized_values);
   const double optimize_s = seconds_since(t_opt);

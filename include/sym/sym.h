@@ -14,8 +14,12 @@
 // there and copies the best values + per-iteration stats back.
 #pragma once
 #include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
+#include <exception>
 #include <limits>
 #include <map>
 #include <memory>
@@ -23,7 +27,9 @@
 #include <sstream>
 #include <stdexcept>
 #include <string>
+#include <thread>
 #include <unordered_map>
+#include <unordered_set>
 #include <utility>
 #include <vector>
 
@@ -254,6 +260,33 @@ struct index_t {
   int32_t tangent_dim{0};
   std::vector<index_entry_t> entries;
 };
+
+namespace internal {
+// fn(begin, end) over contiguous chunks of [0, n) on up to 8 host threads (SFX_HOST_THREADS overrides); read-only
+// lookups in the key maps of a multi-million-factor problem are bound by cache misses and scale with threads
+template <typename Fn>
+inline void ParallelFor(size_t n, const Fn& fn) {
+  size_t nt = std::min<size_t>(std::min<unsigned>(8u, std::max(1u, std::thread::hardware_concurrency())), (n + 65535) / 65536);
+  if (const char* e = std::getenv("SFX_HOST_THREADS")) nt = static_cast<size_t>(std::max(1, std::atoi(e)));
+  if (nt <= 1) {
+    fn(size_t{0}, n);
+    return;
+  }
+  std::vector<std::thread> th;
+  std::vector<std::exception_ptr> err(nt);
+  for (size_t t = 0; t < nt; ++t)
+    th.emplace_back([&, t] {
+      try {
+        fn(n * t / nt, n * (t + 1) / nt);
+      } catch (...) {
+        err[t] = std::current_exception();
+      }
+    });
+  for (auto& x : th) x.join();
+  for (auto& e : err)
+    if (e) std::rethrow_exception(e);
+}
+}  // namespace internal
 
 namespace internal {
 template <typename T, typename = void>
@@ -642,13 +675,11 @@ using Factord = Factor<double>;
 template <typename Scalar>
 std::vector<Key> ComputeKeysToOptimize(const std::vector<Factor<Scalar>>& factors) {
   std::vector<Key> keys;
-  std::unordered_map<Key, bool, KeyHash> seen;
+  std::unordered_set<Key, KeyHash> seen;
+  seen.reserve(factors.size());
   for (const auto& f : factors)
     for (const Key& k : f.OptimizedKeys())
-      if (!seen.count(k)) {
-        seen[k] = true;
-        keys.push_back(k);
-      }
+      if (seen.insert(k).second) keys.push_back(k);
   std::sort(keys.begin(), keys.end(), Key::LexicalLessThan);
   return keys;
 }
@@ -891,6 +922,7 @@ class Optimizer {
       SYM_ASSERT(static_cast<int64_t>(values.Data().size()) == n_values_);
       return;
     }
+    const auto t_index = std::chrono::steady_clock::now();
     std::unordered_map<Key, int, KeyHash> key_index;
     kentries_.clear();
     for (size_t i = 0; i < keys_.size(); ++i) {
@@ -898,48 +930,68 @@ class Optimizer {
       kentries_.push_back(sfx_key_entry{DeviceType(e.type), e.offset, e.storage_dim, e.tangent_dim});
       key_index[keys_[i]] = static_cast<int>(i);
     }
-    struct Batch {
-      int n_args = 0, n_opt = 0;
-      std::vector<std::vector<int32_t>> args, opt;
-      std::vector<int32_t> fidx;
-    };
-    std::map<int, Batch> batches;
-    for (size_t fi = 0; fi < factors_.size(); ++fi) {
-      const Factor<Scalar>& f = factors_[fi];
-      Batch& b = batches[f.Kind()];
-      if (b.args.empty()) {
-        b.n_args = static_cast<int>(f.AllKeys().size());
-        b.n_opt = static_cast<int>(f.OptimizedKeys().size());
-        b.args.resize(b.n_args);
-        b.opt.resize(b.n_opt);
-      }
-      for (int a = 0; a < b.n_args; ++a) b.args[a].push_back(values.IndexEntryAt(f.AllKeys()[a]).offset);
-      for (int o = 0; o < b.n_opt; ++o) {
-        auto it = key_index.find(f.OptimizedKeys()[o]);
-        b.opt[o].push_back(it == key_index.end() ? -1 : it->second);
-      }
-      b.fidx.push_back(static_cast<int32_t>(fi));
-    }
+    // Factors grouped by device kind (batches in ascending kind, slots in factor order).  Pass 1 (serial) numbers the
+    // slots; pass 2 looks every key up -- ~8 hash lookups per factor in maps far larger than the caches -- on up to 8
+    // host threads, writing straight into the flat [argument][slot] arrays the C ABI takes.
+    const size_t nf = factors_.size();
+    std::map<int, int> kind2batch;
+    for (const auto& f : factors_) kind2batch.emplace(f.Kind(), 0);
     batch_kind_.clear();
-    flat_args_.clear();
-    flat_opt_.clear();
-    batch_fidx_.clear();
-    for (auto& kv : batches) {
-      Batch& b = kv.second;
-      std::vector<int32_t> fa, fo;
-      for (auto& v : b.args) fa.insert(fa.end(), v.begin(), v.end());
-      for (auto& v : b.opt) fo.insert(fo.end(), v.begin(), v.end());
+    for (auto& kv : kind2batch) {
+      kv.second = static_cast<int>(batch_kind_.size());
       batch_kind_.push_back(kv.first);
-      flat_args_.push_back(std::move(fa));
-      flat_opt_.push_back(std::move(fo));
-      batch_fidx_.push_back(std::move(b.fidx));
     }
+    const size_t nb = batch_kind_.size();
+    std::vector<int> b_args(nb, -1), b_opt(nb, -1);
+    std::vector<int32_t> batch_of(nf), slot_of(nf), b_n(nb, 0);
+    {
+      int last_kind = -1, last_batch = -1;
+      for (size_t fi = 0; fi < nf; ++fi) {
+        const Factor<Scalar>& f = factors_[fi];
+        if (f.Kind() != last_kind) {
+          last_kind = f.Kind();
+          last_batch = kind2batch[last_kind];
+        }
+        const int bi = last_batch;
+        if (b_args[bi] < 0) {
+          b_args[bi] = static_cast<int>(f.AllKeys().size());
+          b_opt[bi] = static_cast<int>(f.OptimizedKeys().size());
+        }
+        SYM_ASSERT(b_args[bi] == static_cast<int>(f.AllKeys().size()) && b_opt[bi] == static_cast<int>(f.OptimizedKeys().size()));
+        batch_of[fi] = bi;
+        slot_of[fi] = b_n[bi]++;
+      }
+    }
+    flat_args_.assign(nb, {});
+    flat_opt_.assign(nb, {});
+    batch_fidx_.assign(nb, {});
+    for (size_t bi = 0; bi < nb; ++bi) {
+      flat_args_[bi].resize(static_cast<size_t>(b_args[bi]) * b_n[bi]);
+      flat_opt_[bi].resize(static_cast<size_t>(b_opt[bi]) * b_n[bi]);
+      batch_fidx_[bi].resize(b_n[bi]);
+    }
+    internal::ParallelFor(nf, [&](size_t f0, size_t f1) {
+      for (size_t fi = f0; fi < f1; ++fi) {
+        const Factor<Scalar>& f = factors_[fi];
+        const int bi = batch_of[fi];
+        const size_t n = b_n[bi], s = slot_of[fi];
+        for (int a = 0; a < b_args[bi]; ++a) flat_args_[bi][a * n + s] = values.IndexEntryAt(f.AllKeys()[a]).offset;
+        for (int o = 0; o < b_opt[bi]; ++o) {
+          auto it = key_index.find(f.OptimizedKeys()[o]);
+          flat_opt_[bi][o * n + s] = it == key_index.end() ? -1 : it->second;
+        }
+        batch_fidx_[bi][s] = static_cast<int32_t>(fi);
+      }
+    });
     n_values_ = static_cast<int64_t>(values.Data().size());
     int schur_keys = 0;
     if (gpu_.solver == GpuSolverOptions::SCHUR) schur_keys = gpu_.schur_num_keys;
-    if (gpu_.solver == GpuSolverOptions::AUTO) schur_keys = AutoSchurKeys(values, key_index);
+    if (gpu_.solver == GpuSolverOptions::AUTO) schur_keys = AutoSchurKeys(values);
     solver_ = schur_keys > 0 ? SFX_SOLVER_SCHUR : SFX_SOLVER_CHOLESKY;
     schur_keys_ = schur_keys;
+    if (std::getenv("SFX_TIMING"))
+      std::fprintf(stderr, "[sym] indexed %zu factors over %zu optimized keys in %.2f s\n", nf, keys_.size(),
+                   std::chrono::duration<double>(std::chrono::steady_clock::now() - t_index).count());
     handle_ = Create(solver_, schur_keys_);
   }
   // Device problem for the indexed factor graph with the given linear solver (the LM problem, or the
@@ -990,7 +1042,7 @@ class Optimizer {
   }
   // Longest trailing run of keys (in keys_ order) that are vectors of dim <= 3 and never share a
   // factor with each other: eliminating them per block is exactly SparseSchurSolver's C.
-  int AutoSchurKeys(const Values<Scalar>& values, const std::unordered_map<Key, int, KeyHash>& key_index) const {
+  int AutoSchurKeys(const Values<Scalar>& values) const {
     const int nk = static_cast<int>(keys_.size());
     int first = nk;
     while (first > 0) {
@@ -1003,19 +1055,23 @@ class Optimizer {
     if (first == nk) return 0;
     // shrink the run until no factor touches two of its keys (BAL: intrinsics and points are both small vectors
     // and meet in every factor; the run must start behind the last intrinsics key)
-    for (const auto& f : factors_) {
-      int largest = -1, second = -1;
-      for (const Key& k : f.OptimizedKeys()) {
-        auto it = key_index.find(k);
-        if (it == key_index.end() || it->second < first) continue;
-        if (it->second > largest) {
-          second = largest;
-          largest = it->second;
-        } else if (it->second > second) {
-          second = it->second;
+    for (size_t bi = 0; bi < flat_opt_.size(); ++bi) {
+      const size_t n = batch_fidx_[bi].size();
+      const size_t n_opt = n ? flat_opt_[bi].size() / n : 0;
+      for (size_t s = 0; s < n; ++s) {
+        int largest = -1, second = -1;
+        for (size_t o = 0; o < n_opt; ++o) {
+          const int k = flat_opt_[bi][o * n + s];
+          if (k < first) continue;
+          if (k > largest) {
+            second = largest;
+            largest = k;
+          } else if (k > second) {
+            second = k;
+          }
         }
+        if (second >= 0) first = std::max(first, second + 1);
       }
-      if (second >= 0) first = std::max(first, second + 1);
     }
     if (first == 0 || first >= nk) return 0;
     return (nk - first) >= nk / 2 ? nk - first : 0;

@@ -21,18 +21,6 @@
 
 namespace sfx {
 
-// SFX_TIMING=1: wall time of the host analysis phases on stderr (setup cost is outside the LM metric)
-struct PhaseClock {
-  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
-  const bool on = getenv("SFX_TIMING") != nullptr;
-  void lap(const char* what) {
-    if (!on) return;
-    const auto t1 = std::chrono::steady_clock::now();
-    std::fprintf(stderr, "[sfx analysis] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
-    t0 = t1;
-  }
-};
-
 int BlockMatrix::find(int row, int col) const {
   const int* b = row_idx.data() + col_ptr[col];
   const int* e = row_idx.data() + col_ptr[col + 1];

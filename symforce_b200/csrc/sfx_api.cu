@@ -994,6 +994,7 @@ sfx_status sfx_problem_create(const sfx_problem_desc* desc, sfx_problem** out) {
   SFX_API_BEGIN
   SFX_CHECK(desc && out, SFX_ERR_INVALID_ARG, "null argument");
   *out = nullptr;
+  PhaseClock clk;  // SFX_TIMING=1: where the setup time goes
   int ndev = 0;
   cudaError_t ce = cudaGetDeviceCount(&ndev);
   if (ce != cudaSuccess || ndev == 0)
@@ -1012,7 +1013,9 @@ sfx_status sfx_problem_create(const sfx_problem_desc* desc, sfx_problem** out) {
               "rank/world of the descriptor and the communicator differ");
     SFX_CHECK(p->comm->device == desc->device, SFX_ERR_INVALID_ARG, "communicator was created for another device");
   }
+  clk.lap("create: CUDA context");
   analyze_problem(*desc, p->a);
+  clk.lap("create: analysis (total)");
   {
     Analysis& a = p->a;
     const BlockMatrix& sys = a.schur ? a.sp.S : a.H;
@@ -1024,6 +1027,7 @@ sfx_status sfx_problem_create(const sfx_problem_desc* desc, sfx_problem** out) {
     }
     build_front_plan(sys, desc->ordering, sys2ref, a.fp);
   }
+  clk.lap("create: ordering + front plan");
   CUDA_OK(cudaStreamCreateWithFlags(&p->st, cudaStreamNonBlocking));
   CUDA_OK(cudaStreamCreateWithFlags(&p->st2, cudaStreamNonBlocking));
   CUDA_OK(cudaEventCreateWithFlags(&p->ev_fork, cudaEventDisableTiming));
@@ -1032,6 +1036,7 @@ sfx_status sfx_problem_create(const sfx_problem_desc* desc, sfx_problem** out) {
   CUDA_OK(cudaEventCreateWithFlags(&p->ev_join2, cudaEventDisableTiming));
   upload_structures(p);
   CUDA_OK(cudaStreamSynchronize(p->st));
+  clk.lap("create: device structures");
   *out = up.release();
   p = nullptr;
   SFX_API_END(p)

@@ -8,6 +8,9 @@
 //   block  : dense (dim(row node) x dim(col node)) column-major tile of the lower Hessian
 //   front  : dense frontal matrix of one supernode of the multifrontal Cholesky
 #pragma once
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <cstdint>
 #include <stdexcept>
 #include <string>
@@ -165,5 +168,17 @@ void analyze_problem(const sfx_problem_desc& d, Analysis& a);
 void build_csc(Analysis& a);
 void build_front_plan(const BlockMatrix& A, int ordering, const std::vector<int>& ref_scalar_of_sys /* may be empty */,
                       FrontPlan& fp);
+
+// SFX_TIMING=1: wall time of the host analysis phases on stderr (setup cost is outside the LM metric)
+struct PhaseClock {
+  std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+  const bool on = getenv("SFX_TIMING") != nullptr;
+  void lap(const char* what) {
+    if (!on) return;
+    const auto t1 = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[sfx analysis] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
 
 }  // namespace sfx

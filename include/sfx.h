@@ -58,7 +58,9 @@ typedef enum {
   SFX_KIND_IRL_PRIOR = 6,      /* gen/cpp/sym/factors/inverse_range_landmark_prior_factor.h:30 */
   SFX_KIND_BETWEEN_ROT3 = 7,   /* gen/cpp/sym/factors/between_factor_rot3.h */
   SFX_KIND_PRIOR_ROT3 = 8,     /* gen/cpp/sym/factors/prior_factor_rot3.h */
-  SFX_KIND_COUNT = 9
+  SFX_KIND_BARRON = 9,         /* test/symforce_function_codegen_test_data/symengine/gnc_test_data/cpp/symforce/gnc_factors/barron_factor.h:33
+                                  (the factor of test/symforce_gnc_test.cc) */
+  SFX_KIND_COUNT = 10
 } sfx_factor_kind;
 
 /* Mirrors sym::optimizer_params_t field for field (lcmtypes/symforce.lcm:134-200; defaults in

@@ -1,11 +1,12 @@
 // Minimal fixed-size Eigen stand-in for environments without Eigen (like this build image).
 // When real Eigen is on the include path, define SFX_USE_EIGEN and <Eigen/Core> is used instead;
 // the sym:: layer only needs: fixed-size column-major Matrix<Scalar,R,C> with data(), operator(),
-// operator[], Zero(), Identity(), Constant(), size(), RowsAtCompileTime / ColsAtCompileTime.
+// operator[], Zero(), Identity(), Constant(), Ones(), norm(), size(), RowsAtCompileTime / ColsAtCompileTime.
 #pragma once
 #if defined(SFX_USE_EIGEN)
 #include <Eigen/Core>
 #else
+#include <cmath>
 #include <cstring>
 #include <initializer_list>
 namespace Eigen {
@@ -23,6 +24,13 @@ class Matrix {
     for (int i = 0; i < R * C; ++i) m.d_[i] = v;
     return m;
   }
+  static Matrix Ones() { return Constant(Scalar(1)); }
+  Scalar squaredNorm() const {
+    Scalar s = 0;
+    for (int i = 0; i < R * C; ++i) s += d_[i] * d_[i];
+    return s;
+  }
+  Scalar norm() const { return std::sqrt(squaredNorm()); }
   static Matrix Identity() {
     Matrix m;
     for (int i = 0; i < (R < C ? R : C); ++i) m(i, i) = 1;

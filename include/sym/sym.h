@@ -24,6 +24,7 @@
 #include <map>
 #include <memory>
 #include <optional>
+#include <random>
 #include <sstream>
 #include <stdexcept>
 #include <string>
@@ -61,6 +62,8 @@ using Vector3 = Eigen::Matrix<S, 3, 1>;
 template <typename S>
 using Vector4 = Eigen::Matrix<S, 4, 1>;
 template <typename S>
+using Vector5 = Eigen::Matrix<S, 5, 1>;
+template <typename S>
 using Vector6 = Eigen::Matrix<S, 6, 1>;
 template <typename S>
 using Vector7 = Eigen::Matrix<S, 7, 1>;
@@ -69,9 +72,20 @@ using Matrix33 = Eigen::Matrix<S, 3, 3>;
 template <typename S>
 using Matrix66 = Eigen::Matrix<S, 6, 6>;
 using Vector3d = Vector3<double>;
+using Vector5d = Vector5<double>;
 using Vector6d = Vector6<double>;
 using Vector7d = Vector7<double>;
 using Matrix66d = Matrix66<double>;
+
+// sym::Random<Matrix>(gen) (gen/cpp/sym/ops/matrix/storage_ops.h:211-218): a fresh standard normal distribution per
+// call, entries drawn in storage order -- what the reference's tests build their sample data with
+template <typename T, typename Generator>
+T Random(Generator& gen) {
+  std::normal_distribution<typename T::Scalar> distribution{};
+  T m;
+  for (int i = 0; i < static_cast<int>(T::SizeAtCompileTime); ++i) m.data()[i] = distribution(gen);
+  return m;
+}
 
 // ------------------------------------------------------------------------------------------------
 // Key (symforce/opt/key.h)
@@ -589,6 +603,20 @@ void PriorFactorRot3(const Rot3<Scalar>&, const Rot3<Scalar>&, const Eigen::Matr
   internal::DeviceOnly("PriorFactorRot3");
 }
 #endif
+}  // namespace sym
+
+// gnc_factors::BarronFactor (test/symforce_function_codegen_test_data/symengine/gnc_test_data/cpp/symforce/gnc_factors/
+// barron_factor.h:33-40): the factor of the reference's GNC test, a device kind like the functions above
+namespace gnc_factors {
+template <typename Scalar>
+void BarronFactor(const Eigen::Matrix<Scalar, 5, 1>&, const Eigen::Matrix<Scalar, 5, 1>&, const Scalar, const Scalar,
+                  Eigen::Matrix<Scalar, 5, 1>* const = nullptr, Eigen::Matrix<Scalar, 5, 5>* const = nullptr,
+                  Eigen::Matrix<Scalar, 5, 5>* const = nullptr, Eigen::Matrix<Scalar, 5, 1>* const = nullptr) {
+  sym::internal::DeviceOnly("BarronFactor");
+}
+}  // namespace gnc_factors
+
+namespace sym {
 
 // ------------------------------------------------------------------------------------------------
 // Factor (symforce/opt/factor.h)
@@ -612,6 +640,7 @@ inline const std::unordered_map<const void*, KindInfo>& KindRegistry() {
     add(reinterpret_cast<const void*>(&InverseRangeLandmarkPriorFactor<double>), {SFX_KIND_IRL_PRIOR, 5, 1, {0, -1, -1}});
     add(reinterpret_cast<const void*>(&BetweenFactorRot3<double>), {SFX_KIND_BETWEEN_ROT3, 5, 2, {0, 1, -1}});
     add(reinterpret_cast<const void*>(&PriorFactorRot3<double>), {SFX_KIND_PRIOR_ROT3, 4, 1, {0, -1, -1}});
+    add(reinterpret_cast<const void*>(&gnc_factors::BarronFactor<double>), {SFX_KIND_BARRON, 4, 1, {0, -1, -1}});
     return r;
   }();
   return reg;

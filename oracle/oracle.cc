@@ -608,6 +608,7 @@ static inline void eval_factor(int kind, const double* const* a, double* res, do
     case SFX_KIND_IRL_PRIOR: sfx_factor_irl_prior(a[0], a[1], a[2], a[3], a[4], res, J); break;
     case SFX_KIND_BETWEEN_ROT3: sfx_factor_between_rot3(a[0], a[1], a[2], a[3], a[4], res, J); break;
     case SFX_KIND_PRIOR_ROT3: sfx_factor_prior_rot3(a[0], a[1], a[2], a[3], res, J); break;
+    case SFX_KIND_BARRON: sfx_factor_barron(a[0], a[1], a[2], a[3], res, J); break;
     default: throw std::runtime_error("unknown factor kind");
   }
 }

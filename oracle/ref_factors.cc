@@ -20,6 +20,7 @@
 #include <sym/factors/inverse_range_landmark_prior_factor.h>
 #include <sym/factors/prior_factor_pose3.h>
 #include <sym/factors/prior_factor_rot3.h>
+#include <symforce/gnc_factors/barron_factor.h>        // test/symforce_function_codegen_test_data/symengine/gnc_test_data/cpp
 
 template <int R, int C>
 using M = Eigen::Matrix<double, R, C>;
@@ -96,6 +97,12 @@ extern "C" int ref_eval_factor(int kind, const double* const* a, double* res, do
       sym::PriorFactorRot3<double>(sym::Rot3<double>(a[0]), sym::Rot3<double>(a[1]), M<3, 3>(a[2]), a[3][0], &r, &j,
                                    &h, &g);
       out<3, 3>(r, j, h, g, res, J, H, rhs);
+      return 0;
+    }
+    case 9: {
+      M<5, 1> r; M<5, 5> j; M<5, 5> h; M<5, 1> g;
+      gnc_factors::BarronFactor<double>(M<5, 1>(a[0]), M<5, 1>(a[1]), a[2][0], a[3][0], &r, &j, &h, &g);
+      out<5, 5>(r, j, h, g, res, J, H, rhs);
       return 0;
     }
   }

@@ -136,6 +136,13 @@ SFX_KIND_BEGIN(SFX_KIND_PRIOR_ROT3, 3, 3, 1, 4)
     sfx_factor_prior_rot3(a[0], a[1], a[2], a[3], res, J);
   }
 };
+SFX_KIND_BEGIN(SFX_KIND_BARRON, 5, 5, 1, 4)
+  __host__ __device__ static constexpr int dim(int k) { return k == 0 ? 5 : (k == 1 ? 0 : 0); }
+  __host__ __device__ static constexpr int col(int k) { return k == 0 ? 0 : (k == 1 ? 5 : 5); }
+  __device__ static void eval(const double* const* a, double* res, double* J) {
+    sfx_factor_barron(a[0], a[1], a[2], a[3], res, J);
+  }
+};
 
 constexpr int kLinThreads = 128;
 
@@ -642,6 +649,7 @@ void launch_linearize(cudaStream_t st, const Ctrl* ctrl, StatePtrs sp, int mode,
     SFX_CASE(SFX_KIND_IRL_PRIOR)
     SFX_CASE(SFX_KIND_BETWEEN_ROT3)
     SFX_CASE(SFX_KIND_PRIOR_ROT3)
+    SFX_CASE(SFX_KIND_BARRON)
 #undef SFX_CASE
   }
 }

@@ -26,7 +26,8 @@ TYPE_VECTOR, TYPE_ROT3, TYPE_POSE3 = 0, 1, 2
     KIND_IRL_PRIOR,
     KIND_BETWEEN_ROT3,
     KIND_PRIOR_ROT3,
-) = range(9)
+    KIND_BARRON,
+) = range(10)
 SOLVER_CHOLESKY, SOLVER_SCHUR = 0, 1
 ORDERING_METIS_SCALAR, ORDERING_METIS_BLOCK, ORDERING_NATURAL = 0, 1, 2
 STATUS_SUCCESS, STATUS_HIT_ITERATION_LIMIT, STATUS_FAILED = 1, 2, 3

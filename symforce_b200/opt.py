@@ -298,6 +298,7 @@ class _Residuals:
         self.prior_factor_rot3 = self.prior_rot3
         self.inverse_range_landmark_linear_gnc_factor = self.irl_linear_gnc
         self.inverse_range_landmark_prior_factor = self.irl_prior
+        self.barron_factor = self.barron  # test/symforce_gnc_codegen_test.py:24-33
 
     def get(self, r):
         if isinstance(r, Residual):

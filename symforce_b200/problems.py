@@ -592,3 +592,32 @@ def ba_example(seed=42, num_landmarks=20, params=None):
     prob = D.Problem(vb.data(), keys, [between, prior, gnc], params=params, epsilon=eps)
     prob.meta = dict(mu_off=int(mu_off), scale_off=int(scale_off), num_landmarks=num_landmarks)
     return prob
+
+
+# ------------------------------------------------------------------------------------------------
+# The reference's GNC test problem
+# ------------------------------------------------------------------------------------------------
+def gnc_test(params=None):
+    """
+    test/symforce_gnc_test.cc:23-57: x = ones(5), 20 samples y_i (3 outliers near 10, mt19937(42): tests/golden/
+    kat_initial_values.json "gnc_test"), one gnc_factors::BarronFactor(x, y_i, u, e) each, x optimized, optimizer
+    epsilon 1e-12.  Values order as the test fills them: x, e, y_0..y_19, then u (set by GncOptimizer::Optimize).
+    """
+    ys = np.array(_kat_init()["gnc_test"]).reshape(20, 5)
+    vb = ValuesBuilder()
+    x_off = vb.add(np.ones(5))
+    e_off = vb.add([D.K_DEFAULT_EPSILON])
+    y_off = vb.add_many(ys)
+    mu_off = vb.add([0.0])
+    n = 20
+    keys = [(D.TYPE_VECTOR, x_off, 5, 5)]
+    barron = (
+        D.KIND_BARRON,
+        np.array([np.full(n, x_off), y_off, np.full(n, mu_off), np.full(n, e_off)]),
+        np.zeros((1, n), dtype=np.int32),
+        np.arange(n),
+    )
+    p = params if params is not None else D.default_params()
+    prob = D.Problem(vb.data(), keys, [barron], params=p, epsilon=1e-12)
+    prob.meta = dict(mu_off=int(mu_off), x_off=int(x_off))
+    return prob

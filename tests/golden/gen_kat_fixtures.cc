@@ -6,6 +6,7 @@
 //   pose_smoothing      test/symforce_optimizer_test.cc:79-134   (10 Pose3, prior_start.Retract(0.4*N6))
 //   rotation_smoothing  test/symforce_optimizer_test.cc:183-236  (10 Rot3, identity.Retract(0.4*N3))
 //   frozen_keys         test/symforce_optimizer_test.cc:276-312  (3 Rot3, FromTangent(0.4*N3))
+//   gnc_test            test/symforce_gnc_test.cc:33-42          (20 Vector5, 3 outliers)
 // Build & run:  g++ -O2 -std=c++17 gen_kat_fixtures.cc -o /tmp/gen_kat && /tmp/gen_kat > kat_initial_values.json
 #include <cmath>
 #include <cstdio>
@@ -98,7 +99,19 @@ int main() {
       rot3_from_tangent(v, q);
       out.insert(out.end(), q, q + 4);
     }
-    print_arr("frozen_keys", out, true);
+    print_arr("frozen_keys", out, false);
+  }
+  {
+    // test/symforce_gnc_test.cc:33-42: 20 Vector5 samples y_i, the first 3 are outliers around 10
+    std::mt19937 gen(42);
+    std::vector<double> out;
+    for (int i = 0; i < 20; ++i) {
+      double v[5];
+      random_vec<5>(gen, v);
+      for (double& x : v) x = (i < 3 ? 10.0 : 0.0) + 0.1 * x;
+      out.insert(out.end(), v, v + 5);
+    }
+    print_arr("gnc_test", out, true);
   }
   std::printf("}\n");
   return 0;

@@ -36,3 +36,21 @@ def test_gnc_outer_loop_on_oracle():
     st3 = o3.optimize()
     assert sched2 == [0.0] and st2.n_iterations == st3.n_iterations and st2.status == st3.status
     assert np.array_equal(v2, o3.best_values())
+
+
+def test_reference_gnc_known_answers_on_oracle():
+    """test/symforce_gnc_test.cc:23-86 (the reference's own GNC test): 9 iteration records, |x| < 0.1, five times
+    closer to zero than the plain optimization with mu = 0, SUCCESS."""
+    prob = P.gnc_test()
+    o = O.OracleProblem(prob)
+    values = np.array(prob.values, dtype=np.float64, copy=True)
+    st, schedule = gnc_optimize(o, values, prob.meta["mu_off"], prob.params, GNC)
+    x_gnc = values[prob.meta["x_off"]:prob.meta["x_off"] + 5]
+    assert len(o.iterations()) == 9
+    assert st.status == D.STATUS_SUCCESS
+    assert np.linalg.norm(x_gnc) < 0.1
+    o2 = O.OracleProblem(prob)  # regular_optimized_values.Set('u', 0.0); sym::Optimize(params, factors, values)
+    o2.optimize()
+    v2 = o2.best_values()
+    x_regular = v2[prob.meta["x_off"]:prob.meta["x_off"] + 5]
+    assert np.linalg.norm(x_gnc) * 5 < np.linalg.norm(x_regular)

@@ -46,3 +46,31 @@ def test_continue_requires_a_preceding_optimize():
     with pytest.raises(RuntimeError, match="rc=1"):
         g.relax_damping_to_initial()
     g.close()
+
+
+def test_reference_gnc_known_answers():
+    """The reference's own GNC test (test/symforce_gnc_test.cc:23-86) on the GPU path -- gnc_factors::BarronFactor as a
+    device kind, the sample data of the test reproduced from mt19937(42) -- and parity with the oracle on it."""
+    prob = P.gnc_test()
+    g, o = capi.SfxProblem(prob), O.OracleProblem(prob)
+    vg = np.array(prob.values, dtype=np.float64, copy=True)
+    vo = vg.copy()
+    st_g, sched_g = gnc_optimize(g, vg, prob.meta["mu_off"], prob.params, GNC)
+    st_o, sched_o = gnc_optimize(o, vo, prob.meta["mu_off"], prob.params, GNC)
+    x0 = prob.meta["x_off"]
+    x_gnc = vg[x0:x0 + 5]
+    assert len(g.iterations()) == 9                      # CHECK(gnc_stats.iterations.size() == 9)
+    assert np.linalg.norm(x_gnc) < 0.1                   # CHECK(gnc_optimized_x.norm() < 0.1)
+    assert st_g.status == D.STATUS_SUCCESS
+    g2 = capi.SfxProblem(prob)                           # the plain optimization with u = 0
+    g2.optimize()
+    x_regular = g2.best_values()[x0:x0 + 5]
+    assert np.linalg.norm(x_gnc) * 5 < np.linalg.norm(x_regular)
+    # parity with the oracle
+    assert sched_g == sched_o
+    for a, b in zip(g.iterations(), o.iterations()):
+        assert a.iteration == b.iteration and a.update_accepted == b.update_accepted
+        assert abs(a.new_error - b.new_error) <= COST_TOL * abs(b.new_error)
+    assert np.allclose(vg, vo, rtol=1e-7, atol=1e-9)
+    g.close()
+    g2.close()

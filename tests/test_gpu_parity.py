@@ -269,6 +269,9 @@ def test_cpp_examples_through_sym_layer():
     out = subprocess.run([os.path.join(root, "examples", "_build", "bundle_adjustment")], capture_output=True, text=True,
                          timeout=120)
     assert out.returncode == 0 and "GNC_OK" in out.stdout, out.stdout + out.stderr
+    # the reference's own GNC test (test/symforce_gnc_test.cc) written against the sym:: layer
+    out = subprocess.run([os.path.join(root, "examples", "_build", "gnc_test")], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0 and "GNC_TEST_OK" in out.stdout, out.stdout + out.stderr
     out = subprocess.run([os.path.join(root, "examples", "_build", "bundle_adjustment_in_the_large"), "--synthetic",
                           "12", "400", "5"], capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stdout + out.stderr

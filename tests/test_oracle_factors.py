@@ -22,6 +22,10 @@ def random_args(kind, rng):
     for name, dim in zip(meta["arg_names"], meta["arg_dims"]):
         if name == "epsilon":
             a = np.array([D.K_DEFAULT_EPSILON])
+        elif name == "eps":  # barron: kEpsilon of test/symforce_gnc_test.cc:23
+            a = np.array([1e-12])
+        elif name == "mu":
+            a = np.array([rng.uniform(0.0, 0.99)])
         elif dim == 7:  # Pose3
             q = rng.normal(size=4)
             q /= np.linalg.norm(q)

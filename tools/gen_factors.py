@@ -17,6 +17,7 @@ Residual definitions used (reference file:line):
   between / prior         symforce/codegen/geo_factors_codegen.py:53-86
   matching / odometry     symforce/examples/robot_3d_localization/robot_3d_localization.py:115-150
   inverse-range landmark  symforce/codegen/slam_factors_codegen.py:28-50, 162-229
+  barron (GNC test)       test/symforce_gnc_codegen_test.py:24-33
 
 Two files are written, from the same expression DAG but as independent translation units:
   symforce_b200/csrc/gen/factors_gen.cuh   (__device__ functions used by the CUDA linearize kernels)
@@ -199,6 +200,21 @@ def build_kinds():
         ("epsilon", eps),
     ]
     add("prior_rot3", a, ["value"], geo_factors_codegen.prior_factor(*[x[1] for x in a]))
+
+    # 9: Barron-robust difference of two 5-vectors, the factor of the reference's GNC test
+    # (test/symforce_gnc_codegen_test.py:24-33, generated as gnc_factors::BarronFactor and used by
+    # test/symforce_gnc_test.cc:44-48): whiten(x - y) with alpha = compute_alpha_from_mu(mu, eps), delta = 1
+    from symforce.opt.noise_models import BarronNoiseModel  # noqa: PLC0415
+
+    a = [
+        ("x", sf.V5.symbolic("x")),
+        ("y", sf.V5.symbolic("y")),
+        ("mu", sf.Symbol("mu")),
+        ("eps", sf.Symbol("eps")),
+    ]
+    alpha = BarronNoiseModel.compute_alpha_from_mu(a[2][1], a[3][1])
+    noise_model = BarronNoiseModel(alpha=alpha, delta=1, scalar_information=1, x_epsilon=a[3][1])
+    add("barron", a, ["x"], noise_model.whiten(a[0][1] - a[1][1]))
     return kinds
 
 

@@ -732,6 +732,7 @@ struct Problem {
 
   void build(const sfx_problem_desc& d);
   void relinearize(const std::vector<double>& values, Linearization& lin);
+  void jacobian(const std::vector<double>& values, Csc& jac) const;
   void damp(std::vector<double>& H, double lam);
   void undamp(std::vector<double>& H);
   void analyze(const Csc& A);
@@ -948,6 +949,45 @@ void Problem::relinearize(const std::vector<double>& values, Linearization& lin)
   lin.initialized = true;
   tm.linearize += now_s() - t0;
   tm.n_lin++;
+}
+
+// Linearization::jacobian with include_jacobians (linearizer.cc:252-259, 297-313): one triplet per entry of every
+// factor's dense Jacobian block over its optimized keys, in factor order, compressed like Eigen's setFromTriplets
+// (column-major, rows ascending, duplicates summed) into an M x N CSC matrix.
+void Problem::jacobian(const std::vector<double>& values, Csc& jac) const {
+  struct Trip {
+    int row, col;
+    double v;
+  };
+  std::vector<Trip> trips;
+  double res[8], J[8 * 16];
+  const double* a[ORC_MAX_ARGS];
+  for (const FactorHelper& h : factors) {
+    const orc_kind_meta& km = ORC_KIND_META[h.kind];
+    for (int k = 0; k < km.n_args; ++k) a[k] = values.data() + h.arg_off[k];
+    eval_factor(h.kind, a, res, J);
+    const int R = km.res_dim;
+    for (const KeyHelper& kh : h.keys)
+      for (int c = 0; c < kh.tangent_dim; ++c)
+        for (int r = 0; r < R; ++r)
+          trips.push_back(Trip{h.res_off + r, kh.combined_offset + c, J[r + (kh.factor_offset + c) * R]});
+  }
+  std::stable_sort(trips.begin(), trips.end(),
+                   [](const Trip& x, const Trip& y) { return x.col != y.col ? x.col < y.col : x.row < y.row; });
+  jac.n = N;
+  jac.outer.assign(N + 1, 0);
+  jac.inner.clear();
+  jac.val.clear();
+  for (size_t i = 0; i < trips.size(); ++i) {
+    if (i > 0 && trips[i].col == trips[i - 1].col && trips[i].row == trips[i - 1].row) {
+      jac.val.back() += trips[i].v;
+      continue;
+    }
+    jac.inner.push_back(trips[i].row);
+    jac.val.push_back(trips[i].v);
+    jac.outer[trips[i].col + 1]++;
+  }
+  for (int j = 0; j < N; ++j) jac.outer[j + 1] += jac.outer[j];
 }
 
 // DampHessian (levenberg_marquardt_solver.tcc:23-54)
@@ -1329,6 +1369,19 @@ int orc_linearize(void* p, double* residual, double* rhs, double* H) {
     if (residual) std::copy(P->cur_lin.residual.begin(), P->cur_lin.residual.end(), residual);
     if (rhs) std::copy(P->cur_lin.rhs.begin(), P->cur_lin.rhs.end(), rhs);
     if (H) std::copy(P->cur_lin.H.begin(), P->cur_lin.H.end(), H);
+  });
+}
+
+// jacobian at the values last set: pass outer == NULL to query nnz only; any output may be NULL
+int orc_linearize_jacobian(void* p, int64_t* nnz, int32_t* outer, int32_t* inner, double* values) {
+  ORC_TRY(p, {
+    Problem* P = (Problem*)p;
+    orc::Csc jac;
+    P->jacobian(P->cur_values, jac);
+    if (nnz) *nnz = (int64_t)jac.inner.size();
+    if (outer) std::copy(jac.outer.begin(), jac.outer.end(), outer);
+    if (inner) std::copy(jac.inner.begin(), jac.inner.end(), inner);
+    if (values) std::copy(jac.val.begin(), jac.val.end(), values);
   });
 }
 

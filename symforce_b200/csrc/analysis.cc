@@ -975,4 +975,78 @@ void build_csc(Analysis& a) {
   a.csc_built = true;
 }
 
+// Reference layout of Linearization::jacobian (include_jacobians; linearizer.cc:252-259, 297-313): M x N CSC, one
+// entry per (residual row of a factor, tangent column of one of its optimized keys), rows ascending inside a column,
+// i.e. factors in residual order.  All columns of a key hold the same rows, so a factor's R x dim(key) block sits at
+// base + c * colnnz(key) + r: `jac_base` / `jac_colnnz` per (optimized arg, slot) are what jacobian_kernel scatters with.
+void build_jacobian_csc(Analysis& a) {
+  if (a.jac_built) return;
+  SFX_CHECK(a.world == 1, SFX_ERR_UNSUPPORTED, "the Jacobian export is single-GPU");
+  std::vector<int> int2ref(a.N);
+  for (int r = 0; r < a.N; ++r) int2ref[a.ref2int[r]] = r;
+  std::vector<int> key_of_toff(a.N, -1);  // reference tangent offset of a key's first scalar -> key
+  for (int k = 0; k < a.n_keys; ++k) key_of_toff[a.keys[k].ref_toff] = k;
+  struct Ent {
+    int key, res_off, res_dim, batch, opt, slot;
+  };
+  std::vector<Ent> ents;
+  std::vector<uint64_t> ekey;
+  for (size_t b = 0; b < a.batches.size(); ++b) {
+    BatchPlan& bp = a.batches[b];
+    const sfx_kind_meta& km = SFX_KIND_META[bp.kind];
+    bp.jac_base.assign((size_t)bp.n_opt * bp.n, -1);
+    bp.jac_colnnz.assign((size_t)bp.n_opt * bp.n, 0);
+    for (int o = 0; o < bp.n_opt; ++o) {
+      const int g = bp.key_group[o];
+      if (g < 0) continue;
+      for (int s = 0; s < bp.n; ++s) {
+        const int key = key_of_toff[int2ref[bp.rhs_off[(size_t)g * bp.n + s] + bp.key_sub[o]]];
+        SFX_CHECK(key >= 0 && a.keys[key].tdim == km.opt_dims[o], SFX_ERR_STRUCTURE, "Jacobian index: key lookup");
+        ents.push_back(Ent{key, bp.res_off[s], km.res_dim, (int)b, o, s});
+        ekey.push_back(((uint64_t)key << 32) | (uint32_t)bp.res_off[s]);
+      }
+    }
+  }
+  std::vector<uint32_t> order;
+  stable_order_by_key(ekey.data(), ekey.size(), order);  // by (key, residual offset)
+  a.jac_outer.assign(a.N + 1, 0);
+  int64_t nnz = 0;
+  size_t i = 0;
+  std::vector<int64_t> key_begin(a.n_keys + 1, 0);  // CSC position of column 0 of each key
+  std::vector<int> key_colnnz(a.n_keys, 0);
+  for (int k = 0; k < a.n_keys; ++k) {  // keys are in reference (state vector) order
+    key_begin[k] = nnz;
+    int rows = 0;
+    while (i < order.size() && ents[order[i]].key == k) {
+      const Ent& e = ents[order[i]];
+      BatchPlan& bp = a.batches[e.batch];
+      SFX_CHECK(nnz + rows < (int64_t)INT32_MAX, SFX_ERR_UNSUPPORTED,
+                "jacobian has >= 2^31 nonzeros (reference limit, linearizer.cc:303-311)");
+      bp.jac_base[(size_t)e.opt * bp.n + e.slot] = (int32_t)(nnz + rows);
+      rows += e.res_dim;
+      ++i;
+    }
+    key_colnnz[k] = rows;
+    for (int c = 0; c < a.keys[k].tdim; ++c) {
+      nnz += rows;
+      SFX_CHECK(nnz < (int64_t)INT32_MAX, SFX_ERR_UNSUPPORTED,
+                "jacobian has >= 2^31 nonzeros (reference limit, linearizer.cc:303-311)");
+      a.jac_outer[a.keys[k].ref_toff + c + 1] = (int32_t)nnz;
+    }
+  }
+  key_begin[a.n_keys] = nnz;
+  a.jac_nnz = nnz;
+  a.jac_inner.resize(nnz);
+  for (size_t q = 0; q < order.size(); ++q) {
+    const Ent& e = ents[order[q]];
+    BatchPlan& bp = a.batches[e.batch];
+    const int cn = key_colnnz[e.key];
+    bp.jac_colnnz[(size_t)e.opt * bp.n + e.slot] = cn;
+    const int64_t base = bp.jac_base[(size_t)e.opt * bp.n + e.slot];
+    for (int c = 0; c < a.keys[e.key].tdim; ++c)
+      for (int r = 0; r < e.res_dim; ++r) a.jac_inner[base + (int64_t)c * cn + r] = e.res_off + r;
+  }
+  a.jac_built = true;
+}
+
 }  // namespace sfx

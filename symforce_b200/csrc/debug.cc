@@ -61,6 +61,11 @@ extern "C" int sfx_debug_analysis_json(const sfx_problem_desc* d, char** out) {
     arr(o, "csc_outer", a.csc_outer);
     arr(o, "csc_inner", a.csc_inner);
     arr(o, "csc_src", a.csc_src);
+    if (a.world == 1) {
+      build_jacobian_csc(a);
+      arr(o, "jac_outer", a.jac_outer);
+      arr(o, "jac_inner", a.jac_inner);
+    }
     o << "\"batches\":[";
     for (size_t b = 0; b < a.batches.size(); ++b) {
       const BatchPlan& bp = a.batches[b];
@@ -75,6 +80,8 @@ extern "C" int sfx_debug_analysis_json(const sfx_problem_desc* d, char** out) {
       arr(o, "rhs_off", bp.rhs_off);
       arr(o, "diag_off", bp.diag_off);
       arr(o, "off_off", bp.off_off);
+      arr(o, "jac_base", bp.jac_base);
+      arr(o, "jac_colnnz", bp.jac_colnnz);
       arr(o, "factor_index", bp.factor_index, false);
       o << '}';
     }

@@ -78,6 +78,10 @@ struct BatchPlan {
   std::vector<int32_t> diag_off;  // [n_groups][n] value offset of the node's diagonal block
   std::vector<uint32_t> off_off;  // [n_groups*(n_groups-1)/2][n] off-diagonal block offset | flags
   std::vector<int32_t> factor_index;  // [n] caller's factor index of each slot
+  // Jacobian export (build_jacobian_csc): per optimized arg and slot, the position of entry (row 0, column 0) of the
+  // factor's Jacobian block in the CSC value array (-1: key is fixed) and the entry count of that key's columns
+  std::vector<int32_t> jac_base;    // [n_opt][n]
+  std::vector<int32_t> jac_colnnz;  // [n_opt][n]
 };
 constexpr uint32_t kOffExclusive = 0x80000000u;  // block has exactly one contributor: plain store
 constexpr uint32_t kOffTransposed = 0x40000000u; // node(g) < node(h): write the transpose
@@ -162,10 +166,15 @@ struct Analysis {
   std::vector<int32_t> csc_outer, csc_inner;
   std::vector<int32_t> csc_src;  // per CSC entry: H value offset
   int64_t nnz = 0;
+  // Jacobian CSC (reference layout of Linearization::jacobian, M x N); built lazily
+  bool jac_built = false;
+  std::vector<int32_t> jac_outer, jac_inner;
+  int64_t jac_nnz = 0;
 };
 
 void analyze_problem(const sfx_problem_desc& d, Analysis& a);
 void build_csc(Analysis& a);
+void build_jacobian_csc(Analysis& a);
 void build_front_plan(const BlockMatrix& A, int ordering, const std::vector<int>& ref_scalar_of_sys /* may be empty */,
                       FrontPlan& fp);
 

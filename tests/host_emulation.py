@@ -247,3 +247,37 @@ def emulate_solve_step(problem, A, lam):
     else:
         upd = -emulate_fronts_solve(A, Hv, rhs, dvec)
     return upd[np.array(A["ref2int"])], (res, rhs[np.array(A["ref2int"])], Hv[np.array(A["csc_src"])])
+
+
+def emulate_jacobian(problem, A):
+    """What jacobian_kernel writes: every factor's R x dim(key) Jacobian block at jac_base + c * jac_colnnz + r."""
+    lib = O.load()
+    vals = problem.values
+    out = np.full(len(A["jac_inner"]), np.nan)
+    for b in A["batches"]:
+        meta = D.KINDS[b["kind"]]
+        n = b["n"]
+        used = b["used_args"]
+        arg_off = np.array(b["arg_off"]).reshape(len(used), n)
+        n_opt = len(meta["opt_dims"])
+        base = np.array(b["jac_base"]).reshape(n_opt, n)
+        coln = np.array(b["jac_colnnz"]).reshape(n_opt, n)
+        cols = np.concatenate([[0], np.cumsum(meta["opt_dims"])])
+        for s in range(n):
+            args = []
+            for ai, dim in enumerate(meta["arg_dims"]):
+                if ai in used:
+                    o = arg_off[used.index(ai), s]
+                    args.append(vals[o:o + dim])
+                else:
+                    args.append(np.zeros(dim))
+            r, J = factor_J(lib, b["kind"], args)
+            for ka in range(n_opt):
+                if base[ka, s] < 0:
+                    assert b["key_group"][ka] < 0
+                    continue
+                for c in range(meta["opt_dims"][ka]):
+                    p0 = base[ka, s] + c * coln[ka, s]
+                    assert np.all(np.isnan(out[p0:p0 + len(r)])), "two factors write the same Jacobian entries"
+                    out[p0:p0 + len(r)] = J[:, cols[ka] + c]
+    return out

@@ -53,6 +53,19 @@ class OracleProblem(D._LibProblem):
     def _last_error(self):
         return self.lib.orc_last_error().decode()
 
+    def jacobian(self):
+        """Linearization::jacobian at the values last set, as (outer, inner, values) of the M x N CSC matrix."""
+        nnz = C.c_int64()
+        self._check(self.lib.orc_linearize_jacobian(self.h, C.byref(nnz), None, None, None), "linearize_jacobian")
+        N, _, _ = self.dims()
+        outer = np.empty(N + 1, dtype=np.int32)
+        inner = np.empty(nnz.value, dtype=np.int32)
+        val = np.empty(nnz.value)
+        self._check(self.lib.orc_linearize_jacobian(self.h, None, outer.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                    inner.ctypes.data_as(C.POINTER(C.c_int32)),
+                                                    val.ctypes.data_as(C.POINTER(C.c_double))), "linearize_jacobian")
+        return outer, inner, val
+
     def timings(self):
         out = (C.c_double * 8)()
         self.lib.orc_get_timings(self.h, out)

@@ -106,6 +106,32 @@ def test_host_maps_random_bal_shapes(seed, monkeypatch):
     assert np.allclose(upd, upd_o, rtol=1e-8, atol=1e-9 * max(1e-3, np.abs(upd_o).max()))
 
 
+@pytest.mark.parametrize("name", ["pose_smoothing", "frozen_keys", "robot3d", "ba_example", "bal_tiny_schur",
+                                  "bal_tiny_chol", "pose_graph_small"])
+def test_jacobian_index_maps_reproduce_oracle(name):
+    """include_jacobians (linearizer.cc:252-259, 297-313): the CSC pattern of Linearization::jacobian built by the host
+    analysis is the oracle's (triplets compressed like setFromTriplets), the per-slot scatter positions fill every entry
+    exactly once, and J^T J / J^T r of the result are the Hessian and rhs."""
+    import scipy.sparse as sp
+
+    prob = PROBLEMS[name]()
+    A = capi.analysis_json(prob)
+    o = O.OracleProblem(prob)
+    outer, inner, val = o.jacobian()
+    assert np.array_equal(outer, np.array(A["jac_outer"]))
+    assert np.array_equal(inner, np.array(A["jac_inner"]))
+    got = E.emulate_jacobian(prob, A)
+    assert not np.isnan(got).any()
+    assert np.array_equal(got, val)
+    N, M, _ = o.dims()
+    J = sp.csc_matrix((got, inner, outer), shape=(M, N))
+    res, rhs, Hv = o.linearize()
+    ho, hi = o.hessian_pattern()
+    H = sp.csc_matrix((Hv, hi, ho), shape=(N, N)).toarray()
+    assert np.allclose(np.tril((J.T @ J).toarray()), H, rtol=0, atol=1e-12 * np.abs(H).max())
+    assert np.allclose(J.T @ res, rhs, rtol=0, atol=1e-12 * max(1.0, np.abs(rhs).max()))
+
+
 def test_bal_nodes_merge_pose_and_intrinsics():
     prob = P.bal_problem("tiny", solver=D.SOLVER_SCHUR)
     A = capi.analysis_json(prob)

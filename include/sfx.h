@@ -219,7 +219,8 @@ sfx_status sfx_get_best_values(sfx_problem* p, double* values, int64_t n);
  * optimization_iteration_t::values (the data of the Values buffer, whose index the caller already has) and
  * ::residual of iteration record `record` (0 = the record of iteration -1) of the last sfx_optimize[_continue],
  * which must have run with debug_stats set.  Either output may be NULL.  Costs iterations x (Values + residual)
- * of device memory; single GPU.  (jacobian_values / include_jacobians are not produced: the path never forms J.) */
+ * of device memory; single GPU.  (jacobian_values are not kept per iteration: the path never forms J; see
+ * sfx_linearize_jacobian for the Jacobian at given values.) */
 sfx_status sfx_get_iteration_debug(sfx_problem* p, int32_t record, double* values, double* residual);
 
 /* GncOptimizer::Optimize outer loop (symforce/opt/gnc_optimizer.h:53-130, OptimizeContinue :133-142):
@@ -253,6 +254,16 @@ sfx_status sfx_get_hessian_pattern(sfx_problem* p, int32_t* outer, int32_t* inne
  * to sfx_set_values.  Any output may be NULL.  hessian_values is in the CSC order of
  * sfx_get_hessian_pattern. */
 sfx_status sfx_linearize(sfx_problem* p, double* residual, double* rhs, double* hessian_values);
+
+/* Linearization::jacobian with optimizer_params_t::include_jacobians (symforce/opt/linearization.h:58-60;
+ * built by linearizer.cc:252-259, 297-313): the M x N Jacobian in CSC form, rows ascending in every column, one
+ * entry per (residual row of a factor, tangent column of one of its optimized keys).  The LM loop itself never
+ * forms J (it assembles J^T J and J^T r directly), so this is an export evaluated on request.
+ * sfx_get_jacobian_pattern: nnz, column pointers [N+1], row indices [nnz]; any output may be NULL.
+ * sfx_linearize_jacobian: values [nnz] at the values last given to sfx_set_values; leaves the optimizer state
+ * untouched.  Single GPU. */
+sfx_status sfx_get_jacobian_pattern(sfx_problem* p, int64_t* nnz, int32_t* outer, int32_t* inner);
+sfx_status sfx_linearize_jacobian(sfx_problem* p, double* jacobian_values);
 
 /* stats.best_linearization (populate_best_linearization, internal/optimizer_utils.h:71-76) */
 sfx_status sfx_get_best_linearization(sfx_problem* p, double* residual, double* rhs,

@@ -474,6 +474,7 @@ struct SparseMatrixCsc {
 struct SparseLinearization {
   std::vector<double> residual;
   SparseMatrixCsc hessian_lower;
+  SparseMatrixCsc jacobian;  // M x N, filled by Optimizer::Linearize when optimizer_params_t::include_jacobians is set
   std::vector<double> rhs;
   double Error() const {
     double s = 0;
@@ -819,6 +820,17 @@ class Optimizer {
     SparseLinearization lin;
     FillPattern(lin);
     Check(sfx_linearize(handle_, lin.residual.data(), lin.rhs.data(), lin.hessian_lower.values.data()));
+    if (params_.include_jacobians) {  // linearizer.cc:252-259, 297-313
+      int64_t nnz = 0;
+      Check(sfx_get_jacobian_pattern(handle_, &nnz, nullptr, nullptr));
+      lin.jacobian.rows_ = static_cast<int>(lin.residual.size());
+      lin.jacobian.cols_ = static_cast<int>(lin.rhs.size());
+      lin.jacobian.outer.resize(lin.rhs.size() + 1);
+      lin.jacobian.inner.resize(nnz);
+      lin.jacobian.values.resize(nnz);
+      Check(sfx_get_jacobian_pattern(handle_, nullptr, lin.jacobian.outer.data(), lin.jacobian.inner.data()));
+      Check(sfx_linearize_jacobian(handle_, lin.jacobian.values.data()));
+    }
     return lin;
   }
 

@@ -18,7 +18,8 @@ EXPORTS = [
     "sfx_default_params", "sfx_problem_create", "sfx_problem_destroy", "sfx_last_error", "sfx_update_params",
     "sfx_set_values", "sfx_optimize", "sfx_optimize_continue", "sfx_relax_damping_to_initial", "sfx_get_best_values",
     "sfx_update_best_values", "sfx_get_iteration_debug", "sfx_get_iterations", "sfx_get_dims",
-    "sfx_get_hessian_pattern", "sfx_linearize", "sfx_get_best_linearization", "sfx_solve_step",
+    "sfx_get_hessian_pattern", "sfx_linearize", "sfx_get_jacobian_pattern", "sfx_linearize_jacobian",
+    "sfx_get_best_linearization", "sfx_solve_step",
     "sfx_compute_covariance", "sfx_get_ordering", "sfx_get_timings", "sfx_get_info", "sfx_comm_unique_id", "sfx_comm_create",
     "sfx_comm_destroy",
 ]
@@ -130,6 +131,21 @@ class SfxProblem(D._LibProblem):
         self._check(self.lib.sfx_get_iteration_debug(self.h, C.c_int32(record), v.ctypes.data_as(p), r.ctypes.data_as(p)),
                     "get_iteration_debug")
         return v, r
+
+    def jacobian(self):
+        """Linearization::jacobian (include_jacobians) at the values last set: (outer, inner, values) of the M x N CSC."""
+        nnz = C.c_int64()
+        self._check(self.lib.sfx_get_jacobian_pattern(self.h, C.byref(nnz), None, None), "get_jacobian_pattern")
+        N, _, _ = self.dims()
+        outer = np.empty(N + 1, dtype=np.int32)
+        inner = np.empty(nnz.value, dtype=np.int32)
+        val = np.empty(nnz.value)
+        pi = C.POINTER(C.c_int32)
+        self._check(self.lib.sfx_get_jacobian_pattern(self.h, None, outer.ctypes.data_as(pi), inner.ctypes.data_as(pi)),
+                    "get_jacobian_pattern")
+        self._check(self.lib.sfx_linearize_jacobian(self.h, val.ctypes.data_as(C.POINTER(C.c_double))),
+                    "linearize_jacobian")
+        return outer, inner, val
 
     def compute_covariance(self, block_dim, hessian_values=None):
         """Optimizer::ComputeCovariances / ComputeFullCovariance: dense block_dim x block_dim covariance in keys_

@@ -654,6 +654,56 @@ void launch_linearize(cudaStream_t st, const Ctrl* ctrl, StatePtrs sp, int mode,
   }
 }
 
+// Linearization::jacobian export (include_jacobians): one thread per factor slot evaluates the factor and stores its
+// R x dim(key) Jacobian blocks into the reference's CSC value array; positions come from build_jacobian_csc (analysis.cc).
+// Debug / introspection path: never part of an LM iteration.
+template <int KIND>
+__global__ void __launch_bounds__(kLinThreads) jacobian_kernel(const double* __restrict__ values, LinBatch b,
+                                                                const int32_t* __restrict__ jac_base,
+                                                                const int32_t* __restrict__ jac_colnnz,
+                                                                double* __restrict__ out) {
+  using K = Kind<KIND>;
+  const int s = blockIdx.x * kLinThreads + threadIdx.x;
+  if (s >= b.n) return;
+  const double* a[K::NUSED];
+#pragma unroll
+  for (int u = 0; u < K::NUSED; ++u) a[u] = values + __ldg(b.arg_off + (size_t)u * b.n + s);
+  double res[K::R];
+  double J[K::R * K::T];
+  K::eval(a, res, J);
+#pragma unroll
+  for (int ka = 0; ka < K::NOPT; ++ka) {
+    const int base = __ldg(jac_base + (size_t)ka * b.n + s);
+    if (base < 0) continue;
+    const int cn = __ldg(jac_colnnz + (size_t)ka * b.n + s);
+#pragma unroll
+    for (int c = 0; c < K::dim(ka); ++c)
+#pragma unroll
+      for (int q = 0; q < K::R; ++q) out[(size_t)base + (size_t)c * cn + q] = J[q + (K::col(ka) + c) * K::R];
+  }
+}
+
+void launch_jacobian(cudaStream_t st, const double* values, const LinBatch& b, const int32_t* jac_base,
+                     const int32_t* jac_colnnz, double* out) {
+  if (b.n == 0) return;
+  const int grid = (b.n + kLinThreads - 1) / kLinThreads;
+  switch (b.kind) {
+#define SFX_CASE(ID) \
+  case ID: jacobian_kernel<ID><<<grid, kLinThreads, 0, st>>>(values, b, jac_base, jac_colnnz, out); ++g_launches; break;
+    SFX_CASE(SFX_KIND_SNAVELY)
+    SFX_CASE(SFX_KIND_BETWEEN_POSE3)
+    SFX_CASE(SFX_KIND_PRIOR_POSE3)
+    SFX_CASE(SFX_KIND_MATCHING)
+    SFX_CASE(SFX_KIND_ODOMETRY)
+    SFX_CASE(SFX_KIND_IRL_LINEAR_GNC)
+    SFX_CASE(SFX_KIND_IRL_PRIOR)
+    SFX_CASE(SFX_KIND_BETWEEN_ROT3)
+    SFX_CASE(SFX_KIND_PRIOR_ROT3)
+    SFX_CASE(SFX_KIND_BARRON)
+#undef SFX_CASE
+  }
+}
+
 void launch_finish_error(cudaStream_t st, Ctrl* ctrl, int mode, const double* partials, int n_partials) {
   finish_error_kernel<<<1, 1024, 0, st>>>(ctrl, partials, n_partials, mode); ++g_launches;
 }

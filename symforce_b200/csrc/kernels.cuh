@@ -171,6 +171,8 @@ cudaError_t configure_large_kernels();
 // launchers (all asynchronous on `st`)
 void launch_zero_lin(cudaStream_t st, const Ctrl* ctrl, StatePtrs sp, int mode, int64_t n_h, int n_rhs);
 void launch_linearize(cudaStream_t st, const Ctrl* ctrl, StatePtrs sp, int mode, const LinBatch& b, double* partials);
+void launch_jacobian(cudaStream_t st, const double* values, const LinBatch& b, const int32_t* jac_base,
+                     const int32_t* jac_colnnz, double* out);
 void launch_finish_error(cudaStream_t st, Ctrl* ctrl, int mode, const double* partials, int n_partials);
 void launch_damping(cudaStream_t st, Ctrl* ctrl, StatePtrs sp, const int32_t* diag_pos, int N, double* dvec,
                     double* max_diag);

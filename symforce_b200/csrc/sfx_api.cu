@@ -158,6 +158,7 @@ struct sfx_problem {
   int32_t* d_csc_src = nullptr;
   double* d_export = nullptr;
   int64_t export_cap = 0;
+  std::vector<const int32_t*> d_jac_base, d_jac_colnnz;  // per batch, uploaded by ensure_jacobian
   // timing
   std::vector<cudaEvent_t> ev;
   std::vector<int> ev_phase;  // phase ending at event i (event 0 = start)
@@ -928,6 +929,20 @@ void ensure_csc(sfx_problem* p) {
   }
 }
 
+// index maps of the Jacobian export, built and uploaded on first use
+void ensure_jacobian(sfx_problem* p) {
+  build_jacobian_csc(p->a);
+  if (p->d_jac_base.empty())
+    for (const auto& bp : p->a.batches) {
+      p->d_jac_base.push_back(p->pool.upload(bp.jac_base));
+      p->d_jac_colnnz.push_back(p->pool.upload(bp.jac_colnnz));
+    }
+  if (p->export_cap < p->a.jac_nnz) {
+    p->d_export = p->pool.alloc<double>(p->a.jac_nnz);
+    p->export_cap = p->a.jac_nnz;
+  }
+}
+
 void export_linearization(sfx_problem* p, int blk, double* residual, double* rhs, double* Hv) {
   Analysis& a = p->a;
   if (residual)
@@ -1326,6 +1341,30 @@ sfx_status sfx_linearize(sfx_problem* p, double* residual, double* rhs, double* 
   launch_copy_values(p->st, p->sp.values[0], p->d_cur_values, p->a.n_values);
   enqueue_linearize(p, 0);
   export_linearization(p, 0, residual, rhs, hessian_values);
+  SFX_API_END(p)
+}
+
+sfx_status sfx_get_jacobian_pattern(sfx_problem* p, int64_t* nnz, int32_t* outer, int32_t* inner) {
+  SFX_API_BEGIN
+  SFX_CHECK(p, SFX_ERR_INVALID_ARG, "null problem");
+  build_jacobian_csc(p->a);
+  if (nnz) *nnz = p->a.jac_nnz;
+  if (outer) std::copy(p->a.jac_outer.begin(), p->a.jac_outer.end(), outer);
+  if (inner) std::copy(p->a.jac_inner.begin(), p->a.jac_inner.end(), inner);
+  SFX_API_END(p)
+}
+
+sfx_status sfx_linearize_jacobian(sfx_problem* p, double* jacobian_values) {
+  SFX_API_BEGIN
+  SFX_CHECK(p && jacobian_values, SFX_ERR_INVALID_ARG, "null argument");
+  SFX_CHECK(p->values_set, SFX_ERR_INVALID_ARG, "sfx_set_values must be called first");
+  CUDA_OK(cudaSetDevice(p->device));
+  ensure_jacobian(p);
+  // a pure function of the values last set: the LM state (control block, linearizations) is not touched
+  for (size_t b = 0; b < p->lin.size(); ++b)
+    launch_jacobian(p->st, p->d_cur_values, p->lin[b], p->d_jac_base[b], p->d_jac_colnnz[b], p->d_export);
+  CUDA_OK(cudaMemcpyAsync(jacobian_values, p->d_export, sizeof(double) * p->a.jac_nnz, cudaMemcpyDeviceToHost, p->st));
+  CUDA_OK(cudaStreamSynchronize(p->st));
   SFX_API_END(p)
 }
 

@@ -341,10 +341,11 @@ class Factor:
 # Linearization (cc_sym.Linearization, symforce/opt/linearization.h:22-93)
 # ----------------------------------------------------------------------------------------------------------------
 class Linearization:
-    def __init__(self, residual, rhs, outer, inner, hvalues):
+    def __init__(self, residual, rhs, outer, inner, hvalues, jac=None):
         self.residual = residual
         self.rhs = rhs
         self._outer, self._inner, self._hvalues = outer, inner, hvalues
+        self._jac = jac  # (outer, inner, values) when OptimizerParams.include_jacobians
 
     @cached_property
     def hessian_lower(self):
@@ -353,9 +354,15 @@ class Linearization:
         n = self.rhs.shape[0]
         return sp.csc_matrix((self._hvalues, self._inner, self._outer), shape=(n, n))
 
-    @property
+    @cached_property
     def jacobian(self):
-        raise NotImplementedError("the GPU path assembles J^T J and J^T r directly and never forms the Jacobian")
+        """M x N sparse Jacobian (linearization.h:58-60); exported from the device when include_jacobians is set."""
+        if self._jac is None:
+            raise ValueError("jacobian is filled out when OptimizerParams.include_jacobians is True")
+        import scipy.sparse as sp
+
+        outer, inner, values = self._jac
+        return sp.csc_matrix((values, inner, outer), shape=(self.residual.shape[0], self.rhs.shape[0]))
 
     def error(self):
         return 0.5 * float(self.residual @ self.residual)
@@ -627,7 +634,8 @@ class Optimizer:
         gpu = self._device_problem(values)
         res, rhs, H = gpu.linearize()
         outer, inner = gpu.hessian_pattern()
-        return Linearization(res, rhs, outer, inner, H)
+        jac = gpu.jacobian() if self.params.include_jacobians else None
+        return Linearization(res, rhs, outer, inner, H, jac)
 
     def load_iteration_values(self, values_data) -> Values:
         """optimizer.py:366-381: a debug_stats iteration's values (flat storage) as a Python Values."""

@@ -5,7 +5,7 @@ import sys
 import numpy as np
 
 from symforce_b200.geo import K_DEFAULT_EPSILON
-from symforce_b200.opt import Factor, Optimizer, Rot3, Values, residuals
+from symforce_b200.opt import Factor, Optimizer, Pose3, Rot3, Values, residuals
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "examples", "python"))
@@ -35,3 +35,22 @@ def rotation_smoothing(num_samples=10, **kwargs):
     for i in range(num_samples):
         initial_values[x_priors[i]] = Rot3.from_yaw_pitch_roll(roll=0.1 * i)
     return optimizer, initial_values
+
+
+def bal_front(flat):
+    """A flat BAL problem (problems.bal_problem / read_bal) re-expressed with the front: Values c[j], i[j], p[k], P[n], e
+    and one Snavely factor per observation, keys as the reference example orders them
+    (bundle_adjustment_in_the_large.cc:61-118).  Returns (values, factors, optimized_keys)."""
+    m = flat.meta
+    nc, npt = m["n_cams"], m["n_pts"]
+    v = flat.values
+    values = Values()
+    values["c"] = [Pose3.from_storage(v[o:o + 7]) for o in flat.keys[:nc, 1]]
+    values["i"] = [v[o:o + 3].copy() for o in flat.keys[nc:2 * nc, 1]]
+    values["p"] = [v[o:o + 3].copy() for o in flat.keys[2 * nc:, 1]]
+    values["P"] = [v[o:o + 2].copy() for o in flat.batches[0][1][3]]
+    values["e"] = K_DEFAULT_EPSILON
+    factors = [Factor(keys=[f"c[{c}]", f"i[{c}]", f"p[{p}]", f"P[{n}]", "e"], residual=residuals.snavely)
+               for n, (c, p) in enumerate(zip(m["cam"], m["pt"]))]
+    keys = [f"c[{j}]" for j in range(nc)] + [f"i[{j}]" for j in range(nc)] + [f"p[{k}]" for k in range(npt)]
+    return values, factors, keys

@@ -311,3 +311,27 @@ def test_debug_stats_payloads(name):
     with pytest.raises(RuntimeError, match="rc=1"):
         g.iteration_debug(0)
     g.close()
+
+
+def test_bal_text_file_through_python_and_cpp(tmp_path):
+    """The same BAL text file through problems.read_bal + the C ABI and through the C++ example's reader
+    (examples/bundle_adjustment_in_the_large.cc, after bundle_adjustment_in_the_large.cc:61-140): same iteration records."""
+    import os
+    import re
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    path = str(tmp_path / "small.bal")
+    P.write_bal(path, P.bal_problem("small", solver=D.SOLVER_SCHUR))
+    g = capi.SfxProblem(P.read_bal(path))
+    g.optimize()
+    its = g.iterations()
+    subprocess.check_call(["make", "-s", "-C", os.path.join(root, "examples")])
+    out = subprocess.run([os.path.join(root, "examples", "_build", "bundle_adjustment_in_the_large"), path],
+                         capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert "600 points" in out.stdout
+    errs = [float(x) for x in re.findall(r"error: ([0-9.eE+-]+),", out.stdout)]
+    assert len(errs) == len(its)
+    for e, it in zip(errs, its):
+        assert abs(e - it.new_error) <= 1e-7 * abs(it.new_error)
+    g.close()

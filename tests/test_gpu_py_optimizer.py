@@ -8,6 +8,7 @@ import numpy as np
 import pytest
 
 from oracle import covariance_ref as R
+from symforce_b200 import capi, desc as D, problems as P
 from symforce_b200.opt import Optimizer, Pose3
 from tests import oracle_capi as O
 from tests import py_problems as PP
@@ -99,4 +100,27 @@ def test_linearize_and_covariances_through_the_front():
     assert all(np.array_equal(allk[k], by_key[k]) for k in by_key)
     with pytest.raises(ValueError, match="first optimized keys"):
         optimizer.compute_covariances(result.optimized_values, optimizer.optimized_keys[1:3])
+    optimizer.close()
+
+
+def test_bal_through_the_front_uses_the_schur_path():
+    """BAL keys c, i, p through the front: the trailing points are eliminated (solver 'auto'), and the run is the one
+    the flat problem gives through the C ABI."""
+    flat = P.bal_problem("small", solver=D.SOLVER_SCHUR)
+    values, factors, keys = PP.bal_front(flat)
+    optimizer = Optimizer(factors, keys, params=Optimizer.Params(lambda_update_type=Optimizer.Params().lambda_update_type.DYNAMIC))
+    result = optimizer.optimize(values)
+    assert optimizer.problem(values).solver == D.SOLVER_SCHUR
+    g = capi.SfxProblem(flat)
+    st = g.optimize()
+    its = g.iterations()
+    assert len(result.iterations) == len(its) and result.best_index == st.best_index
+    assert int(result.status) == st.status
+    for a, b in zip(result.iterations, its):
+        assert a.update_accepted == bool(b.update_accepted)
+        assert abs(a.new_error - b.new_error) <= 1e-8 * abs(b.new_error)
+    assert result.error() < 0.5 * result.iterations[0].new_error
+    pts = np.array([x for x in result.optimized_values["p"]])
+    assert pts.shape == (flat.meta["n_pts"], 3) and np.isfinite(pts).all()
+    g.close()
     optimizer.close()

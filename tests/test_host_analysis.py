@@ -169,3 +169,35 @@ def test_tile_task_lists_are_dependency_ordered():
                 assert n > 0, (kc, wt, nt, lib.sfx_last_error(None).decode())
     # the range tasks cut the task count of the final-shape level-1 fronts by ~3x
     assert lib.sfx_debug_verify_tasks(18, 41, 4) < lib.sfx_debug_verify_tasks(18, 41, 1) // 2
+
+
+def test_bal_text_file_round_trip(tmp_path):
+    """problems.read_bal reads the BAL text format the way the reference example does
+    (bundle_adjustment_in_the_large.cc:61-118); written from a synthetic problem and read back it gives the same
+    factors and keys and -- up to the sign of the camera quaternions, which the Rodrigues vector does not keep --
+    the same values, hence the same linearization in the oracle."""
+    a = P.bal_problem("tiny", solver=D.SOLVER_SCHUR)
+    path = str(tmp_path / "tiny.bal")
+    P.write_bal(path, a)
+    b = P.read_bal(path)
+    assert np.array_equal(a.keys, b.keys) and b.schur_num_keys == a.schur_num_keys
+    for x, y in zip(a.batches[0][1:], b.batches[0][1:]):
+        assert np.array_equal(x, y)
+    va, vb = a.values.copy(), b.values.copy()
+    for v in (va, vb):
+        q = v[a.meta["cam_off"]:a.meta["cam_off"] + 10 * a.meta["n_cams"]].reshape(-1, 10)
+        q[:, :4] *= np.sign(q[:, 3:4])
+    assert np.allclose(va, vb, rtol=0, atol=1e-14)
+    ra, ga, Ha = O.OracleProblem(a).linearize()
+    rb, gb, Hb = O.OracleProblem(b).linearize()
+    assert np.allclose(ra, rb, rtol=0, atol=1e-10) and np.allclose(Ha, Hb, rtol=1e-12, atol=1e-9 * np.abs(Ha).max())
+    # malformed files are rejected
+    with open(path, "a") as f:
+        f.write("1.0\n")
+    with pytest.raises(ValueError, match="expected"):
+        P.read_bal(path)
+    bad = str(tmp_path / "bad.bal")
+    with open(bad, "w") as f:
+        f.write("1 1 1\n0 5 1.0 2.0\n" + "0 " * 9 + "\n0 0 0\n")
+    with pytest.raises(ValueError, match="not in the file"):
+        P.read_bal(bad)

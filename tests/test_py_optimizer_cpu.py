@@ -143,22 +143,9 @@ def test_bal_lowering_picks_the_schur_solver():
     """A BAL-shaped problem through the front: keys c_j, i_j, p_k as the reference example orders them
     (bundle_adjustment_in_the_large.cc:61-118) -> the trailing points become the Schur block."""
     flat = P.bal_problem("tiny", solver=D.SOLVER_SCHUR)
-    m = flat.meta
-    nc, npt = m["n_cams"], m["n_pts"]
-    values = Values()
-    v = flat.values
-    cam_off = flat.keys[:nc, 1]
-    intr_off = flat.keys[nc:2 * nc, 1]
-    pt_off = flat.keys[2 * nc:, 1]
-    values["c"] = [Pose3.from_storage(v[o:o + 7]) for o in cam_off]
-    values["i"] = [v[o:o + 3].copy() for o in intr_off]
-    values["p"] = [v[o:o + 3].copy() for o in pt_off]
+    npt = flat.meta["n_pts"]
     kind, ao, ok, fi = flat.batches[0]
-    values["P"] = [v[o:o + 2].copy() for o in ao[3]]
-    values["e"] = K_DEFAULT_EPSILON
-    factors = [Factor(keys=[f"c[{c}]", f"i[{c}]", f"p[{p}]", f"P[{n}]", "e"], residual=residuals.snavely)
-               for n, (c, p) in enumerate(zip(m["cam"], m["pt"]))]
-    keys = [f"c[{j}]" for j in range(nc)] + [f"i[{j}]" for j in range(nc)] + [f"p[{k}]" for k in range(npt)]
+    values, factors, keys = PP.bal_front(flat)
     opt = Optimizer(factors, keys, params=Optimizer.Params(lambda_update_type=2))
     prob = opt.problem(values)
     assert prob.solver == D.SOLVER_SCHUR and prob.schur_num_keys == npt

@@ -1049,4 +1049,33 @@ void build_jacobian_csc(Analysis& a) {
   a.jac_built = true;
 }
 
+// BAL fast path: point -> observation slots of a Snavely batch (points identified by the value offset of their
+// diagonal block, group 1): `order` lists the slots grouped by point in ascending block offset, slot order kept inside
+// a point; ptr / diag / rhs describe the groups.  Consumed by bal_point_finalize_kernel.
+void build_point_lists(const BatchPlan& bp, std::vector<int32_t>& order, std::vector<int32_t>& ptr,
+                       std::vector<int32_t>& diag, std::vector<int32_t>& rhs) {
+  const int n = bp.n;
+  const int32_t* pd = bp.diag_off.data() + n;
+  const int32_t* pr = bp.rhs_off.data() + n;
+  {
+    RawBuf<uint64_t> key(n);  // stable radix order instead of a comparison sort of 5 M slots
+    parallel_chunks(n, [&](int64_t i0, int64_t i1) {
+      for (int64_t i = i0; i < i1; ++i) key[i] = (uint64_t)(uint32_t)pd[i];
+    });
+    std::vector<uint32_t> o;
+    stable_order_by_key(key.data(), (size_t)n, o);
+    order.assign(o.begin(), o.end());
+  }
+  ptr.clear();
+  diag.clear();
+  rhs.clear();
+  for (int i = 0; i < n; ++i)
+    if (i == 0 || pd[order[i]] != pd[order[i - 1]]) {
+      ptr.push_back(i);
+      diag.push_back(pd[order[i]]);
+      rhs.push_back(pr[order[i]]);
+    }
+  ptr.push_back(n);
+}
+
 }  // namespace sfx

@@ -203,6 +203,16 @@ extern "C" int sfx_debug_analysis_digest(const sfx_problem_desc* d, char** out) 
       digest(o, n + ".diag_off", bp.diag_off);
       digest(o, n + ".off_off", bp.off_off);
       digest(o, n + ".factor_index", bp.factor_index);
+      if (bp.kind == SFX_KIND_SNAVELY && bp.n_groups == 2) {
+        std::vector<int32_t> order, ptr, dg, rh;
+        PhaseClock clk;
+        build_point_lists(bp, order, ptr, dg, rh);
+        clk.lap("point lists");
+        digest(o, n + ".pf_slot", order);
+        digest(o, n + ".pf_ptr", ptr);
+        digest(o, n + ".pf_diag", dg);
+        digest(o, n + ".pf_rhs", rh);
+      }
     }
     if (a.schur) {
       const SchurPlan& s = a.sp;

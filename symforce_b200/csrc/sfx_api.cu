@@ -373,19 +373,8 @@ void upload_structures(sfx_problem* p) {
       lb.bal_fast = ok ? 1 : 0;
       if (ok && !getenv("SFX_POINT_ATOMICS")) {
         // point -> observation slots (points identified by the offset of their diagonal block)
-        std::vector<int32_t> order(bp.n);
-        for (int i = 0; i < bp.n; ++i) order[i] = i;
-        const int32_t* pd = bp.diag_off.data() + bp.n;
-        const int32_t* pr = bp.rhs_off.data() + bp.n;
-        std::stable_sort(order.begin(), order.end(), [&](int32_t x, int32_t y) { return pd[x] < pd[y]; });
-        std::vector<int32_t> ptr, diag, rhs;
-        for (int i = 0; i < bp.n; ++i)
-          if (i == 0 || pd[order[i]] != pd[order[i - 1]]) {
-            ptr.push_back(i);
-            diag.push_back(pd[order[i]]);
-            rhs.push_back(pr[order[i]]);
-          }
-        ptr.push_back(bp.n);
+        std::vector<int32_t> order, ptr, diag, rhs;
+        build_point_lists(bp, order, ptr, diag, rhs);
         lb.n_pf = (int)diag.size();
         lb.pf_exclusive = (a.batches.size() == 1 && getenv("SFX_PF_STORES")) ? 1 : 0;  // measured: plain stores are ~4% slower than REDs here
         lb.pf_ptr = P.upload(ptr);

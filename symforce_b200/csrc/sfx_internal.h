@@ -175,6 +175,8 @@ struct Analysis {
 void analyze_problem(const sfx_problem_desc& d, Analysis& a);
 void build_csc(Analysis& a);
 void build_jacobian_csc(Analysis& a);
+void build_point_lists(const BatchPlan& bp, std::vector<int32_t>& order, std::vector<int32_t>& ptr,
+                       std::vector<int32_t>& diag, std::vector<int32_t>& rhs);
 void build_front_plan(const BlockMatrix& A, int ordering, const std::vector<int>& ref_scalar_of_sys /* may be empty */,
                       FrontPlan& fp);
 

@@ -128,19 +128,19 @@ class OptimizerParams:
 # Values (symforce/values/values.py: ordered, nested; keys_recursive / items_recursive / to_storage)
 # ----------------------------------------------------------------------------------------------------------------
 def _leaf_storage(v):
-    """(type, storage list, tangent_dim) of one leaf, as cc_sym.Values.set stores it (sym::Values::Set, values.h:95-140:
-    scalars as 1 double, Eigen matrices column-major, geo types by StorageOps)."""
+    """(type, storage as a 1-D float64 array, tangent_dim) of one leaf, as cc_sym.Values.set stores it (sym::Values::Set,
+    values.h:95-140: scalars as 1 double, Eigen matrices column-major, geo types by StorageOps)."""
     if isinstance(v, Pose3):
-        return D.TYPE_POSE3, v.to_storage(), Pose3.TANGENT_DIM
+        return D.TYPE_POSE3, v.data, Pose3.TANGENT_DIM
     if isinstance(v, Rot3):
-        return D.TYPE_ROT3, v.to_storage(), Rot3.TANGENT_DIM
+        return D.TYPE_ROT3, v.data, Rot3.TANGENT_DIM
     if isinstance(v, (bool, int, float, np.integer, np.floating)):
-        return D.TYPE_VECTOR, [float(v)], 1
+        return D.TYPE_VECTOR, np.array([v], dtype=np.float64), 1
     if isinstance(v, np.ndarray):
         if v.ndim > 2:
             raise TypeError(f"arrays with {v.ndim} axes are not a Values leaf; use nested lists for the leading axes")
         flat = np.asarray(v, dtype=np.float64).reshape(-1, order="F")
-        return D.TYPE_VECTOR, [float(x) for x in flat], flat.shape[0]
+        return D.TYPE_VECTOR, flat, flat.shape[0]
     raise TypeError(f"unsupported Values leaf type {type(v).__name__}")
 
 
@@ -152,10 +152,6 @@ def _leaf_from_storage(template, data):
     if isinstance(template, np.ndarray):
         return np.asarray(data, dtype=np.float64).reshape(template.shape, order="F").copy()
     return float(data[0])
-
-
-def _is_container(v):
-    return isinstance(v, (Values, dict, list, tuple))
 
 
 class Values:
@@ -246,7 +242,7 @@ class Values:
     def to_storage(self):
         out = []
         for _, v in self.items_recursive():
-            out.extend(_leaf_storage(v)[1])
+            out.extend(float(x) for x in _leaf_storage(v)[1])
         return out
 
     def to_numerical(self):

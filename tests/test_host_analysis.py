@@ -201,3 +201,71 @@ def test_bal_text_file_round_trip(tmp_path):
         f.write("1 1 1\n0 5 1.0 2.0\n" + "0 " * 9 + "\n0 0 0\n")
     with pytest.raises(ValueError, match="not in the file"):
         P.read_bal(bad)
+
+
+def _random_pose_graph(seed):
+    """Random Pose3 graph: a chain plus random extra between factors and priors, a random subset of poses held fixed,
+    optimized keys in shuffled (not storage) order, factors of the two kinds interleaved in the caller's order."""
+    rng = np.random.default_rng(7000 + seed)
+    n = int(rng.integers(5, 40))
+    poses = np.concatenate([P.quat_exp(rng.normal(0, 0.5, (n, 3))), rng.normal(0, 2.0, (n, 3))], axis=1)
+    vb = P.ValuesBuilder()
+    pose_off = vb.add_many(poses)
+    eps_off = vb.add([D.K_DEFAULT_EPSILON])
+    frozen = rng.random(n) < 0.25
+    frozen[int(rng.integers(0, n))] = False
+    edges = [(i, i + 1) for i in range(n - 1)]
+    for _ in range(int(rng.integers(0, 2 * n))):
+        i, j = (int(x) for x in rng.integers(0, n, 2))
+        if i != j:
+            edges.append((i, j))
+    edges = [(i, j) for i, j in edges if not (frozen[i] and frozen[j])]
+    touched = set(i for e in edges for i in e)
+    priors = [i for i in range(n) if not frozen[i] and (i not in touched or rng.random() < 0.2)]
+    opt = [i for i in rng.permutation(n) if not frozen[i]]
+    key_of = {int(p): k for k, p in enumerate(opt)}
+    keys = [(D.TYPE_POSE3, int(pose_off[p]), 7, 6) for p in opt]
+    ne, npr = len(edges), len(priors)
+    meas = np.concatenate([P.quat_exp(rng.normal(0, 0.3, (ne + npr, 3))), rng.normal(0, 1.0, (ne + npr, 3))], axis=1)
+    meas_off = vb.add_many(meas)
+    si_off = vb.add_many(np.stack([np.diag(rng.uniform(0.5, 3.0, 6)).reshape(-1, order="F") for _ in range(ne + npr)]))
+    order = rng.permutation(ne + npr)  # caller's factor index of each factor
+    between = (
+        D.KIND_BETWEEN_POSE3,
+        np.array([[pose_off[i] for i, _ in edges], [pose_off[j] for _, j in edges], meas_off[:ne], si_off[:ne],
+                  np.full(ne, eps_off)]),
+        np.array([[key_of.get(i, -1) for i, _ in edges], [key_of.get(j, -1) for _, j in edges]]),
+        order[:ne],
+    )
+    batches = [between]
+    if npr:
+        batches.append((
+            D.KIND_PRIOR_POSE3,
+            np.array([[pose_off[i] for i in priors], meas_off[ne:], si_off[ne:], np.full(npr, eps_off)]),
+            np.array([[key_of[i] for i in priors]]),
+            order[ne:],
+        ))
+    ordering = [D.ORDERING_METIS_SCALAR, D.ORDERING_METIS_BLOCK, D.ORDERING_NATURAL][seed % 3]
+    return D.Problem(vb.data(), keys, batches, ordering=ordering)
+
+
+@pytest.mark.parametrize("seed", range(8))
+def test_host_maps_random_pose_graphs(seed, monkeypatch):
+    """Generic (non-BAL) path on random structures: fixed poses inside factors, shuffled key order, two factor kinds
+    interleaved by factor index, all three orderings; Hessian, rhs, LM step and the Jacobian maps against the oracle."""
+    monkeypatch.setenv("SFX_HOST_THREADS", str(1 + seed % 3))
+    prob = _random_pose_graph(seed)
+    A = capi.analysis_json(prob)
+    o = O.OracleProblem(prob)
+    outer, inner = o.hessian_pattern()
+    assert np.array_equal(outer, np.array(A["csc_outer"])) and np.array_equal(inner, np.array(A["csc_inner"]))
+    upd, (res, rhs, H) = E.emulate_solve_step(prob, A, 0.8)
+    res_o, rhs_o, H_o = o.linearize()
+    assert np.allclose(res, res_o, rtol=0, atol=1e-12 * max(1.0, np.abs(res_o).max()))
+    assert np.allclose(H, H_o, rtol=0, atol=1e-12 * max(1.0, np.abs(H_o).max()))
+    assert np.allclose(rhs, rhs_o, rtol=0, atol=1e-11 * max(1.0, np.abs(rhs_o).max()))
+    upd_o = o.solve_step(0.8)
+    assert np.allclose(upd, upd_o, rtol=1e-8, atol=1e-9 * max(1e-3, np.abs(upd_o).max()))
+    jo, ji, jv = o.jacobian()
+    assert np.array_equal(jo, np.array(A["jac_outer"])) and np.array_equal(ji, np.array(A["jac_inner"]))
+    assert np.array_equal(E.emulate_jacobian(prob, A), jv)

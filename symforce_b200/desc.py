@@ -2,8 +2,8 @@
 ctypes mirror of include/sfx.h (structs + enums) and a small builder that lowers a flat
 "values + keys + factor batches" problem into an `sfx_problem_desc`.
 
-This is host-side plumbing for the Python tests and bench.py; the drop-in for C++ callers is the
-`sym::` header layer under include/sym/ which produces the same descriptor.
+This is the plumbing underneath symforce_b200/opt.py (the Python `Optimizer`), the tests and bench.py; the drop-in for
+C++ callers is the `sym::` header layer under include/sym/ which produces the same descriptor.
 """
 import ctypes as C
 import json

@@ -54,3 +54,18 @@ def test_reference_gnc_known_answers_on_oracle():
     v2 = o2.best_values()
     x_regular = v2[prob.meta["x_off"]:prob.meta["x_off"] + 5]
     assert np.linalg.norm(x_gnc) * 5 < np.linalg.norm(x_regular)
+
+
+def test_cpp_gnc_example_builds_the_fixture_data():
+    """examples/gnc_test.cc draws its samples with sym::Random on std::mt19937(42) like the reference test; the values it
+    hands to the optimizer are the committed fixture the oracle / GPU tests use (host-only run: no GPU needed)."""
+    import subprocess
+
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "examples"), "_build/gnc_test"])
+    out = subprocess.run([os.path.join(ROOT, "examples", "_build", "gnc_test")], capture_output=True, text=True,
+                         env=dict(os.environ, GNC_TEST_PRINT_VALUES="1"), timeout=60)
+    assert out.returncode == 0, out.stderr
+    got = np.array([float(x) for x in out.stdout.split()])
+    want = P.gnc_test().values
+    assert got.shape[0] == want.shape[0] - 1  # the Values of the test get `u` later, from GncOptimizer::Optimize
+    assert np.array_equal(got, want[:-1])

@@ -476,9 +476,17 @@ struct SparseLinearization {
   SparseMatrixCsc hessian_lower;
   SparseMatrixCsc jacobian;  // M x N, filled by Optimizer::Linearize when optimizer_params_t::include_jacobians is set
   std::vector<double> rhs;
+  bool IsInitialized() const { return !rhs.empty(); }
   double Error() const {
     double s = 0;
     for (double r : residual) s += r * r;
+    return 0.5 * s;
+  }
+  // linearization.h:62-67: change in error the linear model predicts for an update solved with the given damping
+  double LinearDeltaError(const std::vector<double>& x_update, const std::vector<double>& damping_vector) const {
+    SYM_ASSERT(x_update.size() == rhs.size() && damping_vector.size() == rhs.size());
+    double s = 0;
+    for (size_t i = 0; i < rhs.size(); ++i) s += x_update[i] * (rhs[i] - damping_vector[i] * x_update[i]);
     return 0.5 * s;
   }
 };
@@ -758,6 +766,10 @@ class Optimizer {
   virtual void Optimize(Values<Scalar>& values, int num_iterations, bool populate_best_linearization, Stats& stats) {
     OptimizeImpl(values, num_iterations, populate_best_linearization, stats, /*continue_previous=*/false);
   }
+  // the two shorter forms of optimizer.h:159, 172
+  void Optimize(Values<Scalar>& values, int num_iterations, Stats& stats) { Optimize(values, num_iterations, false, stats); }
+  void Optimize(Values<Scalar>& values, Stats& stats) { Optimize(values, -1, false, stats); }
+  const std::string& GetName() const { return name_; }
 
  protected:
   // OptimizeImpl (internal/optimizer_utils.h:78-101), or -- continue_previous -- GncOptimizer::OptimizeContinue

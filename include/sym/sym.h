@@ -172,6 +172,28 @@ class Rot3 {
   Rot3 Retract(const Vector3<Scalar>& v, Scalar epsilon = kDefaultEpsilon<Scalar>) const {
     return Compose(Rot3(FromTangent(v, epsilon).Data(), false));
   }
+  Rot3 Inverse() const {
+    DataVec d = data_;
+    d[0] = -d[0];
+    d[1] = -d[1];
+    d[2] = -d[2];
+    return Rot3(d, false);
+  }
+  Rot3 Between(const Rot3& b) const { return Inverse().Compose(b); }
+  // gen/cpp/sym/ops/rot3/lie_group_ops.cc:39-60: log map with |w| clamped to 1 - epsilon, sign taken from w
+  Vector3<Scalar> ToTangent(Scalar epsilon = kDefaultEpsilon<Scalar>) const {
+    const Scalar w = data_[3];
+    const Scalar wc = std::min<Scalar>(std::fabs(w), Scalar(1) - epsilon);
+    const Scalar sign = w < 0 ? Scalar(-1) : Scalar(1);
+    const Scalar s = 2 * sign * std::acos(wc) / std::sqrt(Scalar(1) - wc * wc);
+    Vector3<Scalar> v;
+    for (int i = 0; i < 3; ++i) v[i] = s * data_[i];
+    return v;
+  }
+  // tangent v with this->Retract(v) == b
+  Vector3<Scalar> LocalCoordinates(const Rot3& b, Scalar epsilon = kDefaultEpsilon<Scalar>) const {
+    return Between(b).ToTangent(epsilon);
+  }
   Vector3<Scalar> Rotate(const Vector3<Scalar>& p) const {
     const Scalar x = data_[0], y = data_[1], z = data_[2], w = data_[3];
     const Scalar tx = 2 * (y * p[2] - z * p[1]), ty = 2 * (z * p[0] - x * p[2]), tz = 2 * (x * p[1] - y * p[0]);
@@ -230,6 +252,25 @@ class Pose3 {
       t[i] += v[3 + i];
     }
     return Pose3(Rotation().Retract(w, epsilon), t);
+  }
+  Pose3 Inverse() const {
+    const Rot3<Scalar> Ri = Rotation().Inverse();
+    const Vector3<Scalar> t = Ri.Rotate(Position());
+    return Pose3(Ri, Vector3<Scalar>(-t[0], -t[1], -t[2]));
+  }
+  Pose3 Compose(const Pose3& b) const {
+    const Vector3<Scalar> rt = Rotation().Rotate(b.Position()), t = Position();
+    return Pose3(Rotation().Compose(b.Rotation()), Vector3<Scalar>(rt[0] + t[0], rt[1] + t[1], rt[2] + t[2]));
+  }
+  // gen/cpp/sym/ops/pose3/lie_group_ops.cc:105-140: [rotation local coordinates, translation difference]
+  Vector6<Scalar> LocalCoordinates(const Pose3& b, Scalar epsilon = kDefaultEpsilon<Scalar>) const {
+    const Vector3<Scalar> w = Rotation().LocalCoordinates(b.Rotation(), epsilon);
+    Vector6<Scalar> v;
+    for (int i = 0; i < 3; ++i) {
+      v[i] = w[i];
+      v[3 + i] = b.data_[4 + i] - data_[4 + i];
+    }
+    return v;
   }
   const DataVec& Data() const { return data_; }
 
@@ -399,9 +440,156 @@ class Values {
     return index;
   }
   size_t NumEntries() const { return map_.size(); }
+  bool Empty() const { return map_.empty(); }
   const std::vector<Scalar>& Data() const { return data_; }
   Scalar* DataPointer() { return data_.data(); }
   const MapType& Items() const { return map_; }
+
+  // values.cc:69-119: all keys, by default in storage order
+  std::vector<Key> Keys(const bool sort_by_offset = true) const {
+    std::vector<index_entry_t> entries = CreateIndex(sort_by_offset).entries;
+    std::vector<Key> keys;
+    keys.reserve(entries.size());
+    for (const index_entry_t& e : entries) keys.push_back(e.key);
+    return keys;
+  }
+  // values.cc:180-206: index of every key (tangent_dim is -1 when a key has no tangent space)
+  index_t CreateIndex(const bool sort_by_offset) const {
+    index_t index;
+    index.entries.reserve(map_.size());
+    for (const auto& kv : map_) {
+      index.entries.push_back(kv.second);
+      index.storage_dim += kv.second.storage_dim;
+      if (index.tangent_dim >= 0) index.tangent_dim = kv.second.tangent_dim >= 0 ? index.tangent_dim + kv.second.tangent_dim : -1;
+    }
+    if (sort_by_offset)
+      std::sort(index.entries.begin(), index.entries.end(),
+                [](const index_entry_t& a, const index_entry_t& b) { return a.offset < b.offset; });
+    return index;
+  }
+  std::optional<index_entry_t> MaybeIndexEntryAt(const Key& key) const {
+    auto it = map_.find(key);
+    if (it == map_.end()) return {};
+    return it->second;
+  }
+  // values.tcc: SetNew asserts that the key is new
+  template <typename T>
+  void SetNew(const Key& key, const T& value) {
+    const bool added = Set<T>(key, value);
+    if (!added) throw std::runtime_error("SYM_ASSERT: added -- key " + key.str() + " already exists");
+  }
+  // At / Set through an index entry (values.tcc:102-140)
+  template <typename T>
+  T At(const index_entry_t& entry) const {
+    using Tr = internal::StorageTraits<T>;
+    if (entry.type != Tr::kType || entry.storage_dim != Tr::kStorage)
+      throw std::runtime_error("Mismatched types; index entry is type " + std::to_string(static_cast<int>(entry.type)));
+    return Tr::From(data_.data() + entry.offset);
+  }
+  template <typename T>
+  void Set(const index_entry_t& entry, const T& value) {
+    using Tr = internal::StorageTraits<T>;
+    if (entry.type != Tr::kType || entry.storage_dim != Tr::kStorage)
+      throw std::runtime_error("Trying to set index entry of type " + std::to_string(static_cast<int>(entry.type)) +
+                               " with a value of another type");
+    SYM_ASSERT(entry.offset >= 0 && static_cast<size_t>(entry.offset + entry.storage_dim) <= data_.size());
+    std::copy(Tr::Ptr(value), Tr::Ptr(value) + Tr::kStorage, data_.begin() + entry.offset);
+  }
+  // values.cc:160-178: Remove drops the key only; Cleanup compacts the data array and returns the scalars freed
+  bool Remove(const Key& key) { return map_.erase(key) > 0; }
+  void RemoveAll() {
+    map_.clear();
+    data_.clear();
+  }
+  size_t Cleanup() {
+    const std::vector<Scalar> data_copy = data_;
+    const index_t full_index = CreateIndex(/* sort_by_offset = */ true);
+    data_.resize(full_index.storage_dim);
+    SYM_ASSERT(data_copy.size() >= data_.size());
+    size_t new_offset = 0;
+    for (const index_entry_t& entry : full_index.entries) {
+      std::copy_n(data_copy.begin() + entry.offset, entry.storage_dim, data_.begin() + new_offset);
+      map_[entry.key].offset = static_cast<int32_t>(new_offset);
+      new_offset += entry.storage_dim;
+    }
+    return data_copy.size() - data_.size();
+  }
+  // values.cc:262-287: copy the indexed entries from another Values (same layout / separately indexed layouts)
+  void Update(const index_t& index, const Values& other) {
+    SYM_ASSERT(data_.size() == other.data_.size());
+    for (const index_entry_t& entry : index.entries)
+      std::copy_n(other.data_.begin() + entry.offset, entry.storage_dim, data_.begin() + entry.offset);
+  }
+  void Update(const index_t& index_this, const index_t& index_other, const Values& other) {
+    SYM_ASSERT(index_this.entries.size() == index_other.entries.size());
+    for (size_t i = 0; i < index_this.entries.size(); ++i) {
+      const index_entry_t& entry_this = index_this.entries[i];
+      const index_entry_t& entry_other = index_other.entries[i];
+      SYM_ASSERT(entry_this.storage_dim == entry_other.storage_dim);
+      SYM_ASSERT(entry_this.key == entry_other.key);
+      std::copy_n(other.data_.begin() + entry_other.offset, entry_this.storage_dim, data_.begin() + entry_this.offset);
+    }
+  }
+  // values.cc:45-62: like Update for keys that exist here, appends the others
+  void UpdateOrSet(const index_t& index, const Values& other) {
+    for (const index_entry_t& entry_other : index.entries) {
+      auto it = map_.find(entry_other.key);
+      if (it == map_.end()) {
+        index_entry_t e = entry_other;
+        e.offset = static_cast<int32_t>(data_.size());
+        map_[e.key] = e;
+        data_.insert(data_.end(), other.data_.begin() + entry_other.offset,
+                     other.data_.begin() + entry_other.offset + entry_other.storage_dim);
+      } else {
+        SYM_ASSERT(it->second.storage_dim == entry_other.storage_dim);
+        std::copy_n(other.data_.begin() + entry_other.offset, entry_other.storage_dim, data_.begin() + it->second.offset);
+      }
+    }
+  }
+  // values.cc:315-327: x <- x (+) delta for the indexed keys, delta laid out in index order
+  void Retract(const index_t& index, const Scalar* delta, const Scalar epsilon) {
+    SYM_ASSERT(index.tangent_dim >= 0);
+    size_t tangent_inx = 0;
+    for (const index_entry_t& entry : index.entries) {
+      Scalar* t_ptr = data_.data() + entry.offset;
+      const Scalar* d = delta + tangent_inx;
+      if (entry.type == type_t::ROT3) {
+        const Rot3<Scalar> r = internal::StorageTraits<Rot3<Scalar>>::From(t_ptr).Retract(Vector3<Scalar>(d[0], d[1], d[2]), epsilon);
+        std::copy(r.Data().data(), r.Data().data() + 4, t_ptr);
+      } else if (entry.type == type_t::POSE3) {
+        const Pose3<Scalar> p = internal::StorageTraits<Pose3<Scalar>>::From(t_ptr).Retract(
+            Vector6<Scalar>(d[0], d[1], d[2], d[3], d[4], d[5]), epsilon);
+        std::copy(p.Data().data(), p.Data().data() + 7, t_ptr);
+      } else {
+        for (int32_t i = 0; i < entry.tangent_dim; ++i) t_ptr[i] += d[i];
+      }
+      tangent_inx += entry.tangent_dim;
+    }
+  }
+  // values.cc:329-350: tangent vector from this to `others` for the indexed keys
+  std::vector<Scalar> LocalCoordinates(const Values& others, const index_t& index, const Scalar epsilon) const {
+    SYM_ASSERT(index.tangent_dim >= 0);
+    std::vector<Scalar> tangent_vec(index.tangent_dim);
+    size_t tangent_inx = 0;
+    for (const index_entry_t& entry : index.entries) {
+      const Scalar* a = data_.data() + entry.offset;
+      const Scalar* b = others.data_.data() + entry.offset;
+      Scalar* out = tangent_vec.data() + tangent_inx;
+      if (entry.type == type_t::ROT3) {
+        const Vector3<Scalar> v = internal::StorageTraits<Rot3<Scalar>>::From(a).LocalCoordinates(
+            internal::StorageTraits<Rot3<Scalar>>::From(b), epsilon);
+        for (int i = 0; i < 3; ++i) out[i] = v[i];
+      } else if (entry.type == type_t::POSE3) {
+        const Vector6<Scalar> v = internal::StorageTraits<Pose3<Scalar>>::From(a).LocalCoordinates(
+            internal::StorageTraits<Pose3<Scalar>>::From(b), epsilon);
+        for (int i = 0; i < 6; ++i) out[i] = v[i];
+      } else {
+        for (int32_t i = 0; i < entry.tangent_dim; ++i) out[i] = b[i] - a[i];
+      }
+      tangent_inx += entry.tangent_dim;
+    }
+    return tangent_vec;
+  }
 
  private:
   MapType map_;

@@ -10,8 +10,6 @@ entry points both libraries export (sfx_* = the CUDA product, orc_* = the CPU or
 """
 import copy
 
-import numpy as np
-
 
 def gnc_optimize(h, values, mu_off, params, gnc, num_iterations=-1):
     """h: capi.SfxProblem or oracle_capi.OracleProblem; values: float64 buffer (modified in place);

@@ -4,8 +4,6 @@ analysis.cc + symbolic.cc): scatter of per-factor J^T J / J^T r blocks, Schur co
 match lists, multifrontal Cholesky + solves from the front plan.  Executable specification used by
 the CPU tests to validate the host logic against the oracle before any kernel runs.
 """
-import ctypes as C
-
 import numpy as np
 
 from symforce_b200 import desc as D

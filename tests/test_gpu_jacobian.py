@@ -59,7 +59,6 @@ def test_jacobian_export_leaves_the_optimizer_state_alone():
 
 
 def test_python_front_fills_the_jacobian():
-    from symforce_b200.opt import Optimizer
     from tests import py_problems as PP
 
     values, num_landmarks = PP.robot3d.build_values(PP.robot3d.NUM_POSES)

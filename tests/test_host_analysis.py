@@ -3,7 +3,6 @@ CPU tests of the product's host logic (no GPU): the C-ABI library loads and expo
 include/sfx.h, and the structural analysis (index maps, CSC layout, Schur match lists, multifrontal
 plan) replayed in numpy reproduces the oracle's H / rhs / residual / LM step.
 """
-import ctypes as C
 import re
 import os
 

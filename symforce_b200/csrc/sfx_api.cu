@@ -1497,6 +1497,30 @@ int32_t sfx_debug_verify_tasks(int32_t wt, int32_t nt, int32_t kc) {
   }
 }
 
+// debug (host only): the tile task list of such a front as int16 records {type, k, i, j, k1}; returns the number of
+// tasks (call with out == NULL to size the buffer).  Input of tools/simulate_tile_dag.py.
+int32_t sfx_debug_front_tasks(int32_t wt, int32_t nt, int32_t kc, int16_t* out, int32_t capacity) {
+  try {
+    LargeFront x{};
+    x.wt = wt;
+    x.nt = nt;
+    std::vector<LargeTask> tl;
+    build_front_tasks(x, 0, kc, tl);
+    if (out)
+      for (size_t q = 0; q < tl.size() && (int32_t)q < capacity; ++q) {
+        out[5 * q + 0] = (int16_t)tl[q].type;
+        out[5 * q + 1] = tl[q].k;
+        out[5 * q + 2] = tl[q].i;
+        out[5 * q + 3] = tl[q].j;
+        out[5 * q + 4] = tl[q].k1;
+      }
+    return (int32_t)tl.size();
+  } catch (const std::exception& e) {
+    g_create_err = e.what();
+    return -1;
+  }
+}
+
 // debug: average time of `reps` linearizations of state block 0 (zero + kernels + error reduce), with
 // parts of the BAL kernel left out when skip != 0 (timing experiment; leaves an invalid linearization)
 sfx_status sfx_debug_time_linearize(sfx_problem* p, int32_t skip, int32_t reps, float* ms) {

@@ -31,9 +31,14 @@ void get_diag_stamps(unsigned long long* out);
       throw Error(SFX_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__));                   \
   } while (0)
 
+// Device allocations of one problem.  Every upload / memset is issued on the problem's own stream `st` and
+// completed before returning: the library's streams are cudaStreamNonBlocking, so work on the legacy
+// default stream (a plain cudaMemcpy from pageable memory returns once the data is STAGED, cudaMemset on
+// device memory is asynchronous) is not ordered against the kernels that consume these buffers.
 struct DevPool {
   std::vector<void*> ptrs;
   int64_t bytes = 0;
+  cudaStream_t st = nullptr;
   template <typename T>
   T* alloc(size_t n) {
     void* p = nullptr;
@@ -46,9 +51,13 @@ struct DevPool {
   template <typename T>
   T* upload(const std::vector<T>& v) {
     T* p = alloc<T>(v.size());
-    if (!v.empty()) CUDA_OK(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    if (!v.empty()) {
+      CUDA_OK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, st));
+      CUDA_OK(cudaStreamSynchronize(st));  // `v` may be a temporary; the DMA has landed when this returns
+    }
     return p;
   }
+  void zero(void* p, size_t nbytes) { CUDA_OK(cudaMemsetAsync(p, 0, nbytes, st)); }
   ~DevPool() {
     for (void* p : ptrs) cudaFree(p);
   }
@@ -403,8 +412,8 @@ void upload_structures(sfx_problem* p) {
   p->d_upd = P.alloc<double>(a.N);
   p->d_last = P.alloc<double>(a.N);
   p->d_y = P.alloc<double>(a.N);
-  CUDA_OK(cudaMemset(p->d_last, 0, sizeof(double) * a.N));
-  CUDA_OK(cudaMemset(p->d_upd, 0, sizeof(double) * a.N));  // entries of other ranks' landmarks stay 0
+  P.zero(p->d_last, sizeof(double) * a.N);
+  P.zero(p->d_upd, sizeof(double) * a.N);  // entries of other ranks' landmarks stay 0
   if (a.world > 1) {
     p->d_stage = P.alloc<double>(std::max<int64_t>(a.n_values, a.b_values + a.sp.reduced_dim + 1));
     std::vector<unsigned char> mask(a.n_values, a.rank == 0 ? 1 : 0);
@@ -416,9 +425,10 @@ void upload_structures(sfx_problem* p) {
     }
     p->d_vmask = P.upload(mask);
   }
-  CUDA_OK(cudaMemset(p->d_maxdiag, 0, sizeof(double) * a.N));
+  P.zero(p->d_maxdiag, sizeof(double) * a.N);
   p->d_ctrl = P.alloc<Ctrl>(1);
   CUDA_OK(cudaMallocHost(&p->h_ctrl, sizeof(Ctrl)));
+  std::memset(p->h_ctrl, 0, sizeof(Ctrl));  // entry points that come before any sfx_optimize read best_valid / n_iters
   CUDA_OK(cudaHostAlloc(&p->h_done, sizeof(int) * (kMaxIterations + 2), cudaHostAllocMapped));
   CUDA_OK(cudaHostGetDevicePointer(&p->d_done, p->h_done, 0));
   std::memset(p->h_done, 0, sizeof(int) * (kMaxIterations + 2));
@@ -542,7 +552,7 @@ void upload_structures(sfx_problem* p) {
         for (int q = s.r_ptr[j]; q < s.r_ptr[j + 1]; ++q) rnode[q] = j;
       d.r_node = P.upload(rnode);
       d.G = fast ? P.alloc<double>(a.H.n_values + 32) : nullptr;
-      if (fast) CUDA_OK(cudaMemset(d.G + a.H.n_values, 0, 32 * sizeof(double)));
+      if (fast) P.zero(d.G + a.H.n_values, 32 * sizeof(double));
       d.wl = (fast && !getenv("SFX_SCHUR_V1")) ? P.alloc<double>((size_t)s.n_landmarks * 9) : nullptr;
       d.zeros = P.upload(std::vector<double>(8, 0.0));
       d.sl = P.alloc<double>((size_t)s.n_landmarks * 3);
@@ -727,11 +737,25 @@ void upload_structures(sfx_problem* p) {
     p->ld.contrib = P.alloc<double>(contrib_off);
     p->ld.ll_y = P.alloc<uint4>(f.n);
     p->ld.ll_contrib = P.alloc<uint4>(contrib_off);
-    CUDA_OK(cudaMemset(p->ld.ll_y, 0, sizeof(uint4) * std::max<int64_t>(f.n, 1)));
-    CUDA_OK(cudaMemset(p->ld.ll_contrib, 0, sizeof(uint4) * std::max<int64_t>(contrib_off, 1)));
+    P.zero(p->ld.ll_y, sizeof(uint4) * std::max<int64_t>(f.n, 1));
+    P.zero(p->ld.ll_contrib, sizeof(uint4) * std::max<int64_t>(contrib_off, 1));
     CUDA_OK(configure_front_kernels(p->smem_cap_m, f.max_front));
     CUDA_OK(configure_large_kernels());
   }
+}
+
+// optimizer_params_t sanity (the reference SYM_ASSERTs on lambda_update_type INVALID,
+// levenberg_marquardt_solver.tcc:322-339; a zero-initialised struct must not silently run another algorithm)
+void validate_params(const sfx_params& q) {
+  SFX_CHECK(q.lambda_update_type == 1 || q.lambda_update_type == 2, SFX_ERR_INVALID_ARG,
+            "lambda_update_type must be STATIC (1) or DYNAMIC (2)");
+  SFX_CHECK(q.iterations > 0, SFX_ERR_INVALID_ARG, "iterations must be positive");
+  SFX_CHECK(q.initial_lambda >= 0 && q.lambda_lower_bound >= 0 && q.lambda_lower_bound <= q.lambda_upper_bound,
+            SFX_ERR_INVALID_ARG, "need 0 <= lambda_lower_bound <= lambda_upper_bound and initial_lambda >= 0");
+  SFX_CHECK(q.lambda_up_factor > 0 && q.lambda_down_factor > 0, SFX_ERR_INVALID_ARG, "lambda factors must be positive");
+  if (q.lambda_update_type == 2)
+    SFX_CHECK(q.dynamic_lambda_update_beta > 0 && q.dynamic_lambda_update_gamma > 0 && q.dynamic_lambda_update_p > 0,
+              SFX_ERR_INVALID_ARG, "dynamic lambda update needs beta, gamma, p > 0");
 }
 
 void reset_ctrl(sfx_problem* p) {
@@ -1008,6 +1032,7 @@ sfx_status sfx_problem_create(const sfx_problem_desc* desc, sfx_problem** out) {
   std::unique_ptr<sfx_problem> up(new sfx_problem());
   p = up.get();
   p->device = desc->device;
+  validate_params(desc->params);
   p->params = desc->params;
   p->epsilon = desc->epsilon;
   p->ordering = desc->ordering;
@@ -1038,8 +1063,9 @@ sfx_status sfx_problem_create(const sfx_problem_desc* desc, sfx_problem** out) {
   CUDA_OK(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&p->ev_fork2, cudaEventDisableTiming));
   CUDA_OK(cudaEventCreateWithFlags(&p->ev_join2, cudaEventDisableTiming));
+  p->pool.st = p->st;
   upload_structures(p);
-  CUDA_OK(cudaStreamSynchronize(p->st));
+  CUDA_OK(cudaDeviceSynchronize());
   clk.lap("create: device structures");
   *out = up.release();
   p = nullptr;
@@ -1055,6 +1081,7 @@ void sfx_problem_destroy(sfx_problem* p) {
 sfx_status sfx_update_params(sfx_problem* p, const sfx_params* params) {
   SFX_API_BEGIN
   SFX_CHECK(p && params, SFX_ERR_INVALID_ARG, "null argument");
+  validate_params(*params);
   p->params = *params;
   SFX_API_END(p)
 }
@@ -1080,6 +1107,12 @@ static sfx_status optimize_impl(sfx_problem* p, int32_t num_iterations, sfx_stat
   CUDA_OK(cudaSetDevice(p->device));
   Analysis& a = p->a;
   const int64_t launches0 = g_launches;
+  if (cont) {
+    SFX_CHECK(p->can_continue, SFX_ERR_INVALID_ARG,
+              "sfx_optimize_continue must directly follow sfx_optimize / sfx_optimize_continue (SYM_ASSERT: IsInitialized())");
+    SFX_CHECK(p->h_ctrl->n_iters + num_iterations <= kMaxIterations, SFX_ERR_INVALID_ARG,
+              "num_iterations exceeds stats capacity");
+  }
   // debug_stats (optimizer_params_t, lcmtypes/symforce.lcm): keep values and residual of every record
   const bool dbg = p->params.debug_stats != 0;
   if (dbg) {
@@ -1108,10 +1141,6 @@ static sfx_status optimize_impl(sfx_problem* p, int32_t num_iterations, sfx_stat
   }
   p->dbg_valid = dbg && (cont ? p->dbg_valid || p->h_ctrl->n_iters == 0 : true);
   if (cont) {
-    SFX_CHECK(p->can_continue, SFX_ERR_INVALID_ARG,
-              "sfx_optimize_continue must directly follow sfx_optimize / sfx_optimize_continue (SYM_ASSERT: IsInitialized())");
-    SFX_CHECK(p->h_ctrl->n_iters + num_iterations <= kMaxIterations, SFX_ERR_INVALID_ARG,
-              "num_iterations exceeds stats capacity");
     reset_ctrl_continue(p);
   } else {
     // Reset(values): all three state blocks hold the full values buffer; optimized keys are
@@ -1561,6 +1590,7 @@ sfx_status sfx_debug_trace_tasks(sfx_problem* p, unsigned long long* host_out, i
     for (auto& lv : p->lvl_large) ntask = std::max<int64_t>(ntask, lv.t1);
     CUDA_OK(cudaMalloc(&dbuf, sizeof(unsigned long long) * 4 * ntask));
     CUDA_OK(cudaMemset(dbuf, 0, sizeof(unsigned long long) * 4 * ntask));
+    CUDA_OK(cudaDeviceSynchronize());  // legacy-stream memset vs the non-blocking problem streams
     sfx::set_factor_trace(dbuf);
     *n_tasks = (int32_t)ntask;
   } else {

@@ -97,7 +97,10 @@ def test_linearize_and_covariances_through_the_front():
         assert by_key[k].shape == (6, 6) and np.max(np.abs(by_key[k] - blk)) <= 1e-8 * np.max(np.abs(want))
     # compute_covariances with every key is compute_all_covariances; a strict prefix needs a Schur-eliminable tail
     allk = optimizer.compute_covariances(result.optimized_values, optimizer.optimized_keys)
-    assert all(np.array_equal(allk[k], by_key[k]) for k in by_key)
+    # two separate linearizations on the device: the Hessian is accumulated with fp64 atomics, whose order (and so
+    # the last bits) differs from run to run -- same wiring, not the same bits
+    for k in by_key:
+        assert np.max(np.abs(allk[k] - by_key[k])) <= 1e-11 * np.max(np.abs(want)), k
     with pytest.raises(ValueError, match="first optimized keys"):
         optimizer.compute_covariances(result.optimized_values, optimizer.optimized_keys[1:3])
     optimizer.close()

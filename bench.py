@@ -45,6 +45,7 @@ def parse_args():
     ap.add_argument("--workload", default="final")
     ap.add_argument("--cpu-baseline", type=int, default=1, help="0: skip the cpu_baseline leg")
     ap.add_argument("--cpu-workload", default=None)
+    ap.add_argument("--secondary", type=int, default=1, help="0: skip the ladybug / pose_graph secondary entries")
     return ap.parse_args()
 
 
@@ -79,6 +80,13 @@ def workload_config(name):
         "l2": "inputs larger than L2 (block Hessian > 126 MB)" if s["n_obs"] * 27 * 8 > 126e6
               else "working set fits L2 and is NOT flushed (parity/debug workload, not the headline)",
     }
+
+
+def bench_config(name, n_gpus):
+    """`config` of the JSON line: identical in the sfx and the reference arm."""
+    return dict(workload_config(name),
+                parallelism=f"landmarks+observations sharded over {n_gpus} GPUs, NCCL reduce of S" if n_gpus > 1
+                else "1 GPU")
 
 
 def never_exit_params():
@@ -138,7 +146,7 @@ class ClockSampler:
         return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
-def cpu_baseline(workload, max_seconds=40.0):
+def cpu_baseline(workload, max_seconds=40.0, max_iters=20, warmup_iters=0):
     """The oracle (CPU restatement of the reference algorithm, 1 thread like the reference's
     symforce/opt) on a bounded sample of the workload: LM iterations driven like the reference
     benchmark (`Optimize(values, 1)`), timed by the oracle's own phase timers; index building,
@@ -151,19 +159,26 @@ def cpu_baseline(workload, max_seconds=40.0):
     o = O.OracleProblem(prob)
     iters = 0
     per_iter = []
+    first = None
     while True:
         o.reset_timings()
         o.optimize(1)
+        if first is None:  # records of the first LM iteration from the initial values: the in-run parity anchor
+            first = [float(r.new_error) for r in o.iterations()]
         tm = o.timings()
         # one LM iteration = 1 linearize + 1 factorize + 1 solve (the first call linearizes twice)
         per_iter.append(tm["linearize_s"] / max(tm["n_linearize"], 1) + tm["factorize_s"] / max(tm["n_factorize"], 1)
                         + tm["solve_s"] / max(tm["n_factorize"], 1))
         iters += 1
-        if sum(per_iter) > max_seconds / 2 or iters >= 20:
+        if sum(per_iter) > max_seconds / 2 or iters >= max_iters + warmup_iters:
             break
     wall = time.time() - t0
+    warm = min(warmup_iters, iters - 1)
+    per_iter = per_iter[warm:]
+    iters -= warm
     it_s = float(np.mean(per_iter))
     return {
+        "steps_run": iters, "warmup_run": warm, "first_iteration_errors": first,
         "value": 1.0 / it_s, "unit": UNIT, "cores": 1, "kind": "port",
         "sample": f"{iters} LM iteration(s) of the {workload} problem on the CPU oracle ("
                   f"{'simplicial LDLT on H' if workload == 'pose_graph' else 'Schur + simplicial LDLT on S'}, "
@@ -181,11 +196,15 @@ def run_reference(args):
     if rank != 0:
         return
     wl = args.cpu_workload or args.workload
-    cb = cpu_baseline(wl, max_seconds=60.0)
-    cfg = workload_config(wl)
+    # every step is one LM iteration of the full workload on one host core (the reference has no threads); the
+    # run is bounded to ~2.5 minutes, so fewer than --steps iterations may fit: `steps` / `warmup` are the counts
+    # that actually ran (`requested_steps` / `requested_warmup` echo the flags)
+    cb = cpu_baseline(wl, max_seconds=240.0, max_iters=args.steps, warmup_iters=min(max(args.warmup, 0), 1))
+    cfg = bench_config(wl, args.gpus)
     line = {
         "impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / cb["value"], "higher_is_better": True,
+        "steps": cb["steps_run"], "warmup": cb["warmup_run"], "requested_steps": args.steps,
+        "requested_warmup": args.warmup, "ms_per_step": 1e3 / cb["value"], "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": cfg,
         "cpu_baseline": cb,
         "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -193,52 +212,92 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def main():
-    args = parse_args()
-    if args.impl == "reference":
-        run_reference(args)
-        return
+def rooflines(workload, info, ph):
+    """Roofline objects of the three hot phases from the algorithmic bytes / flops of DESIGN.md section 3
+     and the measured per-phase times; returns (linearize, schur, factorize, dominant)."""
+    from symforce_b200 import problems as P
+
+    is_pg = workload == "pose_graph"
+    shape = None if is_pg else P.BAL_SHAPES[workload]
+    n_obs, n_cams, n_pts = (shape["n_obs"], shape["n_cams"], shape["n_pts"]) if shape else (0, 0, 0)
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm = peaks.get("hbm_gbs", 6650.0)
+    hbm_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"
+    traffic = {}
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(workload, {})
+    except Exception:
+        pass
+    lin_bytes = 256 * n_obs + 512 * n_cams + 96 * n_pts
+    if is_pg:  # SURVEY.md 8(d): 688 B per between edge + 272 B per pose
+        lin_bytes = 688 * (POSE_GRAPH["n_poses"] - 1 + POSE_GRAPH["n_loops"]) + 272 * POSE_GRAPH["n_poses"]
+    schur_bytes = 216 * n_obs + 72 * n_pts + 432 * n_cams + 8 * 81 * info["s_blocks"]
+    fac_flops = float(info["factor_flops"])
+    # MEASURED_PEAKS.json has no FP64 figure: the DMMA peak was measured once on this pool's B200 with
+    # tools/micro/fp64_peak.cu (profiles/fp64_peak.json); nominal 40 TFLOP/s otherwise
+    fp64_peak, fp64_src = 40.0, "nominal B200 FP64 tensor 40 TFLOP/s (no FP64 number in MEASURED_PEAKS.json)"
+    try:
+        fp = json.load(open(os.path.join(ROOT, "profiles", "fp64_peak.json")))
+        fp64_peak = float(fp["dmma_tflops"])
+        fp64_src = "profiles/fp64_peak.json: mma.sync.m8n8k4.f64 peak measured with tools/micro/fp64_peak.cu"
+    except Exception:
+        pass
+    rl_lin = {"kernel": "linearize_kernel<between/prior> (+zero, error reduce)" if is_pg else
+                        "linearize_bal_kernel (+zero, point sums, error reduce)", "bound": "hbm",
+              "achieved": lin_bytes / (ph["linearize"] * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+              "traffic": traffic.get("linearize"), "peak_source": hbm_src}
+    rl_lin["frac"] = rl_lin["achieved"] / hbm
+    rl_schur = None
+    if not is_pg:  # no Schur elimination on the pose-graph path
+        rl_schur = {"kernel": "schur_cinv + S-product kernels", "bound": "hbm",
+                    "achieved": schur_bytes / (ph["schur"] * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
+                    "traffic": traffic.get("schur"), "peak_source": hbm_src}
+        rl_schur["frac"] = rl_schur["achieved"] / hbm
+    rl_fac = {"kernel": "large_factor_kernel (tile-DAG supernodal Cholesky, DMMA m8n8k4)", "bound": "tensor",
+              "achieved": fac_flops / (ph["factorize"] * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
+              "traffic": traffic.get("large_factor_kernel"), "peak_source": fp64_src}
+    rl_fac["frac"] = rl_fac["achieved"] / fp64_peak
+    dominant = max([kv for kv in (("factorize", rl_fac), ("schur", rl_schur), ("linearize", rl_lin)) if kv[1]],
+                   key=lambda kv: ph[kv[0]])[1]
+    return rl_lin, rl_schur, rl_fac, dominant
+
+
+def measure(workload, K, W, rank, world, local_rank, comm, sample_clocks):
+    """One workload on the CUDA path: device-resident K iterations + e2e K x Optimize(values, 1); returns a dict
+    (timings are this rank's; the caller takes the max over ranks)."""
     import torch
     import torch.distributed as dist
 
-    from symforce_b200 import capi, desc as D, problems as P
+    from symforce_b200 import capi
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    torch.cuda.set_device(local_rank)
-
-    K, W = args.steps, max(args.warmup, 3)
-    is_pg = args.workload == "pose_graph"
-    assert not (is_pg and world > 1), "pose graphs are single-GPU (replicas only, SURVEY.md 8e)"
-    shape = None if is_pg else P.BAL_SHAPES[args.workload]
-    # multi-GPU: every rank is given the same problem; libsfx shards landmarks + their observations
-    # over the ranks and sums the reduced camera system with one NCCL reduce per iteration
-    prob = make_problem(args.workload)
-    comm = capi.Comm(rank, world, local_rank) if world > 1 else None
+    prob = make_problem(workload)
     t0 = time.time()
     gpu = capi.SfxProblem(prob, device=local_rank, rank=rank, world=world, comm=comm)
     setup_s = time.time() - t0
     info = gpu.info()
-
     pinned = torch.empty(prob.values.shape[0], dtype=torch.float64).pin_memory()
     pinned.numpy()[:] = prob.values
-    out_pinned = torch.empty(prob.values.shape[0], dtype=torch.float64).pin_memory()
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    # in-run parity anchor: initial error and the error after the first LM iteration from the initial values
+    # (compared with the cpu_baseline leg's, which runs the same iteration on the oracle)
+    gpu.set_values(pinned.numpy())
+    gpu.optimize(1)
+    first_errors = [float(r.new_error) for r in gpu.iterations()]
     # warm-up
     gpu.set_values(pinned.numpy())
     gpu.optimize(W)
-
     # clocks are sampled by rank 0 only: N concurrent nvidia-smi pollers contend for the driver and for host cores
     sampler = ClockSampler(local_rank)
-    if rank == 0:
+    if sample_clocks:
         sampler.start()
     # ---- device-resident: K iterations in one call ---------------------------------------------
     gpu.set_values(pinned.numpy())
@@ -250,14 +309,14 @@ def main():
     assert iters_run == K, f"expected {K} iterations, ran {iters_run} (status {st.status})"
     dev_ms = tm["total_ms"]
     # ---- e2e: host buffers, one iteration per call -----------------------------------------------
-    lib = gpu.lib
     barrier()
     t0 = time.perf_counter()
     d2h_bytes = 0
+    h2d_bytes = 0
     diag = [0.0, 0.0, 0.0]
     for _ in range(K):
         ta = time.perf_counter()
-        gpu.set_values(pinned.numpy())
+        h2d_bytes = gpu.set_values(pinned.numpy())
         tb = time.perf_counter()
         gpu.optimize(1)
         tc = time.perf_counter()
@@ -273,9 +332,40 @@ def main():
               f"update_best_values {diag[2] / K * 1e3:.2f} ms", file=sys.stderr, flush=True)
     barrier()
     e2e_s = time.perf_counter() - t0
-    clocks = sampler.stop()
+    clocks = sampler.stop() if sample_clocks else None
+    gpu.close()
+    ph = {"linearize": tm["linearize_ms"] / max(tm["n_linearize"], 1), "schur": tm["schur_ms"] / K,
+          "factorize": tm["factorize_ms"] / K, "solve": tm["solve_ms"] / K, "update": tm["update_ms"] / K}
+    return dict(dev_ms=dev_ms, e2e_s=e2e_s, clocks=clocks, info=info, setup_s=setup_s, phases=ph,
+                launches=int(tm["kernel_launches"]), first_errors=first_errors,
+                h2d_bytes=int(h2d_bytes) if h2d_bytes else int(prob.values.nbytes), d2h_bytes=int(d2h_bytes))
 
-    t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device="cuda")
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    import torch
+    import torch.distributed as dist
+
+    from symforce_b200 import capi
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+
+    K, W = args.steps, max(args.warmup, 3)
+    assert not (args.workload == "pose_graph" and world > 1), "pose graphs are single-GPU (replicas only, SURVEY.md 8e)"
+    # multi-GPU: every rank is given the same problem; libsfx shards landmarks + their observations
+    # over the ranks and sums the reduced camera system over NVLink once per iteration
+    comm = capi.Comm(rank, world, local_rank) if world > 1 else None
+    m = measure(args.workload, K, W, rank, world, local_rank, comm, sample_clocks=(rank == 0))
+
+    t = torch.tensor([m["dev_ms"], m["e2e_s"]], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, e2e_s = float(t[0]), float(t[1])
@@ -283,83 +373,57 @@ def main():
     e2e = K / e2e_s
 
     if rank == 0:
-        n_obs, n_cams, n_pts = (shape["n_obs"], shape["n_cams"], shape["n_pts"]) if shape else (0, 0, 0)
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        hbm = peaks.get("hbm_gbs", 6650.0)
-        hbm_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)"
-        traffic = {}
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload, {})
-        except Exception:
-            pass
-        ph = {
-            "linearize": tm["linearize_ms"] / max(tm["n_linearize"], 1),
-            "schur": tm["schur_ms"] / K, "factorize": tm["factorize_ms"] / K, "solve": tm["solve_ms"] / K,
-            "update": tm["update_ms"] / K}
-        # algorithmic work per launch (DESIGN.md section 3 / SURVEY.md 8d)
-        lin_bytes = 256 * n_obs + 512 * n_cams + 96 * n_pts
-        if is_pg:  # 688 B per between edge + 272 B per pose
-            lin_bytes = 688 * (POSE_GRAPH["n_poses"] - 1 + POSE_GRAPH["n_loops"]) + 272 * POSE_GRAPH["n_poses"]
-        schur_bytes = 216 * n_obs + 72 * n_pts + 432 * n_cams + 8 * 81 * info["s_blocks"]
-        fac_flops = float(info["factor_flops"])
-        # MEASURED_PEAKS.json has no FP64 figure: the DMMA peak was measured once on this pool's B200 with
-        # tools/micro/fp64_peak.cu (profiles/fp64_peak.json); nominal 40 TFLOP/s otherwise
-        fp64_peak, fp64_src = 40.0, "nominal B200 FP64 tensor 40 TFLOP/s (no FP64 number in MEASURED_PEAKS.json)"
-        try:
-            fp = json.load(open(os.path.join(ROOT, "profiles", "fp64_peak.json")))
-            fp64_peak = float(fp["dmma_tflops"])
-            fp64_src = "profiles/fp64_peak.json: mma.sync.m8n8k4.f64 peak measured with tools/micro/fp64_peak.cu"
-        except Exception:
-            pass
-        rl_lin = {"kernel": "linearize_kernel<between/prior> (+zero, error reduce)" if is_pg else
-                            "linearize_bal_kernel (+zero, point finalize, error reduce)", "bound": "hbm",
-                  "achieved": lin_bytes / (ph["linearize"] * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
-                  "traffic": traffic.get("linearize"), "peak_source": hbm_src}
-        rl_lin["frac"] = rl_lin["achieved"] / hbm
-        rl_schur = {"kernel": "schur_cinv + schur_w_rhs + schur_s9 kernels", "bound": "hbm",
-                    "achieved": schur_bytes / (ph["schur"] * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
-                    "traffic": traffic.get("schur"), "peak_source": hbm_src}
-        rl_schur["frac"] = rl_schur["achieved"] / hbm
-        if is_pg:
-            rl_schur = None  # no Schur elimination on this path
-        rl_fac = {"kernel": "large_factor_kernel (tile-DAG supernodal Cholesky, DMMA m8n8k4)", "bound": "tensor",
-                  "achieved": fac_flops / (ph["factorize"] * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
-                  "traffic": traffic.get("large_factor_kernel"),
-                  "peak_source": fp64_src}
-        rl_fac["frac"] = rl_fac["achieved"] / fp64_peak
-        dominant = max([kv for kv in (("factorize", rl_fac), ("schur", rl_schur), ("linearize", rl_lin)) if kv[1]],
-                       key=lambda kv: ph[kv[0]])[1]
+        info, ph = m["info"], m["phases"]
+        rl_lin, rl_schur, rl_fac, dominant = rooflines(args.workload, info, ph)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": dev_ms / K, "higher_is_better": True, "scaling": "strong",  # one fixed problem sharded over N GPUs
             "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": dict(workload_config(args.workload),
-                           parallelism=f"landmarks+observations sharded over {world} GPUs, NCCL reduce of S" if world > 1
-                           else "1 GPU",
-                           reduced_dim=info["reduced_dim"], nnz_L=info["nnz_L"], supernodes=info["num_supernodes"],
-                           levels=info["num_levels"], max_front=info["max_front"], factor_gflop=fac_flops / 1e9,
-                           setup_s=round(setup_s, 2)),
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(prob.values.nbytes),
-                    "d2h_bytes_per_step": int(d2h_bytes)},
-            "gpu_launches": int(tm["kernel_launches"]),
-            "clocks": clocks,
+            "config": bench_config(args.workload, world),
+            "analysis": dict(reduced_dim=info["reduced_dim"], nnz_L=info["nnz_L"], supernodes=info["num_supernodes"],
+                             levels=info["num_levels"], max_front=info["max_front"],
+                             factor_gflop=float(info["factor_flops"]) / 1e9, setup_s=round(m["setup_s"], 2)),
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": m["h2d_bytes"], "d2h_bytes_per_step": m["d2h_bytes"]},
+            "gpu_launches": m["launches"],
+            "clocks": m["clocks"],
             "phases_ms_per_iteration": ph,
             "roofline": dominant,
             "roofline_linearize": rl_lin, "roofline_schur": rl_schur, "roofline_factorize": rl_fac,
         }
+        # secondary workloads (BASELINE.json configs C and E), 1 GPU only: same measurement, shorter
+        if world == 1 and args.workload == "final" and args.secondary:
+            sec = []
+            for wl in ("ladybug", "pose_graph"):
+                try:
+                    ms = measure(wl, K, W, 0, 1, local_rank, None, sample_clocks=False)
+                    rl = rooflines(wl, ms["info"], ms["phases"])
+                    sec.append({"config": bench_config(wl, 1), "value": K / (ms["dev_ms"] * 1e-3), "unit": UNIT,
+                                "ms_per_step": ms["dev_ms"] / K, "e2e": K / ms["e2e_s"],
+                                "phases_ms_per_iteration": ms["phases"], "gpu_launches": ms["launches"],
+                                "roofline": rl[3], "roofline_linearize": rl[0], "roofline_schur": rl[1],
+                                "roofline_factorize": rl[2]})
+                except Exception as e:
+                    sec.append({"config": {"workload": wl}, "failed": str(e)})
+            line["secondary"] = sec
         if args.cpu_baseline:
             try:
-                line["cpu_baseline"] = cpu_baseline(args.cpu_workload or args.workload)
+                cb = cpu_baseline(args.cpu_workload or args.workload)
+                line["cpu_baseline"] = cb
+                if (args.cpu_workload or args.workload) == args.workload and cb.get("first_iteration_errors"):
+                    # the oracle's initial error and first-iteration error against the GPU's, same inputs
+                    ce, ge = cb["first_iteration_errors"], m["first_errors"]
+                    rel = [abs(a - b) / abs(b) for a, b in zip(ge, ce)]
+                    line["parity_check"] = {"what": "0.5*|r|^2 at the initial values and after the first LM iteration, "
+                                                    "GPU vs CPU oracle in this run", "gpu": ge, "oracle": ce,
+                                            "max_rel_diff": max(rel), "tolerance": 1e-9,
+                                            "ok": len(ge) == len(ce) and max(rel) <= 1e-9}
             except Exception as e:  # the checker must not break the bench line
                 line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 1, "kind": "port",
                                         "sample": f"failed: {e}"}
-        print(json.dumps(line))
-    gpu.close()
+        print(json.dumps(line), flush=True)
+        if "parity_check" in line:
+            assert line["parity_check"]["ok"], f"GPU and CPU oracle disagree: {line['parity_check']}"
     if world > 1:
         comm.close()
         dist.destroy_process_group()

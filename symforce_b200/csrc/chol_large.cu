@@ -22,6 +22,7 @@ extern int64_t g_launches;
 constexpr int kT = 64;        // tile size
 constexpr int kLd = 68;       // smem leading dimension (== 4 mod 16: conflict-free DMMA fragment loads)
 constexpr int kLargeThreads = 256;
+constexpr size_t kFactorSmem = 2 * 64 * 68 * sizeof(double);  // dynamic shared memory of large_factor_kernel: As | Bs
 
 __device__ __forceinline__ int ld_acquire(const int* p) {
   int v;
@@ -46,15 +47,16 @@ __device__ __forceinline__ int tile_size(const LargeFront& lf, int t) {
 
 // smem tile <- global (zero padded); identity padding on the diagonal when `ident`
 __device__ __forceinline__ void load_tile(double* S, const double* __restrict__ G, int ldg, int nr, int nc, bool ident) {
-  const int r = threadIdx.x & 63;
-  for (int c = threadIdx.x >> 6; c < kT; c += kLargeThreads / 64) {
-    double v = 0.0;
-    if (r < nr && c < nc)
-      v = __ldcg(G + r + (size_t)c * ldg);
-    else if (ident && r == c)
-      v = 1.0;
-    S[r + c * kLd] = v;
+  const int r = threadIdx.x & 63, c0 = threadIdx.x >> 6;
+  constexpr int kPer = kT / (kLargeThreads / 64);  // 16 columns per thread: all loads in flight before the first store
+  double v[kPer];
+#pragma unroll
+  for (int q = 0; q < kPer; ++q) {
+    const int c = c0 + q * (kLargeThreads / 64);
+    v[q] = (r < nr && c < nc) ? __ldcg(G + r + (size_t)c * ldg) : ((ident && r == c) ? 1.0 : 0.0);
   }
+#pragma unroll
+  for (int q = 0; q < kPer; ++q) S[r + (c0 + q * (kLargeThreads / 64)) * kLd] = v[q];
 }
 
 // acc += A * B^T over the 64-deep smem tiles; warp layout 4 (rows) x 2 (cols), warp tile 16 x 32
@@ -486,16 +488,19 @@ __device__ __forceinline__ void store_frag(const double (&xf)[8][2], double* G, 
 
 // smem <- the final L_kk of pivot tile k from the front (strictly upper part zero, identity padding)
 __device__ __forceinline__ void load_L(double* S, const double* __restrict__ F, int m, int s0, int nb) {
-  const int r = threadIdx.x & 63;
-  for (int c = threadIdx.x >> 6; c < kT; c += kLargeThreads / 64) {
-    double v = 0.0;
-    if (r < nb && c < nb) {
-      if (r >= c) v = __ldcg(F + (s0 + r) + (size_t)(s0 + c) * m);
-    } else if (r == c) {
-      v = 1.0;
-    }
-    S[r + c * kLd] = v;
+  const int r = threadIdx.x & 63, c0 = threadIdx.x >> 6;
+  constexpr int kPer = kT / (kLargeThreads / 64);
+  double v[kPer];
+#pragma unroll
+  for (int q = 0; q < kPer; ++q) {
+    const int c = c0 + q * (kLargeThreads / 64);
+    if (r < nb && c < nb)
+      v[q] = (r >= c) ? __ldcg(F + (s0 + r) + (size_t)(s0 + c) * m) : 0.0;
+    else
+      v[q] = (r == c) ? 1.0 : 0.0;
   }
+#pragma unroll
+  for (int q = 0; q < kPer; ++q) S[r + (c0 + q * (kLargeThreads / 64)) * kLd] = v[q];
 }
 
 __device__ unsigned long long* g_trace = nullptr;
@@ -535,6 +540,9 @@ __global__ void __launch_bounds__(kLargeThreads, 2) large_factor_kernel(Ctrl* ct
       __shared__ int s_pre;
       double* binv_g = ld.binv + lf.linv_off / 8 + (size_t)k * 512;
       // tile (k+1, k) is usually ready before the diagonal tile: fetch it now (into Bs) if so
+      // fused schedule: the children's update matrices are added by EXTEND-ADD tasks of this launch; everything
+      // else in the front depends on POTRF(0), so this is the only wait on the assembly
+      if (k == 0 && lf.n_ea > 0) wait_ge(ld.counters + lf.asm_off, lf.n_ea);
       if (tid == 0) s_pre = (k + 1 < nt) && ld_acquire(cnt + (k + 1) * nt + k) == k;
       wait_eq(cnt + k * nt + k, k);
       if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 1] = gtime();
@@ -595,6 +603,40 @@ __global__ void __launch_bounds__(kLargeThreads, 2) large_factor_kernel(Ctrl* ct
         for (int c = tid >> 6; c < kT; c += kLargeThreads / 64) linv[r + c * kT] = Bs[r + c * kLd];
       }
       __syncthreads();
+      if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 2] = gtime();
+    } else if (task.type == 6) {
+      // ---------------- EXTEND-ADD: update tile (i,j) of this (final) front -> its parent front ----------------
+      const int wt = lf.wt;
+      wait_ge(cnt + i * nt + j, wt);
+      if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 1] = gtime();
+      const LargeFront pf = ld.lf[lf.parent_lf];
+      double* Fp = fd.fronts + pf.off;
+      const int mp = pf.m;
+      const int32_t* rel = fd.f_rel + fd.f_rows_ptr[lf.front] - lf.w;  // indexed by the row of this front
+      const int ri = tile_start(lf, i), ni = tile_size(lf, i);
+      const int cj = tile_start(lf, j), nj = tile_size(lf, j);
+      const int r = tid & 63, c0 = tid >> 6;
+      if (r < ni) {
+        const int pr = __ldg(rel + ri + r);
+        constexpr int kPer = kT / (kLargeThreads / 64);
+        double v[kPer];
+        int pc[kPer];
+#pragma unroll
+        for (int q = 0; q < kPer; ++q) {  // all loads in flight before the first RED
+          const int c = c0 + q * (kLargeThreads / 64);
+          const bool in = c < nj && ri + r >= cj + c;  // lower part (rel is increasing: it lands in the parent's lower part)
+          v[q] = in ? __ldcg(F + (ri + r) + (size_t)(cj + c) * m) : 0.0;
+          pc[q] = in ? __ldg(rel + cj + c) : -1;
+        }
+#pragma unroll
+        for (int q = 0; q < kPer; ++q)
+          if (pc[q] >= 0) atomicAdd(Fp + pr + (size_t)pc[q] * mp, v[q]);
+      }
+      __syncthreads();
+      if (tid == 0) {
+        __threadfence();
+        atomicAdd(ld.counters + pf.asm_off, 1);
+      }
       if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 2] = gtime();
     } else if (task.type == 1) {
       // ---------------- TRSM(i,k): strip-per-warp substitution in registers ----------------
@@ -667,6 +709,7 @@ __global__ void __launch_bounds__(kLargeThreads, 2) large_factor_kernel(Ctrl* ct
         const int ri = tile_start(lf, i), ni = tile_size(lf, i);
         const int cj = tile_start(lf, j), nj = tile_size(lf, j);
         double* C = F + ri + (size_t)cj * m;
+        // all 16 reads of the target in flight before the first store (they may alias for the compiler)
 #pragma unroll
         for (int rb = 0; rb < 2; ++rb)
 #pragma unroll
@@ -675,10 +718,18 @@ __global__ void __launch_bounds__(kLargeThreads, 2) large_factor_kernel(Ctrl* ct
             for (int e = 0; e < 2; ++e) {
               const int r = wr * 16 + rb * 8 + g;
               const int c = wc * 32 + cb * 8 + tq * 2 + e;
-              if (r < ni && c < nj) {
-                double* pc = C + r + (size_t)c * m;
-                *pc = __ldcg(pc) - acc[rb][cb][e];
-              }
+              const double cin = (r < ni && c < nj) ? __ldcg(C + r + (size_t)c * m) : 0.0;
+              acc[rb][cb][e] = cin - acc[rb][cb][e];
+            }
+#pragma unroll
+        for (int rb = 0; rb < 2; ++rb)
+#pragma unroll
+          for (int cb = 0; cb < 4; ++cb)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int r = wr * 16 + rb * 8 + g;
+              const int c = wc * 32 + cb * 8 + tq * 2 + e;
+              if (r < ni && c < nj) C[r + (size_t)c * m] = acc[rb][cb][e];
             }
       }
       publish(cnt + i * nt + j, k1);
@@ -804,12 +855,12 @@ void launch_large_level(cudaStream_t st, Ctrl* ctrl, const FrontDev& fd, const L
     ++g_launches;
   }
   const int ntask = lv.t1 - lv.t0;
-  int grid = ntask < 148 * 3 ? ntask : 148 * 3;
+  const int cap = large_factor_resident_ctas();
+  int grid = ntask < cap ? ntask : cap;
   // single-front levels are bound by the diagonal chain, not by throughput: one CTA per SM is as fast as two
   // (measured) and leaves room for the forward-substitution CTAs that overlap them
   if (grid_cap > 0 && grid > grid_cap) grid = grid_cap;
-  const size_t smem = 2 * kT * kLd * sizeof(double);
-  large_factor_kernel<<<grid, kLargeThreads, smem, st>>>(ctrl, fd, ld, lv.t0, lv.t1, level); ++g_launches;
+  large_factor_kernel<<<grid, kLargeThreads, kFactorSmem, st>>>(ctrl, fd, ld, lv.t0, lv.t1, level); ++g_launches;
 }
 
 
@@ -1325,9 +1376,39 @@ void launch_large_solve_bwd(cudaStream_t st, const Ctrl* ctrl, const FrontDev& f
   ++g_launches;
 }
 
+// All levels from the first fused one up in ONE launch: the assembly jobs that do not depend on fronts of this
+// launch (children factored by earlier launches), then the tile tasks of every fused front in the order of the
+// host-side list schedule (sfx_api.cu: build_fused_schedule), extend-adds included.
+void launch_large_fused(cudaStream_t st, Ctrl* ctrl, const FrontDev& fd, const LargeDev& ld, int t0, int t1, int j0,
+                        int j1, int queue_slot, const double* sys_static, StatePtrs sp, int use_state_H,
+                        const double* dvec) {
+  if (j1 > j0) {
+    large_assemble_kernel<<<(j1 - j0 + 7) / 8, 256, 0, st>>>(ctrl, fd, ld, sys_static, sp, use_state_H, dvec, j0, j1, 0);
+    ++g_launches;
+  }
+  const int ntask = t1 - t0;
+  if (ntask <= 0) return;
+  const int cap = large_factor_resident_ctas();
+  const int grid = ntask < cap ? ntask : cap;
+  large_factor_kernel<<<grid, kLargeThreads, kFactorSmem, st>>>(ctrl, fd, ld, t0, t1, queue_slot); ++g_launches;
+}
+
+// The spin-waits of the tile-DAG kernel need every CTA of a launch resident: grids are capped at what the device
+// holds (occupancy x SM count), never at a hard-coded SM count.
+static int g_resident_ctas = 0;
+int large_factor_resident_ctas() {
+  if (g_resident_ctas == 0) {
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, large_factor_kernel, kLargeThreads, kFactorSmem);
+    g_resident_ctas = sms * (per_sm > 0 ? per_sm : 1);
+  }
+  return g_resident_ctas;
+}
+
 cudaError_t configure_large_kernels() {
-  cudaError_t e = cudaFuncSetAttribute(large_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)(2 * kT * kLd * sizeof(double)));
+  cudaError_t e = cudaFuncSetAttribute(large_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFactorSmem);
   if (e != cudaSuccess) return e;
   e = cudaFuncSetAttribute(large_solve_fwd2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
   if (e != cudaSuccess) return e;

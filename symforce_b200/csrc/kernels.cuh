@@ -121,12 +121,15 @@ struct LargeFront {
   int cnt_off;       // offset of the nt*nt tile version counters
   int front;         // front id
   int flag_off;      // solve flags: [wt] forward published, [wt] backward contribution counters
-  int pad;
+  int parent_lf;     // fused schedule: large-front index of the parent (-1: root, or the parent is assembled between launches)
   int64_t contrib_off;  // backward-solve contribution slots: wt * nt * 64 doubles
+  int n_ea;          // fused schedule: extend-add tasks (type 6) that assemble this front inside the factor kernel
+  int asm_off;       // ... and the counter (in LargeDev::counters) they bump; DIAG(0) waits for n_ea
 };
 struct LargeTask {
   int lf;
-  short type, k, i, j;  // type: 1 TRSM(i,k), 2 UPDATE(i,j,k), 3 DIAG(k), 4 UPDATE(i,j,[k,k1)), 5 INV(k)
+  short type, k, i, j;  // type: 1 TRSM(i,k), 2 UPDATE(i,j,k), 3 DIAG(k), 4 UPDATE(i,j,[k,k1)), 5 INV(k),
+                        //       6 EXTEND-ADD of update tile (i,j) of front `lf` into its parent front
   short k1, pad;
 };
 struct LargeJob {
@@ -167,6 +170,10 @@ void launch_large_preassemble(cudaStream_t st, const Ctrl* ctrl, const FrontDev&
                               int pre_j1, int damp_j0, int damp_j1);
 void launch_large_zero(cudaStream_t st, const Ctrl* ctrl, const FrontDev& fd, const LargeDev& ld, int n_jobs);
 cudaError_t configure_large_kernels();
+int large_factor_resident_ctas();  // CTAs of large_factor_kernel the device keeps resident (occupancy x SM count)
+void launch_large_fused(cudaStream_t st, Ctrl* ctrl, const FrontDev& fd, const LargeDev& ld, int t0, int t1, int j0,
+                        int j1, int queue_slot, const double* sys_static, StatePtrs sp, int use_state_H,
+                        const double* dvec);
 
 // launchers (all asynchronous on `st`)
 void launch_zero_lin(cudaStream_t st, const Ctrl* ctrl, StatePtrs sp, int mode, int64_t n_h, int n_rhs);

@@ -11,6 +11,7 @@
 #include <cstring>
 #include <functional>
 #include <memory>
+#include <queue>
 #include <string>
 #include <vector>
 
@@ -130,6 +131,8 @@ struct sfx_problem {
   cudaStream_t st = nullptr;
   cudaStream_t st2 = nullptr;  // side stream: front zeroing overlaps damping + Schur
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fork2 = nullptr, ev_join2 = nullptr;
+  int fused_T0 = -1;  // first level of the fused top of the elimination tree (-1: none)
+  int fused_t0 = 0, fused_t1 = 0, fused_j0 = 0, fused_j1 = 0;
   int n_large_fronts = 0;
   int n_zero_jobs = 0;
   unsigned solve_epoch = 0;
@@ -316,6 +319,413 @@ void verify_task_list(const LargeFront& x, const std::vector<LargeTask>& tl) {
                                              ") ends at version " + std::to_string(C(i, j)) + ", expected " +
                                              std::to_string(want));
     }
+}
+
+// ---- fused schedule of the top of the elimination tree -------------------------------------------------------
+// All large fronts from level T0 up run in ONE launch of the tile-DAG kernel: the children's update matrices are
+// added by EXTEND-ADD tasks (type 6, one per update tile) and a front's DIAG(0) waits for them, so a parent's
+// diagonal chain overlaps the trailing updates of its siblings' subtrees instead of idling behind a level barrier.
+// The task order is the start order of a list schedule (critical-path priority, `workers` CTAs, task durations
+// from the task trace of round 1) simulated here once; CTAs claim tasks in that order and spin on tile versions,
+// which cannot deadlock because every dependency starts -- hence sits -- earlier in the list.
+struct FusedDur {
+  // us, from the task trace of round 1 (profiles/r01_results.md); DIAG = POTRF | TRSM(k+1,k) | UPDATE(k+1,k+1,k)
+  double potrf = 14.0, diag_trsm = 5.0, diag_syrk = 5.0, trsm = 7.7, update = 9.0, range_step = 6.0, range_fix = 2.0,
+         inv = 16.0, ea = 3.0;
+};
+void build_fused_schedule(const std::vector<LargeFront>& lfs, int lf_begin, int lf_end, int Kc, int workers,
+                          std::vector<LargeTask>& out) {
+  struct Edge {
+    int to;
+    double lag;  // the successor may start `lag` after this task started (output offset - input offset)
+  };
+  struct Node {
+    LargeTask t;
+    double dur, bl, ready;
+    std::vector<Edge> succ;
+    int indeg;
+  };
+  struct Writer {
+    int id = -1;
+    double out = 0.0;  // offset into the writer task at which the tile is published
+  };
+  FusedDur D;
+  if (const char* e = getenv("SFX_SIM_POTRF_US")) D.potrf = atof(e);
+  if (const char* e = getenv("SFX_SIM_DIAG_TAIL_US")) D.diag_trsm = D.diag_syrk = 0.5 * atof(e);
+  if (const char* e = getenv("SFX_SIM_RANGE_STEP_US")) D.range_step = atof(e);
+  std::vector<Node> g;
+  std::vector<std::vector<int>> ea_of(lfs.size());  // per parent large front: its extend-add tasks
+  auto add_dep = [&](const Writer& w, int to, double in_off) {
+    if (w.id < 0) return;
+    g[w.id].succ.push_back(Edge{to, w.out - in_off});
+    g[to].indeg++;
+  };
+  for (int li = lf_begin; li < lf_end; ++li) {
+    const LargeFront& x = lfs[li];
+    std::vector<LargeTask> tl;
+    build_front_tasks(x, li, Kc, tl);
+    verify_task_list(x, tl);
+    const int nt = x.nt, wt = x.wt;
+    std::vector<Writer> writer((size_t)nt * nt);
+    auto Wr = [&](int i, int j) -> Writer& { return writer[(size_t)i * nt + j]; };
+    for (const LargeTask& t : tl) {
+      const int id = (int)g.size();
+      const int k = t.k, i = t.i, j = t.j;
+      g.push_back(Node{t, 0.0, 0.0, 0.0, {}, 0});
+      switch (t.type) {
+        case 3: {
+          const bool more = k + 1 < nt;
+          g[id].dur = D.potrf + (more ? D.diag_trsm + D.diag_syrk : 0.0);
+          if (k == 0)
+            for (int e : ea_of[li]) add_dep(Writer{e, g[e].dur}, id, 0.0);
+          add_dep(Wr(k, k), id, 0.0);
+          Wr(k, k) = Writer{id, D.potrf};
+          if (more) {
+            add_dep(Wr(k + 1, k), id, D.potrf);
+            add_dep(Wr(k + 1, k + 1), id, D.potrf + D.diag_trsm);
+            Wr(k + 1, k) = Writer{id, D.potrf + D.diag_trsm};
+            Wr(k + 1, k + 1) = Writer{id, g[id].dur};
+          }
+          break;
+        }
+        case 5:
+          g[id].dur = D.inv;
+          add_dep(Wr(k, k), id, 0.0);
+          break;
+        case 1:
+          g[id].dur = D.trsm;
+          add_dep(Wr(k, k), id, 0.0);
+          add_dep(Wr(i, k), id, 0.0);
+          Wr(i, k) = Writer{id, g[id].dur};
+          break;
+        case 2:
+          g[id].dur = D.update;
+          add_dep(Wr(i, k), id, 0.0);
+          if (j != i) add_dep(Wr(j, k), id, 0.0);
+          add_dep(Wr(i, j), id, D.update - D.range_fix);
+          Wr(i, j) = Writer{id, g[id].dur};
+          break;
+        case 4:
+          g[id].dur = D.range_fix + D.range_step * (t.k1 - k);
+          for (int kk = k; kk < t.k1; ++kk) {  // operands are consumed one pivot step at a time
+            add_dep(Wr(i, kk), id, D.range_step * (kk - k));
+            if (j != i) add_dep(Wr(j, kk), id, D.range_step * (kk - k));
+          }
+          add_dep(Wr(i, j), id, g[id].dur - D.range_fix);
+          Wr(i, j) = Writer{id, g[id].dur};
+          break;
+        default: throw Error(SFX_ERR_INVALID_ARG, "internal: unknown tile task type");
+      }
+    }
+    if (x.parent_lf >= 0)
+      for (int j = wt; j < nt; ++j)
+        for (int i = j; i < nt; ++i) {
+          const int id = (int)g.size();
+          g.push_back(Node{LargeTask{li, 6, 0, (short)i, (short)j, 0, 0}, D.ea, 0.0, 0.0, {}, 0});
+          add_dep(Wr(i, j), id, 0.0);
+          ea_of[x.parent_lf].push_back(id);
+        }
+  }
+  // bottom levels (construction order is topological: fronts by ascending level, per-front lists valid)
+  const int n = (int)g.size();
+  double cp = 0.0;
+  for (int id = n - 1; id >= 0; --id) {
+    double m = g[id].dur;
+    for (const Edge& e : g[id].succ) m = std::max(m, e.lag + g[e.to].bl);
+    g[id].bl = m;
+    cp = std::max(cp, m);
+  }
+  // list scheduling: a free CTA takes the ready task with the longest path to the end
+  using Ev = std::pair<double, int>;
+  std::priority_queue<Ev, std::vector<Ev>, std::greater<Ev>> running;  // (finish time, task)
+  std::priority_queue<Ev, std::vector<Ev>, std::greater<Ev>> avail;    // (ready time, task): every predecessor started
+  std::priority_queue<Ev> ready;                                        // (bottom level, task): ready now
+  for (int id = 0; id < n; ++id)
+    if (g[id].indeg == 0) avail.push({0.0, id});
+  int free_w = std::max(1, workers);
+  double now = 0.0;
+  out.reserve(out.size() + n);
+  int started = 0;
+  while (started < n) {
+    while (!avail.empty() && avail.top().first <= now) {
+      ready.push({g[avail.top().second].bl, avail.top().second});
+      avail.pop();
+    }
+    if (free_w > 0 && !ready.empty()) {
+      const int id = ready.top().second;
+      ready.pop();
+      out.push_back(g[id].t);
+      running.push({now + g[id].dur, id});
+      --free_w;
+      ++started;
+      for (const Edge& e : g[id].succ) {
+        g[e.to].ready = std::max(g[e.to].ready, now + e.lag);
+        if (--g[e.to].indeg == 0) avail.push({g[e.to].ready, e.to});
+      }
+      continue;
+    }
+    double next = 1e300;
+    if (!running.empty() && free_w == 0) next = running.top().first;
+    if (!avail.empty()) next = std::min(next, avail.top().first);
+    if (free_w > 0 && !running.empty() && avail.empty()) next = running.top().first;
+    if (next >= 1e300) throw Error(SFX_ERR_INVALID_ARG, "internal: fused schedule has a dependency cycle");
+    // workers whose task finished by `next` become free
+    now = std::max(now, next);
+    while (!running.empty() && running.top().first <= now) {
+      running.pop();
+      ++free_w;
+    }
+  }
+  if (getenv("SFX_TIMING")) {
+    while (!running.empty()) {
+      now = std::max(now, running.top().first);
+      running.pop();
+    }
+    double busy[7] = {0, 0, 0, 0, 0, 0, 0};
+    int cnt[7] = {0, 0, 0, 0, 0, 0, 0};
+    for (int id = 0; id < n; ++id) {
+      busy[g[id].t.type] += g[id].dur;
+      cnt[g[id].t.type]++;
+    }
+    std::fprintf(stderr,
+                 "[sfx analysis] fused schedule: %d tasks on %d CTAs, modelled span %.0f us (critical path %.0f us); CTA-ms busy: "
+                 "TRSM %d/%.0f UPDATE %d/%.0f DIAG %d/%.0f RANGE %d/%.0f INV %d/%.0f EA %d/%.0f\n",
+                 n, workers, now, cp, cnt[1], busy[1] / 1e3, cnt[2], busy[2] / 1e3, cnt[3], busy[3] / 1e3, cnt[4], busy[4] / 1e3,
+                 cnt[5], busy[5] / 1e3, cnt[6], busy[6] / 1e3);
+  }
+}
+
+// Replays a fused list against the tile version counters and the assembly counters: every wait condition of
+// chol_large.cu must already hold when its task comes up, and every tile must end up final.
+void verify_fused_list(const std::vector<LargeFront>& lfs, int lf_begin, int lf_end, const std::vector<LargeTask>& tl,
+                       size_t t_begin) {
+  std::vector<std::vector<int>> cnt(lfs.size());
+  std::vector<int> assembled(lfs.size(), 0);
+  for (int li = lf_begin; li < lf_end; ++li) cnt[li].assign((size_t)lfs[li].nt * lfs[li].nt, 0);
+  auto fail = [&](const LargeTask& t, const char* why) {
+    throw Error(SFX_ERR_INVALID_ARG, std::string("internal: fused task list invalid (") + why + ") front " +
+                                         std::to_string(t.lf) + " type " + std::to_string(t.type) + " k " +
+                                         std::to_string(t.k) + " i " + std::to_string(t.i) + " j " + std::to_string(t.j));
+  };
+  for (size_t q = t_begin; q < tl.size(); ++q) {
+    const LargeTask& t = tl[q];
+    if (t.lf < lf_begin || t.lf >= lf_end) fail(t, "front out of range");
+    const LargeFront& x = lfs[t.lf];
+    const int nt = x.nt;
+    auto C = [&](int i, int j) -> int& { return cnt[t.lf][(size_t)i * nt + j]; };
+    const int k = t.k, i = t.i, j = t.j;
+    switch (t.type) {
+      case 3:
+        if (k == 0 && assembled[t.lf] != x.n_ea) fail(t, "front not assembled");
+        if (C(k, k) != k) fail(t, "diag not ready");
+        C(k, k) = k + 1;
+        if (k + 1 < nt) {
+          if (C(k + 1, k) != k) fail(t, "diag trsm");
+          C(k + 1, k) = k + 1;
+          if (C(k + 1, k + 1) != k) fail(t, "diag update");
+          C(k + 1, k + 1) = k + 1;
+        }
+        break;
+      case 5:
+        if (C(k, k) < k + 1) fail(t, "inv");
+        break;
+      case 1:
+        if (C(k, k) < k + 1 || C(i, k) != k) fail(t, "trsm");
+        C(i, k) = k + 1;
+        break;
+      case 2:
+        if (C(i, k) < k + 1 || C(j, k) < k + 1 || C(i, j) != k) fail(t, "update");
+        C(i, j) = k + 1;
+        break;
+      case 4:
+        for (int kk = k; kk < t.k1; ++kk)
+          if (C(i, kk) < kk + 1 || C(j, kk) < kk + 1) fail(t, "range operands");
+        if (C(i, j) != k) fail(t, "range target");
+        C(i, j) = t.k1;
+        break;
+      case 6:
+        if (x.parent_lf < lf_begin || x.parent_lf >= lf_end) fail(t, "extend-add without a fused parent");
+        if (j < x.wt || C(i, j) != x.wt) fail(t, "extend-add of a tile that is not final");
+        assembled[x.parent_lf]++;
+        break;
+      default: fail(t, "type");
+    }
+  }
+  for (int li = lf_begin; li < lf_end; ++li) {
+    const LargeFront& x = lfs[li];
+    if (assembled[li] != x.n_ea) throw Error(SFX_ERR_INVALID_ARG, "internal: fused front misses extend-add tasks");
+    for (int j = 0; j < x.nt; ++j)
+      for (int i = j; i < x.nt; ++i)
+        if (cnt[li][(size_t)i * x.nt + j] != (j < x.wt ? j + 1 : x.wt))
+          throw Error(SFX_ERR_INVALID_ARG, "internal: fused list leaves a tile unfinished");
+  }
+}
+
+// Host-side plan of the large-front path: which fronts go to the tile-DAG kernel, their tile task lists (per level,
+// or ONE fused list from level fused_T0 up), assembly jobs and workspace offsets.  No device calls: `workers` is the
+// number of CTAs of large_factor_kernel the device keeps resident (input of the list schedule).
+struct LargeHostPlan {
+  std::vector<int> lvl_fronts;
+  std::vector<LargeFront> lfs;
+  std::vector<LargeTask> tasks;
+  std::vector<LargeJob> jobs, pre_jobs, damp_jobs;
+  int64_t linv_off = 0, cnt_off = 0, flag_off = 0, contrib_off = 0;
+};
+void plan_large_fronts(sfx_problem* p, int workers, LargeHostPlan& hp) {
+  FrontPlan& f = p->a.fp;
+  // ---- split every level into small fronts (one CTA each, in shared memory) and large fronts
+  //      (tile-DAG kernel); small ones first in level_fronts
+  if (const char* e = getenv("SFX_SMALL_MAX")) p->small_max_m = std::min(atoi(e), p->smem_cap_m);
+  const int T = 64;
+  std::vector<int>& lvl_fronts = hp.lvl_fronts;
+  lvl_fronts = f.level_fronts;
+  p->lvl_max_m.assign(f.n_levels, 0);
+  p->lvl_small_cnt.assign(f.n_levels, 0);
+  p->lvl_large.assign(f.n_levels, LargeLevel{});
+  std::vector<LargeFront>& lfs = hp.lfs;
+  std::vector<LargeTask>& tasks = hp.tasks;
+  std::vector<LargeJob>&jobs = hp.jobs, &pre_jobs = hp.pre_jobs, &damp_jobs = hp.damp_jobs;
+  int64_t &linv_off = hp.linv_off, &cnt_off = hp.cnt_off, &flag_off = hp.flag_off, &contrib_off = hp.contrib_off;
+  auto is_small = [&](int s) { return f.f_w[s] + f.f_u[s] <= p->small_max_m; };
+  // first level of the fused top: no small fronts from there up (see build_fused_schedule)
+  int T0 = f.n_levels;
+  if (!getenv("SFX_NO_FUSE")) {
+    while (T0 > 0) {
+      bool all_large = true;
+      for (int q = f.level_ptr[T0 - 1]; q < f.level_ptr[T0] && all_large; ++q) all_large = !is_small(f.level_fronts[q]);
+      if (!all_large) break;
+      --T0;
+    }
+    if (T0 >= f.n_levels - 1) T0 = f.n_levels;  // a single level gains nothing
+  }
+  p->fused_T0 = T0 < f.n_levels ? T0 : -1;
+  std::vector<int> lf_of_front(f.n_fronts, -1);
+  for (int l = 0; l < f.n_levels; ++l) {
+    int* b = lvl_fronts.data() + f.level_ptr[l];
+    int* e = lvl_fronts.data() + f.level_ptr[l + 1];
+    const bool fused = l >= T0;
+    int* mid = std::stable_partition(b, e, is_small);
+    p->lvl_small_cnt[l] = (int)(mid - b);
+    for (int* q = b; q < mid; ++q) p->lvl_max_m[l] = std::max(p->lvl_max_m[l], f.f_w[*q] + f.f_u[*q]);
+    LargeLevel& lv = p->lvl_large[l];
+    lv.lf0 = (int)lfs.size();
+    lv.n_lf = (int)(e - mid);
+    lv.t0 = (int)tasks.size();
+    lv.j0 = (int)jobs.size();
+    lv.max_m = 0;
+    lv.max_nt = 0;
+    int max_wt = 0;
+    for (int* q = mid; q < e; ++q) {
+      const int s = *q;
+      LargeFront x{};
+      x.off = f.f_off[s];
+      x.m = f.f_w[s] + f.f_u[s];
+      x.w = f.f_w[s];
+      x.wt = (x.w + T - 1) / T;
+      x.nt = x.wt + (f.f_u[s] + T - 1) / T;
+      x.linv_off = linv_off;
+      x.cnt_off = (int)cnt_off;
+      x.front = s;
+      x.flag_off = (int)flag_off;
+      x.contrib_off = contrib_off;
+      x.parent_lf = -1;
+      x.n_ea = 0;
+      x.asm_off = 0;
+      lf_of_front[s] = (int)lfs.size();
+      flag_off += 2 * x.wt;
+      contrib_off += (int64_t)x.wt * x.nt * T;
+      lv.max_nt = std::max(lv.max_nt, x.nt);
+      linv_off += (int64_t)x.wt * T * T;
+      cnt_off += (int64_t)x.nt * x.nt;
+      SFX_CHECK(cnt_off < (int64_t)INT32_MAX, SFX_ERR_UNSUPPORTED, "too many tiles");
+      lv.max_m = std::max(lv.max_m, x.m);
+      max_wt = std::max(max_wt, x.wt);
+      const int li = (int)lfs.size();
+      lfs.push_back(x);
+      // assembly jobs
+      // system-matrix block copies and damping do not depend on the children: they run for all levels
+      // at once before level 0 (copies as plain stores: every entry has one source block); only the
+      // extend-add of the children stays between the levels
+      for (int c = f.f_copy_ptr[s]; c < f.f_copy_ptr[s + 1]; ++c) pre_jobs.push_back(LargeJob{li, 0, c, 0, 0});
+      for (int r = 0; r < x.w; r += 1024) damp_jobs.push_back(LargeJob{li, 2, 0, r, std::min(x.w, r + 1024)});
+      for (int ci = f.f_child_ptr[s]; ci < f.f_child_ptr[s + 1]; ++ci) {
+        const int c = f.f_child[ci];
+        const int uc = f.f_u[c];
+        if (fused && f.f_level[c] >= T0) continue;  // assembled by EXTEND-ADD tasks inside the fused launch
+        int c0 = 0;
+        while (c0 < uc) {
+          int c1 = c0;
+          int64_t el = 0;
+          while (c1 < uc && el < 1024) {
+            el += uc - c1;
+            ++c1;
+          }
+          jobs.push_back(LargeJob{li, 1, c, c0, c1});
+          c0 = c1;
+        }
+      }
+    }
+    // tasks: per front in an order that keeps every dependency earlier in the list (see
+    // chol_large.cu), then merged across the fronts of the level in proportion to their work so that
+    // the window of tasks in flight always spans all fronts (one front's critical path hides behind
+    // the others' trailing updates)
+    if (!fused) {
+      const int Kc = getenv("SFX_KC") ? std::max(1, atoi(getenv("SFX_KC"))) : 6;
+      std::vector<std::vector<LargeTask>> per(lv.n_lf);
+      for (int q = 0; q < lv.n_lf; ++q) {
+        // (shorter panels for narrow fronts were measured: slightly slower, 4.87 vs 4.82 ms at Final-shape)
+        build_front_tasks(lfs[lv.lf0 + q], lv.lf0 + q, Kc, per[q]);
+        verify_task_list(lfs[lv.lf0 + q], per[q]);
+      }
+      // proportional merge by cumulative cost
+      auto cost = [](const LargeTask& t) { return t.type == 4 ? (double)(t.k1 - t.k) : t.type == 3 ? 3.0 : 1.0; };
+      std::vector<double> tot(lv.n_lf, 0.0);
+      double longest = 0;
+      for (int q = 0; q < lv.n_lf; ++q) {
+        for (auto& t : per[q]) tot[q] += cost(t);
+        longest = std::max(longest, tot[q]);
+      }
+      std::vector<size_t> pos(lv.n_lf, 0);
+      std::vector<double> done(lv.n_lf, 0.0);
+      const int nsteps = 4096;
+      for (int step = 1; step <= nsteps; ++step)
+        for (int q = 0; q < lv.n_lf; ++q) {
+          const double upto = tot[q] * step / nsteps;
+          while (pos[q] < per[q].size() && done[q] < upto) {
+            done[q] += cost(per[q][pos[q]]);
+            tasks.push_back(per[q][pos[q]++]);
+          }
+        }
+      for (int q = 0; q < lv.n_lf; ++q)
+        while (pos[q] < per[q].size()) tasks.push_back(per[q][pos[q]++]);
+      (void)longest;
+    }
+    lv.t1 = (int)tasks.size();
+    lv.j1 = (int)jobs.size();
+    lv.solve_p = lv.n_lf > 0 ? std::max(1, std::min(lv.max_nt, 144 / lv.n_lf)) : 1;
+  }
+  if (T0 < f.n_levels) {
+    // fused top: parents, extend-add counts and assembly counters, then the list schedule
+    const int lf_begin = p->lvl_large[T0].lf0, lf_end = (int)lfs.size();
+    for (int li = lf_begin; li < lf_end; ++li) {
+      const int par = f.f_parent[lfs[li].front];
+      if (par < 0) continue;
+      const int pl = lf_of_front[par];
+      SFX_CHECK(pl >= lf_begin, SFX_ERR_INVALID_ARG, "internal: parent of a fused front is not fused");
+      lfs[li].parent_lf = pl;
+      const int ntu = lfs[li].nt - lfs[li].wt;
+      lfs[pl].n_ea += ntu * (ntu + 1) / 2;
+    }
+    for (int li = lf_begin; li < lf_end; ++li) lfs[li].asm_off = (int)cnt_off++;
+    SFX_CHECK(cnt_off < (int64_t)INT32_MAX, SFX_ERR_UNSUPPORTED, "too many tiles");
+    const int Kc = getenv("SFX_KC") ? std::max(1, atoi(getenv("SFX_KC"))) : 6;
+    p->fused_t0 = (int)tasks.size();
+    build_fused_schedule(lfs, lf_begin, lf_end, Kc, workers, tasks);
+    verify_fused_list(lfs, lf_begin, lf_end, tasks, (size_t)p->fused_t0);
+    p->fused_t1 = (int)tasks.size();
+    p->fused_j0 = p->lvl_large[T0].j0;
+    p->fused_j1 = (int)jobs.size();
+  }
 }
 
 void upload_structures(sfx_problem* p) {
@@ -586,117 +996,14 @@ void upload_structures(sfx_problem* p) {
     d.fronts = P.alloc<double>(f.front_values);
     d.twork = P.alloc<double>(f.solve_ws);
     d.ywork = P.alloc<double>(f.n);
-    // ---- split every level into small fronts (one CTA each, in shared memory) and large fronts
-    //      (tile-DAG kernel); small ones first in level_fronts
-    if (const char* e = getenv("SFX_SMALL_MAX")) p->small_max_m = std::min(atoi(e), p->smem_cap_m);
-    const int T = 64;
-    std::vector<int> lvl_fronts(f.level_fronts);
-    p->lvl_max_m.assign(f.n_levels, 0);
-    p->lvl_small_cnt.assign(f.n_levels, 0);
-    p->lvl_large.assign(f.n_levels, LargeLevel{});
-    std::vector<LargeFront> lfs;
-    std::vector<LargeTask> tasks;
-    std::vector<LargeJob> jobs, pre_jobs, damp_jobs;
-    int64_t linv_off = 0, cnt_off = 0, flag_off = 0, contrib_off = 0;
-    for (int l = 0; l < f.n_levels; ++l) {
-      int* b = lvl_fronts.data() + f.level_ptr[l];
-      int* e = lvl_fronts.data() + f.level_ptr[l + 1];
-      auto is_small = [&](int s) { return f.f_w[s] + f.f_u[s] <= p->small_max_m; };
-      int* mid = std::stable_partition(b, e, is_small);
-      p->lvl_small_cnt[l] = (int)(mid - b);
-      for (int* q = b; q < mid; ++q) p->lvl_max_m[l] = std::max(p->lvl_max_m[l], f.f_w[*q] + f.f_u[*q]);
-      LargeLevel& lv = p->lvl_large[l];
-      lv.lf0 = (int)lfs.size();
-      lv.n_lf = (int)(e - mid);
-      lv.t0 = (int)tasks.size();
-      lv.j0 = (int)jobs.size();
-      lv.max_m = 0;
-      lv.max_nt = 0;
-      int max_wt = 0;
-      for (int* q = mid; q < e; ++q) {
-        const int s = *q;
-        LargeFront x{};
-        x.off = f.f_off[s];
-        x.m = f.f_w[s] + f.f_u[s];
-        x.w = f.f_w[s];
-        x.wt = (x.w + T - 1) / T;
-        x.nt = x.wt + (f.f_u[s] + T - 1) / T;
-        x.linv_off = linv_off;
-        x.cnt_off = (int)cnt_off;
-        x.front = s;
-        x.flag_off = (int)flag_off;
-        x.contrib_off = contrib_off;
-        flag_off += 2 * x.wt;
-        contrib_off += (int64_t)x.wt * x.nt * T;
-        lv.max_nt = std::max(lv.max_nt, x.nt);
-        linv_off += (int64_t)x.wt * T * T;
-        cnt_off += (int64_t)x.nt * x.nt;
-        SFX_CHECK(cnt_off < (int64_t)INT32_MAX, SFX_ERR_UNSUPPORTED, "too many tiles");
-        lv.max_m = std::max(lv.max_m, x.m);
-        max_wt = std::max(max_wt, x.wt);
-        const int li = (int)lfs.size();
-        lfs.push_back(x);
-        // assembly jobs
-        // system-matrix block copies and damping do not depend on the children: they run for all levels
-        // at once before level 0 (copies as plain stores: every entry has one source block); only the
-        // extend-add of the children stays between the levels
-        for (int c = f.f_copy_ptr[s]; c < f.f_copy_ptr[s + 1]; ++c) pre_jobs.push_back(LargeJob{li, 0, c, 0, 0});
-        for (int r = 0; r < x.w; r += 1024) damp_jobs.push_back(LargeJob{li, 2, 0, r, std::min(x.w, r + 1024)});
-        for (int ci = f.f_child_ptr[s]; ci < f.f_child_ptr[s + 1]; ++ci) {
-          const int c = f.f_child[ci];
-          const int uc = f.f_u[c];
-          int c0 = 0;
-          while (c0 < uc) {
-            int c1 = c0;
-            int64_t el = 0;
-            while (c1 < uc && el < 1024) {
-              el += uc - c1;
-              ++c1;
-            }
-            jobs.push_back(LargeJob{li, 1, c, c0, c1});
-            c0 = c1;
-          }
-        }
-      }
-      // tasks: per front in an order that keeps every dependency earlier in the list (see
-      // chol_large.cu), then merged across the fronts of the level in proportion to their work so that
-      // the window of tasks in flight always spans all fronts (one front's critical path hides behind
-      // the others' trailing updates)
-      {
-        const int Kc = getenv("SFX_KC") ? std::max(1, atoi(getenv("SFX_KC"))) : 6;
-        std::vector<std::vector<LargeTask>> per(lv.n_lf);
-        for (int q = 0; q < lv.n_lf; ++q) {
-          // (shorter panels for narrow fronts were measured: slightly slower, 4.87 vs 4.82 ms at Final-shape)
-          build_front_tasks(lfs[lv.lf0 + q], lv.lf0 + q, Kc, per[q]);
-          verify_task_list(lfs[lv.lf0 + q], per[q]);
-        }
-        // proportional merge by cumulative cost
-        auto cost = [](const LargeTask& t) { return t.type == 4 ? (double)(t.k1 - t.k) : t.type == 3 ? 3.0 : 1.0; };
-        std::vector<double> tot(lv.n_lf, 0.0);
-        double longest = 0;
-        for (int q = 0; q < lv.n_lf; ++q) {
-          for (auto& t : per[q]) tot[q] += cost(t);
-          longest = std::max(longest, tot[q]);
-        }
-        std::vector<size_t> pos(lv.n_lf, 0);
-        std::vector<double> done(lv.n_lf, 0.0);
-        const int nsteps = 4096;
-        for (int step = 1; step <= nsteps; ++step)
-          for (int q = 0; q < lv.n_lf; ++q) {
-            const double upto = tot[q] * step / nsteps;
-            while (pos[q] < per[q].size() && done[q] < upto) {
-              done[q] += cost(per[q][pos[q]]);
-              tasks.push_back(per[q][pos[q]++]);
-            }
-          }
-        for (int q = 0; q < lv.n_lf; ++q)
-          while (pos[q] < per[q].size()) tasks.push_back(per[q][pos[q]++]);
-        (void)longest;
-      }
-      lv.t1 = (int)tasks.size();
-      lv.j1 = (int)jobs.size();
-      lv.solve_p = lv.n_lf > 0 ? std::max(1, std::min(lv.max_nt, 144 / lv.n_lf)) : 1;
-    }
+    CUDA_OK(configure_large_kernels());
+    LargeHostPlan hp;
+    plan_large_fronts(p, large_factor_resident_ctas(), hp);
+    std::vector<int>& lvl_fronts = hp.lvl_fronts;
+    std::vector<LargeFront>& lfs = hp.lfs;
+    std::vector<LargeTask>& tasks = hp.tasks;
+    std::vector<LargeJob>&jobs = hp.jobs, &pre_jobs = hp.pre_jobs, &damp_jobs = hp.damp_jobs;
+    const int64_t linv_off = hp.linv_off, cnt_off = hp.cnt_off, flag_off = hp.flag_off, contrib_off = hp.contrib_off;
     d.level_fronts = up32(lvl_fronts);
     p->n_large_fronts = (int)lfs.size();
     {
@@ -826,7 +1133,7 @@ int chain_top_level(const sfx_problem* p) {
   const FrontPlan& f = p->a.fp;
   // measured at Final-shape: the solve phase drops 1.01 -> 0.86 ms but the chain-bound levels slow down by the same
   // amount (the substitution CTAs share SMs with the diagonal-chain CTAs), so this stays opt-in
-  if (!getenv("SFX_SOLVE_OVERLAP") || getenv("SFX_SOLVE_V1")) return 0;
+  if (!getenv("SFX_SOLVE_OVERLAP") || getenv("SFX_SOLVE_V1") || p->fused_T0 >= 0) return 0;
   int T = f.n_levels;
   while (T > 0 && p->lvl_large[T - 1].n_lf == 1 && p->lvl_small_cnt[T - 1] == 0) --T;
   if (T >= f.n_levels || T == 0) return 0;
@@ -864,6 +1171,11 @@ void enqueue_factorize(sfx_problem* p, int overlap_T = 0, const double* rhs_stat
   launch_large_preassemble(p->st, p->d_ctrl, p->fd, p->ld, sys, p->sp, use_H, dv, p->pre_j0, p->pre_j1, p->damp_j0,
                            p->damp_j1);
   for (int l = 0; l < f.n_levels; ++l) {
+    if (l == p->fused_T0) {
+      launch_large_fused(p->st, p->d_ctrl, p->fd, p->ld, p->fused_t0, p->fused_t1, p->fused_j0, p->fused_j1, l, sys, p->sp,
+                         use_H, dv);
+      break;
+    }
     if (overlap_T > 0 && l == overlap_T) {
       begin_tri_solves(p);
       CUDA_OK(cudaEventRecord(p->ev_fork2, p->st));
@@ -1550,6 +1862,40 @@ int32_t sfx_debug_front_tasks(int32_t wt, int32_t nt, int32_t kc, int16_t* out, 
   }
 }
 
+// debug (host only): plans the large-front path of a problem for `workers` resident CTAs and reports
+// "fused_T0 n_large_fronts n_tasks n_fused_tasks n_ea_tasks n_jobs"; the fused list has passed verify_fused_list.
+// Returns 0, or 1 with sfx_last_error(NULL) set.
+int32_t sfx_debug_large_plan(const sfx_problem_desc* desc, int32_t workers, int64_t out[6]) {
+  try {
+    sfx_problem pr;
+    pr.params = desc->params;
+    analyze_problem(*desc, pr.a);
+    Analysis& a = pr.a;
+    const BlockMatrix& sys = a.schur ? a.sp.S : a.H;
+    std::vector<int> sys2ref;
+    if (desc->ordering == SFX_ORDERING_METIS_SCALAR) {
+      std::vector<int> int2ref(a.N);
+      for (int r = 0; r < a.N; ++r) int2ref[a.ref2int[r]] = r;
+      sys2ref.assign(int2ref.begin(), int2ref.begin() + sys.node_off[sys.n_nodes]);
+    }
+    build_front_plan(sys, desc->ordering, sys2ref, a.fp);
+    LargeHostPlan hp;
+    plan_large_fronts(&pr, workers, hp);
+    int64_t n_ea = 0;
+    for (int q = pr.fused_t0; q < pr.fused_t1; ++q) n_ea += hp.tasks[q].type == 6;
+    out[0] = pr.fused_T0;
+    out[1] = (int64_t)hp.lfs.size();
+    out[2] = (int64_t)hp.tasks.size();
+    out[3] = pr.fused_t1 - pr.fused_t0;
+    out[4] = n_ea;
+    out[5] = (int64_t)hp.jobs.size();
+    return 0;
+  } catch (const std::exception& e) {
+    g_create_err = e.what();
+    return 1;
+  }
+}
+
 // debug: average time of `reps` linearizations of state block 0 (zero + kernels + error reduce), with
 // parts of the BAL kernel left out when skip != 0 (timing experiment; leaves an invalid linearization)
 sfx_status sfx_debug_time_linearize(sfx_problem* p, int32_t skip, int32_t reps, float* ms) {
@@ -1588,6 +1934,7 @@ sfx_status sfx_debug_trace_tasks(sfx_problem* p, unsigned long long* host_out, i
   if (!host_out) {  // arm
     ntask = 0;
     for (auto& lv : p->lvl_large) ntask = std::max<int64_t>(ntask, lv.t1);
+    ntask = std::max<int64_t>(ntask, p->fused_t1);
     CUDA_OK(cudaMalloc(&dbuf, sizeof(unsigned long long) * 4 * ntask));
     CUDA_OK(cudaMemset(dbuf, 0, sizeof(unsigned long long) * 4 * ntask));
     CUDA_OK(cudaDeviceSynchronize());  // legacy-stream memset vs the non-blocking problem streams

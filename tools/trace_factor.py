@@ -18,11 +18,15 @@ t = buf.astype(np.int64)
 ok = t[:, 0] > 0
 t0 = t[ok, 0].min()
 claim, ready, done, potrf = (t[:, 0] - t0) / 1e3, (t[:, 1] - t0) / 1e3, (t[:, 2] - t0) / 1e3, (t[:, 3] - t0) / 1e3
-for ty, name in [(3, "DIAG"), (1, "TRSM"), (2, "UPDATE"), (4, "RANGE"), (5, "INV")]:
+for ty, name in [(3, "DIAG"), (1, "TRSM"), (2, "UPDATE"), (4, "RANGE"), (5, "INV"), (6, "EXTEND-ADD")]:
+    if not (ok & (info[:, 1] == ty)).any():
+        continue
     m = ok & (info[:, 1] == ty)
     print(f"{name}: n={m.sum()} wait(claim->ready) mean {np.mean(ready[m]-claim[m]):.1f} us  exec(ready->done) mean {np.mean(done[m]-ready[m]):.1f} us  p90 {np.percentile(done[m]-ready[m],90):.1f}")
 m = ok & (info[:, 1] == 3)
 print("DIAG potrf part (ready->potrf published) mean us:", np.mean(potrf[m] - ready[m]))
+print(f"all tasks: span {done[ok].max() - claim[ok].min():.0f} us, busy {np.sum(done[ok] - ready[ok]) / 1e3:.1f} CTA-ms, "
+      f"waiting {np.sum(ready[ok] - claim[ok]) / 1e3:.1f} CTA-ms")
 # critical path of the biggest front: DIAG done times by k
 lf = np.bincount(info[m, 0]).argmax()
 mm = m & (info[:, 0] == lf)

@@ -37,7 +37,7 @@ def load():
             raise RuntimeError(
                 f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "(symforce_b200 has no CPU fallback)")
-        _lib = C.CDLL(LIB_PATH)
+        _lib = C.CDLL(os.environ.get("SFX_LIB", LIB_PATH))  # SFX_LIB: A/B runs against another build
         _lib.sfx_last_error.restype = C.c_char_p
         _lib.sfx_last_error.argtypes = [C.c_void_p]
     return _lib

@@ -31,7 +31,7 @@ struct Ctrl {
   int skip_linearize;     // first-iteration linearize of Init only when not valid
   double red[8];          // reduction results: 0: new |r|^2 sum, 1: upd.(rhs - D.upd), 2: last.upd, 3: |last|^2, 4: |upd|^2
   int chol_fail;          // non-positive pivot seen
-  int pad;
+  int fail_where;         // tile-DAG path: (large front + 1) << 16 | pivot tile of the first failing POTRF (0: none)
   sfx_iteration iters[kMaxIterations + 1];
 };
 
@@ -156,6 +156,7 @@ struct LargeDev {
   double* contrib;  // backward-solve contribution slots (v1 solves)
   uint4* ll_y;       // v2 solves: LL slots of the forward solution (elimination order)
   uint4* ll_contrib; // v2 solves: LL slots of the backward contributions (same indexing as contrib)
+  int range_v1;      // range updates: 1 = register-staged double buffer, 0 = cp.async ring
 };
 void launch_large_level(cudaStream_t st, Ctrl* ctrl, const FrontDev& fd, const LargeDev& ld, const LargeLevel& lv,
                         int level, const double* sys_static, StatePtrs sp, int use_state_H, const double* dvec,

@@ -993,7 +993,7 @@ void upload_structures(sfx_problem* p) {
     }
     d.copies = P.upload(cp);
     d.scalar_perm = up32(f.scalar_perm);
-    d.fronts = P.alloc<double>(f.front_values);
+    d.fronts = P.alloc<double>(f.front_values + 128);  // slack: the range updates copy 16-byte aligned covers of tile columns
     d.twork = P.alloc<double>(f.solve_ws);
     d.ywork = P.alloc<double>(f.n);
     CUDA_OK(configure_large_kernels());
@@ -1026,6 +1026,7 @@ void upload_structures(sfx_problem* p) {
       p->n_zero_jobs = (int)zj.size();
       p->ld.zero_jobs = P.upload(zj);
     }
+    p->ld.range_v1 = getenv("SFX_RANGE_V2") ? 0 : 1;
     p->ld.lf = P.upload(lfs);
     p->ld.tasks = P.upload(tasks);
     p->pre_j0 = (int)jobs.size();
@@ -1860,6 +1861,16 @@ int32_t sfx_debug_front_tasks(int32_t wt, int32_t nt, int32_t kc, int16_t* out, 
     g_create_err = e.what();
     return -1;
   }
+}
+
+// debug: {chol_fail, fail_where} of the control block on the device right now
+sfx_status sfx_debug_chol_fail(sfx_problem* p, int32_t out[2]) {
+  SFX_API_BEGIN
+  SFX_CHECK(p && out, SFX_ERR_INVALID_ARG, "null argument");
+  CUDA_OK(cudaSetDevice(p->device));
+  CUDA_OK(cudaMemcpyAsync(out, (char*)p->d_ctrl + offsetof(Ctrl, chol_fail), 2 * sizeof(int), cudaMemcpyDeviceToHost, p->st));
+  CUDA_OK(cudaStreamSynchronize(p->st));
+  SFX_API_END(p)
 }
 
 // debug (host only): plans the large-front path of a problem for `workers` resident CTAs and reports

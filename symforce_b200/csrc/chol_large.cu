@@ -22,9 +22,7 @@ extern int64_t g_launches;
 constexpr int kT = 64;        // tile size
 constexpr int kLd = 68;       // smem leading dimension (== 4 mod 16: conflict-free DMMA fragment loads)
 constexpr int kLargeThreads = 256;
-// dynamic shared memory of large_factor_kernel: the three-stage ring of the range updates (two 64 x 32 operand halves
-// per stage); the two full tiles As | Bs of the other task types fit in its first two stages
-constexpr size_t kFactorSmem = 3 * 2 * 32 * 68 * sizeof(double);
+constexpr size_t kFactorSmem = 2 * 64 * 68 * sizeof(double);  // dynamic shared memory of large_factor_kernel: As | Bs
 
 __device__ __forceinline__ int ld_acquire(const int* p) {
   int v;
@@ -327,63 +325,6 @@ __device__ __forceinline__ void half_gemm(const double* As, const double* Bs, do
   }
 }
 
-// ---- range updates, v2: operand half tiles travel global -> shared with 16-byte cp.async.cg (LDGSTS, L1 bypassed)
-// through a three-stage ring: no registers, no store instructions and one block barrier per half tile.
-// Tile rows start at w + 64 t and columns at multiples of m, so a 64-double column segment is only 8-byte aligned:
-// the copy takes the 16-byte aligned COVER of the segment (33 chunks = 66 doubles, the shared-memory column holds
-// 68) and the consumer skips the leading element where there is one.  The skip depends on the column's parity
-// only, and a DMMA lane always reads columns of one parity (k = 4 q + tq), so it is a per-lane constant.
-// Rows past the end of a partial tile are whatever follows in the front: they only feed output rows that are
-// never stored.  Columns past the end of the (last, partial) pivot tile are zero-filled: they are the k dimension.
-constexpr int kRangeStages = 3;
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait() {
-  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
-}
-__device__ __forceinline__ void cp_async16(double* smem_dst, const double* gsrc, bool valid) {
-  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem_dst);
-  const int n = valid ? 16 : 0;  // src-size 0: zero fill
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(sa), "l"(gsrc), "r"(n) : "memory");
-}
-// S: 32 columns x kLd; G: element (row 0 of the tile, first column of the half); nc_left: valid columns from there
-__device__ __forceinline__ void issue_half16(double* S, const double* G, int m, int nc_left) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-#pragma unroll
-  for (int cc = 0; cc < 4; ++cc) {
-    const int c = warp * 4 + cc;
-    const double* g = G + (size_t)c * m;
-    const double* ga = (const double*)((uintptr_t)g & ~(uintptr_t)15);
-    cp_async16(S + c * kLd + 2 * lane, ga + 2 * lane, c < nc_left);
-  }
-  if (lane < 4) {  // 33rd chunk of the warp's four columns
-    const int c = warp * 4 + lane;
-    const double* g = G + (size_t)c * m;
-    const double* ga = (const double*)((uintptr_t)g & ~(uintptr_t)15);
-    cp_async16(S + c * kLd + 64, ga + 64, c < nc_left);
-  }
-}
-// acc += A * B^T over a 32-deep half tile pair; sa / sb: this lane's leading-element skip in the A / B columns it reads
-__device__ __forceinline__ void half_gemm_sh(const double* As, const double* Bs, int sa, int sb, double (&acc)[2][4][2]) {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int wr = warp & 3, wc = warp >> 2;
-  const int g = lane >> 2, tq = lane & 3;
-  const double* ap = As + (wr * 16 + g) + tq * kLd + sa;
-  const double* bp = Bs + (wc * 32 + g) + tq * kLd + sb;
-#pragma unroll
-  for (int kk = 0; kk < kHalf; kk += 4) {
-    double a[2], b[4];
-#pragma unroll
-    for (int rb = 0; rb < 2; ++rb) a[rb] = ap[rb * 8 + kk * kLd];
-#pragma unroll
-    for (int cb = 0; cb < 4; ++cb) b[cb] = bp[cb * 8 + kk * kLd];
-#pragma unroll
-    for (int rb = 0; rb < 2; ++rb)
-#pragma unroll
-      for (int cb = 0; cb < 4; ++cb) mma884(acc[rb][cb][0], acc[rb][cb][1], a[rb], b[cb]);
-  }
-}
-
 // ---- v2 critical path: panel Cholesky / panel substitution without shuffles or explicit inverses -----
 // C(8x8 tile (rb, cb) of Cs) -= X[rb rows][c0..c0+8) * Y[cb rows][c0..c0+8)^T   (one warp, two DMMA k-steps)
 __device__ __forceinline__ void rank8_tile(double* Cs, const double* Xs, const double* Ys, int rb, int cb, int c0) {
@@ -413,6 +354,7 @@ __device__ void potrf_64_v2(double* As, double* s_binv, int* fail) {
     const int c0 = 8 * p;
     const bool row_thread = tid < kT && tid >= c0;
     const bool inv_thread = tid >= kT && tid < kT + 8;
+    double out[8];  // row thread: its row of L in this panel; inverse thread: its column of the block inverse
     if (row_thread || inv_thread) {
       double D[8][8], ri[8];
 #pragma unroll
@@ -439,29 +381,25 @@ __device__ void potrf_64_v2(double* As, double* s_binv, int* fail) {
       }
       if (row_thread) {
         const int jr = tid - c0;
-        double x[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           double v = a[j];
 #pragma unroll
-          for (int c = 0; c < j; ++c) v -= x[c] * D[j][c];
-          x[j] = v * ri[j];
+          for (int c = 0; c < j; ++c) v -= out[c] * D[j][c];
+          out[j] = v * ri[j];
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) As[tid + (c0 + j) * kLd] = jr >= j ? x[j] : 0.0;
+        for (int j = 0; j < 8; ++j) out[j] = jr >= j ? out[j] : 0.0;
       } else {
         // column e of the inverse of the 8x8 block: y = L^-1 e_e by forward substitution
         const int e = tid - kT;
-        double y[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           double v = (i == e) ? 1.0 : 0.0;
 #pragma unroll
-          for (int c = 0; c < i; ++c) v -= D[i][c] * y[c];
-          y[i] = (i >= e) ? v * ri[i] : 0.0;
+          for (int c = 0; c < i; ++c) v -= D[i][c] * out[c];
+          out[i] = (i >= e) ? v * ri[i] : 0.0;
         }
-#pragma unroll
-        for (int i = 0; i < 8; ++i) s_binv[p * 64 + i + 8 * e] = y[i];
       }
     }
     else if (warp >= 3 && p >= 1 && p <= 6) {
@@ -471,6 +409,17 @@ __device__ void potrf_64_v2(double* As, double* s_binv, int* fail) {
       for (int cb = p + 1; cb < 8; ++cb)
         for (int rb = cb; rb < 8; ++rb, ++t)
           if (t % 5 == warp - 3) rank8_tile(As, As, As, rb, cb, c0 - 8);
+    }
+    // Every thread has read the 8 x 8 diagonal block (rows c0 .. c0 + 7 of the panel) before its owner rows are
+    // overwritten with L.  Without this barrier a warp that runs late (rows 32..63, the inverse threads) factors a
+    // half-written block: a shared-memory race that stayed invisible while all warps took the same time to get here.
+    __syncthreads();
+    if (row_thread) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) As[tid + (c0 + j) * kLd] = out[j];
+    } else if (inv_thread) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) s_binv[p * 64 + i + 8 * (tid - kT)] = out[i];
     }
     __syncthreads();
     // rank-8 update of the next panel's tile column only (one tile per warp); the rest overlaps the next panel
@@ -711,7 +660,7 @@ __global__ void __launch_bounds__(kLargeThreads, 2) large_factor_kernel(Ctrl* ct
         while (ld_acquire(cnt + i * nt + k) != k) __nanosleep(32);
       }
       __syncthreads();
-      if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 1] = gtime();
+          if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 1] = gtime();
       const int s0 = tile_start(lf, k), nb = tile_size(lf, k);
       const int ri = tile_start(lf, i), ni = tile_size(lf, i);
       double xf[8][2];
@@ -747,79 +696,36 @@ __global__ void __launch_bounds__(kLargeThreads, 2) large_factor_kernel(Ctrl* ct
       }
       __syncthreads();
       const bool all_ready = s_all_ready != 0;
-      const double* Gi = F + tile_start(lf, i);
-      const double* Gj = F + tile_start(lf, j);
-      auto issue = [&](int h) {
+      // register-staged double buffer (ld.global.cg -> registers -> st.shared): measured faster than a cp.async ring
+      // (8- or 16-byte copies, three stages) whose 104 KB of shared memory leaves the SM almost no L1
+      double ra[kHalfPerThread], rb_[kHalfPerThread];
+      auto fetch = [&](int h) {
         const int kk = k + (h >> 1);
         if ((h & 1) == 0 && !all_ready) {
-          // operands of step kk must be final
           if (tid == 0) {
             while (ld_acquire(cnt + i * nt + kk) < kk + 1) __nanosleep(32);
             while (ld_acquire(cnt + j * nt + kk) < kk + 1) __nanosleep(32);
           }
           __syncthreads();
         }
-        double* st = sm + (h % kRangeStages) * 2 * kHalfDoubles;
-        const int c0 = (h & 1) * kHalf;
-        const int nc_left = tile_size(lf, kk) - c0;
-        const size_t col = (size_t)(kk * kT + c0) * m;
-        issue_half16(st, Gi + col, m, nc_left);
-        issue_half16(st + kHalfDoubles, Gj + col, m, nc_left);
-        cp_async_commit();
+        load_half(ra, F, m, lf, i, kk, (h & 1) * kHalf);
+        load_half(rb_, F, m, lf, j, kk, (h & 1) * kHalf);
       };
-      if (ld.range_v1) {
-        // register-staged double buffer (ld.global.cg -> registers -> st.shared)
-        double ra[kHalfPerThread], rb_[kHalfPerThread];
-        auto fetch = [&](int h) {
-          const int kk = k + (h >> 1);
-          if ((h & 1) == 0 && !all_ready) {
-            if (tid == 0) {
-              while (ld_acquire(cnt + i * nt + kk) < kk + 1) __nanosleep(32);
-              while (ld_acquire(cnt + j * nt + kk) < kk + 1) __nanosleep(32);
-            }
-            __syncthreads();
-          }
-          load_half(ra, F, m, lf, i, kk, (h & 1) * kHalf);
-          load_half(rb_, F, m, lf, j, kk, (h & 1) * kHalf);
-        };
-        fetch(0);
-        if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 1] = gtime();
-        store_half(sm, ra);
-        store_half(sm + kHalfDoubles, rb_);
-        __syncthreads();
-        for (int h = 0; h < nh; ++h) {
-          double* cur = sm + (h & 1) * 2 * kHalfDoubles;
-          double* nxt = sm + ((h + 1) & 1) * 2 * kHalfDoubles;
-          if (h + 1 < nh) fetch(h + 1);
-          half_gemm(cur, cur + kHalfDoubles, acc);
-          if (h + 1 < nh) {
-            store_half(nxt, ra);
-            store_half(nxt + kHalfDoubles, rb_);
-          }
-          __syncthreads();
-        }
-      } else {
-      issue(0);
+      fetch(0);
       if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 1] = gtime();
-      issue(1);  // nh >= 2
-      {
-        const int tqp = tid & 1;  // parity of the columns this lane reads (k = 4 q + tq)
-        const int mpar = m & 1;
-        for (int h = 0; h < nh; ++h) {
-          if (h + 1 < nh)
-            cp_async_wait<1>();
-          else
-            cp_async_wait<0>();
-          __syncthreads();  // half h has landed for everyone, and everyone is done with half h - 1
-          if (h + 2 < nh) issue(h + 2);
-          const double* cur = sm + (h % kRangeStages) * 2 * kHalfDoubles;
-          const size_t col = (size_t)(k + (h >> 1)) * kT + (h & 1) * kHalf;  // first column of the half (even)
-          const int ca = (int)((col * (size_t)mpar + (size_t)tqp * mpar) & 1);  // parity contribution of the column
-          const int sa = (int)((((uintptr_t)Gi >> 3) + ca) & 1);
-          const int sb = (int)((((uintptr_t)Gj >> 3) + ca) & 1);
-          half_gemm_sh(cur, cur + kHalfDoubles, sa, sb, acc);
+      store_half(sm, ra);
+      store_half(sm + kHalfDoubles, rb_);
+      __syncthreads();
+      for (int h = 0; h < nh; ++h) {
+        double* cur = sm + (h & 1) * 2 * kHalfDoubles;
+        double* nxt = sm + ((h + 1) & 1) * 2 * kHalfDoubles;
+        if (h + 1 < nh) fetch(h + 1);
+        half_gemm(cur, cur + kHalfDoubles, acc);
+        if (h + 1 < nh) {
+          store_half(nxt, ra);
+          store_half(nxt + kHalfDoubles, rb_);
         }
-      }
+        __syncthreads();
       }
       // C tile: all earlier updates applied
       wait_eq(cnt + i * nt + j, k);
@@ -869,7 +775,7 @@ __global__ void __launch_bounds__(kLargeThreads, 2) large_factor_kernel(Ctrl* ct
         }
       }
       __syncthreads();
-      if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 1] = gtime();
+          if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 1] = gtime();
       const int ck = tile_start(lf, k), nk = tile_size(lf, k);
       load_tile(As, F + tile_start(lf, i) + (size_t)ck * m, m, tile_size(lf, i), nk, false);
       if (trsm)
@@ -1152,6 +1058,11 @@ constexpr int kSLd = 65;  // conflict-free for both T*x (lanes over rows) and T^
 __device__ __forceinline__ void cp_async8(double* smem, const double* g) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(s), "l"(g) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void issue_tile(double* T, const double* __restrict__ G, int ldg, int nr, int nc) {
   const int r = threadIdx.x & 63;

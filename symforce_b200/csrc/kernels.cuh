@@ -156,7 +156,6 @@ struct LargeDev {
   double* contrib;  // backward-solve contribution slots (v1 solves)
   uint4* ll_y;       // v2 solves: LL slots of the forward solution (elimination order)
   uint4* ll_contrib; // v2 solves: LL slots of the backward contributions (same indexing as contrib)
-  int range_v1;      // range updates: 1 = register-staged double buffer, 0 = cp.async ring
 };
 void launch_large_level(cudaStream_t st, Ctrl* ctrl, const FrontDev& fd, const LargeDev& ld, const LargeLevel& lv,
                         int level, const double* sys_static, StatePtrs sp, int use_state_H, const double* dvec,

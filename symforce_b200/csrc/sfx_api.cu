@@ -993,7 +993,7 @@ void upload_structures(sfx_problem* p) {
     }
     d.copies = P.upload(cp);
     d.scalar_perm = up32(f.scalar_perm);
-    d.fronts = P.alloc<double>(f.front_values + 128);  // slack: the range updates copy 16-byte aligned covers of tile columns
+    d.fronts = P.alloc<double>(f.front_values);
     d.twork = P.alloc<double>(f.solve_ws);
     d.ywork = P.alloc<double>(f.n);
     CUDA_OK(configure_large_kernels());
@@ -1026,7 +1026,6 @@ void upload_structures(sfx_problem* p) {
       p->n_zero_jobs = (int)zj.size();
       p->ld.zero_jobs = P.upload(zj);
     }
-    p->ld.range_v1 = getenv("SFX_RANGE_V2") ? 0 : 1;
     p->ld.lf = P.upload(lfs);
     p->ld.tasks = P.upload(tasks);
     p->pre_j0 = (int)jobs.size();
@@ -1861,6 +1860,45 @@ int32_t sfx_debug_front_tasks(int32_t wt, int32_t nt, int32_t kc, int16_t* out, 
     g_create_err = e.what();
     return -1;
   }
+}
+
+// debug: the reduced camera system S (block values, n from the first call with out == NULL) as the last Schur pass left it
+sfx_status sfx_debug_read_S(sfx_problem* p, double* out, int64_t* n) {
+  SFX_API_BEGIN
+  SFX_CHECK(p && n && p->a.schur, SFX_ERR_INVALID_ARG, "not a Schur problem");
+  *n = p->a.sp.S.n_values;
+  if (out) {
+    CUDA_OK(cudaSetDevice(p->device));
+    CUDA_OK(cudaMemcpyAsync(out, p->sd.S, sizeof(double) * (size_t)*n, cudaMemcpyDeviceToHost, p->st));
+    CUDA_OK(cudaStreamSynchronize(p->st));
+  }
+  SFX_API_END(p)
+}
+
+// debug: the frontal matrices as the last factorization left them; *n = number of doubles; geometry of the large fronts
+// as int64 records {off, m, w, wt, nt} in `lf_info` (capacity lf_cap records, *n_lf = count)
+sfx_status sfx_debug_read_fronts(sfx_problem* p, double* out, int64_t* n, int64_t* lf_info, int32_t lf_cap, int32_t* n_lf) {
+  SFX_API_BEGIN
+  SFX_CHECK(p && n, SFX_ERR_INVALID_ARG, "null argument");
+  *n = p->a.fp.front_values;
+  CUDA_OK(cudaSetDevice(p->device));
+  if (out) {
+    CUDA_OK(cudaMemcpyAsync(out, p->fd.fronts, sizeof(double) * (size_t)*n, cudaMemcpyDeviceToHost, p->st));
+    CUDA_OK(cudaStreamSynchronize(p->st));
+  }
+  if (lf_info && n_lf) {
+    std::vector<LargeFront> lfs(p->n_large_fronts);
+    CUDA_OK(cudaMemcpy(lfs.data(), p->ld.lf, sizeof(LargeFront) * lfs.size(), cudaMemcpyDeviceToHost));
+    *n_lf = (int32_t)lfs.size();
+    for (int i = 0; i < std::min<int>(lf_cap, *n_lf); ++i) {
+      lf_info[5 * i + 0] = lfs[i].off;
+      lf_info[5 * i + 1] = lfs[i].m;
+      lf_info[5 * i + 2] = lfs[i].w;
+      lf_info[5 * i + 3] = lfs[i].wt;
+      lf_info[5 * i + 4] = lfs[i].nt;
+    }
+  }
+  SFX_API_END(p)
 }
 
 // debug: {chol_fail, fail_where} of the control block on the device right now

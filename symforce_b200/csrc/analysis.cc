@@ -377,6 +377,7 @@ void analyze_problem(const sfx_problem_desc& d, Analysis& a) {
     while (r + 1 < a.world) lm_rank_begin[++r] = nk;
     lm_rank_begin[a.world] = nk;
   }
+  a.lm_rank_begin = lm_rank_begin;
   auto owner_of = [&](const FactorRef& fr) -> int {
     if (a.world == 1) return 0;
     const sfx_factor_batch& fb = d.batches[fr.batch];

@@ -76,6 +76,9 @@ struct NcclApi {
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Reduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Broadcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void*, void*, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
   const char* (*GetErrorString)(ncclResult_t) = nullptr;
 };
 static NcclApi& nccl() {
@@ -98,6 +101,9 @@ static NcclApi& nccl() {
     api.AllReduce = (decltype(api.AllReduce))sym("ncclAllReduce");
     api.Reduce = (decltype(api.Reduce))sym("ncclReduce");
     api.Broadcast = (decltype(api.Broadcast))sym("ncclBroadcast");
+    api.AllGather = (decltype(api.AllGather))sym("ncclAllGather");
+    api.GroupStart = (decltype(api.GroupStart))sym("ncclGroupStart");
+    api.GroupEnd = (decltype(api.GroupEnd))sym("ncclGroupEnd");
     api.GetErrorString = (decltype(api.GetErrorString))sym("ncclGetErrorString");
   }
   return api;
@@ -142,6 +148,10 @@ struct sfx_problem {
   bool dbg_valid = false;
   bool can_continue = false;  // the control block is the one the last sfx_optimize[_continue] left
   std::vector<std::pair<int64_t, int64_t>> opt_ranges;  // merged storage ranges of the optimized keys
+  // multi-GPU: storage range [first, second) of the landmarks every rank owns, when each is one contiguous run of the
+  // values buffer (BAL: points are stored in key order); empty otherwise (masked all-reduce fallback)
+  std::vector<std::pair<int64_t, int64_t>> rank_lm_range;
+  int64_t values_chunk = 0;  // multi-GPU: doubles of the values buffer every rank uploads (ceil(n_values / world))
   int pre_j0 = 0, pre_j1 = 0, damp_j0 = 0, damp_j1 = 0;  // assembly jobs run before level 0 (copies, damping)
   Ctrl* d_ctrl = nullptr;
   Ctrl* h_ctrl = nullptr;  // pinned
@@ -816,7 +826,23 @@ void upload_structures(sfx_problem* p) {
     p->sp.rhs[b] = P.alloc<double>(a.N);
     p->sp.res[b] = P.alloc<double>(a.M);
   }
-  p->d_cur_values = P.alloc<double>(a.n_values);
+  p->values_chunk = (a.n_values + a.world - 1) / a.world;
+  p->d_cur_values = P.alloc<double>(p->values_chunk * a.world);
+  if (a.world > 1 && (int)a.lm_rank_begin.size() == a.world + 1) {
+    bool ok = true;
+    for (int r = 0; r < a.world && ok; ++r) {
+      int64_t lo = INT64_MAX, hi = -1, tot = 0;
+      for (int k = a.lm_rank_begin[r]; k < a.lm_rank_begin[r + 1]; ++k) {
+        lo = std::min<int64_t>(lo, a.keys[k].voff);
+        hi = std::max<int64_t>(hi, (int64_t)a.keys[k].voff + a.keys[k].sdim);
+        tot += a.keys[k].sdim;
+      }
+      if (tot == 0) lo = hi = 0;
+      ok = tot == hi - lo;  // contiguous: nothing else lives inside the run
+      p->rank_lm_range.emplace_back(lo, hi);
+    }
+    if (!ok) p->rank_lm_range.clear();
+  }
   p->d_dvec = P.alloc<double>(a.N);
   p->d_maxdiag = P.alloc<double>(a.N);
   p->d_upd = P.alloc<double>(a.N);
@@ -1268,6 +1294,26 @@ void ensure_jacobian(sfx_problem* p) {
   }
 }
 
+// multi-GPU: `src` holds the replicated keys and this rank's landmarks; returns a buffer with every rank's landmarks.
+// Contiguous landmark runs travel as one broadcast per owner over NVLink; other layouts as a masked all-reduce.
+const double* gather_sharded_values(sfx_problem* p, const double* src, int64_t n) {
+  if (!p->rank_lm_range.empty()) {
+    CUDA_OK(cudaMemcpyAsync(p->d_stage, src, sizeof(double) * n, cudaMemcpyDeviceToDevice, p->st));
+    NCCL_OK(nccl().GroupStart());
+    for (int r = 0; r < p->a.world; ++r) {
+      const auto& x = p->rank_lm_range[r];
+      if (x.second > x.first)
+        NCCL_OK(nccl().Broadcast(p->d_stage + x.first, p->d_stage + x.first, (size_t)(x.second - x.first), ncclDouble, r,
+                                 p->comm->comm, p->st));
+    }
+    NCCL_OK(nccl().GroupEnd());
+    return p->d_stage;
+  }
+  launch_mask_values(p->st, src, p->d_vmask, n, p->d_stage);
+  NCCL_OK(nccl().AllReduce(p->d_stage, p->d_stage, (size_t)n, ncclDouble, ncclSum, p->comm->comm, p->st));
+  return p->d_stage;
+}
+
 void export_linearization(sfx_problem* p, int blk, double* residual, double* rhs, double* Hv) {
   Analysis& a = p->a;
   if (residual)
@@ -1403,7 +1449,16 @@ sfx_status sfx_set_values(sfx_problem* p, const double* values, int64_t n) {
   SFX_CHECK(p && values, SFX_ERR_INVALID_ARG, "null argument");
   SFX_CHECK(n == p->a.n_values, SFX_ERR_INVALID_ARG, "values length mismatch");
   CUDA_OK(cudaSetDevice(p->device));
-  CUDA_OK(cudaMemcpyAsync(p->d_cur_values, values, sizeof(double) * n, cudaMemcpyHostToDevice, p->st));
+  if (p->a.world > 1 && !getenv("SFX_FULL_UPLOAD")) {
+    // every rank holds the same Values (the sharded solve is SPMD): each uploads one slice over its own PCIe link and
+    // the slices are exchanged over NVLink -- n / world doubles per rank through PCIe instead of n
+    const int64_t c = p->values_chunk, lo = std::min<int64_t>(n, c * p->a.rank), hi = std::min<int64_t>(n, lo + c);
+    if (hi > lo)
+      CUDA_OK(cudaMemcpyAsync(p->d_cur_values + lo, values + lo, sizeof(double) * (hi - lo), cudaMemcpyHostToDevice, p->st));
+    NCCL_OK(nccl().AllGather(p->d_cur_values + c * p->a.rank, p->d_cur_values, (size_t)c, ncclDouble, p->comm->comm, p->st));
+  } else {
+    CUDA_OK(cudaMemcpyAsync(p->d_cur_values, values, sizeof(double) * n, cudaMemcpyHostToDevice, p->st));
+  }
   CUDA_OK(cudaStreamSynchronize(p->st));
   p->values_set = true;
   SFX_API_END(p)
@@ -1572,12 +1627,7 @@ sfx_status sfx_get_best_values(sfx_problem* p, double* values, int64_t n) {
   SFX_CHECK(p->h_ctrl->best_valid, SFX_ERR_INVALID_ARG, "SYM_ASSERT: state_.BestIsValid()");
   CUDA_OK(cudaSetDevice(p->device));
   const double* src = p->sp.values[p->h_ctrl->best_idx];
-  if (p->a.world > 1) {
-    // every rank holds the cameras and its own landmarks: masked all-reduce assembles the full buffer
-    launch_mask_values(p->st, src, p->d_vmask, n, p->d_stage);
-    NCCL_OK(nccl().AllReduce(p->d_stage, p->d_stage, (size_t)n, ncclDouble, ncclSum, p->comm->comm, p->st));
-    src = p->d_stage;
-  }
+  if (p->a.world > 1) src = gather_sharded_values(p, src, n);
   CUDA_OK(cudaMemcpyAsync(values, src, sizeof(double) * n, cudaMemcpyDeviceToHost, p->st));
   CUDA_OK(cudaStreamSynchronize(p->st));
   SFX_API_END(p)
@@ -1597,14 +1647,18 @@ sfx_status sfx_update_best_values(sfx_problem* p, double* values, int64_t n, int
   }
   const double* src = p->sp.values[p->h_ctrl->best_idx];
   if (a.world > 1) {
-    // every rank holds the cameras and its own landmarks: a masked all-reduce per optimized range assembles them
-    for (const auto& x : p->opt_ranges) {
-      const int64_t len = x.second - x.first;
-      launch_mask_values(p->st, src + x.first, p->d_vmask + x.first, len, p->d_stage + x.first);
-      NCCL_OK(nccl().AllReduce(p->d_stage + x.first, p->d_stage + x.first, (size_t)len, ncclDouble, ncclSum,
-                               p->comm->comm, p->st));
+    if (!p->rank_lm_range.empty()) {
+      src = gather_sharded_values(p, src, n);
+    } else {
+      // every rank holds the cameras and its own landmarks: a masked all-reduce per optimized range assembles them
+      for (const auto& x : p->opt_ranges) {
+        const int64_t len = x.second - x.first;
+        launch_mask_values(p->st, src + x.first, p->d_vmask + x.first, len, p->d_stage + x.first);
+        NCCL_OK(nccl().AllReduce(p->d_stage + x.first, p->d_stage + x.first, (size_t)len, ncclDouble, ncclSum,
+                                 p->comm->comm, p->st));
+      }
+      src = p->d_stage;
     }
-    src = p->d_stage;
   }
   int64_t total = 0;
   for (const auto& x : p->opt_ranges) {

@@ -156,6 +156,7 @@ struct Analysis {
   int64_t h_accum_values = 0; // prefix of H values that is accumulated (must be zeroed)
   int64_t b_values = 0;       // prefix holding every block among reduced nodes (B); summed across ranks
   int rank = 0, world = 1;
+  std::vector<int> lm_rank_begin;  // multi-GPU: first landmark key of every rank (world + 1 entries, identical on all ranks)
   std::vector<int32_t> diag_pos;  // per internal scalar: H value offset of its diagonal entry
   std::vector<BatchPlan> batches;
   bool schur = false;

@@ -312,7 +312,10 @@ enum {
   SFX_INFO_SCHUR_PAIRS = 10,
   SFX_INFO_MAX_FRONT = 11,
   SFX_INFO_DEVICE_BYTES = 12,
-  SFX_INFO_COUNT = 13
+  SFX_INFO_CHOL_FAILURES = 13,  /* iterations of the last sfx_optimize whose LLT met a non-positive pivot (step rejected) */
+  SFX_INFO_NONFINITE_UPDATES = 14, /* iterations of the last sfx_optimize with a non-finite update vector */
+  SFX_INFO_ZERO_DIAGONAL = 15,  /* debug_checks: damped diagonal entries below epsilon (CheckHessianDiagonal) */
+  SFX_INFO_COUNT = 16
 };
 sfx_status sfx_get_info(sfx_problem* p, int64_t* out, int32_t capacity);
 

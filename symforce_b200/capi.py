@@ -25,7 +25,8 @@ EXPORTS = [
 ]
 
 INFO_NAMES = ["N", "M", "nnz_H", "num_nodes", "reduced_dim", "nnz_L", "num_supernodes", "num_levels",
-              "factor_flops", "s_blocks", "schur_pairs", "max_front", "device_bytes"]
+              "factor_flops", "s_blocks", "schur_pairs", "max_front", "device_bytes", "chol_failures",
+              "nonfinite_updates", "zero_diagonal"]
 
 _lib = None
 

@@ -732,6 +732,12 @@ __global__ void damping_kernel(Ctrl* ctrl, StatePtrs sp, const int32_t* __restri
   }
   if (p.use_unit_damping) d += lam;
   dvec[i] = d;
+  if (p.debug_checks) {  // CheckHessianDiagonal: zero on the diagonal after damping
+    if (fabs(H[diag_pos[i]] + d) < ctrl->epsilon) {
+      const int slot = atomicAdd(&ctrl->n_zero_diag, 1);
+      if (slot < 15) ctrl->zero_diag_idx[slot] = i;
+    }
+  }
 }
 
 __global__ void damping_flag_kernel(Ctrl* ctrl) {
@@ -2043,6 +2049,11 @@ __global__ void lm_end_kernel(Ctrl* c, const double* __restrict__ upd, double* _
       status = 3;
       c->failure_reason = 1;
     }
+    if (c->chol_fail) {  // LLT met a non-positive pivot: the step is NaN (rejected below); counted, not hidden
+      c->n_chol_fail++;
+      c->chol_fail = 0;
+    }
+    if (!isfinite(c->red[4])) c->n_nonfinite_update++;
     sfx_iteration& it = c->iters[c->n_iters];
     it.iteration = c->iteration;
     it.current_lambda = c->lambda;

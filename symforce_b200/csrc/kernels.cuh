@@ -32,6 +32,11 @@ struct Ctrl {
   double red[8];          // reduction results: 0: new |r|^2 sum, 1: upd.(rhs - D.upd), 2: last.upd, 3: |last|^2, 4: |upd|^2
   int chol_fail;          // non-positive pivot seen
   int fail_where;         // tile-DAG path: (large front + 1) << 16 | pivot tile of the first failing POTRF (0: none)
+  // diagnostics of the run (debug_checks / verbose, levenberg_marquardt_solver.tcc:57-90, 225-227)
+  int n_chol_fail;        // iterations whose factorization met a non-positive pivot (the step is NaN and gets rejected)
+  int n_nonfinite_update; // iterations with a non-finite update vector
+  int n_zero_diag;        // damped diagonal entries below epsilon seen by the damping pass (debug_checks)
+  int zero_diag_idx[15];  // the first of them (internal tangent order)
   sfx_iteration iters[kMaxIterations + 1];
 };
 

@@ -1121,6 +1121,8 @@ void reset_ctrl_continue(sfx_problem* p) {
   c->done = 0;
   c->failure_reason = 0;
   c->chol_fail = 0;
+  c->fail_where = 0;
+  c->n_chol_fail = c->n_nonfinite_update = c->n_zero_diag = 0;
   CUDA_OK(cudaMemcpyAsync(p->d_ctrl, c, offsetof(Ctrl, iters), cudaMemcpyHostToDevice, p->st));
   std::memset(p->h_done, 0, sizeof(int) * (kMaxIterations + 2));
 }
@@ -1474,6 +1476,7 @@ static sfx_status optimize_impl(sfx_problem* p, int32_t num_iterations, sfx_stat
   CUDA_OK(cudaSetDevice(p->device));
   Analysis& a = p->a;
   const int64_t launches0 = g_launches;
+  const int n_iters_before = cont ? p->h_ctrl->n_iters : 0;
   if (cont) {
     SFX_CHECK(p->can_continue, SFX_ERR_INVALID_ARG,
               "sfx_optimize_continue must directly follow sfx_optimize / sfx_optimize_continue (SYM_ASSERT: IsInitialized())");
@@ -1570,6 +1573,38 @@ static sfx_status optimize_impl(sfx_problem* p, int32_t num_iterations, sfx_stat
     if (e != cudaSuccess) throw Error(SFX_ERR_CUDA, std::string("kernel failure: ") + cudaGetErrorString(e));
   }
   const Ctrl& c = *p->h_ctrl;
+  // optimizer_params_t::verbose / debug_checks: the reference logs from inside Iterate (spdlog, stdout); the records
+  // live on the device until here, so the same lines come out after the run, on stderr
+  if ((p->params.verbose || p->params.debug_checks) && a.rank == 0) {
+    const int first = cont ? std::max(n_iters_before, 1) : 1;
+    if (p->params.verbose) {
+      double prev = c.n_iters > 0 ? c.iters[0].new_error : 0.0;
+      for (int i = 1; i < c.n_iters; ++i) {
+        const sfx_iteration& it = c.iters[i];
+        const double gain = (prev - it.new_error) / (prev - it.new_error_linear);
+        if (i >= first)
+          std::fprintf(stderr,
+                       "LM<sfx> [iter %4d] lambda: %.3e, error prev/linear/new: %.3e/%.3e/%.3e, rel reduction: %.5e, "
+                       "gain ratio: %.5e\n",
+                       it.iteration, it.current_lambda, prev, it.new_error_linear, it.new_error, it.relative_reduction, gain);
+        if (it.update_accepted) prev = it.new_error;
+      }
+    }
+    if (c.n_chol_fail > 0)
+      std::fprintf(stderr, "LM<sfx> the Cholesky factorization met a non-positive pivot in %d iteration(s): those steps are "
+                           "non-finite and were rejected (lambda = %.2e at the end)\n", c.n_chol_fail, c.lambda);
+    if (p->params.debug_checks) {
+      if (c.n_nonfinite_update > 0)
+        std::fprintf(stderr, "LM<sfx> Encountered non-finite values in the update vector in %d iteration(s)\n",
+                     c.n_nonfinite_update);
+      if (c.n_zero_diag > 0) {
+        std::string idx;
+        for (int i = 0; i < std::min(c.n_zero_diag, 15); ++i) idx += (i ? ", " : "") + std::to_string(c.zero_diag_idx[i]);
+        std::fprintf(stderr, "LM<sfx> Zero on diagonal after damping (epsilon = %.2e) at internal indices: [%s%s]\n", c.epsilon,
+                     idx.c_str(), c.n_zero_diag > 15 ? (", ... (" + std::to_string(c.n_zero_diag - 15) + " omitted)").c_str() : "");
+      }
+    }
+  }
   sfx_stats s{};
   s.status = c.done ? c.done : 2;  // HIT_ITERATION_LIMIT
   s.failure_reason = c.done == 3 ? c.failure_reason : 0;
@@ -2077,6 +2112,9 @@ sfx_status sfx_get_info(sfx_problem* p, int64_t* out, int32_t capacity) {
   v[SFX_INFO_SCHUR_PAIRS] = a.schur ? (int64_t)a.sp.m_lm.size() : 0;
   v[SFX_INFO_MAX_FRONT] = a.fp.max_front;
   v[SFX_INFO_DEVICE_BYTES] = p->pool.bytes;
+  v[SFX_INFO_CHOL_FAILURES] = p->h_ctrl->n_chol_fail;
+  v[SFX_INFO_NONFINITE_UPDATES] = p->h_ctrl->n_nonfinite_update;
+  v[SFX_INFO_ZERO_DIAGONAL] = p->h_ctrl->n_zero_diag;
   for (int i = 0; i < std::min<int>(capacity, SFX_INFO_COUNT); ++i) out[i] = v[i];
   SFX_API_END(p)
 }

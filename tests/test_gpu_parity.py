@@ -335,3 +335,30 @@ def test_bal_text_file_through_python_and_cpp(tmp_path):
     for e, it in zip(errs, its):
         assert abs(e - it.new_error) <= 1e-7 * abs(it.new_error)
     g.close()
+
+
+def test_verbose_and_debug_checks_report_from_the_device_records(capfd):
+    """optimizer_params_t::verbose / debug_checks (levenberg_marquardt_solver.tcc:57-90, 105-113): one line per iteration
+    with the reference's fields, and the diagnostics counters through sfx_get_info."""
+    prob = P.bal_problem("small", solver=D.SOLVER_SCHUR, params=_params(verbose=1, debug_checks=1))
+    gpu = capi.SfxProblem(prob, device=0)
+    st = gpu.optimize()
+    its = gpu.iterations()
+    err = capfd.readouterr().err
+    lines = [l for l in err.splitlines() if l.startswith("LM<sfx> [iter")]
+    assert len(lines) == len(its) - 1
+    assert "lambda:" in lines[0] and "error prev/linear/new:" in lines[0] and "gain ratio:" in lines[0]
+    info = gpu.info()
+    assert info["chol_failures"] == 0 and info["nonfinite_updates"] == 0 and info["zero_diagonal"] == 0
+    assert st.status == D.STATUS_SUCCESS
+    gpu.close()
+
+
+def test_invalid_params_are_rejected():
+    """A zero-initialised / inconsistent optimizer_params_t must not silently run another algorithm."""
+    p = _params(lambda_update_type=0)
+    with pytest.raises(RuntimeError, match="lambda_update_type"):
+        capi.SfxProblem(P.bal_problem("tiny", solver=D.SOLVER_SCHUR, params=p), device=0)
+    p = _params(lambda_lower_bound=10.0, lambda_upper_bound=1.0)
+    with pytest.raises(RuntimeError, match="lambda_lower_bound"):
+        capi.SfxProblem(P.bal_problem("tiny", solver=D.SOLVER_SCHUR, params=p), device=0)

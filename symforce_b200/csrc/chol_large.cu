@@ -522,7 +522,7 @@ void set_factor_trace(unsigned long long* buf) { cudaMemcpyToSymbol(g_trace, &bu
 void get_diag_stamps(unsigned long long* out) { cudaMemcpyFromSymbol(out, g_diag_stamps, sizeof(unsigned long long) * 8 * 512); }
 
 __global__ void __launch_bounds__(kLargeThreads, 2) large_factor_kernel(Ctrl* ctrl, FrontDev fd, LargeDev ld, int t0,
-                                                                     int t1, int level) {
+                                                                     int t1, int level, int fwd) {
   extern __shared__ __align__(16) double sm[];
   double* As = sm;
   double* Bs = sm + kT * kLd;
@@ -617,7 +617,10 @@ __global__ void __launch_bounds__(kLargeThreads, 2) large_factor_kernel(Ctrl* ct
         const int r = tid & 63;
         for (int c = tid >> 6; c < kT; c += kLargeThreads / 64) linv[r + c * kT] = Bs[r + c * kLd];
       }
-      __syncthreads();
+      if (fwd)
+        publish(ld.counters + lf.vc_off + nt + lf.wt + k, 1);  // L_kk^-1 ready for the fused forward substitution
+      else
+        __syncthreads();
       if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 2] = gtime();
     } else if (task.type == 6) {
       // ---------------- EXTEND-ADD: update tile (i,j) of this (final) front -> its parent front ----------------
@@ -651,6 +654,88 @@ __global__ void __launch_bounds__(kLargeThreads, 2) large_factor_kernel(Ctrl* ct
       if (tid == 0) {
         __threadfence();
         atomicAdd(ld.counters + pf.asm_off, 1);
+      }
+      if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 2] = gtime();
+    } else if (task.type >= 8) {
+      // ---------------- fused forward substitution L y = b (fd.ywork gets y, pivot rows in elimination order) -----
+      // 8: y_k = L_kk^-1 b_k     9: b_i -= L(i,k) y_k     10: update rows of b -> the parent's b
+      if (!fwd) continue;  // a factorization without a right-hand side (covariances)
+      int* vc = ld.counters + lf.vc_off;  // [nt] updates applied to row tile | [wt] y published | [wt] L_kk^-1 ready | [1]
+      double* b = ld.fwd_b + lf.fb_off;
+      const int wt = lf.wt;
+      double* red = sm;          // 256 partial sums
+      double* xs = sm + 256;     // 64 operand entries
+      if (task.type == 8) {
+        if (tid == 0) {
+          if (k == 0)
+            while (ld_acquire(vc + nt + 2 * wt) < lf.n_vch) __nanosleep(32);
+          while (ld_acquire(vc + k) < k) __nanosleep(32);
+          while (ld_acquire(vc + nt + wt + k) < 1) __nanosleep(32);
+        }
+        __syncthreads();
+        if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 1] = gtime();
+        const int s0 = tile_start(lf, k), nb = tile_size(lf, k);
+        if (tid < kT) xs[tid] = tid < nb ? __ldcg(b + s0 + tid) : 0.0;
+        const double* linv = ld.linv + lf.linv_off + (size_t)k * kT * kT;
+        const int r = tid & 63, gq = tid >> 6;
+        double lv[kT / 4];
+#pragma unroll
+        for (int q = 0; q < kT / 4; ++q) lv[q] = __ldcg(linv + r + (size_t)(gq + 4 * q) * kT);
+        __syncthreads();
+        double v = 0.0;
+#pragma unroll
+        for (int q = 0; q < kT / 4; ++q) v += lv[q] * xs[gq + 4 * q];
+        red[gq * 64 + r] = v;
+        __syncthreads();
+        if (tid < nb) fd.ywork[fd.f_piv[lf.front] + s0 + tid] = red[tid] + red[64 + tid] + red[128 + tid] + red[192 + tid];
+        publish(vc + nt + k, 1);
+      } else if (task.type == 9) {
+        if (tid == 0) {
+          while (ld_acquire(vc + nt + k) < 1) __nanosleep(32);
+          while (ld_acquire(cnt + i * nt + k) < k + 1) __nanosleep(32);
+        }
+        __syncthreads();
+        if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 1] = gtime();
+        const int s0 = tile_start(lf, k), nk = tile_size(lf, k);
+        const int ri = tile_start(lf, i), ni = tile_size(lf, i);
+        if (tid < kT) xs[tid] = tid < nk ? __ldcg(fd.ywork + fd.f_piv[lf.front] + s0 + tid) : 0.0;
+        const double* Lt = F + ri + (size_t)s0 * m;
+        const int r = tid & 63, gq = tid >> 6;
+        double lv[kT / 4];
+#pragma unroll
+        for (int q = 0; q < kT / 4; ++q) {
+          const int c = gq + 4 * q;
+          lv[q] = (r < ni && c < nk) ? __ldcg(Lt + r + (size_t)c * m) : 0.0;
+        }
+        __syncthreads();
+        double v = 0.0;
+#pragma unroll
+        for (int q = 0; q < kT / 4; ++q) v += lv[q] * xs[gq + 4 * q];
+        red[gq * 64 + r] = v;
+        __syncthreads();
+        if (tid < ni) atomicAdd(b + ri + tid, -(red[tid] + red[64 + tid] + red[128 + tid] + red[192 + tid]));
+        __syncthreads();
+        if (tid == 0) {
+          __threadfence();
+          atomicAdd(vc + i, 1);
+        }
+      } else {
+        // every update row tile has received its wt contributions
+        if (tid < 32) {
+          for (int q = wt + tid; q < nt; q += 32)
+            while (ld_acquire(vc + q) < wt) __nanosleep(32);
+        }
+        __syncthreads();
+        if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 1] = gtime();
+        const LargeFront pf = ld.lf[lf.parent_lf];
+        double* pb = ld.fwd_b + pf.fb_off;
+        const int32_t* rel = fd.f_rel + fd.f_rows_ptr[lf.front];
+        for (int q = tid; q < m - lf.w; q += kLargeThreads) atomicAdd(pb + __ldg(rel + q), __ldcg(b + lf.w + q));
+        __syncthreads();
+        if (tid == 0) {
+          __threadfence();
+          atomicAdd(ld.counters + pf.vc_off + pf.nt + 2 * pf.wt, 1);
+        }
       }
       if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 2] = gtime();
     } else if (task.type == 1) {
@@ -887,7 +972,7 @@ void launch_large_level(cudaStream_t st, Ctrl* ctrl, const FrontDev& fd, const L
   // single-front levels are bound by the diagonal chain, not by throughput: one CTA per SM is as fast as two
   // (measured) and leaves room for the forward-substitution CTAs that overlap them
   if (grid_cap > 0 && grid > grid_cap) grid = grid_cap;
-  large_factor_kernel<<<grid, kLargeThreads, kFactorSmem, st>>>(ctrl, fd, ld, lv.t0, lv.t1, level); ++g_launches;
+  large_factor_kernel<<<grid, kLargeThreads, kFactorSmem, st>>>(ctrl, fd, ld, lv.t0, lv.t1, level, 0); ++g_launches;
 }
 
 
@@ -1403,12 +1488,43 @@ void launch_large_solve_bwd(cudaStream_t st, const Ctrl* ctrl, const FrontDev& f
   ++g_launches;
 }
 
+// Right-hand sides of the fused fronts for the forward substitution inside the factor kernel: pivot rows from the
+// system right-hand side, update rows zero, plus the update vectors of children factored by earlier launches.
+__global__ void __launch_bounds__(256) large_fwd_init_kernel(const Ctrl* __restrict__ ctrl, FrontDev fd, LargeDev ld, int lf0,
+                                                              int first_fused_level, const int32_t* __restrict__ f_level,
+                                                              const double* __restrict__ rhs_static, StatePtrs sp,
+                                                              int use_state_rhs) {
+  if (ctrl->done) return;
+  const LargeFront lf = ld.lf[lf0 + blockIdx.x];
+  const int s = lf.front, w = lf.w, m = lf.m;
+  const double* rhs = use_state_rhs ? sp.rhs[ctrl->init_idx] : rhs_static;
+  double* b = ld.fwd_b + lf.fb_off;
+  for (int r = threadIdx.x; r < m; r += 256) b[r] = r < w ? rhs[fd.scalar_perm[fd.f_piv[s] + r]] : 0.0;
+  __syncthreads();
+  for (int ci = fd.f_child_ptr[s]; ci < fd.f_child_ptr[s + 1]; ++ci) {
+    const int c = fd.f_child[ci];
+    if (f_level[c] >= first_fused_level) continue;  // added by a task of the factor kernel
+    const int uc = fd.f_u[c];
+    const double* t = fd.twork + fd.f_toff[c];
+    const int32_t* rel = fd.f_rel + fd.f_rows_ptr[c];
+    for (int q = threadIdx.x; q < uc; q += 256) b[rel[q]] += t[q];  // rows of one child are distinct
+    __syncthreads();
+  }
+}
+void launch_large_fwd_init(cudaStream_t st, const Ctrl* ctrl, const FrontDev& fd, const LargeDev& ld, int lf0, int n_lf,
+                           int first_fused_level, const int32_t* f_level, const double* rhs_static, StatePtrs sp,
+                           int use_state_rhs) {
+  if (n_lf <= 0) return;
+  large_fwd_init_kernel<<<n_lf, 256, 0, st>>>(ctrl, fd, ld, lf0, first_fused_level, f_level, rhs_static, sp, use_state_rhs);
+  ++g_launches;
+}
+
 // All levels from the first fused one up in ONE launch: the assembly jobs that do not depend on fronts of this
 // launch (children factored by earlier launches), then the tile tasks of every fused front in the order of the
 // host-side list schedule (sfx_api.cu: build_fused_schedule), extend-adds included.
 void launch_large_fused(cudaStream_t st, Ctrl* ctrl, const FrontDev& fd, const LargeDev& ld, int t0, int t1, int j0,
                         int j1, int queue_slot, const double* sys_static, StatePtrs sp, int use_state_H,
-                        const double* dvec) {
+                        const double* dvec, int fwd) {
   if (j1 > j0) {
     large_assemble_kernel<<<(j1 - j0 + 7) / 8, 256, 0, st>>>(ctrl, fd, ld, sys_static, sp, use_state_H, dvec, j0, j1, 0);
     ++g_launches;
@@ -1417,7 +1533,7 @@ void launch_large_fused(cudaStream_t st, Ctrl* ctrl, const FrontDev& fd, const L
   if (ntask <= 0) return;
   const int cap = large_factor_resident_ctas();
   const int grid = ntask < cap ? ntask : cap;
-  large_factor_kernel<<<grid, kLargeThreads, kFactorSmem, st>>>(ctrl, fd, ld, t0, t1, queue_slot); ++g_launches;
+  large_factor_kernel<<<grid, kLargeThreads, kFactorSmem, st>>>(ctrl, fd, ld, t0, t1, queue_slot, fwd); ++g_launches;
 }
 
 // The spin-waits of the tile-DAG kernel need every CTA of a launch resident: grids are capped at what the device

@@ -130,11 +130,18 @@ struct LargeFront {
   int64_t contrib_off;  // backward-solve contribution slots: wt * nt * 64 doubles
   int n_ea;          // fused schedule: extend-add tasks (type 6) that assemble this front inside the factor kernel
   int asm_off;       // ... and the counter (in LargeDev::counters) they bump; DIAG(0) waits for n_ea
+  // fused forward substitution (tasks 8-10): the front's right-hand side b (m doubles at LargeDev::fwd_b + fb_off) and
+  // its counters in LargeDev::counters at vc_off: [nt] updates applied to tile row i | [wt] y_k published |
+  // [wt] L_kk^-1 ready | [1] children's update vectors added
+  int fb_off, vc_off;
+  int n_vch;         // fused children whose update vector is added by a VEC-EXTEND-ADD task
+  int pad2;
 };
 struct LargeTask {
   int lf;
   short type, k, i, j;  // type: 1 TRSM(i,k), 2 UPDATE(i,j,k), 3 DIAG(k), 4 UPDATE(i,j,[k,k1)), 5 INV(k),
-                        //       6 EXTEND-ADD of update tile (i,j) of front `lf` into its parent front
+                        //       6 EXTEND-ADD of update tile (i,j) of front `lf` into its parent front,
+                        //       8 y_k = L_kk^-1 b_k, 9 b_i -= L(i,k) y_k, 10 update part of b -> the parent's b
   short k1, pad;
 };
 struct LargeJob {
@@ -161,6 +168,7 @@ struct LargeDev {
   double* contrib;  // backward-solve contribution slots (v1 solves)
   uint4* ll_y;       // v2 solves: LL slots of the forward solution (elimination order)
   uint4* ll_contrib; // v2 solves: LL slots of the backward contributions (same indexing as contrib)
+  double* fwd_b;     // fused forward substitution: right-hand sides of the fused fronts
 };
 void launch_large_level(cudaStream_t st, Ctrl* ctrl, const FrontDev& fd, const LargeDev& ld, const LargeLevel& lv,
                         int level, const double* sys_static, StatePtrs sp, int use_state_H, const double* dvec,
@@ -178,7 +186,10 @@ cudaError_t configure_large_kernels();
 int large_factor_resident_ctas();  // CTAs of large_factor_kernel the device keeps resident (occupancy x SM count)
 void launch_large_fused(cudaStream_t st, Ctrl* ctrl, const FrontDev& fd, const LargeDev& ld, int t0, int t1, int j0,
                         int j1, int queue_slot, const double* sys_static, StatePtrs sp, int use_state_H,
-                        const double* dvec);
+                        const double* dvec, int fwd);
+void launch_large_fwd_init(cudaStream_t st, const Ctrl* ctrl, const FrontDev& fd, const LargeDev& ld, int lf0, int n_lf,
+                           int first_fused_level, const int32_t* f_level, const double* rhs_static, StatePtrs sp,
+                           int use_state_rhs);
 
 // launchers (all asynchronous on `st`)
 void launch_zero_lin(cudaStream_t st, const Ctrl* ctrl, StatePtrs sp, int mode, int64_t n_h, int n_rhs);

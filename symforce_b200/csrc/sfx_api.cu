@@ -139,6 +139,8 @@ struct sfx_problem {
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fork2 = nullptr, ev_join2 = nullptr;
   int fused_T0 = -1;  // first level of the fused top of the elimination tree (-1: none)
   int fused_t0 = 0, fused_t1 = 0, fused_j0 = 0, fused_j1 = 0;
+  bool fused_fwd = false;       // the forward substitution of the fused fronts rides inside the factor kernel
+  int32_t* d_f_level = nullptr; // front -> level (large_fwd_init_kernel)
   int n_large_fronts = 0;
   int n_zero_jobs = 0;
   unsigned solve_epoch = 0;
@@ -341,9 +343,9 @@ void verify_task_list(const LargeFront& x, const std::vector<LargeTask>& tl) {
 struct FusedDur {
   // us, from the task trace of round 1 (profiles/r01_results.md); DIAG = POTRF | TRSM(k+1,k) | UPDATE(k+1,k+1,k)
   double potrf = 14.0, diag_trsm = 5.0, diag_syrk = 5.0, trsm = 7.7, update = 9.0, range_step = 6.0, range_fix = 2.0,
-         inv = 16.0, ea = 3.0;
+         inv = 16.0, ea = 3.0, vsolve = 2.5, gemv = 2.5, veav = 3.0;
 };
-void build_fused_schedule(const std::vector<LargeFront>& lfs, int lf_begin, int lf_end, int Kc, int workers,
+void build_fused_schedule(const std::vector<LargeFront>& lfs, int lf_begin, int lf_end, int Kc, int workers, bool with_fwd,
                           std::vector<LargeTask>& out) {
   struct Edge {
     int to;
@@ -365,6 +367,7 @@ void build_fused_schedule(const std::vector<LargeFront>& lfs, int lf_begin, int 
   if (const char* e = getenv("SFX_SIM_RANGE_STEP_US")) D.range_step = atof(e);
   std::vector<Node> g;
   std::vector<std::vector<int>> ea_of(lfs.size());  // per parent large front: its extend-add tasks
+  std::vector<std::vector<int>> veav_of(lfs.size());  // ... and the vector extend-adds of the forward substitution
   auto add_dep = [&](const Writer& w, int to, double in_off) {
     if (w.id < 0) return;
     g[w.id].succ.push_back(Edge{to, w.out - in_off});
@@ -435,6 +438,38 @@ void build_fused_schedule(const std::vector<LargeFront>& lfs, int lf_begin, int 
           add_dep(Wr(i, j), id, 0.0);
           ea_of[x.parent_lf].push_back(id);
         }
+    if (with_fwd) {
+      // forward substitution riding behind the factorization: y_k = L_kk^-1 b_k (8), b_i -= L(i,k) y_k (9), update
+      // rows of b into the parent (10)
+      std::vector<int> inv_of(wt, -1);
+      for (int id = 0; id < (int)g.size(); ++id)
+        if (g[id].t.lf == li && g[id].t.type == 5) inv_of[g[id].t.k] = id;
+      std::vector<std::vector<int>> into(nt);  // GEMV tasks that update row tile i
+      std::vector<int> gemv_update;            // ... those of the update rows
+      for (int k = 0; k < wt; ++k) {
+        const int vs = (int)g.size();
+        g.push_back(Node{LargeTask{li, 8, (short)k, (short)k, (short)k, 0, 0}, D.vsolve, 0.0, 0.0, {}, 0});
+        add_dep(Writer{inv_of[k], D.inv}, vs, 0.0);
+        for (int e : into[k]) add_dep(Writer{e, D.gemv}, vs, 0.0);
+        if (k == 0)
+          for (int e : veav_of[li]) add_dep(Writer{e, D.veav}, vs, 0.0);
+        for (int i = k + 1; i < nt; ++i) {
+          const int id = (int)g.size();
+          g.push_back(Node{LargeTask{li, 9, (short)k, (short)i, (short)k, 0, 0}, D.gemv, 0.0, 0.0, {}, 0});
+          add_dep(Writer{vs, D.vsolve}, id, 0.0);
+          add_dep(Wr(i, k), id, 0.0);  // the final writer of L(i,k): TRSM(i,k) or DIAG(k)
+          into[i].push_back(id);
+          if (i >= wt) gemv_update.push_back(id);
+        }
+      }
+      if (x.parent_lf >= 0) {
+        const int id = (int)g.size();
+        g.push_back(Node{LargeTask{li, 10, 0, 0, 0, 0, 0}, D.veav, 0.0, 0.0, {}, 0});
+        for (int e : gemv_update) add_dep(Writer{e, D.gemv}, id, 0.0);
+        if (gemv_update.empty() && wt > 0) add_dep(Writer{id - 1, D.vsolve}, id, 0.0);
+        veav_of[x.parent_lf].push_back(id);
+      }
+    }
   }
   // bottom levels (construction order is topological: fronts by ascending level, per-front lists valid)
   const int n = (int)g.size();
@@ -491,17 +526,17 @@ void build_fused_schedule(const std::vector<LargeFront>& lfs, int lf_begin, int 
       now = std::max(now, running.top().first);
       running.pop();
     }
-    double busy[7] = {0, 0, 0, 0, 0, 0, 0};
-    int cnt[7] = {0, 0, 0, 0, 0, 0, 0};
+    double busy[11] = {0};
+    int cnt[11] = {0};
     for (int id = 0; id < n; ++id) {
       busy[g[id].t.type] += g[id].dur;
       cnt[g[id].t.type]++;
     }
     std::fprintf(stderr,
                  "[sfx analysis] fused schedule: %d tasks on %d CTAs, modelled span %.0f us (critical path %.0f us); CTA-ms busy: "
-                 "TRSM %d/%.0f UPDATE %d/%.0f DIAG %d/%.0f RANGE %d/%.0f INV %d/%.0f EA %d/%.0f\n",
+                 "TRSM %d/%.0f UPDATE %d/%.0f DIAG %d/%.0f RANGE %d/%.0f INV %d/%.0f EA %d/%.0f FWD %d/%.0f\n",
                  n, workers, now, cp, cnt[1], busy[1] / 1e3, cnt[2], busy[2] / 1e3, cnt[3], busy[3] / 1e3, cnt[4], busy[4] / 1e3,
-                 cnt[5], busy[5] / 1e3, cnt[6], busy[6] / 1e3);
+                 cnt[5], busy[5] / 1e3, cnt[6], busy[6] / 1e3, cnt[8] + cnt[9] + cnt[10], (busy[8] + busy[9] + busy[10]) / 1e3);
   }
 }
 
@@ -511,6 +546,14 @@ void verify_fused_list(const std::vector<LargeFront>& lfs, int lf_begin, int lf_
                        size_t t_begin) {
   std::vector<std::vector<int>> cnt(lfs.size());
   std::vector<int> assembled(lfs.size(), 0);
+  // forward substitution: per front updates applied to row tile i, y_k published, L_kk^-1 ready, children vectors added
+  std::vector<std::vector<int>> bcount(lfs.size()), ypub(lfs.size()), invd(lfs.size());
+  std::vector<int> vasm(lfs.size(), 0), n_fwd(lfs.size(), 0);
+  for (int li = lf_begin; li < lf_end; ++li) {
+    bcount[li].assign(lfs[li].nt, 0);
+    ypub[li].assign(lfs[li].wt, 0);
+    invd[li].assign(lfs[li].wt, 0);
+  }
   for (int li = lf_begin; li < lf_end; ++li) cnt[li].assign((size_t)lfs[li].nt * lfs[li].nt, 0);
   auto fail = [&](const LargeTask& t, const char* why) {
     throw Error(SFX_ERR_INVALID_ARG, std::string("internal: fused task list invalid (") + why + ") front " +
@@ -538,6 +581,24 @@ void verify_fused_list(const std::vector<LargeFront>& lfs, int lf_begin, int lf_
         break;
       case 5:
         if (C(k, k) < k + 1) fail(t, "inv");
+        invd[t.lf][k] = 1;
+        break;
+      case 8:
+        if (k == 0 && vasm[t.lf] != x.n_vch) fail(t, "forward: children's vectors missing");
+        if (!invd[t.lf][k] || bcount[t.lf][k] != k) fail(t, "forward: y_k not ready");
+        ypub[t.lf][k] = 1;
+        n_fwd[t.lf]++;
+        break;
+      case 9:
+        if (!ypub[t.lf][k] || C(i, k) < k + 1) fail(t, "forward: gemv operands");
+        bcount[t.lf][i]++;
+        n_fwd[t.lf]++;
+        break;
+      case 10:
+        for (int q = x.wt; q < nt; ++q)
+          if (bcount[t.lf][q] != x.wt) fail(t, "forward: update rows incomplete");
+        if (x.parent_lf < lf_begin || x.parent_lf >= lf_end) fail(t, "forward: no fused parent");
+        vasm[x.parent_lf]++;
         break;
       case 1:
         if (C(k, k) < k + 1 || C(i, k) != k) fail(t, "trsm");
@@ -564,6 +625,11 @@ void verify_fused_list(const std::vector<LargeFront>& lfs, int lf_begin, int lf_
   for (int li = lf_begin; li < lf_end; ++li) {
     const LargeFront& x = lfs[li];
     if (assembled[li] != x.n_ea) throw Error(SFX_ERR_INVALID_ARG, "internal: fused front misses extend-add tasks");
+    if (n_fwd[li] > 0) {
+      if (vasm[li] != x.n_vch) throw Error(SFX_ERR_INVALID_ARG, "internal: fused forward substitution misses a child vector");
+      for (int k2 = 0; k2 < x.wt; ++k2)
+        if (!ypub[li][k2]) throw Error(SFX_ERR_INVALID_ARG, "internal: fused forward substitution leaves a pivot tile unsolved");
+    }
     for (int j = 0; j < x.nt; ++j)
       for (int i = j; i < x.nt; ++i)
         if (cnt[li][(size_t)i * x.nt + j] != (j < x.wt ? j + 1 : x.wt))
@@ -579,7 +645,7 @@ struct LargeHostPlan {
   std::vector<LargeFront> lfs;
   std::vector<LargeTask> tasks;
   std::vector<LargeJob> jobs, pre_jobs, damp_jobs;
-  int64_t linv_off = 0, cnt_off = 0, flag_off = 0, contrib_off = 0;
+  int64_t linv_off = 0, cnt_off = 0, flag_off = 0, contrib_off = 0, fwd_b_size = 0;
 };
 void plan_large_fronts(sfx_problem* p, int workers, LargeHostPlan& hp) {
   FrontPlan& f = p->a.fp;
@@ -641,6 +707,7 @@ void plan_large_fronts(sfx_problem* p, int workers, LargeHostPlan& hp) {
       x.parent_lf = -1;
       x.n_ea = 0;
       x.asm_off = 0;
+      x.fb_off = x.vc_off = x.n_vch = x.pad2 = 0;
       lf_of_front[s] = (int)lfs.size();
       flag_off += 2 * x.wt;
       contrib_off += (int64_t)x.wt * x.nt * T;
@@ -727,10 +794,22 @@ void plan_large_fronts(sfx_problem* p, int workers, LargeHostPlan& hp) {
       lfs[pl].n_ea += ntu * (ntu + 1) / 2;
     }
     for (int li = lf_begin; li < lf_end; ++li) lfs[li].asm_off = (int)cnt_off++;
+    // fused forward substitution: right-hand sides and counters of the fused fronts
+    p->fused_fwd = !getenv("SFX_NO_FUSED_FWD");
+    int64_t fb = 0;
+    for (int li = lf_begin; li < lf_end; ++li) {
+      lfs[li].fb_off = (int)fb;
+      fb += lfs[li].m;
+      lfs[li].vc_off = (int)cnt_off;
+      cnt_off += lfs[li].nt + 2 * lfs[li].wt + 1;
+      if (p->fused_fwd && lfs[li].parent_lf >= 0) lfs[lfs[li].parent_lf].n_vch++;
+    }
+    SFX_CHECK(fb < (int64_t)INT32_MAX, SFX_ERR_UNSUPPORTED, "fused fronts too large");
+    hp.fwd_b_size = fb;
     SFX_CHECK(cnt_off < (int64_t)INT32_MAX, SFX_ERR_UNSUPPORTED, "too many tiles");
     const int Kc = getenv("SFX_KC") ? std::max(1, atoi(getenv("SFX_KC"))) : 6;
     p->fused_t0 = (int)tasks.size();
-    build_fused_schedule(lfs, lf_begin, lf_end, Kc, workers, tasks);
+    build_fused_schedule(lfs, lf_begin, lf_end, Kc, workers, p->fused_fwd, tasks);
     verify_fused_list(lfs, lf_begin, lf_end, tasks, (size_t)p->fused_t0);
     p->fused_t1 = (int)tasks.size();
     p->fused_j0 = p->lvl_large[T0].j0;
@@ -1052,6 +1131,8 @@ void upload_structures(sfx_problem* p) {
       p->n_zero_jobs = (int)zj.size();
       p->ld.zero_jobs = P.upload(zj);
     }
+    p->ld.fwd_b = P.alloc<double>(std::max<int64_t>(hp.fwd_b_size, 1));
+    p->d_f_level = up32(f.f_level);
     p->ld.lf = P.upload(lfs);
     p->ld.tasks = P.upload(tasks);
     p->pre_j0 = (int)jobs.size();
@@ -1185,7 +1266,11 @@ void enqueue_fwd_levels(sfx_problem* p, cudaStream_t st, int l0, int l1, const d
 
 // overlap_T > 0: begins the triangular solves too -- the forward substitution of the levels below overlap_T runs on
 // the side stream while the levels from overlap_T up factor (with one CTA per SM); joined before returning
-void enqueue_factorize(sfx_problem* p, int overlap_T = 0, const double* rhs_static = nullptr, int use_state_rhs = 0) {
+// with_fwd: the forward substitution of (rhs_static | the state right-hand side) is part of this call -- levels below
+// the fused top by their own kernels, the fused fronts by tasks of the factor kernel; returns true when it was, and
+// enqueue_tri_solves must then be told that every level is done (fwd_done_below = n_levels)
+bool enqueue_factorize(sfx_problem* p, int overlap_T = 0, const double* rhs_static = nullptr, int use_state_rhs = 0,
+                       bool with_fwd = false) {
   Analysis& a = p->a;
   const FrontPlan& f = a.fp;
   const double* sys = a.schur ? p->sd.S : nullptr;
@@ -1200,9 +1285,16 @@ void enqueue_factorize(sfx_problem* p, int overlap_T = 0, const double* rhs_stat
                            p->damp_j1);
   for (int l = 0; l < f.n_levels; ++l) {
     if (l == p->fused_T0) {
+      const bool fwd = with_fwd && p->fused_fwd;
+      if (fwd) {
+        begin_tri_solves(p);
+        enqueue_fwd_levels(p, p->st, 0, l, rhs_static, use_state_rhs);
+        launch_large_fwd_init(p->st, p->d_ctrl, p->fd, p->ld, p->lvl_large[l].lf0, p->n_large_fronts - p->lvl_large[l].lf0, l,
+                              p->d_f_level, rhs_static, p->sp, use_state_rhs);
+      }
       launch_large_fused(p->st, p->d_ctrl, p->fd, p->ld, p->fused_t0, p->fused_t1, p->fused_j0, p->fused_j1, l, sys, p->sp,
-                         use_H, dv);
-      break;
+                         use_H, dv, fwd ? 1 : 0);
+      return fwd;
     }
     if (overlap_T > 0 && l == overlap_T) {
       begin_tri_solves(p);
@@ -1218,6 +1310,7 @@ void enqueue_factorize(sfx_problem* p, int overlap_T = 0, const double* rhs_stat
                        (overlap_T > 0 && l >= overlap_T) ? 148 : 0);
   }
   if (overlap_T > 0) CUDA_OK(cudaStreamWaitEvent(p->st, p->ev_join2, 0));
+  return false;
 }
 
 // forward + backward substitution with the current factor; rhs in system scalar order (rhs_static, or
@@ -1260,9 +1353,9 @@ void enqueue_solve(sfx_problem* p, const std::function<void(int)>& mark) {
   }
   (void)f;
   const int T = chain_top_level(p);
-  enqueue_factorize(p, T, a.schur ? p->sd.rhs_red : nullptr, a.schur ? 0 : 1);
+  const bool fwd_done = enqueue_factorize(p, T, a.schur ? p->sd.rhs_red : nullptr, a.schur ? 0 : 1, /*with_fwd=*/true);
   mark(PH_FACTOR);
-  enqueue_tri_solves(p, a.schur ? p->sd.rhs_red : nullptr, a.schur ? 0 : 1, T);
+  enqueue_tri_solves(p, a.schur ? p->sd.rhs_red : nullptr, a.schur ? 0 : 1, fwd_done ? a.fp.n_levels : T);
   if (a.schur) {
     launch_unpermute(p->st, p->d_ctrl, p->fd, p->d_y, 1.0);
     if (mg) NCCL_OK(nccl().Broadcast(p->d_y, p->d_y, (size_t)a.sp.reduced_dim, ncclDouble, 0, p->comm->comm, p->st));

@@ -878,6 +878,16 @@ class Factor {
         throw std::runtime_error("SYM_ASSERT: keys_to_optimize must be the linearized arguments, in argument order");
     return f;
   }
+  // Factor::Jacobian(func, keys_to_func, keys_to_optimize) (factor.h:195-196): the reference evaluates residual and
+  // Jacobian with `func` and forms H = J^T J, rhs = J^T r itself (factor.tcc:24-81).  The device kinds do exactly
+  // that -- their kernels compute (residual, J) and accumulate J^T J / J^T r -- so a generated function with a device
+  // implementation lowers to the same kind whether it is handed to Hessian() or to Jacobian().  Host functors
+  // (lambdas, std::function) have no device implementation and are rejected like in Hessian(): no CPU fallback.
+  template <typename Functor>
+  static Factor Jacobian(Functor&& func, const std::vector<Key>& keys_to_func,
+                         const std::vector<Key>& keys_to_optimize = {}) {
+    return Hessian(std::forward<Functor>(func), keys_to_func, keys_to_optimize, /*requires_jacobian=*/true);
+  }
   const std::vector<Key>& AllKeys() const { return keys_; }
   const std::vector<Key>& OptimizedKeys() const { return keys_to_optimize_; }
   int Kind() const { return kind_; }

@@ -77,5 +77,25 @@ int main() {
   }
   d.RemoveAll();
   std::printf("misc %d %d\n", (int)threw, (int)d.Empty());
+
+  // Factor::Jacobian (factor.h:195-196) lowers a generated function onto the same device kind as Factor::Hessian;
+  // keys_to_optimize defaults to the linearized arguments; host functors are rejected (no CPU fallback)
+  const std::vector<sym::Key> bkeys = {{'P', 0}, {'P', 1}, {'T', 0}, {'I', 0}, 'e'};
+  const sym::Factord fj = sym::Factord::Jacobian(sym::BetweenFactorPose3<double>, bkeys);
+  const sym::Factord fh = sym::Factord::Hessian(sym::BetweenFactorPose3<double>, bkeys, {{'P', 0}, {'P', 1}});
+  bool lambda_rejected = false;
+  try {
+    (void)sym::Factord::Jacobian([](double, double*, double*) {}, {'s'});
+  } catch (const std::runtime_error&) {
+    lambda_rejected = true;
+  }
+  bool wrong_keys_rejected = false;
+  try {
+    (void)sym::Factord::Jacobian(sym::BetweenFactorPose3<double>, bkeys, {{'P', 1}, {'P', 0}});
+  } catch (const std::runtime_error&) {
+    wrong_keys_rejected = true;
+  }
+  std::printf("factor_jacobian %d %d %zu %zu %d %d\n", (int)(fj.Kind() == fh.Kind()), (int)(fj.OptimizedKeys() == fh.OptimizedKeys()),
+              fj.AllKeys().size(), fj.OptimizedKeys().size(), (int)lambda_rejected, (int)wrong_keys_rejected);
   return 0;
 }

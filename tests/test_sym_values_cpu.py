@@ -61,3 +61,6 @@ def test_values_api_against_geo(tmp_path):
     assert np.allclose(_f(rec, "update_or_set"), np.concatenate([v[:7], v[11:14], [-1.0], w[7:11]]), **tol)
     assert rec["entry"] == ["1"] and _f(rec, "at_entry").tolist() == [1.0, -1.0, 0.5]
     assert rec["set_entry"] == ["7"] and rec["misc"] == ["1", "1"]
+    # Factor::Jacobian: same kind and optimized keys as Factor::Hessian, 5 keys / 2 optimized, lambdas and reordered
+    # keys_to_optimize rejected
+    assert rec["factor_jacobian"] == ["1", "1", "5", "2", "1", "1"]

@@ -530,6 +530,11 @@ __global__ void __launch_bounds__(kLargeThreads, 2) large_factor_kernel(Ctrl* ct
   __shared__ double s_binv[512];  // inverses of the eight 8x8 diagonal blocks of the current L_kk
   if (ctrl->done) return;
   const int tid = threadIdx.x;
+  // the trace pointer is read once: a __device__ variable is a global load, and the acquire polls of this kernel keep
+  // invalidating L1, so `if (g_trace ...)` at every stamp cost three or four L2 round trips per task
+  unsigned long long* const trace = g_trace;
+  int cur_lf = -1;
+  LargeFront lf_cache{};
   for (;;) {
     if (tid == 0) s_task = t0 + atomicAdd(&ld.queue[level], 1);
     __syncthreads();
@@ -537,12 +542,16 @@ __global__ void __launch_bounds__(kLargeThreads, 2) large_factor_kernel(Ctrl* ct
     __syncthreads();
     if (t >= t1) break;
     const LargeTask task = ld.tasks[t];
-    const LargeFront lf = ld.lf[task.lf];
+    if (task.lf != cur_lf) {  // consecutive tasks of a CTA often belong to the same front
+      lf_cache = ld.lf[task.lf];
+      cur_lf = task.lf;
+    }
+    const LargeFront& lf = lf_cache;
     double* F = fd.fronts + lf.off;
     const int m = lf.m, nt = lf.nt;
     int* cnt = ld.counters + lf.cnt_off;
     const int k = task.k, i = task.i, j = task.j;
-    if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 0] = gtime();
+    if (trace && tid == 0) trace[(size_t)t * 4 + 0] = gtime();
     if (task.type == 3) {
       // ---------------- DIAG(k): POTRF(k), then TRSM(k+1,k) and UPDATE(k+1,k+1,k) on the critical path
       __shared__ int s_pre;
@@ -553,13 +562,13 @@ __global__ void __launch_bounds__(kLargeThreads, 2) large_factor_kernel(Ctrl* ct
       if (k == 0 && lf.n_ea > 0) wait_ge(ld.counters + lf.asm_off, lf.n_ea);
       if (tid == 0) s_pre = (k + 1 < nt) && ld_acquire(cnt + (k + 1) * nt + k) == k;
       wait_eq(cnt + k * nt + k, k);
-      if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 1] = gtime();
+      if (trace && tid == 0) trace[(size_t)t * 4 + 1] = gtime();
       const int s0 = tile_start(lf, k), nb = tile_size(lf, k);
       const bool pre = s_pre != 0;
       load_tile(As, F + s0 + (size_t)s0 * m, m, nb, nb, true);
       if (pre) load_tile(Bs, F + tile_start(lf, k + 1) + (size_t)s0 * m, m, tile_size(lf, k + 1), nb, false);
       __syncthreads();
-      if (g_trace && tid == 0 && k < 512) g_diag_stamps[k * 8 + 0] = gtime();
+      if (trace && tid == 0 && k < 512) g_diag_stamps[k * 8 + 0] = gtime();
       potrf_64_v2(As, s_binv, &ctrl->chol_fail);
       __syncthreads();
       // first non-positive pivot tile of the factorization: (large front + 1) << 16 | pivot tile, for diagnostics
@@ -568,7 +577,7 @@ __global__ void __launch_bounds__(kLargeThreads, 2) large_factor_kernel(Ctrl* ct
         for (int q = 0; q < nb; ++q) nanp = nanp || !(As[q + q * kLd] > 0.0);
         if (nanp) atomicCAS(&ctrl->fail_where, 0, ((task.lf + 1) << 16) | k);
       }
-      if (g_trace && tid == 0 && k < 512) g_diag_stamps[k * 8 + 1] = gtime();
+      if (trace && tid == 0 && k < 512) g_diag_stamps[k * 8 + 1] = gtime();
       {
         const int r = tid & 63;
         for (int c = tid >> 6; c < kT; c += kLargeThreads / 64)
@@ -577,8 +586,8 @@ __global__ void __launch_bounds__(kLargeThreads, 2) large_factor_kernel(Ctrl* ct
         binv_g[tid + 256] = s_binv[tid + 256];
       }
       publish(cnt + k * nt + k, k + 1);
-      if (g_trace && tid == 0 && k < 512) g_diag_stamps[k * 8 + 2] = gtime();
-      if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 3] = gtime();  // POTRF published
+      if (trace && tid == 0 && k < 512) g_diag_stamps[k * 8 + 2] = gtime();
+      if (trace && tid == 0) trace[(size_t)t * 4 + 3] = gtime();  // POTRF published
       if (k + 1 < nt) {
         // TRSM(k+1, k) against L_kk still in shared memory; result to the front and to Bs for the SYRK
         const int ri = tile_start(lf, k + 1), ni = tile_size(lf, k + 1);
@@ -597,17 +606,17 @@ __global__ void __launch_bounds__(kLargeThreads, 2) large_factor_kernel(Ctrl* ct
         trsm_frag_64(xf, As, s_binv);
         store_frag(xf, F + ri + (size_t)s0 * m, m, ni, nb, Bs);
         publish(cnt + (k + 1) * nt + k, k + 1);
-        if (g_trace && tid == 0 && k < 512) g_diag_stamps[k * 8 + 3] = gtime();
+        if (trace && tid == 0 && k < 512) g_diag_stamps[k * 8 + 3] = gtime();
         // UPDATE(k+1, k+1, k)
         wait_eq(cnt + (k + 1) * nt + (k + 1), k);
         gemm_store(F, m, lf, k + 1, k + 1, Bs, Bs, false, nullptr);
         publish(cnt + (k + 1) * nt + (k + 1), k + 1);
       }
-      if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 2] = gtime();
+      if (trace && tid == 0) trace[(size_t)t * 4 + 2] = gtime();
     } else if (task.type == 5) {
       // ---------------- INV(k): L_kk^-1 for the triangular solves (off the critical path) ----------------
       wait_ge(cnt + k * nt + k, k + 1);
-      if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 1] = gtime();
+      if (trace && tid == 0) trace[(size_t)t * 4 + 1] = gtime();
       const int s0 = tile_start(lf, k), nb = tile_size(lf, k);
       load_L(As, F, m, s0, nb);
       __syncthreads();
@@ -621,12 +630,12 @@ __global__ void __launch_bounds__(kLargeThreads, 2) large_factor_kernel(Ctrl* ct
         publish(ld.counters + lf.vc_off + nt + lf.wt + k, 1);  // L_kk^-1 ready for the fused forward substitution
       else
         __syncthreads();
-      if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 2] = gtime();
+      if (trace && tid == 0) trace[(size_t)t * 4 + 2] = gtime();
     } else if (task.type == 6) {
       // ---------------- EXTEND-ADD: update tile (i,j) of this (final) front -> its parent front ----------------
       const int wt = lf.wt;
       wait_ge(cnt + i * nt + j, wt);
-      if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 1] = gtime();
+      if (trace && tid == 0) trace[(size_t)t * 4 + 1] = gtime();
       const LargeFront pf = ld.lf[lf.parent_lf];
       double* Fp = fd.fronts + pf.off;
       const int mp = pf.m;
@@ -655,7 +664,7 @@ __global__ void __launch_bounds__(kLargeThreads, 2) large_factor_kernel(Ctrl* ct
         __threadfence();
         atomicAdd(ld.counters + pf.asm_off, 1);
       }
-      if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 2] = gtime();
+      if (trace && tid == 0) trace[(size_t)t * 4 + 2] = gtime();
     } else if (task.type >= 8) {
       // ---------------- fused forward substitution L y = b (fd.ywork gets y, pivot rows in elimination order) -----
       // 8: y_k = L_kk^-1 b_k     9: b_i -= L(i,k) y_k     10: update rows of b -> the parent's b
@@ -673,7 +682,7 @@ __global__ void __launch_bounds__(kLargeThreads, 2) large_factor_kernel(Ctrl* ct
           while (ld_acquire(vc + nt + wt + k) < 1) __nanosleep(32);
         }
         __syncthreads();
-        if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 1] = gtime();
+        if (trace && tid == 0) trace[(size_t)t * 4 + 1] = gtime();
         const int s0 = tile_start(lf, k), nb = tile_size(lf, k);
         if (tid < kT) xs[tid] = tid < nb ? __ldcg(b + s0 + tid) : 0.0;
         const double* linv = ld.linv + lf.linv_off + (size_t)k * kT * kT;
@@ -695,7 +704,7 @@ __global__ void __launch_bounds__(kLargeThreads, 2) large_factor_kernel(Ctrl* ct
           while (ld_acquire(cnt + i * nt + k) < k + 1) __nanosleep(32);
         }
         __syncthreads();
-        if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 1] = gtime();
+        if (trace && tid == 0) trace[(size_t)t * 4 + 1] = gtime();
         const int s0 = tile_start(lf, k), nk = tile_size(lf, k);
         const int ri = tile_start(lf, i), ni = tile_size(lf, i);
         if (tid < kT) xs[tid] = tid < nk ? __ldcg(fd.ywork + fd.f_piv[lf.front] + s0 + tid) : 0.0;
@@ -726,7 +735,7 @@ __global__ void __launch_bounds__(kLargeThreads, 2) large_factor_kernel(Ctrl* ct
             while (ld_acquire(vc + q) < wt) __nanosleep(32);
         }
         __syncthreads();
-        if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 1] = gtime();
+        if (trace && tid == 0) trace[(size_t)t * 4 + 1] = gtime();
         const LargeFront pf = ld.lf[lf.parent_lf];
         double* pb = ld.fwd_b + pf.fb_off;
         const int32_t* rel = fd.f_rel + fd.f_rows_ptr[lf.front];
@@ -737,7 +746,7 @@ __global__ void __launch_bounds__(kLargeThreads, 2) large_factor_kernel(Ctrl* ct
           atomicAdd(ld.counters + pf.vc_off + pf.nt + 2 * pf.wt, 1);
         }
       }
-      if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 2] = gtime();
+      if (trace && tid == 0) trace[(size_t)t * 4 + 2] = gtime();
     } else if (task.type == 1) {
       // ---------------- TRSM(i,k): strip-per-warp substitution in registers ----------------
       if (tid == 0) {
@@ -745,7 +754,7 @@ __global__ void __launch_bounds__(kLargeThreads, 2) large_factor_kernel(Ctrl* ct
         while (ld_acquire(cnt + i * nt + k) != k) __nanosleep(32);
       }
       __syncthreads();
-          if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 1] = gtime();
+          if (trace && tid == 0) trace[(size_t)t * 4 + 1] = gtime();
       const int s0 = tile_start(lf, k), nb = tile_size(lf, k);
       const int ri = tile_start(lf, i), ni = tile_size(lf, i);
       double xf[8][2];
@@ -760,7 +769,7 @@ __global__ void __launch_bounds__(kLargeThreads, 2) large_factor_kernel(Ctrl* ct
       trsm_frag_64(xf, As, s_binv);
       store_frag(xf, F + ri + (size_t)s0 * m, m, ni, nb, nullptr);
       publish(cnt + i * nt + k, k + 1);
-      if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 2] = gtime();
+      if (trace && tid == 0) trace[(size_t)t * 4 + 2] = gtime();
     } else if (task.type == 4) {
       // ---------------- UPDATE(i, j, [k, k1)) ----------------
       const int k1 = task.k1;
@@ -797,7 +806,7 @@ __global__ void __launch_bounds__(kLargeThreads, 2) large_factor_kernel(Ctrl* ct
         load_half(rb_, F, m, lf, j, kk, (h & 1) * kHalf);
       };
       fetch(0);
-      if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 1] = gtime();
+      if (trace && tid == 0) trace[(size_t)t * 4 + 1] = gtime();
       store_half(sm, ra);
       store_half(sm + kHalfDoubles, rb_);
       __syncthreads();
@@ -845,7 +854,7 @@ __global__ void __launch_bounds__(kLargeThreads, 2) large_factor_kernel(Ctrl* ct
             }
       }
       publish(cnt + i * nt + j, k1);
-      if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 2] = gtime();
+      if (trace && tid == 0) trace[(size_t)t * 4 + 2] = gtime();
     } else {
       // ---------------- UPDATE(i,j,k) ----------------
       const bool trsm = false;
@@ -860,7 +869,7 @@ __global__ void __launch_bounds__(kLargeThreads, 2) large_factor_kernel(Ctrl* ct
         }
       }
       __syncthreads();
-          if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 1] = gtime();
+          if (trace && tid == 0) trace[(size_t)t * 4 + 1] = gtime();
       const int ck = tile_start(lf, k), nk = tile_size(lf, k);
       load_tile(As, F + tile_start(lf, i) + (size_t)ck * m, m, tile_size(lf, i), nk, false);
       if (trsm)
@@ -870,7 +879,7 @@ __global__ void __launch_bounds__(kLargeThreads, 2) large_factor_kernel(Ctrl* ct
       __syncthreads();
       gemm_store(F, m, lf, i, trsm ? k : j, As, Bs, trsm, nullptr);
       publish(cnt + i * nt + (trsm ? k : j), k + 1);
-      if (g_trace && tid == 0) g_trace[(size_t)t * 4 + 2] = gtime();
+      if (trace && tid == 0) trace[(size_t)t * 4 + 2] = gtime();
     }
   }
 }

@@ -137,6 +137,7 @@ struct sfx_problem {
   cudaStream_t st = nullptr;
   cudaStream_t st2 = nullptr;  // side stream: front zeroing overlaps damping + Schur
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fork2 = nullptr, ev_join2 = nullptr;
+  int sm_count = 148;  // multiprocessors of the device (cudaDevAttrMultiProcessorCount at create)
   int fused_T0 = -1;  // first level of the fused top of the elimination tree (-1: none)
   int fused_t0 = 0, fused_t1 = 0, fused_j0 = 0, fused_j1 = 0;
   bool fused_fwd = false;       // the forward substitution of the fused fronts rides inside the factor kernel
@@ -779,7 +780,12 @@ void plan_large_fronts(sfx_problem* p, int workers, LargeHostPlan& hp) {
     }
     lv.t1 = (int)tasks.size();
     lv.j1 = (int)jobs.size();
-    lv.solve_p = lv.n_lf > 0 ? std::max(1, std::min(lv.max_nt, 144 / lv.n_lf)) : 1;
+    // cooperative solves: P CTAs per front, one CTA per SM (their spin-waits need every CTA of a launch resident);
+    // the SM count comes from the device, a few SMs are left free
+    lv.solve_p = lv.n_lf > 0 ? std::max(1, std::min(lv.max_nt, std::max(1, p->sm_count - 4) / lv.n_lf)) : 1;
+    // (P == 1: a front's only CTA waits for nobody, so levels with more fronts than SMs are fine)
+    SFX_CHECK(lv.solve_p == 1 || lv.n_lf * lv.solve_p <= std::max(1, p->sm_count), SFX_ERR_UNSUPPORTED,
+              "internal: cooperative solve grid exceeds the SM count");
   }
   if (T0 < f.n_levels) {
     // fused top: parents, extend-add counts and assembly counters, then the list schedule
@@ -1307,7 +1313,7 @@ bool enqueue_factorize(sfx_problem* p, int overlap_T = 0, const double* rhs_stat
       launch_front_factor(p->st, p->d_ctrl, p->fd, sys, p->sp, use_H, dv, f.level_ptr[l], p->lvl_small_cnt[l],
                           p->lvl_max_m[l]);
     launch_large_level(p->st, p->d_ctrl, p->fd, p->ld, p->lvl_large[l], l, sys, p->sp, use_H, dv,
-                       (overlap_T > 0 && l >= overlap_T) ? 148 : 0);
+                       (overlap_T > 0 && l >= overlap_T) ? p->sm_count : 0);
   }
   if (overlap_T > 0) CUDA_OK(cudaStreamWaitEvent(p->st, p->ev_join2, 0));
   return false;
@@ -1485,6 +1491,7 @@ sfx_status sfx_problem_create(const sfx_problem_desc* desc, sfx_problem** out) {
   std::unique_ptr<sfx_problem> up(new sfx_problem());
   p = up.get();
   p->device = desc->device;
+  CUDA_OK(cudaDeviceGetAttribute(&p->sm_count, cudaDevAttrMultiProcessorCount, desc->device));
   validate_params(desc->params);
   p->params = desc->params;
   p->epsilon = desc->epsilon;

@@ -43,7 +43,7 @@ def _replay(shape):
     return gold, st, its, best
 
 
-def _compare(gold, st, its, best):
+def _compare(gold, st, its, best, cost_tol=COST_TOL, values_tol=1e-5):
     assert st.status == gold["status"], (st.status, gold["status"])
     assert len(its) == gold["n_records"], (len(its), gold["n_records"])  # same iteration count
     assert st.best_index == gold["best_index"]
@@ -59,17 +59,17 @@ def _compare(gold, st, its, best):
         assert r.update_accepted == g["update_accepted"], (r.iteration, "accept/reject differs")
         rel = abs(r.new_error - g["new_error"]) / abs(g["new_error"])
         worst = max(worst, rel)
-        assert rel <= COST_TOL, (r.iteration, r.new_error, g["new_error"], rel)
+        assert rel <= cost_tol, (r.iteration, r.new_error, g["new_error"], rel)
         assert abs(r.current_lambda - g["current_lambda"]) <= lam_tol * abs(g["current_lambda"]), (
             r.iteration, r.current_lambda, g["current_lambda"], lam_tol)
     final = its[st.best_index].new_error
-    assert abs(final - gold["final_error"]) <= COST_TOL * abs(gold["final_error"]), (final, gold["final_error"])
+    assert abs(final - gold["final_error"]) <= cost_tol * abs(gold["final_error"]), (final, gold["final_error"])
     fp = gold["best_values"]
     idx = np.array(fp["sample_idx"])
     want = np.array(fp["sample"])
     assert best.shape[0] == fp["n"]
     # best values: the optimum is flat along the gauge directions, so storage agrees less tightly than the cost
-    assert np.max(np.abs(best[idx] - want)) <= 1e-5 * max(1.0, np.max(np.abs(want)))
+    assert np.max(np.abs(best[idx] - want)) <= values_tol * max(1.0, np.max(np.abs(want)))
     assert abs(np.linalg.norm(best) - fp["l2"]) <= 1e-7 * fp["l2"]
     return worst
 
@@ -86,6 +86,24 @@ def test_final_shape_history_matches_the_oracle_fixture():
     gold, st, its, best = _replay("final")
     worst = _compare(gold, st, its, best)
     print(f"final: {len(its) - 1} iterations, worst relative error deviation {worst:.2e}")
+
+
+def test_pose_graph_100k_history_matches_the_oracle_fixture():
+    """BASELINE.json configs[4] (SparseCholeskySolver path, 1 GPU): the first 10 LM iterations of the 100k-pose graph
+    -- two of them rejected -- against the oracle fixture.  The costs fall from 4.6e11 to 3.2e8 through steps with large
+    rotations; iteration costs agree to 1e-7 relative (measured ~1e-9), the tolerance round 1 established for this path."""
+    path = os.path.join(ROOT, "tests", "golden", "pose_graph_100k_history.json")
+    gold = json.load(open(path))
+    params = D.default_params()
+    params.iterations = gold["params"]["iterations"]
+    prob = P.pose_graph_problem(gold["shape"]["n_poses"], gold["shape"]["n_loops"], params=params)
+    gpu = capi.SfxProblem(prob, device=0)
+    st = gpu.optimize()
+    its = gpu.iterations()
+    best = gpu.best_values()
+    gpu.close()
+    worst = _compare(gold, st, its, best, cost_tol=1e-7, values_tol=1e-4)
+    print(f"pose graph: {len(its) - 1} iterations, worst relative error deviation {worst:.2e}")
 
 
 def _n_gpus():

@@ -13,6 +13,15 @@ pytestmark = pytest.mark.gpu
 
 H_TOL = 1e-9
 COST_TOL = 1e-8
+# north star: the LM step within 1e-9 relative (measured on the B200: see the table in test_lm_step_matches_oracle)
+STEP_TOL_DEFAULT = 1e-9
+# Measured (B200, round 2): 2e-16 .. 5e-14 on the pose / rotation / robot3d / config-A problems, 2e-12 .. 1.3e-11 on BAL at
+# lambda = 1, 3e-13 with diagonal damping.  BAL with UNIT damping at lambda = 1e-3 is the exception: the gauge freedom
+# leaves seven eigenvalues of H at lambda, cond(H + lambda I) ~ 1e12, so any backward-stable solve carries ~cond * eps
+# = 1e-4 of relative error in the step; the two implementations (LL^T on METIS fronts vs up-looking LDL^T) still agree
+# to 4.2e-10 .. 4.4e-9.  Those cases are held to 1e-8; everything else to the north star's 1e-9.
+STEP_TOL = {(n, 1e-3): 1e-8 for n in ("bal_tiny_schur", "bal_small_schur", "bal_small_chol", "bal_small_natural",
+                                      "bal_small_block", "bal_ladybug")}
 
 
 def _ordering(p, o):
@@ -90,9 +99,11 @@ def test_lm_step_matches_oracle(solved, name, lam):
     upd_g = gpu.solve_step(lam)
     upd_c = cpu.solve_step(lam)
     assert np.all(np.isfinite(upd_g))
+    e = relerr(upd_g, upd_c)
+    print(f"LMSTEP {name} lam={lam:g} relerr={e:.2e}")
     # steps are compared against the step's scale (ill-conditioned problems lose digits in both
     # implementations, which solve with different orderings / LL^T vs LDL^T)
-    assert relerr(upd_g, upd_c) < 1e-7 if name.startswith("pose_graph") else relerr(upd_g, upd_c) < 1e-8
+    assert e < STEP_TOL.get((name, lam), STEP_TOL_DEFAULT), e
 
 
 @pytest.mark.parametrize("name", list(PROBLEMS))

@@ -39,10 +39,23 @@ def main():
     shape = sys.argv[1] if len(sys.argv) > 1 else "final"
     iters = int(sys.argv[2]) if len(sys.argv) > 2 else 50
     params = D.default_params()
-    params.lambda_update_type = D.LAMBDA_DYNAMIC
     params.iterations = iters
     t0 = time.time()
+    if shape == "pose_graph":
+        # BASELINE.json configs[4]: 100k Pose3 poses + 20k loop closures, DefaultOptimizerParams (STATIC lambda)
+        prob = P.pose_graph_problem(100000, 20000, params=params)
+        return run(prob, "pose_graph_100k", {"n_poses": 100000, "n_loops": 20000}, {"seed": 0x51A4},
+                   {"lambda_update_type": "STATIC", "iterations": iters, "rest": "DefaultOptimizerParams (optimizer.cc:8-56)"}, t0)
+    params.lambda_update_type = D.LAMBDA_DYNAMIC
     prob = P.bal_problem(shape, solver=D.SOLVER_SCHUR, params=params)
+    s = P.BAL_SHAPES[shape]
+    return run(prob, f"{shape}_shape", {k: s[k] for k in ("n_cams", "n_pts", "n_obs", "window")},
+               {"structure": 0xBA1, "noise": 0xBA2},
+               {"lambda_update_type": "DYNAMIC", "iterations": iters, "rest": "DefaultOptimizerParams (optimizer.cc:8-56)"}, t0)
+
+
+def run(prob, name, shape_desc, seeds, params_desc, t0):
+    shape = name
     print(f"problem built in {time.time() - t0:.1f} s", flush=True)
     t0 = time.time()
     o = O.OracleProblem(prob)
@@ -53,13 +66,12 @@ def main():
     its = o.iterations()
     tm = o.timings()
     best = o.best_values()
-    s = P.BAL_SHAPES[shape]
     out = {
         "generator": "tools/gen_bal_golden.py " + shape,
         "oracle": "oracle/oracle.cc (CPU restatement of levenberg_marquardt_solver.tcc:139-343 + SparseSchurSolver + LDLT)",
-        "shape": {k: s[k] for k in ("n_cams", "n_pts", "n_obs", "window")},
-        "seeds": {"structure": 0xBA1, "noise": 0xBA2},
-        "params": {"lambda_update_type": "DYNAMIC", "iterations": iters, "rest": "DefaultOptimizerParams (optimizer.cc:8-56)"},
+        "shape": shape_desc,
+        "seeds": seeds,
+        "params": params_desc,
         "status": int(st.status), "failure_reason": int(st.failure_reason), "best_index": int(st.best_index),
         "n_records": len(its),
         "records": [{"iteration": int(r.iteration), "current_lambda": float(r.current_lambda),
@@ -70,7 +82,7 @@ def main():
         "oracle_wall_s": wall,
         "oracle_timings": tm,
     }
-    path = os.path.join(ROOT, "tests", "golden", f"{shape}_shape_history.json")
+    path = os.path.join(ROOT, "tests", "golden", f"{name}_history.json")
     with open(path, "w") as f:
         json.dump(out, f)
     print(f"wrote {path}: {len(its)} records, status {st.status}, best {st.best_index}, final error "

@@ -14,6 +14,9 @@ pytestmark = pytest.mark.gpu
 H_TOL = 1e-9
 COST_TOL = 1e-8
 # north star: the LM step within 1e-9 relative (measured on the B200: see the table in test_lm_step_matches_oracle)
+# per-iteration cost and lambda: measured worst deviations over the 14 problems (B200, round 2) are 5e-13 for the cost
+# (4e-10 on frozen_keys, whose costs fall below 1e-15 absolute) and 7e-12 for lambda; both are held to 1e-9
+ITER_COST_TOL = 1e-9
 STEP_TOL_DEFAULT = 1e-9
 # Measured (B200, round 2): 2e-16 .. 5e-14 on the pose / rotation / robot3d / config-A problems, 2e-12 .. 1.3e-11 on BAL at
 # lambda = 1, 3e-13 with diagonal damping.  BAL with UNIT damping at lambda = 1e-3 is the exception: the gauge freedom
@@ -117,11 +120,16 @@ def test_optimize_matches_oracle(solved, name):
     assert st_g.failure_reason == st_c.failure_reason
     assert len(it_g) == len(it_c), (len(it_g), len(it_c))
     assert st_g.best_index == st_c.best_index
+    worst_e = worst_l = 0.0
     for a, b in zip(it_g, it_c):
         assert a.iteration == b.iteration
         assert a.update_accepted == b.update_accepted
-        assert a.new_error == pytest.approx(b.new_error, rel=1e-6, abs=1e-14)
-        assert a.current_lambda == pytest.approx(b.current_lambda, rel=1e-6)
+        worst_e = max(worst_e, abs(a.new_error - b.new_error) / max(abs(b.new_error), 1e-14))
+        worst_l = max(worst_l, abs(a.current_lambda - b.current_lambda) / abs(b.current_lambda))
+    print(f"LMHIST {name} records={len(it_g)} worst_rel_error={worst_e:.2e} worst_rel_lambda={worst_l:.2e}")
+    for a, b in zip(it_g, it_c):
+        assert a.new_error == pytest.approx(b.new_error, rel=ITER_COST_TOL, abs=1e-14)
+        assert a.current_lambda == pytest.approx(b.current_lambda, rel=1e-9)
     e_g, e_c = it_g[st_g.best_index].new_error, it_c[st_c.best_index].new_error
     assert e_g == pytest.approx(e_c, rel=COST_TOL, abs=1e-15)
     vg, vc = gpu.best_values(), cpu.best_values()

@@ -663,19 +663,25 @@ void plan_large_fronts(sfx_problem* p, int workers, LargeHostPlan& hp) {
   std::vector<LargeTask>& tasks = hp.tasks;
   std::vector<LargeJob>&jobs = hp.jobs, &pre_jobs = hp.pre_jobs, &damp_jobs = hp.damp_jobs;
   int64_t &linv_off = hp.linv_off, &cnt_off = hp.cnt_off, &flag_off = hp.flag_off, &contrib_off = hp.contrib_off;
-  auto is_small = [&](int s) { return f.f_w[s] + f.f_u[s] <= p->small_max_m; };
-  // first level of the fused top: no small fronts from there up (see build_fused_schedule)
+  auto fits_small = [&](int s) { return f.f_w[s] + f.f_u[s] <= p->small_max_m; };
+  // First level of the fused top (see build_fused_schedule).  Every front from there up runs as a tile-DAG front, also
+  // the few that would fit the one-CTA-per-front kernel: a one-tile front costs ~45 us of CTA time there, so a budget
+  // of them is cheaper than the five launches per level they would otherwise keep alive (the 100 k pose graph: levels
+  // 3-17 fused with 567 such fronts instead of levels 8-17).
   int T0 = f.n_levels;
   if (!getenv("SFX_NO_FUSE")) {
+    int budget = getenv("SFX_FUSE_SMALL_BUDGET") ? atoi(getenv("SFX_FUSE_SMALL_BUDGET")) : 600;
     while (T0 > 0) {
-      bool all_large = true;
-      for (int q = f.level_ptr[T0 - 1]; q < f.level_ptr[T0] && all_large; ++q) all_large = !is_small(f.level_fronts[q]);
-      if (!all_large) break;
+      int n_small = 0;
+      for (int q = f.level_ptr[T0 - 1]; q < f.level_ptr[T0]; ++q) n_small += fits_small(f.level_fronts[q]) ? 1 : 0;
+      if (n_small > budget) break;
+      budget -= n_small;
       --T0;
     }
     if (T0 >= f.n_levels - 1) T0 = f.n_levels;  // a single level gains nothing
   }
   p->fused_T0 = T0 < f.n_levels ? T0 : -1;
+  auto is_small = [&](int s) { return fits_small(s) && f.f_level[s] < T0; };
   std::vector<int> lf_of_front(f.n_fronts, -1);
   for (int l = 0; l < f.n_levels; ++l) {
     int* b = lvl_fronts.data() + f.level_ptr[l];

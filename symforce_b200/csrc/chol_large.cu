@@ -553,64 +553,84 @@ __global__ void __launch_bounds__(kLargeThreads, 2) large_factor_kernel(Ctrl* ct
     const int k = task.k, i = task.i, j = task.j;
     if (trace && tid == 0) trace[(size_t)t * 4 + 0] = gtime();
     if (task.type == 3) {
-      // ---------------- DIAG(k): POTRF(k), then TRSM(k+1,k) and UPDATE(k+1,k+1,k) on the critical path
+      // ---------------- DIAG(k): POTRF(k), then TRSM(k+1,k) and UPDATE(k+1,k+1,k) on the critical path.
+      // Sticky fronts (fused schedule): this CTA keeps the chain -- after UPDATE(k+1,k+1,k) the tile stays in shared
+      // memory and the loop goes on with POTRF(k+1): no store + fence + publish + acquire + reload between two steps.
       __shared__ int s_pre;
-      double* binv_g = ld.binv + lf.linv_off / 8 + (size_t)k * 512;
-      // tile (k+1, k) is usually ready before the diagonal tile: fetch it now (into Bs) if so
-      // fused schedule: the children's update matrices are added by EXTEND-ADD tasks of this launch; everything
-      // else in the front depends on POTRF(0), so this is the only wait on the assembly
-      if (k == 0 && lf.n_ea > 0) wait_ge(ld.counters + lf.asm_off, lf.n_ea);
-      if (tid == 0) s_pre = (k + 1 < nt) && ld_acquire(cnt + (k + 1) * nt + k) == k;
-      wait_eq(cnt + k * nt + k, k);
-      if (trace && tid == 0) trace[(size_t)t * 4 + 1] = gtime();
-      const int s0 = tile_start(lf, k), nb = tile_size(lf, k);
-      const bool pre = s_pre != 0;
-      load_tile(As, F + s0 + (size_t)s0 * m, m, nb, nb, true);
-      if (pre) load_tile(Bs, F + tile_start(lf, k + 1) + (size_t)s0 * m, m, tile_size(lf, k + 1), nb, false);
-      __syncthreads();
-      if (trace && tid == 0 && k < 512) g_diag_stamps[k * 8 + 0] = gtime();
-      potrf_64_v2(As, s_binv, &ctrl->chol_fail);
-      __syncthreads();
-      // first non-positive pivot tile of the factorization: (large front + 1) << 16 | pivot tile, for diagnostics
-      if (tid == 0 && ctrl->chol_fail && ctrl->fail_where == 0) {
-        bool nanp = false;
-        for (int q = 0; q < nb; ++q) nanp = nanp || !(As[q + q * kLd] > 0.0);
-        if (nanp) atomicCAS(&ctrl->fail_where, 0, ((task.lf + 1) << 16) | k);
-      }
-      if (trace && tid == 0 && k < 512) g_diag_stamps[k * 8 + 1] = gtime();
-      {
-        const int r = tid & 63;
-        for (int c = tid >> 6; c < kT; c += kLargeThreads / 64)
-          if (r < nb && c < nb && r >= c) F[(s0 + r) + (size_t)(s0 + c) * m] = As[r + c * kLd];
-        binv_g[tid] = s_binv[tid];
-        binv_g[tid + 256] = s_binv[tid + 256];
-      }
-      publish(cnt + k * nt + k, k + 1);
-      if (trace && tid == 0 && k < 512) g_diag_stamps[k * 8 + 2] = gtime();
-      if (trace && tid == 0) trace[(size_t)t * 4 + 3] = gtime();  // POTRF published
-      if (k + 1 < nt) {
-        // TRSM(k+1, k) against L_kk still in shared memory; result to the front and to Bs for the SYRK
-        const int ri = tile_start(lf, k + 1), ni = tile_size(lf, k + 1);
-        double xf[8][2];
-        if (pre) {
-          const int lane = tid & 31, warp = tid >> 5;
-          const int r = warp * 8 + (lane >> 2), tq = lane & 3;
-#pragma unroll
-          for (int cb = 0; cb < 8; ++cb)
-#pragma unroll
-            for (int e = 0; e < 2; ++e) xf[cb][e] = Bs[r + (cb * 8 + 2 * tq + e) * kLd];
-        } else {
-          wait_eq(cnt + (k + 1) * nt + k, k);
-          load_frag(xf, F + ri + (size_t)s0 * m, m, ni, nb);
+      const bool sticky = lf.sticky != 0;
+      bool handed = false;  // As already holds tile (kd,kd) with every update applied
+      for (int kd = k;; ++kd) {
+        double* binv_g = ld.binv + lf.linv_off / 8 + (size_t)kd * 512;
+        // fused schedule: the children's update matrices are added by EXTEND-ADD tasks of this launch; everything
+        // else in the front depends on POTRF(0), so this is the only wait on the assembly
+        if (kd == 0 && lf.n_ea > 0) wait_ge(ld.counters + lf.asm_off, lf.n_ea);
+        // tile (kd+1, kd) is usually ready before the diagonal tile: fetch it now (into Bs) if so
+        if (tid == 0) s_pre = (kd + 1 < nt) && ld_acquire(cnt + (kd + 1) * nt + kd) == kd;
+        if (!handed)
+          wait_eq(cnt + kd * nt + kd, kd);
+        else
+          __syncthreads();
+        if (trace && tid == 0 && kd == k) trace[(size_t)t * 4 + 1] = gtime();
+        const int s0 = tile_start(lf, kd), nb = tile_size(lf, kd);
+        const bool pre = s_pre != 0;
+        if (!handed) load_tile(As, F + s0 + (size_t)s0 * m, m, nb, nb, true);
+        if (pre) load_tile(Bs, F + tile_start(lf, kd + 1) + (size_t)s0 * m, m, tile_size(lf, kd + 1), nb, false);
+        __syncthreads();
+        if (trace && tid == 0 && kd < 512) g_diag_stamps[kd * 8 + 0] = gtime();
+        potrf_64_v2(As, s_binv, &ctrl->chol_fail);
+        __syncthreads();
+        // first non-positive pivot tile of the factorization: (large front + 1) << 16 | pivot tile, for diagnostics
+        if (tid == 0 && ctrl->chol_fail && ctrl->fail_where == 0) {
+          bool nanp = false;
+          for (int q = 0; q < nb; ++q) nanp = nanp || !(As[q + q * kLd] > 0.0);
+          if (nanp) atomicCAS(&ctrl->fail_where, 0, ((task.lf + 1) << 16) | kd);
         }
-        trsm_frag_64(xf, As, s_binv);
-        store_frag(xf, F + ri + (size_t)s0 * m, m, ni, nb, Bs);
-        publish(cnt + (k + 1) * nt + k, k + 1);
-        if (trace && tid == 0 && k < 512) g_diag_stamps[k * 8 + 3] = gtime();
-        // UPDATE(k+1, k+1, k)
-        wait_eq(cnt + (k + 1) * nt + (k + 1), k);
-        gemm_store(F, m, lf, k + 1, k + 1, Bs, Bs, false, nullptr);
-        publish(cnt + (k + 1) * nt + (k + 1), k + 1);
+        if (trace && tid == 0 && kd < 512) g_diag_stamps[kd * 8 + 1] = gtime();
+        {
+          const int r = tid & 63;
+          for (int c = tid >> 6; c < kT; c += kLargeThreads / 64)
+            if (r < nb && c < nb && r >= c) F[(s0 + r) + (size_t)(s0 + c) * m] = As[r + c * kLd];
+          binv_g[tid] = s_binv[tid];
+          binv_g[tid + 256] = s_binv[tid + 256];
+        }
+        publish(cnt + kd * nt + kd, kd + 1);
+        if (trace && tid == 0 && kd < 512) g_diag_stamps[kd * 8 + 2] = gtime();
+        if (trace && tid == 0 && kd == k) trace[(size_t)t * 4 + 3] = gtime();  // POTRF published
+        handed = false;
+        if (kd + 1 < nt) {
+          // TRSM(kd+1, kd) against L_kk still in shared memory; result to the front and to Bs for the SYRK
+          const int ri = tile_start(lf, kd + 1), ni = tile_size(lf, kd + 1);
+          double xf[8][2];
+          if (pre) {
+            const int lane = tid & 31, warp = tid >> 5;
+            const int r = warp * 8 + (lane >> 2), tq = lane & 3;
+#pragma unroll
+            for (int cb = 0; cb < 8; ++cb)
+#pragma unroll
+              for (int e = 0; e < 2; ++e) xf[cb][e] = Bs[r + (cb * 8 + 2 * tq + e) * kLd];
+          } else {
+            wait_eq(cnt + (kd + 1) * nt + kd, kd);
+            load_frag(xf, F + ri + (size_t)s0 * m, m, ni, nb);
+          }
+          trsm_frag_64(xf, As, s_binv);
+          store_frag(xf, F + ri + (size_t)s0 * m, m, ni, nb, Bs);
+          publish(cnt + (kd + 1) * nt + kd, kd + 1);
+          if (trace && tid == 0 && kd < 512) g_diag_stamps[kd * 8 + 3] = gtime();
+          // UPDATE(kd+1, kd+1, kd)
+          wait_eq(cnt + (kd + 1) * nt + (kd + 1), kd);
+          if (sticky && kd + 1 < lf.wt) {
+            // the updated tile goes straight into As for the next POTRF (identity padding restored); the copy in the
+            // front is written too but nobody waits for it: its next reader is this CTA
+            gemm_store(F, m, lf, kd + 1, kd + 1, Bs, Bs, false, As);
+            __syncthreads();
+            if (tid >= ni && tid < kT) As[tid + tid * kLd] = 1.0;
+            handed = true;
+          } else {
+            gemm_store(F, m, lf, kd + 1, kd + 1, Bs, Bs, false, nullptr);
+            publish(cnt + (kd + 1) * nt + (kd + 1), kd + 1);
+          }
+        }
+        if (!handed) break;
       }
       if (trace && tid == 0) trace[(size_t)t * 4 + 2] = gtime();
     } else if (task.type == 5) {

@@ -135,7 +135,8 @@ struct LargeFront {
   // [wt] L_kk^-1 ready | [1] children's update vectors added
   int fb_off, vc_off;
   int n_vch;         // fused children whose update vector is added by a VEC-EXTEND-ADD task
-  int pad2;
+  int sticky;        // fused schedule: the CTA that claims DIAG(0) runs the whole diagonal chain DIAG(0..wt-1); the
+                     // updated tile (k+1,k+1) stays in shared memory between the steps (no DIAG(k > 0) list entries)
 };
 struct LargeTask {
   int lf;

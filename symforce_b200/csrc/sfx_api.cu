@@ -344,7 +344,7 @@ void verify_task_list(const LargeFront& x, const std::vector<LargeTask>& tl) {
 struct FusedDur {
   // us, from the task trace of round 1 (profiles/r01_results.md); DIAG = POTRF | TRSM(k+1,k) | UPDATE(k+1,k+1,k)
   double potrf = 14.0, diag_trsm = 5.0, diag_syrk = 5.0, trsm = 7.7, update = 9.0, range_step = 6.0, range_fix = 2.0,
-         inv = 16.0, ea = 3.0, vsolve = 2.5, gemv = 2.5, veav = 3.0;
+         inv = 16.0, ea = 3.0, vsolve = 2.5, gemv = 2.5, veav = 3.0, sticky_gain = 5.0;
 };
 void build_fused_schedule(const std::vector<LargeFront>& lfs, int lf_begin, int lf_end, int Kc, int workers, bool with_fwd,
                           std::vector<LargeTask>& out) {
@@ -357,6 +357,8 @@ void build_fused_schedule(const std::vector<LargeFront>& lfs, int lf_begin, int 
     double dur, bl, ready;
     std::vector<Edge> succ;
     int indeg;
+    int chain = 0;  // sticky chain: 1 = DIAG(0) (takes a CTA and keeps it), 2 = DIAG(k > 0) (runs on that CTA, no list
+                    // entry), +4 = last step of the chain (its end frees the CTA)
   };
   struct Writer {
     int id = -1;
@@ -390,6 +392,10 @@ void build_fused_schedule(const std::vector<LargeFront>& lfs, int lf_begin, int 
         case 3: {
           const bool more = k + 1 < nt;
           g[id].dur = D.potrf + (more ? D.diag_trsm + D.diag_syrk : 0.0);
+          if (x.sticky) {
+            g[id].chain = (k == 0 ? 1 : 2) | (k == wt - 1 ? 4 : 0);
+            if (k > 0) g[id].dur -= D.sticky_gain;  // no store + publish + acquire + reload of tile (k,k)
+          }
           if (k == 0)
             for (int e : ea_of[li]) add_dep(Writer{e, g[e].dur}, id, 0.0);
           add_dep(Wr(k, k), id, 0.0);
@@ -492,28 +498,52 @@ void build_fused_schedule(const std::vector<LargeFront>& lfs, int lf_begin, int 
   double now = 0.0;
   out.reserve(out.size() + n);
   int started = 0;
-  while (started < n) {
-    while (!avail.empty() && avail.top().first <= now) {
-      ready.push({g[avail.top().second].bl, avail.top().second});
-      avail.pop();
+  auto start_task = [&](int id, double at) {
+    ++started;
+    for (const Edge& e : g[id].succ) {
+      g[e.to].ready = std::max(g[e.to].ready, at + e.lag);
+      if (--g[e.to].indeg == 0) avail.push({g[e.to].ready, e.to});
     }
+  };
+  std::priority_queue<Ev, std::vector<Ev>, std::greater<Ev>> chain_end;  // ends of the last steps of sticky chains
+  while (started < n) {
+    bool moved = false;
+    while (!avail.empty() && avail.top().first <= now) {
+      const int id = avail.top().second;
+      avail.pop();
+      if (g[id].chain & 2) {
+        // a later step of a sticky chain: runs on the chain's own CTA as soon as it is ready, no list entry
+        start_task(id, now);
+        if (g[id].chain & 4) chain_end.push({now + g[id].dur, id});
+        moved = true;
+      } else {
+        ready.push({g[id].bl, id});
+      }
+    }
+    while (!chain_end.empty() && chain_end.top().first <= now) {
+      chain_end.pop();
+      ++free_w;
+      moved = true;
+    }
+    if (moved) continue;
     if (free_w > 0 && !ready.empty()) {
       const int id = ready.top().second;
       ready.pop();
       out.push_back(g[id].t);
-      running.push({now + g[id].dur, id});
+      // DIAG(0) of a sticky chain keeps its CTA until the chain's last step ends (a one-step chain: like any task)
+      if ((g[id].chain & 1) && !(g[id].chain & 4))
+        ;  // the CTA is released by chain_end
+      else
+        running.push({now + g[id].dur, id});
       --free_w;
-      ++started;
-      for (const Edge& e : g[id].succ) {
-        g[e.to].ready = std::max(g[e.to].ready, now + e.lag);
-        if (--g[e.to].indeg == 0) avail.push({g[e.to].ready, e.to});
-      }
+      start_task(id, now);
       continue;
     }
     double next = 1e300;
     if (!running.empty() && free_w == 0) next = running.top().first;
     if (!avail.empty()) next = std::min(next, avail.top().first);
-    if (free_w > 0 && !running.empty() && avail.empty()) next = running.top().first;
+    if (!chain_end.empty()) next = std::min(next, chain_end.top().first);
+    if (free_w > 0 && !running.empty() && avail.empty()) next = std::min(next, running.top().first);
     if (next >= 1e300) throw Error(SFX_ERR_INVALID_ARG, "internal: fused schedule has a dependency cycle");
     // workers whose task finished by `next` become free
     now = std::max(now, next);
@@ -561,6 +591,27 @@ void verify_fused_list(const std::vector<LargeFront>& lfs, int lf_begin, int lf_
                                          std::to_string(t.lf) + " type " + std::to_string(t.type) + " k " +
                                          std::to_string(t.k) + " i " + std::to_string(t.i) + " j " + std::to_string(t.j));
   };
+  // sticky chains: DIAG(0) activates the chain; its later steps run as soon as their inputs are there (in the kernel:
+  // on the CTA that holds the chain, which spins), i.e. after whichever list task produced the last input
+  std::vector<int> chain_k(lfs.size(), -1);
+  std::vector<int> active;
+  auto advance = [&](int li) {
+    const LargeFront& x = lfs[li];
+    const int nt = x.nt;
+    auto C = [&](int i, int j) -> int& { return cnt[li][(size_t)i * nt + j]; };
+    bool any = false;
+    while (chain_k[li] >= 0 && chain_k[li] < x.wt) {
+      const int kd = chain_k[li];
+      if (kd == 0 && assembled[li] != x.n_ea) break;
+      if (C(kd, kd) != kd) break;
+      if (kd + 1 < nt && (C(kd + 1, kd) != kd || C(kd + 1, kd + 1) != kd)) break;
+      C(kd, kd) = kd + 1;
+      if (kd + 1 < nt) C(kd + 1, kd) = C(kd + 1, kd + 1) = kd + 1;
+      chain_k[li] = kd + 1;
+      any = true;
+    }
+    return any;
+  };
   for (size_t q = t_begin; q < tl.size(); ++q) {
     const LargeTask& t = tl[q];
     if (t.lf < lf_begin || t.lf >= lf_end) fail(t, "front out of range");
@@ -570,6 +621,13 @@ void verify_fused_list(const std::vector<LargeFront>& lfs, int lf_begin, int lf_
     const int k = t.k, i = t.i, j = t.j;
     switch (t.type) {
       case 3:
+        if (x.sticky) {
+          if (k != 0) fail(t, "sticky front with a DIAG(k > 0) list entry");
+          chain_k[t.lf] = 0;
+          active.push_back(t.lf);
+          if (!advance(t.lf)) fail(t, "sticky chain cannot start");
+          break;
+        }
         if (k == 0 && assembled[t.lf] != x.n_ea) fail(t, "front not assembled");
         if (C(k, k) != k) fail(t, "diag not ready");
         C(k, k) = k + 1;
@@ -622,7 +680,21 @@ void verify_fused_list(const std::vector<LargeFront>& lfs, int lf_begin, int lf_
         break;
       default: fail(t, "type");
     }
+    // chain CTAs run concurrently with the list: let every active chain take the steps that became possible
+    for (bool again = true; again;) {
+      again = false;
+      for (size_t a = 0; a < active.size(); ++a)
+        if (advance(active[a])) again = true;
+    }
+    for (size_t a = 0; a < active.size();)
+      if (chain_k[active[a]] >= lfs[active[a]].wt) {
+        active[a] = active.back();
+        active.pop_back();
+      } else {
+        ++a;
+      }
   }
+  if (!active.empty()) throw Error(SFX_ERR_INVALID_ARG, "internal: a sticky diagonal chain cannot finish");
   for (int li = lf_begin; li < lf_end; ++li) {
     const LargeFront& x = lfs[li];
     if (assembled[li] != x.n_ea) throw Error(SFX_ERR_INVALID_ARG, "internal: fused front misses extend-add tasks");
@@ -714,7 +786,7 @@ void plan_large_fronts(sfx_problem* p, int workers, LargeHostPlan& hp) {
       x.parent_lf = -1;
       x.n_ea = 0;
       x.asm_off = 0;
-      x.fb_off = x.vc_off = x.n_vch = x.pad2 = 0;
+      x.fb_off = x.vc_off = x.n_vch = x.sticky = 0;
       lf_of_front[s] = (int)lfs.size();
       flag_off += 2 * x.wt;
       contrib_off += (int64_t)x.wt * x.nt * T;
@@ -819,6 +891,16 @@ void plan_large_fronts(sfx_problem* p, int workers, LargeHostPlan& hp) {
     SFX_CHECK(fb < (int64_t)INT32_MAX, SFX_ERR_UNSUPPORTED, "fused fronts too large");
     hp.fwd_b_size = fb;
     SFX_CHECK(cnt_off < (int64_t)INT32_MAX, SFX_ERR_UNSUPPORTED, "too many tiles");
+    // sticky diagonal chains: the fronts with the longest chains, at most a quarter of the resident CTAs (a chain CTA
+    // waits for tasks that come later in the list, so enough other CTAs must stay free to claim them)
+    if (!getenv("SFX_NO_STICKY")) {
+      std::vector<int> cand;
+      for (int li = lf_begin; li < lf_end; ++li)
+        if (lfs[li].wt >= 6) cand.push_back(li);
+      std::sort(cand.begin(), cand.end(), [&](int x, int y) { return lfs[x].wt != lfs[y].wt ? lfs[x].wt > lfs[y].wt : x < y; });
+      const size_t cap = (size_t)std::max(1, workers / 4);
+      for (size_t q = 0; q < cand.size() && q < cap; ++q) lfs[cand[q]].sticky = 1;
+    }
     const int Kc = getenv("SFX_KC") ? std::max(1, atoi(getenv("SFX_KC"))) : 6;
     p->fused_t0 = (int)tasks.size();
     build_fused_schedule(lfs, lf_begin, lf_end, Kc, workers, p->fused_fwd, tasks);

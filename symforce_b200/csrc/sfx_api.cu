@@ -1036,6 +1036,7 @@ void upload_structures(sfx_problem* p) {
   }
   P.zero(p->d_maxdiag, sizeof(double) * a.N);
   p->d_ctrl = P.alloc<Ctrl>(1);
+  P.zero(p->d_ctrl, sizeof(Ctrl));  // the whole block (iteration records included) is read back after every run
   CUDA_OK(cudaMallocHost(&p->h_ctrl, sizeof(Ctrl)));
   std::memset(p->h_ctrl, 0, sizeof(Ctrl));  // entry points that come before any sfx_optimize read best_valid / n_iters
   CUDA_OK(cudaHostAlloc(&p->h_done, sizeof(int) * (kMaxIterations + 2), cudaHostAllocMapped));

@@ -1573,6 +1573,8 @@ int large_factor_resident_ctas() {
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    // the occupancy query answers 0 for this much dynamic shared memory until the kernel has been allowed to use it
+    cudaFuncSetAttribute(large_factor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kFactorSmem);
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, large_factor_kernel, kLargeThreads, kFactorSmem);
     g_resident_ctas = sms * (per_sm > 0 ? per_sm : 1);
   }

@@ -138,6 +138,8 @@ struct sfx_problem {
   cudaStream_t st2 = nullptr;  // side stream: front zeroing overlaps damping + Schur
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fork2 = nullptr, ev_join2 = nullptr;
   int sm_count = 148;  // multiprocessors of the device (cudaDevAttrMultiProcessorCount at create)
+  int plan_nd_depth = -1;  // plan chosen by choose_front_plan: -1 METIS_NodeND as the reference orders, 0 METIS_NodeND
+                           // with capped cumulative amalgamation, d >= 2 dissect to depth d + sweep
   int fused_T0 = -1;  // first level of the fused top of the elimination tree (-1: none)
   int fused_t0 = 0, fused_t1 = 0, fused_j0 = 0, fused_j1 = 0;
   bool fused_fwd = false;       // the forward substitution of the fused fronts rides inside the factor kernel
@@ -342,12 +344,15 @@ void verify_task_list(const LargeFront& x, const std::vector<LargeTask>& tl) {
 // from the task trace of round 1) simulated here once; CTAs claim tasks in that order and spin on tile versions,
 // which cannot deadlock because every dependency starts -- hence sits -- earlier in the list.
 struct FusedDur {
-  // us, from the task trace of round 1 (profiles/r01_results.md); DIAG = POTRF | TRSM(k+1,k) | UPDATE(k+1,k+1,k)
+  // us, from the task trace of round 1 (profiles/r01_results.md); DIAG = POTRF | TRSM(k+1,k) | UPDATE(k+1,k+1,k).
+  // (The round-2 trace has shorter tasks -- TRSM 6.8, UPDATE 7.9, RANGE step 5.3, INV 12.7, EXTEND-ADD 5.5 -- but the
+  // list these priorities produce with the round-2 numbers ran slower: METIS plan 4.13 vs 3.94 ms, measured.)
   double potrf = 14.0, diag_trsm = 5.0, diag_syrk = 5.0, trsm = 7.7, update = 9.0, range_step = 6.0, range_fix = 2.0,
          inv = 16.0, ea = 3.0, vsolve = 2.5, gemv = 2.5, veav = 3.0, sticky_gain = 5.0;
 };
-void build_fused_schedule(const std::vector<LargeFront>& lfs, int lf_begin, int lf_end, int Kc, int workers, bool with_fwd,
-                          std::vector<LargeTask>& out) {
+// Returns the modelled span of the launch (us).
+double build_fused_schedule(const std::vector<LargeFront>& lfs, int lf_begin, int lf_end, int Kc, int workers, bool with_fwd,
+                            std::vector<LargeTask>& out) {
   struct Edge {
     int to;
     double lag;  // the successor may start `lag` after this task started (output offset - input offset)
@@ -552,11 +557,15 @@ void build_fused_schedule(const std::vector<LargeFront>& lfs, int lf_begin, int 
       ++free_w;
     }
   }
+  while (!running.empty()) {
+    now = std::max(now, running.top().first);
+    running.pop();
+  }
+  while (!chain_end.empty()) {
+    now = std::max(now, chain_end.top().first);
+    chain_end.pop();
+  }
   if (getenv("SFX_TIMING")) {
-    while (!running.empty()) {
-      now = std::max(now, running.top().first);
-      running.pop();
-    }
     double busy[11] = {0};
     int cnt[11] = {0};
     for (int id = 0; id < n; ++id) {
@@ -569,6 +578,7 @@ void build_fused_schedule(const std::vector<LargeFront>& lfs, int lf_begin, int 
                  n, workers, now, cp, cnt[1], busy[1] / 1e3, cnt[2], busy[2] / 1e3, cnt[3], busy[3] / 1e3, cnt[4], busy[4] / 1e3,
                  cnt[5], busy[5] / 1e3, cnt[6], busy[6] / 1e3, cnt[8] + cnt[9] + cnt[10], (busy[8] + busy[9] + busy[10]) / 1e3);
   }
+  return now;
 }
 
 // Replays a fused list against the tile version counters and the assembly counters: every wait condition of
@@ -719,6 +729,7 @@ struct LargeHostPlan {
   std::vector<LargeTask> tasks;
   std::vector<LargeJob> jobs, pre_jobs, damp_jobs;
   int64_t linv_off = 0, cnt_off = 0, flag_off = 0, contrib_off = 0, fwd_b_size = 0;
+  double model_span_us = -1.0;  // modelled span of the fused launch (-1: no fused launch)
 };
 void plan_large_fronts(sfx_problem* p, int workers, LargeHostPlan& hp) {
   FrontPlan& f = p->a.fp;
@@ -903,12 +914,62 @@ void plan_large_fronts(sfx_problem* p, int workers, LargeHostPlan& hp) {
     }
     const int Kc = getenv("SFX_KC") ? std::max(1, atoi(getenv("SFX_KC"))) : 6;
     p->fused_t0 = (int)tasks.size();
-    build_fused_schedule(lfs, lf_begin, lf_end, Kc, workers, p->fused_fwd, tasks);
+    hp.model_span_us = build_fused_schedule(lfs, lf_begin, lf_end, Kc, workers, p->fused_fwd, tasks);
     verify_fused_list(lfs, lf_begin, lf_end, tasks, (size_t)p->fused_t0);
     p->fused_t1 = (int)tasks.size();
     p->fused_j0 = p->lvl_large[T0].j0;
     p->fused_j1 = (int)jobs.size();
   }
+}
+
+// Ordering + front plan of the system the Cholesky factors.  The reference's ordering (METIS_NodeND, symbolic.cc) is
+// always planned; for systems of a few thousand block variables whose whole elimination tree runs as ONE fused
+// tile-DAG launch, "dissect to depth d, then sweep" candidates are planned as well and the plan with the shortest
+// modelled launch (the list-schedule model of build_fused_schedule, calibrated against task traces) is kept.  Any
+// fill-reducing permutation gives the same factorization up to rounding; only the time differs.  SFX_ORDERING_SEARCH=0
+// keeps the reference's ordering.
+void choose_front_plan(sfx_problem* p, const BlockMatrix& sys, int ordering, const std::vector<int>& sys2ref, int workers) {
+  FrontPlan& fp = p->a.fp;
+  build_front_plan(sys, ordering, sys2ref, fp);
+  p->plan_nd_depth = -1;
+  const char* e = getenv("SFX_ORDERING_SEARCH");
+  if ((e && atoi(e) == 0) || ordering == SFX_ORDERING_NATURAL || getenv("SFX_ND_DEPTH")) return;
+  if (sys.n_nodes < 256 || sys.n_nodes > 8192 || workers <= 0) return;
+  auto model = [&](FrontPlan& f, double& span) {
+    sfx_problem tmp;
+    tmp.sm_count = p->sm_count;
+    tmp.small_max_m = p->small_max_m;
+    tmp.smem_cap_m = p->smem_cap_m;
+    tmp.a.fp = std::move(f);
+    LargeHostPlan hp;
+    plan_large_fronts(&tmp, workers, hp);
+    f = std::move(tmp.a.fp);
+    span = hp.model_span_us;
+    return tmp.fused_T0 == 0 && span > 0.0;  // the model covers a fully fused tree only
+  };
+  double best = 0.0;
+  if (!model(fp, best)) return;
+  const double base = best;
+  for (int depth = 1; depth <= 4; ++depth) {
+    PlanOptions opt;
+    opt.nd_depth = depth == 1 ? -1 : depth;  // first candidate: METIS_NodeND with the amalgamation rules of the others
+    opt.relax = 0.10;
+    opt.cumulative = true;
+    opt.max_merge_w = 1024;
+    FrontPlan cand;
+    build_front_plan(sys, ordering, sys2ref, cand, opt);
+    double span = 0.0;
+    if (model(cand, span) && span < 0.97 * best) {
+      best = span;
+      fp = std::move(cand);
+      p->plan_nd_depth = opt.nd_depth < 0 ? 0 : depth;
+    }
+  }
+  if (getenv("SFX_TIMING"))
+    std::fprintf(stderr, "[sfx analysis] ordering: modelled factor launch %.0f us with METIS_NodeND, %.0f us chosen (%s)\n",
+                 base, best, p->plan_nd_depth < 0    ? "METIS_NodeND"
+                 : p->plan_nd_depth == 0 ? "METIS_NodeND, capped amalgamation"
+                                         : ("dissect to depth " + std::to_string(p->plan_nd_depth) + ", then sweep").c_str());
 }
 
 void upload_structures(sfx_problem* p) {
@@ -1603,7 +1664,7 @@ sfx_status sfx_problem_create(const sfx_problem_desc* desc, sfx_problem** out) {
       for (int r = 0; r < a.N; ++r) int2ref[a.ref2int[r]] = r;
       sys2ref.assign(int2ref.begin(), int2ref.begin() + sys.node_off[sys.n_nodes]);
     }
-    build_front_plan(sys, desc->ordering, sys2ref, a.fp);
+    choose_front_plan(p, sys, desc->ordering, sys2ref, large_factor_resident_ctas());
   }
   clk.lap("create: ordering + front plan");
   CUDA_OK(cudaStreamCreateWithFlags(&p->st, cudaStreamNonBlocking));
@@ -2205,7 +2266,7 @@ int32_t sfx_debug_large_plan(const sfx_problem_desc* desc, int32_t workers, int6
       for (int r = 0; r < a.N; ++r) int2ref[a.ref2int[r]] = r;
       sys2ref.assign(int2ref.begin(), int2ref.begin() + sys.node_off[sys.n_nodes]);
     }
-    build_front_plan(sys, desc->ordering, sys2ref, a.fp);
+    choose_front_plan(&pr, sys, desc->ordering, sys2ref, workers);
     LargeHostPlan hp;
     plan_large_fronts(&pr, workers, hp);
     int64_t n_ea = 0;

@@ -178,8 +178,18 @@ void build_csc(Analysis& a);
 void build_jacobian_csc(Analysis& a);
 void build_point_lists(const BatchPlan& bp, std::vector<int32_t>& order, std::vector<int32_t>& ptr,
                        std::vector<int32_t>& diag, std::vector<int32_t>& rhs);
+// nd_depth >= 0 replaces METIS_NodeND by "dissect to that depth, then sweep" (symbolic.cc); `relax` is the share of
+// explicit zeros relaxed amalgamation accepts in a merged front -- per merge, or over everything the merged supernode
+// has absorbed when `cumulative`.
+struct PlanOptions {
+  int nd_depth = -1;
+  double relax = 0.08;
+  bool cumulative = false;
+  int max_merge_w = 0;  // > 0: no merge produces a supernode wider than this (a merged front is ONE diagonal chain for
+                        // the tile-DAG kernel: siblings that would have run side by side get serialised)
+};
 void build_front_plan(const BlockMatrix& A, int ordering, const std::vector<int>& ref_scalar_of_sys /* may be empty */,
-                      FrontPlan& fp);
+                      FrontPlan& fp, const PlanOptions& opt = PlanOptions());
 
 // SFX_TIMING=1: wall time of the host analysis phases on stderr (setup cost is outside the LM metric)
 struct PhaseClock {

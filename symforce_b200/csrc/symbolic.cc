@@ -30,7 +30,158 @@ static void metis(std::vector<int64_t>& xadj, std::vector<int64_t>& adj, std::ve
   SFX_CHECK(rc == 1, SFX_ERR_STRUCTURE, "METIS_NodeND failed");
 }
 
-void build_front_plan(const BlockMatrix& A, int ordering, const std::vector<int>& sys2ref, FrontPlan& fp) {
+extern "C" int METIS_ComputeVertexSeparator(int64_t* nvtxs, int64_t* xadj, int64_t* adjncy, int64_t* vwgt,
+                                            int64_t* options, int64_t* sepsize, int64_t* part);
+
+// ---- "dissect, then sweep" ordering -------------------------------------------------------------------------------
+// Nested dissection only as deep as the device needs independent subtrees (2^depth of them), then every subdomain is
+// eliminated in one sweep (Cuthill-McKee from the vertex farthest from the subdomain's separators).  On banded systems
+// (camera chains, trajectories; the synthetic BAL ring is one) a swept subdomain carries the band and ONE border in
+// its fronts until the sweep reaches the other end, where full nested dissection carries both borders everywhere:
+// about half the factorization flops of the subdomains, and the sweep's column-by-column dependency is exactly what
+// the tile-DAG kernel pipelines.  Which depth (or plain METIS_NodeND) to use is decided by the caller from the
+// modelled factorization time.
+namespace {
+struct Dissector {
+  const std::vector<std::vector<int>>& adj;  // symmetric node adjacency (no self loops)
+  const std::vector<int>& dim;
+  std::vector<int> loc;        // scratch: vertex -> local index (-1 outside the current subgraph)
+  std::vector<char> is_border; // vertices adjacent to an enclosing separator
+  std::vector<int> out;        // elimination order
+
+  void induced(const std::vector<int>& vs, std::vector<int64_t>& xadj, std::vector<int64_t>& ad) {
+    for (size_t i = 0; i < vs.size(); ++i) loc[vs[i]] = (int)i;
+    xadj.assign(vs.size() + 1, 0);
+    ad.clear();
+    for (size_t i = 0; i < vs.size(); ++i) {
+      for (int u : adj[vs[i]])
+        if (loc[u] >= 0) ad.push_back(loc[u]);
+      xadj[i + 1] = (int64_t)ad.size();
+    }
+    for (int v : vs) loc[v] = -1;
+  }
+  // Cuthill-McKee sweep of every component; starts at the vertex farthest from the border vertices of the component
+  // (a pseudo-peripheral vertex when there are none), so the border joins the fronts last.
+  void sweep(const std::vector<int>& vs) {
+    std::vector<int64_t> xadj, ad;
+    induced(vs, xadj, ad);
+    const int n = (int)vs.size();
+    std::vector<int> dist(n), comp, q;
+    std::vector<char> done(n, 0);
+    auto bfs = [&](const std::vector<int>& src, const std::vector<int>& within) {
+      for (int v : within) dist[v] = -1;
+      q.clear();
+      for (int v : src) {
+        dist[v] = 0;
+        q.push_back(v);
+      }
+      for (size_t h = 0; h < q.size(); ++h)
+        for (int64_t e = xadj[q[h]]; e < xadj[q[h] + 1]; ++e)
+          if (dist[ad[e]] < 0) {
+            dist[ad[e]] = dist[q[h]] + 1;
+            q.push_back((int)ad[e]);
+          }
+      return q.back();
+    };
+    for (int s0 = 0; s0 < n; ++s0) {
+      if (done[s0]) continue;
+      // component of s0
+      std::fill(dist.begin(), dist.end(), -1);
+      bfs({s0}, {});
+      comp = q;
+      std::vector<int> border;
+      for (int v : comp)
+        if (is_border[vs[v]]) border.push_back(v);
+      int start;
+      if (!border.empty()) {
+        start = bfs(border, comp);
+      } else {
+        start = bfs({s0}, comp);
+        start = bfs({start}, comp);
+      }
+      // Cuthill-McKee from `start`: BFS, neighbours by increasing degree
+      for (int v : comp) dist[v] = -1;
+      std::vector<int> ord{start};
+      dist[start] = 0;
+      std::vector<int> nb;
+      for (size_t h = 0; h < ord.size(); ++h) {
+        nb.clear();
+        for (int64_t e = xadj[ord[h]]; e < xadj[ord[h] + 1]; ++e)
+          if (dist[ad[e]] < 0) {
+            dist[ad[e]] = 0;
+            nb.push_back((int)ad[e]);
+          }
+        std::sort(nb.begin(), nb.end(), [&](int a, int b) {
+          const int64_t da = xadj[a + 1] - xadj[a], db = xadj[b + 1] - xadj[b];
+          return da != db ? da < db : a < b;
+        });
+        for (int u : nb) ord.push_back(u);
+      }
+      for (int v : ord) {
+        done[v] = 1;
+        out.push_back(vs[v]);
+      }
+    }
+  }
+  void dissect(const std::vector<int>& vs, int depth) {
+    if (vs.empty()) return;
+    if (depth <= 0 || vs.size() < 8) {
+      sweep(vs);
+      return;
+    }
+    std::vector<int64_t> xadj, ad;
+    induced(vs, xadj, ad);
+    int64_t n = (int64_t)vs.size(), sep = 0;
+    if (ad.empty()) {
+      for (int v : vs) out.push_back(v);
+      return;
+    }
+    std::vector<int64_t> vw(n), part(n);
+    for (int64_t i = 0; i < n; ++i) vw[i] = dim[vs[i]];
+    const int rc = METIS_ComputeVertexSeparator(&n, xadj.data(), ad.data(), vw.data(), nullptr, &sep, part.data());
+    SFX_CHECK(rc == 1, SFX_ERR_STRUCTURE, "METIS_ComputeVertexSeparator failed");
+    std::vector<int> part_of[3];
+    for (int64_t i = 0; i < n; ++i) part_of[part[i] < 0 || part[i] > 2 ? 2 : part[i]].push_back(vs[i]);
+    if (part_of[0].empty() || part_of[1].empty()) {
+      sweep(vs);
+      return;
+    }
+    // vertices next to the new separator become border vertices of their side
+    std::vector<int> marked;
+    for (int v : part_of[2])
+      for (int u : adj[v])
+        if (!is_border[u]) {
+          is_border[u] = 1;
+          marked.push_back(u);
+        }
+    dissect(part_of[0], depth - 1);
+    dissect(part_of[1], depth - 1);
+    for (int u : marked) is_border[u] = 0;
+    sweep(part_of[2]);
+  }
+};
+}  // namespace
+
+void dissect_then_sweep(const std::vector<std::vector<int>>& adj, const std::vector<int>& dim, int depth,
+                        std::vector<int>& order) {
+  const int nn = (int)adj.size();
+  Dissector d{adj, dim, std::vector<int>(nn, -1), std::vector<char>(nn, 0), {}};
+  d.out.reserve(nn);
+  std::vector<int> all(nn);
+  std::iota(all.begin(), all.end(), 0);
+  d.dissect(all, depth);
+  SFX_CHECK((int)d.out.size() == nn, SFX_ERR_STRUCTURE, "internal: dissection lost vertices");
+  order = d.out;
+}
+
+void build_front_plan(const BlockMatrix& A, int ordering, const std::vector<int>& sys2ref, FrontPlan& fp,
+                      const PlanOptions& opt_in) {
+  PlanOptions opt = opt_in;
+  // experiment knobs (override the caller's choice)
+  if (getenv("SFX_ND_DEPTH")) opt.nd_depth = atoi(getenv("SFX_ND_DEPTH"));
+  if (getenv("SFX_RELAX")) opt.relax = atof(getenv("SFX_RELAX"));
+  if (getenv("SFX_RELAX_CUM")) opt.cumulative = atoi(getenv("SFX_RELAX_CUM")) != 0;
+  if (getenv("SFX_MAX_MERGE_W")) opt.max_merge_w = atoi(getenv("SFX_MAX_MERGE_W"));
   const int nn = A.n_nodes;
   const int n = A.node_off[nn];
   fp = FrontPlan{};
@@ -47,7 +198,14 @@ void build_front_plan(const BlockMatrix& A, int ordering, const std::vector<int>
   // ---- ordering -> pos_of[node] ------------------------------------------------------------------
   std::vector<int> order(nn);  // elimination position -> node
   std::iota(order.begin(), order.end(), 0);
-  if (ordering == SFX_ORDERING_METIS_BLOCK) {
+  const int nd_depth = opt.nd_depth;
+  if (nd_depth >= 0 && ordering != SFX_ORDERING_NATURAL) {
+    for (int i = 0; i < nn; ++i) {
+      std::sort(adj[i].begin(), adj[i].end());
+      adj[i].erase(std::unique(adj[i].begin(), adj[i].end()), adj[i].end());
+    }
+    dissect_then_sweep(adj, A.node_dim, nd_depth, order);
+  } else if (ordering == SFX_ORDERING_METIS_BLOCK) {
     std::vector<int64_t> xadj(nn + 1, 0), ad, iperm;
     for (int i = 0; i < nn; ++i) {
       std::sort(adj[i].begin(), adj[i].end());
@@ -178,13 +336,25 @@ void build_front_plan(const BlockMatrix& A, int ordering, const std::vector<int>
   std::vector<int> dim_pos(nn);
   for (int p = 0; p < nn; ++p) dim_pos[p] = A.node_dim[order[p]];
   std::vector<int> sn_first, sn_last;  // position ranges
-  for (int p = 0; p < nn; ++p) {
-    bool merge = p > 0 && parent[p - 1] == p && st[p - 1].size() == st[p].size() + 1;
-    if (merge)
-      sn_last.back() = p;
-    else {
-      sn_first.push_back(p);
-      sn_last.push_back(p);
+  {
+    std::vector<int> n_children(nn, 0);
+    for (int p = 0; p < nn; ++p)
+      if (parent[p] >= 0) n_children[parent[p]]++;
+    int cur_w = 0;
+    for (int p = 0; p < nn; ++p) {
+      bool merge = p > 0 && parent[p - 1] == p && st[p - 1].size() == st[p].size() + 1;
+      // a column with several children starts its own supernode when the run before it is already wide (a quarter of
+      // max_merge_w): that run and its sibling subtrees then stay separate fronts the tile-DAG kernel works on side by
+      // side, instead of one diagonal chain
+      if (merge && opt.max_merge_w > 0 && n_children[p] > 1 && 4 * cur_w >= opt.max_merge_w) merge = false;
+      if (merge) {
+        sn_last.back() = p;
+        cur_w += dim_pos[p];
+      } else {
+        sn_first.push_back(p);
+        sn_last.push_back(p);
+        cur_w = dim_pos[p];
+      }
     }
   }
   // relaxed amalgamation: merge a supernode into its parent when contiguous and cheap
@@ -205,6 +375,7 @@ void build_front_plan(const BlockMatrix& A, int ordering, const std::vector<int>
       return u;
     };
     std::vector<int> sw(ns), su(ns);
+    std::vector<double> sz(ns, 0.0);  // explicit zeros a supernode has accumulated through merges
     for (int s = 0; s < ns; ++s) {
       sw[s] = width(s);
       su[s] = uheight(s);
@@ -219,10 +390,13 @@ void build_front_plan(const BlockMatrix& A, int ordering, const std::vector<int>
         const double mp = wp + up;
         const double zeros = wc * (mp - uc);  // rows of the parent front absent from the child
         const double merged = (wc + wp) * (wc + wp + up);
-        static const double relax_big = getenv("SFX_RELAX") ? atof(getenv("SFX_RELAX")) : 0.08;  // experiment knob
-        bool ok = zeros <= 0.0 || (wc + wp <= 48 && zeros <= 0.35 * merged) || zeros <= relax_big * merged;
+        const double relax_big = opt.relax;
+        const double ztot = opt.cumulative ? zeros + sz[c] + sz[s] : zeros;
+        bool ok = zeros <= 0.0 || (wc + wp <= 48 && zeros <= 0.35 * merged) || ztot <= relax_big * merged;
+        if (opt.max_merge_w > 0 && wc + wp > opt.max_merge_w) ok = false;
         if (!ok) break;
         // merge c into s
+        sz[s] += sz[c] + zeros;
         alive[c] = 0;
         sn_first[s] = sn_first[c];
         for (int p = sn_first[c]; p <= sn_last[c]; ++p) sn_of[p] = s;

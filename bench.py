@@ -257,10 +257,28 @@ def rooflines(workload, info, ph):
                     "achieved": schur_bytes / (ph["schur"] * 1e-3) / 1e9, "peak": hbm, "unit": "GB/s",
                     "traffic": traffic.get("schur"), "peak_source": hbm_src}
         rl_schur["frac"] = rl_schur["achieved"] / hbm
+        # the S product gathers both whitened 3 x 9 blocks of every (landmark, camera pair) match through L2: that
+        # traffic, not HBM, is what bounds it (profiles/r02_results.md); measured L2 read peak: tools/micro/l2_peak.cu
+        try:
+            l2 = json.load(open(os.path.join(ROOT, "profiles", "l2_peak.json")))
+            l2_peak = float(l2["l2_read_gbs"])
+            l2_bytes = 432 * info["schur_pairs"] + schur_bytes
+            rl_schur["l2"] = {"bound": "l2", "achieved": l2_bytes / (ph["schur"] * 1e-3) / 1e9, "peak": l2_peak,
+                              "unit": "GB/s", "frac": l2_bytes / (ph["schur"] * 1e-3) / 1e9 / l2_peak,
+                              "bytes": "432 B per match (two 216-byte blocks) + the HBM figure",
+                              "peak_source": "profiles/l2_peak.json (tools/micro/l2_peak.cu)"}
+        except Exception:
+            pass
     rl_fac = {"kernel": "large_factor_kernel (tile-DAG supernodal Cholesky, DMMA m8n8k4)", "bound": "tensor",
               "achieved": fac_flops / (ph["factorize"] * 1e-3) / 1e12, "peak": fp64_peak, "unit": "TFLOP/s",
               "traffic": traffic.get("large_factor_kernel"), "peak_source": fp64_src}
     rl_fac["frac"] = rl_fac["achieved"] / fp64_peak
+    # `achieved` counts the flops of the plan that ran; the plan is chosen by modelled time and may need fewer flops than
+    # the reference's METIS_NodeND ordering would (sfx_get_info: plan, ref_ordering_flops)
+    rl_fac["plan"] = {-1: "METIS_NodeND", 0: "METIS_NodeND, capped amalgamation"}.get(
+        info.get("plan", -1), "dissect to depth %d, then sweep" % info.get("plan", -1))
+    if info.get("ref_ordering_flops"):
+        rl_fac["gflop_ref_ordering"] = float(info["ref_ordering_flops"]) / 1e9
     dominant = max([kv for kv in (("factorize", rl_fac), ("schur", rl_schur), ("linearize", rl_lin)) if kv[1]],
                    key=lambda kv: ph[kv[0]])[1]
     return rl_lin, rl_schur, rl_fac, dominant

@@ -315,7 +315,11 @@ enum {
   SFX_INFO_CHOL_FAILURES = 13,  /* iterations of the last sfx_optimize whose LLT met a non-positive pivot (step rejected) */
   SFX_INFO_NONFINITE_UPDATES = 14, /* iterations of the last sfx_optimize with a non-finite update vector */
   SFX_INFO_ZERO_DIAGONAL = 15,  /* debug_checks: damped diagonal entries below epsilon (CheckHessianDiagonal) */
-  SFX_INFO_COUNT = 16
+  SFX_INFO_PLAN = 16,  /* front plan the library chose by modelled factorization time: -1 METIS_NodeND as the reference
+                          orders (Eigen::MetisOrdering, sparse_cholesky_solver.tcc:13-30), 0 the same ordering with capped
+                          amalgamation, d >= 2 nested dissection to depth d + a sweep of every subdomain */
+  SFX_INFO_REF_ORDERING_FLOPS = 17, /* factorization flops of the METIS_NodeND plan (SFX_INFO_FACTOR_FLOPS: chosen plan) */
+  SFX_INFO_COUNT = 18
 };
 sfx_status sfx_get_info(sfx_problem* p, int64_t* out, int32_t capacity);
 

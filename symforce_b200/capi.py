@@ -26,7 +26,7 @@ EXPORTS = [
 
 INFO_NAMES = ["N", "M", "nnz_H", "num_nodes", "reduced_dim", "nnz_L", "num_supernodes", "num_levels",
               "factor_flops", "s_blocks", "schur_pairs", "max_front", "device_bytes", "chol_failures",
-              "nonfinite_updates", "zero_diagonal"]
+              "nonfinite_updates", "zero_diagonal", "plan", "ref_ordering_flops"]
 
 _lib = None
 

@@ -140,6 +140,7 @@ struct sfx_problem {
   int sm_count = 148;  // multiprocessors of the device (cudaDevAttrMultiProcessorCount at create)
   int plan_nd_depth = -1;  // plan chosen by choose_front_plan: -1 METIS_NodeND as the reference orders, 0 METIS_NodeND
                            // with capped cumulative amalgamation, d >= 2 dissect to depth d + sweep
+  double ref_plan_flops = 0.0;  // factorization flops of the METIS_NodeND plan
   int fused_T0 = -1;  // first level of the fused top of the elimination tree (-1: none)
   int fused_t0 = 0, fused_t1 = 0, fused_j0 = 0, fused_j1 = 0;
   bool fused_fwd = false;       // the forward substitution of the fused fronts rides inside the factor kernel
@@ -511,6 +512,8 @@ double build_fused_schedule(const std::vector<LargeFront>& lfs, int lf_begin, in
     }
   };
   std::priority_queue<Ev, std::vector<Ev>, std::greater<Ev>> chain_end;  // ends of the last steps of sticky chains
+  const bool util_bins = getenv("SFX_TIMING") && atoi(getenv("SFX_TIMING")) >= 2;  // modelled utilisation per 100 us
+  std::vector<double> util;
   while (started < n) {
     bool moved = false;
     while (!avail.empty() && avail.top().first <= now) {
@@ -535,6 +538,13 @@ double build_fused_schedule(const std::vector<LargeFront>& lfs, int lf_begin, in
       const int id = ready.top().second;
       ready.pop();
       out.push_back(g[id].t);
+      if (util_bins) {
+        for (double t = now; t < now + g[id].dur; t += 10.0) {
+          const size_t b = (size_t)(t / 100.0);
+          if (b >= util.size()) util.resize(b + 1, 0.0);
+          util[b] += std::min(10.0, now + g[id].dur - t);
+        }
+      }
       // DIAG(0) of a sticky chain keeps its CTA until the chain's last step ends (a one-step chain: like any task)
       if ((g[id].chain & 1) && !(g[id].chain & 4))
         ;  // the CTA is released by chain_end
@@ -564,6 +574,11 @@ double build_fused_schedule(const std::vector<LargeFront>& lfs, int lf_begin, in
   while (!chain_end.empty()) {
     now = std::max(now, chain_end.top().first);
     chain_end.pop();
+  }
+  if (util_bins) {
+    std::fprintf(stderr, "[sfx analysis] modelled busy CTAs per 100 us:");
+    for (double u : util) std::fprintf(stderr, " %.0f", u / 100.0);
+    std::fprintf(stderr, "\n");
   }
   if (getenv("SFX_TIMING")) {
     double busy[11] = {0};
@@ -932,6 +947,7 @@ void choose_front_plan(sfx_problem* p, const BlockMatrix& sys, int ordering, con
   FrontPlan& fp = p->a.fp;
   build_front_plan(sys, ordering, sys2ref, fp);
   p->plan_nd_depth = -1;
+  p->ref_plan_flops = fp.flops;
   const char* e = getenv("SFX_ORDERING_SEARCH");
   if ((e && atoi(e) == 0) || ordering == SFX_ORDERING_NATURAL || getenv("SFX_ND_DEPTH")) return;
   if (sys.n_nodes < 256 || sys.n_nodes > 8192 || workers <= 0) return;
@@ -2365,6 +2381,8 @@ sfx_status sfx_get_info(sfx_problem* p, int64_t* out, int32_t capacity) {
   v[SFX_INFO_CHOL_FAILURES] = p->h_ctrl->n_chol_fail;
   v[SFX_INFO_NONFINITE_UPDATES] = p->h_ctrl->n_nonfinite_update;
   v[SFX_INFO_ZERO_DIAGONAL] = p->h_ctrl->n_zero_diag;
+  v[SFX_INFO_PLAN] = p->plan_nd_depth;
+  v[SFX_INFO_REF_ORDERING_FLOPS] = (int64_t)p->ref_plan_flops;
   for (int i = 0; i < std::min<int>(capacity, SFX_INFO_COUNT); ++i) out[i] = v[i];
   SFX_API_END(p)
 }

@@ -268,3 +268,28 @@ def test_host_maps_random_pose_graphs(seed, monkeypatch):
     jo, ji, jv = o.jacobian()
     assert np.array_equal(jo, np.array(A["jac_outer"])) and np.array_equal(ji, np.array(A["jac_inner"]))
     assert np.array_equal(E.emulate_jacobian(prob, A), jv)
+
+
+@pytest.mark.parametrize("depth", [0, 1, 2, 3])
+@pytest.mark.parametrize("name", ["bal_tiny_schur", "bal_tiny_chol", "pose_graph_small", "robot3d", "ring"])
+def test_dissect_then_sweep_ordering_reproduces_oracle(name, depth, monkeypatch):
+    """The ordering candidates of choose_front_plan (symbolic.cc: nested dissection to a fixed depth, then a
+    Cuthill-McKee sweep of every subdomain; cumulative, width-capped relaxed amalgamation) through the host replay:
+    the fronts, extend-add maps and assembly copies of such a plan must give the oracle's step."""
+    monkeypatch.setenv("SFX_ND_DEPTH", str(depth))
+    monkeypatch.setenv("SFX_RELAX", "0.10")
+    monkeypatch.setenv("SFX_RELAX_CUM", "1")
+    monkeypatch.setenv("SFX_MAX_MERGE_W", "36" if depth % 2 else "1024")
+    if name == "ring":
+        # a camera ring with a covisibility window, the structure of the synthetic Final-shape problem in small
+        prob = P.bal_problem(n_cams=40, n_pts=400, n_obs=1400, window=3, solver=D.SOLVER_SCHUR)
+    else:
+        prob = PROBLEMS[name]()
+    A = capi.analysis_json(prob)
+    perm = A["fronts"]["perm_nodes"]
+    assert sorted(perm) == list(range(len(perm)))
+    assert sorted(A["fronts"]["scalar_perm"]) == list(range(A["fronts"]["n"]))
+    o = O.OracleProblem(prob)
+    upd, (res, rhs, H) = E.emulate_solve_step(prob, A, 0.37)
+    upd_o = o.solve_step(0.37)
+    assert np.allclose(upd, upd_o, rtol=1e-8, atol=1e-9 * max(1e-3, np.abs(upd_o).max()))

@@ -1190,18 +1190,50 @@ __global__ void __launch_bounds__(kSchurWarps * 32) schur_s_dmma_kernel(const Ct
 //     offsets are loaded once per 32 matches (one coalesced load) and broadcast with shuffles; the
 //     loads of the next four k-steps (16 per lane) are in flight while the current four issue.
 constexpr int kWThreads = 128;
+#ifndef SFX_W_CHUNKS
+#define SFX_W_CHUNKS 4
+#endif
+constexpr int kWChunks = SFX_W_CHUNKS;  // schur_w_rhs_kernel<true>: chunks of 32 blocks per warp
 #ifndef SFX_W_MINB
 #define SFX_W_MINB 5
 #endif
+// DIAG: the warp also accumulates S_II -= sum over its 32 blocks W^T W from the staged blocks: 24 DMMA k-steps over the
+// 96 stacked point rows (A and B operand are the same value: W^T W), border row / corner as FMAs.
+template <bool DIAG>
 __global__ void __launch_bounds__(kWThreads, SFX_W_MINB) schur_w_rhs_kernel(const Ctrl* __restrict__ ctrl, StatePtrs sp,
                                                                 SchurDev sd) {
   __shared__ double stage[kWThreads / 32][32 * 27];
   if (ctrl->done) return;
-  const int q = blockIdx.x * kWThreads + threadIdx.x;
-  const bool valid = q < sd.n_entries;
-  const int qc = valid ? q : sd.n_entries - 1;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const double* __restrict__ H = sp.H[ctrl->init_idx];
+  // DIAG: a warp takes kWChunks consecutive chunks of 32 blocks and keeps the S_II accumulators in registers across
+  // them (flushed with REDs when the camera changes): a camera's ~2,800 blocks otherwise send ~90 warps' worth of REDs
+  // to the same 81 addresses
+  constexpr int kIter = DIAG ? kWChunks : 1;
+  const int g_ = lane >> 2, tq_ = lane & 3;
+  double acc0 = 0.0, acc1 = 0.0, row8 = 0.0, corner = 0.0;
+  int accI = -1;
+  auto flush = [&]() {
+    if (accI < 0) return;
+    row8 += __shfl_xor_sync(0xffffffffu, row8, 1);
+    row8 += __shfl_xor_sync(0xffffffffu, row8, 2);
+    corner += __shfl_xor_sync(0xffffffffu, corner, 1);
+    corner += __shfl_xor_sync(0xffffffffu, corner, 2);
+    // lower triangle only: the front assembly reads S_II as a lower block (FrontPlan::Copy::lower_only)
+    double* out = sd.S + sd.s_diag_off[accI];
+    if (g_ >= 2 * tq_) atomicAdd(out + g_ + (2 * tq_) * 9, -acc0);
+    if (g_ >= 2 * tq_ + 1) atomicAdd(out + g_ + (2 * tq_ + 1) * 9, -acc1);
+    if (tq_ == 0) atomicAdd(out + 8 + g_ * 9, -row8);
+    if (lane == 2) atomicAdd(out + 8 + 8 * 9, -corner);
+    acc0 = acc1 = row8 = corner = 0.0;
+    accI = -1;
+  };
+#pragma unroll 1
+  for (int it = 0; it < kIter; ++it) {
+  const int q = (blockIdx.x * (kWThreads / 32) + warp) * (32 * kIter) + it * 32 + lane;
+  if (q - lane >= sd.n_entries) break;
+  const bool valid = q < sd.n_entries;
+  const int qc = valid ? q : sd.n_entries - 1;
   const int I = __ldg(sd.r_node + qc);
   const int l = __ldg(sd.r_lm + qc);
   const int eoff = __ldg(sd.r_eoff + qc);
@@ -1244,6 +1276,25 @@ __global__ void __launch_bounds__(kWThreads, SFX_W_MINB) schur_w_rhs_kernel(cons
     double* dst = sd.G + eoff0;
 #pragma unroll
     for (int i = 0; i < 27; ++i) dst[i * 32 + lane] = st[i * 32 + lane];
+    if (DIAG) {
+      // element (point row k = 3 e + a, camera column c) of the stacked 96 x 9 matrix sits at st[27 e + 3 c + a]
+      if (accI != I0) {
+        flush();
+        accI = I0;
+      }
+#pragma unroll 8
+      for (int s4 = 0; s4 < 24; ++s4) {
+        const int kk = 4 * s4 + tq_;
+        const int en = (kk * 171) >> 9;  // kk / 3
+        const double* wp = st + 27 * en + (kk - 3 * en);
+        const double a = wp[3 * g_];
+        const double a8 = wp[24];
+        dmma884(acc0, acc1, a, a);
+        row8 += a8 * a;
+        corner += a8 * a8;
+      }
+      __syncwarp();  // the staging area is rewritten by the next chunk
+    }
   } else {
     const double* e = H + eoff;
     double* g = sd.G + eoff;
@@ -1258,6 +1309,15 @@ __global__ void __launch_bounds__(kWThreads, SFX_W_MINB) schur_w_rhs_kernel(cons
         g[3 * c + 2] = w2;
         r[c] = w0 * u0 + w1 * u1 + w2 * u2;
       }
+    }
+    if (DIAG && valid) {
+      // ragged warp (camera boundary, tail): the lane's own block, read back from what it has just written
+      double* out = sd.S + sd.s_diag_off[I];
+#pragma unroll 1
+      for (int c = 0; c < 9; ++c)
+#pragma unroll 1
+        for (int rr = c; rr < 9; ++rr)
+          atomicAdd(out + rr + c * 9, -(g[3 * rr] * g[3 * c] + g[3 * rr + 1] * g[3 * c + 1] + g[3 * rr + 2] * g[3 * c + 2]));
     }
   }
   const int to = sd.node_toff[I];
@@ -1275,6 +1335,25 @@ __global__ void __launch_bounds__(kWThreads, SFX_W_MINB) schur_w_rhs_kernel(cons
     for (int c = 0; c < 16; ++c)
       if (c < dI) atomicAdd(sd.rhs_red + to + c, -r[c]);
   }
+  }  // chunks
+  if (DIAG) flush();
+}
+
+// S_II <- B_II + damping (rank 0 / single GPU; zero elsewhere) for the diagonal blocks schur_w_rhs_kernel<true> accumulates
+__global__ void schur_diag_init_kernel(const Ctrl* __restrict__ ctrl, StatePtrs sp, SchurDev sd,
+                                       const double* __restrict__ dvec) {
+  if (ctrl->done) return;
+  const int q = blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= sd.n_reduced_nodes * 81) return;
+  const int I = q / 81, idx = q - 81 * I;
+  const int r = idx % 9, c = idx / 9;
+  double v = 0.0;
+  if (sd.add_b) {
+    const int bsrc = sd.s_diag_bsrc[I];
+    if (bsrc >= 0) v = sp.H[ctrl->init_idx][bsrc + idx];
+    if (r == c) v += dvec[sd.node_toff[I] + r];
+  }
+  sd.S[sd.s_diag_off[I] + idx] = v;
 }
 
 struct alignas(16) SItem2 {
@@ -1418,7 +1497,7 @@ __global__ void __launch_bounds__(kS9Warps * 32, SFX_S9_MINB) schur_s9_kernel(co
   const int wid = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nw = gridDim.x * kS9Warps;
   int item = blockIdx.x * kS9Warps + wid;
-  if (item >= sd.n_items) return;
+  if (item >= sd.n_items3) return;
   const double* __restrict__ W = sd.G;
   const double* __restrict__ H = sp.H[ctrl->init_idx];
   const int4* __restrict__ hdr = reinterpret_cast<const int4*>(sd.items3);
@@ -1453,7 +1532,7 @@ __global__ void __launch_bounds__(kS9Warps * 32, SFX_S9_MINB) schur_s9_kernel(co
   load_group(offs[wid][0], 0, 0);
   for (;;) {
     const int nitem = item + nw;
-    const bool more = nitem < sd.n_items;
+    const bool more = nitem < sd.n_items3;
     int4 hn = make_int4(0, 0, 0, 0);
     int na = 0, nb = 0, nc = 0, nd = 0;
     if (more) {
@@ -1618,11 +1697,17 @@ void launch_schur(cudaStream_t st, const Ctrl* ctrl, StatePtrs sp, const SchurDe
     if (ig * 256 < sd.reduced_dim) ig = (sd.reduced_dim + 255) / 256;
     schur_rhs_init_kernel<<<ig, 256, 0, st>>>(ctrl, sp, sd); ++g_launches;
     if (sd.wl != nullptr) {
-      schur_w_rhs_kernel<<<(sd.n_entries + kWThreads - 1) / kWThreads, kWThreads, 0, st>>>(ctrl, sp, sd); ++g_launches;
+      if (sd.items3 != nullptr && sd.s_diag_off != nullptr) {
+        schur_diag_init_kernel<<<(sd.n_reduced_nodes * 81 + 255) / 256, 256, 0, st>>>(ctrl, sp, sd, dvec); ++g_launches;
+        schur_w_rhs_kernel<true><<<(sd.n_entries + kWThreads * kWChunks - 1) / (kWThreads * kWChunks), kWThreads, 0, st>>>(ctrl, sp, sd);
+        ++g_launches;
+      } else {
+        schur_w_rhs_kernel<false><<<(sd.n_entries + kWThreads - 1) / kWThreads, kWThreads, 0, st>>>(ctrl, sp, sd); ++g_launches;
+      }
       if (sd.items3 != nullptr) {
         int grid = 148 * SFX_S9_MINB;
-        if (grid * kS9Warps > sd.n_items) grid = (sd.n_items + kS9Warps - 1) / kS9Warps;
-        schur_s9_kernel<<<grid, kS9Warps * 32, 0, st>>>(ctrl, sp, sd, dvec); ++g_launches;
+        if (grid * kS9Warps > sd.n_items3) grid = (sd.n_items3 + kS9Warps - 1) / kS9Warps;
+        if (grid > 0) { schur_s9_kernel<<<grid, kS9Warps * 32, 0, st>>>(ctrl, sp, sd, dvec); ++g_launches; }
         return;
       }
       schur_s2_kernel<<<(sd.n_items + kSchurWarps - 1) / kSchurWarps, kSchurWarps * 32, 0, st>>>(ctrl, sp, sd, dvec);

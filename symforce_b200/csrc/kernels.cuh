@@ -89,6 +89,12 @@ struct SchurDev {
   double* G;   // same offsets as the E blocks in H (v1: C^-1 E; v2: W = L^-1 E)
   double* wl;  // v2: [n_landmarks][9] = L^-1 (i00 i10 i11 i20 i21 i22), u = L^-1 w; nullptr selects v1
   const double* zeros;  // 8 zero doubles (padding lanes of the DMMA fragments load from here)
+  // s9 with the diagonal blocks taken out: S_II -= sum_l W_Il^T W_Il is accumulated by schur_w_rhs_kernel from the
+  // blocks it has just whitened (a third of all matches are (I, I) pairs); items3 / pm_* then list the off-diagonal
+  // blocks only (n_items3 of them) and schur_diag_init_kernel stores B_II + damping before the accumulation
+  const int64_t* s_diag_off;   // per reduced node: offset of S_II in S (nullptr: diagonal blocks are s9 items)
+  const int32_t* s_diag_bsrc;  // ... offset of B_II in H (-1: none)
+  int n_items3;
   const void* items3;  // s9: 16-byte headers {s_off lo, s_off hi, bsrc, flags|dI<<8|dJ<<16|diag<<24|cnt<<25}; nullptr: use items2
   const int32_t *pm_i, *pm_j;  // s9: match offsets, 64 slots per item, unused slots -> zero block behind W
   const int32_t* item_toI;     // v3: tangent offset of the row node (damping of diagonal blocks)

@@ -1194,19 +1194,38 @@ void upload_structures(sfx_problem* p) {
         d.items2 = P.upload(hdr);
         if (v3) {
           // padded per-item match offsets + 16-byte headers for the persistent kernel
-          std::vector<int32_t> h3(ib.size() * 4), pmi(ib.size() * 64, zero_block), pmj(ib.size() * 64, zero_block),
-              toI(ib.size());
-          for (size_t q = 0; q < ib.size(); ++q) {
-            const int32_t* h = &hdr[q * 8];
-            h3[q * 4 + 0] = h[4];
-            h3[q * 4 + 1] = h[5];
-            h3[q * 4 + 2] = h[6];
-            h3[q * 4 + 3] = h[2] | (ic[q] << 25);
-            toI[q] = h[3];
-            for (int c = 0; c < ic[q]; ++c) {
-              pmi[q * 64 + c] = s.m_eoff_i[im[q] + c];
-              pmj[q * 64 + c] = s.m_eoff_j[im[q] + c];
+          // the diagonal blocks are accumulated by schur_w_rhs_kernel (every reduced node needs its S_II block for that)
+          std::vector<int64_t> diag_off(s.first_lm_node, -1);
+          std::vector<int32_t> diag_bsrc(s.first_lm_node, -1);
+          for (int b = 0; b < d.n_sblocks; ++b)
+            if (srow[b] == scol[b]) {
+              diag_off[srow[b]] = s.S.blk_off[b];
+              diag_bsrc[srow[b]] = s.s_b_src[b];
             }
+          bool fuse_diag = !getenv("SFX_S9_DIAG_ITEMS");
+          for (int i = 0; i < s.first_lm_node && fuse_diag; ++i) fuse_diag = diag_off[i] >= 0;
+          std::vector<size_t> keep;  // items of the persistent kernel
+          for (size_t q = 0; q < ib.size(); ++q)
+            if (!fuse_diag || srow[ib[q]] != scol[ib[q]]) keep.push_back(q);
+          std::vector<int32_t> h3(keep.size() * 4), pmi(keep.size() * 64, zero_block), pmj(keep.size() * 64, zero_block),
+              toI(keep.size());
+          for (size_t o = 0; o < keep.size(); ++o) {
+            const size_t q = keep[o];
+            const int32_t* h = &hdr[q * 8];
+            h3[o * 4 + 0] = h[4];
+            h3[o * 4 + 1] = h[5];
+            h3[o * 4 + 2] = h[6];
+            h3[o * 4 + 3] = h[2] | (ic[q] << 25);
+            toI[o] = h[3];
+            for (int c = 0; c < ic[q]; ++c) {
+              pmi[o * 64 + c] = s.m_eoff_i[im[q] + c];
+              pmj[o * 64 + c] = s.m_eoff_j[im[q] + c];
+            }
+          }
+          d.n_items3 = (int)keep.size();
+          if (fuse_diag) {
+            d.s_diag_off = P.upload(diag_off);
+            d.s_diag_bsrc = P.upload(diag_bsrc);
           }
           d.items3 = P.upload(h3);
           d.pm_i = P.upload(pmi);

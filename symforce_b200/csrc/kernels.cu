@@ -59,7 +59,12 @@ __device__ __forceinline__ double block_sum(double v) {
   return r;
 }
 
-__device__ __forceinline__ int sel_block(const Ctrl* c, int mode) { return mode == 0 ? c->init_idx : c->new_idx; }
+// mode 0: the Init block (skipped when its linearization is valid), 1: the New block, 2: block kEagerBlock
+// unconditionally and whatever the control block says (eager linearization of freshly uploaded values, sfx_set_values)
+constexpr int kModeEager = 2;
+__device__ __forceinline__ int sel_block(const Ctrl* c, int mode) {
+  return mode == kModeEager ? kEagerBlock : (mode == 0 ? c->init_idx : c->new_idx);
+}
 
 // ------------------------------------------------------------------------------------------------
 // K1: linearize
@@ -304,9 +309,9 @@ constexpr int kPbufStride = 9;
 template <int SKIP>
 __global__ void __launch_bounds__(kBalThreads, SFX_BAL_MINB) linearize_bal_kernel(const Ctrl* __restrict__ ctrl, StatePtrs sp,
                                                                     LinBatch b, int mode,
-                                                                    double* __restrict__ partials) {
+                                                                    double* __restrict__ partials, int block0) {
   __shared__ double stage[kBalThreads / 32][32 * 27];
-  if (ctrl->done) return;
+  if (mode != kModeEager && ctrl->done) return;
   const int blk = sel_block(ctrl, mode);
   if (mode == 0 && ctrl->lin_valid[blk]) return;
   const double* __restrict__ values = sp.values[blk];
@@ -314,7 +319,8 @@ __global__ void __launch_bounds__(kBalThreads, SFX_BAL_MINB) linearize_bal_kerne
   double* __restrict__ rhs = sp.rhs[blk];
   double* __restrict__ resid = sp.res[blk];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int s = blockIdx.x * kBalThreads + threadIdx.x;
+  const int cta = blockIdx.x + block0;  // (block0 > 0: the launch covers a sub-range of the batch)
+  const int s = cta * kBalThreads + threadIdx.x;
   const bool valid = s < b.n;
   const int sc = valid ? s : b.n - 1;
   double res[2], J[24];
@@ -430,7 +436,7 @@ __global__ void __launch_bounds__(kBalThreads, SFX_BAL_MINB) linearize_bal_kerne
         st[lane * kPbufStride + 6 + r] = J[2 * (9 + r)] * res[0] + J[2 * (9 + r) + 1] * res[1];
     }
     __syncwarp();
-    double* dst = b.pbuf + (size_t)(blockIdx.x * kBalThreads + warp * 32) * kPbufStride;
+    double* dst = b.pbuf + (size_t)(cta * kBalThreads + warp * 32) * kPbufStride;
 #pragma unroll
     for (int i = 0; i < kPbufStride; ++i) SFX_ST_STREAM(dst + i * 32 + lane, st[i * 32 + lane]);
     __syncwarp();
@@ -476,14 +482,14 @@ __global__ void __launch_bounds__(kBalThreads, SFX_BAL_MINB) linearize_bal_kerne
     }
   }
   const double tot = block_sum<kBalThreads>(err);
-  if (threadIdx.x == 0) partials[b.partial_base + blockIdx.x] = tot;
+  if (threadIdx.x == 0) partials[b.partial_base + cta] = tot;
 }
 
 // sums the per-observation point contributions of linearize_bal_kernel in slot order (deterministic)
 // and adds the total to the point's diagonal block and rhs
 __global__ void __launch_bounds__(128) bal_point_finalize_kernel(const Ctrl* __restrict__ ctrl, StatePtrs sp, LinBatch b,
                                                                  int mode) {
-  if (ctrl->done) return;
+  if (mode != kModeEager && ctrl->done) return;
   const int blk = sel_block(ctrl, mode);
   if (mode == 0 && ctrl->lin_valid[blk]) return;
   const int pt = blockIdx.x * blockDim.x + threadIdx.x;
@@ -524,7 +530,7 @@ __global__ void __launch_bounds__(128) bal_point_finalize_kernel(const Ctrl* __r
 }
 
 __global__ void zero_lin_kernel(const Ctrl* __restrict__ ctrl, StatePtrs sp, int mode, int64_t n_h, int n_rhs) {
-  if (ctrl->done) return;
+  if (mode != kModeEager && ctrl->done) return;
   const int blk = sel_block(ctrl, mode);
   if (mode == 0 && ctrl->lin_valid[blk]) return;
   double* H = sp.H[blk];
@@ -535,14 +541,35 @@ __global__ void zero_lin_kernel(const Ctrl* __restrict__ ctrl, StatePtrs sp, int
 }
 
 // sums the per-CTA partials deterministically; err[target] = 0.5 * sum
-__global__ void finish_error_kernel(Ctrl* ctrl, const double* __restrict__ partials, int n, int mode) {
-  if (ctrl->done) return;
+__global__ void finish_error_kernel(Ctrl* ctrl, const double* __restrict__ partials, int n, int mode,
+                                    double* __restrict__ eager_err) {
+  if (mode != kModeEager && ctrl->done) return;
   const int blk = sel_block(ctrl, mode);
   if (mode == 0 && ctrl->lin_valid[blk]) return;
   double v = 0;
   for (int i = threadIdx.x; i < n; i += 1024) v += partials[i];
   const double tot = block_sum<1024>(v);
-  if (threadIdx.x == 0) ctrl->red[0] = 0.5 * tot;  // this rank's part; committed by commit_error_kernel
+  if (threadIdx.x == 0) {
+    if (mode == kModeEager)
+      *eager_err = 0.5 * tot;  // kept beside the control block (which the next Optimize resets) until it is adopted
+    else
+      ctrl->red[0] = 0.5 * tot;  // this rank's part; committed by commit_error_kernel
+  }
+}
+
+// the Init block takes over the linearization sfx_set_values computed while the values were still arriving
+__global__ void adopt_eager_kernel(Ctrl* ctrl, const double* __restrict__ eager_err) {
+  if (ctrl->done) return;
+  if (ctrl->init_idx != kEagerBlock) {  // cannot happen (see kEagerBlock); never solve with another block's leftovers
+    ctrl->done = 3;  // FAILED
+    ctrl->failure_reason = 2;
+    return;
+  }
+  ctrl->err[kEagerBlock] = *eager_err;
+  ctrl->lin_valid[kEagerBlock] = 1;
+}
+void launch_adopt_eager(cudaStream_t st, Ctrl* ctrl, const double* eager_err) {
+  adopt_eager_kernel<<<1, 1, 0, st>>>(ctrl, eager_err); ++g_launches;
 }
 
 // err[target] = (all-reduced) red[0]; marks the linearization valid
@@ -616,12 +643,24 @@ void launch_zero_lin(cudaStream_t st, const Ctrl* ctrl, StatePtrs sp, int mode, 
 }
 
 int g_lin_skip = 0;  // debug (sfx_debug_time_linearize): parts of linearize_bal_kernel to leave out
+// BAL fast path over the CTAs [block0, block1) of the batch (128 observations each), without the per-point sums
+void launch_linearize_bal_range(cudaStream_t st, const Ctrl* ctrl, StatePtrs sp, int mode, const LinBatch& b, double* partials,
+                                int block0, int block1) {
+  if (block1 <= block0) return;
+  linearize_bal_kernel<0><<<block1 - block0, kBalThreads, 0, st>>>(ctrl, sp, b, mode, partials, block0); ++g_launches;
+}
+void launch_bal_point_finalize(cudaStream_t st, const Ctrl* ctrl, StatePtrs sp, int mode, const LinBatch& b) {
+  if (b.pbuf == nullptr) return;
+  bal_point_finalize_kernel<<<(b.n_pf + 127) / 128, 128, 0, st>>>(ctrl, sp, b, mode); ++g_launches;
+}
+int linearize_bal_blocks(const LinBatch& b) { return (b.n + kBalThreads - 1) / kBalThreads; }
+
 void launch_linearize(cudaStream_t st, const Ctrl* ctrl, StatePtrs sp, int mode, const LinBatch& b, double* partials) {
   const int grid = (b.n + kLinThreads - 1) / kLinThreads;
   if (b.bal_fast) {
     switch (g_lin_skip) {
 #define SFX_SKIP_CASE(V) \
-  case V: linearize_bal_kernel<V><<<grid, kBalThreads, 0, st>>>(ctrl, sp, b, mode, partials); break;
+  case V: linearize_bal_kernel<V><<<grid, kBalThreads, 0, st>>>(ctrl, sp, b, mode, partials, 0); break;
       SFX_SKIP_CASE(1)
       SFX_SKIP_CASE(2)
       SFX_SKIP_CASE(4)
@@ -629,7 +668,7 @@ void launch_linearize(cudaStream_t st, const Ctrl* ctrl, StatePtrs sp, int mode,
       SFX_SKIP_CASE(8)
       SFX_SKIP_CASE(15)
 #undef SFX_SKIP_CASE
-      default: linearize_bal_kernel<0><<<grid, kBalThreads, 0, st>>>(ctrl, sp, b, mode, partials); break;
+      default: linearize_bal_kernel<0><<<grid, kBalThreads, 0, st>>>(ctrl, sp, b, mode, partials, 0); break;
     }
     ++g_launches;
     if (b.pbuf != nullptr && !(g_lin_skip & 2)) {
@@ -704,8 +743,8 @@ void launch_jacobian(cudaStream_t st, const double* values, const LinBatch& b, c
   }
 }
 
-void launch_finish_error(cudaStream_t st, Ctrl* ctrl, int mode, const double* partials, int n_partials) {
-  finish_error_kernel<<<1, 1024, 0, st>>>(ctrl, partials, n_partials, mode); ++g_launches;
+void launch_finish_error(cudaStream_t st, Ctrl* ctrl, int mode, const double* partials, int n_partials, double* eager_err) {
+  finish_error_kernel<<<1, 1024, 0, st>>>(ctrl, partials, n_partials, mode, eager_err); ++g_launches;
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -203,7 +203,19 @@ void launch_zero_lin(cudaStream_t st, const Ctrl* ctrl, StatePtrs sp, int mode, 
 void launch_linearize(cudaStream_t st, const Ctrl* ctrl, StatePtrs sp, int mode, const LinBatch& b, double* partials);
 void launch_jacobian(cudaStream_t st, const double* values, const LinBatch& b, const int32_t* jac_base,
                      const int32_t* jac_colnnz, double* out);
-void launch_finish_error(cudaStream_t st, Ctrl* ctrl, int mode, const double* partials, int n_partials);
+void launch_finish_error(cudaStream_t st, Ctrl* ctrl, int mode, const double* partials, int n_partials,
+                         double* eager_err = nullptr);
+// eager linearization of freshly uploaded values (mode 2, sfx_set_values): the BAL batch in CTA ranges, then the point
+// sums and the error; launch_adopt_eager hands the result to the Init block of the next Optimize
+constexpr int kLinModeEager = 2;
+// the state block the eager linearization is written to: the Init block of the first iteration after a reset
+// (reset_ctrl: init 0, new 1; lm_begin_kernel swaps the two at the start of every iteration)
+constexpr int kEagerBlock = 1;
+void launch_linearize_bal_range(cudaStream_t st, const Ctrl* ctrl, StatePtrs sp, int mode, const LinBatch& b, double* partials,
+                                int block0, int block1);
+void launch_bal_point_finalize(cudaStream_t st, const Ctrl* ctrl, StatePtrs sp, int mode, const LinBatch& b);
+int linearize_bal_blocks(const LinBatch& b);
+void launch_adopt_eager(cudaStream_t st, Ctrl* ctrl, const double* eager_err);
 void launch_damping(cudaStream_t st, Ctrl* ctrl, StatePtrs sp, const int32_t* diag_pos, int N, double* dvec,
                     double* max_diag);
 void launch_schur(cudaStream_t st, const Ctrl* ctrl, StatePtrs sp, const SchurDev& sd, const double* dvec);

@@ -193,9 +193,19 @@ struct sfx_problem {
   sfx_timings tm{};
   sfx_stats last_stats{};
   bool values_set = false;
+  // eager linearization (single GPU, one BAL fast-path batch whose pixel arguments are one ascending run of the values
+  // buffer): sfx_set_values uploads the pixels in chunks and linearizes every chunk of observations as it lands -- the
+  // Init linearization of the next sfx_optimize hides behind the upload, which then adopts it (adopt_eager_kernel)
+  bool eager_ok = false;
+  int64_t eager_pix_base = 0;
+  double* d_eager_err = nullptr;
+  bool eager_valid = false;     // block kEagerBlock holds the linearization of d_cur_values, untouched since
+  bool lin0_clobbered = false;  // ... and therefore no longer the one the last Optimize left there
+  std::vector<cudaEvent_t> ev_up;
 
   ~sfx_problem() {
     for (auto e : ev) cudaEventDestroy(e);
+    for (auto e : ev_up) cudaEventDestroy(e);
     if (st) cudaStreamDestroy(st);
     if (st2) cudaStreamDestroy(st2);
     if (dbg_values) cudaFree(dbg_values);
@@ -1366,6 +1376,8 @@ void validate_params(const sfx_params& q) {
 void reset_ctrl(sfx_problem* p) {
   Ctrl* c = p->h_ctrl;
   p->can_continue = false;
+  p->eager_valid = false;  // every caller goes on to overwrite the state blocks
+  p->lin0_clobbered = false;
   std::memset(c, 0, offsetof(Ctrl, iters));
   c->p = p->params;
   c->epsilon = p->epsilon;
@@ -1710,6 +1722,28 @@ sfx_status sfx_problem_create(const sfx_problem_desc* desc, sfx_problem** out) {
   CUDA_OK(cudaEventCreateWithFlags(&p->ev_join2, cudaEventDisableTiming));
   p->pool.st = p->st;
   upload_structures(p);
+  {
+    // eager linearization at sfx_set_values: one BAL fast-path batch whose pixel argument of observation s sits at
+    // base + 2 s of the values buffer (the reference example's layout: measurements stored in observation order)
+    const Analysis& a = p->a;
+    bool ok = a.world == 1 && p->lin.size() == 1 && p->lin[0].bal_fast && !getenv("SFX_NO_EAGER_LINEARIZE");
+    if (ok) {
+      const auto& ao = a.batches[0].arg_off;
+      const int64_t nb = p->lin[0].n;
+      ok = nb > 0 && (int64_t)ao.size() >= 4 * nb;
+      const int64_t base = ok ? ao[3 * nb] : 0;
+      for (int64_t q = 0; q < nb && ok; ++q) ok = ao[3 * nb + q] == base + 2 * q;
+      ok = ok && base >= 0 && base + 2 * nb <= a.n_values;
+      // no other argument may live inside the pixel run (it is uploaded after the first kernels have started)
+      for (int k = 0; k < 3 && ok; ++k)
+        for (int64_t q = 0; q < nb && ok; ++q) ok = ao[k * nb + q] + 16 <= base || ao[k * nb + q] >= base + 2 * nb;
+      if (ok) {
+        p->eager_ok = true;
+        p->eager_pix_base = base;
+        p->d_eager_err = p->pool.alloc<double>(1);
+      }
+    }
+  }
   CUDA_OK(cudaDeviceSynchronize());
   clk.lap("create: device structures");
   *out = up.release();
@@ -1743,10 +1777,49 @@ sfx_status sfx_set_values(sfx_problem* p, const double* values, int64_t n) {
     if (hi > lo)
       CUDA_OK(cudaMemcpyAsync(p->d_cur_values + lo, values + lo, sizeof(double) * (hi - lo), cudaMemcpyHostToDevice, p->st));
     NCCL_OK(nccl().AllGather(p->d_cur_values + c * p->a.rank, p->d_cur_values, (size_t)c, ncclDouble, p->comm->comm, p->st));
+  } else if (p->eager_ok) {
+    // everything but the pixels first, then the pixels in chunks on the side stream; the main stream linearizes the
+    // observations of a chunk (into state block kEagerBlock, reading the upload buffer) as soon as its event fires
+    const LinBatch& lb = p->lin[0];
+    const int blocks = linearize_bal_blocks(lb);
+    const int n_chunks = std::max(1, std::min(8, blocks / 1024));
+    while ((int)p->ev_up.size() < n_chunks + 1) {
+      cudaEvent_t e;
+      CUDA_OK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      p->ev_up.push_back(e);
+    }
+    const int64_t pb = p->eager_pix_base, pe = pb + 2 * (int64_t)lb.n;
+    p->eager_valid = false;
+    if (pb > 0) CUDA_OK(cudaMemcpyAsync(p->d_cur_values, values, sizeof(double) * pb, cudaMemcpyHostToDevice, p->st2));
+    if (pe < n)
+      CUDA_OK(cudaMemcpyAsync(p->d_cur_values + pe, values + pe, sizeof(double) * (n - pe), cudaMemcpyHostToDevice, p->st2));
+    CUDA_OK(cudaEventRecord(p->ev_up[0], p->st2));
+    StatePtrs spx = p->sp;
+    spx.values[kEagerBlock] = p->d_cur_values;
+    CUDA_OK(cudaStreamWaitEvent(p->st, p->ev_up[0], 0));
+    launch_zero_lin(p->st, p->d_ctrl, spx, kLinModeEager, p->a.h_accum_values, p->a.N);
+    for (int c = 0; c < n_chunks; ++c) {
+      const int b0 = (int)((int64_t)blocks * c / n_chunks), b1 = (int)((int64_t)blocks * (c + 1) / n_chunks);
+      const int64_t v0 = pb + 2 * 128 * (int64_t)b0, v1 = std::min(pe, pb + 2 * 128 * (int64_t)b1);
+      CUDA_OK(cudaMemcpyAsync(p->d_cur_values + v0, values + v0, sizeof(double) * (v1 - v0), cudaMemcpyHostToDevice, p->st2));
+      CUDA_OK(cudaEventRecord(p->ev_up[c + 1], p->st2));
+      CUDA_OK(cudaStreamWaitEvent(p->st, p->ev_up[c + 1], 0));
+      launch_linearize_bal_range(p->st, p->d_ctrl, spx, kLinModeEager, lb, p->d_partials, b0, b1);
+    }
+    launch_bal_point_finalize(p->st, p->d_ctrl, spx, kLinModeEager, lb);
+    launch_finish_error(p->st, p->d_ctrl, kLinModeEager, p->d_partials, p->n_partials, p->d_eager_err);
+    CUDA_OK(cudaStreamSynchronize(p->st2));
+    CUDA_OK(cudaStreamSynchronize(p->st));
+    p->eager_valid = true;
+    p->lin0_clobbered = true;
+    p->can_continue = false;  // (that state block no longer holds what the last Optimize left)
+    p->values_set = true;
+    return SFX_OK;
   } else {
     CUDA_OK(cudaMemcpyAsync(p->d_cur_values, values, sizeof(double) * n, cudaMemcpyHostToDevice, p->st));
   }
   CUDA_OK(cudaStreamSynchronize(p->st));
+  p->eager_valid = false;
   p->values_set = true;
   SFX_API_END(p)
 }
@@ -1795,6 +1868,8 @@ static sfx_status optimize_impl(sfx_problem* p, int32_t num_iterations, sfx_stat
     }
   }
   p->dbg_valid = dbg && (cont ? p->dbg_valid || p->h_ctrl->n_iters == 0 : true);
+  // the linearization sfx_set_values computed while uploading is the Init linearization of this run
+  const bool adopt = !cont && p->eager_valid && !dbg;
   if (cont) {
     reset_ctrl_continue(p);
   } else {
@@ -1828,7 +1903,10 @@ static sfx_status optimize_impl(sfx_problem* p, int32_t num_iterations, sfx_stat
     }
     launch_lm_begin(p->st, p->d_ctrl);
     if (i == 0) {
-      enqueue_linearize(p, /*mode=*/0);
+      if (adopt)
+        launch_adopt_eager(p->st, p->d_ctrl, p->d_eager_err);
+      else
+        enqueue_linearize(p, /*mode=*/0);
       launch_lm_after_first_linearize(p->st, p->d_ctrl);
       if (dbg) launch_debug_snapshot(p->st, p->d_ctrl, p->sp, 1, a.n_values, a.M, p->dbg_cap, p->dbg_values, p->dbg_res);
       mark(PH_LIN);
@@ -2076,7 +2154,7 @@ sfx_status sfx_get_best_linearization(sfx_problem* p, double* residual, double* 
   SFX_API_BEGIN
   SFX_CHECK(p, SFX_ERR_INVALID_ARG, "null problem");
   const Ctrl& c = *p->h_ctrl;
-  SFX_CHECK(c.best_valid && c.lin_valid[c.best_idx], SFX_ERR_INVALID_ARG,
+  SFX_CHECK(c.best_valid && c.lin_valid[c.best_idx] && !(p->lin0_clobbered && c.best_idx == kEagerBlock), SFX_ERR_INVALID_ARG,
             "SYM_ASSERT: state_.BestIsValid() && Best().GetLinearization().IsInitialized()");
   CUDA_OK(cudaSetDevice(p->device));
   export_linearization(p, c.best_idx, residual, rhs, hessian_values);

@@ -176,7 +176,7 @@ def test_update_best_values_equals_full_copy(name):
 
 @pytest.mark.parametrize("env", ["SFX_SCHUR_V2", "SFX_SCHUR_V1", "SFX_NO_SCHUR_FAST", "SFX_POINT_ATOMICS", "SFX_SOLVE_V1",
                                  "SFX_NO_BAL_FAST", "SFX_KC=1", "SFX_KC=3", "SFX_SOLVE_OVERLAP", "SFX_ND_DEPTH=2",
-                                 "SFX_ND_DEPTH=1"])
+                                 "SFX_ND_DEPTH=1", "SFX_NO_EAGER_LINEARIZE", "SFX_S9_DIAG_ITEMS"])
 def test_alternative_kernel_paths_match_default(env):
     """Every alternative device path kept in the library (generic-dimension Schur kernels, first-generation solves,
     atomics instead of the per-point sum, other panel widths of the tile-DAG Cholesky) reproduces the default path's
@@ -410,3 +410,38 @@ def test_fused_factor_launch_matches_oracle(plan, monkeypatch):
         assert a.new_error == pytest.approx(b.new_error, rel=1e-9)
     assert gpu.info()["chol_failures"] == 0
     gpu.close()
+
+
+def test_eager_linearization_follows_the_uploaded_values():
+    """sfx_set_values linearizes the uploaded values while the upload is still running (BAL fast path) and the next
+    sfx_optimize adopts that linearization: a second upload of OTHER values, API calls between upload and optimize, and a
+    continued optimization must all behave as without it."""
+    prob = P.bal_problem("ladybug", solver=D.SOLVER_SCHUR)
+    cpu = O.OracleProblem(prob)
+    st_c = cpu.optimize()
+    want = [(it.new_error, it.update_accepted) for it in cpu.iterations()]
+    g = capi.SfxProblem(prob)
+    # (1) perturbed values first, then the real ones: the adopted linearization must be the second upload's
+    other = prob.values.copy()
+    other[-2000:-1] += 0.05
+    g.set_values(other)
+    g.set_values(prob.values)
+    g.optimize()
+    got = [(it.new_error, it.update_accepted) for it in g.iterations()]
+    assert len(got) == len(want)
+    for (e1, a1), (e0, a0) in zip(got, want):
+        assert a1 == a0 and abs(e1 - e0) <= COST_TOL * abs(e0)
+    # (2) an export between upload and optimize resets the state: the plain path must take over
+    g.set_values(prob.values)
+    res, rhs, H = g.linearize()
+    g.optimize()
+    got2 = [(it.new_error, it.update_accepted) for it in g.iterations()]
+    assert [a for _, a in got2] == [a for _, a in want]
+    assert abs(got2[-1][0] - want[-1][0]) <= COST_TOL * abs(want[-1][0])
+    # (3) optimize twice from one upload: the second run re-linearizes by itself
+    g.set_values(prob.values)
+    g.optimize(2)
+    g.optimize()
+    got3 = [(it.new_error, it.update_accepted) for it in g.iterations()]
+    assert len(got3) == len(want) and abs(got3[-1][0] - want[-1][0]) <= COST_TOL * abs(want[-1][0])
+    g.close()

@@ -582,6 +582,7 @@ void analyze_problem(const sfx_problem_desc& d, Analysis& a) {
       off += (int64_t)a.nodes[row].dim * a.nodes[col].dim;
     }
   }
+  off = (off + 15) & ~(int64_t)15;  // the exclusive blocks start on a 128-byte boundary (bulk copies stream them)
   a.h_accum_values = off;
   for (size_t c = 0; c < contribs.size(); ++c) {  // contribs are in (plan, slot, pair) order
     int b = contrib_blk[c];

@@ -1219,6 +1219,46 @@ __global__ void __launch_bounds__(kSchurWarps * 32) schur_s_dmma_kernel(const Ct
       }
 }
 
+// ---- TMA (cp.async.bulk, 1-D) + mbarrier helpers of the streamed kernels -----------------------------------------
+constexpr int kTmaSlots = 128;   // slots per tile (27,648 B)
+#ifndef SFX_TMA_STAGES
+#define SFX_TMA_STAGES 2
+#endif
+#ifndef SFX_TMA_CTAS
+#define SFX_TMA_CTAS 3
+#endif
+// measured at Final-shape (1.08 GB of E blocks): 4 stages x 2 CTAs per SM 0.243 ms, 3 x 2 0.243, 2 x 4 0.216, 2 x 3 0.210
+// (5.7 TB/s); the per-entry kernel it replaces: 0.291 ms
+constexpr int kTmaStages = SFX_TMA_STAGES;
+constexpr int kTmaCtas = SFX_TMA_CTAS;
+constexpr int kTmaTileBytes = kTmaSlots * 27 * 8;
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
 // ---- K3 fast path, v2 ------------------------------------------------------------------------------
 // (1) schur_w_rhs_kernel: W = L^-1 E (whitened point-camera blocks, written to the second buffer at the
 //     offsets of E) and the reduced rhs v_I - sum W^T u.  A warp's 32 blocks are one contiguous run in
@@ -1707,6 +1747,75 @@ __global__ void __launch_bounds__(kGThreads) schur_back_accum_kernel(const Ctrl*
   atomicAdd(sd.sl + (size_t)l * 3 + 1, s1);
   atomicAdd(sd.sl + (size_t)l * 3 + 2, s2);
 }
+// ---- TMA-streamed variant of schur_back_accum_kernel ------------------------------------------------------------
+// Persistent CTAs walk the slot array of H's camera columns (SchurDev::slot_*) tile by tile: one thread issues a
+// cp.async.bulk (TMA, 1-D) of the next tile into a shared-memory ring and arms the stage's mbarrier with the byte
+// count; all threads wait on the barrier's phase, take one slot each (27 doubles at stride 27: conflict-free), and a
+// block barrier hands the stage back to the producer.  No registers or load instructions are spent on the stream.
+__global__ void __launch_bounds__(kTmaSlots, kTmaCtas) schur_back_accum_tma_kernel(const Ctrl* __restrict__ ctrl, StatePtrs sp,
+                                                                            SchurDev sd, const double* __restrict__ y) {
+  extern __shared__ __align__(128) unsigned char tma_smem[];
+  double* ring = reinterpret_cast<double*>(tma_smem);
+  __shared__ __align__(8) uint64_t full[kTmaStages];
+  if (ctrl->done) return;
+  const double* __restrict__ H = sp.H[ctrl->init_idx] + sd.slot_base;
+  const int n_tiles = (sd.n_slots + kTmaSlots - 1) / kTmaSlots;
+  const int tid = threadIdx.x;
+  auto tile_bytes = [&](int t) {
+    const int ns = min(kTmaSlots, sd.n_slots - t * kTmaSlots);
+    return (uint32_t)((ns * 27 * 8 + 15) & ~15);  // (an odd tail reads 8 bytes into the landmark blocks behind)
+  };
+  if (tid == 0) {
+    for (int s = 0; s < kTmaStages; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (tid == 0) {
+    for (int s = 0; s < kTmaStages; ++s) {
+      const int t = blockIdx.x + s * gridDim.x;
+      if (t < n_tiles) {
+        mbar_expect_tx(&full[s], tile_bytes(t));
+        tma_load_1d(ring + (size_t)s * kTmaSlots * 27, H + (size_t)t * kTmaSlots * 27, tile_bytes(t), &full[s]);
+      }
+    }
+  }
+  int it = 0;
+  for (int t = blockIdx.x; t < n_tiles; t += gridDim.x, ++it) {
+    const int s = it % kTmaStages;
+    const uint32_t parity = (it / kTmaStages) & 1;
+    const int slot = t * kTmaSlots + tid;
+    int l = -1, I = 0;
+    if (slot < sd.n_slots) {
+      l = __ldg(sd.slot_lm + slot);
+      I = __ldg(sd.slot_node + slot);
+    }
+    mbar_wait(&full[s], parity);
+    if (l >= 0) {
+      const double* e = ring + (size_t)s * kTmaSlots * 27 + tid * 27;
+      const double* yi = y + sd.node_toff[I];
+      double s0 = 0, s1 = 0, s2 = 0;
+#pragma unroll
+      for (int c = 0; c < 9; ++c) {
+        const double yc = __ldg(yi + c);
+        s0 += e[3 * c] * yc;
+        s1 += e[3 * c + 1] * yc;
+        s2 += e[3 * c + 2] * yc;
+      }
+      atomicAdd(sd.sl + (size_t)l * 3, s0);
+      atomicAdd(sd.sl + (size_t)l * 3 + 1, s1);
+      atomicAdd(sd.sl + (size_t)l * 3 + 2, s2);
+    }
+    __syncthreads();  // every thread is done with the stage
+    if (tid == 0) {
+      const int tn = t + kTmaStages * gridDim.x;
+      if (tn < n_tiles) {
+        mbar_expect_tx(&full[s], tile_bytes(tn));
+        tma_load_1d(ring + (size_t)s * kTmaSlots * 27, H + (size_t)tn * kTmaSlots * 27, tile_bytes(tn), &full[s]);
+      }
+    }
+  }
+}
+
 __global__ void schur_back_final_kernel(const Ctrl* __restrict__ ctrl, SchurDev sd, const double* __restrict__ y,
                                         double* __restrict__ upd) {
   if (ctrl->done) return;
@@ -1738,6 +1847,9 @@ void launch_schur(cudaStream_t st, const Ctrl* ctrl, StatePtrs sp, const SchurDe
     if (sd.wl != nullptr) {
       if (sd.items3 != nullptr && sd.s_diag_off != nullptr) {
         schur_diag_init_kernel<<<(sd.n_reduced_nodes * 81 + 255) / 256, 256, 0, st>>>(ctrl, sp, sd, dvec); ++g_launches;
+        // (a cp.async.bulk-streamed variant of this kernel -- two-stage ring, whitening in place, bulk store of W -- was
+        // measured at 0.69 ms with three and 0.63 ms with four CTAs per SM against 0.62 ms: the kernel is bound by its
+        // per-tile shared-memory work and the read/write mix, not by load issue; see profiles/r02_results.md)
         schur_w_rhs_kernel<true><<<(sd.n_entries + kWThreads * kWChunks - 1) / (kWThreads * kWChunks), kWThreads, 0, st>>>(ctrl, sp, sd);
         ++g_launches;
       } else {
@@ -1766,7 +1878,19 @@ void launch_schur_back(cudaStream_t st, const Ctrl* ctrl, StatePtrs sp, const Sc
                        double* upd) {
   int n = sd.n_landmarks > sd.reduced_dim ? sd.n_landmarks : sd.reduced_dim;
   if (sd.fast3) {
-    schur_back_accum_kernel<<<(sd.n_entries + kGThreads - 1) / kGThreads, kGThreads, 0, st>>>(ctrl, sp, sd, y);
+    if (sd.n_slots > 0) {
+      static bool configured = false;
+      const int smem = kTmaStages * kTmaTileBytes;
+      if (!configured) {
+        cudaFuncSetAttribute(schur_back_accum_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        configured = true;
+      }
+      const int n_tiles = (sd.n_slots + kTmaSlots - 1) / kTmaSlots;
+      const int grid = n_tiles < 148 * kTmaCtas ? n_tiles : 148 * kTmaCtas;
+      schur_back_accum_tma_kernel<<<grid, kTmaSlots, smem, st>>>(ctrl, sp, sd, y);
+    } else {
+      schur_back_accum_kernel<<<(sd.n_entries + kGThreads - 1) / kGThreads, kGThreads, 0, st>>>(ctrl, sp, sd, y);
+    }
     ++g_launches;
     schur_back_final_kernel<<<(n + 127) / 128, 128, 0, st>>>(ctrl, sd, y, upd); ++g_launches;
     return;

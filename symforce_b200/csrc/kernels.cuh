@@ -99,6 +99,12 @@ struct SchurDev {
   const int32_t *pm_i, *pm_j;  // s9: match offsets, 64 slots per item, unused slots -> zero block behind W
   const int32_t* item_toI;     // v3: tangent offset of the row node (damping of diagonal blocks)
   const void* items2;  // v2: packed 32-byte item headers (SItem2 in kernels.cu)
+  // slot view of the camera columns of H (BAL shape: every block there is 27 doubles or the 81 = 3 x 27 doubles of a
+  // camera's diagonal block, so the region is an array of 27-double slots that bulk copies stream tile by tile)
+  const int32_t* slot_lm;    // per slot: landmark of the E block in it, -1 for the slots of a diagonal block
+  const int32_t* slot_node;  // per slot: reduced node (camera) of the column it belongs to
+  int n_slots;               // 0: the blocks are not laid out that way, per-entry kernels are used
+  int64_t slot_base;         // offset of slot 0 in H (even: bulk copies need 16-byte aligned sources)
   double* sl;  // [n_landmarks][3] back-substitution accumulators
   double* cinv;   // [n_landmarks][9]
   double* tl;     // [n_landmarks][3]

@@ -6,7 +6,9 @@
 #include <algorithm>
 #include <chrono>
 #include <cmath>
+#include <array>
 #include <cstdio>
+#include <map>
 #include <cstdlib>
 #include <cstring>
 #include <functional>
@@ -524,6 +526,8 @@ double build_fused_schedule(const std::vector<LargeFront>& lfs, int lf_begin, in
   std::priority_queue<Ev, std::vector<Ev>, std::greater<Ev>> chain_end;  // ends of the last steps of sticky chains
   const bool util_bins = getenv("SFX_TIMING") && atoi(getenv("SFX_TIMING")) >= 2;  // modelled utilisation per 100 us
   std::vector<double> util;
+  std::vector<std::array<double, 11>> util_type;
+  std::vector<std::map<int, double>> util_lf;
   while (started < n) {
     bool moved = false;
     while (!avail.empty() && avail.top().first <= now) {
@@ -553,6 +557,10 @@ double build_fused_schedule(const std::vector<LargeFront>& lfs, int lf_begin, in
           const size_t b = (size_t)(t / 100.0);
           if (b >= util.size()) util.resize(b + 1, 0.0);
           util[b] += std::min(10.0, now + g[id].dur - t);
+          if (b >= util_type.size()) util_type.resize(b + 1);
+          util_type[b][g[id].t.type] += std::min(10.0, now + g[id].dur - t);
+          if (b >= util_lf.size()) util_lf.resize(b + 1);
+          util_lf[b][g[id].t.lf] += std::min(10.0, now + g[id].dur - t);
         }
       }
       // DIAG(0) of a sticky chain keeps its CTA until the chain's last step ends (a one-step chain: like any task)
@@ -589,6 +597,16 @@ double build_fused_schedule(const std::vector<LargeFront>& lfs, int lf_begin, in
     std::fprintf(stderr, "[sfx analysis] modelled busy CTAs per 100 us:");
     for (double u : util) std::fprintf(stderr, " %.0f", u / 100.0);
     std::fprintf(stderr, "\n");
+    if (atoi(getenv("SFX_TIMING")) >= 3)
+      for (size_t b = 0; b < util_type.size(); ++b) {
+        std::fprintf(stderr, "[sfx analysis]   bin %2zu: by type", b);
+        for (int ty = 1; ty < 11; ++ty)
+          if (util_type[b][ty] > 50.0) std::fprintf(stderr, " t%d=%.0f", ty, util_type[b][ty] / 100.0);
+        std::fprintf(stderr, " | by front");
+        for (auto& kv : util_lf[b])
+          if (kv.second > 300.0) std::fprintf(stderr, " f%d(w%d)=%.0f", kv.first, lfs[kv.first].w, kv.second / 100.0);
+        std::fprintf(stderr, "\n");
+      }
   }
   if (getenv("SFX_TIMING")) {
     double busy[11] = {0};
@@ -1082,7 +1100,7 @@ void upload_structures(sfx_problem* p) {
   // state
   for (int b = 0; b < 3; ++b) {
     p->sp.values[b] = P.alloc<double>(a.n_values);
-    p->sp.H[b] = P.alloc<double>(a.H.n_values);
+    p->sp.H[b] = P.alloc<double>(a.H.n_values + 2);  // (+2: a bulk copy of an odd tail reads 8 bytes further)
     p->sp.rhs[b] = P.alloc<double>(a.N);
     p->sp.res[b] = P.alloc<double>(a.M);
   }
@@ -1272,6 +1290,37 @@ void upload_structures(sfx_problem* p) {
       d.wl = (fast && !getenv("SFX_SCHUR_V1")) ? P.alloc<double>((size_t)s.n_landmarks * 9) : nullptr;
       d.zeros = P.upload(std::vector<double>(8, 0.0));
       d.sl = P.alloc<double>((size_t)s.n_landmarks * 3);
+      // slot view for the TMA-streamed kernels: every E block of an own landmark on a multiple of 27 doubles, every
+      // reduced node 9-dimensional, and nothing but such blocks and the 81-double camera diagonal blocks before the
+      // last of them
+      d.n_slots = 0;
+      d.slot_base = 0;
+      bool slots = fast && !getenv("SFX_NO_TMA") && !s.r_eoff.empty();
+      for (int i = 0; i < s.first_lm_node && slots; ++i) slots = a.nodes[i].dim == 9;
+      int64_t first = INT64_MAX, last = 0;
+      for (size_t q = 0; q < s.r_eoff.size(); ++q) {
+        first = std::min<int64_t>(first, s.r_eoff[q]);
+        last = std::max<int64_t>(last, s.r_eoff[q]);
+      }
+      slots = slots && first % 2 == 0;  // 16-byte aligned source of the bulk copies
+      for (size_t q = 0; q < s.r_eoff.size() && slots; ++q) slots = (s.r_eoff[q] - first) % 27 == 0;
+      if (slots) {
+        const int64_t ns = (last - first) / 27 + 1;
+        // (an odd number of slots makes the last bulk copy read 8 bytes past the last block: keep them inside H)
+        slots = ns < (int64_t)INT32_MAX / 32 && first + ns * 27 <= a.H.n_values + 1 && ns <= 2 * (int64_t)s.r_eoff.size();
+        if (slots) {
+          std::vector<int32_t> slm((size_t)ns, -1), snode((size_t)ns, 0);
+          for (int j = 0; j < s.first_lm_node; ++j)
+            for (int q = s.r_ptr[j]; q < s.r_ptr[j + 1]; ++q) {
+              slm[(s.r_eoff[q] - first) / 27] = s.r_lm[q];
+              snode[(s.r_eoff[q] - first) / 27] = j;
+            }
+          d.slot_lm = P.upload(slm);
+          d.slot_node = P.upload(snode);
+          d.n_slots = (int)ns;
+          d.slot_base = first;
+        }
+      }
     }
   }
   // fronts

@@ -1230,7 +1230,9 @@ void upload_structures(sfx_problem* p) {
               diag_off[srow[b]] = s.S.blk_off[b];
               diag_bsrc[srow[b]] = s.s_b_src[b];
             }
-          bool fuse_diag = !getenv("SFX_S9_DIAG_ITEMS");
+          // (with few cameras the REDs of all warps meet on a handful of blocks: Ladybug-shape, 49 cameras, is 0.023 ms
+          // per iteration slower with the fusion than without)
+          bool fuse_diag = !getenv("SFX_S9_DIAG_ITEMS") && (s.first_lm_node >= 256 || getenv("SFX_S9_DIAG_FUSE"));
           for (int i = 0; i < s.first_lm_node && fuse_diag; ++i) fuse_diag = diag_off[i] >= 0;
           std::vector<size_t> keep;  // items of the persistent kernel
           for (size_t q = 0; q < ib.size(); ++q)

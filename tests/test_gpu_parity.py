@@ -176,7 +176,7 @@ def test_update_best_values_equals_full_copy(name):
 
 @pytest.mark.parametrize("env", ["SFX_SCHUR_V2", "SFX_SCHUR_V1", "SFX_NO_SCHUR_FAST", "SFX_POINT_ATOMICS", "SFX_SOLVE_V1",
                                  "SFX_NO_BAL_FAST", "SFX_KC=1", "SFX_KC=3", "SFX_SOLVE_OVERLAP", "SFX_ND_DEPTH=2",
-                                 "SFX_ND_DEPTH=1", "SFX_NO_EAGER_LINEARIZE", "SFX_S9_DIAG_ITEMS"])
+                                 "SFX_ND_DEPTH=1", "SFX_NO_EAGER_LINEARIZE", "SFX_S9_DIAG_FUSE"])
 def test_alternative_kernel_paths_match_default(env):
     """Every alternative device path kept in the library (generic-dimension Schur kernels, first-generation solves,
     atomics instead of the per-point sum, other panel widths of the tile-DAG Cholesky) reproduces the default path's

@@ -298,9 +298,11 @@ __device__ __forceinline__ int value_of_lane(int lane) {
 }
 
 constexpr int kBalThreads = 128;
-// per-observation point contribution: 6 + 3 doubles (padding to 10 for aligned 16-byte gather loads was measured:
-// slower, 0.84 vs 0.81 ms per linearization at Final-shape)
-constexpr int kPbufStride = 9;
+// per-observation point record: the 2 x 3 point Jacobian and the residual, 8 doubles = two whole 32-byte sectors of a
+// 64-byte aligned slot.  bal_point_finalize_kernel forms J_p^T J_p and J_p^T r from it (18 FMAs per observation) with two
+// 32-byte loads; the 9-double record of the products it replaces made every gathered slot touch three or four sectors
+// (0.70 GB of DRAM reads for 0.36 GB of records).
+constexpr int kPbufStride = 8;
 #ifndef SFX_BAL_MINB
 #define SFX_BAL_MINB 5  // 96 registers, 68 B of spills: 0.83 -> 0.80 ms at final-shape (6: 80 registers, slower)
 #endif
@@ -424,17 +426,10 @@ __global__ void __launch_bounds__(kBalThreads, SFX_BAL_MINB) linearize_bal_kerne
     // per-observation contribution (6 lower entries + 3 rhs) written coalesced; summed per point by
     // bal_point_finalize_kernel (no atomics on the 12 scattered point values of every observation)
     double* st = stage[warp];
-    {
-      int q = 0;
 #pragma unroll
-      for (int c = 0; c < 3; ++c)
-#pragma unroll
-        for (int r = c; r < 3; ++r)
-          st[lane * kPbufStride + q++] = J[2 * (9 + r)] * J[2 * (9 + c)] + J[2 * (9 + r) + 1] * J[2 * (9 + c) + 1];
-#pragma unroll
-      for (int r = 0; r < 3; ++r)
-        st[lane * kPbufStride + 6 + r] = J[2 * (9 + r)] * res[0] + J[2 * (9 + r) + 1] * res[1];
-    }
+    for (int q = 0; q < 6; ++q) st[lane * kPbufStride + q] = J[18 + q];
+    st[lane * kPbufStride + 6] = res[0];
+    st[lane * kPbufStride + 7] = res[1];
     __syncwarp();
     double* dst = b.pbuf + (size_t)(cta * kBalThreads + warp * 32) * kPbufStride;
 #pragma unroll
@@ -500,8 +495,16 @@ __global__ void __launch_bounds__(128) bal_point_finalize_kernel(const Ctrl* __r
   const int q1 = __ldg(b.pf_ptr + pt + 1);
   for (int q = __ldg(b.pf_ptr + pt); q < q1; ++q) {
     const double* __restrict__ src = b.pbuf + (size_t)__ldg(b.pf_slot + q) * kPbufStride;
+    double j[8];  // J[2 c + i] = d res_i / d x_c for the point columns c = 0..2, then res
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(j[0]), "=d"(j[1]), "=d"(j[2]), "=d"(j[3]) : "l"(src));
+    asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(j[4]), "=d"(j[5]), "=d"(j[6]), "=d"(j[7]) : "l"(src + 4));
+    int o = 0;
 #pragma unroll
-    for (int i = 0; i < 9; ++i) a[i] += src[i];
+    for (int c = 0; c < 3; ++c)
+#pragma unroll
+      for (int r = c; r < 3; ++r) a[o++] += j[2 * r] * j[2 * c] + j[2 * r + 1] * j[2 * c + 1];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) a[6 + r] += j[2 * r] * j[6] + j[2 * r + 1] * j[7];
   }
   double* Hd = sp.H[blk] + __ldg(b.pf_diag + pt);
   double* rh = sp.rhs[blk] + __ldg(b.pf_rhs + pt);

@@ -1088,7 +1088,7 @@ void upload_structures(sfx_problem* p) {
         lb.pf_slot = P.upload(order);
         lb.pf_diag = P.upload(diag);
         lb.pf_rhs = P.upload(rhs);
-        lb.pbuf = P.alloc<double>((size_t)((bp.n + 127) / 128) * 128 * 10);  // kPbufStride
+        lb.pbuf = P.alloc<double>((size_t)((bp.n + 127) / 128) * 128 * 8);  // kPbufStride (kernels.cu); 256-byte aligned
       }
     }
     lb.partial_base = partial_base;

@@ -645,6 +645,17 @@ void launch_zero_lin(cudaStream_t st, const Ctrl* ctrl, StatePtrs sp, int mode, 
   zero_lin_kernel<<<grid, 256, 0, st>>>(ctrl, sp, mode, n_h, n_rhs); ++g_launches;
 }
 
+// multiprocessors of the current device (grid-stride / persistent launches are sized in multiples of it)
+static int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+
 int g_lin_skip = 0;  // debug (sfx_debug_time_linearize): parts of linearize_bal_kernel to leave out
 // BAL fast path over the CTAs [block0, block1) of the batch (128 observations each), without the per-point sums
 void launch_linearize_bal_range(cudaStream_t st, const Ctrl* ctrl, StatePtrs sp, int mode, const LinBatch& b, double* partials,
@@ -1859,7 +1870,7 @@ void launch_schur(cudaStream_t st, const Ctrl* ctrl, StatePtrs sp, const SchurDe
         schur_w_rhs_kernel<false><<<(sd.n_entries + kWThreads - 1) / kWThreads, kWThreads, 0, st>>>(ctrl, sp, sd); ++g_launches;
       }
       if (sd.items3 != nullptr) {
-        int grid = 148 * SFX_S9_MINB;
+        int grid = sm_count() * SFX_S9_MINB;
         if (grid * kS9Warps > sd.n_items3) grid = (sd.n_items3 + kS9Warps - 1) / kS9Warps;
         if (grid > 0) { schur_s9_kernel<<<grid, kS9Warps * 32, 0, st>>>(ctrl, sp, sd, dvec); ++g_launches; }
         return;
@@ -1889,7 +1900,7 @@ void launch_schur_back(cudaStream_t st, const Ctrl* ctrl, StatePtrs sp, const Sc
         configured = true;
       }
       const int n_tiles = (sd.n_slots + kTmaSlots - 1) / kTmaSlots;
-      const int grid = n_tiles < 148 * kTmaCtas ? n_tiles : 148 * kTmaCtas;
+      const int grid = n_tiles < sm_count() * kTmaCtas ? n_tiles : sm_count() * kTmaCtas;
       schur_back_accum_tma_kernel<<<grid, kTmaSlots, smem, st>>>(ctrl, sp, sd, y);
     } else {
       schur_back_accum_kernel<<<(sd.n_entries + kGThreads - 1) / kGThreads, kGThreads, 0, st>>>(ctrl, sp, sd, y);

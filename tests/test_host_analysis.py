@@ -293,3 +293,35 @@ def test_dissect_then_sweep_ordering_reproduces_oracle(name, depth, monkeypatch)
     upd, (res, rhs, H) = E.emulate_solve_step(prob, A, 0.37)
     upd_o = o.solve_step(0.37)
     assert np.allclose(upd, upd_o, rtol=1e-8, atol=1e-9 * max(1e-3, np.abs(upd_o).max()))
+
+
+def test_plan_search_on_a_camera_ring(monkeypatch):
+    """choose_front_plan (sfx_api.cu) on a 320-camera ring: the METIS_NodeND plan and the dissect-then-sweep candidates
+    are all planned for 296 resident CTAs, their fused task lists pass verify_fused_list (every wait condition of the
+    tile-DAG kernel holds in list order), and the search never keeps a plan the model rates slower than the reference's."""
+    import ctypes as C
+    import re
+
+    prob = P.bal_problem(n_cams=320, n_pts=6000, n_obs=26000, window=12, solver=D.SOLVER_SCHUR)
+    lib = capi.load()
+    d, keep = prob.desc(rank=0, world=1, comm=None)
+    res = (C.c_int64 * 6)()
+    assert lib.sfx_debug_large_plan(C.byref(d), 296, res) == 0, lib.sfx_last_error(None).decode()
+    fused_T0, n_large, n_tasks, n_fused = res[0], res[1], res[2], res[3]
+    assert fused_T0 == 0 and n_large >= 3 and n_fused == n_tasks > 0
+    monkeypatch.setenv("SFX_ORDERING_SEARCH", "0")
+    res0 = (C.c_int64 * 6)()
+    assert lib.sfx_debug_large_plan(C.byref(d), 296, res0) == 0
+    assert res0[0] == 0 and res0[3] > 0
+
+
+def test_exclusive_blocks_start_on_a_128_byte_boundary():
+    """The landmark-camera blocks only one factor writes come last in H, in observation order, and start on a multiple
+    of 16 doubles: the TMA-streamed kernels copy them in 27,648-byte tiles (cp.async.bulk needs 16-byte aligned sources)."""
+    for prob in (P.bal_problem("tiny", solver=D.SOLVER_SCHUR), P.bal_problem("small", solver=D.SOLVER_SCHUR),
+                 P.bal_problem(n_cams=7, n_pts=31, n_obs=100, window=3, solver=D.SOLVER_SCHUR)):
+        A = capi.analysis_json(prob)
+        assert A["h_accum_values"] % 16 == 0
+        eoff = np.array(A["schur_plan"]["r_eoff"])
+        assert eoff.min() == A["h_accum_values"]
+        assert np.array_equal(np.sort(eoff), A["h_accum_values"] + 27 * np.arange(eoff.shape[0]))

@@ -2023,6 +2023,86 @@ __global__ void __launch_bounds__(kFrontThreads) front_factor_kernel(Ctrl* ctrl,
   }
 }
 
+// One WARP per front for levels whose fronts have at most 32 rows (pose-graph leaves and their parents: 6-12 pivots,
+// a few dozen rows; tens of thousands of them per level): the front lives in an 8 KB slice of shared memory, lane i owns
+// row i, every step is warp-synchronous (no block barrier), and a CTA of four warps works on four fronts.  Same
+// operations on every entry in the same order as front_factor_kernel (updates of an entry arrive by increasing pivot).
+constexpr int kWarpFrontM = kWarpFrontRows;
+constexpr int kWarpFrontWarps = 4;
+__global__ void __launch_bounds__(kWarpFrontWarps * 32) front_factor_warp_kernel(Ctrl* ctrl, FrontDev fd,
+                                                                                  const double* __restrict__ sys_static,
+                                                                                  StatePtrs sp, int use_state_H,
+                                                                                  const double* __restrict__ dvec,
+                                                                                  int lvl_begin, int lvl_count) {
+  __shared__ double smem_f[kWarpFrontWarps][kWarpFrontM * kWarpFrontM];
+  if (ctrl->done) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int fi = blockIdx.x * kWarpFrontWarps + warp;
+  if (fi >= lvl_count) return;
+  const int s = fd.level_fronts[lvl_begin + fi];
+  const int w = fd.f_w[s], u = fd.f_u[s], m = w + u;
+  const double* sys = use_state_H ? sp.H[ctrl->init_idx] : sys_static;
+  double* Fg = fd.fronts + fd.f_off[s];
+  double* F = smem_f[warp];
+  const int ld = m;
+  for (int i = lane; i < m * m; i += 32) F[i] = 0.0;
+  __syncwarp();
+  for (int ci = fd.f_copy_ptr[s]; ci < fd.f_copy_ptr[s + 1]; ++ci) {
+    const FrontCopy c = fd.copies[ci];
+    const int ne = c.rows * c.cols;
+    for (int e = lane; e < ne; e += 32) {
+      const int r = e % c.rows, cc = e / c.rows;
+      if (c.lower_only && r < cc) continue;
+      const double v = sys[c.src + r + (int64_t)cc * c.src_ld];
+      if (c.transposed)
+        F[(c.dst_row + cc) + (c.dst_col + r) * ld] += v;
+      else
+        F[(c.dst_row + r) + (c.dst_col + cc) * ld] += v;
+    }
+    __syncwarp();  // (two blocks of a front never overlap, but keep the order of the block-barrier kernel)
+  }
+  if (dvec != nullptr && lane < w) F[lane + lane * ld] += dvec[fd.scalar_perm[fd.f_piv[s] + lane]];
+  __syncwarp();
+  for (int ci = fd.f_child_ptr[s]; ci < fd.f_child_ptr[s + 1]; ++ci) {
+    const int c = fd.f_child[ci];
+    const int wc = fd.f_w[c], uc = fd.f_u[c], mc = wc + uc;
+    const double* U = fd.fronts + fd.f_off[c] + wc + (size_t)wc * mc;
+    const int32_t* rel = fd.f_rel + fd.f_rows_ptr[c];
+    for (int e = lane; e < uc * uc; e += 32) {
+      const int i = e % uc, j = e / uc;
+      if (i < j) continue;
+      F[rel[i] + rel[j] * ld] += U[i + (size_t)j * mc];
+    }
+    __syncwarp();
+  }
+  // partial Cholesky, right-looking, lane = row
+  for (int k = 0; k < w; ++k) {
+    double d = F[k + k * ld];
+    if (!(d > 0.0)) {
+      ctrl->chol_fail = 1;
+      d = __longlong_as_double(0x7ff8000000000000LL);
+    }
+    const double piv = sqrt(d);
+    __syncwarp();
+    double lik = 0.0;
+    if (lane == k) F[k + k * ld] = piv;
+    if (lane > k && lane < m) {
+      lik = F[lane + k * ld] / piv;
+      F[lane + k * ld] = lik;
+    }
+    __syncwarp();
+    for (int j = k + 1; j < m; ++j) {
+      const double ljk = F[j + k * ld];
+      if (lane >= j && lane < m) F[lane + j * ld] -= lik * ljk;
+    }
+    __syncwarp();
+  }
+  for (int e = lane; e < m * m; e += 32) {
+    const int i = e % m, j = e / m;
+    if (i >= j) Fg[e] = F[e];
+  }
+}
+
 // Threads per CTA of the one-CTA-per-front kernels: levels of tiny fronts (pose-graph leaves: 6 pivots, a few dozen
 // rows) run more fronts per SM with 64 or 128 threads than with 256 mostly idle ones
 static int small_front_threads(int max_m) { return max_m <= 32 ? 64 : max_m <= 64 ? 128 : kFrontThreads; }
@@ -2030,6 +2110,13 @@ static int small_front_threads(int max_m) { return max_m <= 32 ? 64 : max_m <= 6
 void launch_front_factor(cudaStream_t st, Ctrl* ctrl, const FrontDev& fd, const double* sysvals_static, StatePtrs sp,
                          int use_state_H, const double* dvec, int lvl_begin, int lvl_count, int smem_m_max) {
   // smem_m_max: fronts with m <= smem_m_max are factored in shared memory (chosen per launch)
+  static const bool no_warp_fronts = getenv("SFX_NO_WARP_FRONTS") != nullptr;  // A/B knob
+  if (smem_m_max <= kWarpFrontM && !no_warp_fronts) {
+    front_factor_warp_kernel<<<(lvl_count + kWarpFrontWarps - 1) / kWarpFrontWarps, kWarpFrontWarps * 32, 0, st>>>(
+        ctrl, fd, sysvals_static, sp, use_state_H, dvec, lvl_begin, lvl_count);
+    ++g_launches;
+    return;
+  }
   const size_t smem = (size_t)smem_m_max * smem_m_max * sizeof(double);
   front_factor_kernel<<<lvl_count, small_front_threads(smem_m_max), smem, st>>>(ctrl, fd, sysvals_static, sp, use_state_H,
                                                                                 dvec, lvl_begin, smem_m_max); ++g_launches;

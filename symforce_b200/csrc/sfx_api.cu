@@ -179,6 +179,8 @@ struct sfx_problem {
   FrontDev fd{};
   std::vector<int> lvl_max_m;      // largest SMALL front per level
   std::vector<int> lvl_small_cnt;  // small fronts per level (listed first in level_fronts)
+  std::vector<int> lvl_tiny_cnt;   // ... of which the first ones have at most 32 rows (one warp per front)
+  std::vector<int> lvl_rest_max_m; // largest small front per level that is not tiny
   std::vector<LargeLevel> lvl_large;
   LargeDev ld{};
   int64_t n_counters = 0, n_sflags = 0;
@@ -784,6 +786,8 @@ void plan_large_fronts(sfx_problem* p, int workers, LargeHostPlan& hp) {
   lvl_fronts = f.level_fronts;
   p->lvl_max_m.assign(f.n_levels, 0);
   p->lvl_small_cnt.assign(f.n_levels, 0);
+  p->lvl_tiny_cnt.assign(f.n_levels, 0);
+  p->lvl_rest_max_m.assign(f.n_levels, 0);
   p->lvl_large.assign(f.n_levels, LargeLevel{});
   std::vector<LargeFront>& lfs = hp.lfs;
   std::vector<LargeTask>& tasks = hp.tasks;
@@ -816,6 +820,9 @@ void plan_large_fronts(sfx_problem* p, int workers, LargeHostPlan& hp) {
     int* mid = std::stable_partition(b, e, is_small);
     p->lvl_small_cnt[l] = (int)(mid - b);
     for (int* q = b; q < mid; ++q) p->lvl_max_m[l] = std::max(p->lvl_max_m[l], f.f_w[*q] + f.f_u[*q]);
+    int* tiny_end = std::stable_partition(b, mid, [&](int s) { return f.f_w[s] + f.f_u[s] <= kWarpFrontRows; });
+    p->lvl_tiny_cnt[l] = (int)(tiny_end - b);
+    for (int* q = tiny_end; q < mid; ++q) p->lvl_rest_max_m[l] = std::max(p->lvl_rest_max_m[l], f.f_w[*q] + f.f_u[*q]);
     LargeLevel& lv = p->lvl_large[l];
     lv.lf0 = (int)lfs.size();
     lv.n_lf = (int)(e - mid);
@@ -1557,9 +1564,12 @@ bool enqueue_factorize(sfx_problem* p, int overlap_T = 0, const double* rhs_stat
       enqueue_fwd_levels(p, p->st2, 0, overlap_T, rhs_static, use_state_rhs);
       CUDA_OK(cudaEventRecord(p->ev_join2, p->st2));
     }
-    if (p->lvl_small_cnt[l] > 0)
-      launch_front_factor(p->st, p->d_ctrl, p->fd, sys, p->sp, use_H, dv, f.level_ptr[l], p->lvl_small_cnt[l],
-                          p->lvl_max_m[l]);
+    // small fronts: the ones with at most 32 rows one warp each, the others one CTA each
+    if (p->lvl_tiny_cnt[l] > 0)
+      launch_front_factor(p->st, p->d_ctrl, p->fd, sys, p->sp, use_H, dv, f.level_ptr[l], p->lvl_tiny_cnt[l], kWarpFrontRows);
+    if (p->lvl_small_cnt[l] > p->lvl_tiny_cnt[l])
+      launch_front_factor(p->st, p->d_ctrl, p->fd, sys, p->sp, use_H, dv, f.level_ptr[l] + p->lvl_tiny_cnt[l],
+                          p->lvl_small_cnt[l] - p->lvl_tiny_cnt[l], p->lvl_rest_max_m[l]);
     launch_large_level(p->st, p->d_ctrl, p->fd, p->ld, p->lvl_large[l], l, sys, p->sp, use_H, dv,
                        (overlap_T > 0 && l >= overlap_T) ? p->sm_count : 0);
   }

@@ -8,7 +8,7 @@ B="python bench.py --steps 2 --warmup 1 --cpu-baseline 0 --secondary 0"
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_$R.csv $B > gpurun_out/pp0.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:large_factor -s 3 -c 1 -o gpurun_out/prof_factor_$R -f $B > gpurun_out/pp1.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:schur_s9 -s 2 -c 1 -o gpurun_out/prof_s9_$R -f $B > gpurun_out/pp2.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:linearize_bal -s 8 -c 1 -o gpurun_out/prof_lin_$R -f $B > gpurun_out/pp3.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:linearize_bal -s 16 -c 1 -o gpurun_out/prof_lin_$R -f $B > gpurun_out/pp3.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:schur_w_rhs -s 2 -c 1 -o gpurun_out/prof_w_$R -f $B > gpurun_out/pp4.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:bal_point_finalize -s 2 -c 1 -o gpurun_out/prof_fin_$R -f $B > gpurun_out/pp5.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:schur_cinv -s 2 -c 1 -o gpurun_out/prof_cinv_$R -f $B > gpurun_out/pp6.log 2>&1

@@ -279,6 +279,9 @@ def rooflines(workload, info, ph):
         info.get("plan", -1), "dissect to depth %d, then sweep" % info.get("plan", -1))
     if info.get("ref_ordering_flops"):
         rl_fac["gflop_ref_ordering"] = float(info["ref_ordering_flops"]) / 1e9
+        # the same time against the flops the reference's ordering needs for this factorization (not the headline: the
+        # fraction above is what the hardware did)
+        rl_fac["frac_ref_ordering"] = float(info["ref_ordering_flops"]) / (ph["factorize"] * 1e-3) / 1e12 / fp64_peak
     dominant = max([kv for kv in (("factorize", rl_fac), ("schur", rl_schur), ("linearize", rl_lin)) if kv[1]],
                    key=lambda kv: ph[kv[0]])[1]
     return rl_lin, rl_schur, rl_fac, dominant

@@ -6,6 +6,8 @@
 //   A: Schur problem, ComputeCovariances(cameras)        -> the LM problem's own Schur solver
 //   B: Cholesky problem, ComputeCovariances(cameras)     -> sibling problem with the requested split
 //   C: Cholesky problem, ComputeAllCovariances           -> (H + eps I)^-1
+//   D: Schur problem, ComputeCovariances(cameras, c_is_block_diagonal = false) -> general-C path on a sibling problem
+//   E: Cholesky problem, ComputeCovariances(first three poses, false): C holds poses, intrinsics and points
 #include <cmath>
 #include <cstdio>
 #include <random>
@@ -112,6 +114,13 @@ int main() {
   const auto info_b = opt_b.ComputeCovariances(lin_b, cam_keys, cov_b);
   opt_b.ComputeAllCovariances(lin_b, cov_c);
 
+  // D, E: the general-C branch (internal/covariance_utils.h:41-103, 142-145)
+  CovMap cov_d, cov_e;
+  const auto info_d = opt_a.ComputeCovariances(opt_a.Linearize(va), cam_keys, cov_d, /*c_is_block_diagonal=*/false);
+  const std::vector<sym::Key> three_poses(cam_keys.begin(), cam_keys.begin() + 3);
+  const auto info_e = opt_b.ComputeCovariances(lin_b, three_poses, cov_e, /*c_is_block_diagonal=*/false);
+  const double d_ad = MaxRelDiff(cov_a, cov_d, cam_keys), d_ce = MaxRelDiff(cov_e, cov_c, three_poses);
+
   const double final_a = stats_a.iterations[stats_a.best_index].new_error;
   const double final_b = stats_b.iterations[stats_b.best_index].new_error;
   const double d_ab = MaxRelDiff(cov_a, cov_b, cam_keys), d_bc = MaxRelDiff(cov_b, cov_c, cam_keys);
@@ -119,9 +128,12 @@ int main() {
   std::printf("covariance keys: A %zu B %zu C %zu (of %zu optimized keys)\n", cov_a.size(), cov_b.size(), cov_c.size(),
               opt_b.Keys().size());
   std::printf("max rel diff A vs B: %.3e\nmax rel diff B vs C: %.3e\n", d_ab, d_bc);
+  std::printf("max rel diff A vs D: %.3e\nmax rel diff E vs C: %.3e\n", d_ad, d_ce);
   std::printf("sigma(f) of camera 0: %.6e\n", std::sqrt(cov_a.at(INTRINSICS.WithSuper(0))(0, 0)));
   const bool ok = info_a == sym::kSuccess && info_b == sym::kSuccess && cov_a.size() == cam_keys.size() &&
                   cov_c.size() == opt_b.Keys().size() && d_ab < 1e-6 && d_bc < 1e-6 &&
+                  info_d == sym::kSuccess && info_e == sym::kSuccess && cov_d.size() == cam_keys.size() &&
+                  cov_e.size() == three_poses.size() && d_ad < 1e-6 && d_ce < 1e-6 &&
                   std::fabs(final_a - final_b) < 1e-8 * final_b;
   std::printf(ok ? "COVARIANCE_OK\n" : "COVARIANCE_FAIL\n");
   return ok ? 0 : 1;

@@ -1,5 +1,7 @@
 // robot_3d_localization on the GPU path, written against the sym:: API exactly like the reference
 // example (symforce/examples/robot_3d_localization/run_dynamic_size.cc:25-105, common.h:24-62).
+#include <algorithm>
+#include <cmath>
 #include <cstdio>
 
 #include <sym/sym.h>
@@ -45,6 +47,8 @@ int main() {
                  sym::Vector3d::FromData(kBodyTLandmark + 3 * (i * kNumLandmarks + j)));
   values.Set(Keys::EPSILON, sym::kDefaultEpsilond);
 
+  const sym::Valuesd initial_values = values;
+
   std::vector<sym::Factord> factors;
   for (int i = 0; i < kNumPoses; i++)
     for (int j = 0; j < kNumLandmarks; j++) factors.push_back(CreateMatchingFactor(i, j));
@@ -79,6 +83,38 @@ int main() {
       std::printf("Covariance trace %d: %.12e\n", i, tr);
     }
   }
+  // debug_stats + include_jacobians (optimization_stats.h:40-75, levenberg_marquardt_solver.tcc:115-122, 165-176):
+  // every record carries update / values / residual / jacobian_values; J^T r of the best record, rebuilt through
+  // JacobianView, is the rhs of the linearization at the optimized values
+  bool debug_ok = false;
+  {
+    params.debug_stats = true;
+    params.include_jacobians = true;
+    sym::Optimizer<double> debug_optimizer(params, factors, "Robot3DDebugStats");
+    sym::Valuesd debug_values = initial_values;
+    const auto debug_stats = debug_optimizer.Optimize(debug_values);
+    const auto& rec = debug_stats.iterations[debug_stats.best_index];
+    const auto J = debug_stats.JacobianView(rec);
+    const auto lin = debug_optimizer.Linearize(debug_values);
+    double worst = 0, scale = 0;
+    for (int c = 0; c < J.cols(); ++c) {
+      double jtr = 0;
+      for (int k = J.outerIndexPtr()[c]; k < J.outerIndexPtr()[c + 1]; ++k)
+        jtr += J.valuePtr()[k] * rec.residual[J.innerIndexPtr()[k]];
+      worst = std::max(worst, std::abs(jtr - lin.rhs[c]));
+      scale = std::max(scale, std::abs(lin.rhs[c]));
+    }
+    const size_t N = lin.rhs.size();
+    debug_ok = debug_stats.iterations.size() == stats.iterations.size() && worst <= 1e-9 * scale &&
+               J.rows() == static_cast<int>(rec.residual.size()) && J.cols() == static_cast<int>(N) &&
+               J.nonZeros() == lin.jacobian.nonZeros() && rec.update.size() == N &&
+               debug_stats.iterations.front().update.empty() &&
+               debug_stats.iterations.front().jacobian_values.size() == rec.jacobian_values.size() &&
+               debug_stats.linear_solver_ordering.size() == N && debug_stats.cholesky_factor_sparsity.shape.empty();
+    std::printf("Debug stats: %zu records, J %d x %d nnz %lld, |J^T r - rhs| %.3e of %.3e: %s\n",
+                debug_stats.iterations.size(), J.rows(), J.cols(), static_cast<long long>(J.nonZeros()), worst, scale,
+                debug_ok ? "DEBUG_STATS_OK" : "DEBUG_STATS_MISMATCH");
+  }
   // same acceptance check as test/symforce_examples_robot_3d_localization_test.py:49-51
-  return (stats.status == sym::optimization_status_t::SUCCESS && best_iter.new_error < 140) ? 0 : 1;
+  return (debug_ok && stats.status == sym::optimization_status_t::SUCCESS && best_iter.new_error < 140) ? 0 : 1;
 }

@@ -218,10 +218,21 @@ sfx_status sfx_get_best_values(sfx_problem* p, double* values, int64_t n);
 /* optimizer_params_t::debug_stats (lcmtypes/symforce.lcm:236-246, levenberg_marquardt_solver.tcc:166-171,245-250):
  * optimization_iteration_t::values (the data of the Values buffer, whose index the caller already has) and
  * ::residual of iteration record `record` (0 = the record of iteration -1) of the last sfx_optimize[_continue],
- * which must have run with debug_stats set.  Either output may be NULL.  Costs iterations x (Values + residual)
- * of device memory; single GPU.  (jacobian_values are not kept per iteration: the path never forms J; see
- * sfx_linearize_jacobian for the Jacobian at given values.) */
+ * which must have run with debug_stats set.  Either output may be NULL.  Costs iterations x (Values + residual +
+ * update) of device memory; single GPU. */
 sfx_status sfx_get_iteration_debug(sfx_problem* p, int32_t record, double* values, double* residual);
+
+/* optimization_iteration_t::update of the same record (levenberg_marquardt_solver.tcc:116, update_ of :217): the N
+ * entries of the step this iteration tried, in the reference's tangent order; zeros for record 0 (the record of
+ * iteration -1, where the reference leaves the vector empty). */
+sfx_status sfx_get_iteration_update(sfx_problem* p, int32_t record, double* update);
+
+/* optimization_iteration_t::jacobian_values of the same record (levenberg_marquardt_solver.tcc:120-121, :172-175;
+ * JacobianValues of linearization.h:180): the nnz values of the Jacobian at the record's values, in the CSC order of
+ * sfx_get_jacobian_pattern (= OptimizationStats::jacobian_sparsity).  The LM loop never forms J, so nothing is kept per
+ * iteration: J is re-evaluated on request from the record's snapshot of the Values buffer by the kernel behind
+ * sfx_linearize_jacobian (bit-identical to evaluating it inside the iteration).  Does not touch the optimizer state. */
+sfx_status sfx_get_iteration_jacobian(sfx_problem* p, int32_t record, double* jacobian_values);
 
 /* GncOptimizer::Optimize outer loop (symforce/opt/gnc_optimizer.h:53-130, OptimizeContinue :133-142):
  * sfx_optimize_continue = LevenbergMarquardtSolver::ResetState(values) (levenberg_marquardt_solver.h:178-183) with
@@ -275,11 +286,14 @@ sfx_status sfx_get_best_linearization(sfx_problem* p, double* residual, double* 
  * created with the Schur solver: `keys` are the keys in front of the eliminated landmarks,
  * block_dim = their tangent dimension, covariance = (B - E (C + eps I)^-1 E^T)^-1, column-major
  * block_dim x block_dim in keys_ order.  For a problem created with the Cholesky solver:
- * Optimizer::ComputeFullCovariance / ComputeAllCovariances (optimizer.tcc:113-121, 201-206 ->
- * LevenbergMarquardtSolver::ComputeCovariance, levenberg_marquardt_solver.tcc:345-356):
- * block_dim = N, covariance = (H + eps I)^-1.  hessian_values: Linearization::hessian_lower values
+ * block_dim = N is Optimizer::ComputeFullCovariance / ComputeAllCovariances (optimizer.tcc:113-121, 201-206 ->
+ * LevenbergMarquardtSolver::ComputeCovariance, levenberg_marquardt_solver.tcc:345-356): covariance = (H + eps I)^-1;
+ * block_dim < N is ComputeCovariances with c_is_block_diagonal = false, C of any structure
+ * (internal/covariance_utils.h:41-103, 142-145: S = B - E C^-1 E^T with eps on the diagonal of C, covariance = S^-1),
+ * computed as the leading block of the inverse of the matrix damped on C, from block_dim solves with the sparse
+ * Cholesky factor of the whole matrix.  hessian_values: Linearization::hessian_lower values
  * in the CSC order of sfx_get_hessian_pattern, or NULL for the best linearization of the last
- * sfx_optimize.  Other blocks: SFX_ERR_UNSUPPORTED; a non-positive pivot: SFX_ERR_NUMERICAL. */
+ * sfx_optimize.  Other blocks of a Schur problem: SFX_ERR_UNSUPPORTED; a non-positive pivot: SFX_ERR_NUMERICAL. */
 sfx_status sfx_compute_covariance(sfx_problem* p, const double* hessian_values, int32_t block_dim,
                                   double* covariance);
 

@@ -642,8 +642,17 @@ struct optimization_iteration_t {
   double relative_reduction{0};
   bool update_accepted{false};
   double update_angle_change{0};
-  // debug_stats only (symforce.lcm:236-246): the data of the Values buffer and the residual of this record
-  std::vector<double> values, residual;
+  // debug_stats only (symforce.lcm:247-257; levenberg_marquardt_solver.tcc:115-122, 165-176): the update this iteration
+  // tried (empty in the record of iteration -1), the data of the Values buffer, the residual, and -- with
+  // include_jacobians -- the values of the Jacobian in the order of OptimizationStats::jacobian_sparsity
+  std::vector<double> update, values, residual, jacobian_values;
+};
+
+// lcmtypes/symforce.lcm:268-277
+struct sparse_matrix_structure_t {
+  std::vector<int32_t> row_indices;      // size nnz
+  std::vector<int32_t> column_pointers;  // size cols + 1 (linearization.h:94-100)
+  std::vector<int64_t> shape;            // (rows, cols); empty when not filled
 };
 
 // Linearization container (symforce/opt/linearization.h:27-77) with the CSC pieces the reference's
@@ -724,6 +733,27 @@ struct OptimizationStats {
   optimization_status_t status{optimization_status_t::INVALID};
   int32_t failure_reason{0};
   std::optional<SparseLinearization> best_linearization{};
+  // debug_stats only (optimization_stats.h:40-60).  jacobian_sparsity additionally needs include_jacobians.
+  // linear_solver_ordering: elimination position -> scalar index of the system the linear solver factors (the reduced
+  // camera system under Schur elimination).  cholesky_factor_sparsity stays default constructed, as the reference
+  // leaves it for a solver that does not expose L(): the factor here is a supernodal LL^T held as dense fronts.
+  sparse_matrix_structure_t jacobian_sparsity{};
+  std::vector<int32_t> linear_solver_ordering{};
+  sparse_matrix_structure_t cholesky_factor_sparsity{};
+
+  // optimization_stats.h:67-75: the Jacobian of an iteration record (a copy; the reference returns a Map)
+  SparseMatrixCsc JacobianView(const optimization_iteration_t& iteration) const {
+    SYM_ASSERT(jacobian_sparsity.shape.size() == 2 &&
+               "Jacobian sparsity is empty, did you set debug_stats = true and include_jacobians = true?");
+    SYM_ASSERT(jacobian_sparsity.row_indices.size() == iteration.jacobian_values.size());
+    SparseMatrixCsc J;
+    J.rows_ = static_cast<int>(jacobian_sparsity.shape[0]);
+    J.cols_ = static_cast<int>(jacobian_sparsity.shape[1]);
+    J.outer = jacobian_sparsity.column_pointers;
+    J.inner = jacobian_sparsity.row_indices;
+    J.values = iteration.jacobian_values;
+    return J;
+  }
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -993,16 +1023,40 @@ class Optimizer {
       o.update_angle_change = it.update_angle_change;
       stats.iterations.push_back(o);
     }
+    stats.jacobian_sparsity = {};
+    stats.linear_solver_ordering.clear();
+    stats.cholesky_factor_sparsity = {};
     if (params_.debug_stats) {
       int32_t N = 0, M = 0;
-      int64_t nnz = 0;
+      int64_t nnz = 0, jnnz = 0;
       Check(sfx_get_dims(handle_, &N, &M, &nnz));
-      for (size_t i = 0; i < stats.iterations.size(); ++i) {
-        stats.iterations[i].values.resize(values.Data().size());
-        stats.iterations[i].residual.resize(M);
-        Check(sfx_get_iteration_debug(handle_, static_cast<int32_t>(i), stats.iterations[i].values.data(),
-                                      stats.iterations[i].residual.data()));
+      if (params_.include_jacobians) {  // levenberg_marquardt_solver.tcc:172-175
+        Check(sfx_get_jacobian_pattern(handle_, &jnnz, nullptr, nullptr));
+        stats.jacobian_sparsity.row_indices.resize(jnnz);
+        stats.jacobian_sparsity.column_pointers.resize(N + 1);
+        stats.jacobian_sparsity.shape = {M, N};
+        Check(sfx_get_jacobian_pattern(handle_, nullptr, stats.jacobian_sparsity.column_pointers.data(),
+                                       stats.jacobian_sparsity.row_indices.data()));
       }
+      for (size_t i = 0; i < stats.iterations.size(); ++i) {
+        auto& rec = stats.iterations[i];
+        rec.values.resize(values.Data().size());
+        rec.residual.resize(M);
+        Check(sfx_get_iteration_debug(handle_, static_cast<int32_t>(i), rec.values.data(), rec.residual.data()));
+        if (rec.iteration >= 0) {
+          rec.update.resize(N);
+          Check(sfx_get_iteration_update(handle_, static_cast<int32_t>(i), rec.update.data()));
+        }
+        // (the reference fills the jacobian of records >= 0 whenever the linearization carries one, tcc:120-121)
+        if (params_.include_jacobians) {
+          rec.jacobian_values.resize(jnnz);
+          Check(sfx_get_iteration_jacobian(handle_, static_cast<int32_t>(i), rec.jacobian_values.data()));
+        }
+      }
+      int32_t n_ord = 0;  // levenberg_marquardt_solver.tcc:209-212
+      Check(sfx_get_ordering(handle_, nullptr, 0, &n_ord));
+      stats.linear_solver_ordering.resize(n_ord);
+      Check(sfx_get_ordering(handle_, stats.linear_solver_ordering.data(), n_ord, &n_ord));
     }
     stats.best_index = st.best_index;
     stats.status = static_cast<optimization_status_t>(st.status);
@@ -1053,9 +1107,10 @@ class Optimizer {
   }
 
   // ComputeCovariances (optimizer.tcc:177-199): marginal covariance of `keys`, which must be the first
-  // keys of Keys() in order; every later key is eliminated with the Schur complement.  The GPU path has
-  // the block-diagonal-C solver only (c_is_block_diagonal = true: each eliminated key is a vector of
-  // dim <= 3 that shares no factor with another eliminated key).
+  // keys of Keys() in order; every later key is eliminated with the Schur complement.
+  // c_is_block_diagonal = true: each eliminated key is a vector of dim <= 3 that shares no factor with another
+  // eliminated key (SparseSchurSolver on the device).  false: C may have any structure
+  // (covariance_utils.h:41-103); the block comes from the sparse Cholesky factor of the whole matrix, damped on C.
   ComputationInfo ComputeCovariances(const SparseLinearization& linearization, const std::vector<Key>& keys,
                                      std::unordered_map<Key, MatrixX<Scalar>, KeyHash>& covariances_by_key,
                                      const bool c_is_block_diagonal = true) {
@@ -1066,13 +1121,23 @@ class Optimizer {
       ComputeAllCovariances(linearization, covariances_by_key);
       return kSuccess;
     }
-    if (!c_is_block_diagonal)
-      throw std::runtime_error("sym::Optimizer::ComputeCovariances: the GPU path only has the block-diagonal C solver");
     int block_dim = 0;
     for (size_t i = 0; i < keys.size(); ++i) block_dim += kentries_[i].tangent_dim;
-    const int n_elim = static_cast<int>(keys_.size() - keys.size());
+    const int n_elim = c_is_block_diagonal ? static_cast<int>(keys_.size() - keys.size()) : 0;
     sfx_problem* h = handle_;
-    if (!(solver_ == SFX_SOLVER_SCHUR && schur_keys_ == n_elim)) {
+    if (!c_is_block_diagonal) {
+      if (solver_ != SFX_SOLVER_CHOLESKY) {  // sibling problem that factors the whole H, as for ComputeFullCovariance
+        if (cov_handle_ && cov_schur_keys_ != 0) {
+          sfx_problem_destroy(cov_handle_);
+          cov_handle_ = nullptr;
+        }
+        if (!cov_handle_) {
+          cov_handle_ = Create(SFX_SOLVER_CHOLESKY, 0);
+          cov_schur_keys_ = 0;
+        }
+        h = cov_handle_;
+      }
+    } else if (!(solver_ == SFX_SOLVER_SCHUR && schur_keys_ == n_elim)) {
       // the LM solve uses another split (or none): a sibling problem with the same structure and the
       // requested Schur split, built once (the reference builds a SparseSchurSolver per call, covariance_utils.h:141-145)
       if (cov_handle_ && cov_schur_keys_ != n_elim) {

@@ -17,7 +17,8 @@ LIB_PATH = os.environ.get("SFX_LIB") or os.path.join(_HERE, "lib", "libsfx.so") 
 EXPORTS = [
     "sfx_default_params", "sfx_problem_create", "sfx_problem_destroy", "sfx_last_error", "sfx_update_params",
     "sfx_set_values", "sfx_optimize", "sfx_optimize_continue", "sfx_relax_damping_to_initial", "sfx_get_best_values",
-    "sfx_update_best_values", "sfx_get_iteration_debug", "sfx_get_iterations", "sfx_get_dims",
+    "sfx_update_best_values", "sfx_get_iteration_debug", "sfx_get_iteration_update", "sfx_get_iteration_jacobian",
+    "sfx_get_iterations", "sfx_get_dims",
     "sfx_get_hessian_pattern", "sfx_linearize", "sfx_get_jacobian_pattern", "sfx_linearize_jacobian",
     "sfx_get_best_linearization", "sfx_solve_step",
     "sfx_compute_covariance", "sfx_get_ordering", "sfx_get_timings", "sfx_get_info", "sfx_comm_unique_id", "sfx_comm_create",
@@ -133,17 +134,39 @@ class SfxProblem(D._LibProblem):
                     "get_iteration_debug")
         return v, r
 
-    def jacobian(self):
-        """Linearization::jacobian (include_jacobians) at the values last set: (outer, inner, values) of the M x N CSC."""
+    def iteration_update(self, record):
+        """debug_stats: optimization_iteration_t::update of a record (reference tangent order; zeros for record 0)."""
+        N, _, _ = self.dims()
+        u = np.empty(N)
+        self._check(self.lib.sfx_get_iteration_update(self.h, C.c_int32(record), u.ctypes.data_as(C.POINTER(C.c_double))),
+                    "get_iteration_update")
+        return u
+
+    def iteration_jacobian(self, record):
+        """debug_stats: optimization_iteration_t::jacobian_values of a record, in the CSC order of jacobian()."""
+        nnz = C.c_int64()
+        self._check(self.lib.sfx_get_jacobian_pattern(self.h, C.byref(nnz), None, None), "get_jacobian_pattern")
+        val = np.empty(nnz.value)
+        self._check(self.lib.sfx_get_iteration_jacobian(self.h, C.c_int32(record), val.ctypes.data_as(C.POINTER(C.c_double))),
+                    "get_iteration_jacobian")
+        return val
+
+    def jacobian_pattern(self):
+        """CSC pattern of Linearization::jacobian: (column pointers [N + 1], row indices [nnz])."""
         nnz = C.c_int64()
         self._check(self.lib.sfx_get_jacobian_pattern(self.h, C.byref(nnz), None, None), "get_jacobian_pattern")
         N, _, _ = self.dims()
         outer = np.empty(N + 1, dtype=np.int32)
         inner = np.empty(nnz.value, dtype=np.int32)
-        val = np.empty(nnz.value)
         pi = C.POINTER(C.c_int32)
         self._check(self.lib.sfx_get_jacobian_pattern(self.h, None, outer.ctypes.data_as(pi), inner.ctypes.data_as(pi)),
                     "get_jacobian_pattern")
+        return outer, inner
+
+    def jacobian(self):
+        """Linearization::jacobian (include_jacobians) at the values last set: (outer, inner, values) of the M x N CSC."""
+        outer, inner = self.jacobian_pattern()
+        val = np.empty(inner.shape[0])
         self._check(self.lib.sfx_linearize_jacobian(self.h, val.ctypes.data_as(C.POINTER(C.c_double))),
                     "linearize_jacobian")
         return outer, inner, val

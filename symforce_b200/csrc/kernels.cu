@@ -2478,10 +2478,13 @@ __global__ void copy_kernel(double* __restrict__ dst, const double* __restrict__
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = src[i];
 }
-// debug_stats: optimization_iteration_t::values / residual of the record about to be written
-// (levenberg_marquardt_solver.tcc:166-171 for the record of iteration -1 = Init, :245-250 for New)
+// debug_stats: optimization_iteration_t::values / residual / update of the record about to be written
+// (levenberg_marquardt_solver.tcc:166-171 for the record of iteration -1 = Init, :115-119 for New; the update in the
+// reference's tangent order, zeros in the record of iteration -1)
 __global__ void debug_snapshot_kernel(const Ctrl* __restrict__ c, StatePtrs sp, int first, int64_t n_values, int M,
-                                      int cap, double* __restrict__ dv, double* __restrict__ dr) {
+                                      int cap, double* __restrict__ dv, double* __restrict__ dr,
+                                      const double* __restrict__ upd, const int32_t* __restrict__ ref2int, int N,
+                                      double* __restrict__ du) {
   if (c->done) return;
   if (first && c->iteration != 0) return;  // the record of iteration -1 exists only after a Reset
   const int blk = first ? c->init_idx : c->new_idx;
@@ -2492,14 +2495,17 @@ __global__ void debug_snapshot_kernel(const Ctrl* __restrict__ c, StatePtrs sp, 
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_values; i += stride) dv[(size_t)rec * n_values + i] = v[i];
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < M; i += stride) dr[(size_t)rec * M + i] = r[i];
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < N; i += stride)
+    du[(size_t)rec * N + i] = first ? 0.0 : upd[ref2int[i]];
 }
 void launch_debug_snapshot(cudaStream_t st, const Ctrl* ctrl, StatePtrs sp, int first, int64_t n_values, int M, int cap,
-                           double* dv, double* dr) {
+                           double* dv, double* dr, const double* upd, const int32_t* ref2int, int N, double* du) {
   int64_t work = n_values > M ? n_values : M;
+  if (N > work) work = N;
   int grid = (int)((work + 255) / 256);
   if (grid > 148 * 8) grid = 148 * 8;
   if (grid < 1) grid = 1;
-  debug_snapshot_kernel<<<grid, 256, 0, st>>>(ctrl, sp, first, n_values, M, cap, dv, dr); ++g_launches;
+  debug_snapshot_kernel<<<grid, 256, 0, st>>>(ctrl, sp, first, n_values, M, cap, dv, dr, upd, ref2int, N, du); ++g_launches;
 }
 
 void launch_copy_values(cudaStream_t st, double* dst, const double* src, int64_t n) {

@@ -247,7 +247,7 @@ void launch_lm_begin(cudaStream_t st, Ctrl* ctrl);
 void launch_lm_after_first_linearize(cudaStream_t st, Ctrl* ctrl);
 void launch_lm_end(cudaStream_t st, Ctrl* ctrl, const double* upd, double* last_upd, int N, int* host_done);
 void launch_debug_snapshot(cudaStream_t st, const Ctrl* ctrl, StatePtrs sp, int first, int64_t n_values, int M, int cap,
-                           double* dv, double* dr);
+                           double* dv, double* dr, const double* upd, const int32_t* ref2int, int N, double* du);
 void launch_copy_values(cudaStream_t st, double* dst, const double* src, int64_t n);
 void launch_export_csc(cudaStream_t st, const double* Hvals, const int32_t* csc_src, int64_t nnz, double* out);
 cudaError_t configure_front_kernels(int smem_m_max, int max_front);

@@ -151,7 +151,7 @@ struct sfx_problem {
   int n_zero_jobs = 0;
   unsigned solve_epoch = 0;
   // debug_stats: per-record snapshots of values / residual (allocated on first use)
-  double *dbg_values = nullptr, *dbg_res = nullptr;
+  double *dbg_values = nullptr, *dbg_res = nullptr, *dbg_upd = nullptr;
   int dbg_cap = 0;
   bool dbg_valid = false;
   bool can_continue = false;  // the control block is the one the last sfx_optimize[_continue] left
@@ -214,6 +214,7 @@ struct sfx_problem {
     if (st2) cudaStreamDestroy(st2);
     if (dbg_values) cudaFree(dbg_values);
     if (dbg_res) cudaFree(dbg_res);
+    if (dbg_upd) cudaFree(dbg_upd);
     if (ev_fork) cudaEventDestroy(ev_fork);
     if (ev_join) cudaEventDestroy(ev_join);
     if (ev_fork2) cudaEventDestroy(ev_fork2);
@@ -1918,10 +1919,13 @@ static sfx_status optimize_impl(sfx_problem* p, int32_t num_iterations, sfx_stat
     SFX_CHECK(a.world == 1, SFX_ERR_UNSUPPORTED, "debug_stats snapshots are single-GPU only");
     const int need = (cont ? p->h_ctrl->n_iters : 0) + num_iterations + 1;
     if (need > p->dbg_cap) {
-      double *nv = nullptr, *nr = nullptr;
+      double *nv = nullptr, *nr = nullptr, *nu = nullptr;
       if (cudaMalloc(&nv, sizeof(double) * (size_t)need * a.n_values) != cudaSuccess ||
-          cudaMalloc(&nr, sizeof(double) * (size_t)need * std::max(a.M, 1)) != cudaSuccess) {
+          cudaMalloc(&nr, sizeof(double) * (size_t)need * std::max(a.M, 1)) != cudaSuccess ||
+          cudaMalloc(&nu, sizeof(double) * (size_t)need * std::max(a.N, 1)) != cudaSuccess) {
         if (nv) cudaFree(nv);
+        if (nr) cudaFree(nr);
+        cudaGetLastError();
         throw Error(SFX_ERR_CUDA, "out of device memory for the debug_stats snapshots (iterations x Values)");
       }
       if (cont && p->dbg_valid) {  // keep the records of the stages before
@@ -1929,12 +1933,16 @@ static sfx_status optimize_impl(sfx_problem* p, int32_t num_iterations, sfx_stat
                                 cudaMemcpyDeviceToDevice, p->st));
         CUDA_OK(cudaMemcpyAsync(nr, p->dbg_res, sizeof(double) * (size_t)p->h_ctrl->n_iters * a.M, cudaMemcpyDeviceToDevice,
                                 p->st));
+        CUDA_OK(cudaMemcpyAsync(nu, p->dbg_upd, sizeof(double) * (size_t)p->h_ctrl->n_iters * a.N, cudaMemcpyDeviceToDevice,
+                                p->st));
         CUDA_OK(cudaStreamSynchronize(p->st));
       }
       if (p->dbg_values) cudaFree(p->dbg_values);
       if (p->dbg_res) cudaFree(p->dbg_res);
+      if (p->dbg_upd) cudaFree(p->dbg_upd);
       p->dbg_values = nv;
       p->dbg_res = nr;
+      p->dbg_upd = nu;
       p->dbg_cap = need;
     }
   }
@@ -1979,7 +1987,8 @@ static sfx_status optimize_impl(sfx_problem* p, int32_t num_iterations, sfx_stat
       else
         enqueue_linearize(p, /*mode=*/0);
       launch_lm_after_first_linearize(p->st, p->d_ctrl);
-      if (dbg) launch_debug_snapshot(p->st, p->d_ctrl, p->sp, 1, a.n_values, a.M, p->dbg_cap, p->dbg_values, p->dbg_res);
+      if (dbg) launch_debug_snapshot(p->st, p->d_ctrl, p->sp, 1, a.n_values, a.M, p->dbg_cap, p->dbg_values, p->dbg_res,
+                                     p->d_upd, p->d_ref2int, a.N, p->dbg_upd);
       mark(PH_LIN);
     }
     enqueue_solve(p, mark);
@@ -1987,7 +1996,8 @@ static sfx_status optimize_impl(sfx_problem* p, int32_t num_iterations, sfx_stat
                    p->d_key_itoff, a.n_keys, p->d_upd);
     mark(PH_UPDATE);
     enqueue_linearize(p, /*mode=*/1);
-    if (dbg) launch_debug_snapshot(p->st, p->d_ctrl, p->sp, 0, a.n_values, a.M, p->dbg_cap, p->dbg_values, p->dbg_res);
+    if (dbg) launch_debug_snapshot(p->st, p->d_ctrl, p->sp, 0, a.n_values, a.M, p->dbg_cap, p->dbg_values, p->dbg_res,
+                                     p->d_upd, p->d_ref2int, a.N, p->dbg_upd);
     mark(PH_LIN);
     launch_step_reduce(p->st, p->d_ctrl, p->sp, p->d_upd, p->d_dvec, p->d_last, a.N, p->d_partials,
                        (a.world > 1 && a.rank != 0) ? a.sp.reduced_dim : 0);
@@ -2156,6 +2166,35 @@ sfx_status sfx_get_iteration_debug(sfx_problem* p, int32_t record, double* value
   SFX_API_END(p)
 }
 
+sfx_status sfx_get_iteration_update(sfx_problem* p, int32_t record, double* update) {
+  SFX_API_BEGIN
+  SFX_CHECK(p && update, SFX_ERR_INVALID_ARG, "null argument");
+  SFX_CHECK(p->dbg_valid, SFX_ERR_INVALID_ARG, "the last optimization did not run with optimizer_params_t::debug_stats");
+  SFX_CHECK(record >= 0 && record < p->h_ctrl->n_iters && record < p->dbg_cap, SFX_ERR_INVALID_ARG, "no such iteration record");
+  CUDA_OK(cudaSetDevice(p->device));
+  CUDA_OK(cudaMemcpyAsync(update, p->dbg_upd + (size_t)record * p->a.N, sizeof(double) * p->a.N, cudaMemcpyDeviceToHost,
+                          p->st));
+  CUDA_OK(cudaStreamSynchronize(p->st));
+  SFX_API_END(p)
+}
+
+sfx_status sfx_get_iteration_jacobian(sfx_problem* p, int32_t record, double* jacobian_values) {
+  SFX_API_BEGIN
+  SFX_CHECK(p && jacobian_values, SFX_ERR_INVALID_ARG, "null argument");
+  SFX_CHECK(p->dbg_valid, SFX_ERR_INVALID_ARG, "the last optimization did not run with optimizer_params_t::debug_stats");
+  SFX_CHECK(record >= 0 && record < p->h_ctrl->n_iters && record < p->dbg_cap, SFX_ERR_INVALID_ARG, "no such iteration record");
+  CUDA_OK(cudaSetDevice(p->device));
+  ensure_jacobian(p);
+  // J is a pure function of the values: evaluated from the record's snapshot of the Values buffer, by the kernel
+  // sfx_linearize_jacobian runs (the LM loop itself never forms J); the optimizer state is not touched
+  const double* v = p->dbg_values + (size_t)record * p->a.n_values;
+  for (size_t b = 0; b < p->lin.size(); ++b)
+    launch_jacobian(p->st, v, p->lin[b], p->d_jac_base[b], p->d_jac_colnnz[b], p->d_export);
+  CUDA_OK(cudaMemcpyAsync(jacobian_values, p->d_export, sizeof(double) * p->a.jac_nnz, cudaMemcpyDeviceToHost, p->st));
+  CUDA_OK(cudaStreamSynchronize(p->st));
+  SFX_API_END(p)
+}
+
 sfx_status sfx_get_iterations(sfx_problem* p, sfx_iteration* buf, int32_t capacity, int32_t* n) {
   SFX_API_BEGIN
   SFX_CHECK(p && n, SFX_ERR_INVALID_ARG, "null argument");
@@ -2239,9 +2278,14 @@ sfx_status sfx_compute_covariance(sfx_problem* p, const double* hessian_values, 
   Analysis& a = p->a;
   SFX_CHECK(a.world == 1, SFX_ERR_UNSUPPORTED, "covariances are computed on one GPU");
   const int sys_dim = a.schur ? a.sp.reduced_dim : a.N;
-  SFX_CHECK(block_dim == sys_dim, SFX_ERR_UNSUPPORTED,
-            "covariance block must be the block the linear solver factors: all keys before the Schur-eliminated "
-            "landmarks, or every key of a problem solved without Schur elimination");
+  // a Schur problem inverts its reduced system (block-diagonal C, SparseSchurSolver::SInvInPlace); a problem solved
+  // without Schur elimination yields any leading block: the general-C path of internal/covariance_utils.h:41-103
+  // (S = B - E C^-1 E^T, covariance = S^-1), computed as the leading block_dim x block_dim block of
+  // (H + epsilon on the diagonal of C)^-1 from block_dim solves with the sparse factor of the whole matrix
+  SFX_CHECK(a.schur ? block_dim == sys_dim : (block_dim >= 1 && block_dim <= sys_dim), SFX_ERR_UNSUPPORTED,
+            "covariance block must be the block the linear solver factors (all keys before the Schur-eliminated "
+            "landmarks), or a leading block of a problem solved without Schur elimination");
+  const int nb = block_dim;
   CUDA_OK(cudaSetDevice(p->device));
   Ctrl* c = p->h_ctrl;
   int blk;
@@ -2269,6 +2313,8 @@ sfx_status sfx_compute_covariance(sfx_problem* p, const double* hessian_values, 
   {
     std::vector<double> dv(a.N, p->epsilon);
     if (a.schur) std::fill(dv.begin(), dv.begin() + sys_dim, 0.0);
+    if (!a.schur && nb < sys_dim)  // covariance_utils.h:131-135: only the marginalized block is damped
+      for (int r = 0; r < nb; ++r) dv[a.ref2int[r]] = 0.0;
     CUDA_OK(cudaMemcpyAsync(p->d_dvec, dv.data(), sizeof(double) * a.N, cudaMemcpyHostToDevice, p->st));
     CUDA_OK(cudaStreamSynchronize(p->st));
   }
@@ -2278,17 +2324,18 @@ sfx_status sfx_compute_covariance(sfx_problem* p, const double* hessian_values, 
   // S^-1 = solves against the identity (SparseSchurSolver::SInvInPlace, sparse_schur_solver.tcc:165-170), column by column
   double *d_unit = nullptr, *d_cov = nullptr;
   CUDA_OK(cudaMalloc(&d_unit, sizeof(double) * sys_dim));
-  if (cudaMalloc(&d_cov, sizeof(double) * (size_t)sys_dim * sys_dim) != cudaSuccess) {
+  if (cudaMalloc(&d_cov, sizeof(double) * (size_t)sys_dim * nb) != cudaSuccess) {
     cudaFree(d_unit);
+    cudaGetLastError();
     throw Error(SFX_ERR_CUDA, "out of device memory for the covariance block");
   }
   CUDA_OK(cudaMemsetAsync(d_unit, 0, sizeof(double) * sys_dim, p->st));
-  for (int j = 0; j < sys_dim; ++j) {
-    launch_set_unit(p->st, d_unit, j, j > 0 ? j - 1 : -1);
+  for (int r = 0; r < nb; ++r) {  // column r of the inverse, in the internal row order
+    launch_set_unit(p->st, d_unit, a.ref2int[r], r > 0 ? a.ref2int[r - 1] : -1);
     enqueue_tri_solves(p, d_unit, 0);
-    launch_unpermute(p->st, p->d_ctrl, p->fd, d_cov + (size_t)j * sys_dim, 1.0);
+    launch_unpermute(p->st, p->d_ctrl, p->fd, d_cov + (size_t)r * sys_dim, 1.0);
   }
-  std::vector<double> cov_int((size_t)sys_dim * sys_dim);
+  std::vector<double> cov_int((size_t)sys_dim * nb);
   CUDA_OK(cudaMemcpyAsync(cov_int.data(), d_cov, sizeof(double) * cov_int.size(), cudaMemcpyDeviceToHost, p->st));
   int fail = 0;
   CUDA_OK(cudaMemcpyAsync(&fail, (char*)p->d_ctrl + offsetof(Ctrl, chol_fail), sizeof(int), cudaMemcpyDeviceToHost, p->st));
@@ -2302,9 +2349,8 @@ sfx_status sfx_compute_covariance(sfx_problem* p, const double* hessian_values, 
   cudaFree(d_cov);
   SFX_CHECK(!fail, SFX_ERR_NUMERICAL, "the matrix to invert is not positive definite");
   // internal tangent order -> keys_ order
-  for (int cj = 0; cj < sys_dim; ++cj)
-    for (int ri = 0; ri < sys_dim; ++ri)
-      covariance[ri + (size_t)cj * sys_dim] = cov_int[a.ref2int[ri] + (size_t)a.ref2int[cj] * sys_dim];
+  for (int cj = 0; cj < nb; ++cj)
+    for (int ri = 0; ri < nb; ++ri) covariance[ri + (size_t)cj * nb] = cov_int[a.ref2int[ri] + (size_t)cj * sys_dim];
   SFX_API_END(p)
 }
 

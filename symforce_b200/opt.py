@@ -86,6 +86,16 @@ class optimization_iteration_t:
     # debug_stats payloads (empty otherwise), levenberg_marquardt_solver.tcc:115-122, 166-177
     values: np.ndarray = None
     residual: np.ndarray = None
+    update: np.ndarray = None  # empty in the record of iteration -1
+    jacobian_values: np.ndarray = None  # with include_jacobians: in the order of Result.jacobian_sparsity
+
+
+@dataclass
+class sparse_matrix_structure_t:
+    """lcmtypes/symforce.lcm:268-277"""
+    row_indices: np.ndarray = None
+    column_pointers: np.ndarray = None
+    shape: tuple = ()
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -373,7 +383,11 @@ class Linearization:
 class _Stats:
     """cc_sym.OptimizationStats (lcmtypes/symforce.lcm:302-330) read back through the C ABI."""
 
-    def __init__(self, st, iterations, best_linearization, ordering):
+    def __init__(self, st, iterations, best_linearization, ordering, jacobian_sparsity=None):
+        self.jacobian_sparsity = jacobian_sparsity if jacobian_sparsity is not None else sparse_matrix_structure_t()
+        # not exposed by this linear solver (supernodal LL^T in dense fronts): default constructed, as the reference
+        # leaves it for solvers without L() (optimization_stats.h:55-60)
+        self.cholesky_factor_sparsity = sparse_matrix_structure_t()
         self.status = optimization_status_t(st.status)
         self.failure_reason = int(st.failure_reason)
         self.best_index = int(st.best_index)
@@ -423,6 +437,24 @@ class Optimizer:
         @property
         def linear_solver_ordering(self):
             return self._stats.linear_solver_ordering
+
+        @property
+        def jacobian_sparsity(self):
+            return self._stats.jacobian_sparsity
+
+        @property
+        def cholesky_factor_sparsity(self):
+            return self._stats.cholesky_factor_sparsity
+
+        def jacobian_view(self, iteration):
+            """OptimizationStats::JacobianView (optimization_stats.h:67-75): the M x N Jacobian of a debug_stats record."""
+            sparsity = self._stats.jacobian_sparsity
+            if len(sparsity.shape) != 2:
+                raise ValueError("Jacobian sparsity is empty, did you set debug_stats = true and include_jacobians = true?")
+            import scipy.sparse as sp
+
+            return sp.csc_matrix((iteration.jacobian_values, sparsity.row_indices, sparsity.column_pointers),
+                                 shape=sparsity.shape)
 
         def error(self):
             return self.iterations[self.best_index].new_error
@@ -615,7 +647,15 @@ class Optimizer:
                 update_accepted=bool(it.update_accepted), update_angle_change=it.update_angle_change)
             if self.params.debug_stats:
                 rec.values, rec.residual = gpu.iteration_debug(r)
+                rec.update = gpu.iteration_update(r) if it.iteration >= 0 else np.zeros(0)
+                if self.params.include_jacobians:
+                    rec.jacobian_values = gpu.iteration_jacobian(r)
             its.append(rec)
+        jac_sparsity = None
+        if self.params.debug_stats and self.params.include_jacobians:  # levenberg_marquardt_solver.tcc:172-175
+            n, m, _ = gpu.dims()
+            j_outer, j_inner = gpu.jacobian_pattern()
+            jac_sparsity = sparse_matrix_structure_t(row_indices=j_inner, column_pointers=j_outer, shape=(m, n))
         best_lin = None
         if populate_best_linearization:
             res, rhs, H = gpu.best_linearization()
@@ -623,7 +663,7 @@ class Optimizer:
             best_lin = Linearization(res, rhs, outer, inner, H)
         ordering = gpu.ordering() if self.params.debug_stats else np.zeros(0, dtype=np.int32)
         return Optimizer.Result(initial_values=initial_guess, optimized_values=optimized_values,
-                                _stats=_Stats(st, its, best_lin, ordering))
+                                _stats=_Stats(st, its, best_lin, ordering, jac_sparsity))
 
     def linearize(self, values: Values) -> Linearization:
         """optimizer.py:360-364 -> Optimizer::Linearize (optimizer.tcc:85-92)."""
@@ -687,7 +727,10 @@ class Optimizer:
     def compute_all_covariances(self, optimized_value: Values):
         return self._split_by_key(self.compute_full_covariance(optimized_value), self.optimized_keys)
 
-    def compute_covariances(self, optimized_value: Values, keys):
+    def compute_covariances(self, optimized_value: Values, keys, c_is_block_diagonal=True):
+        """optimizer.py:294-321 -> Optimizer::ComputeCovariances (optimizer.tcc:177-199).  c_is_block_diagonal (the C++
+        argument, optimizer.h:207-220): True eliminates the later keys with the block-diagonal Schur solver, False allows
+        any structure of C (covariance_utils.h:41-103)."""
         keys = list(keys)
         if keys != self.optimized_keys[:len(keys)] or not keys:
             raise ValueError("keys must be the first optimized keys, in order (CheckKeyOrderMatchesLinearizerKeysStart)")
@@ -695,7 +738,8 @@ class Optimizer:
             return self.compute_all_covariances(optimized_value)
         lin = self.linearize(optimized_value)
         dim = sum(self._layout[k][3] for k in keys)
-        cov = self._cov_problem(len(self.optimized_keys) - len(keys)).compute_covariance(dim, lin._hvalues)
+        n_elim = len(self.optimized_keys) - len(keys) if c_is_block_diagonal else 0
+        cov = self._cov_problem(n_elim).compute_covariance(dim, lin._hvalues)
         return self._split_by_key(np.array(cov), keys)
 
     def close(self):

@@ -58,6 +58,42 @@ def test_full_covariance_robot3d():
     g.close()
 
 
+@pytest.mark.parametrize("name, blocks", [("robot3d", (6, 12, 29)), ("pose_graph", (6, 60)), ("bal_small_chol", (9, 45))])
+def test_general_c_covariance_block(name, blocks):
+    """ComputeCovariances with c_is_block_diagonal = false (optimizer.tcc:177-199 -> covariance_utils.h:124-147 ->
+    FromSparseC :41-103): a leading block of a problem solved without Schur elimination, C of any structure (6-dim poses
+    that share factors; cameras and points).  Against the numpy restatement on the same exported linearization."""
+    if name == "robot3d":
+        prob = P.robot_3d_localization()
+    elif name == "pose_graph":
+        prob = P.pose_graph_problem(n_poses=40, n_loops=12)
+    else:
+        prob = P.bal_problem("small", solver=D.SOLVER_CHOLESKY)
+    g = capi.SfxProblem(prob)
+    g.optimize()
+    N, _, _ = g.dims()
+    H, (outer, inner, Hv_best) = _dense_best(g)
+    Hv = Hv_best.copy()
+    if name == "bal_small_chol":  # gauge freedom: a unit prior on every diagonal entry, as in the Schur test below
+        for c in range(N):
+            Hv[outer[c]] += 1.0
+        H = H + np.eye(N)
+    for b in blocks:
+        want = R.covariance_block(H, b, prob.epsilon, c_is_block_diagonal=False)
+        got = g.compute_covariance(b, hessian_values=Hv)
+        assert got.shape == (b, b)
+        e = relerr(got, want)
+        print(f"GENERALC {name} block={b} of {N} relerr={e:.2e}")
+        assert e < COV_TOL
+        assert np.allclose(got, got.T, rtol=1e-8, atol=1e-14 * np.abs(got).max())
+    # the whole system is still the damped inverse, and the optimizer state is untouched
+    if name != "bal_small_chol":
+        assert relerr(g.compute_covariance(N), R.full_covariance(H, prob.epsilon)) < COV_TOL
+    _, _, Hv2 = g.best_linearization()
+    assert np.array_equal(Hv2, Hv_best)
+    g.close()
+
+
 def test_schur_covariance_block_bal_fast_path():
     # BAL shape (9-dim cameras, 3-dim points: W / s9 kernels); the gauge freedom makes the undamped S singular, so
     # the linearization handed in is the exported one with a prior of weight 1 on every diagonal entry

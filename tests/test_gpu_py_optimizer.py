@@ -50,6 +50,24 @@ def test_robot_3d_localization_python_example():
     assert np.allclose(loaded.to_storage(), got, rtol=0, atol=0)
     assert abs(0.5 * rec.residual @ rec.residual - rec.new_error) <= 1e-9 * rec.new_error
     assert sorted(result.linear_solver_ordering.tolist()) == list(range(30))
+    assert rec.update.shape == (30,) and result.iterations[0].update.shape == (0,)
+    assert rec.jacobian_values is None and result.jacobian_sparsity.shape == ()  # include_jacobians is off
+    with pytest.raises(ValueError, match="include_jacobians"):
+        result.jacobian_view(rec)
+
+    # debug_stats + include_jacobians: OptimizationStats::JacobianView of a record (optimization_stats.h:67-75) is the
+    # Jacobian Optimizer::Linearize yields at that record's values
+    optimizer.params.include_jacobians = True
+    with_j = optimizer.optimize(values)
+    rec_j = with_j.iterations[with_j.best_index]
+    J = with_j.jacobian_view(rec_j)
+    assert J.shape == (rec_j.residual.shape[0], 30) and with_j.jacobian_sparsity.shape == J.shape
+    J_lin = optimizer.linearize(with_j.optimized_values).jacobian
+    assert (J != J_lin).nnz == 0
+    # rhs = J^T r of the same record
+    lin_best = optimizer.linearize(with_j.optimized_values)
+    assert np.allclose(J.T @ rec_j.residual, lin_best.rhs, rtol=0, atol=1e-9 * np.abs(lin_best.rhs).max())
+    optimizer.params.include_jacobians = False
 
     # a second optimize on the same optimizer starts over from the given Values
     again = optimizer.optimize(values)
@@ -103,6 +121,15 @@ def test_linearize_and_covariances_through_the_front():
         assert np.max(np.abs(allk[k] - by_key[k])) <= 1e-11 * np.max(np.abs(want)), k
     with pytest.raises(ValueError, match="first optimized keys"):
         optimizer.compute_covariances(result.optimized_values, optimizer.optimized_keys[1:3])
+    # a strict prefix whose tail is NOT Schur-eliminable (6-dim poses tied by odometry): the general-C branch
+    # (c_is_block_diagonal = False, covariance_utils.h:41-103) = the leading block of the inverse damped on C only
+    first_two = optimizer.compute_covariances(result.optimized_values, optimizer.optimized_keys[:2],
+                                              c_is_block_diagonal=False)
+    want_two = R.covariance_block(Hd, 12, optimizer.epsilon, c_is_block_diagonal=False)
+    assert list(first_two) == optimizer.optimized_keys[:2]
+    for i, k in enumerate(first_two):
+        blk = want_two[6 * i:6 * i + 6, 6 * i:6 * i + 6]
+        assert np.max(np.abs(first_two[k] - blk)) <= 1e-8 * np.max(np.abs(want_two)), k
     optimizer.close()
 
 

@@ -90,6 +90,7 @@ int main() {
   {
     params.debug_stats = true;
     params.include_jacobians = true;
+    params.check_derivatives = true;  // SYM_ASSERTs internal::CheckDerivatives at the values of every record
     sym::Optimizer<double> debug_optimizer(params, factors, "Robot3DDebugStats");
     sym::Valuesd debug_values = initial_values;
     const auto debug_stats = debug_optimizer.Optimize(debug_values);
@@ -105,7 +106,11 @@ int main() {
       scale = std::max(scale, std::abs(lin.rhs[c]));
     }
     const size_t N = lin.rhs.size();
-    debug_ok = debug_stats.iterations.size() == stats.iterations.size() && worst <= 1e-9 * scale &&
+    std::array<double, 3> derivative_errors{};
+    const bool derivatives_ok = debug_optimizer.CheckDerivatives(debug_values, &derivative_errors);
+    std::printf("Derivative check: numerical J %.3e, J^T J %.3e, J^T r %.3e\n", derivative_errors[0], derivative_errors[1],
+                derivative_errors[2]);
+    debug_ok = derivatives_ok && debug_stats.iterations.size() == stats.iterations.size() && worst <= 1e-9 * scale &&
                J.rows() == static_cast<int>(rec.residual.size()) && J.cols() == static_cast<int>(N) &&
                J.nonZeros() == lin.jacobian.nonZeros() && rec.update.size() == N &&
                debug_stats.iterations.front().update.empty() &&

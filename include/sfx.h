@@ -276,6 +276,17 @@ sfx_status sfx_linearize(sfx_problem* p, double* residual, double* rhs, double* 
 sfx_status sfx_get_jacobian_pattern(sfx_problem* p, int64_t* nnz, int32_t* outer, int32_t* inner);
 sfx_status sfx_linearize_jacobian(sfx_problem* p, double* jacobian_values);
 
+/* optimizer_params_t::check_derivatives (symforce/opt/optimizer.tcc:39, 261-272 -> internal::CheckDerivatives,
+ * internal/derivative_checker.h:32-123) at the values last given to sfx_set_values: the linearization is compared with
+ *   (0) the numerical Jacobian of the residual -- central differences in the tangent space with step sqrt(epsilon)
+ *       (util.h:97-127), every perturbed residual evaluated by the device's retract + linearize -- tolerance
+ *       10 sqrt(epsilon);  (1) hessian_lower against J^T J and (2) rhs against J^T r, tolerance sqrt(epsilon);
+ * all three as Eigen's isApprox does (|x - y|_F <= tol * min(|x|_F, |y|_F)).  rel_errors[3] (may be NULL) receives the
+ * three ratios, *ok whether all are within tolerance (the reference SYM_ASSERTs on it), numerical_jacobian (may be
+ * NULL) the dense M x N column-major numerical Jacobian.  Relinearizes 2 N times and forms dense matrices on the host:
+ * M * N <= 2^24 and N <= 4096, SFX_ERR_UNSUPPORTED beyond.  Resets the optimizer state like sfx_linearize.  Single GPU. */
+sfx_status sfx_check_derivatives(sfx_problem* p, double* rel_errors, int32_t* ok, double* numerical_jacobian);
+
 /* stats.best_linearization (populate_best_linearization, internal/optimizer_utils.h:71-76) */
 sfx_status sfx_get_best_linearization(sfx_problem* p, double* residual, double* rhs,
                                       double* hessian_values);

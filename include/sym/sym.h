@@ -14,6 +14,7 @@
 // there and copies the best values + per-iteration stats back.
 #pragma once
 #include <algorithm>
+#include <array>
 #include <chrono>
 #include <cstdio>
 #include <cmath>
@@ -977,12 +978,14 @@ class Optimizer {
     if (keys_.empty()) keys_ = ComputeKeysToOptimize(factors_);
     SYM_ASSERT(!factors_.empty());
     SYM_ASSERT(!keys_.empty());
+    SYM_ASSERT(!params.check_derivatives || params.include_jacobians);  // optimizer.tcc:39, 62
   }
   Optimizer(const Optimizer&) = delete;
   Optimizer& operator=(const Optimizer&) = delete;
   virtual ~Optimizer() {
     if (handle_) sfx_problem_destroy(handle_);
     if (cov_handle_) sfx_problem_destroy(cov_handle_);
+    if (check_handle_) sfx_problem_destroy(check_handle_);
   }
 
   // Optimize(values, num_iterations, populate_best_linearization) (optimizer.tcc:79-89)
@@ -1005,6 +1008,10 @@ class Optimizer {
   void OptimizeImpl(Values<Scalar>& values, int num_iterations, bool populate_best_linearization, Stats& stats,
                     bool continue_previous) {
     Initialize(values);
+    // check_derivatives (optimizer.tcc:261-272): the reference asserts inside its linearize function, i.e. at the values
+    // of every linearization; here the same assertion runs on a sibling problem (the LM state is not disturbed) at the
+    // initial values before the run and, after it, at the values of every record (debug_stats) or at the best values
+    if (params_.check_derivatives) CheckDerivativesAt(values.Data().data(), values.Data().size());
     Check(sfx_set_values(handle_, values.Data().data(), static_cast<int64_t>(values.Data().size())));
     sfx_stats st{};
     Check(continue_previous ? sfx_optimize_continue(handle_, num_iterations, &st) : sfx_optimize(handle_, num_iterations, &st));
@@ -1064,6 +1071,13 @@ class Optimizer {
     // values = nonlinear_solver.GetBestValues() (internal/optimizer_utils.h:69)
     // (only the optimized keys changed: Values::Update semantics move a fraction of the buffer over PCIe)
     Check(sfx_update_best_values(handle_, values.DataPointer(), static_cast<int64_t>(values.Data().size()), nullptr));
+    if (params_.check_derivatives) {
+      if (params_.debug_stats)
+        for (size_t i = 1; i < stats.iterations.size(); ++i)
+          CheckDerivativesAt(stats.iterations[i].values.data(), stats.iterations[i].values.size());
+      else
+        CheckDerivativesAt(values.Data().data(), values.Data().size());
+    }
     if (populate_best_linearization) {
       SparseLinearization lin;
       FillPattern(lin);
@@ -1095,7 +1109,16 @@ class Optimizer {
       Check(sfx_get_jacobian_pattern(handle_, nullptr, lin.jacobian.outer.data(), lin.jacobian.inner.data()));
       Check(sfx_linearize_jacobian(handle_, lin.jacobian.values.data()));
     }
+    if (params_.check_derivatives) CheckDerivativesAt(values.Data().data(), values.Data().size());
     return lin;
+  }
+
+  // internal::CheckDerivatives (internal/derivative_checker.h:32-123) at the given Values data, SYM_ASSERTed as the
+  // reference's linearize function does (optimizer.tcc:266-268); rel_errors (jacobian, hessian, rhs) for callers that
+  // want the numbers.  Runs on a sibling problem with the same structure.
+  bool CheckDerivatives(const Values<Scalar>& values, std::array<double, 3>* rel_errors = nullptr) {
+    Initialize(values);
+    return CheckDerivativesImpl(values.Data().data(), values.Data().size(), rel_errors);
   }
 
   // ComputeAllCovariances (optimizer.tcc:113-121): (H + eps I)^-1 split by key
@@ -1221,8 +1244,9 @@ class Optimizer {
     p.enable_bold_updates = q.enable_bold_updates;
     return p;
   }
-  void Check(sfx_status s) const {
-    if (s != SFX_OK) throw std::runtime_error(std::string("sym::Optimizer<") + name_ + ">: " + sfx_last_error(handle_));
+  void Check(sfx_status s) const { Check(s, handle_); }
+  void Check(sfx_status s, sfx_problem* h) const {
+    if (s != SFX_OK) throw std::runtime_error(std::string("sym::Optimizer<") + name_ + ">: " + sfx_last_error(h));
   }
   static int DeviceType(type_t t) {
     switch (t) {
@@ -1312,6 +1336,18 @@ class Optimizer {
   }
   // Device problem for the indexed factor graph with the given linear solver (the LM problem, or the
   // sibling ComputeCovariances needs when it eliminates a different set of keys).
+  bool CheckDerivativesImpl(const Scalar* data, size_t n, std::array<double, 3>* rel_errors) {
+    if (!check_handle_) check_handle_ = Create(solver_, schur_keys_);
+    Check(sfx_set_values(check_handle_, data, static_cast<int64_t>(n)), check_handle_);
+    int32_t ok = 0;
+    double err[3] = {0, 0, 0};
+    Check(sfx_check_derivatives(check_handle_, err, &ok, nullptr), check_handle_);
+    if (rel_errors) *rel_errors = {err[0], err[1], err[2]};
+    return ok != 0;
+  }
+  void CheckDerivativesAt(const Scalar* data, size_t n) {
+    SYM_ASSERT(CheckDerivativesImpl(data, n, nullptr) && "internal::CheckDerivatives(linearizer_, values, index_, linearization, epsilon_)");
+  }
   sfx_problem* Create(int solver, int schur_keys) {
     std::vector<sfx_factor_batch> fb;
     for (size_t bi = 0; bi < batch_kind_.size(); ++bi) {
@@ -1419,6 +1455,7 @@ class Optimizer {
   std::vector<std::vector<int32_t>> flat_args_, flat_opt_, batch_fidx_;
   int solver_{SFX_SOLVER_CHOLESKY}, schur_keys_{0};
   sfx_problem* cov_handle_{nullptr};
+  sfx_problem* check_handle_{nullptr};  // check_derivatives: same structure and solver, its own LM state
   int cov_schur_keys_{-1};
 };
 using Optimizerd = Optimizer<double>;

@@ -19,7 +19,7 @@ EXPORTS = [
     "sfx_set_values", "sfx_optimize", "sfx_optimize_continue", "sfx_relax_damping_to_initial", "sfx_get_best_values",
     "sfx_update_best_values", "sfx_get_iteration_debug", "sfx_get_iteration_update", "sfx_get_iteration_jacobian",
     "sfx_get_iterations", "sfx_get_dims",
-    "sfx_get_hessian_pattern", "sfx_linearize", "sfx_get_jacobian_pattern", "sfx_linearize_jacobian",
+    "sfx_get_hessian_pattern", "sfx_linearize", "sfx_get_jacobian_pattern", "sfx_linearize_jacobian", "sfx_check_derivatives",
     "sfx_get_best_linearization", "sfx_solve_step",
     "sfx_compute_covariance", "sfx_get_ordering", "sfx_get_timings", "sfx_get_info", "sfx_comm_unique_id", "sfx_comm_create",
     "sfx_comm_destroy",
@@ -170,6 +170,19 @@ class SfxProblem(D._LibProblem):
         self._check(self.lib.sfx_linearize_jacobian(self.h, val.ctypes.data_as(C.POINTER(C.c_double))),
                     "linearize_jacobian")
         return outer, inner, val
+
+    def check_derivatives(self, want_numerical_jacobian=False):
+        """internal::CheckDerivatives (derivative_checker.h:32-123) at the values last set: (ok, {jacobian, hessian, rhs
+        relative errors}[, dense M x N numerical Jacobian]).  Resets the optimizer state like linearize()."""
+        N, M, _ = self.dims()
+        err = (C.c_double * 3)()
+        ok = C.c_int32(0)
+        nj = np.empty((M, N), order="F") if want_numerical_jacobian else None
+        self._check(self.lib.sfx_check_derivatives(self.h, err, C.byref(ok),
+                                                   nj.ctypes.data_as(C.POINTER(C.c_double)) if nj is not None else None),
+                    "check_derivatives")
+        out = (bool(ok.value), {"jacobian": err[0], "hessian": err[1], "rhs": err[2]})
+        return out + (nj,) if want_numerical_jacobian else out
 
     def compute_covariance(self, block_dim, hessian_values=None):
         """Optimizer::ComputeCovariances / ComputeFullCovariance: dense block_dim x block_dim covariance in keys_

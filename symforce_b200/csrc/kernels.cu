@@ -2542,6 +2542,13 @@ __global__ void set_unit_kernel(double* v, int j, int prev) {
   v[j] = 1.0;
 }
 void launch_set_unit(cudaStream_t st, double* v, int j, int prev) { set_unit_kernel<<<1, 1, 0, st>>>(v, j, prev); ++g_launches; }
+__global__ void set_entry_kernel(double* v, int j, double value, int prev) {
+  if (prev >= 0) v[prev] = 0.0;
+  v[j] = value;
+}
+void launch_set_entry(cudaStream_t st, double* v, int j, double value, int prev) {
+  set_entry_kernel<<<1, 1, 0, st>>>(v, j, value, prev); ++g_launches;
+}
 
 __global__ void permute_vec_kernel(const double* __restrict__ in, const int32_t* __restrict__ ref2int, int N,
                                    double* __restrict__ out) {

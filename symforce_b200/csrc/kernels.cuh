@@ -254,6 +254,7 @@ cudaError_t configure_front_kernels(int smem_m_max, int max_front);
 constexpr int kWarpFrontRows = 32;  // small fronts up to this many rows are factored by one warp each (kernels.cu)
 void launch_import_csc(cudaStream_t st, const double* in, const int32_t* csc_src, int64_t nnz, double* Hvals);
 void launch_set_unit(cudaStream_t st, double* v, int j, int prev);
+void launch_set_entry(cudaStream_t st, double* v, int j, double value, int prev);  // v[prev] = 0 (prev >= 0), v[j] = value
 void launch_permute_vec(cudaStream_t st, const double* in, const int32_t* ref2int, int N, double* out);
 
 }  // namespace sfx

@@ -12,6 +12,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <functional>
+#include <limits>
 #include <memory>
 #include <queue>
 #include <string>
@@ -2257,6 +2258,122 @@ sfx_status sfx_linearize_jacobian(sfx_problem* p, double* jacobian_values) {
     launch_jacobian(p->st, p->d_cur_values, p->lin[b], p->d_jac_base[b], p->d_jac_colnnz[b], p->d_export);
   CUDA_OK(cudaMemcpyAsync(jacobian_values, p->d_export, sizeof(double) * p->a.jac_nnz, cudaMemcpyDeviceToHost, p->st));
   CUDA_OK(cudaStreamSynchronize(p->st));
+  SFX_API_END(p)
+}
+
+sfx_status sfx_check_derivatives(sfx_problem* p, double* rel_errors, int32_t* ok, double* numerical_jacobian) {
+  SFX_API_BEGIN
+  SFX_CHECK(p && ok, SFX_ERR_INVALID_ARG, "null argument");
+  SFX_CHECK(p->values_set, SFX_ERR_INVALID_ARG, "sfx_set_values must be called first");
+  Analysis& a = p->a;
+  SFX_CHECK(a.world == 1, SFX_ERR_UNSUPPORTED, "derivatives are checked on one GPU");
+  const int N = a.N, M = a.M;
+  SFX_CHECK((int64_t)M * N <= (int64_t(1) << 24) && N <= 4096, SFX_ERR_UNSUPPORTED,
+            "check_derivatives forms the dense M x N Jacobian and N x N Hessian on the host and relinearizes 2 N times: "
+            "a debugging aid for small problems (M * N <= 2^24, N <= 4096)");
+  CUDA_OK(cudaSetDevice(p->device));
+  ensure_jacobian(p);
+  // the linearization to check: at the values last set, like sfx_linearize
+  reset_ctrl(p);
+  // Init and New hold the whole Values buffer: retract only writes the optimized keys of New
+  for (int b = 0; b < 2; ++b) launch_copy_values(p->st, p->sp.values[b], p->d_cur_values, a.n_values);
+  enqueue_linearize(p, 0);
+  std::vector<double> res(M), rhs(N), Hv;
+  build_csc(a);
+  Hv.resize(a.nnz);
+  export_linearization(p, 0, res.data(), rhs.data(), Hv.data());
+  std::vector<double> Jv(a.jac_nnz);
+  for (size_t b = 0; b < p->lin.size(); ++b)
+    launch_jacobian(p->st, p->d_cur_values, p->lin[b], p->d_jac_base[b], p->d_jac_colnnz[b], p->d_export);
+  CUDA_OK(cudaMemcpyAsync(Jv.data(), p->d_export, sizeof(double) * a.jac_nnz, cudaMemcpyDeviceToHost, p->st));
+  // numerical Jacobian by central differences in the tangent space (util.h:97-127 with delta = sqrt(epsilon), as
+  // derivative_checker.h:54-56 calls it): New = Init (+) (+-delta e_c), residual of New
+  const double delta = std::sqrt(p->epsilon);
+  std::vector<double> numJ((size_t)M * N), rp(M), rm(M);
+  CUDA_OK(cudaMemsetAsync(p->d_upd, 0, sizeof(double) * N, p->st));
+  int prev = -1;
+  for (int c = 0; c < N; ++c) {
+    const int ic = a.ref2int[c];
+    for (int sgn = 0; sgn < 2; ++sgn) {
+      launch_set_entry(p->st, p->d_upd, ic, sgn == 0 ? delta : -delta, prev);
+      prev = ic;
+      launch_retract(p->st, p->d_ctrl, p->sp, p->d_key_type, p->d_key_voff, p->d_key_sdim, p->d_key_tdim, p->d_key_itoff,
+                     a.n_keys, p->d_upd);
+      enqueue_linearize(p, 1);
+      CUDA_OK(cudaMemcpyAsync(sgn == 0 ? rp.data() : rm.data(), p->sp.res[1], sizeof(double) * M, cudaMemcpyDeviceToHost,
+                              p->st));
+    }
+    CUDA_OK(cudaStreamSynchronize(p->st));
+    double* col = numJ.data() + (size_t)c * M;
+    for (int r = 0; r < M; ++r) col[r] = ((rp[r] - res[r]) - (rm[r] - res[r])) / (2.0 * delta);
+  }
+  CUDA_OK(cudaMemsetAsync(p->d_upd, 0, sizeof(double) * N, p->st));
+  // the state blocks hold perturbed values now: back to a clean slate (as after sfx_linearize)
+  reset_ctrl(p);
+  CUDA_OK(cudaStreamSynchronize(p->st));
+  // Eigen's isApprox: |x - y|_F <= prec * min(|x|_F, |y|_F)
+  auto rel = [](double diff2, double na2, double nb2) {
+    const double m = std::sqrt(std::min(na2, nb2));
+    return diff2 == 0.0 ? 0.0 : (m > 0.0 ? std::sqrt(diff2) / m : std::numeric_limits<double>::infinity());
+  };
+  // (1) numerical vs analytic Jacobian, 10 sqrt(epsilon) (derivative_checker.h:58-59)
+  double dj = 0, nj = 0, nn = 0;
+  for (int c = 0; c < N; ++c) {
+    const double* col = numJ.data() + (size_t)c * M;
+    int q = a.jac_outer[c];
+    const int q1 = a.jac_outer[c + 1];
+    for (int r = 0; r < M; ++r) {
+      double ja = 0.0;
+      if (q < q1 && a.jac_inner[q] == r) ja = Jv[q++];
+      dj += (col[r] - ja) * (col[r] - ja);
+      nj += ja * ja;
+      nn += col[r] * col[r];
+    }
+  }
+  const double e_j = rel(dj, nj, nn);
+  // (2) hessian_lower (symmetrized) vs J^T J, sqrt(epsilon) (:78-98); (3) rhs vs J^T r, sqrt(epsilon) (:101-117)
+  std::vector<std::vector<std::pair<int, double>>> rows(M);
+  for (int c = 0; c < N; ++c)
+    for (int q = a.jac_outer[c]; q < a.jac_outer[c + 1]; ++q) rows[a.jac_inner[q]].push_back({c, Jv[q]});
+  std::vector<double> JtJ((size_t)N * N, 0.0), Jtr(N, 0.0);
+  for (int r = 0; r < M; ++r)
+    for (const auto& x : rows[r]) {
+      Jtr[x.first] += x.second * res[r];
+      for (const auto& y : rows[r])
+        if (y.first >= x.first) JtJ[(size_t)y.first + (size_t)x.first * N] += x.second * y.second;  // lower triangle
+    }
+  double dh = 0, nh = 0, nq = 0;
+  {
+    std::vector<double> Hd((size_t)N * N, 0.0);
+    for (int c = 0; c < N; ++c)
+      for (int q = a.csc_outer[c]; q < a.csc_outer[c + 1]; ++q) Hd[(size_t)a.csc_inner[q] + (size_t)c * N] = Hv[q];
+    for (int c = 0; c < N; ++c)
+      for (int r = c; r < N; ++r) {
+        const double x = Hd[(size_t)r + (size_t)c * N], y = JtJ[(size_t)r + (size_t)c * N];
+        const double w = r == c ? 1.0 : 2.0;  // both triangles of the full matrices
+        dh += w * (x - y) * (x - y);
+        nh += w * x * x;
+        nq += w * y * y;
+      }
+  }
+  const double e_h = rel(dh, nh, nq);
+  double dr = 0, nr = 0, nt = 0;
+  for (int c = 0; c < N; ++c) {
+    dr += (rhs[c] - Jtr[c]) * (rhs[c] - Jtr[c]);
+    nr += rhs[c] * rhs[c];
+    nt += Jtr[c] * Jtr[c];
+  }
+  const double e_r = rel(dr, nr, nt);
+  if (rel_errors) {
+    rel_errors[0] = e_j;
+    rel_errors[1] = e_h;
+    rel_errors[2] = e_r;
+  }
+  *ok = (e_j <= 10.0 * delta && e_h <= delta && e_r <= delta) ? 1 : 0;
+  if (numerical_jacobian) std::copy(numJ.begin(), numJ.end(), numerical_jacobian);
+  if (!*ok && p->params.verbose)
+    std::fprintf(stderr, "[sfx] derivative check failed: |J_num - J| %.3e (tol %.3e), |H - J^T J| %.3e, |rhs - J^T r| %.3e (tol %.3e)\n",
+                 e_j, 10.0 * delta, e_h, e_r, delta);
   SFX_API_END(p)
 }
 

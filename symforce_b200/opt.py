@@ -495,6 +495,9 @@ class Optimizer:
             self._factor_opt_keys.append(factor_opt_keys)
 
         self.params = OptimizerParams(verbose=True) if params is None else params
+        # SYM_ASSERT(!params.check_derivatives || params.include_jacobians) (optimizer.tcc:39, 62)
+        assert not self.params.check_derivatives or self.params.include_jacobians, \
+            "check_derivatives needs include_jacobians"
         self.epsilon = float(epsilon)
         if solver not in ("auto", "cholesky", "schur") and not isinstance(solver, int):
             raise ValueError("solver must be 'auto', 'cholesky', 'schur' or a number of trailing keys to eliminate")
@@ -507,6 +510,7 @@ class Optimizer:
         self._gpu = None  # capi.SfxProblem
         self._cov_gpu = None
         self._cov_split = None
+        self._check_gpu = None  # check_derivatives: same structure and solver, its own LM state
 
     # -- lowering to the flat problem of include/sfx.h --------------------------------------------------------------
     def _initialize(self, values: Values):
@@ -636,8 +640,14 @@ class Optimizer:
                  populate_best_linearization: bool = False) -> "Optimizer.Result":
         """optimizer.py:322-358 -> Optimizer::Optimize (optimizer.tcc:59-83)."""
         gpu = self._device_problem(initial_guess)
+        # check_derivatives (optimizer.tcc:261-272): the reference asserts at the values of every linearization; here on a
+        # sibling problem at the initial values and, after the run, at every record's values (debug_stats) or the best ones
+        if self.params.check_derivatives:
+            self._assert_derivatives(self._storage(initial_guess))
         st = gpu.optimize(num_iterations)
         best = gpu.best_values()
+        if self.params.check_derivatives and not self.params.debug_stats:
+            self._assert_derivatives(best)
         optimized_values = self._values_from_storage(initial_guess, best)
         its = []
         for r, it in enumerate(gpu.iterations()):
@@ -650,6 +660,8 @@ class Optimizer:
                 rec.update = gpu.iteration_update(r) if it.iteration >= 0 else np.zeros(0)
                 if self.params.include_jacobians:
                     rec.jacobian_values = gpu.iteration_jacobian(r)
+                if self.params.check_derivatives and r > 0:
+                    self._assert_derivatives(rec.values)
             its.append(rec)
         jac_sparsity = None
         if self.params.debug_stats and self.params.include_jacobians:  # levenberg_marquardt_solver.tcc:172-175
@@ -671,7 +683,30 @@ class Optimizer:
         res, rhs, H = gpu.linearize()
         outer, inner = gpu.hessian_pattern()
         jac = gpu.jacobian() if self.params.include_jacobians else None
+        if self.params.check_derivatives:
+            self._assert_derivatives(self._storage(values))
         return Linearization(res, rhs, outer, inner, H, jac)
+
+    def check_derivatives(self, values: Values):
+        """internal::CheckDerivatives (internal/derivative_checker.h:32-123) at `values`: (ok, relative errors of the
+        Jacobian against central differences, of hessian_lower against J^T J, of rhs against J^T r)."""
+        self._device_problem(values)
+        return self._check_derivatives(self._storage(values))
+
+    def _check_derivatives(self, data):
+        if self._check_gpu is None:
+            p = copy.copy(self._problem)
+            p.values = np.ascontiguousarray(data, dtype=np.float64)
+            self._check_gpu = capi.SfxProblem(p, device=self._device)
+        else:
+            self._check_gpu.set_values(np.ascontiguousarray(data, dtype=np.float64))
+        return self._check_gpu.check_derivatives()
+
+    def _assert_derivatives(self, data):
+        ok, err = self._check_derivatives(data)
+        if not ok:
+            raise RuntimeError("SYM_ASSERT: internal::CheckDerivatives(linearizer_, values, index_, linearization, epsilon_): "
+                               f"{err}")
 
     def load_iteration_values(self, values_data) -> Values:
         """optimizer.py:366-381: a debug_stats iteration's values (flat storage) as a Python Values."""
@@ -743,7 +778,7 @@ class Optimizer:
         return self._split_by_key(np.array(cov), keys)
 
     def close(self):
-        for g in (self._gpu, self._cov_gpu):
+        for g in (self._gpu, self._cov_gpu, self._check_gpu):
             if g is not None:
                 g.close()
-        self._gpu = self._cov_gpu = None
+        self._gpu = self._cov_gpu = self._check_gpu = None

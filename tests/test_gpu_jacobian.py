@@ -72,3 +72,40 @@ def test_python_front_fills_the_jacobian():
     assert J.shape == (lin.residual.shape[0], 30)
     assert np.allclose(J.T @ lin.residual, lin.rhs, rtol=0, atol=1e-9 * np.abs(lin.rhs).max())
     optimizer.close()
+
+
+@pytest.mark.parametrize("name", ["robot3d", "ba_example", "frozen_keys", "bal_small_schur", "pose_graph"])
+def test_check_derivatives(name):
+    """optimizer_params_t::check_derivatives (optimizer.tcc:261-272 -> internal/derivative_checker.h:32-123):
+    sfx_check_derivatives compares the device's linearization with central differences of the device's residual (step
+    sqrt(epsilon), tolerance 10 sqrt(epsilon)) and with J^T J / J^T r (tolerance sqrt(epsilon)).  The numerical Jacobian is
+    also held against the ORACLE's analytic Jacobian, which ties the check to something the device did not compute."""
+    prob = PROBLEMS[name]()
+    g, o = capi.SfxProblem(prob), O.OracleProblem(prob)
+    ok, err, num_j = g.check_derivatives(want_numerical_jacobian=True)
+    print(f"CHECKDERIV {name} " + " ".join(f"{k}={v:.2e}" for k, v in err.items()))
+    tol = np.sqrt(prob.epsilon)
+    assert ok and err["jacobian"] <= 10 * tol and err["hessian"] <= tol and err["rhs"] <= tol
+    assert err["hessian"] < 1e-12 and err["rhs"] < 1e-9  # these two are exact up to the summation order
+    outer, inner, val = o.jacobian()
+    N, M, _ = g.dims()
+    J = sp.csc_matrix((val, inner, outer), shape=(M, N)).toarray()
+    assert num_j.shape == (M, N)
+    assert np.linalg.norm(num_j - J) <= 10 * tol * min(np.linalg.norm(J), np.linalg.norm(num_j))
+    # like linearize(), the check leaves a reset optimizer: the next optimize starts over and matches a fresh problem
+    st = g.optimize()
+    g2 = capi.SfxProblem(prob)
+    st2 = g2.optimize()
+    assert st.n_iterations == st2.n_iterations and st.best_index == st2.best_index
+    assert g.iterations()[st.best_index].new_error == pytest.approx(g2.iterations()[st2.best_index].new_error, rel=1e-9)
+    g.close()
+    g2.close()
+
+
+def test_check_derivatives_is_a_small_problem_tool():
+    g = capi.SfxProblem(P.bal_problem("ladybug", solver=D.SOLVER_SCHUR))
+    with pytest.raises(RuntimeError, match="rc=3"):  # SFX_ERR_UNSUPPORTED: N = 23,769
+        g.check_derivatives()
+    st = g.optimize(2)  # still usable
+    assert st.n_iterations == 3
+    g.close()

@@ -67,6 +67,13 @@ def test_robot_3d_localization_python_example():
     # rhs = J^T r of the same record
     lin_best = optimizer.linearize(with_j.optimized_values)
     assert np.allclose(J.T @ rec_j.residual, lin_best.rhs, rtol=0, atol=1e-9 * np.abs(lin_best.rhs).max())
+    # check_derivatives (optimizer.tcc:261-272): asserted at the initial values and at every record's values
+    ok, err = optimizer.check_derivatives(values)
+    assert ok and err["jacobian"] < 1e-6 and err["hessian"] < 1e-12
+    optimizer.params.check_derivatives = True
+    checked = optimizer.optimize(values)
+    assert len(checked.iterations) == len(result.iterations)
+    optimizer.params.check_derivatives = False
     optimizer.params.include_jacobians = False
 
     # a second optimize on the same optimizer starts over from the given Values

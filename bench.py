@@ -116,7 +116,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, text=True)
         except Exception:
             self.proc = None
@@ -313,13 +313,15 @@ def measure(workload, K, W, rank, world, local_rank, comm, sample_clocks):
     gpu.set_values(pinned.numpy())
     gpu.optimize(1)
     first_errors = [float(r.new_error) for r in gpu.iterations()]
-    # warm-up
-    gpu.set_values(pinned.numpy())
-    gpu.optimize(W)
-    # clocks are sampled by rank 0 only: N concurrent nvidia-smi pollers contend for the driver and for host cores
+    # clocks are sampled by rank 0 only: N concurrent nvidia-smi pollers contend for the driver and for host cores.
+    # The poller (50 ms period) starts before the warm-up so that it is up and reporting when the timed regions run
+    # (K = 10 iterations are ~65 ms device-resident + ~95 ms end to end); it is stopped right after them.
     sampler = ClockSampler(local_rank)
     if sample_clocks:
         sampler.start()
+    # warm-up
+    gpu.set_values(pinned.numpy())
+    gpu.optimize(W)
     # ---- device-resident: K iterations in one call ---------------------------------------------
     gpu.set_values(pinned.numpy())
     barrier()

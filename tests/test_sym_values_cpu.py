@@ -64,3 +64,20 @@ def test_values_api_against_geo(tmp_path):
     # Factor::Jacobian: same kind and optimized keys as Factor::Hessian, 5 keys / 2 optimized, lambdas and reordered
     # keys_to_optimize rejected
     assert rec["factor_jacobian"] == ["1", "1", "5", "2", "1", "1"]
+
+
+def test_cpp_callers_build_and_refuse_to_run_without_a_gpu():
+    """Every C++17 caller of include/sym/sym.h under examples/ compiles and links against libsfx.so on a CPU-only box
+    (all entry points the header layer binds are exported), and on a box without a CUDA device the optimizer throws
+    instead of computing anything on the host: the product path has no CPU fallback."""
+    import torch
+
+    subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "examples")])
+    for name in ("robot_3d_localization", "bundle_adjustment_in_the_large", "covariance_check", "bundle_adjustment", "gnc_test"):
+        assert os.path.exists(os.path.join(ROOT, "examples", "_build", name)), name
+    if torch.cuda.is_available():
+        return
+    out = subprocess.run([os.path.join(ROOT, "examples", "_build", "robot_3d_localization")], capture_output=True, text=True,
+                         timeout=60)
+    assert out.returncode != 0
+    assert "no CUDA device: libsfx has no CPU fallback" in out.stderr
